@@ -1,0 +1,304 @@
+/* SPDX-License-Identifier: MIT
+ *
+ * libssym — B200-native batched STARK verifier: the C-ABI drop-in boundary.
+ *
+ * Every entry point below replaces one `.simf` function (or one Simplicity jet
+ * family) of starkware-bitcoin/stark-symphony; the reference location each one
+ * stands in for is cited as `file:line` relative to the reference root.  The
+ * reference has no FFI of its own for this path (it is one `simfony run` process
+ * per proof, simfony-cli/src/main.rs:163-209): these are the symbols a
+ * `verify-batch` sub-command next to `build/run` would bind.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; all sizes in elements unless stated.
+ *  - return value: 0 = ok, <0 = usage or CUDA error (ssym_last_error() has text).
+ *    A rejected proof is DATA (accept bit 0 / non-zero status), never an error.
+ *  - field elements are raw `uint32_t` exactly as the jets see them; nothing is
+ *    canonicalised on load (m31.simf:17-44 semantics for arbitrary u32).
+ *  - a 256-bit digest is 8 `uint32_t` words, word 0 = most significant 32 bits of
+ *    the big-endian u256 (channel.simf:48-58 `split_256` order).
+ *  - `memspace`: SSYM_MEM_DEVICE pointers are device pointers on the handle's
+ *    GPU (inputs already resident in HBM); SSYM_MEM_HOST pointers are host
+ *    pointers (pinned or pageable) and the call performs the H2D / D2H copies.
+ *  - no CPU fallback exists: every compute entry point runs CUDA kernels on an
+ *    sm_100-class device or fails with SSYM_ERR_CUDA.
+ */
+#ifndef SSYM_H
+#define SSYM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSYM_OK 0
+#define SSYM_ERR_USAGE (-1)
+#define SSYM_ERR_CUDA (-2)
+#define SSYM_ERR_PARSE (-3)
+#define SSYM_ERR_NOMEM (-4)
+
+#define SSYM_MEM_DEVICE 0
+#define SSYM_MEM_HOST 1
+
+/* ------------------------------------------------------------------------- */
+/* Stwo verifier configuration (stwo-verifier/src/config.simf:10-51)          */
+/* ------------------------------------------------------------------------- */
+
+/* Semantics switch (SURVEY.md "Read this first", finding 3 / Appendix A):
+ *  REF_LITERAL        exactly what the .simf text computes at reference HEAD.
+ *  PROVER_CONSISTENT  the three HEAD inconsistencies (F1-F3) resolved the way
+ *                     the prover of tests/data/proof.json behaves. */
+#define SSYM_MODE_REF_LITERAL 0
+#define SSYM_MODE_PROVER_CONSISTENT 1
+
+#define SSYM_NUM_COLUMNS 4        /* config.simf:14 NUM_COLUMNS                     */
+#define SSYM_NUM_CP_PARTITIONS 16 /* evals/composition_poly.simf:13                 */
+#define SSYM_MAX_QUERIES 16       /* config.simf:42 NUM_FRI_QUERIES (prod)          */
+#define SSYM_MAX_FRI_LAYERS 9     /* first layer + NUM_FRI_LAYERS (config.simf:47)  */
+
+typedef struct ssym_stwo_config {
+    uint32_t trace_log;    /* TRACE_LOG_SIZE      config.simf:17,35 */
+    uint32_t lde_log;      /* LDE_LOG_SIZE        config.simf:21,39 */
+    uint32_t n_queries;    /* NUM_FRI_QUERIES     config.simf:25,43  (1..16)        */
+    uint32_t n_fri_layers; /* NUM_FRI_LAYERS      config.simf:29,47  (inner, 0..8)  */
+    uint32_t mode;         /* SSYM_MODE_*                                           */
+    uint32_t reserved;
+    uint64_t pow_target;   /* POW_TARGET_64       config.simf:32,51 */
+} ssym_stwo_config_t;
+
+/* The two presets of config.simf (TESTING / production). */
+int ssym_stwo_config_preset(const char *name /* "prod" | "testing" */, uint32_t mode,
+                            ssym_stwo_config_t *out);
+
+/* Packed wire format of one Stwo proof (all little-endian u32 words; digests as
+ * 8 words, most significant first).  Sections, in order, each starting on a
+ * 32-byte boundary (Q = n_queries, L = n_fri_layers, G = lde_log):
+ *   header   : commit[3][8] | oods_trace[4][4] | oods_cp[16][4] | fri_first_root[8]
+ *              | fri_inner_root[L][8] | last_coeff[4] | pow_nonce {hi, lo}
+ *   qvals    : per query { trace_vals[4], cp_vals[16] }
+ *   trace_sib: [Q][G][8]         (leaf -> root order, merkle.simf:39-44)
+ *   cp_sib   : [Q][G][8]
+ *   fri_wit  : [L+1][Q][4]
+ *   fri_sib  : layer l = 0..L : [Q][G-1-l][8]
+ * It mirrors the witness tuple of stwo-verifier/src/main.simf:9-25 (COMMITMENTS,
+ * DECOMMITMENTS, OODS_EVALS, FRI_COMMITMENTS, FRI_DECOMMITMENTS, POW_NONCE). */
+typedef struct ssym_stwo_layout {
+    uint32_t off_commit, off_oods_trace, off_oods_cp, off_fri_first_root;
+    uint32_t off_fri_inner_root, off_last_coeff, off_pow_nonce;
+    uint32_t off_qvals, off_trace_sib, off_cp_sib, off_fri_wit;
+    uint32_t off_fri_sib[SSYM_MAX_FRI_LAYERS];
+    uint32_t stride_words;    /* distance between consecutive proofs, in u32 words  */
+    uint32_t algorithmic_bytes; /* payload bytes without alignment padding          */
+} ssym_stwo_layout_t;        /* all offsets in u32 words from the proof's base      */
+
+int ssym_stwo_layout(const ssym_stwo_config_t *cfg, ssym_stwo_layout_t *out);
+
+/* Per-proof status word: 0 = accept.  Bits are ordered by the reference's
+ * program order (verifier.simf:32-58) at stage granularity. */
+#define SSYM_ST_DRAW_EXHAUSTED (1u << 0)   /* channel.simf:125,132 unwrap_left after 256 tries */
+#define SSYM_ST_OODS_INV_ZERO (1u << 1)    /* m31.simf:118-122 inside channel.simf:146 / wide_fibonacci.simf:61 */
+#define SSYM_ST_OODS_CP_MISMATCH (1u << 2) /* deep/oods.simf:58 */
+#define SSYM_ST_POW_FAIL (1u << 3)         /* pow.simf:32 */
+#define SSYM_ST_TRACE_MERKLE (1u << 4)     /* evals/verify.simf:56 -> merkle.simf:42-43 */
+#define SSYM_ST_CP_MERKLE (1u << 5)        /* evals/verify.simf:66 -> merkle.simf:42-43 */
+#define SSYM_ST_ANSWER_INV_ZERO (1u << 6)  /* deep/quotients.simf:22 */
+#define SSYM_ST_FRI_MERKLE(l) (1u << (7 + (l))) /* fri/layers.simf:47, layer l = 0..8 */
+#define SSYM_ST_FOLD_INV_ZERO (1u << 16)   /* fri/folding.simf:20,34 */
+#define SSYM_ST_FINAL_LOG (1u << 17)       /* fri/verify.simf:127  (REF_LITERAL only) */
+#define SSYM_ST_LAST_QUERY (1u << 18)      /* fri/layers.simf:75   (REF_LITERAL only) */
+#define SSYM_ST_LAST_EVAL (1u << 19)       /* fri/layers.simf:76 */
+#define SSYM_ST_SHAPE (1u << 31)           /* witness shape cannot satisfy merkle.simf:42 / the types */
+
+/* Optional per-proof trace: every value-bearing intermediate of verify_proof,
+ * for bit-exact parity diffs against the oracle (the reference's equivalent is
+ * `simfony debug` + Tracker, simfony-cli/src/tracker.rs:48-80). */
+typedef struct ssym_stwo_trace {
+    uint32_t status;
+    uint32_t first_fail; /* 0 = accept, else (stage<<16 | layer<<8 | query), stage = bit index of status */
+    uint32_t digest_commit[8]; /* after evals_commit      evals/commit.simf:20-35 */
+    uint32_t cp_alpha[4];
+    uint32_t oods_x[4], oods_y[4]; /* channel.simf:143-150 */
+    uint32_t cp_eval[4];           /* wide_fibonacci.simf:56-62 */
+    uint32_t cp_sampled[4];        /* composition_poly.simf:47-59 */
+    uint32_t digest_oods[8];       /* after channel_mix_oods_evals deep/oods.simf:23-39 */
+    uint32_t deep_alpha[4];
+    uint32_t fri_alpha[SSYM_MAX_FRI_LAYERS][4]; /* fri/commit.simf:36-45 */
+    uint32_t digest_fri[8];                     /* after fri_commit fri/commit.simf:72-85 */
+    uint32_t digest_pow[8];                     /* after check_proof_of_work pow.simf:22-35 */
+    uint32_t pow_value[2];                      /* {hi, lo} of the compared u64 */
+    uint32_t queries[SSYM_MAX_QUERIES];         /* fri/queries.simf:30-43 */
+    uint32_t fri_answer[SSYM_MAX_QUERIES][4];   /* fri/answers.simf:97-129 */
+    uint32_t folded[SSYM_MAX_FRI_LAYERS][SSYM_MAX_QUERIES][4]; /* fri/folding.simf:15-41 */
+    uint32_t trace_root[SSYM_MAX_QUERIES][8];   /* recomputed roots, merkle.simf:41 */
+    uint32_t cp_root[SSYM_MAX_QUERIES][8];
+    uint32_t fri_root[SSYM_MAX_FRI_LAYERS][SSYM_MAX_QUERIES][8];
+    uint32_t mask_trace, mask_cp, mask_answer_inv; /* bit q = query q failed that check */
+    uint32_t mask_fri[SSYM_MAX_FRI_LAYERS];
+    uint32_t mask_fold_inv[SSYM_MAX_FRI_LAYERS];
+    uint32_t mask_last_query, mask_last_eval;
+    uint32_t pad_[3];
+} ssym_stwo_trace_t;
+
+/* ------------------------------------------------------------------------- */
+/* stark101 (stark101/src/verifier.simf:17-42)                                 */
+/* ------------------------------------------------------------------------- */
+
+#define SSYM_S101_MAX_LIST 31 /* List<_, 32> holds 0..31 items (merkle.simf:19, fri.simf:49) */
+
+/* Packed stark101 proof: a variable-length record of u32 words.
+ *   [0]      total_words of this record (including this header)
+ *   [1]      n_layers (0..31)
+ *   [2..4]   sibling counts of the three trace decommitments (f(x), f(gx), f(g^2 x))
+ *   [5]      fri_last_layer
+ *   [6..7]   reserved (0)
+ *   [8..15]  p_mt_root
+ *   [16..18] f(x), f(gx), f(g^2 x)      [19] reserved
+ *   [20 ..]  siblings of eval 0, eval 1, eval 2 (8 words each, leaf -> root)
+ *   then per FRI layer: root[8] | beta | cpa | cpb | n_sib_a | n_sib_b | 0 0 0 |
+ *                       siblings a | siblings b
+ * mirroring witnesses P_MT_ROOT, P_EVALS, FRI_LAYERS, FRI_LAST_LAYER
+ * (stark101/src/main.simf:12-20).  A batch is the concatenation of records plus
+ * an offsets array (u64 word offsets, n+1 entries). */
+#define SSYM_S101_ST_TRACE_MERKLE(i) (1u << (i))     /* air.simf:41, eval i = 0..2 */
+#define SSYM_S101_ST_BETA (1u << 3)                  /* fri.simf:43 */
+#define SSYM_S101_ST_DIV (1u << 4)                   /* field.simf:46 gcd != 1 / loop exhausted */
+#define SSYM_S101_ST_LAYER_CP (1u << 5)              /* fri.simf:77 */
+#define SSYM_S101_ST_LAYER_MERKLE_A (1u << 6)        /* fri.simf:79 */
+#define SSYM_S101_ST_LAYER_MERKLE_B (1u << 7)        /* fri.simf:80 */
+#define SSYM_S101_ST_LAST (1u << 8)                  /* fri.simf:90 */
+#define SSYM_S101_ST_SHAPE (1u << 31)
+
+typedef struct ssym_s101_trace {
+    uint32_t status;
+    uint32_t first_fail_layer; /* first FRI layer with any failing check, or 0xffffffff */
+    uint32_t alpha[3];         /* air.simf:30-36 */
+    uint32_t idx;              /* verifier.simf:32 */
+    uint32_t x;                /* air.simf:58-60 */
+    uint32_t cp0;              /* air.simf:94-101 */
+    uint32_t n_layers;
+    uint32_t beta_drawn[SSYM_S101_MAX_LIST]; /* fri.simf:42 */
+    uint32_t cp_ev[SSYM_S101_MAX_LIST + 1];  /* cp value entering layer i; [n_layers] = final */
+    uint32_t layer_mask[SSYM_S101_MAX_LIST]; /* per layer: bit0 cp!=cpa, bit1 merkle a, bit2 merkle b, bit3 beta */
+    uint32_t state_final[8];                 /* channel state after the three evaluations are mixed */
+    uint32_t trace_root[3][8];               /* recomputed roots of the three trace decommitments */
+} ssym_s101_trace_t;
+
+/* ------------------------------------------------------------------------- */
+/* Handle                                                                     */
+/* ------------------------------------------------------------------------- */
+
+typedef struct ssym_ctx ssym_ctx_t;
+
+/* One handle per GPU; thread-safe per handle (one host thread per GPU). */
+int ssym_create(int device, ssym_ctx_t **out);
+void ssym_destroy(ssym_ctx_t *ctx);
+const char *ssym_last_error(void);
+const char *ssym_version(void);
+/* Use a caller-owned stream (e.g. torch's current stream) for all subsequent
+ * device-resident calls on this handle; NULL restores the handle's own stream. */
+int ssym_set_stream(ssym_ctx_t *ctx, void *cuda_stream);
+int ssym_synchronize(ssym_ctx_t *ctx);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+uint64_t ssym_launch_count(const ssym_ctx_t *ctx);
+
+/* ------------------------------------------------------------------------- */
+/* Whole-proof batch verification                                             */
+/* ------------------------------------------------------------------------- */
+
+/* verify_proof for n packed Stwo proofs (stwo-verifier/src/verifier.simf:32-58).
+ *  packed      : n * layout.stride_words u32 words
+ *  accept_bits : (n+31)/32 u32 words; bit i = 1 iff proof i is accepted
+ *  status      : NULL or n status words (SSYM_ST_*)
+ *  trace       : NULL or n ssym_stwo_trace_t
+ * All four pointers live in `memspace`.  Asynchronous on the handle's stream
+ * for SSYM_MEM_DEVICE; synchronous for SSYM_MEM_HOST (copies included). */
+int ssym_stwo_verify_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const uint32_t *packed,
+                           size_t n, uint32_t *accept_bits, uint32_t *status,
+                           ssym_stwo_trace_t *trace, int memspace);
+
+/* verify_proof for n packed stark101 proofs (stark101/src/verifier.simf:24-42).
+ *  blob / offsets : concatenated records and n+1 word offsets */
+int ssym_stark101_verify_batch(ssym_ctx_t *ctx, const uint32_t *blob, const uint64_t *offsets,
+                               size_t n, uint32_t *accept_bits, uint32_t *status,
+                               ssym_s101_trace_t *trace, int memspace);
+
+/* ------------------------------------------------------------------------- */
+/* Element-wise jets / .simf functions (parity + config-4 microbenchmarks)    */
+/* All arrays have n elements (CM31 = 2 words, QM31 = 4 words per element,     */
+/* interleaved as the .simf tuples are).  `fail` (NULL or n bytes) receives 1   */
+/* where the .simf function would hit assert!(false) (inverse of bitwise 0).   */
+/* ------------------------------------------------------------------------- */
+int ssym_m31_add(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/m31.simf:22-26 */
+int ssym_m31_sub(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/m31.simf:35-37 */
+int ssym_m31_neg(ssym_ctx_t *, const uint32_t *a, uint32_t *out, size_t n, int memspace);                   /* fields/m31.simf:29-32 */
+int ssym_m31_mul(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/m31.simf:40-45 */
+int ssym_m31_inv(ssym_ctx_t *, const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n, int memspace);    /* fields/m31.simf:117-132 */
+int ssym_cm31_mul(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/cm31.simf:79-86 */
+int ssym_cm31_inv(ssym_ctx_t *, const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n, int memspace);     /* fields/cm31.simf:88-93 */
+int ssym_qm31_add(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/qm31.simf:36-40 */
+int ssym_qm31_sub(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/qm31.simf:49-53 */
+int ssym_qm31_mul(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/qm31.simf:73-80 */
+int ssym_qm31_inv(ssym_ctx_t *, const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n, int memspace);     /* fields/qm31.simf:87-98 */
+int ssym_qm31_mul_m31(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace);  /* fields/qm31.simf:56-59 */
+int ssym_qm31_mul_cm31(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace); /* fields/qm31.simf:62-65 */
+
+/* circle_point_index_to_m31_point (groups/m31_point.simf:103-106): out = n * {x, y}. */
+int ssym_circle_point(ssym_ctx_t *, const uint32_t *index, uint32_t *out_xy, size_t n, int memspace);
+
+/* circle_fold / line_fold (fri/folding.simf:15-41): per element a left-leaf
+ * position, f(p), f(-p) and the fold alpha; one log_size for the whole call. */
+int ssym_circle_fold(ssym_ctx_t *, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p,
+                     const uint32_t *alpha, uint32_t log_size, uint32_t *out, uint8_t *fail, size_t n, int memspace);
+int ssym_line_fold(ssym_ctx_t *, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p,
+                   const uint32_t *alpha, uint32_t log_size, uint32_t *out, uint8_t *fail, size_t n, int memspace);
+
+/* sha256_pair (hasher.simf:27-32): out[i] = SHA-256(left[i] || right[i]). */
+int ssym_sha256_pair(ssym_ctx_t *, const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, int memspace);
+
+/* merkle_verify_32 without the asserts (merkle.simf:39-44): n paths of the same
+ * depth; siblings[i][depth][8]; writes the recomputed root and the final `path`
+ * (== 1 iff merkle.simf:42 holds).  ok_bits (NULL or (n+31)/32 words): bit i = 1
+ * iff path == 1 and root == expected_root[i] (expected_root may be NULL). */
+int ssym_merkle_root_from_path(ssym_ctx_t *, const uint32_t *leaf, const uint32_t *auth_path,
+                               const uint32_t *siblings, uint32_t depth, const uint32_t *expected_root,
+                               uint32_t *out_root, uint32_t *out_path, uint32_t *ok_bits, size_t n, int memspace);
+
+/* Channel transitions (channel.simf:31-172, fri/queries.simf:14-43).  A channel
+ * state is 9 words: digest[8] | n_sent.  In-place on `state`. */
+int ssym_channel_mix_u256(ssym_ctx_t *, uint32_t *state, const uint32_t *input, size_t n, int memspace);
+int ssym_channel_mix_u64(ssym_ctx_t *, uint32_t *state, const uint32_t *input_hi_lo, size_t n, int memspace);
+int ssym_channel_draw_qm31(ssym_ctx_t *, uint32_t *state, uint32_t *out, uint8_t *fail, size_t n, int memspace);
+int ssym_channel_draw_queries(ssym_ctx_t *, uint32_t *state, uint32_t log_size, uint32_t n_queries,
+                              uint32_t *out /* n * n_queries */, size_t n, int memspace);
+
+/* stark101 field jets (stark101/src/field.simf:14-94), p = 3*2^30 + 1. */
+int ssym_s101_mul_mod(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int memspace);
+int ssym_s101_div_mod(ssym_ctx_t *, const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *fail, size_t n, int memspace);
+
+/* Register-only IADD3 / LOP3 / SHF probe: returns measured 32-bit integer
+ * ops/s on this device (the INT32 roofline denominator). */
+int ssym_int32_peak_probe(ssym_ctx_t *, double *out_ops_per_s, double *out_ms);
+
+/* ------------------------------------------------------------------------- */
+/* Witness ingestion (host side; simfony-cli/src/main.rs:77-81 parse_witness)  */
+/* ------------------------------------------------------------------------- */
+
+/* Parse the text of a `.wit` JSON file produced by
+ * stwo-verifier/scripts/generate_wit.py:106-245 and pack it (one proof).
+ * `out` must hold layout.stride_words words.  Returns 0, or SSYM_ERR_PARSE when
+ * the text is not a witness of the program's types.  *shape_reject is set to 1
+ * when the witness is well-typed but a list length makes merkle.simf:42 fail
+ * (the record is then zero-filled and must be reported as rejected). */
+int ssym_stwo_pack_wit(const ssym_stwo_config_t *cfg, const char *json_text, size_t len,
+                       uint32_t *out, int *shape_reject);
+
+/* Same for stark101 `.wit` (stark101/scripts/generate_wit.py:7-30).  On entry
+ * *out_words is the capacity of `out`; on return the record length. */
+int ssym_s101_pack_wit(const char *json_text, size_t len, uint32_t *out, size_t *out_words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSYM_H */
