@@ -1,0 +1,383 @@
+#!/usr/bin/env python3
+"""Headline benchmark: Stwo proofs verified per second on N B200s (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): the reference's own `stwo-verifier/tests/data/proof.json` witness (prod preset:
+LDE 2^13, 16 queries, 1+8 FRI layers, 54 488 B packed, 3 806 SHA-256 compressions) replicated x1024 per GPU.
+A step = one pass of verify_proof over that batch.  Weak scaling: every rank verifies its own 1024-proof shard and the
+only exchange is the accept-bitmap gather.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 1024] [--mode ref-literal|prover-consistent]
+
+`value`  : whole-job proofs/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`    : the same metric through the C-ABI with HOST (pinned) buffers: H2D of the packed batch + D2H of the bitmap
+           inside the timed region.
+`roofline` / `roofline_int32` : the dominant kernel (stwo_merkle_kernel) against HBM and against the measured INT32 rate.
+`cpu_baseline` : the C oracle (a port of the .simf programs; the reference binary cannot be built here) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_PROOF = 54488
+COMPRESSIONS_PER_PROOF = 3806      # SURVEY.md section 8d (46 channel + 880 trace/CP decommit + 2880 FRI)
+MERKLE_COMPRESSIONS_PER_PROOF = 3760
+LITERAL_OPS_PER_COMPRESSION = 2296  # FIPS 180-4 literal: 64*26 + 48*13 + 8
+LITERAL_OPS_PER_PROOF = 3806 * 2296 + 65486 * 6 + 55220 * 4
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_workload(S, batch, mode_name):
+    import numpy as np
+
+    mode = S.MODE_REF_LITERAL if mode_name == "ref-literal" else S.MODE_PROVER_CONSISTENT
+    cfg = S.stwo_config("prod", mode)
+    text = open(os.path.join(ROOT, "tests", "golden", "stwo_proof_prod.wit")).read()
+    packed, bad = S.witness.pack_stwo_wits([text], cfg)
+    assert not bad[0]
+    lo = S.stwo_layout(cfg)
+    assert lo.algorithmic_bytes == ALG_BYTES_PER_PROOF
+    return cfg, lo, np.tile(packed, batch)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def oracle_run(orc, ocfg, packed, n, threads, proofs_total):
+    """Verify `proofs_total` proofs (cycling through the n-proof batch) on `threads` threads; returns seconds."""
+    from oracle import oracle as O
+
+    per = (proofs_total + threads - 1) // threads
+    ptr = packed.ctypes.data_as(O.u32p)
+
+    def work(t):
+        done, begin = 0, (t * per) % n
+        while done < per:
+            m = min(per - done, n - begin)
+            orc.lib.oracle_stwo_verify_batch(C.byref(ocfg), ptr, begin, begin + m, None, None, None)
+            done += m
+            begin = (begin + m) % n
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0, per * threads
+
+
+def cpu_baseline(cfg, packed, n, budget_s=15.0):
+    from oracle import oracle as O
+
+    orc = O.Oracle()
+    ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    threads = cpu_threads()
+    t1, _ = oracle_run(orc, ocfg, packed, n, 1, 8)
+    per_proof = t1 / 8
+    total = int(max(threads * 8, min(budget_s / per_proof, 64 * n)))
+    dt, done = oracle_run(orc, ocfg, packed, n, threads, total)
+    return {"value": done / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
+            "sample": f"{done} proofs (cycling the same {n}-proof batch) on {threads} threads, {dt:.2f} s wall; oracle/ssym_oracle.c -O3, "
+                      "plain C SHA-256 (the reference's `simfony run` cannot be built here: no Rust, un-vendored crates)",
+            "compressions_per_s": done * COMPRESSIONS_PER_PROOF / dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path = the oracle port (see cpu_baseline.kind), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+
+    from oracle import oracle as O
+    from oracle import witparse as W
+
+    mode = O.MODE_REF_LITERAL if args.mode == "ref-literal" else O.MODE_PROVER_CONSISTENT
+    ocfg = O.make_config("prod", mode)
+    wit = W.load_wit(open(os.path.join(ROOT, "tests", "golden", "stwo_proof_prod.wit")).read())
+    one, _ = W.pack_stwo(wit, 16, 8, 13)
+    n = args.batch
+    packed = np.tile(one, n)
+    orc = O.Oracle()
+    threads = cpu_threads()
+    t1, _ = oracle_run(orc, ocfg, packed, n, 1, 8)
+    per_proof = t1 / 8
+    budget = 100.0
+    m = int(max(threads, min(n, budget * threads / ((args.steps + args.warmup) * per_proof))))
+    for _ in range(args.warmup):
+        oracle_run(orc, ocfg, packed, n, threads, m)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        _, d = oracle_run(orc, ocfg, packed, n, threads, m)
+        done += d
+    dt = time.perf_counter() - t0
+    value = done / dt
+    sample = f"{done // args.steps} proofs per step (of the {n}-proof batch) x {args.steps} steps on {threads} threads"
+    line = {
+        "impl": "reference", "metric": "stwo_proofs_verified_per_s", "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "reference fixture stwo-verifier/tests/data/proof.json replicated",
+        "config": {"workload": f"stwo-verifier proof.json witness (prod preset) replicated x{n}", "mode": args.mode, "batch_per_gpu": n},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
+
+    def __init__(self, torch_device_index):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop = threading.Event()
+        self.ok = False
+        self.max_mhz = None
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            log(f"clock sampling unavailable: {e}")
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self.stop.wait(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.ok:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="proofs per GPU per step (BASELINE config: 1024)")
+    ap.add_argument("--mode", default="ref-literal", choices=["ref-literal", "prover-consistent"])
+    ap.add_argument("--copies", type=int, default=4, help="distinct device copies of the batch rotated through (defeats L2 reuse)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps or 20
+        args.warmup = 3 if args.warmup is None else args.warmup
+        return run_reference(args)
+    args.steps = args.steps or 2000
+    args.warmup = max(3, 50 if args.warmup is None else args.warmup)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libssym has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    import stark_symphony_b200 as S
+    from importlib import import_module
+
+    sharding = import_module("stark_symphony_b200.sharding")
+
+    n = args.batch
+    cfg, lo, host_batch = load_workload(S, n, args.mode)
+    ver = S.Verifier(local_rank)
+    stream = torch.cuda.current_stream()
+    ver.set_stream(stream.cuda_stream)
+
+    # R distinct device copies of the batch, rotated: R * n * 54.5 KB > 126 MB L2, so no step finds its input in L2
+    copies = max(1, args.copies)
+    dev = [torch.from_numpy(host_batch.view(np.int32)).cuda() for _ in range(copies)]
+    accept = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    total_n = n * world
+
+    def step(k):
+        ver.stwo_verify_batch(dev[k % copies], cfg, n, accept_out=accept, status_out=status)
+        if world > 1:
+            return sharding.gather_accept_bitmaps(accept, total_n, world)
+        return accept
+
+    int32_ops, probe_ms = ver.int32_peak_probe()
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    ver.profile_read()
+    ver.profile_enable(True)
+    launches0 = ver.launch_count
+    with ClockSampler(local_rank) as clocks:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(args.steps):
+            full = step(k)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+    ver.profile_enable(False)
+    launches = ver.launch_count - launches0
+    prof = ver.profile_read()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = total_n * args.steps / (ms_max * 1e-3)
+
+    # correctness of what was timed (outside the timed region): every rank's statuses against the oracle on a slice
+    st = status.cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(full.cpu().numpy().view(np.uint8), bitorder="little")[:total_n]
+    accepted = int(bits.sum())
+    if rank == 0:
+        from oracle import oracle as O
+
+        orc = O.Oracle()
+        ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+        _, o_status, _ = orc.stwo_verify_batch(ocfg, host_batch, 4)
+        assert (st[:4] == o_status).all() and (st == st[0]).all(), "GPU status differs from the oracle"
+        assert accepted == (total_n if args.mode == "prover-consistent" else 0)
+
+    # end to end: host (pinned) buffers through the same C-ABI call, copies inside the timed region
+    pinned = torch.empty(host_batch.size, dtype=torch.int32).pin_memory()
+    pinned.numpy()[:] = host_batch.view(np.int32)
+    host_view = pinned.numpy().view(np.uint32)
+    acc_host = torch.empty((n + 31) // 32, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    ver.set_stream(None)
+    e2e_steps = max(5, min(args.steps, 100))
+    for _ in range(3):
+        ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc_host)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc_host)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_n * e2e_steps / float(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json (driver-measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        mk_ms, mk_n = prof.get("stwo_merkle", (0.0, 0))
+        mk_avg_ms = mk_ms / max(mk_n, 1)
+        kernel_ms = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
+        share = mk_ms / max(sum(v[0] for v in prof.values()), 1e-9)
+        hbm_achieved = n * ALG_BYTES_PER_PROOF / (mk_avg_ms * 1e-3) / 1e9 if mk_avg_ms else 0.0
+        lit_ops = n * MERKLE_COMPRESSIONS_PER_PROOF * LITERAL_OPS_PER_COMPRESSION / (mk_avg_ms * 1e-3) if mk_avg_ms else 0.0
+        line = {
+            "metric": "stwo_proofs_verified_per_s", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "reference fixture stwo-verifier/tests/data/proof.json (via generate_wit.py) replicated; no synthetic prover exists",
+            "config": {"workload": f"stwo-verifier proof.json witness (prod preset: LDE 2^13, 16 queries, 1+8 FRI layers) replicated x{n} per GPU",
+                       "mode": args.mode, "batch_per_gpu": n, "accepted": accepted,
+                       "l2": f"rotating {copies} distinct device copies of the batch ({copies * n * lo.stride_words * 4 / 1e6:.0f} MB > 126 MB L2)",
+                       "parallelism": f"proof-sharded x{world}, accept-bitmap all_gather per step" if world > 1 else "single GPU"},
+            "merkle_hashes_per_s": value * MERKLE_COMPRESSIONS_PER_PROOF / 2.0,
+            "sha256_compressions_per_s": value * COMPRESSIONS_PER_PROOF,
+            "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n * lo.stride_words * 4), "d2h_bytes_per_step": int(acc_host.nbytes),
+                    "steps": e2e_steps, "note": "ssym_stwo_verify_batch(SSYM_MEM_HOST): pinned host batch -> chunked double-buffered H2D -> kernels -> D2H bitmap"},
+            "gpu_launches": int(launches),
+            "kernel_ms": kernel_ms,
+            "roofline": {"bound": "hbm", "kernel": "stwo_merkle_kernel", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": hbm_achieved / hbm_peak if hbm_peak else None, "traffic": None, "peak_source": peak_src,
+                         "kernel_share_of_step": share, "avg_launch_ms": mk_avg_ms,
+                         "note": "the kernel is INT32-ALU bound (170 int-ops per byte), not HBM bound: see roofline_int32"},
+            "roofline_int32": {"bound": "int32_alu", "kernel": "stwo_merkle_kernel", "achieved": lit_ops / 1e12, "peak": int32_ops / 1e12, "unit": "Tops/s",
+                               "frac": lit_ops / int32_ops if int32_ops else None,
+                               "convention": "achieved = FIPS-180-4-literal 2296 ops x compressions / kernel time (SURVEY 8d); peak = measured SHF/LOP3/IADD3 "
+                                             "machine-instruction lanes/s (ssym_int32_peak_probe); LOP3/IADD3 fusion makes >1.0 possible",
+                               "probe_ms": probe_ms},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg, host_batch, n)
+        print(json.dumps(line), flush=True)
+    ver.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

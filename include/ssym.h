@@ -32,6 +32,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this API is exported */
+#endif
 
 #define SSYM_OK 0
 #define SSYM_ERR_USAGE (-1)
@@ -203,6 +206,14 @@ int ssym_synchronize(ssym_ctx_t *ctx);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t ssym_launch_count(const ssym_ctx_t *ctx);
 
+/* Per-kernel device timing (CUDA events recorded around every verifier kernel on the launching stream).
+ * Kernel ids: 0 stwo transcript, 1 stwo query, 2 stwo merkle, 3 stwo finalize, 4 stark101 transcript,
+ * 5 stark101 merkle, 6 stark101 finalize.  ssym_profile_read synchronises the stream, adds up the elapsed
+ * time and launch count per kernel id since the last read (arrays of SSYM_PROFILE_KERNELS) and resets. */
+#define SSYM_PROFILE_KERNELS 8
+int ssym_profile_enable(ssym_ctx_t *ctx, int on);
+int ssym_profile_read(ssym_ctx_t *ctx, double *ms_per_kernel, uint64_t *launches_per_kernel);
+
 /* ------------------------------------------------------------------------- */
 /* Whole-proof batch verification                                             */
 /* ------------------------------------------------------------------------- */
@@ -298,6 +309,9 @@ int ssym_stwo_pack_wit(const ssym_stwo_config_t *cfg, const char *json_text, siz
  * *out_words is the capacity of `out`; on return the record length. */
 int ssym_s101_pack_wit(const char *json_text, size_t len, uint32_t *out, size_t *out_words);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,597 @@
+// SPDX-License-Identifier: MIT
+// C-ABI of libssym (include/ssym.h): handle, memory staging, chunked launch of the verifier kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ssym.h"
+#include "jets_kernels.cuh"
+#include "s101_kernels.cuh"
+#include "stwo_kernels.cuh"
+
+using namespace ssym;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                           \
+    do {                                                                                                         \
+        cudaError_t e_ = (expr);                                                                                 \
+        if (e_ != cudaSuccess) return fail(SSYM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct EventProfiler : Profiler {
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t cur = nullptr;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int, cudaStream_t s) override { cur = get(); cudaEventRecord(cur, s); }
+    void end(int id, cudaStream_t s) override {
+        cudaEvent_t b = get();
+        cudaEventRecord(b, s);
+        recs.push_back({id, cur, b});
+    }
+    void collect(double *ms, uint64_t *cnt) {
+        for (Rec &r : recs) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.id >= 0 && r.id < SSYM_PROFILE_KERNELS) { ms[r.id] += t; cnt[r.id] += 1; }
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    ~EventProfiler() {
+        for (Rec &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+};
+
+struct ssym_ctx {
+    int device = 0;
+    EventProfiler profiler;
+    bool profiling = false;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    uint64_t launches = 0;
+    // Stwo scratch (per chunk) and domain tables (per config)
+    DevBuf stwo_ctx, stwo_evals, status;
+    DevBuf tab_point, tab_fold, tab_flag;
+    uint32_t tab_G = 0, tab_L = 0xffffffffu;
+    uint32_t fold_off[SSYM_MAX_FRI_LAYERS] = {0};
+    // host-memspace staging
+    DevBuf stage[2], d_accept, d_status, d_trace, d_offsets;
+    // stark101 scratch
+    DevBuf s101_ctx;
+    // jets staging
+    DevBuf tmp[6];
+};
+
+static const size_t STWO_DEVICE_CHUNK = 32768; // proofs per launch group (bounds scratch: ~3 KB / proof)
+
+extern "C" {
+
+const char *ssym_last_error(void) { return g_last_error.c_str(); }
+const char *ssym_version(void) { return "libssym 0.1 (sm_100a)"; }
+
+int ssym_create(int device, ssym_ctx_t **out) {
+    if (!out) return fail(SSYM_ERR_USAGE, "out is NULL");
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(SSYM_ERR_CUDA, "no such CUDA device");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SSYM_ERR_CUDA, "libssym is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+    CUDA_TRY(cudaSetDevice(device));
+    ssym_ctx *c = new ssym_ctx();
+    c->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return SSYM_OK;
+}
+
+void ssym_destroy(ssym_ctx_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf *bufs[] = {&c->stwo_ctx, &c->stwo_evals, &c->status, &c->tab_point, &c->tab_fold, &c->tab_flag, &c->stage[0], &c->stage[1],
+                      &c->d_accept, &c->d_status, &c->d_trace, &c->d_offsets, &c->s101_ctx};
+    for (DevBuf *b : bufs) b->release();
+    for (DevBuf &b : c->tmp) b.release();
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(c->ev_h2d[i]);
+        cudaEventDestroy(c->ev_done[i]);
+    }
+    cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int ssym_set_stream(ssym_ctx_t *c, void *cuda_stream) {
+    if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return SSYM_OK;
+}
+int ssym_synchronize(ssym_ctx_t *c) {
+    if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SSYM_OK;
+}
+uint64_t ssym_launch_count(const ssym_ctx_t *c) { return c ? c->launches : 0; }
+int ssym_profile_enable(ssym_ctx_t *c, int on) {
+    if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
+    c->profiling = on != 0;
+    return SSYM_OK;
+}
+int ssym_profile_read(ssym_ctx_t *c, double *ms, uint64_t *cnt) {
+    if (!c || !ms || !cnt) return fail(SSYM_ERR_USAGE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < SSYM_PROFILE_KERNELS; i++) { ms[i] = 0; cnt[i] = 0; }
+    c->profiler.collect(ms, cnt);
+    return SSYM_OK;
+}
+
+/* ---- configuration / layout -------------------------------------------------------------------- */
+int ssym_stwo_config_preset(const char *name, uint32_t mode, ssym_stwo_config_t *out) {
+    if (!name || !out || mode > 1) return fail(SSYM_ERR_USAGE, "bad preset arguments");
+    memset(out, 0, sizeof *out);
+    out->mode = mode;
+    out->pow_target = 0x07ffffffffffffffull; // config.simf:32,51
+    if (!strcmp(name, "prod")) { // config.simf:34-52
+        out->trace_log = 9; out->lde_log = 13; out->n_queries = 16; out->n_fri_layers = 8;
+    } else if (!strcmp(name, "testing")) { // config.simf:16-33
+        out->trace_log = 3; out->lde_log = 4; out->n_queries = 1; out->n_fri_layers = 2;
+    } else {
+        return fail(SSYM_ERR_USAGE, "unknown preset (prod | testing)");
+    }
+    return SSYM_OK;
+}
+
+static uint32_t align8(uint32_t w) { return (w + 7u) & ~7u; }
+
+int ssym_stwo_layout(const ssym_stwo_config_t *cfg, ssym_stwo_layout_t *o) {
+    if (!cfg || !o) return fail(SSYM_ERR_USAGE, "NULL argument");
+    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log;
+    if (Q < 1 || Q > SSYM_MAX_QUERIES || L + 1 > SSYM_MAX_FRI_LAYERS || G < L + 1 || G > 30 || cfg->mode > 1 || cfg->trace_log > 255)
+        return fail(SSYM_ERR_USAGE, "unsupported Stwo configuration");
+    memset(o, 0, sizeof *o);
+    uint32_t w = 0, alg = 0;
+    o->off_commit = w; w += 24;
+    o->off_oods_trace = w; w += 16;
+    o->off_oods_cp = w; w += 64;
+    o->off_fri_first_root = w; w += 8;
+    o->off_fri_inner_root = w; w += 8 * L;
+    o->off_last_coeff = w; w += 4;
+    o->off_pow_nonce = w; w += 2;
+    alg += w; w = align8(w);
+    o->off_qvals = w; w += Q * 20; alg += Q * 20; w = align8(w);
+    o->off_trace_sib = w; w += Q * G * 8; alg += Q * G * 8;
+    o->off_cp_sib = w; w += Q * G * 8; alg += Q * G * 8;
+    o->off_fri_wit = w; w += (L + 1) * Q * 4; alg += (L + 1) * Q * 4; w = align8(w);
+    for (uint32_t l = 0; l <= L; l++) {
+        o->off_fri_sib[l] = w;
+        w += Q * (G - 1 - l) * 8;
+        alg += Q * (G - 1 - l) * 8;
+    }
+    o->stride_words = align8(w);
+    o->algorithmic_bytes = alg * 4;
+    return SSYM_OK;
+}
+
+} // extern "C"
+
+/* ---- Stwo batch ---------------------------------------------------------------------------------- */
+static int ensure_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg) {
+    const uint32_t G = cfg.lde_log, L = cfg.n_fri_layers;
+    if (c->tab_G == G && c->tab_L == L) return SSYM_OK;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l <= L; l++) {
+        c->fold_off[l] = off;
+        off += 1u << (G - l - 1);
+    }
+    CUDA_TRY(c->tab_point.ensure(sizeof(uint2) << G));
+    CUDA_TRY(c->tab_fold.ensure(sizeof(uint32_t) * off));
+    CUDA_TRY(c->tab_flag.ensure(sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(c->tab_flag.p, 0, sizeof(uint32_t), c->stream));
+    launch_stwo_tables(G, L, c->tab_point.as<uint2>(), c->tab_fold.as<uint32_t>(), c->fold_off, c->tab_flag.as<uint32_t>(), c->stream);
+    c->launches += 1;
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, c->tab_flag.p, sizeof flag, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    if (flag) return fail(SSYM_ERR_USAGE, "Stwo configuration has a fold domain containing a zero coordinate");
+    c->tab_G = G;
+    c->tab_L = L;
+    return SSYM_OK;
+}
+
+static int stwo_launch_chunk(ssym_ctx *c, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, const uint32_t *d_packed,
+                             size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s) {
+    const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers;
+    for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
+        const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
+        CUDA_TRY(c->stwo_ctx.ensure(m * StwoCtxLayout::WORDS * sizeof(uint32_t)));
+        CUDA_TRY(c->stwo_evals.ensure(m * (size_t)(L + 1) * Q * 4 * sizeof(uint32_t)));
+        StwoParams p;
+        p.cfg = cfg;
+        p.lo = lo;
+        p.tab.point = c->tab_point.as<uint2>();
+        p.tab.fold_inv = c->tab_fold.as<uint32_t>();
+        for (uint32_t l = 0; l < SSYM_MAX_FRI_LAYERS; l++) p.tab.fold_off[l] = c->fold_off[l];
+        p.packed = d_packed + done * (size_t)lo.stride_words;
+        p.ctx = c->stwo_ctx.as<uint32_t>();
+        p.fri_evals = c->stwo_evals.as<uint32_t>();
+        if (d_status_out) {
+            p.status = d_status_out + done;
+        } else {
+            CUDA_TRY(c->status.ensure(m * sizeof(uint32_t)));
+            p.status = c->status.as<uint32_t>();
+        }
+        p.trace = d_trace ? d_trace + done : nullptr;
+        p.n = (uint32_t)m;
+        if (p.trace) CUDA_TRY(cudaMemsetAsync(p.trace, 0, m * sizeof(ssym_stwo_trace_t), s));
+        launch_stwo_verify(p, d_accept + done / 32, s, &c->launches, c->profiling ? &c->profiler : nullptr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SSYM_OK;
+}
+
+extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n,
+                                      uint32_t *accept_bits, uint32_t *status, ssym_stwo_trace_t *trace, int memspace) {
+    if (!c || !cfg || !accept_bits || (!packed && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    ssym_stwo_layout_t lo;
+    int rc = ssym_stwo_layout(cfg, &lo);
+    if (rc) return rc;
+    if (n == 0) return SSYM_OK;
+    if (n > 0xffffffffull / SSYM_MAX_QUERIES) return fail(SSYM_ERR_USAGE, "batch too large for one call");
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = ensure_tables(c, *cfg);
+    if (rc) return rc;
+    if (memspace == SSYM_MEM_DEVICE) return stwo_launch_chunk(c, *cfg, lo, packed, n, accept_bits, status, trace, c->stream);
+    if (memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+
+    // Host buffers: double-buffered H2D on the copy stream overlapped with the kernels of the previous chunk.
+    const size_t stride_b = (size_t)lo.stride_words * 4;
+    size_t hc = ((n + 3) / 4 + 31) & ~(size_t)31;
+    hc = std::max<size_t>(256, std::min<size_t>(hc, 2048));
+    hc = std::min(hc, (n + 31) & ~(size_t)31);
+    const size_t n_words = (n + 31) / 32;
+    CUDA_TRY(c->stage[0].ensure(hc * stride_b));
+    CUDA_TRY(c->stage[1].ensure(hc * stride_b));
+    CUDA_TRY(c->d_accept.ensure(n_words * 4));
+    CUDA_TRY(c->d_status.ensure(n * 4));
+    if (trace) CUDA_TRY(c->d_trace.ensure(n * sizeof(ssym_stwo_trace_t)));
+    cudaStream_t s = c->stream;
+    size_t chunk = 0;
+    for (size_t done = 0; done < n; done += hc, chunk++) {
+        const size_t m = std::min(hc, n - done);
+        const int b = (int)(chunk & 1);
+        if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(c->stage[b].p, packed + done * (size_t)lo.stride_words, m * stride_b, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
+        rc = stwo_launch_chunk(c, *cfg, lo, c->stage[b].as<uint32_t>(), m, c->d_accept.as<uint32_t>() + done / 32,
+                               c->d_status.as<uint32_t>() + done, trace ? c->d_trace.as<ssym_stwo_trace_t>() + done : nullptr, s);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_done[b], s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_stwo_trace_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    return SSYM_OK;
+}
+
+/* ---- stark101 batch -------------------------------------------------------------------------------- */
+extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, const uint64_t *offsets, size_t n, uint32_t *accept_bits,
+                                          uint32_t *status, ssym_s101_trace_t *trace, int memspace) {
+    if (!c || !accept_bits || ((!blob || !offsets) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (n == 0) return SSYM_OK;
+    if (n > 0x7fffffffull) return fail(SSYM_ERR_USAGE, "batch too large for one call");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    CUDA_TRY(c->s101_ctx.ensure(n * S101_CTX_WORDS * sizeof(uint32_t)));
+    S101Params p;
+    p.ctx = c->s101_ctx.as<uint32_t>();
+    p.n = (uint32_t)n;
+    p.max_layers = SSYM_S101_MAX_LIST;
+    if (memspace == SSYM_MEM_DEVICE) {
+        p.blob = blob;
+        p.offsets = offsets;
+        if (status) p.status = status;
+        else { CUDA_TRY(c->status.ensure(n * 4)); p.status = c->status.as<uint32_t>(); }
+        p.trace = trace;
+        if (trace) CUDA_TRY(cudaMemsetAsync(trace, 0, n * sizeof(ssym_s101_trace_t), s));
+        launch_s101_verify(p, accept_bits, s, &c->launches, c->profiling ? &c->profiler : nullptr);
+        CUDA_TRY(cudaGetLastError());
+        return SSYM_OK;
+    }
+    if (memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    const uint64_t total_words = offsets[n];
+    uint32_t max_layers = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (offsets[i + 1] < offsets[i] + 20 || blob[offsets[i]] != offsets[i + 1] - offsets[i])
+            return fail(SSYM_ERR_USAGE, "stark101 offsets do not match the record lengths");
+        max_layers = std::max(max_layers, std::min<uint32_t>(blob[offsets[i] + 1], SSYM_S101_MAX_LIST));
+    }
+    p.max_layers = max_layers;
+    const size_t n_words = (n + 31) / 32;
+    CUDA_TRY(c->stage[0].ensure(total_words * 4));
+    CUDA_TRY(c->d_offsets.ensure((n + 1) * 8));
+    CUDA_TRY(c->d_accept.ensure(n_words * 4));
+    CUDA_TRY(c->d_status.ensure(n * 4));
+    if (trace) CUDA_TRY(c->d_trace.ensure(n * sizeof(ssym_s101_trace_t)));
+    CUDA_TRY(cudaMemcpyAsync(c->stage[0].p, blob, total_words * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->d_offsets.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    p.blob = c->stage[0].as<uint32_t>();
+    p.offsets = c->d_offsets.as<uint64_t>();
+    p.status = c->d_status.as<uint32_t>();
+    p.trace = trace ? c->d_trace.as<ssym_s101_trace_t>() : nullptr;
+    if (trace) CUDA_TRY(cudaMemsetAsync(p.trace, 0, n * sizeof(ssym_s101_trace_t), s));
+    launch_s101_verify(p, c->d_accept.as<uint32_t>(), s, &c->launches, c->profiling ? &c->profiler : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_s101_trace_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SSYM_OK;
+}
+
+/* ---- element-wise jets ------------------------------------------------------------------------------- */
+namespace {
+// Stages host arrays through the handle's temp buffers; for device memspace it is a pass-through.
+struct Staging {
+    ssym_ctx *c;
+    int memspace;
+    int slot = 0;
+    struct Out { void *host; void *dev; size_t bytes; };
+    std::vector<Out> outs;
+    int err = 0;
+    Staging(ssym_ctx *c_, int m) : c(c_), memspace(m) {}
+    template <class T>
+    const T *in(const T *ptr, size_t count) {
+        if (memspace == SSYM_MEM_DEVICE || !ptr) return ptr;
+        DevBuf &b = c->tmp[slot++];
+        if (b.ensure(count * sizeof(T) + 16) != cudaSuccess || cudaMemcpyAsync(b.p, ptr, count * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { err = 1; return nullptr; }
+        return b.as<T>();
+    }
+    template <class T>
+    T *out(T *ptr, size_t count, bool copy_in = false) {
+        if (memspace == SSYM_MEM_DEVICE || !ptr) return ptr;
+        DevBuf &b = c->tmp[slot++];
+        if (b.ensure(count * sizeof(T) + 16) != cudaSuccess) { err = 1; return nullptr; }
+        if (copy_in && cudaMemcpyAsync(b.p, ptr, count * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { err = 1; return nullptr; }
+        outs.push_back({ptr, b.p, count * sizeof(T)});
+        return b.as<T>();
+    }
+    int finish() {
+        if (err) return fail(SSYM_ERR_CUDA, "staging allocation / copy failed");
+        CUDA_TRY(cudaGetLastError());
+        if (memspace == SSYM_MEM_DEVICE) return SSYM_OK;
+        for (auto &o : outs) CUDA_TRY(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return SSYM_OK;
+    }
+};
+
+int field_jet(ssym_ctx *c, int op, const uint32_t *a, int wa, const uint32_t *b, int wb, uint32_t *out, int wo, uint8_t *failp, size_t n, int memspace) {
+    if (!c || !a || !out || (wb && !b)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Staging st(c, memspace);
+    const uint32_t *da = st.in(a, n * wa);
+    const uint32_t *db = wb ? st.in(b, n * wb) : nullptr;
+    uint32_t *dout = st.out(out, n * wo);
+    uint8_t *dfail = st.out(failp, n);
+    if (st.err) return st.finish();
+    if (launch_field_jet(op, da, db, dout, dfail, n, c->stream)) return fail(SSYM_ERR_USAGE, "unknown jet");
+    c->launches += n ? 1 : 0;
+    return st.finish();
+}
+} // namespace
+
+extern "C" {
+int ssym_m31_add(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_M31_ADD, a, 1, b, 1, o, 1, nullptr, n, m); }
+int ssym_m31_sub(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_M31_SUB, a, 1, b, 1, o, 1, nullptr, n, m); }
+int ssym_m31_neg(ssym_ctx_t *c, const uint32_t *a, uint32_t *o, size_t n, int m) { return field_jet(c, JET_M31_NEG, a, 1, nullptr, 0, o, 1, nullptr, n, m); }
+int ssym_m31_mul(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_M31_MUL, a, 1, b, 1, o, 1, nullptr, n, m); }
+int ssym_m31_inv(ssym_ctx_t *c, const uint32_t *a, uint32_t *o, uint8_t *f, size_t n, int m) { return field_jet(c, JET_M31_INV, a, 1, nullptr, 0, o, 1, f, n, m); }
+int ssym_cm31_mul(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_CM31_MUL, a, 2, b, 2, o, 2, nullptr, n, m); }
+int ssym_cm31_inv(ssym_ctx_t *c, const uint32_t *a, uint32_t *o, uint8_t *f, size_t n, int m) { return field_jet(c, JET_CM31_INV, a, 2, nullptr, 0, o, 2, f, n, m); }
+int ssym_qm31_add(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_QM31_ADD, a, 4, b, 4, o, 4, nullptr, n, m); }
+int ssym_qm31_sub(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_QM31_SUB, a, 4, b, 4, o, 4, nullptr, n, m); }
+int ssym_qm31_mul(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_QM31_MUL, a, 4, b, 4, o, 4, nullptr, n, m); }
+int ssym_qm31_inv(ssym_ctx_t *c, const uint32_t *a, uint32_t *o, uint8_t *f, size_t n, int m) { return field_jet(c, JET_QM31_INV, a, 4, nullptr, 0, o, 4, f, n, m); }
+int ssym_qm31_mul_m31(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_QM31_MUL_M31, a, 4, b, 1, o, 4, nullptr, n, m); }
+int ssym_qm31_mul_cm31(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n, int m) { return field_jet(c, JET_QM31_MUL_CM31, a, 4, b, 2, o, 4, nullptr, n, m); }
+
+int ssym_circle_point(ssym_ctx_t *c, const uint32_t *index, uint32_t *out_xy, size_t n, int memspace) {
+    if (!c || !index || !out_xy) return fail(SSYM_ERR_USAGE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Staging st(c, memspace);
+    const uint32_t *di = st.in(index, n);
+    uint32_t *dout = st.out(out_xy, 2 * n);
+    if (st.err) return st.finish();
+    launch_circle_point(di, dout, n, c->stream);
+    c->launches += n ? 1 : 0;
+    return st.finish();
+}
+
+static int fold_impl(ssym_ctx_t *c, bool circle, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p, const uint32_t *alpha,
+                     uint32_t log_size, uint32_t *out, uint8_t *failp, size_t n, int memspace) {
+    if (!c || !position || !f_p || !f_neg_p || !alpha || !out) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (log_size > 31) return fail(SSYM_ERR_USAGE, "log_size > 31");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Staging st(c, memspace);
+    const uint32_t *dp = st.in(position, n), *da = st.in(f_p, 4 * n), *db = st.in(f_neg_p, 4 * n), *dal = st.in(alpha, 4 * n);
+    uint32_t *dout = st.out(out, 4 * n);
+    uint8_t *dfail = st.out(failp, n);
+    if (st.err) return st.finish();
+    launch_fold(circle, dp, da, db, dal, log_size, dout, dfail, n, c->stream);
+    c->launches += n ? 1 : 0;
+    return st.finish();
+}
+int ssym_circle_fold(ssym_ctx_t *c, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p, const uint32_t *alpha,
+                     uint32_t log_size, uint32_t *out, uint8_t *f, size_t n, int m) {
+    return fold_impl(c, true, position, f_p, f_neg_p, alpha, log_size, out, f, n, m);
+}
+int ssym_line_fold(ssym_ctx_t *c, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p, const uint32_t *alpha,
+                   uint32_t log_size, uint32_t *out, uint8_t *f, size_t n, int m) {
+    return fold_impl(c, false, position, f_p, f_neg_p, alpha, log_size, out, f, n, m);
+}
+
+int ssym_sha256_pair(ssym_ctx_t *c, const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, int memspace) {
+    if (!c || !left || !right || !out) return fail(SSYM_ERR_USAGE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Staging st(c, memspace);
+    const uint32_t *dl = st.in(left, 8 * n), *dr = st.in(right, 8 * n);
+    uint32_t *dout = st.out(out, 8 * n);
+    if (st.err) return st.finish();
+    launch_sha256_pair(dl, dr, dout, n, c->stream);
+    c->launches += n ? 1 : 0;
+    return st.finish();
+}
+
+int ssym_merkle_root_from_path(ssym_ctx_t *c, const uint32_t *leaf, const uint32_t *auth_path, const uint32_t *siblings, uint32_t depth,
+                               const uint32_t *expected_root, uint32_t *out_root, uint32_t *out_path, uint32_t *ok_bits, size_t n, int memspace) {
+    if (!c || !leaf || !auth_path || (!siblings && depth)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (depth > 31) return fail(SSYM_ERR_USAGE, "List<u256, 32> holds at most 31 siblings");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Staging st(c, memspace);
+    // more than 6 arrays may need staging: stage the two small per-path arrays together with the big ones
+    const uint32_t *dl = st.in(leaf, 8 * n), *da = st.in(auth_path, n), *ds = st.in(siblings, (size_t)depth * 8 * n);
+    const uint32_t *de = st.in(expected_root, 8 * n);
+    uint32_t *dr = st.out(out_root, 8 * n);
+    if (st.err) return st.finish();
+    // out_path and ok_bits share the last temp slot when both are requested from host memory
+    uint32_t *dp = nullptr, *dk = nullptr;
+    const size_t kw = (n + 31) / 32;
+    if (memspace == SSYM_MEM_DEVICE) {
+        dp = out_path;
+        dk = ok_bits;
+    } else if (out_path || ok_bits) {
+        DevBuf &b = c->tmp[5];
+        if (b.ensure((n + kw) * 4 + 16) != cudaSuccess) return fail(SSYM_ERR_CUDA, "staging allocation failed");
+        if (out_path) { dp = b.as<uint32_t>(); st.outs.push_back({out_path, dp, n * 4}); }
+        if (ok_bits) { dk = b.as<uint32_t>() + n; st.outs.push_back({ok_bits, dk, kw * 4}); }
+    }
+    launch_merkle_path(dl, da, ds, depth, de, dr, dp, dk, n, c->stream);
+    c->launches += n ? 1 : 0;
+    return st.finish();
+}
+
+static int channel_impl(ssym_ctx_t *c, int op, uint32_t *state, const uint32_t *input, size_t in_words, uint32_t *out, size_t out_words,
+                        uint8_t *failp, uint32_t log_size, uint32_t n_queries, size_t n, int memspace) {
+    if (!c || !state) return fail(SSYM_ERR_USAGE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Staging st(c, memspace);
+    uint32_t *dst = st.out(state, 9 * n, true);
+    const uint32_t *din = in_words ? st.in(input, in_words * n) : nullptr;
+    uint32_t *dout = out_words ? st.out(out, out_words * n) : nullptr;
+    uint8_t *dfail = st.out(failp, n);
+    if (st.err) return st.finish();
+    launch_channel(op, dst, din, dout, dfail, log_size, n_queries, n, c->stream);
+    c->launches += n ? 1 : 0;
+    return st.finish();
+}
+int ssym_channel_mix_u256(ssym_ctx_t *c, uint32_t *state, const uint32_t *input, size_t n, int m) {
+    if (!input) return fail(SSYM_ERR_USAGE, "NULL argument");
+    return channel_impl(c, CHAN_MIX_U256, state, input, 8, nullptr, 0, nullptr, 0, 0, n, m);
+}
+int ssym_channel_mix_u64(ssym_ctx_t *c, uint32_t *state, const uint32_t *input_hi_lo, size_t n, int m) {
+    if (!input_hi_lo) return fail(SSYM_ERR_USAGE, "NULL argument");
+    return channel_impl(c, CHAN_MIX_U64, state, input_hi_lo, 2, nullptr, 0, nullptr, 0, 0, n, m);
+}
+int ssym_channel_draw_qm31(ssym_ctx_t *c, uint32_t *state, uint32_t *out, uint8_t *f, size_t n, int m) {
+    if (!out) return fail(SSYM_ERR_USAGE, "NULL argument");
+    return channel_impl(c, CHAN_DRAW_QM31, state, nullptr, 0, out, 4, f, 0, 0, n, m);
+}
+int ssym_channel_draw_queries(ssym_ctx_t *c, uint32_t *state, uint32_t log_size, uint32_t n_queries, uint32_t *out, size_t n, int m) {
+    if (!out || n_queries == 0 || n_queries > 64 || log_size > 31) return fail(SSYM_ERR_USAGE, "bad draw_queries arguments");
+    return channel_impl(c, CHAN_DRAW_QUERIES, state, nullptr, 0, out, n_queries, nullptr, log_size, n_queries, n, m);
+}
+
+static int s101_field_impl(ssym_ctx_t *c, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *failp, size_t n, int memspace) {
+    if (!c || !a || !b || !out) return fail(SSYM_ERR_USAGE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Staging st(c, memspace);
+    const uint32_t *da = st.in(a, n), *db = st.in(b, n);
+    uint32_t *dout = st.out(out, n);
+    uint8_t *dfail = st.out(failp, n);
+    if (st.err) return st.finish();
+    launch_s101_field(op, da, db, dout, dfail, n, c->stream);
+    c->launches += n ? 1 : 0;
+    return st.finish();
+}
+int ssym_s101_mul_mod(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int m) { return s101_field_impl(c, 0, a, b, out, nullptr, n, m); }
+int ssym_s101_div_mod(ssym_ctx_t *c, const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *f, size_t n, int m) { return s101_field_impl(c, 1, a, b, out, f, n, m); }
+
+int ssym_int32_peak_probe(ssym_ctx_t *c, double *out_ops_per_s, double *out_ms) {
+    if (!c || !out_ops_per_s) return fail(SSYM_ERR_USAGE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->tmp[0].ensure(256));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best_ms = 1e30, ops = 0;
+    for (int rep = 0; rep < 6; rep++) { // first reps warm the clocks
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        ops = launch_int32_probe(c->tmp[0].as<uint32_t>(), c->stream, nullptr);
+        c->launches += 1;
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep >= 2) best_ms = std::min(best_ms, (double)ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_TRY(cudaGetLastError());
+    *out_ops_per_s = ops / (best_ms * 1e-3);
+    if (out_ms) *out_ms = best_ms;
+    return SSYM_OK;
+}
+
+} // extern "C"

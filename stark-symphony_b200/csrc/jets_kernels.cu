@@ -1,0 +1,335 @@
+// SPDX-License-Identifier: MIT
+//
+// Element-wise kernels behind the jet-level C-ABI (include/ssym.h): one reference function applied to
+// n independent inputs.  They serve the parity tests (GPU == oracle on every jet) and the config-4
+// microbenchmarks (BASELINE.json: M31/QM31 mul/inv, circle-FRI fold over 2^28 elements, Merkle-path sweep).
+// The field kernels are HBM-bound: 128-bit loads/stores, grid-stride over 148 x 8 CTAs.
+#include "jets_kernels.cuh"
+
+#include "field.cuh"
+#include "sha256.cuh"
+
+namespace ssym {
+
+static inline dim3 stream_grid(size_t n_items, int block) {
+    size_t blocks = (n_items + block - 1) / block;
+    const size_t cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return dim3((unsigned)blocks);
+}
+
+// ---- M31: 4 elements per thread -----------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ uint32_t m31_op(uint32_t a, uint32_t b) {
+    if (OP == JET_M31_ADD) return m31_add(a, b);
+    if (OP == JET_M31_SUB) return m31_sub(a, b);
+    if (OP == JET_M31_MUL) return m31_mul(a, b);
+    return m31_neg(a);
+}
+template <int OP>
+__global__ void __launch_bounds__(256) m31_binary_kernel(const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
+    const size_t nv = n / 4, stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(a), *b4 = reinterpret_cast<const uint4 *>(b);
+    uint4 *o4 = reinterpret_cast<uint4 *>(out);
+    for (size_t i = tid; i < nv; i += stride) {
+        const uint4 x = __ldg(a4 + i);
+        const uint4 y = OP == JET_M31_NEG ? x : __ldg(b4 + i);
+        o4[i] = make_uint4(m31_op<OP>(x.x, y.x), m31_op<OP>(x.y, y.y), m31_op<OP>(x.z, y.z), m31_op<OP>(x.w, y.w));
+    }
+    for (size_t i = nv * 4 + tid; i < n; i += stride) out[i] = m31_op<OP>(a[i], OP == JET_M31_NEG ? 0u : b[i]);
+}
+__global__ void __launch_bounds__(256) m31_inv_kernel(const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool f = false;
+        out[i] = m31_inv(a[i], f);
+        if (fail) fail[i] = f;
+    }
+}
+
+// ---- CM31 / QM31: one element per thread -----------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256) ext_kernel(const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *fail, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool f = false;
+        if (OP == JET_CM31_MUL || OP == JET_CM31_INV) {
+            const uint2 x = __ldg(reinterpret_cast<const uint2 *>(a) + i);
+            CM31 r;
+            if (OP == JET_CM31_MUL) {
+                const uint2 y = __ldg(reinterpret_cast<const uint2 *>(b) + i);
+                r = cm31_mul(cm31(x.x, x.y), cm31(y.x, y.y));
+            } else {
+                r = cm31_inv(cm31(x.x, x.y), f);
+            }
+            reinterpret_cast<uint2 *>(out)[i] = make_uint2(r.a, r.b);
+        } else {
+            const QM31 x = qm31_load4(a + 4 * i);
+            QM31 r;
+            if (OP == JET_QM31_ADD) r = qm31_add(x, qm31_load4(b + 4 * i));
+            else if (OP == JET_QM31_SUB) r = qm31_sub(x, qm31_load4(b + 4 * i));
+            else if (OP == JET_QM31_MUL) r = qm31_mul(x, qm31_load4(b + 4 * i));
+            else if (OP == JET_QM31_MUL_M31) r = qm31_mul_m31(x, __ldg(b + i));
+            else if (OP == JET_QM31_MUL_CM31) {
+                const uint2 y = __ldg(reinterpret_cast<const uint2 *>(b) + i);
+                r = qm31_mul_cm31(x, cm31(y.x, y.y));
+            } else r = qm31_inv(x, f);
+            qm31_store4(out + 4 * i, r);
+        }
+        if (fail && (OP == JET_CM31_INV || OP == JET_QM31_INV)) fail[i] = f;
+    }
+}
+
+int launch_field_jet(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    const dim3 g4 = stream_grid((n + 3) / 4, 256), g1 = stream_grid(n, 256);
+    switch (op) {
+    case JET_M31_ADD: m31_binary_kernel<JET_M31_ADD><<<g4, 256, 0, s>>>(a, b, out, n); break;
+    case JET_M31_SUB: m31_binary_kernel<JET_M31_SUB><<<g4, 256, 0, s>>>(a, b, out, n); break;
+    case JET_M31_MUL: m31_binary_kernel<JET_M31_MUL><<<g4, 256, 0, s>>>(a, b, out, n); break;
+    case JET_M31_NEG: m31_binary_kernel<JET_M31_NEG><<<g4, 256, 0, s>>>(a, a, out, n); break;
+    case JET_M31_INV: m31_inv_kernel<<<g1, 256, 0, s>>>(a, out, fail, n); break;
+    case JET_CM31_MUL: ext_kernel<JET_CM31_MUL><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_CM31_INV: ext_kernel<JET_CM31_INV><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_QM31_ADD: ext_kernel<JET_QM31_ADD><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_QM31_SUB: ext_kernel<JET_QM31_SUB><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_QM31_MUL: ext_kernel<JET_QM31_MUL><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_QM31_INV: ext_kernel<JET_QM31_INV><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_QM31_MUL_M31: ext_kernel<JET_QM31_MUL_M31><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_QM31_MUL_CM31: ext_kernel<JET_QM31_MUL_CM31><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    default: return -1;
+    }
+    return 0;
+}
+
+// ---- circle_point_index_to_m31_point ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) circle_point_kernel(const uint32_t *index, uint32_t *out_xy, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const M31Point p = circle_point_index_to_m31_point(index[i]);
+        reinterpret_cast<uint2 *>(out_xy)[i] = make_uint2(p.x, p.y);
+    }
+}
+void launch_circle_point(const uint32_t *index, uint32_t *out_xy, size_t n, cudaStream_t s) {
+    if (n) circle_point_kernel<<<stream_grid(n, 256), 256, 0, s>>>(index, out_xy, n);
+}
+
+// ---- circle_fold / line_fold (fri/folding.simf:15-41) ---------------------------------------------------
+// The twiddle (1/y or 1/x of the domain point at the bit-reversed position) is recomputed per element with the
+// literal 32-step double-and-add + addition-chain inverse: 4 B of position in, no table traffic.
+template <bool CIRCLE>
+__global__ void __launch_bounds__(256) fold_kernel(const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p,
+                                                   const uint32_t *alpha, uint32_t log_size, uint32_t *out, uint8_t *fail, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t pos = bit_reverse_position(position[i], log_size);
+        M31 v;
+        if (CIRCLE) v = circle_point_index_to_m31_point(circle_position_to_point_index(log_size, pos)).y;
+        else v = circle_point_index_to_m31_point(line_position_to_point_index(log_size, pos)).x;
+        bool f = false;
+        const M31 inv = m31_inv(v, f);
+        const QM31 a = qm31_load4(f_p + 4 * i), b = qm31_load4(f_neg_p + 4 * i);
+        const QM31 f0 = qm31_add(a, b);
+        const QM31 f1 = qm31_mul_m31(qm31_sub(a, b), inv);
+        qm31_store4(out + 4 * i, qm31_add(f0, qm31_mul(qm31_load4(alpha + 4 * i), f1)));
+        if (fail) fail[i] = f;
+    }
+}
+void launch_fold(bool circle, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p, const uint32_t *alpha,
+                 uint32_t log_size, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s) {
+    if (!n) return;
+    if (circle) fold_kernel<true><<<stream_grid(n, 256), 256, 0, s>>>(position, f_p, f_neg_p, alpha, log_size, out, fail, n);
+    else fold_kernel<false><<<stream_grid(n, 256), 256, 0, s>>>(position, f_p, f_neg_p, alpha, log_size, out, fail, n);
+}
+
+// ---- hashing ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld_digest(const uint32_t *src, uint32_t (&d)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src)), b = __ldg(reinterpret_cast<const uint4 *>(src) + 1);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void st_digest(uint32_t *dst, const uint32_t (&d)[8]) {
+    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+__global__ void __launch_bounds__(128) sha256_pair_kernel(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t l[8], r[8], o[8];
+    ld_digest(left + 8 * i, l);
+    ld_digest(right + 8 * i, r);
+    sha256_pair(l, r, o);
+    st_digest(out + 8 * i, o);
+}
+void launch_sha256_pair(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, cudaStream_t s) {
+    if (n) sha256_pair_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(left, right, out, n);
+}
+
+// merkle_verify_32 (merkle.simf:39-44) for n paths of equal depth: one thread per path, sibling i+1 prefetched
+// while level i is hashed.  32*depth + 68 bytes in, <= 36 bytes + 1 bit out per path, 2*depth compressions.
+__global__ void __launch_bounds__(128) merkle_path_kernel(const uint32_t *leaf, const uint32_t *auth_path, const uint32_t *siblings,
+                                                          uint32_t depth, const uint32_t *expected_root, uint32_t *out_root,
+                                                          uint32_t *out_path, uint32_t *ok_bits, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    const size_t ii = active ? i : 0;
+    uint32_t cur[8], nxt[8];
+    ld_digest(leaf + 8 * ii, cur);
+    uint32_t path = auth_path[ii];
+    const uint32_t *sib = siblings + ii * (size_t)depth * 8;
+    if (depth) ld_digest(sib, nxt);
+#pragma unroll 1
+    for (uint32_t lvl = 0; lvl < depth; lvl++) {
+        uint32_t w[16];
+        const bool cur_left = (path & 1u) == 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            w[k] = cur_left ? cur[k] : nxt[k];
+            w[8 + k] = cur_left ? nxt[k] : cur[k];
+        }
+        if (lvl + 1 < depth) ld_digest(sib + 8 * (lvl + 1), nxt);
+        sha256_64B(w, cur);
+        path >>= 1;
+    }
+    bool ok = path == 1u;
+    if (expected_root) {
+        uint32_t r[8];
+        ld_digest(expected_root + 8 * ii, r);
+#pragma unroll
+        for (int k = 0; k < 8; k++) ok = ok && cur[k] == r[k];
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, active && ok);
+    if (active) {
+        if (out_root) st_digest(out_root + 8 * i, cur);
+        if (out_path) out_path[i] = path;
+        if (ok_bits && (threadIdx.x & 31) == 0) ok_bits[i >> 5] = ballot;
+    }
+}
+void launch_merkle_path(const uint32_t *leaf, const uint32_t *auth_path, const uint32_t *siblings, uint32_t depth,
+                        const uint32_t *expected_root, uint32_t *out_root, uint32_t *out_path, uint32_t *ok_bits, size_t n,
+                        cudaStream_t s) {
+    if (n) merkle_path_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(leaf, auth_path, siblings, depth, expected_root, out_root, out_path, ok_bits, n);
+}
+
+// ---- channel transitions (channel.simf:36-172, fri/queries.simf:14-43); state = digest[8] | n_sent ----------
+__device__ __forceinline__ void chan_draw(uint32_t (&d)[8], uint32_t &n_sent, uint32_t (&out)[8]) {
+    uint32_t m[9];
+#pragma unroll
+    for (int k = 0; k < 8; k++) m[k] = d[k];
+    m[8] = n_sent;
+    sha256_short<9>(m, out);
+    n_sent += 1u;
+}
+__global__ void __launch_bounds__(128) channel_kernel(int op, uint32_t *state, const uint32_t *input, uint32_t *out, uint8_t *fail,
+                                                      uint32_t log_size, uint32_t n_queries, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t d[8], n_sent = state[9 * i + 8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) d[k] = state[9 * i + k];
+    if (op == CHAN_MIX_U256) {
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { w[k] = d[k]; w[8 + k] = input[8 * i + k]; }
+        sha256_64B(w, d);
+        n_sent = 0;
+    } else if (op == CHAN_MIX_U64) {
+        uint32_t m[10];
+#pragma unroll
+        for (int k = 0; k < 8; k++) m[k] = d[k];
+        m[8] = input[2 * i];
+        m[9] = input[2 * i + 1];
+        sha256_short<10>(m, d);
+        n_sent = 0;
+    } else if (op == CHAN_DRAW_QM31) {
+        uint32_t w[8];
+        bool ok = false;
+#pragma unroll 1
+        for (int counter = 0; counter < 256 && !ok; counter++) {
+            chan_draw(d, n_sent, w);
+            ok = w[0] < 4294967294u && w[1] < 4294967294u && w[2] < 4294967294u && w[3] < 4294967294u;
+        }
+        for (int k = 0; k < 4; k++) out[4 * i + k] = m31_reduce(w[k]);
+        if (fail) fail[i] = !ok;
+    } else if (op == CHAN_DRAW_QUERIES) {
+        const uint32_t mask = shl32(log_size & 0xff, 1u) - 1u;
+#pragma unroll 1
+        for (uint32_t q0 = 0; q0 < n_queries; q0 += 8) {
+            uint32_t w[8];
+            chan_draw(d, n_sent, w);
+            for (uint32_t j = 0; j < 8 && q0 + j < n_queries; j++) out[i * n_queries + q0 + j] = w[j] & mask;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) state[9 * i + k] = d[k];
+    state[9 * i + 8] = n_sent;
+}
+void launch_channel(int op, uint32_t *state, const uint32_t *input, uint32_t *out, uint8_t *fail, uint32_t log_size,
+                    uint32_t n_queries, size_t n, cudaStream_t s) {
+    if (n) channel_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(op, state, input, out, fail, log_size, n_queries, n);
+}
+
+// ---- stark101 field jets (stark101/src/field.simf) ----------------------------------------------------------
+#define S101_P 3221225473u
+__global__ void __launch_bounds__(256) s101_field_kernel(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *fail, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (op == 0) {
+            out[i] = (uint32_t)(((uint64_t)a[i] * b[i]) % S101_P);
+        } else { // div_mod field.simf:42-66
+            uint32_t t = 0, r = S101_P, new_t = 1, new_r = b[i];
+            bool done = false, f = false;
+            for (uint32_t counter = 0; counter < 65536u; counter++) {
+                if (new_r == 0) { f = r != 1; done = true; break; }
+                const uint32_t q = r / new_r;
+                const uint32_t qt = (uint32_t)(((uint64_t)q * new_t) % S101_P), qr = (uint32_t)(((uint64_t)q * new_r) % S101_P);
+                const uint32_t nt = (uint32_t)(((uint64_t)t + (uint32_t)(S101_P - qt)) % S101_P);
+                const uint32_t nr = (uint32_t)(((uint64_t)r + (uint32_t)(S101_P - qr)) % S101_P);
+                t = new_t; new_t = nt; r = new_r; new_r = nr;
+            }
+            if (!done) f = true;
+            out[i] = (uint32_t)(((uint64_t)a[i] * t) % S101_P);
+            if (fail) fail[i] = f;
+        }
+    }
+}
+void launch_s101_field(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s) {
+    if (n) s101_field_kernel<<<stream_grid(n, 256), 256, 0, s>>>(op, a, b, out, fail, n);
+}
+
+// ---- INT32 roofline probe ------------------------------------------------------------------------------------
+// Register-only stream of the three instruction kinds SHA-256 is made of (SHF.R.W funnel-shift rotates, LOP3
+// three-input logic, IADD3 three-input adds), 8 independent chains per thread so the ALU pipe, not latency,
+// is the limit.  Each inner step is written as exactly 3 rotates + 1 xor3 + 1 add3 = 5 machine instructions
+// per chain (checked in the SASS: profiles/*_sass_probe.txt); ops/s = threads * steps * chains * 5 / time.
+#define PROBE_CHAINS 8
+#define PROBE_STEPS 4096
+__global__ void __launch_bounds__(256) int32_probe_kernel(uint32_t *sink, uint32_t seed) {
+    uint32_t x[PROBE_CHAINS], y[PROBE_CHAINS];
+#pragma unroll
+    for (int c = 0; c < PROBE_CHAINS; c++) {
+        x[c] = seed + threadIdx.x * 2654435761u + c;
+        y[c] = seed ^ (blockIdx.x + 0x9e3779b9u * c);
+    }
+#pragma unroll 4
+    for (int it = 0; it < PROBE_STEPS; it++) {
+#pragma unroll
+        for (int c = 0; c < PROBE_CHAINS; c++) {
+            const uint32_t r = rotr32(x[c], 6) ^ rotr32(x[c], 11) ^ rotr32(x[c], 25); // 3 SHF + 1 LOP3
+            x[c] = y[c];
+            y[c] = y[c] + r + 0x428a2f98u; // 1 IADD3
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < PROBE_CHAINS; c++) acc ^= x[c] + y[c];
+    if (acc == 0x12345678u) sink[0] = acc; // keep the work alive
+}
+double launch_int32_probe(uint32_t *sink, cudaStream_t s, int *blocks_out) {
+    const int blocks = 148 * 8; // 8 CTAs of 256 threads per SM = full occupancy
+    int32_probe_kernel<<<blocks, 256, 0, s>>>(sink, 1u);
+    if (blocks_out) *blocks_out = blocks;
+    return (double)blocks * 256.0 * PROBE_STEPS * PROBE_CHAINS * 5.0; // machine-instruction lanes executed
+}
+
+} // namespace ssym

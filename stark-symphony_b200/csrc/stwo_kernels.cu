@@ -1,0 +1,598 @@
+// SPDX-License-Identifier: MIT
+// Kernels of the batched Stwo verifier; see stwo_kernels.cuh for the decomposition.
+#include "stwo_kernels.cuh"
+
+namespace ssym {
+
+typedef StwoCtxLayout CX;
+
+// ------------------------------------------------------------------------------------------
+// Transcript helpers (K1).  The compression function is deliberately NOT inlined here: a
+// transcript is ~46 dependent compressions per proof, so one hot copy in the I-cache beats
+// 46 cold ones.
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void sha_compress_call(uint32_t *h, const uint32_t *blk) {
+    uint32_t hh[8], w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) hh[i] = h[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = blk[i];
+    sha_compress(hh, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = hh[i];
+}
+
+// SHA-256 of (a[0..na) || b[0..nb)) big-endian words.
+__device__ __noinline__ void sha256_2part(const uint32_t *a, int na, const uint32_t *b, int nb, uint32_t *out) {
+    uint32_t h[8];
+    sha_iv(h);
+    const int nwords = na + nb;
+    const int nblocks = (nwords + 3 + 15) >> 4;
+    for (int blk = 0; blk < nblocks; blk++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int i = blk * 16 + j;
+            uint32_t v = 0;
+            if (i < na) v = a[i];
+            else if (i < nwords) v = b[i - na];
+            else if (i == nwords) v = 0x80000000u;
+            else if (i == nblocks * 16 - 1) v = (uint32_t)nwords * 32u;
+            w[j] = v;
+        }
+        sha_compress_call(h, w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = h[i];
+}
+
+struct Channel { // channel.simf:18-22 ChannelState = (u256 digest, u32 n_sent)
+    uint32_t d[8];
+    uint32_t n_sent;
+};
+__device__ __forceinline__ void channel_draw_u256(Channel &c, uint32_t *out) { // channel.simf:36-44
+    uint32_t ns = c.n_sent;
+    sha256_2part(c.d, 8, &ns, 1, out);
+    c.n_sent = c.n_sent + 1u;
+}
+__device__ __forceinline__ void channel_mix(Channel &c, const uint32_t *in, int nwords) { // channel.simf:154-173, fri/commit.simf:48-57, deep/oods.simf:23-39
+    uint32_t out[8];
+    sha256_2part(c.d, 8, in, nwords, out);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c.d[i] = out[i];
+    c.n_sent = 0;
+}
+// channel_draw_qm31 = channel_draw_m31x4 (channel.simf:115-141): retry (<= 256 draws) until the first four words are < 2p
+__device__ __noinline__ QM31 channel_draw_qm31(Channel &c, bool &exhausted) {
+    uint32_t w[8];
+    bool ok = false;
+    for (int counter = 0; counter < 256 && !ok; counter++) {
+        channel_draw_u256(c, w);
+        ok = w[0] < 4294967294u && w[1] < 4294967294u && w[2] < 4294967294u && w[3] < 4294967294u;
+    }
+    exhausted = exhausted || !ok;
+    return qm31(m31_reduce(w[0]), m31_reduce(w[1]), m31_reduce(w[2]), m31_reduce(w[3]));
+}
+
+// Out-of-line field helpers for the once-per-proof code (keeps K1 compact).
+__device__ __noinline__ QM31 qm31_mul_nl(QM31 x, QM31 y) { return qm31_mul(x, y); }
+__device__ __noinline__ QM31 qm31_inv_nl(QM31 x, bool &fail) { return qm31_inv(x, fail); }
+
+// composition_poly_eval_from_partitions                       evals/composition_poly.simf:38-44
+__device__ QM31 cp_from_partitions(QM31 c0, QM31 c1, QM31 c2, QM31 c3) {
+    QM31 res = qm31_add(c0, qm31_mul_nl(c1, qm31(0, 1, 0, 0)));
+    res = qm31_add(res, qm31_mul_nl(c2, qm31(0, 0, 1, 0)));
+    res = qm31_add(res, qm31_mul_nl(c3, qm31(0, 0, 0, 1)));
+    return res;
+}
+
+struct LineCoeffs {
+    QM31 a, b, c;
+};
+// deep_quotient_interpolant_coefficients                      deep/quotients.simf:25-35
+__device__ __noinline__ LineCoeffs interpolant_coefficients(QM31 py, QM31 sv, QM31 alpha_i) {
+    QM31 a = qm31c(cm31(0, 0), cm31_neg(cm31_dbl(sv.i)));
+    QM31 b = qm31c(cm31(0, 0), cm31_neg(cm31_dbl(py.i)));
+    QM31 a_py = qm31_mul(a, py);
+    QM31 b_val = qm31_mul(b, sv);
+    QM31 c = qm31_sub(b_val, a_py);
+    LineCoeffs r;
+    r.a = qm31_mul(alpha_i, a);
+    r.b = qm31_mul(alpha_i, b);
+    r.c = qm31_mul(alpha_i, c);
+    return r;
+}
+
+__device__ __forceinline__ void store_point(uint32_t *w, QM31 x, QM31 y) {
+    qm31_store(w, x);
+    qm31_store(w + 4, y);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: transcript.  verifier.simf:36-51 up to and including fri_generate_queries.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) stwo_transcript_kernel(StwoParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const ssym_stwo_layout_t &lo = p.lo;
+    const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
+    uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
+    ssym_stwo_trace_t *tr = p.trace ? p.trace + i : nullptr;
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
+    const bool literal = p.cfg.mode == SSYM_MODE_REF_LITERAL;
+    uint32_t status = 0;
+    bool exhausted = false, inv_zero = false;
+
+    Channel ch; // channel_init channel.simf:31-33
+#pragma unroll
+    for (int k = 0; k < 8; k++) ch.d[k] = 0;
+    ch.n_sent = 0;
+
+    // evals_commit                                            evals/commit.simf:20-35
+    channel_mix(ch, pk + lo.off_commit, 8);
+    channel_mix(ch, pk + lo.off_commit + 8, 8);
+    const QM31 cp_alpha = channel_draw_qm31(ch, exhausted);
+    channel_mix(ch, pk + lo.off_commit + 16, 8);
+    if (tr) {
+        for (int k = 0; k < 8; k++) tr->digest_commit[k] = ch.d[k];
+        qm31_store(tr->cp_alpha, cp_alpha);
+    }
+
+    // oods                                                    deep/oods.simf:44-64
+    QM31 px, py;
+    { // channel_draw_qm31_point channel.simf:143-151
+        QM31 t = channel_draw_qm31(ch, exhausted);
+        QM31 t_sq = qm31_mul_nl(t, t);
+        QM31 inv = qm31_inv_nl(qm31_add(qm31_one(), t_sq), inv_zero);
+        px = qm31_mul_nl(qm31_sub(qm31_one(), t_sq), inv);
+        py = qm31_mul_nl(qm31_add(t, t), inv);
+    }
+    channel_mix(ch, pk + lo.off_oods_trace, 80); // 4 trace + 16 CP samples are contiguous in the packed header
+    QM31 cp_eval;
+    { // eval_composition_poly wide_fibonacci.simf:24-62
+        QM31 acc = qm31_zero(), a = qm31_zero(), b = qm31_zero();
+        uint32_t skip_2 = 0;
+#pragma unroll 1
+        for (int col = 0; col < SSYM_NUM_COLUMNS; col++) {
+            QM31 c = qm31_load4(pk + lo.off_oods_trace + 4 * col);
+            if (skip_2 == 2) {
+                QM31 constraint = qm31_sub(c, qm31_add(qm31_mul_nl(b, b), qm31_mul_nl(a, a)));
+                acc = qm31_add(qm31_mul_nl(acc, cp_alpha), constraint);
+            } else {
+                skip_2++;
+            }
+            a = b;
+            b = c;
+        }
+        // vanishing_poly_eval composition_poly.simf:66-71: pi^(log_size-1)(x)
+        const uint32_t n_iter = (p.cfg.trace_log - 1u) & 0xff;
+        QM31 v = px;
+#pragma unroll 1
+        for (uint32_t counter = 0; counter < 256 && counter != n_iter; counter++) {
+            QM31 s = qm31_mul_nl(v, v);
+            v = qm31_sub(qm31_add(s, s), qm31_one());
+        }
+        cp_eval = qm31_mul_nl(acc, qm31_inv_nl(v, inv_zero));
+    }
+    QM31 sampled;
+    { // composition_poly_eval_from_decomposed composition_poly.simf:47-59 (index = 4*coord + poly)
+        const uint32_t *e = pk + lo.off_oods_cp;
+        QM31 part[4];
+#pragma unroll 1
+        for (int poly = 0; poly < 4; poly++)
+            part[poly] = cp_from_partitions(qm31_load4(e + 4 * poly), qm31_load4(e + 4 * (4 + poly)), qm31_load4(e + 4 * (8 + poly)),
+                                            qm31_load4(e + 4 * (12 + poly)));
+        QM31 res = qm31_add(part[0], qm31_mul_nl(part[1], py));
+        res = qm31_add(res, qm31_mul_nl(part[2], px));
+        sampled = qm31_add(res, qm31_mul_nl(part[3], qm31_mul_nl(px, py)));
+    }
+    if (!qm31_eq(cp_eval, sampled)) status |= SSYM_ST_OODS_CP_MISMATCH; // deep/oods.simf:58
+    const QM31 deep_alpha = channel_draw_qm31(ch, exhausted);
+    if (tr) {
+        qm31_store(tr->oods_x, px);
+        qm31_store(tr->oods_y, py);
+        qm31_store(tr->cp_eval, cp_eval);
+        qm31_store(tr->cp_sampled, sampled);
+        for (int k = 0; k < 8; k++) tr->digest_oods[k] = ch.d[k];
+        qm31_store(tr->deep_alpha, deep_alpha);
+    }
+
+    // fri_commit                                              fri/commit.simf:72-85
+#pragma unroll 1
+    for (uint32_t l = 0; l <= L; l++) {
+        channel_mix(ch, l == 0 ? pk + lo.off_fri_first_root : pk + lo.off_fri_inner_root + 8 * (l - 1), 8);
+        QM31 alpha = channel_draw_qm31(ch, exhausted);
+        qm31_store(ctx + CX::FRI_ALPHA + 4 * l, alpha);
+        if (tr) qm31_store(tr->fri_alpha[l], alpha);
+    }
+    channel_mix(ch, pk + lo.off_last_coeff, 4); // channel_mix_line_poly
+#pragma unroll
+    for (int k = 0; k < 4; k++) ctx[CX::LAST_COEFF + k] = pk[lo.off_last_coeff + k];
+    if (tr)
+        for (int k = 0; k < 8; k++) tr->digest_fri[k] = ch.d[k];
+
+    // check_proof_of_work                                     pow.simf:22-35
+    channel_mix(ch, pk + lo.off_pow_nonce, 2); // channel_mix_u64: {hi, lo} big-endian
+    {
+        const uint64_t value = ((uint64_t)__byte_perm(ch.d[7], 0, 0x0123) << 32) | __byte_perm(ch.d[6], 0, 0x0123);
+        if (!(value < p.cfg.pow_target)) status |= SSYM_ST_POW_FAIL;
+        if (tr) {
+            for (int k = 0; k < 8; k++) tr->digest_pow[k] = ch.d[k];
+            tr->pow_value[0] = (uint32_t)(value >> 32);
+            tr->pow_value[1] = (uint32_t)value;
+        }
+    }
+
+    // fri_generate_queries                                    fri/queries.simf:30-43
+    {
+        const uint32_t mask = shl32(G & 0xff, 1u) - 1u;
+#pragma unroll 1
+        for (uint32_t q0 = 0; q0 < Q; q0 += 8) {
+            uint32_t w[8];
+            channel_draw_u256(ch, w);
+            for (uint32_t j = 0; j < 8 && q0 + j < Q; j++) {
+                ctx[CX::QUERIES + q0 + j] = w[j] & mask;
+                if (tr) tr->queries[q0 + j] = w[j] & mask;
+            }
+        }
+    }
+
+    // Per-proof part of fri_answer (fri/answers.simf:97-129): the line coefficients depend only on
+    // the OODS point / samples / alpha, not on the query, so they are computed once here.
+    {
+        QM31 alpha_i = deep_alpha;
+        QM31 sum_a = qm31_zero(), sum_c = qm31_zero();
+        if (literal) {
+            store_point(ctx + CX::POINT_A, px, py);
+#pragma unroll 1
+            for (int k = 0; k < 20; k++) { // 4 trace columns, then 16 CP partitions: contiguous samples
+                LineCoeffs lc = interpolant_coefficients(py, qm31_load4(pk + lo.off_oods_trace + 4 * k), alpha_i);
+                qm31_store4(ctx + CX::B_COEFF + 4 * k, lc.b);
+                sum_a = qm31_add(sum_a, lc.a);
+                sum_c = qm31_add(sum_c, lc.c);
+                alpha_i = qm31_mul_nl(alpha_i, deep_alpha);
+            }
+            qm31_store4(ctx + CX::SUM_A_A, sum_a);
+            qm31_store4(ctx + CX::SUM_C_A, sum_c);
+            qm31_store4(ctx + CX::BATCH_COEFF, alpha_i); // alpha^21
+        } else {
+            // batch A = the 16 CP partitions sampled at 2*P, batch B = the 4 trace columns at P
+            QM31 p2x = qm31_point_dbl_x(px);
+            QM31 xy = qm31_mul_nl(px, py);
+            QM31 p2y = qm31_add(xy, xy);
+            store_point(ctx + CX::POINT_A, p2x, p2y);
+            store_point(ctx + CX::POINT_B, px, py);
+#pragma unroll 1
+            for (int k = 0; k < 16; k++) {
+                LineCoeffs lc = interpolant_coefficients(p2y, qm31_load4(pk + lo.off_oods_cp + 4 * k), alpha_i);
+                qm31_store4(ctx + CX::B_COEFF + 4 * k, lc.b);
+                sum_a = qm31_add(sum_a, lc.a);
+                sum_c = qm31_add(sum_c, lc.c);
+                alpha_i = qm31_mul_nl(alpha_i, deep_alpha);
+            }
+            qm31_store4(ctx + CX::SUM_A_A, sum_a);
+            qm31_store4(ctx + CX::SUM_C_A, sum_c);
+            sum_a = qm31_zero();
+            sum_c = qm31_zero();
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                LineCoeffs lc = interpolant_coefficients(py, qm31_load4(pk + lo.off_oods_trace + 4 * k), alpha_i);
+                qm31_store4(ctx + CX::B_COEFF + 4 * (16 + k), lc.b);
+                sum_a = qm31_add(sum_a, lc.a);
+                sum_c = qm31_add(sum_c, lc.c);
+                alpha_i = qm31_mul_nl(alpha_i, deep_alpha);
+            }
+            qm31_store4(ctx + CX::SUM_A_B, sum_a);
+            qm31_store4(ctx + CX::SUM_C_B, sum_c);
+        }
+    }
+
+    if (exhausted) status |= SSYM_ST_DRAW_EXHAUSTED;
+    if (inv_zero) status |= SSYM_ST_OODS_INV_ZERO;
+    if (literal && ((G - (L + 1u)) & 0xff) != 0) status |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
+    p.status[i] = status;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: per (proof, query): fri_answer (fri/answers.simf:97-129) + the folds of fri_verify
+// (fri/layers.simf:51-78, fri/folding.simf:15-41).  The Merkle halves of those functions are K3.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ CM31 denominator_inverse(const uint32_t *pt, M31Point r, bool &fail) { // deep/quotients.simf:15-22
+    CM31 prx = cm31(pt[0], pt[1]), pix = cm31(pt[2], pt[3]), pry = cm31(pt[4], pt[5]), piy = cm31(pt[6], pt[7]);
+    CM31 dx = cm31_sub_m31(prx, r.x);
+    CM31 dy = cm31_sub_m31(pry, r.y);
+    CM31 d = cm31_sub(cm31_mul(dx, piy), cm31_mul(dy, pix));
+    return cm31_inv(d, fail);
+}
+
+// sum_k b_k * v_k - (R.y * sum_a + sum_c): the batch's quotient numerator accumulator
+// (= the fold of quotient_numerator_aggregate, fri/answers.simf:40-58, regrouped; all operands are exact
+// field values and only the b_k * v_k products see raw witness words, exactly as in deep_quotient_nominator)
+__device__ __forceinline__ QM31 batch_numerator(const uint32_t *bcoef, const uint32_t *vals, int n, const uint32_t *sum_a,
+                                                const uint32_t *sum_c, M31 ry) {
+    QM31 s = qm31_zero();
+#pragma unroll 4
+    for (int k = 0; k < n; k++) s = qm31_add(s, qm31_mul_m31(qm31_load4(bcoef + 4 * k), vals[k]));
+    QM31 a_py = qm31_mul_m31(qm31_load4(sum_a), ry);
+    return qm31_sub(s, qm31_add(a_py, qm31_load4(sum_c)));
+}
+
+__global__ void __launch_bounds__(128) stwo_query_kernel(StwoParams p) {
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= p.n * Q) return;
+    const uint32_t i = item / Q, q = item % Q;
+    const ssym_stwo_layout_t &lo = p.lo;
+    const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
+    const uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
+    ssym_stwo_trace_t *tr = p.trace ? p.trace + i : nullptr;
+    const bool literal = p.cfg.mode == SSYM_MODE_REF_LITERAL;
+    uint32_t status = 0;
+
+    const uint32_t query = ctx[CX::QUERIES + q];
+    const uint2 rp = p.tab.point[query]; // domain point of the query, fri/answers.simf:108-110
+    const M31Point R = m31_point(rp.x, rp.y);
+    uint32_t vals[20];
+    {
+        const uint4 *v4 = reinterpret_cast<const uint4 *>(pk + lo.off_qvals + 20 * q); // 80-byte records: 16-byte aligned
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            uint4 v = v4[k];
+            vals[4 * k] = v.x; vals[4 * k + 1] = v.y; vals[4 * k + 2] = v.z; vals[4 * k + 3] = v.w;
+        }
+    }
+    QM31 eval;
+    bool inv_fail = false;
+    if (literal) {
+        CM31 den_inv = denominator_inverse(ctx + CX::POINT_A, R, inv_fail);
+        QM31 acc = batch_numerator(ctx + CX::B_COEFF, vals, 20, ctx + CX::SUM_A_A, ctx + CX::SUM_C_A, R.y);
+        eval = qm31_mul(qm31_mul_cm31(acc, den_inv), qm31_load4(ctx + CX::BATCH_COEFF)); // fri/answers.simf:126
+    } else {
+        CM31 den_a = denominator_inverse(ctx + CX::POINT_A, R, inv_fail);
+        CM31 den_b = denominator_inverse(ctx + CX::POINT_B, R, inv_fail);
+        QM31 num_a = batch_numerator(ctx + CX::B_COEFF, vals + 4, 16, ctx + CX::SUM_A_A, ctx + CX::SUM_C_A, R.y);
+        QM31 num_b = batch_numerator(ctx + CX::B_COEFF + 64, vals, 4, ctx + CX::SUM_A_B, ctx + CX::SUM_C_B, R.y);
+        eval = qm31_add(qm31_mul_cm31(num_a, den_a), qm31_mul_cm31(num_b, den_b));
+    }
+    if (inv_fail) {
+        status |= SSYM_ST_ANSWER_INV_ZERO;
+        if (tr) atomicOr(&tr->mask_answer_inv, 1u << q);
+    }
+    if (tr) qm31_store(tr->fri_answer[q], eval);
+
+    uint32_t *ev_out = p.fri_evals + (size_t)i * (L + 1) * Q * 4;
+    uint32_t fq = query;
+#pragma unroll 1
+    for (uint32_t l = 0; l <= L; l++) { // fri_verify_query fri/layers.simf:51-69 (without verify_decommitment)
+        qm31_store4(ev_out + (l * Q + q) * 4, eval);
+        const QM31 witness = qm31_load4(pk + lo.off_fri_wit + (l * Q + q) * 4);
+        const bool even = (fq & 1u) == 0; // adjacent_leaves fri/layers.simf:29-37
+        const QM31 e0 = even ? eval : witness, e1 = even ? witness : eval;
+        const M31 inv = p.tab.fold_inv[p.tab.fold_off[l] + (fq >> 1)];
+        if (inv == 0) { // m31_inv(0): fri/folding.simf:20,34 assert
+            status |= SSYM_ST_FOLD_INV_ZERO;
+            if (tr) atomicOr(&tr->mask_fold_inv[l], 1u << q);
+        }
+        const QM31 f0 = qm31_add(e0, e1);
+        const QM31 f1 = qm31_mul_m31(qm31_sub(e0, e1), inv);
+        eval = qm31_add(f0, qm31_mul(qm31_load4(ctx + CX::FRI_ALPHA + 4 * l), f1));
+        if (tr) qm31_store(tr->folded[l][q], eval);
+        fq >>= 1; // divide_32(position, 2)
+    }
+    // fri_verify_last_layer fri/layers.simf:73-78
+    if (literal && fq != 0) {
+        status |= SSYM_ST_LAST_QUERY;
+        if (tr) atomicOr(&tr->mask_last_query, 1u << q);
+    }
+    if (!qm31_eq(eval, qm31_load4(ctx + CX::LAST_COEFF))) {
+        status |= SSYM_ST_LAST_EVAL;
+        if (tr) atomicOr(&tr->mask_last_eval, 1u << q);
+    }
+    if (status) atomicOr(&p.status[i], status);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: every Merkle decommitment of the proof as an independent hash chain
+// (merkle.simf:22-44 under evals/verify.simf:50-68 and fri/layers.simf:40-48).
+// A warp's 32 lanes are 32 consecutive (proof, query) pairs of ONE chain type, so the lanes of a
+// warp run chains of identical length: no divergence.  Chain types are scheduled longest first.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t (&d)[8]) { // 32-byte aligned
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src));
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(src) + 1);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+    d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+
+__global__ void __launch_bounds__(128) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type) {
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    // warp -> (chain type rank, group); rank 0 = CP (1 + 2 + 2G compressions... longest), 1 = FRI layer 0,
+    // 2 = trace, 3.. = FRI layers 1..L
+    const uint32_t rank = warp / groups_per_type, group = warp % groups_per_type;
+    if (rank >= L + 3) return;
+    const uint32_t item = group * 32 + lane;
+    const bool active = item < p.n * Q;
+    const uint32_t i = active ? item / Q : 0, q = active ? item % Q : 0;
+    const ssym_stwo_layout_t &lo = p.lo;
+    const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
+    const uint32_t query = p.ctx[(size_t)i * CX::WORDS + CX::QUERIES + q];
+
+    uint32_t cur[8];
+    const uint32_t *sib, *root;
+    uint32_t n_sib, path, fail_bit, layer = 0;
+    int kind; // 0 trace, 1 cp, 2 fri
+    if (rank == 0 || rank == 2) {
+        const uint32_t *qv = pk + lo.off_qvals + 20 * q;
+        if (rank == 2) { // hash_node_m31_trace hasher.simf:85-90: 16-byte leaf
+            kind = 0;
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(qv));
+            const uint32_t m[4] = {v.x, v.y, v.z, v.w};
+            sha256_short<4>(m, cur);
+            sib = pk + lo.off_trace_sib + q * G * 8;
+            root = pk + lo.off_commit + 8;
+            fail_bit = SSYM_ST_TRACE_MERKLE;
+        } else { // hash_node_m31_cp hasher.simf:93-97: 64-byte leaf
+            kind = 1;
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(qv + 4) + k);
+                w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
+            sha256_64B(w, cur);
+            sib = pk + lo.off_cp_sib + q * G * 8;
+            root = pk + lo.off_commit + 16;
+            fail_bit = SSYM_ST_CP_MERKLE;
+        }
+        n_sib = G;
+        path = query + shl32(G & 0xff, 1u); // evals/verify.simf:54,64
+    } else { // verify_decommitment fri/layers.simf:40-48
+        kind = 2;
+        layer = rank == 1 ? 0 : rank - 2;
+        const uint32_t fq = query >> layer;
+        const uint32_t *evp = p.fri_evals + ((size_t)i * (L + 1) * Q + layer * Q + q) * 4;
+        const uint4 ev = *reinterpret_cast<const uint4 *>(evp);
+        const uint4 wt = __ldg(reinterpret_cast<const uint4 *>(pk + lo.off_fri_wit + (layer * Q + q) * 4));
+        const bool even = (fq & 1u) == 0;
+        const uint32_t m0[4] = {even ? ev.x : wt.x, even ? ev.y : wt.y, even ? ev.z : wt.z, even ? ev.w : wt.w};
+        const uint32_t m1[4] = {even ? wt.x : ev.x, even ? wt.y : ev.y, even ? wt.z : ev.z, even ? wt.w : ev.w};
+        uint32_t l0[8], l1[8];
+        sha256_short<4>(m0, l0); // hash_node_qm31 hasher.simf:100-104
+        sha256_short<4>(m1, l1);
+        sha256_pair(l0, l1, cur);
+        n_sib = G - 1 - layer;
+        sib = pk + lo.off_fri_sib[layer] + q * n_sib * 8;
+        root = layer == 0 ? pk + lo.off_fri_first_root : pk + lo.off_fri_inner_root + 8 * (layer - 1);
+        fail_bit = SSYM_ST_FRI_MERKLE(layer);
+        const uint32_t position = fq & ~1u;
+        path = (position + shl32((G - layer) & 0xff, 1u)) >> 1;
+    }
+
+    // merkle_verify_32 merkle.simf:39-44: fold the siblings, prefetching one level ahead
+    uint32_t nxt[8];
+    if (n_sib) load_digest(sib, nxt);
+#pragma unroll 1
+    for (uint32_t lvl = 0; lvl < n_sib; lvl++) {
+        uint32_t w[16];
+        const bool cur_left = (path & 1u) == 0; // divides_32(2, path): sha256_pair(cur, sib) else (sib, cur)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            w[k] = cur_left ? cur[k] : nxt[k];
+            w[8 + k] = cur_left ? nxt[k] : cur[k];
+        }
+        if (lvl + 1 < n_sib) load_digest(sib + 8 * (lvl + 1), nxt);
+        sha256_64B(w, cur);
+        path >>= 1;
+    }
+    uint32_t r[8];
+    load_digest(root, r);
+    bool ok = path == 1u; // merkle.simf:42
+#pragma unroll
+    for (int k = 0; k < 8; k++) ok = ok && (cur[k] == r[k]); // merkle.simf:43
+    if (active && !ok) atomicOr(&p.status[i], fail_bit);
+    if (active && p.trace) {
+        ssym_stwo_trace_t *tr = p.trace + i;
+        uint32_t *dst = kind == 0 ? tr->trace_root[q] : kind == 1 ? tr->cp_root[q] : tr->fri_root[layer][q];
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[k] = cur[k];
+        if (!ok) atomicOr(kind == 0 ? &tr->mask_trace : kind == 1 ? &tr->mask_cp : &tr->mask_fri[layer], 1u << q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: status -> accept bitmap (+ first failing assert in reference program order for the trace)
+// ------------------------------------------------------------------------------------------
+__device__ uint32_t first_fail_code(const ssym_stwo_config_t &cfg, const ssym_stwo_trace_t *t, uint32_t s) {
+    if (!s) return 0;
+    if (s & SSYM_ST_SHAPE) return 31u << 16;
+    for (uint32_t b = 0; b <= 3; b++)
+        if (s & (1u << b)) return b << 16;
+    for (uint32_t q = 0; q < cfg.n_queries; q++) { // evals/verify.simf:71-78
+        if (t->mask_trace & (1u << q)) return (4u << 16) | q;
+        if (t->mask_cp & (1u << q)) return (5u << 16) | q;
+    }
+    for (uint32_t q = 0; q < cfg.n_queries; q++)
+        if (t->mask_answer_inv & (1u << q)) return (6u << 16) | q;
+    for (uint32_t l = 0; l <= cfg.n_fri_layers; l++)
+        for (uint32_t q = 0; q < cfg.n_queries; q++) {
+            if (t->mask_fri[l] & (1u << q)) return ((7u + l) << 16) | (l << 8) | q;
+            if (t->mask_fold_inv[l] & (1u << q)) return (16u << 16) | (l << 8) | q;
+        }
+    if (s & SSYM_ST_FINAL_LOG) return 17u << 16;
+    for (uint32_t q = 0; q < cfg.n_queries; q++) {
+        if (t->mask_last_query & (1u << q)) return (18u << 16) | q;
+        if (t->mask_last_eval & (1u << q)) return (19u << 16) | q;
+    }
+    return 30u << 16;
+}
+
+__global__ void __launch_bounds__(256) stwo_finalize_kernel(StwoParams p, uint32_t *accept_bits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = i < p.n ? p.status[i] : 1u;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, s == 0);
+    if ((threadIdx.x & 31) == 0 && i < p.n) accept_bits[i >> 5] = ballot;
+    if (i < p.n && p.trace) {
+        p.trace[i].status = s;
+        p.trace[i].first_fail = first_fail_code(p.cfg, p.trace + i, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Domain tables
+// ------------------------------------------------------------------------------------------
+__global__ void stwo_tables_kernel(uint32_t G, uint32_t L, uint2 *point, uint32_t *fold_inv, StwoTables offs, uint32_t *zero_flag) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_point = 1u << G;
+    if (t < n_point) {
+        const M31Point pt = circle_point_index_to_m31_point(circle_position_to_point_index(G, bit_reverse_position(t, G)));
+        point[t] = make_uint2(pt.x, pt.y);
+        return;
+    }
+    uint32_t j = t - n_point;
+    for (uint32_t l = 0; l <= L; l++) {
+        const uint32_t cnt = 1u << (G - l - 1);
+        if (j < cnt) {
+            const uint32_t log = G - l, position = 2 * j;
+            M31 v;
+            if (l == 0) v = circle_point_index_to_m31_point(circle_position_to_point_index(log, bit_reverse_position(position, log))).y;
+            else v = circle_point_index_to_m31_point(line_position_to_point_index(log, bit_reverse_position(position, log))).x;
+            bool fail = false;
+            fold_inv[offs.fold_off[l] + j] = m31_inv(v, fail);
+            if (fail) atomicOr(zero_flag, 1u);
+            return;
+        }
+        j -= cnt;
+    }
+}
+
+void launch_stwo_tables(uint32_t G, uint32_t L, uint2 *point, uint32_t *fold_inv, const uint32_t *fold_off, uint32_t *zero_flag,
+                        cudaStream_t s) {
+    StwoTables offs{};
+    uint32_t total = 1u << G;
+    for (uint32_t l = 0; l <= L; l++) {
+        offs.fold_off[l] = fold_off[l];
+        total += 1u << (G - l - 1);
+    }
+    stwo_tables_kernel<<<(total + 127) / 128, 128, 0, s>>>(G, L, point, fold_inv, offs, zero_flag);
+}
+
+void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof) {
+    if (p.n == 0) return;
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
+    if (prof) prof->begin(0, s);
+    stwo_transcript_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p);
+    if (prof) { prof->end(0, s); prof->begin(1, s); }
+    const uint32_t items = p.n * Q;
+    stwo_query_kernel<<<(items + 127) / 128, 128, 0, s>>>(p);
+    if (prof) { prof->end(1, s); prof->begin(2, s); }
+    const uint32_t groups = (items + 31) / 32;
+    const uint64_t warps = (uint64_t)groups * (L + 3);
+    stwo_merkle_kernel<<<(uint32_t)((warps + 3) / 4), 128, 0, s>>>(p, groups);
+    if (prof) { prof->end(2, s); prof->begin(3, s); }
+    stwo_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
+    if (prof) prof->end(3, s);
+    if (launch_counter) *launch_counter += 4;
+}
+
+} // namespace ssym
