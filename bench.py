@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="proofs per GPU per step (BASELINE config: 1024)")
     ap.add_argument("--mode", default="ref-literal", choices=["ref-literal", "prover-consistent"])
     ap.add_argument("--copies", type=int, default=4, help="distinct device copies of the batch rotated through (defeats L2 reuse)")
+    ap.add_argument("--pipeline", type=int, default=2, help="batches in flight per GPU (ssym_set_pipeline_depth); 1 = strictly serial steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -252,25 +253,37 @@ def main():
     n = args.batch
     cfg, lo, host_batch = load_workload(S, n, args.mode)
     ver = S.Verifier(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the library and the timing events share it
+    torch.cuda.set_stream(stream)
     ver.set_stream(stream.cuda_stream)
 
     # R distinct device copies of the batch, rotated: R * n * 54.5 KB > 126 MB L2, so no step finds its input in L2
-    copies = max(1, args.copies)
+    depth = max(1, min(4, args.pipeline))
+    copies = max(1, args.copies, depth)
     dev = [torch.from_numpy(host_batch.view(np.int32)).cuda() for _ in range(copies)]
-    accept = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
-    status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ver.set_pipeline_depth(depth)
+    # outputs: one bitmap row per step (never reused inside the timed region), one status buffer per in-flight batch
+    words = (n + 31) // 32
+    rows = max(args.steps, args.warmup)
+    accept_all = torch.zeros((rows, words), dtype=torch.int32, device="cuda")
+    gathered = torch.zeros((world, rows, words), dtype=torch.int32, device="cuda") if world > 1 else None
+    statuses = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(depth)]
     total_n = n * world
 
     def step(k):
-        ver.stwo_verify_batch(dev[k % copies], cfg, n, accept_out=accept, status_out=status)
+        """One pass of verify_proof over one batch (asynchronous; with depth > 1 up to `depth` batches are in flight)."""
+        ver.stwo_verify_batch(dev[k % copies], cfg, n, accept_out=accept_all[k], status_out=statuses[k % depth])
+
+    def finish():
+        """Order all in-flight batches into the timing stream, then the job's only exchange: the accept-bitmap gather."""
+        ver.join()
         if world > 1:
-            return sharding.gather_accept_bitmaps(accept, total_n, world)
-        return accept
+            dist.all_gather_into_tensor(gathered.view(-1), accept_all.view(-1))
 
     int32_ops, probe_ms = ver.int32_peak_probe()
     for k in range(args.warmup):
         step(k)
+    finish()
     torch.cuda.synchronize()
     ver.profile_read()
     ver.profile_enable(True)
@@ -282,7 +295,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for k in range(args.steps):
-            full = step(k)
+            step(k)
+        finish()
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -298,9 +312,13 @@ def main():
     value = total_n * args.steps / (ms_max * 1e-3)
 
     # correctness of what was timed (outside the timed region): every rank's statuses against the oracle on a slice
+    status = statuses[(args.steps - 1) % depth]
     st = status.cpu().numpy().view(np.uint32)
-    bits = np.unpackbits(full.cpu().numpy().view(np.uint8), bitorder="little")[:total_n]
+    last = (gathered[:, args.steps - 1, :] if world > 1 else accept_all[args.steps - 1]).contiguous().cpu().numpy()
+    bits = np.concatenate([np.unpackbits(r.view(np.uint8), bitorder="little")[:n] for r in last.reshape(world, words)])
     accepted = int(bits.sum())
+    first_rows = accept_all[: args.steps].cpu().numpy()
+    assert (first_rows == first_rows[0]).all(), "steps disagree"
     if rank == 0:
         from oracle import oracle as O
 
@@ -351,7 +369,8 @@ def main():
             "config": {"workload": f"stwo-verifier proof.json witness (prod preset: LDE 2^13, 16 queries, 1+8 FRI layers) replicated x{n} per GPU",
                        "mode": args.mode, "batch_per_gpu": n, "accepted": accepted,
                        "l2": f"rotating {copies} distinct device copies of the batch ({copies * n * lo.stride_words * 4 / 1e6:.0f} MB > 126 MB L2)",
-                       "parallelism": f"proof-sharded x{world}, accept-bitmap all_gather per step" if world > 1 else "single GPU"},
+                       "pipeline": f"{depth} batches in flight per GPU (ssym_set_pipeline_depth); per-kernel times below are per launch, kernels of consecutive steps overlap" if depth > 1 else "serial steps",
+                       "parallelism": f"proof-sharded x{world} (one process per GPU, no data-path collective), one NCCL all_gather of the accept bitmaps of all steps inside the timed region" if world > 1 else "single GPU"},
             "merkle_hashes_per_s": value * MERKLE_COMPRESSIONS_PER_PROOF / 2.0,
             "sha256_compressions_per_s": value * COMPRESSIONS_PER_PROOF,
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n * lo.stride_words * 4), "d2h_bytes_per_step": int(acc_host.nbytes),

@@ -203,6 +203,13 @@ const char *ssym_version(void);
  * device-resident calls on this handle; NULL restores the handle's own stream. */
 int ssym_set_stream(ssym_ctx_t *ctx, void *cuda_stream);
 int ssym_synchronize(ssym_ctx_t *ctx);
+/* Pipeline depth D (1..4, default 1) for device-resident ssym_stwo_verify_batch calls: call k runs on internal
+ * stream k % D (forked from the handle's stream at call time), so up to D consecutive batches are in flight and the
+ * latency-bound channel kernel of one batch overlaps the Merkle kernel of the previous one.  With D > 1 results are
+ * ordered into the handle's stream only by ssym_join (device-side wait, no host sync) or ssym_synchronize, and the
+ * caller must not reuse an input / output buffer within D consecutive calls without a join in between. */
+int ssym_set_pipeline_depth(ssym_ctx_t *ctx, int depth);
+int ssym_join(ssym_ctx_t *ctx);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t ssym_launch_count(const ssym_ctx_t *ctx);
 

@@ -75,6 +75,8 @@ SYMBOLS = {
     "ssym_version": (C.c_char_p, []),
     "ssym_set_stream": (_I, [_V, _V]),
     "ssym_synchronize": (_I, [_V]),
+    "ssym_set_pipeline_depth": (_I, [_V, _I]),
+    "ssym_join": (_I, [_V]),
     "ssym_launch_count": (C.c_uint64, [_V]),
     "ssym_profile_enable": (_I, [_V, _I]),
     "ssym_profile_read": (_I, [_V, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -87,8 +87,20 @@ struct ssym_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     uint64_t launches = 0;
-    // Stwo scratch (per chunk) and domain tables (per config)
-    DevBuf stwo_ctx, stwo_evals, status;
+    // Pipeline lanes: call k of ssym_stwo_verify_batch(SSYM_MEM_DEVICE) runs on lane k % depth, each lane with its own
+    // stream and scratch, so consecutive calls overlap on the GPU (the channel kernel of call k+1 is a latency-bound
+    // chain that hides behind the Merkle kernel of call k).  depth 1 = everything on the handle's stream.
+    struct Lane {
+        cudaStream_t s = nullptr;
+        cudaEvent_t in = nullptr, done = nullptr;
+        DevBuf stwo_ctx, stwo_evals, status;
+        bool pending = false;
+    };
+    static const int MAX_DEPTH = 4;
+    Lane lanes[MAX_DEPTH];
+    int depth = 1;
+    uint64_t calls = 0;
+    // domain tables (per config)
     DevBuf tab_point, tab_fold, tab_flag;
     uint32_t tab_G = 0, tab_L = 0xffffffffu;
     uint32_t fold_off[SSYM_MAX_FRI_LAYERS] = {0};
@@ -124,6 +136,11 @@ int ssym_create(int device, ssym_ctx_t **out) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
+    for (auto &l : c->lanes) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&l.in, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    }
     c->stream = c->own_stream;
     *out = c;
     return SSYM_OK;
@@ -133,7 +150,13 @@ void ssym_destroy(ssym_ctx_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->stwo_ctx, &c->stwo_evals, &c->status, &c->tab_point, &c->tab_fold, &c->tab_flag, &c->stage[0], &c->stage[1],
+    for (auto &l : c->lanes) {
+        l.stwo_ctx.release(); l.stwo_evals.release(); l.status.release();
+        cudaStreamDestroy(l.s);
+        cudaEventDestroy(l.in);
+        cudaEventDestroy(l.done);
+    }
+    DevBuf *bufs[] = {&c->tab_point, &c->tab_fold, &c->tab_flag, &c->stage[0], &c->stage[1],
                       &c->d_accept, &c->d_status, &c->d_trace, &c->d_offsets, &c->s101_ctx};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : c->tmp) b.release();
@@ -151,9 +174,26 @@ int ssym_set_stream(ssym_ctx_t *c, void *cuda_stream) {
     c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return SSYM_OK;
 }
-int ssym_synchronize(ssym_ctx_t *c) {
+int ssym_set_pipeline_depth(ssym_ctx_t *c, int depth) {
+    if (!c || depth < 1 || depth > ssym_ctx::MAX_DEPTH) return fail(SSYM_ERR_USAGE, "pipeline depth must be 1..4");
+    int rc = ssym_join(c);
+    if (rc) return rc;
+    c->depth = depth;
+    return SSYM_OK;
+}
+int ssym_join(ssym_ctx_t *c) {
     if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
     CUDA_TRY(cudaSetDevice(c->device));
+    for (auto &l : c->lanes)
+        if (l.pending) {
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, l.done, 0));
+            l.pending = false;
+        }
+    return SSYM_OK;
+}
+int ssym_synchronize(ssym_ctx_t *c) {
+    int rc = ssym_join(c);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SSYM_OK;
 }
@@ -165,8 +205,8 @@ int ssym_profile_enable(ssym_ctx_t *c, int on) {
 }
 int ssym_profile_read(ssym_ctx_t *c, double *ms, uint64_t *cnt) {
     if (!c || !ms || !cnt) return fail(SSYM_ERR_USAGE, "NULL argument");
-    CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int rc = ssym_synchronize(c);
+    if (rc) return rc;
     for (int i = 0; i < SSYM_PROFILE_KERNELS; i++) { ms[i] = 0; cnt[i] = 0; }
     c->profiler.collect(ms, cnt);
     return SSYM_OK;
@@ -246,13 +286,13 @@ static int ensure_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg) {
     return SSYM_OK;
 }
 
-static int stwo_launch_chunk(ssym_ctx *c, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, const uint32_t *d_packed,
+static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, const uint32_t *d_packed,
                              size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s) {
     const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers;
     for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
         const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
-        CUDA_TRY(c->stwo_ctx.ensure(m * StwoCtxLayout::WORDS * sizeof(uint32_t)));
-        CUDA_TRY(c->stwo_evals.ensure(m * (size_t)(L + 1) * Q * 4 * sizeof(uint32_t)));
+        CUDA_TRY(lane.stwo_ctx.ensure(m * StwoCtxLayout::WORDS * sizeof(uint32_t)));
+        CUDA_TRY(lane.stwo_evals.ensure(m * (size_t)(L + 1) * Q * 4 * sizeof(uint32_t)));
         StwoParams p;
         p.cfg = cfg;
         p.lo = lo;
@@ -260,13 +300,13 @@ static int stwo_launch_chunk(ssym_ctx *c, const ssym_stwo_config_t &cfg, const s
         p.tab.fold_inv = c->tab_fold.as<uint32_t>();
         for (uint32_t l = 0; l < SSYM_MAX_FRI_LAYERS; l++) p.tab.fold_off[l] = c->fold_off[l];
         p.packed = d_packed + done * (size_t)lo.stride_words;
-        p.ctx = c->stwo_ctx.as<uint32_t>();
-        p.fri_evals = c->stwo_evals.as<uint32_t>();
+        p.ctx = lane.stwo_ctx.as<uint32_t>();
+        p.fri_evals = lane.stwo_evals.as<uint32_t>();
         if (d_status_out) {
             p.status = d_status_out + done;
         } else {
-            CUDA_TRY(c->status.ensure(m * sizeof(uint32_t)));
-            p.status = c->status.as<uint32_t>();
+            CUDA_TRY(lane.status.ensure(m * sizeof(uint32_t)));
+            p.status = lane.status.as<uint32_t>();
         }
         p.trace = d_trace ? d_trace + done : nullptr;
         p.n = (uint32_t)m;
@@ -288,7 +328,18 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     CUDA_TRY(cudaSetDevice(c->device));
     rc = ensure_tables(c, *cfg);
     if (rc) return rc;
-    if (memspace == SSYM_MEM_DEVICE) return stwo_launch_chunk(c, *cfg, lo, packed, n, accept_bits, status, trace, c->stream);
+    if (memspace == SSYM_MEM_DEVICE) {
+        if (c->depth == 1) return stwo_launch_chunk(c, c->lanes[0], *cfg, lo, packed, n, accept_bits, status, trace, c->stream);
+        // pipelined: fork from the handle's stream into lane k % depth; joined by ssym_join / ssym_synchronize
+        ssym_ctx::Lane &lane = c->lanes[c->calls++ % c->depth];
+        CUDA_TRY(cudaEventRecord(lane.in, c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.in, 0));
+        rc = stwo_launch_chunk(c, lane, *cfg, lo, packed, n, accept_bits, status, trace, lane.s);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(lane.done, lane.s));
+        lane.pending = true;
+        return SSYM_OK;
+    }
     if (memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
 
     // Host buffers: double-buffered H2D on the copy stream overlapped with the kernels of the previous chunk.
@@ -311,7 +362,7 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
         CUDA_TRY(cudaMemcpyAsync(c->stage[b].p, packed + done * (size_t)lo.stride_words, m * stride_b, cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
-        rc = stwo_launch_chunk(c, *cfg, lo, c->stage[b].as<uint32_t>(), m, c->d_accept.as<uint32_t>() + done / 32,
+        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, c->stage[b].as<uint32_t>(), m, c->d_accept.as<uint32_t>() + done / 32,
                                c->d_status.as<uint32_t>() + done, trace ? c->d_trace.as<ssym_stwo_trace_t>() + done : nullptr, s);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev_done[b], s));
@@ -341,7 +392,7 @@ extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, c
         p.blob = blob;
         p.offsets = offsets;
         if (status) p.status = status;
-        else { CUDA_TRY(c->status.ensure(n * 4)); p.status = c->status.as<uint32_t>(); }
+        else { CUDA_TRY(c->lanes[0].status.ensure(n * 4)); p.status = c->lanes[0].status.as<uint32_t>(); }
         p.trace = trace;
         if (trace) CUDA_TRY(cudaMemsetAsync(trace, 0, n * sizeof(ssym_s101_trace_t), s));
         launch_s101_verify(p, accept_bits, s, &c->launches, c->profiling ? &c->profiler : nullptr);

@@ -74,7 +74,95 @@ __device__ __noinline__ QM31 channel_draw_qm31(Channel &c, bool &exhausted) {
     return qm31(m31_reduce(w[0]), m31_reduce(w[1]), m31_reduce(w[2]), m31_reduce(w[3]));
 }
 
-// Out-of-line field helpers for the once-per-proof code (keeps K1 compact).
+// ------------------------------------------------------------------------------------------
+// K1: the Fiat-Shamir channel of verify_proof (verifier.simf:36-51).  The channel state only ever
+// absorbs proof data (roots, samples, nonce): none of the field arithmetic feeds back into it, so the
+// whole transcript is one dependent chain of ~46 SHA-256 compressions per proof — one thread per
+// proof, raw draws written to the per-proof context for K2.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const ssym_stwo_layout_t &lo = p.lo;
+    const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
+    uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
+    ssym_stwo_trace_t *tr = p.trace ? p.trace + i : nullptr;
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
+    uint32_t status = 0;
+    bool exhausted = false;
+
+    Channel ch; // channel_init channel.simf:31-33
+#pragma unroll
+    for (int k = 0; k < 8; k++) ch.d[k] = 0;
+    ch.n_sent = 0;
+
+    // evals_commit                                            evals/commit.simf:20-35
+    channel_mix(ch, pk + lo.off_commit, 8);
+    channel_mix(ch, pk + lo.off_commit + 8, 8);
+    const QM31 cp_alpha = channel_draw_qm31(ch, exhausted);
+    channel_mix(ch, pk + lo.off_commit + 16, 8);
+    qm31_store4(ctx + CX::CP_ALPHA, cp_alpha);
+    if (tr) {
+        for (int k = 0; k < 8; k++) tr->digest_commit[k] = ch.d[k];
+        qm31_store(tr->cp_alpha, cp_alpha);
+    }
+    // oods: draw the point parameter t, absorb the samples, draw the DEEP alpha    deep/oods.simf:44-64
+    qm31_store4(ctx + CX::OODS_T, channel_draw_qm31(ch, exhausted)); // channel.simf:143-144
+    channel_mix(ch, pk + lo.off_oods_trace, 80);                     // 4 trace + 16 CP samples are contiguous in the packed header
+    const QM31 deep_alpha = channel_draw_qm31(ch, exhausted);
+    qm31_store4(ctx + CX::DEEP_ALPHA, deep_alpha);
+    if (tr) {
+        for (int k = 0; k < 8; k++) tr->digest_oods[k] = ch.d[k];
+        qm31_store(tr->deep_alpha, deep_alpha);
+    }
+    // fri_commit                                              fri/commit.simf:72-85
+#pragma unroll 1
+    for (uint32_t l = 0; l <= L; l++) {
+        channel_mix(ch, l == 0 ? pk + lo.off_fri_first_root : pk + lo.off_fri_inner_root + 8 * (l - 1), 8);
+        const QM31 alpha = channel_draw_qm31(ch, exhausted);
+        qm31_store4(ctx + CX::FRI_ALPHA + 4 * l, alpha);
+        if (tr) qm31_store(tr->fri_alpha[l], alpha);
+    }
+    channel_mix(ch, pk + lo.off_last_coeff, 4); // channel_mix_line_poly
+    if (tr)
+        for (int k = 0; k < 8; k++) tr->digest_fri[k] = ch.d[k];
+    // check_proof_of_work                                     pow.simf:22-35
+    channel_mix(ch, pk + lo.off_pow_nonce, 2); // channel_mix_u64: {hi, lo} big-endian
+    {
+        const uint64_t value = ((uint64_t)__byte_perm(ch.d[7], 0, 0x0123) << 32) | __byte_perm(ch.d[6], 0, 0x0123);
+        if (!(value < p.cfg.pow_target)) status |= SSYM_ST_POW_FAIL;
+        if (tr) {
+            for (int k = 0; k < 8; k++) tr->digest_pow[k] = ch.d[k];
+            tr->pow_value[0] = (uint32_t)(value >> 32);
+            tr->pow_value[1] = (uint32_t)value;
+        }
+    }
+    // fri_generate_queries                                    fri/queries.simf:30-43
+    {
+        const uint32_t mask = shl32(G & 0xff, 1u) - 1u;
+#pragma unroll 1
+        for (uint32_t q0 = 0; q0 < Q; q0 += 8) {
+            uint32_t w[8];
+            channel_draw_u256(ch, w);
+            for (uint32_t j = 0; j < 8 && q0 + j < Q; j++) {
+                ctx[CX::QUERIES + q0 + j] = w[j] & mask;
+                if (tr) tr->queries[q0 + j] = w[j] & mask;
+            }
+        }
+    }
+    if (exhausted) status |= SSYM_ST_DRAW_EXHAUSTED;
+    if (p.cfg.mode == SSYM_MODE_REF_LITERAL && ((G - (L + 1u)) & 0xff) != 0) status |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
+    p.status[i] = status;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: all field arithmetic of verify_proof, one warp per proof:
+//   phase A  OODS point from t, composition polynomial at the point vs. the recombined samples (deep/oods.simf:44-64)
+//   phase B  lane k < 20: DEEP line coefficients of column k with alpha^(k+1) (deep/quotients.simf:25-35); the
+//            coefficients depend only on the proof, not on the query, so they are computed once, in parallel
+//   phase C  lane q < Q: fri_answer of query q (fri/answers.simf:97-129) and its 1+L folds (fri/layers.simf:51-78,
+//            fri/folding.simf:15-41); the Merkle halves of those functions are K3
+// ------------------------------------------------------------------------------------------
 __device__ __noinline__ QM31 qm31_mul_nl(QM31 x, QM31 y) { return qm31_mul(x, y); }
 __device__ __noinline__ QM31 qm31_inv_nl(QM31 x, bool &fail) { return qm31_inv(x, fail); }
 
@@ -103,60 +191,85 @@ __device__ __noinline__ LineCoeffs interpolant_coefficients(QM31 py, QM31 sv, QM
     return r;
 }
 
-__device__ __forceinline__ void store_point(uint32_t *w, QM31 x, QM31 y) {
-    qm31_store(w, x);
-    qm31_store(w + 4, y);
+__device__ __forceinline__ QM31 qm31_shfl(QM31 v, int src) {
+    return qm31(__shfl_sync(0xffffffffu, v.r.a, src), __shfl_sync(0xffffffffu, v.r.b, src), __shfl_sync(0xffffffffu, v.i.a, src),
+                __shfl_sync(0xffffffffu, v.i.b, src));
+}
+// Sum of canonical field elements over the warp (exact field addition is associative, so the butterfly order gives
+// the same canonical value as the reference's left-to-right fold, fri/answers.simf:52).
+__device__ __forceinline__ QM31 qm31_warp_sum(QM31 v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        QM31 o = qm31(__shfl_xor_sync(0xffffffffu, v.r.a, off), __shfl_xor_sync(0xffffffffu, v.r.b, off),
+                      __shfl_xor_sync(0xffffffffu, v.i.a, off), __shfl_xor_sync(0xffffffffu, v.i.b, off));
+        v = qm31_add(v, o);
+    }
+    return v;
 }
 
-// ------------------------------------------------------------------------------------------
-// K1: transcript.  verifier.simf:36-51 up to and including fri_generate_queries.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) stwo_transcript_kernel(StwoParams p) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
+__device__ __forceinline__ CM31 denominator_inverse(QM31 px, QM31 py, M31Point r, bool &fail) { // deep/quotients.simf:15-22
+    CM31 dx = cm31_sub_m31(px.r, r.x);
+    CM31 dy = cm31_sub_m31(py.r, r.y);
+    CM31 d = cm31_sub(cm31_mul(dx, py.i), cm31_mul(dy, px.i));
+    return cm31_inv(d, fail);
+}
+
+// sum_k b_k * v_k - (R.y * sum_a + sum_c): the batch's quotient numerator accumulator (= the fold of
+// quotient_numerator_aggregate, fri/answers.simf:40-58, regrouped; all operands are exact field values and only the
+// b_k * v_k products see raw witness words, exactly as in deep_quotient_nominator, deep/quotients.simf:38-44)
+__device__ __forceinline__ QM31 batch_numerator(const uint32_t *bcoef, const uint32_t *vals, int n, QM31 sum_a, QM31 sum_c, M31 ry) {
+    QM31 s = qm31_zero();
+#pragma unroll 4
+    for (int k = 0; k < n; k++) s = qm31_add(s, qm31_mul_m31(qm31_load4(bcoef + 4 * k), vals[k]));
+    return qm31_sub(s, qm31_add(qm31_mul_m31(sum_a, ry), sum_c));
+}
+
+#define K2_WARPS 4
+__global__ void __launch_bounds__(32 * K2_WARPS) stwo_query_kernel(StwoParams p) {
+    __shared__ __align__(16) uint32_t s_b[K2_WARPS][20 * 4];
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * K2_WARPS + wib;
+    if (i >= p.n) return; // warp-uniform
     const ssym_stwo_layout_t &lo = p.lo;
     const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
-    uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
+    const uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
     ssym_stwo_trace_t *tr = p.trace ? p.trace + i : nullptr;
-    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
     const bool literal = p.cfg.mode == SSYM_MODE_REF_LITERAL;
     uint32_t status = 0;
-    bool exhausted = false, inv_zero = false;
 
-    Channel ch; // channel_init channel.simf:31-33
-#pragma unroll
-    for (int k = 0; k < 8; k++) ch.d[k] = 0;
-    ch.n_sent = 0;
-
-    // evals_commit                                            evals/commit.simf:20-35
-    channel_mix(ch, pk + lo.off_commit, 8);
-    channel_mix(ch, pk + lo.off_commit + 8, 8);
-    const QM31 cp_alpha = channel_draw_qm31(ch, exhausted);
-    channel_mix(ch, pk + lo.off_commit + 16, 8);
-    if (tr) {
-        for (int k = 0; k < 8; k++) tr->digest_commit[k] = ch.d[k];
-        qm31_store(tr->cp_alpha, cp_alpha);
-    }
-
-    // oods                                                    deep/oods.simf:44-64
+    // ---- phase A (every lane computes the point; lanes 0..3 split the recombination) ----
+    bool inv_zero = false;
     QM31 px, py;
     { // channel_draw_qm31_point channel.simf:143-151
-        QM31 t = channel_draw_qm31(ch, exhausted);
-        QM31 t_sq = qm31_mul_nl(t, t);
-        QM31 inv = qm31_inv_nl(qm31_add(qm31_one(), t_sq), inv_zero);
+        const QM31 t = qm31_load4(ctx + CX::OODS_T);
+        const QM31 t_sq = qm31_mul_nl(t, t);
+        const QM31 inv = qm31_inv_nl(qm31_add(qm31_one(), t_sq), inv_zero);
         px = qm31_mul_nl(qm31_sub(qm31_one(), t_sq), inv);
         py = qm31_mul_nl(qm31_add(t, t), inv);
     }
-    channel_mix(ch, pk + lo.off_oods_trace, 80); // 4 trace + 16 CP samples are contiguous in the packed header
-    QM31 cp_eval;
-    { // eval_composition_poly wide_fibonacci.simf:24-62
+    const QM31 pxy = qm31_mul_nl(px, py);
+    {
+        // composition_poly_eval_from_decomposed composition_poly.simf:47-59 (index = 4*coord + poly): lane = poly
+        const uint32_t *e = pk + lo.off_oods_cp;
+        const uint32_t poly = lane & 3;
+        QM31 part = cp_from_partitions(qm31_load4(e + 4 * poly), qm31_load4(e + 4 * (4 + poly)), qm31_load4(e + 4 * (8 + poly)),
+                                       qm31_load4(e + 4 * (12 + poly)));
+        const QM31 factor = poly == 1 ? py : poly == 2 ? px : pxy; // F_a + y F_b + x F_c + xy F_d
+        const QM31 term = poly == 0 ? part : qm31_mul_nl(part, factor);
+        QM31 sampled = qm31_shfl(term, 0);
+        sampled = qm31_add(sampled, qm31_shfl(term, 1));
+        sampled = qm31_add(sampled, qm31_shfl(term, 2));
+        sampled = qm31_add(sampled, qm31_shfl(term, 3));
+        // eval_composition_poly wide_fibonacci.simf:24-62
+        const QM31 cp_alpha = qm31_load4(ctx + CX::CP_ALPHA);
         QM31 acc = qm31_zero(), a = qm31_zero(), b = qm31_zero();
         uint32_t skip_2 = 0;
 #pragma unroll 1
         for (int col = 0; col < SSYM_NUM_COLUMNS; col++) {
-            QM31 c = qm31_load4(pk + lo.off_oods_trace + 4 * col);
+            const QM31 c = qm31_load4(pk + lo.off_oods_trace + 4 * col);
             if (skip_2 == 2) {
-                QM31 constraint = qm31_sub(c, qm31_add(qm31_mul_nl(b, b), qm31_mul_nl(a, a)));
+                const QM31 constraint = qm31_sub(c, qm31_add(qm31_mul_nl(b, b), qm31_mul_nl(a, a)));
                 acc = qm31_add(qm31_mul_nl(acc, cp_alpha), constraint);
             } else {
                 skip_2++;
@@ -169,226 +282,116 @@ __global__ void __launch_bounds__(64) stwo_transcript_kernel(StwoParams p) {
         QM31 v = px;
 #pragma unroll 1
         for (uint32_t counter = 0; counter < 256 && counter != n_iter; counter++) {
-            QM31 s = qm31_mul_nl(v, v);
-            v = qm31_sub(qm31_add(s, s), qm31_one());
+            const QM31 sq = qm31_mul_nl(v, v);
+            v = qm31_sub(qm31_add(sq, sq), qm31_one());
         }
-        cp_eval = qm31_mul_nl(acc, qm31_inv_nl(v, inv_zero));
-    }
-    QM31 sampled;
-    { // composition_poly_eval_from_decomposed composition_poly.simf:47-59 (index = 4*coord + poly)
-        const uint32_t *e = pk + lo.off_oods_cp;
-        QM31 part[4];
-#pragma unroll 1
-        for (int poly = 0; poly < 4; poly++)
-            part[poly] = cp_from_partitions(qm31_load4(e + 4 * poly), qm31_load4(e + 4 * (4 + poly)), qm31_load4(e + 4 * (8 + poly)),
-                                            qm31_load4(e + 4 * (12 + poly)));
-        QM31 res = qm31_add(part[0], qm31_mul_nl(part[1], py));
-        res = qm31_add(res, qm31_mul_nl(part[2], px));
-        sampled = qm31_add(res, qm31_mul_nl(part[3], qm31_mul_nl(px, py)));
-    }
-    if (!qm31_eq(cp_eval, sampled)) status |= SSYM_ST_OODS_CP_MISMATCH; // deep/oods.simf:58
-    const QM31 deep_alpha = channel_draw_qm31(ch, exhausted);
-    if (tr) {
-        qm31_store(tr->oods_x, px);
-        qm31_store(tr->oods_y, py);
-        qm31_store(tr->cp_eval, cp_eval);
-        qm31_store(tr->cp_sampled, sampled);
-        for (int k = 0; k < 8; k++) tr->digest_oods[k] = ch.d[k];
-        qm31_store(tr->deep_alpha, deep_alpha);
+        const QM31 cp_eval = qm31_mul_nl(acc, qm31_inv_nl(v, inv_zero));
+        if (!qm31_eq(cp_eval, sampled)) status |= SSYM_ST_OODS_CP_MISMATCH; // deep/oods.simf:58
+        if (inv_zero) status |= SSYM_ST_OODS_INV_ZERO;
+        if (tr && lane == 0) {
+            qm31_store(tr->oods_x, px);
+            qm31_store(tr->oods_y, py);
+            qm31_store(tr->cp_eval, cp_eval);
+            qm31_store(tr->cp_sampled, sampled);
+        }
     }
 
-    // fri_commit                                              fri/commit.simf:72-85
-#pragma unroll 1
-    for (uint32_t l = 0; l <= L; l++) {
-        channel_mix(ch, l == 0 ? pk + lo.off_fri_first_root : pk + lo.off_fri_inner_root + 8 * (l - 1), 8);
-        QM31 alpha = channel_draw_qm31(ch, exhausted);
-        qm31_store(ctx + CX::FRI_ALPHA + 4 * l, alpha);
-        if (tr) qm31_store(tr->fri_alpha[l], alpha);
+    // ---- phase B: lane k computes the line coefficients of column k (aggregation order) with alpha^(k+1) ----
+    const QM31 deep_alpha = qm31_load4(ctx + CX::DEEP_ALPHA);
+    QM31 p2x = px, p2y = py; // sample point of batch A
+    if (!literal) {          // the 16 CP partitions are sampled at 2*P
+        p2x = qm31_point_dbl_x(px);
+        p2y = qm31_add(pxy, pxy);
     }
-    channel_mix(ch, pk + lo.off_last_coeff, 4); // channel_mix_line_poly
+    QM31 sum_a_A, sum_c_A, sum_a_B, sum_c_B, batch_coeff;
+    {
+        const uint32_t k = lane < 20 ? lane : 19;
+        QM31 alpha_pow = qm31_one(), base = deep_alpha; // alpha^(k+1) by square-and-multiply (exact field ops: same value as the running product)
+#pragma unroll 1
+        for (uint32_t bit = 0; bit < 5; bit++) {
+            const QM31 t = qm31_mul_nl(alpha_pow, base);
+            if (((k + 1) >> bit) & 1u) alpha_pow = t;
+            base = qm31_mul_nl(base, base);
+        }
+        // literal: columns = 4 trace then 16 CP, all at P.  prover-consistent: 16 CP at 2P, then 4 trace at P.
+        const bool in_A = literal || k < 16;
+        const uint32_t *sv = literal ? pk + lo.off_oods_trace + 4 * k : (k < 16 ? pk + lo.off_oods_cp + 4 * k : pk + lo.off_oods_trace + 4 * (k - 16));
+        const LineCoeffs lc = interpolant_coefficients(in_A ? p2y : py, qm31_load4(sv), alpha_pow);
+        if (lane < 20) qm31_store4(&s_b[wib][4 * lane], lc.b);
+        const QM31 zero = qm31_zero();
+        sum_a_A = qm31_warp_sum(lane < 20 && in_A ? lc.a : zero);
+        sum_c_A = qm31_warp_sum(lane < 20 && in_A ? lc.c : zero);
+        sum_a_B = qm31_warp_sum(lane < 20 && !in_A ? lc.a : zero);
+        sum_c_B = qm31_warp_sum(lane < 20 && !in_A ? lc.c : zero);
+        batch_coeff = qm31_mul_nl(qm31_shfl(alpha_pow, 19), deep_alpha); // alpha^21
+    }
+    __syncwarp();
+
+    // ---- phase C: lane q = query q ----
+    if (lane < Q) {
+        const uint32_t q = lane;
+        const uint32_t query = ctx[CX::QUERIES + q];
+        const uint2 rp = p.tab.point[query]; // domain point of the query, fri/answers.simf:108-110
+        const M31Point R = m31_point(rp.x, rp.y);
+        uint32_t vals[20];
+        {
+            const uint4 *v4 = reinterpret_cast<const uint4 *>(pk + lo.off_qvals + 20 * q); // 80-byte records: 16-byte aligned
 #pragma unroll
-    for (int k = 0; k < 4; k++) ctx[CX::LAST_COEFF + k] = pk[lo.off_last_coeff + k];
-    if (tr)
-        for (int k = 0; k < 8; k++) tr->digest_fri[k] = ch.d[k];
-
-    // check_proof_of_work                                     pow.simf:22-35
-    channel_mix(ch, pk + lo.off_pow_nonce, 2); // channel_mix_u64: {hi, lo} big-endian
-    {
-        const uint64_t value = ((uint64_t)__byte_perm(ch.d[7], 0, 0x0123) << 32) | __byte_perm(ch.d[6], 0, 0x0123);
-        if (!(value < p.cfg.pow_target)) status |= SSYM_ST_POW_FAIL;
-        if (tr) {
-            for (int k = 0; k < 8; k++) tr->digest_pow[k] = ch.d[k];
-            tr->pow_value[0] = (uint32_t)(value >> 32);
-            tr->pow_value[1] = (uint32_t)value;
-        }
-    }
-
-    // fri_generate_queries                                    fri/queries.simf:30-43
-    {
-        const uint32_t mask = shl32(G & 0xff, 1u) - 1u;
-#pragma unroll 1
-        for (uint32_t q0 = 0; q0 < Q; q0 += 8) {
-            uint32_t w[8];
-            channel_draw_u256(ch, w);
-            for (uint32_t j = 0; j < 8 && q0 + j < Q; j++) {
-                ctx[CX::QUERIES + q0 + j] = w[j] & mask;
-                if (tr) tr->queries[q0 + j] = w[j] & mask;
+            for (int k = 0; k < 5; k++) {
+                const uint4 v = __ldg(v4 + k);
+                vals[4 * k] = v.x; vals[4 * k + 1] = v.y; vals[4 * k + 2] = v.z; vals[4 * k + 3] = v.w;
             }
         }
-    }
-
-    // Per-proof part of fri_answer (fri/answers.simf:97-129): the line coefficients depend only on
-    // the OODS point / samples / alpha, not on the query, so they are computed once here.
-    {
-        QM31 alpha_i = deep_alpha;
-        QM31 sum_a = qm31_zero(), sum_c = qm31_zero();
+        QM31 eval;
+        bool inv_fail = false;
         if (literal) {
-            store_point(ctx + CX::POINT_A, px, py);
-#pragma unroll 1
-            for (int k = 0; k < 20; k++) { // 4 trace columns, then 16 CP partitions: contiguous samples
-                LineCoeffs lc = interpolant_coefficients(py, qm31_load4(pk + lo.off_oods_trace + 4 * k), alpha_i);
-                qm31_store4(ctx + CX::B_COEFF + 4 * k, lc.b);
-                sum_a = qm31_add(sum_a, lc.a);
-                sum_c = qm31_add(sum_c, lc.c);
-                alpha_i = qm31_mul_nl(alpha_i, deep_alpha);
-            }
-            qm31_store4(ctx + CX::SUM_A_A, sum_a);
-            qm31_store4(ctx + CX::SUM_C_A, sum_c);
-            qm31_store4(ctx + CX::BATCH_COEFF, alpha_i); // alpha^21
+            const CM31 den_inv = denominator_inverse(px, py, R, inv_fail);
+            const QM31 acc = batch_numerator(s_b[wib], vals, 20, sum_a_A, sum_c_A, R.y);
+            eval = qm31_mul(qm31_mul_cm31(acc, den_inv), batch_coeff); // fri/answers.simf:126
         } else {
-            // batch A = the 16 CP partitions sampled at 2*P, batch B = the 4 trace columns at P
-            QM31 p2x = qm31_point_dbl_x(px);
-            QM31 xy = qm31_mul_nl(px, py);
-            QM31 p2y = qm31_add(xy, xy);
-            store_point(ctx + CX::POINT_A, p2x, p2y);
-            store_point(ctx + CX::POINT_B, px, py);
+            const CM31 den_a = denominator_inverse(p2x, p2y, R, inv_fail);
+            const CM31 den_b = denominator_inverse(px, py, R, inv_fail);
+            const QM31 num_a = batch_numerator(s_b[wib], vals + 4, 16, sum_a_A, sum_c_A, R.y);
+            const QM31 num_b = batch_numerator(s_b[wib] + 64, vals, 4, sum_a_B, sum_c_B, R.y);
+            eval = qm31_add(qm31_mul_cm31(num_a, den_a), qm31_mul_cm31(num_b, den_b));
+        }
+        if (inv_fail) {
+            status |= SSYM_ST_ANSWER_INV_ZERO;
+            if (tr) atomicOr(&tr->mask_answer_inv, 1u << q);
+        }
+        if (tr) qm31_store(tr->fri_answer[q], eval);
+
+        uint32_t *ev_out = p.fri_evals + (size_t)i * (L + 1) * Q * 4;
+        uint32_t fq = query;
 #pragma unroll 1
-            for (int k = 0; k < 16; k++) {
-                LineCoeffs lc = interpolant_coefficients(p2y, qm31_load4(pk + lo.off_oods_cp + 4 * k), alpha_i);
-                qm31_store4(ctx + CX::B_COEFF + 4 * k, lc.b);
-                sum_a = qm31_add(sum_a, lc.a);
-                sum_c = qm31_add(sum_c, lc.c);
-                alpha_i = qm31_mul_nl(alpha_i, deep_alpha);
+        for (uint32_t l = 0; l <= L; l++) { // fri_verify_query fri/layers.simf:51-69 (without verify_decommitment)
+            qm31_store4(ev_out + (l * Q + q) * 4, eval);
+            const QM31 witness = qm31_load4(pk + lo.off_fri_wit + (l * Q + q) * 4);
+            const bool even = (fq & 1u) == 0; // adjacent_leaves fri/layers.simf:29-37
+            const QM31 e0 = even ? eval : witness, e1 = even ? witness : eval;
+            const M31 inv = p.tab.fold_inv[p.tab.fold_off[l] + (fq >> 1)];
+            if (inv == 0) { // m31_inv(0): fri/folding.simf:20,34 assert
+                status |= SSYM_ST_FOLD_INV_ZERO;
+                if (tr) atomicOr(&tr->mask_fold_inv[l], 1u << q);
             }
-            qm31_store4(ctx + CX::SUM_A_A, sum_a);
-            qm31_store4(ctx + CX::SUM_C_A, sum_c);
-            sum_a = qm31_zero();
-            sum_c = qm31_zero();
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                LineCoeffs lc = interpolant_coefficients(py, qm31_load4(pk + lo.off_oods_trace + 4 * k), alpha_i);
-                qm31_store4(ctx + CX::B_COEFF + 4 * (16 + k), lc.b);
-                sum_a = qm31_add(sum_a, lc.a);
-                sum_c = qm31_add(sum_c, lc.c);
-                alpha_i = qm31_mul_nl(alpha_i, deep_alpha);
-            }
-            qm31_store4(ctx + CX::SUM_A_B, sum_a);
-            qm31_store4(ctx + CX::SUM_C_B, sum_c);
+            const QM31 f0 = qm31_add(e0, e1);
+            const QM31 f1 = qm31_mul_m31(qm31_sub(e0, e1), inv);
+            eval = qm31_add(f0, qm31_mul(qm31_load4(ctx + CX::FRI_ALPHA + 4 * l), f1));
+            if (tr) qm31_store(tr->folded[l][q], eval);
+            fq >>= 1; // divide_32(position, 2)
+        }
+        // fri_verify_last_layer fri/layers.simf:73-78
+        if (literal && fq != 0) {
+            status |= SSYM_ST_LAST_QUERY;
+            if (tr) atomicOr(&tr->mask_last_query, 1u << q);
+        }
+        if (!qm31_eq(eval, qm31_load4(pk + lo.off_last_coeff))) {
+            status |= SSYM_ST_LAST_EVAL;
+            if (tr) atomicOr(&tr->mask_last_eval, 1u << q);
         }
     }
-
-    if (exhausted) status |= SSYM_ST_DRAW_EXHAUSTED;
-    if (inv_zero) status |= SSYM_ST_OODS_INV_ZERO;
-    if (literal && ((G - (L + 1u)) & 0xff) != 0) status |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
-    p.status[i] = status;
-}
-
-// ------------------------------------------------------------------------------------------
-// K2: per (proof, query): fri_answer (fri/answers.simf:97-129) + the folds of fri_verify
-// (fri/layers.simf:51-78, fri/folding.simf:15-41).  The Merkle halves of those functions are K3.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ CM31 denominator_inverse(const uint32_t *pt, M31Point r, bool &fail) { // deep/quotients.simf:15-22
-    CM31 prx = cm31(pt[0], pt[1]), pix = cm31(pt[2], pt[3]), pry = cm31(pt[4], pt[5]), piy = cm31(pt[6], pt[7]);
-    CM31 dx = cm31_sub_m31(prx, r.x);
-    CM31 dy = cm31_sub_m31(pry, r.y);
-    CM31 d = cm31_sub(cm31_mul(dx, piy), cm31_mul(dy, pix));
-    return cm31_inv(d, fail);
-}
-
-// sum_k b_k * v_k - (R.y * sum_a + sum_c): the batch's quotient numerator accumulator
-// (= the fold of quotient_numerator_aggregate, fri/answers.simf:40-58, regrouped; all operands are exact
-// field values and only the b_k * v_k products see raw witness words, exactly as in deep_quotient_nominator)
-__device__ __forceinline__ QM31 batch_numerator(const uint32_t *bcoef, const uint32_t *vals, int n, const uint32_t *sum_a,
-                                                const uint32_t *sum_c, M31 ry) {
-    QM31 s = qm31_zero();
-#pragma unroll 4
-    for (int k = 0; k < n; k++) s = qm31_add(s, qm31_mul_m31(qm31_load4(bcoef + 4 * k), vals[k]));
-    QM31 a_py = qm31_mul_m31(qm31_load4(sum_a), ry);
-    return qm31_sub(s, qm31_add(a_py, qm31_load4(sum_c)));
-}
-
-__global__ void __launch_bounds__(128) stwo_query_kernel(StwoParams p) {
-    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
-    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= p.n * Q) return;
-    const uint32_t i = item / Q, q = item % Q;
-    const ssym_stwo_layout_t &lo = p.lo;
-    const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
-    const uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
-    ssym_stwo_trace_t *tr = p.trace ? p.trace + i : nullptr;
-    const bool literal = p.cfg.mode == SSYM_MODE_REF_LITERAL;
-    uint32_t status = 0;
-
-    const uint32_t query = ctx[CX::QUERIES + q];
-    const uint2 rp = p.tab.point[query]; // domain point of the query, fri/answers.simf:108-110
-    const M31Point R = m31_point(rp.x, rp.y);
-    uint32_t vals[20];
-    {
-        const uint4 *v4 = reinterpret_cast<const uint4 *>(pk + lo.off_qvals + 20 * q); // 80-byte records: 16-byte aligned
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            uint4 v = v4[k];
-            vals[4 * k] = v.x; vals[4 * k + 1] = v.y; vals[4 * k + 2] = v.z; vals[4 * k + 3] = v.w;
-        }
-    }
-    QM31 eval;
-    bool inv_fail = false;
-    if (literal) {
-        CM31 den_inv = denominator_inverse(ctx + CX::POINT_A, R, inv_fail);
-        QM31 acc = batch_numerator(ctx + CX::B_COEFF, vals, 20, ctx + CX::SUM_A_A, ctx + CX::SUM_C_A, R.y);
-        eval = qm31_mul(qm31_mul_cm31(acc, den_inv), qm31_load4(ctx + CX::BATCH_COEFF)); // fri/answers.simf:126
-    } else {
-        CM31 den_a = denominator_inverse(ctx + CX::POINT_A, R, inv_fail);
-        CM31 den_b = denominator_inverse(ctx + CX::POINT_B, R, inv_fail);
-        QM31 num_a = batch_numerator(ctx + CX::B_COEFF, vals + 4, 16, ctx + CX::SUM_A_A, ctx + CX::SUM_C_A, R.y);
-        QM31 num_b = batch_numerator(ctx + CX::B_COEFF + 64, vals, 4, ctx + CX::SUM_A_B, ctx + CX::SUM_C_B, R.y);
-        eval = qm31_add(qm31_mul_cm31(num_a, den_a), qm31_mul_cm31(num_b, den_b));
-    }
-    if (inv_fail) {
-        status |= SSYM_ST_ANSWER_INV_ZERO;
-        if (tr) atomicOr(&tr->mask_answer_inv, 1u << q);
-    }
-    if (tr) qm31_store(tr->fri_answer[q], eval);
-
-    uint32_t *ev_out = p.fri_evals + (size_t)i * (L + 1) * Q * 4;
-    uint32_t fq = query;
-#pragma unroll 1
-    for (uint32_t l = 0; l <= L; l++) { // fri_verify_query fri/layers.simf:51-69 (without verify_decommitment)
-        qm31_store4(ev_out + (l * Q + q) * 4, eval);
-        const QM31 witness = qm31_load4(pk + lo.off_fri_wit + (l * Q + q) * 4);
-        const bool even = (fq & 1u) == 0; // adjacent_leaves fri/layers.simf:29-37
-        const QM31 e0 = even ? eval : witness, e1 = even ? witness : eval;
-        const M31 inv = p.tab.fold_inv[p.tab.fold_off[l] + (fq >> 1)];
-        if (inv == 0) { // m31_inv(0): fri/folding.simf:20,34 assert
-            status |= SSYM_ST_FOLD_INV_ZERO;
-            if (tr) atomicOr(&tr->mask_fold_inv[l], 1u << q);
-        }
-        const QM31 f0 = qm31_add(e0, e1);
-        const QM31 f1 = qm31_mul_m31(qm31_sub(e0, e1), inv);
-        eval = qm31_add(f0, qm31_mul(qm31_load4(ctx + CX::FRI_ALPHA + 4 * l), f1));
-        if (tr) qm31_store(tr->folded[l][q], eval);
-        fq >>= 1; // divide_32(position, 2)
-    }
-    // fri_verify_last_layer fri/layers.simf:73-78
-    if (literal && fq != 0) {
-        status |= SSYM_ST_LAST_QUERY;
-        if (tr) atomicOr(&tr->mask_last_query, 1u << q);
-    }
-    if (!qm31_eq(eval, qm31_load4(ctx + CX::LAST_COEFF))) {
-        status |= SSYM_ST_LAST_EVAL;
-        if (tr) atomicOr(&tr->mask_last_eval, 1u << q);
-    }
-    if (status) atomicOr(&p.status[i], status);
+    status = __reduce_or_sync(0xffffffffu, status);
+    if (lane == 0 && status) atomicOr(&p.status[i], status);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -581,10 +584,10 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     if (p.n == 0) return;
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
     if (prof) prof->begin(0, s);
-    stwo_transcript_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p);
+    stwo_channel_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p);
     if (prof) { prof->end(0, s); prof->begin(1, s); }
     const uint32_t items = p.n * Q;
-    stwo_query_kernel<<<(items + 127) / 128, 128, 0, s>>>(p);
+    stwo_query_kernel<<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s>>>(p);
     if (prof) { prof->end(1, s); prof->begin(2, s); }
     const uint32_t groups = (items + 31) / 32;
     const uint64_t warps = (uint64_t)groups * (L + 3);

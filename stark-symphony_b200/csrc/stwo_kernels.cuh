@@ -3,9 +3,9 @@
 // Batched verify_proof of the Stwo wide-Fibonacci verifier (stwo-verifier/src/verifier.simf:32-58)
 // as four kernels over a batch of packed proofs (layout: include/ssym.h):
 //
-//   K1 stwo_transcript_kernel  one thread per proof     Fiat-Shamir transcript, OODS check, PoW, queries,
-//                                                      per-proof DEEP line coefficients
-//   K2 stwo_query_kernel       one thread per (proof, query)   DEEP quotient (fri_answer) + the 1+L folds
+//   K1 stwo_channel_kernel     one thread per proof     Fiat-Shamir channel: ~46 dependent compressions, PoW, queries
+//   K2 stwo_query_kernel       one warp per proof       all field arithmetic: OODS check, DEEP line coefficients
+//                                                      (lane = column), fri_answer + the 1+L folds (lane = query)
 //   K3 stwo_merkle_kernel      one thread per hash chain  all 2*Q + (L+1)*Q Merkle decommitments
 //   K4 stwo_finalize_kernel    status words -> accept bitmap
 //
@@ -21,20 +21,15 @@
 
 namespace ssym {
 
-// Per-proof context written by K1, read by K2 / K3 (u32 words).
+// Per-proof context written by K1 (the channel), read by K2 / K3 (u32 words).
 struct StwoCtxLayout {
     enum : uint32_t {
-        STATUS = 0,
-        QUERIES = 4,                // [16]
-        FRI_ALPHA = 20,             // [9][4]
-        LAST_COEFF = 56,            // [4]
-        POINT_A = 60,               // sample point of batch A  {x.r, x.i, y.r, y.i} as 8 words
-        POINT_B = 68,               // sample point of batch B (PROVER_CONSISTENT only)
-        SUM_A_A = 76, SUM_C_A = 80, // sum of a_k, c_k over batch A
-        SUM_A_B = 84, SUM_C_B = 88, // same for batch B
-        BATCH_COEFF = 92,           // alpha^21 (REF_LITERAL only)
-        B_COEFF = 96,               // [20][4]  b_k = alpha^k * b(point), in aggregation order
-        WORDS = 176
+        QUERIES = 0,     // [16]   fri/queries.simf:30-43
+        CP_ALPHA = 16,   // [4]    evals/commit.simf:29
+        OODS_T = 20,     // [4]    the QM31 draw the OODS point is built from, channel.simf:144
+        DEEP_ALPHA = 24, // [4]    deep/oods.simf:61
+        FRI_ALPHA = 28,  // [9][4] fri/commit.simf:42
+        WORDS = 64
     };
 };
 

@@ -67,10 +67,20 @@ class Verifier:
     # ---- plumbing ------------------------------------------------------------------------------------
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         """Run device-resident calls on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        if cuda_stream == 0:
+            raise SsymError("pass a non-default stream handle (e.g. torch.cuda.Stream().cuda_stream); None restores the handle's own stream")
         check(self.lib.ssym_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     def synchronize(self) -> None:
         check(self.lib.ssym_synchronize(self.h))
+
+    def set_pipeline_depth(self, depth: int) -> None:
+        """Keep up to `depth` device-resident stwo batches in flight (see ssym_set_pipeline_depth in include/ssym.h)."""
+        check(self.lib.ssym_set_pipeline_depth(self.h, depth))
+
+    def join(self) -> None:
+        """Order all in-flight batches into the handle's stream (device-side wait only)."""
+        check(self.lib.ssym_join(self.h))
 
     @property
     def launch_count(self) -> int:
