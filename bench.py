@@ -219,7 +219,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="proofs per GPU per step (BASELINE config: 1024)")
     ap.add_argument("--mode", default="ref-literal", choices=["ref-literal", "prover-consistent"])
     ap.add_argument("--copies", type=int, default=4, help="distinct device copies of the batch rotated through (defeats L2 reuse)")
-    ap.add_argument("--pipeline", type=int, default=2, help="batches in flight per GPU (ssym_set_pipeline_depth); 1 = strictly serial steps")
+    ap.add_argument("--pipeline", type=int, default=4, help="batches in flight per GPU (ssym_set_pipeline_depth); 1 = strictly serial steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

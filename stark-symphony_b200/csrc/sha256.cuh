@@ -70,16 +70,39 @@ __device__ __forceinline__ void sha_iv(uint32_t (&h)[8]) {
     h[4] = SSYM_SHA_IV4; h[5] = SSYM_SHA_IV5; h[6] = SSYM_SHA_IV6; h[7] = SSYM_SHA_IV7;
 }
 
-#define SSYM_SHA_ROUND(a, b, c, d, e, f, g, h, kw)           \
-    {                                                        \
-        uint32_t t1_ = (h) + Sig1(e) + Ch(e, f, g) + (kw);   \
-        uint32_t t2_ = Sig0(a) + Maj(a, b, c);               \
-        (d) += t1_;                                          \
-        (h) = t1_ + t2_;                                     \
+// ---- pipe balancing -------------------------------------------------------------------------------------
+// On sm_100 the rotates / LOP3s / IADD3s of SHA-256 all issue to the ALU pipe (64 lanes/clk/SM), which is what
+// bounds the Merkle kernels (ncu: alu pipe 94 % busy, fma pipe 6 %).  An integer add can instead be issued as
+// IMAD x*1+y on the otherwise idle FMA pipe — but only if ptxas cannot see that the multiplier is 1, so the `1`
+// arrives as a kernel parameter (`one`).  ADDMODE selects which adds are moved:
+//   0  plain C adds (ptxas decides; it picks IADD3/VIADD for ~70 % of them)
+//   1  every add of the round function and of the message schedule as IMAD
+//   2  round-function adds as IMAD, message-schedule adds left to ptxas
+//   3  only the T1 chain (h + K + W + Sigma1 + Ch) as IMAD
+template <int ADDMODE>
+struct ShaAdd {
+    uint32_t one;
+    __device__ __forceinline__ uint32_t fma(uint32_t a, uint32_t b) const {
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+        return d;
+    }
+    __device__ __forceinline__ uint32_t t1(uint32_t a, uint32_t b) const { return ADDMODE >= 1 ? fma(a, b) : a + b; }    // T1 chain
+    __device__ __forceinline__ uint32_t rnd(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE == 2) ? fma(a, b) : a + b; } // rest of the round
+    __device__ __forceinline__ uint32_t sch(uint32_t a, uint32_t b) const { return ADDMODE == 1 ? fma(a, b) : a + b; }  // message schedule
+};
+
+#define SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, h, kw)                        \
+    {                                                                        \
+        uint32_t t1_ = A.t1(A.t1(h, kw), A.t1(Sig1(e), Ch(e, f, g)));        \
+        uint32_t t2_ = A.rnd(Sig0(a), Maj(a, b, c));                         \
+        (d) = A.rnd(d, t1_);                                                 \
+        (h) = A.rnd(t1_, t2_);                                               \
     }
 
 // One compression of `h` with the 16-word block `w` (w is consumed: it becomes the rolling schedule).
-__device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]) {
+template <int ADDMODE>
+__device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16], const ShaAdd<ADDMODE> A) {
     constexpr ShaK K = sha_k_table();
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
@@ -88,61 +111,139 @@ __device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int i = (t + j) & 15;
-                w[i] = w[i] + sig0(w[(i + 1) & 15]) + w[(i + 9) & 15] + sig1(w[(i + 14) & 15]);
+                w[i] = A.sch(A.sch(w[i], sig0(w[(i + 1) & 15])), A.sch(w[(i + 9) & 15], sig1(w[(i + 14) & 15])));
             }
         }
-        SSYM_SHA_ROUND(a, b, c, d, e, f, g, hh, K.k[t + 0] + w[(t + 0) & 15]);
-        SSYM_SHA_ROUND(hh, a, b, c, d, e, f, g, K.k[t + 1] + w[(t + 1) & 15]);
-        SSYM_SHA_ROUND(g, hh, a, b, c, d, e, f, K.k[t + 2] + w[(t + 2) & 15]);
-        SSYM_SHA_ROUND(f, g, hh, a, b, c, d, e, K.k[t + 3] + w[(t + 3) & 15]);
-        SSYM_SHA_ROUND(e, f, g, hh, a, b, c, d, K.k[t + 4] + w[(t + 4) & 15]);
-        SSYM_SHA_ROUND(d, e, f, g, hh, a, b, c, K.k[t + 5] + w[(t + 5) & 15]);
-        SSYM_SHA_ROUND(c, d, e, f, g, hh, a, b, K.k[t + 6] + w[(t + 6) & 15]);
-        SSYM_SHA_ROUND(b, c, d, e, f, g, hh, a, K.k[t + 7] + w[(t + 7) & 15]);
+        SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.t1(w[(t + 0) & 15], K.k[t + 0]));
+        SSYM_SHA_ROUND(A, hh, a, b, c, d, e, f, g, A.t1(w[(t + 1) & 15], K.k[t + 1]));
+        SSYM_SHA_ROUND(A, g, hh, a, b, c, d, e, f, A.t1(w[(t + 2) & 15], K.k[t + 2]));
+        SSYM_SHA_ROUND(A, f, g, hh, a, b, c, d, e, A.t1(w[(t + 3) & 15], K.k[t + 3]));
+        SSYM_SHA_ROUND(A, e, f, g, hh, a, b, c, d, A.t1(w[(t + 4) & 15], K.k[t + 4]));
+        SSYM_SHA_ROUND(A, d, e, f, g, hh, a, b, c, A.t1(w[(t + 5) & 15], K.k[t + 5]));
+        SSYM_SHA_ROUND(A, c, d, e, f, g, hh, a, b, A.t1(w[(t + 6) & 15], K.k[t + 6]));
+        SSYM_SHA_ROUND(A, b, c, d, e, f, g, hh, a, A.t1(w[(t + 7) & 15], K.k[t + 7]));
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
+__device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]) { sha_compress<0>(h, w, ShaAdd<0>{1u}); }
 
 // Compression of the constant padding block that ends every 64-byte message.
-__device__ __forceinline__ void sha_compress_pad64(uint32_t (&h)[8]) {
+template <int ADDMODE>
+__device__ __forceinline__ void sha_compress_pad64(uint32_t (&h)[8], const ShaAdd<ADDMODE> A) {
     constexpr ShaKW KW = sha_pad64_kw();
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
     for (int t = 0; t < 64; t += 8) {
-        SSYM_SHA_ROUND(a, b, c, d, e, f, g, hh, KW.kw[t + 0]);
-        SSYM_SHA_ROUND(hh, a, b, c, d, e, f, g, KW.kw[t + 1]);
-        SSYM_SHA_ROUND(g, hh, a, b, c, d, e, f, KW.kw[t + 2]);
-        SSYM_SHA_ROUND(f, g, hh, a, b, c, d, e, KW.kw[t + 3]);
-        SSYM_SHA_ROUND(e, f, g, hh, a, b, c, d, KW.kw[t + 4]);
-        SSYM_SHA_ROUND(d, e, f, g, hh, a, b, c, KW.kw[t + 5]);
-        SSYM_SHA_ROUND(c, d, e, f, g, hh, a, b, KW.kw[t + 6]);
-        SSYM_SHA_ROUND(b, c, d, e, f, g, hh, a, KW.kw[t + 7]);
+        SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, KW.kw[t + 0]);
+        SSYM_SHA_ROUND(A, hh, a, b, c, d, e, f, g, KW.kw[t + 1]);
+        SSYM_SHA_ROUND(A, g, hh, a, b, c, d, e, f, KW.kw[t + 2]);
+        SSYM_SHA_ROUND(A, f, g, hh, a, b, c, d, e, KW.kw[t + 3]);
+        SSYM_SHA_ROUND(A, e, f, g, hh, a, b, c, d, KW.kw[t + 4]);
+        SSYM_SHA_ROUND(A, d, e, f, g, hh, a, b, c, KW.kw[t + 5]);
+        SSYM_SHA_ROUND(A, c, d, e, f, g, hh, a, b, KW.kw[t + 6]);
+        SSYM_SHA_ROUND(A, b, c, d, e, f, g, hh, a, KW.kw[t + 7]);
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+// ---- rolled variants --------------------------------------------------------------------------------------
+// The fully unrolled pair hash is ~2300 instructions = 37 KB of SASS, more than the 32 KB L1.5 instruction cache:
+// ncu shows 11-19 % instruction-cache misses and `no_instruction` stalls in the Merkle kernels.  The rolled form
+// keeps 16 rounds (one period of the rolling message schedule, two rotations of the 8 working variables) unrolled
+// and loops over the four groups, reading K[t] (or K[t]+W[t] of the padding block) from constant memory.
+struct ShaK4 {
+    uint4 v[16];
+};
+static __constant__ ShaK4 c_sha_k4 = {{
+    {0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5}, {0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5},
+    {0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3}, {0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174},
+    {0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc}, {0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da},
+    {0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7}, {0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967},
+    {0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13}, {0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85},
+    {0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3}, {0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070},
+    {0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5}, {0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3},
+    {0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208}, {0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2}}};
+// K[t] + W[t] of the 64-byte padding block (generated from sha_pad64_kw(); checked by a static_assert below)
+static __constant__ ShaK4 c_sha_kwpad4 = {{
+    {0xc28a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5}, {0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5},
+    {0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3}, {0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf374},
+    {0x649b69c1, 0xf0fe4786, 0x0fe1edc6, 0x240cf254}, {0x4fe9346f, 0x6cc984be, 0x61b9411e, 0x16f988fa},
+    {0xf2c65152, 0xa88e5a6d, 0xb019fc65, 0xb9d99ec7}, {0x9a1231c3, 0xe70eeaa0, 0xfdb1232b, 0xc7353eb0},
+    {0x3069bad5, 0xcb976d5f, 0x5a0f118f, 0xdc1eeefd}, {0x0a35b689, 0xde0b7a04, 0x58f4ca9d, 0xe15d5b16},
+    {0x007f3e86, 0x37088980, 0xa507ea32, 0x6fab9537}, {0x17406110, 0x0d8cd6f1, 0xcdaa3b6d, 0xc0bbbe37},
+    {0x83613bda, 0xdb48a363, 0x0b02e931, 0x6fd15ca7}, {0x521afaca, 0x31338431, 0x6ed41a95, 0x6d437890},
+    {0xc39c91f2, 0x9eccabbd, 0xb5c9a0e6, 0x532fb63c}, {0xd2c741c6, 0x07237ea3, 0xa4954b68, 0x4c191d76}}};
+
+#define SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, h, k0, k1, k2, k3) \
+    SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, h, k0)                   \
+    SSYM_SHA_ROUND(A, h, a, b, c, d, e, f, g, k1)                   \
+    SSYM_SHA_ROUND(A, g, h, a, b, c, d, e, f, k2)                   \
+    SSYM_SHA_ROUND(A, f, g, h, a, b, c, d, e, k3)
+
+template <int ADDMODE>
+__device__ __forceinline__ void sha_compress_rolled(uint32_t (&h)[8], uint32_t (&w)[16], const ShaAdd<ADDMODE> A) {
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll 1
+    for (int grp = 0; grp < 4; grp++) {
+        if (grp) {
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                w[i] = A.sch(A.sch(w[i], sig0(w[(i + 1) & 15])), A.sch(w[(i + 9) & 15], sig1(w[(i + 14) & 15])));
+        }
+        const uint4 k0 = c_sha_k4.v[grp * 4 + 0], k1 = c_sha_k4.v[grp * 4 + 1], k2 = c_sha_k4.v[grp * 4 + 2], k3 = c_sha_k4.v[grp * 4 + 3];
+        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.t1(w[0], k0.x), A.t1(w[1], k0.y), A.t1(w[2], k0.z), A.t1(w[3], k0.w));
+        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, A.t1(w[4], k1.x), A.t1(w[5], k1.y), A.t1(w[6], k1.z), A.t1(w[7], k1.w));
+        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.t1(w[8], k2.x), A.t1(w[9], k2.y), A.t1(w[10], k2.z), A.t1(w[11], k2.w));
+        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, A.t1(w[12], k3.x), A.t1(w[13], k3.y), A.t1(w[14], k3.z), A.t1(w[15], k3.w));
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+template <int ADDMODE>
+__device__ __forceinline__ void sha_compress_pad64_rolled(uint32_t (&h)[8], const ShaAdd<ADDMODE> A) {
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll 1
+    for (int grp = 0; grp < 4; grp++) {
+        const uint4 k0 = c_sha_kwpad4.v[grp * 4 + 0], k1 = c_sha_kwpad4.v[grp * 4 + 1], k2 = c_sha_kwpad4.v[grp * 4 + 2], k3 = c_sha_kwpad4.v[grp * 4 + 3];
+        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, k0.x, k0.y, k0.z, k0.w);
+        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, k1.x, k1.y, k1.z, k1.w);
+        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, k2.x, k2.y, k2.z, k2.w);
+        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, k3.x, k3.y, k3.z, k3.w);
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+template <int ADDMODE>
+__device__ __forceinline__ void sha256_64B_rolled(uint32_t (&w)[16], uint32_t (&out)[8], const ShaAdd<ADDMODE> A) {
+    sha_iv(out);
+    sha_compress_rolled<ADDMODE>(out, w, A);
+    sha_compress_pad64_rolled<ADDMODE>(out, A);
 }
 
 // SHA-256 of a 64-byte message given as 16 big-endian words (2 compressions).  Used by
 // sha256_pair (hasher.simf:27-32), channel_mix_u256 (channel.simf:154-162) and the CP leaf
 // (hash_node_m31_cp, hasher.simf:93-97).  `w` is clobbered.
-__device__ __forceinline__ void sha256_64B(uint32_t (&w)[16], uint32_t (&out)[8]) {
+template <int ADDMODE>
+__device__ __forceinline__ void sha256_64B(uint32_t (&w)[16], uint32_t (&out)[8], const ShaAdd<ADDMODE> A) {
     sha_iv(out);
-    sha_compress(out, w);
-    sha_compress_pad64(out);
+    sha_compress<ADDMODE>(out, w, A);
+    sha_compress_pad64<ADDMODE>(out, A);
 }
+__device__ __forceinline__ void sha256_64B(uint32_t (&w)[16], uint32_t (&out)[8]) { sha256_64B<0>(w, out, ShaAdd<0>{1u}); }
 
 // sha256_pair(left, right)
-__device__ __forceinline__ void sha256_pair(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8]) {
+template <int ADDMODE>
+__device__ __forceinline__ void sha256_pair(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8], const ShaAdd<ADDMODE> A) {
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) { w[i] = l[i]; w[8 + i] = r[i]; }
-    sha256_64B(w, out);
+    sha256_64B<ADDMODE>(w, out, A);
 }
+__device__ __forceinline__ void sha256_pair(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8]) { sha256_pair<0>(l, r, out, ShaAdd<0>{1u}); }
 
 // SHA-256 of a short message of `NBYTES` (multiple of 4, <= 52) given as words: one compression.
 // Covers sha256(u256) (32 B), sha256_32 (4 B), trace / QM31 leaves (16 B), channel draws (36 B),
 // channel_mix_u64 (40 B), channel_mix_line_poly (48 B), stark101 channel_mix_32 (36 B).
-template <int NWORDS>
-__device__ __forceinline__ void sha256_short(const uint32_t (&m)[NWORDS], uint32_t (&out)[8]) {
+template <int NWORDS, int ADDMODE>
+__device__ __forceinline__ void sha256_short(const uint32_t (&m)[NWORDS], uint32_t (&out)[8], const ShaAdd<ADDMODE> A) {
     static_assert(NWORDS >= 1 && NWORDS <= 13, "single-block messages only");
     uint32_t w[16];
 #pragma unroll
@@ -152,8 +253,10 @@ __device__ __forceinline__ void sha256_short(const uint32_t (&m)[NWORDS], uint32
     w[NWORDS] = 0x80000000u;
     w[15] = NWORDS * 32u;
     sha_iv(out);
-    sha_compress(out, w);
+    sha_compress<ADDMODE>(out, w, A);
 }
+template <int NWORDS>
+__device__ __forceinline__ void sha256_short(const uint32_t (&m)[NWORDS], uint32_t (&out)[8]) { sha256_short<NWORDS, 0>(m, out, ShaAdd<0>{1u}); }
 
 // SHA-256 of an arbitrary message of `nwords` 32-bit big-endian words, word i supplied by `get(i)`.
 // One compression body in a rolled block loop: compact code for the transcript kernels, where

@@ -2,6 +2,15 @@
 // Kernels of the batched Stwo verifier; see stwo_kernels.cuh for the decomposition.
 #include "stwo_kernels.cuh"
 
+#include <cstdlib>
+
+#ifndef SSYM_DEFAULT_ADDMODE
+#define SSYM_DEFAULT_ADDMODE 1
+#endif
+#ifndef SSYM_DEFAULT_ROLLED
+#define SSYM_DEFAULT_ROLLED 1
+#endif
+
 namespace ssym {
 
 typedef StwoCtxLayout CX;
@@ -407,11 +416,19 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t (&d)[8
     d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
 }
 
-__global__ void __launch_bounds__(128) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type) {
+// Every chain is run by ONE hashing loop, so the kernel contains a single copy of the compression code (the fully
+// unrolled pair hash alone is 37 KB of SASS; several inlined copies thrash the instruction cache).  A chain is a few
+// "pre" steps that produce its first node, then one pair hash per sibling:
+//   trace : pre 0 = SHA-256(4 words)                       hash_node_m31_trace   hasher.simf:85-90
+//   cp    : pre 0 = SHA-256(16 words)                      hash_node_m31_cp      hasher.simf:93-97
+//   fri   : pre 0 = SHA-256(e0), pre 1 = SHA-256(e1), pre 2 = sha256_pair        fri/layers.simf:40-48
+template <int ADDMODE, bool ROLLED>
+__global__ void __launch_bounds__(128) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, uint32_t one) {
+    const ShaAdd<ADDMODE> A{one};
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    // warp -> (chain type rank, group); rank 0 = CP (1 + 2 + 2G compressions... longest), 1 = FRI layer 0,
-    // 2 = trace, 3.. = FRI layers 1..L
+    // warp -> (chain type rank, group); ranks are ordered longest chain first: 0 = CP, 1 = FRI layer 0, 2 = trace,
+    // 3.. = FRI layers 1..L
     const uint32_t rank = warp / groups_per_type, group = warp % groups_per_type;
     if (rank >= L + 3) return;
     const uint32_t item = group * 32 + lane;
@@ -421,72 +438,93 @@ __global__ void __launch_bounds__(128) stwo_merkle_kernel(StwoParams p, uint32_t
     const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
     const uint32_t query = p.ctx[(size_t)i * CX::WORDS + CX::QUERIES + q];
 
-    uint32_t cur[8];
-    const uint32_t *sib, *root;
-    uint32_t n_sib, path, fail_bit, layer = 0;
+    const uint32_t *sib, *root, *msg; // msg: where the chain's leaf data lives
+    uint32_t n_sib, n_pre, path, fail_bit, layer = 0;
+    bool fri_even = true;
     int kind; // 0 trace, 1 cp, 2 fri
     if (rank == 0 || rank == 2) {
-        const uint32_t *qv = pk + lo.off_qvals + 20 * q;
-        if (rank == 2) { // hash_node_m31_trace hasher.simf:85-90: 16-byte leaf
+        msg = pk + lo.off_qvals + 20 * q + (rank == 0 ? 4 : 0);
+        if (rank == 2) {
             kind = 0;
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(qv));
-            const uint32_t m[4] = {v.x, v.y, v.z, v.w};
-            sha256_short<4>(m, cur);
             sib = pk + lo.off_trace_sib + q * G * 8;
             root = pk + lo.off_commit + 8;
             fail_bit = SSYM_ST_TRACE_MERKLE;
-        } else { // hash_node_m31_cp hasher.simf:93-97: 64-byte leaf
+        } else {
             kind = 1;
-            uint32_t w[16];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(qv + 4) + k);
-                w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-            }
-            sha256_64B(w, cur);
             sib = pk + lo.off_cp_sib + q * G * 8;
             root = pk + lo.off_commit + 16;
             fail_bit = SSYM_ST_CP_MERKLE;
         }
+        n_pre = 1;
         n_sib = G;
         path = query + shl32(G & 0xff, 1u); // evals/verify.simf:54,64
-    } else { // verify_decommitment fri/layers.simf:40-48
+    } else {
         kind = 2;
         layer = rank == 1 ? 0 : rank - 2;
         const uint32_t fq = query >> layer;
-        const uint32_t *evp = p.fri_evals + ((size_t)i * (L + 1) * Q + layer * Q + q) * 4;
-        const uint4 ev = *reinterpret_cast<const uint4 *>(evp);
-        const uint4 wt = __ldg(reinterpret_cast<const uint4 *>(pk + lo.off_fri_wit + (layer * Q + q) * 4));
-        const bool even = (fq & 1u) == 0;
-        const uint32_t m0[4] = {even ? ev.x : wt.x, even ? ev.y : wt.y, even ? ev.z : wt.z, even ? ev.w : wt.w};
-        const uint32_t m1[4] = {even ? wt.x : ev.x, even ? wt.y : ev.y, even ? wt.z : ev.z, even ? wt.w : ev.w};
-        uint32_t l0[8], l1[8];
-        sha256_short<4>(m0, l0); // hash_node_qm31 hasher.simf:100-104
-        sha256_short<4>(m1, l1);
-        sha256_pair(l0, l1, cur);
+        msg = pk + lo.off_fri_wit + (layer * Q + q) * 4; // the witness; the evaluation comes from K2's scratch
+        fri_even = (fq & 1u) == 0;                        // adjacent_leaves fri/layers.simf:29-37
+        n_pre = 3;
         n_sib = G - 1 - layer;
         sib = pk + lo.off_fri_sib[layer] + q * n_sib * 8;
         root = layer == 0 ? pk + lo.off_fri_first_root : pk + lo.off_fri_inner_root + 8 * (layer - 1);
         fail_bit = SSYM_ST_FRI_MERKLE(layer);
-        const uint32_t position = fq & ~1u;
-        path = (position + shl32((G - layer) & 0xff, 1u)) >> 1;
+        path = ((fq & ~1u) + shl32((G - layer) & 0xff, 1u)) >> 1;
     }
+    const uint32_t *evp = p.fri_evals + ((size_t)i * (L + 1) * Q + layer * Q + q) * 4;
 
-    // merkle_verify_32 merkle.simf:39-44: fold the siblings, prefetching one level ahead
-    uint32_t nxt[8];
-    if (n_sib) load_digest(sib, nxt);
-#pragma unroll 1
-    for (uint32_t lvl = 0; lvl < n_sib; lvl++) {
-        uint32_t w[16];
-        const bool cur_left = (path & 1u) == 0; // divides_32(2, path): sha256_pair(cur, sib) else (sib, cur)
+    uint32_t cur[8], nxt[8]; // nxt: next sibling (prefetched one level ahead); during the FRI pre steps: the first leaf hash
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            w[k] = cur_left ? cur[k] : nxt[k];
-            w[8 + k] = cur_left ? nxt[k] : cur[k];
+    for (int k = 0; k < 8; k++) cur[k] = nxt[k] = 0;
+    const uint32_t total = n_pre + n_sib;
+#pragma unroll 1
+    for (uint32_t step = 0; step < total; step++) {
+        uint32_t w[16];
+        bool two_blocks = true; // 64-byte message: data block + the constant padding block
+        if (step < n_pre) {
+            if (kind == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(msg) + k);
+                    w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                }
+            } else if (kind == 2 && step == 2) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) { w[k] = nxt[k]; w[8 + k] = cur[k]; }
+            } else { // 16-byte message in one block: trace leaf, or the left (step 0) / right (step 1) FRI leaf
+                const bool take_eval = kind == 2 && ((step == 0) == fri_even);
+                const uint4 v = take_eval ? *reinterpret_cast<const uint4 *>(evp) : __ldg(reinterpret_cast<const uint4 *>(msg));
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                w[4] = 0x80000000u;
+#pragma unroll
+                for (int k = 5; k < 15; k++) w[k] = 0;
+                w[15] = 128u;
+                two_blocks = false;
+                if (kind == 2 && step == 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) nxt[k] = cur[k];
+                }
+            }
+            if (step + 1 == n_pre && n_sib) load_digest(sib, nxt);
+        } else { // merkle_compute_step merkle.simf:22-30
+            const uint32_t lvl = step - n_pre;
+            const bool cur_left = (path & 1u) == 0; // divides_32(2, path): sha256_pair(cur, sib) else (sib, cur)
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                w[k] = cur_left ? cur[k] : nxt[k];
+                w[8 + k] = cur_left ? nxt[k] : cur[k];
+            }
+            if (lvl + 1 < n_sib) load_digest(sib + 8 * (lvl + 1), nxt);
+            path >>= 1;
         }
-        if (lvl + 1 < n_sib) load_digest(sib + 8 * (lvl + 1), nxt);
-        sha256_64B(w, cur);
-        path >>= 1;
+        sha_iv(cur);
+        if (ROLLED) {
+            sha_compress_rolled<ADDMODE>(cur, w, A);
+            if (two_blocks) sha_compress_pad64_rolled<ADDMODE>(cur, A);
+        } else {
+            sha_compress<ADDMODE>(cur, w, A);
+            if (two_blocks) sha_compress_pad64<ADDMODE>(cur, A);
+        }
     }
     uint32_t r[8];
     load_digest(root, r);
@@ -591,7 +629,21 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     if (prof) { prof->end(1, s); prof->begin(2, s); }
     const uint32_t groups = (items + 31) / 32;
     const uint64_t warps = (uint64_t)groups * (L + 3);
-    stwo_merkle_kernel<<<(uint32_t)((warps + 3) / 4), 128, 0, s>>>(p, groups);
+    // tuning knobs (sha256.cuh): which adds go to the FMA pipe, and whether the 64 rounds are rolled into 4 x 16
+    static const int addmode = [] { const char *e = getenv("SSYM_ADDMODE"); return e ? atoi(e) : SSYM_DEFAULT_ADDMODE; }();
+    static const int rolled = [] { const char *e = getenv("SSYM_ROLLED"); return e ? atoi(e) : SSYM_DEFAULT_ROLLED; }();
+    const uint32_t grid = (uint32_t)((warps + 3) / 4);
+#define SSYM_LAUNCH_MERKLE(AM, RL) stwo_merkle_kernel<AM, RL><<<grid, 128, 0, s>>>(p, groups, 1u)
+    switch (addmode * 2 + (rolled ? 1 : 0)) { // `one` = 1 must stay opaque to ptxas
+    case 1: SSYM_LAUNCH_MERKLE(0, true); break;
+    case 2: SSYM_LAUNCH_MERKLE(1, false); break;
+    case 3: SSYM_LAUNCH_MERKLE(1, true); break;
+    case 4: SSYM_LAUNCH_MERKLE(2, false); break;
+    case 5: SSYM_LAUNCH_MERKLE(2, true); break;
+    case 6: SSYM_LAUNCH_MERKLE(3, false); break;
+    case 7: SSYM_LAUNCH_MERKLE(3, true); break;
+    default: SSYM_LAUNCH_MERKLE(0, false); break;
+    }
     if (prof) { prof->end(2, s); prof->begin(3, s); }
     stwo_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
     if (prof) prof->end(3, s);
