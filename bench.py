@@ -30,6 +30,7 @@ COMPRESSIONS_PER_PROOF = 3806      # SURVEY.md section 8d (46 channel + 880 trac
 MERKLE_COMPRESSIONS_PER_PROOF = 3760
 LITERAL_OPS_PER_COMPRESSION = 2296  # FIPS 180-4 literal: 64*26 + 48*13 + 8
 LITERAL_OPS_PER_PROOF = 3806 * 2296 + 65486 * 6 + 55220 * 4
+NCU_DRAM_BYTES_PER_LAUNCH = 58_397_440  # stwo_merkle_kernel at 1024 proofs: 58.25 MB read + 0.15 MB written (profiles/)
 
 
 def log(*a):
@@ -285,8 +286,6 @@ def main():
         step(k)
     finish()
     torch.cuda.synchronize()
-    ver.profile_read()
-    ver.profile_enable(True)
     launches0 = ver.launch_count
     with ClockSampler(local_rank) as clocks:
         if world > 1:
@@ -302,14 +301,29 @@ def main():
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
-    ver.profile_enable(False)
     launches = ver.launch_count - launches0
-    prof = ver.profile_read()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = total_n * args.steps / (ms_max * 1e-3)
+
+    # Per-kernel durations for the roofline: the same steps issued strictly serially (depth 1), with CUDA events around
+    # every kernel on the launching stream (ssym_profile_enable), so each kernel is timed alone on the GPU.
+    ver.set_pipeline_depth(1)
+    ver.profile_read()
+    ver.profile_enable(True)
+    serial_steps = max(3, min(args.steps, 200))
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for k in range(serial_steps):
+        step(k)
+    e3.record(stream)
+    torch.cuda.synchronize()
+    serial_ms_per_step = e2.elapsed_time(e3) / serial_steps
+    ver.profile_enable(False)
+    prof = ver.profile_read()
+    ver.set_pipeline_depth(depth)
 
     # correctness of what was timed (outside the timed region): every rank's statuses against the oracle on a slice
     status = statuses[(args.steps - 1) % depth]
@@ -334,6 +348,17 @@ def main():
     host_view = pinned.numpy().view(np.uint32)
     acc_host = torch.empty((n + 31) // 32, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     ver.set_stream(None)
+    pin_t = torch.empty(host_batch.size, dtype=torch.int32, device="cuda")
+    pin_t.copy_(pinned, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        pin_t.copy_(pinned, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 5 * host_batch.nbytes / (c0.elapsed_time(c1) * 1e-3) / 1e9  # plain pinned H2D copy of the same batch: the PCIe ceiling of e2e
+    del pin_t
     e2e_steps = max(5, min(args.steps, 100))
     for _ in range(3):
         ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc_host)
@@ -374,11 +399,17 @@ def main():
             "merkle_hashes_per_s": value * MERKLE_COMPRESSIONS_PER_PROOF / 2.0,
             "sha256_compressions_per_s": value * COMPRESSIONS_PER_PROOF,
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n * lo.stride_words * 4), "d2h_bytes_per_step": int(acc_host.nbytes),
-                    "steps": e2e_steps, "note": "ssym_stwo_verify_batch(SSYM_MEM_HOST): pinned host batch -> chunked double-buffered H2D -> kernels -> D2H bitmap"},
+                    "steps": e2e_steps, "h2d_gbs_achieved": e2e_value / world * lo.stride_words * 4 / 1e9, "h2d_gbs_plain_copy": h2d_gbs,
+                    "note": "ssym_stwo_verify_batch(SSYM_MEM_HOST): pinned host batch -> chunked double-buffered H2D -> kernels -> D2H bitmap; "
+                            "bound by the host link: compare h2d_gbs_achieved with a plain pinned copy of the same bytes"},
             "gpu_launches": int(launches),
-            "kernel_ms": kernel_ms,
+            "kernel_ms": kernel_ms, "serial_ms_per_step": serial_ms_per_step,
+            "kernel_ms_note": "per-launch CUDA-event durations from a strictly serial pass (pipeline depth 1) of the same steps; the headline "
+                              "`value` keeps `pipeline` batches in flight so kernels of consecutive steps overlap",
             "roofline": {"bound": "hbm", "kernel": "stwo_merkle_kernel", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": hbm_achieved / hbm_peak if hbm_peak else None, "traffic": None, "peak_source": peak_src,
+                         "frac": hbm_achieved / hbm_peak if hbm_peak else None,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == 1024 else None, "traffic_source": "profiles/r01_merkle_ncu_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture, 1024 proofs per launch)",
+                         "algorithmic_bytes_per_launch": n * ALG_BYTES_PER_PROOF, "peak_source": peak_src,
                          "kernel_share_of_step": share, "avg_launch_ms": mk_avg_ms,
                          "note": "the kernel is INT32-ALU bound (170 int-ops per byte), not HBM bound: see roofline_int32"},
             "roofline_int32": {"bound": "int32_alu", "kernel": "stwo_merkle_kernel", "achieved": lit_ops / 1e12, "peak": int32_ops / 1e12, "unit": "Tops/s",

@@ -214,7 +214,7 @@ int ssym_join(ssym_ctx_t *ctx);
 uint64_t ssym_launch_count(const ssym_ctx_t *ctx);
 
 /* Per-kernel device timing (CUDA events recorded around every verifier kernel on the launching stream).
- * Kernel ids: 0 stwo transcript, 1 stwo query, 2 stwo merkle, 3 stwo finalize, 4 stark101 transcript,
+ * Kernel ids: 0 stwo channel, 1 stwo query, 2 stwo merkle, 3 stwo finalize, 4 stark101 transcript,
  * 5 stark101 merkle, 6 stark101 finalize.  ssym_profile_read synchronises the stream, adds up the elapsed
  * time and launch count per kernel id since the last read (arrays of SSYM_PROFILE_KERNELS) and resets. */
 #define SSYM_PROFILE_KERNELS 8

@@ -86,7 +86,7 @@ class Verifier:
     def launch_count(self) -> int:
         return int(self.lib.ssym_launch_count(self.h))
 
-    KERNEL_NAMES = ("stwo_transcript", "stwo_query", "stwo_merkle", "stwo_finalize", "s101_transcript", "s101_merkle", "s101_finalize", "other")
+    KERNEL_NAMES = ("stwo_channel", "stwo_query", "stwo_merkle", "stwo_finalize", "s101_transcript", "s101_merkle", "s101_finalize", "other")
 
     def profile_enable(self, on: bool = True) -> None:
         """Record CUDA events around every verifier kernel on the launching stream."""
