@@ -30,7 +30,7 @@ COMPRESSIONS_PER_PROOF = 3806      # SURVEY.md section 8d (46 channel + 880 trac
 MERKLE_COMPRESSIONS_PER_PROOF = 3760
 LITERAL_OPS_PER_COMPRESSION = 2296  # FIPS 180-4 literal: 64*26 + 48*13 + 8
 LITERAL_OPS_PER_PROOF = 3806 * 2296 + 65486 * 6 + 55220 * 4
-NCU_DRAM_BYTES_PER_LAUNCH = 58_397_440  # stwo_merkle_kernel at 1024 proofs: 58.25 MB read + 0.15 MB written (profiles/)
+NCU_DRAM_BYTES_PER_LAUNCH = 58_279_936  # stwo_merkle_kernel at 1024 proofs: 58.09 MB read + 0.19 MB written (profiles/r01_ncu_summary.md)
 
 
 def log(*a):
@@ -408,7 +408,7 @@ def main():
                               "`value` keeps `pipeline` batches in flight so kernels of consecutive steps overlap",
             "roofline": {"bound": "hbm", "kernel": "stwo_merkle_kernel", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_achieved / hbm_peak if hbm_peak else None,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == 1024 else None, "traffic_source": "profiles/r01_merkle_ncu_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture, 1024 proofs per launch)",
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == 1024 else None, "traffic_source": "profiles/r01_ncu_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture, 1024 proofs per launch)",
                          "algorithmic_bytes_per_launch": n * ALG_BYTES_PER_PROOF, "peak_source": peak_src,
                          "kernel_share_of_step": share, "avg_launch_ms": mk_avg_ms,
                          "note": "the kernel is INT32-ALU bound (170 int-ops per byte), not HBM bound: see roofline_int32"},

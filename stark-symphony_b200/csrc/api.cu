@@ -110,6 +110,9 @@ struct ssym_ctx {
     DevBuf s101_ctx;
     // jets staging
     DevBuf tmp[6];
+    // twiddle-inverse tables of ssym_circle_fold / ssym_line_fold, per log_size (built on first use when the call is big enough to pay for it)
+    DevBuf fold_table[2][32];
+    bool fold_table_ready[2][32] = {{false}};
 };
 
 static const size_t STWO_DEVICE_CHUNK = 32768; // proofs per launch group (bounds scratch: ~3 KB / proof)
@@ -160,6 +163,8 @@ void ssym_destroy(ssym_ctx_t *c) {
                       &c->d_accept, &c->d_status, &c->d_trace, &c->d_offsets, &c->s101_ctx};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : c->tmp) b.release();
+    for (auto &row : c->fold_table)
+        for (DevBuf &b : row) b.release();
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(c->ev_h2d[i]);
         cudaEventDestroy(c->ev_done[i]);
@@ -520,7 +525,20 @@ static int fold_impl(ssym_ctx_t *c, bool circle, const uint32_t *position, const
     uint32_t *dout = st.out(out, 4 * n);
     uint8_t *dfail = st.out(failp, n);
     if (st.err) return st.finish();
-    launch_fold(circle, dp, da, db, dal, log_size, dout, dfail, n, c->stream);
+    // The twiddle 1/y (1/x) depends only on (log_size, position): for calls with at least as many elements as the domain has
+    // positions, look it up in a table built once with the literal functions instead of recomputing ~300 M31 products per element.
+    const uint32_t *table = nullptr;
+    if (log_size >= 1 && log_size <= 24 && n >= ((size_t)1 << log_size)) {
+        const int t = circle ? 0 : 1;
+        if (!c->fold_table_ready[t][log_size]) {
+            CUDA_TRY(c->fold_table[t][log_size].ensure(sizeof(uint32_t) << log_size));
+            launch_fold_table(circle, log_size, c->fold_table[t][log_size].as<uint32_t>(), c->stream);
+            c->launches += 1;
+            c->fold_table_ready[t][log_size] = true;
+        }
+        table = c->fold_table[t][log_size].as<uint32_t>();
+    }
+    launch_fold(circle, dp, da, db, dal, log_size, table, dout, dfail, n, c->stream);
     c->launches += n ? 1 : 0;
     return st.finish();
 }

@@ -118,17 +118,45 @@ void launch_circle_point(const uint32_t *index, uint32_t *out_xy, size_t n, cuda
 // ---- circle_fold / line_fold (fri/folding.simf:15-41) ---------------------------------------------------
 // The twiddle (1/y or 1/x of the domain point at the bit-reversed position) is recomputed per element with the
 // literal 32-step double-and-add + addition-chain inverse: 4 B of position in, no table traffic.
+// twiddle_inv(position) = m31_inv(y or x of the domain point at bit_reverse_position(position, log_size)), literal.
+template <bool CIRCLE>
+__device__ __forceinline__ M31 fold_twiddle_inv(uint32_t position, uint32_t log_size, bool &f) {
+    const uint32_t pos = bit_reverse_position(position, log_size);
+    M31 v;
+    if (CIRCLE) v = circle_point_index_to_m31_point(circle_position_to_point_index(log_size, pos)).y;
+    else v = circle_point_index_to_m31_point(line_position_to_point_index(log_size, pos)).x;
+    return m31_inv(v, f);
+}
+// Table of twiddle inverses for every position < 2^log_size (built with the literal functions, so lookups are bit-identical).
+template <bool CIRCLE>
+__global__ void __launch_bounds__(256) fold_table_kernel(uint32_t log_size, uint32_t *table) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1u << log_size)) return;
+    bool f = false;
+    const M31 inv = fold_twiddle_inv<CIRCLE>(t, log_size, f);
+    table[t] = inv; // inv == 0 <=> the coordinate was 0 (the .simf assert): lookups re-derive the flag from that
+}
+void launch_fold_table(bool circle, uint32_t log_size, uint32_t *table, cudaStream_t s) {
+    const uint32_t n = 1u << log_size;
+    if (circle) fold_table_kernel<true><<<(n + 255) / 256, 256, 0, s>>>(log_size, table);
+    else fold_table_kernel<false><<<(n + 255) / 256, 256, 0, s>>>(log_size, table);
+}
+
 template <bool CIRCLE>
 __global__ void __launch_bounds__(256) fold_kernel(const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p,
-                                                   const uint32_t *alpha, uint32_t log_size, uint32_t *out, uint8_t *fail, size_t n) {
+                                                   const uint32_t *alpha, uint32_t log_size, const uint32_t *table, uint32_t *out,
+                                                   uint8_t *fail, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t pos = bit_reverse_position(position[i], log_size);
-        M31 v;
-        if (CIRCLE) v = circle_point_index_to_m31_point(circle_position_to_point_index(log_size, pos)).y;
-        else v = circle_point_index_to_m31_point(line_position_to_point_index(log_size, pos)).x;
         bool f = false;
-        const M31 inv = m31_inv(v, f);
+        const uint32_t position_i = position[i];
+        M31 inv;
+        if (table && position_i < (1u << log_size)) {
+            inv = __ldg(table + position_i);
+            f = inv == 0;
+        } else {
+            inv = fold_twiddle_inv<CIRCLE>(position_i, log_size, f);
+        }
         const QM31 a = qm31_load4(f_p + 4 * i), b = qm31_load4(f_neg_p + 4 * i);
         const QM31 f0 = qm31_add(a, b);
         const QM31 f1 = qm31_mul_m31(qm31_sub(a, b), inv);
@@ -137,10 +165,10 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint32_t *position, con
     }
 }
 void launch_fold(bool circle, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p, const uint32_t *alpha,
-                 uint32_t log_size, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s) {
+                 uint32_t log_size, const uint32_t *table, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s) {
     if (!n) return;
-    if (circle) fold_kernel<true><<<stream_grid(n, 256), 256, 0, s>>>(position, f_p, f_neg_p, alpha, log_size, out, fail, n);
-    else fold_kernel<false><<<stream_grid(n, 256), 256, 0, s>>>(position, f_p, f_neg_p, alpha, log_size, out, fail, n);
+    if (circle) fold_kernel<true><<<stream_grid(n, 256), 256, 0, s>>>(position, f_p, f_neg_p, alpha, log_size, table, out, fail, n);
+    else fold_kernel<false><<<stream_grid(n, 256), 256, 0, s>>>(position, f_p, f_neg_p, alpha, log_size, table, out, fail, n);
 }
 
 // ---- hashing ----------------------------------------------------------------------------------------------
@@ -152,24 +180,28 @@ __device__ __forceinline__ void st_digest(uint32_t *dst, const uint32_t (&d)[8])
     reinterpret_cast<uint4 *>(dst)[0] = make_uint4(d[0], d[1], d[2], d[3]);
     reinterpret_cast<uint4 *>(dst)[1] = make_uint4(d[4], d[5], d[6], d[7]);
 }
-__global__ void __launch_bounds__(128) sha256_pair_kernel(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n) {
+__global__ void __launch_bounds__(128) sha256_pair_kernel(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, uint32_t one) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t l[8], r[8], o[8];
+    const ShaAdd<1> A{one};
+    uint32_t l[8], r[8], o[8], w[16];
     ld_digest(left + 8 * i, l);
     ld_digest(right + 8 * i, r);
-    sha256_pair(l, r, o);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { w[k] = l[k]; w[8 + k] = r[k]; }
+    sha256_64B_rolled<1>(w, o, A);
     st_digest(out + 8 * i, o);
 }
 void launch_sha256_pair(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, cudaStream_t s) {
-    if (n) sha256_pair_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(left, right, out, n);
+    if (n) sha256_pair_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(left, right, out, n, 1u);
 }
 
 // merkle_verify_32 (merkle.simf:39-44) for n paths of equal depth: one thread per path, sibling i+1 prefetched
 // while level i is hashed.  32*depth + 68 bytes in, <= 36 bytes + 1 bit out per path, 2*depth compressions.
 __global__ void __launch_bounds__(128) merkle_path_kernel(const uint32_t *leaf, const uint32_t *auth_path, const uint32_t *siblings,
                                                           uint32_t depth, const uint32_t *expected_root, uint32_t *out_root,
-                                                          uint32_t *out_path, uint32_t *ok_bits, size_t n) {
+                                                          uint32_t *out_path, uint32_t *ok_bits, size_t n, uint32_t one) {
+    const ShaAdd<1> A{one}; // adds on the FMA pipe, rounds rolled 4 x 16: same hashing core as stwo_merkle_kernel
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     const size_t ii = active ? i : 0;
@@ -188,7 +220,7 @@ __global__ void __launch_bounds__(128) merkle_path_kernel(const uint32_t *leaf, 
             w[8 + k] = cur_left ? nxt[k] : cur[k];
         }
         if (lvl + 1 < depth) ld_digest(sib + 8 * (lvl + 1), nxt);
-        sha256_64B(w, cur);
+        sha256_64B_rolled<1>(w, cur, A);
         path >>= 1;
     }
     bool ok = path == 1u;
@@ -208,7 +240,7 @@ __global__ void __launch_bounds__(128) merkle_path_kernel(const uint32_t *leaf, 
 void launch_merkle_path(const uint32_t *leaf, const uint32_t *auth_path, const uint32_t *siblings, uint32_t depth,
                         const uint32_t *expected_root, uint32_t *out_root, uint32_t *out_path, uint32_t *ok_bits, size_t n,
                         cudaStream_t s) {
-    if (n) merkle_path_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(leaf, auth_path, siblings, depth, expected_root, out_root, out_path, ok_bits, n);
+    if (n) merkle_path_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(leaf, auth_path, siblings, depth, expected_root, out_root, out_path, ok_bits, n, 1u);
 }
 
 // ---- channel transitions (channel.simf:36-172, fri/queries.simf:14-43); state = digest[8] | n_sent ----------

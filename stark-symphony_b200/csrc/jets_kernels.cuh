@@ -16,8 +16,9 @@ enum { CHAN_MIX_U256 = 0, CHAN_MIX_U64, CHAN_DRAW_QM31, CHAN_DRAW_QUERIES };
 
 int launch_field_jet(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s);
 void launch_circle_point(const uint32_t *index, uint32_t *out_xy, size_t n, cudaStream_t s);
+void launch_fold_table(bool circle, uint32_t log_size, uint32_t *table, cudaStream_t s);
 void launch_fold(bool circle, const uint32_t *position, const uint32_t *f_p, const uint32_t *f_neg_p, const uint32_t *alpha,
-                 uint32_t log_size, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s);
+                 uint32_t log_size, const uint32_t *table, uint32_t *out, uint8_t *fail, size_t n, cudaStream_t s);
 void launch_sha256_pair(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, cudaStream_t s);
 void launch_merkle_path(const uint32_t *leaf, const uint32_t *auth_path, const uint32_t *siblings, uint32_t depth,
                         const uint32_t *expected_root, uint32_t *out_root, uint32_t *out_path, uint32_t *ok_bits, size_t n,

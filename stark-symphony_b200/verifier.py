@@ -104,7 +104,7 @@ class Verifier:
             import torch
 
             tdt = {np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]  # bit patterns; torch has no general uint32 ops
-            return torch.zeros(shape, dtype=tdt, device=like.device)
+            return torch.empty(shape, dtype=tdt, device=like.device)  # every output element is written by the kernels
         return np.zeros(shape, dtype=dtype)
 
     @staticmethod
