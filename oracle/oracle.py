@@ -90,7 +90,7 @@ def build(force: bool = False) -> str:
     """Compile liboracle.so from oracle/ssym_oracle.c (gcc).  Building the checker is not using it."""
     src = os.path.join(_HERE, "ssym_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "ssym.h")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(os.path.join(_HERE, "stwo_prover_ref.c"))):
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     return _LIB_PATH
 
@@ -313,6 +313,31 @@ class Oracle:
         self.lib.oracle_stwo_verify_batch(C.byref(cfg), ptr(packed), begin, end, ptr(accept), ptr(status),
                                           C.cast(traces, C.c_void_p) if want_trace else None)
         return accept, status, traces
+
+    def stwo_prove_batch(self, cfg: StwoConfig, seeds, threads: int = 1) -> np.ndarray:
+        """CPU reference prover (oracle/stwo_prover_ref.c): one packed proof per seed, shape (n, stride_words)."""
+        lo = self.stwo_layout(cfg)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        n = len(seeds)
+        out = np.zeros((n, lo.stride_words), dtype=np.uint32)
+        fn = self.lib.oracle_stwo_prove_batch
+        fn.restype = C.c_int
+        sp = seeds.ctypes.data_as(C.POINTER(C.c_uint64))
+
+        def run(b, e):
+            return fn(C.byref(cfg), sp, C.c_size_t(b), C.c_size_t(e), ptr(out))
+
+        if threads <= 1 or n <= 1:
+            rcs = [run(0, n)]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            threads = min(threads, n)
+            cuts = [n * i // threads for i in range(threads + 1)]
+            with ThreadPoolExecutor(threads) as ex:
+                rcs = list(ex.map(lambda i: run(cuts[i], cuts[i + 1]), range(threads)))
+        if any(rcs):
+            raise RuntimeError(f"reference prover failed its own low-degree checks: {rcs}")
+        return out
 
     def s101_verify_batch(self, blob: np.ndarray, offsets: np.ndarray, want_trace: bool = False):
         n = len(offsets) - 1

@@ -1270,3 +1270,6 @@ EXPORT int oracle_s101_fri_read_commitment(uint32_t *st, const uint32_t *root, u
 }
 EXPORT size_t oracle_sizeof_stwo_trace(void) { return sizeof(ssym_stwo_trace_t); }
 EXPORT size_t oracle_sizeof_s101_trace(void) { return sizeof(ssym_s101_trace_t); }
+
+/* CPU reference prover for the wide-Fibonacci AIR (test infrastructure; the checker of the GPU prover). */
+#include "stwo_prover_ref.c"
