@@ -41,6 +41,7 @@ extern "C" {
 #define SSYM_ERR_CUDA (-2)
 #define SSYM_ERR_PARSE (-3)
 #define SSYM_ERR_NOMEM (-4)
+#define SSYM_ERR_INTERNAL (-5)
 
 #define SSYM_MEM_DEVICE 0
 #define SSYM_MEM_HOST 1
@@ -241,6 +242,25 @@ int ssym_stwo_verify_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const
 int ssym_stark101_verify_batch(ssym_ctx_t *ctx, const uint32_t *blob, const uint64_t *offsets,
                                size_t n, uint32_t *accept_bits, uint32_t *status,
                                ssym_s101_trace_t *trace, int memspace);
+
+/* ------------------------------------------------------------------------- */
+/* Batched prover for the AIR verify_proof checks */
+/* ------------------------------------------------------------------------- */
+
+/* Proves n instances of the wide-Fibonacci AIR of stwo-verifier/src/constraints/wide_fibonacci.simf:24-62
+ * (trace of 2^trace_log rows: c0 = 1, c1 = SplitMix64(seed, row) mod p, c2 = c0^2 + c1^2, c3 = c1^2 + c2^2) and
+ * writes n packed proofs (ssym_stwo_layout) that ssym_stwo_verify_batch accepts in SSYM_MODE_PROVER_CONSISTENT:
+ * trace / composition commitments (evals/commit.simf:20-35), samples at the OODS point and its double
+ * (deep/oods.simf:44-64, evals/composition_poly.simf:47-59), DEEP quotient (fri/answers.simf:97-129 with
+ * Appendix A item 1), circle + line FRI layers (fri/commit.simf:72-85, fri/folding.simf:15-41), proof of work
+ * (pow.simf:22-35; the smallest passing nonce) and the decommitments of the drawn queries.  The reference has no
+ * prover (its fixtures come from an external fork): this exists so that BASELINE configs 3 and 5 can run on
+ * DISTINCT proofs.  Requires n_fri_layers == trace_log - 1 and trace_log < lde_log <= 13 (both presets).
+ *  seeds      : n u64, in `memspace`
+ *  packed_out : n * layout.stride_words u32 words, in `memspace`
+ * Synchronous (returns after the proofs are written).  cfg->mode is ignored. */
+int ssym_stwo_prove_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const uint64_t *seeds, size_t n,
+                          uint32_t *packed_out, int memspace);
 
 /* ------------------------------------------------------------------------- */
 /* Element-wise jets / .simf functions (parity + config-4 microbenchmarks)    */

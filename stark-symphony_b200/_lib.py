@@ -82,6 +82,7 @@ SYMBOLS = {
     "ssym_profile_read": (_I, [_V, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ssym_stwo_verify_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _V, _V, _I]),
     "ssym_stark101_verify_batch": (_I, [_V, _V, _V, _SZ, _V, _V, _V, _I]),
+    "ssym_stwo_prove_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _I]),
     "ssym_m31_add": (_I, [_V, _V, _V, _V, _SZ, _I]),
     "ssym_m31_sub": (_I, [_V, _V, _V, _V, _SZ, _I]),
     "ssym_m31_neg": (_I, [_V, _V, _V, _SZ, _I]),

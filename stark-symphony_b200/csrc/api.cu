@@ -10,6 +10,7 @@
 
 #include "../../include/ssym.h"
 #include "jets_kernels.cuh"
+#include "prover_kernels.cuh"
 #include "s101_kernels.cuh"
 #include "stwo_kernels.cuh"
 
@@ -106,6 +107,10 @@ struct ssym_ctx {
     uint32_t fold_off[SSYM_MAX_FRI_LAYERS] = {0};
     // host-memspace staging
     DevBuf stage[2], d_accept, d_status, d_trace, d_offsets;
+    // prover: twiddle tables per (trace_log, lde_log) and per-chunk scratch
+    DevBuf prv_tw[2], prv_itw[2], prv_vanish, prv_flag, prv_seeds, prv_out;
+    DevBuf prv_scratch[9];
+    uint32_t prv_T = 0, prv_G = 0;
     // stark101 scratch
     DevBuf s101_ctx;
     // jets staging
@@ -163,6 +168,9 @@ void ssym_destroy(ssym_ctx_t *c) {
                       &c->d_accept, &c->d_status, &c->d_trace, &c->d_offsets, &c->s101_ctx};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : c->tmp) b.release();
+    for (DevBuf &b : c->prv_scratch) b.release();
+    for (int i = 0; i < 2; i++) { c->prv_tw[i].release(); c->prv_itw[i].release(); }
+    c->prv_vanish.release(); c->prv_flag.release(); c->prv_seeds.release(); c->prv_out.release();
     for (auto &row : c->fold_table)
         for (DevBuf &b : row) b.release();
     for (int i = 0; i < 2; i++) {
@@ -377,6 +385,104 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_stwo_trace_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    return SSYM_OK;
+}
+
+/* ---- Stwo prover ------------------------------------------------------------------------------------ */
+static uint32_t m31_pow2_inv(uint32_t n) { /* 2^-n mod p = 2^(31 - n mod 31) mod p */
+    return 1u << ((31u - n % 31u) % 31u);
+}
+
+extern "C" int ssym_stwo_prove_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint64_t *seeds, size_t n, uint32_t *packed_out,
+                                     int memspace) {
+    if (!c || !cfg || ((!seeds || !packed_out) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    ssym_stwo_layout_t lo;
+    int rc = ssym_stwo_layout(cfg, &lo);
+    if (rc) return rc;
+    const uint32_t T = cfg->trace_log, G = cfg->lde_log, L = cfg->n_fri_layers;
+    if (T < 2 || G <= T || G > SSYM_PRV_MAX_LOG || L != T - 1)
+        return fail(SSYM_ERR_USAGE, "prover needs 2 <= trace_log < lde_log <= 13 and n_fri_layers == trace_log - 1 (both presets of config.simf do)");
+    if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    if (n == 0) return SSYM_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = ensure_tables(c, *cfg);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    if (c->prv_T != T || c->prv_G != G) {
+        const uint32_t logs[2] = {T, G};
+        for (int d = 0; d < 2; d++) {
+            CUDA_TRY(c->prv_tw[d].ensure(sizeof(uint32_t) << logs[d]));
+            CUDA_TRY(c->prv_itw[d].ensure(sizeof(uint32_t) << logs[d]));
+            launch_prv_tables(logs[d], c->prv_tw[d].as<uint32_t>(), c->prv_itw[d].as<uint32_t>(), s);
+        }
+        CUDA_TRY(c->prv_vanish.ensure(sizeof(uint32_t) << G));
+        launch_prv_vanish(T, G, c->tab_point.as<uint2>(), c->prv_vanish.as<uint32_t>(), s);
+        CUDA_TRY(c->prv_flag.ensure(sizeof(uint32_t)));
+        c->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        c->prv_T = T;
+        c->prv_G = G;
+    }
+    PrvParams p;
+    memset(&p, 0, sizeof p);
+    p.cfg = *cfg;
+    p.lo = lo;
+    p.tr = PrvDomain{c->prv_tw[0].as<uint32_t>(), c->prv_itw[0].as<uint32_t>(), T, m31_pow2_inv(T)};
+    p.lde = PrvDomain{c->prv_tw[1].as<uint32_t>(), c->prv_itw[1].as<uint32_t>(), G, m31_pow2_inv(G)};
+    p.point = c->tab_point.as<uint2>();
+    p.vanish_inv = c->prv_vanish.as<uint32_t>();
+    const size_t NT = (size_t)1 << T, NG = (size_t)1 << G;
+    uint32_t fo = 0, to = 0;
+    for (uint32_t l = 0; l <= L + 1; l++) { p.fev_off[l] = fo; fo += 4u * (uint32_t)(NG >> l); }
+    p.fev_stride = fo;
+    for (uint32_t l = 0; l <= L; l++) { p.ftree_off[l] = to; to += 8u * 2u * (uint32_t)(NG >> l); }
+    p.ftree_stride = to;
+    // words of scratch per proof, per buffer
+    const size_t per[9] = {PrvCtx::WORDS, 4 * NT, 4 * NG, 8 * NT, 16 * NG, 16 * NG, 16 * NG, p.fev_stride, p.ftree_stride};
+    size_t per_total = 0;
+    for (size_t w : per) per_total += w * 4;
+    size_t chunk = std::max<size_t>(1, std::min<size_t>({n, (size_t)4096, ((size_t)8 << 30) / per_total}));
+    for (int b = 0; b < 9; b++) CUDA_TRY(c->prv_scratch[b].ensure(chunk * per[b] * 4));
+    p.pctx = c->prv_scratch[0].as<uint32_t>();
+    p.tcoef = c->prv_scratch[1].as<uint32_t>();
+    p.tlde = c->prv_scratch[2].as<uint32_t>();
+    p.cpcoef = c->prv_scratch[3].as<uint32_t>();
+    p.cplde = c->prv_scratch[4].as<uint32_t>();
+    p.tree_t = c->prv_scratch[5].as<uint32_t>();
+    p.tree_c = c->prv_scratch[6].as<uint32_t>();
+    p.fev = c->prv_scratch[7].as<uint32_t>();
+    p.ftree = c->prv_scratch[8].as<uint32_t>();
+    p.flag = c->prv_flag.as<uint32_t>();
+    CUDA_TRY(cudaMemsetAsync(p.flag, 0, sizeof(uint32_t), s));
+    const size_t stride_b = (size_t)lo.stride_words * 4;
+    if (memspace == SSYM_MEM_HOST) {
+        CUDA_TRY(c->prv_seeds.ensure(chunk * sizeof(uint64_t)));
+        CUDA_TRY(c->prv_out.ensure(chunk * stride_b));
+    }
+    for (size_t done = 0; done < n; done += chunk) {
+        const size_t m = std::min(chunk, n - done);
+        if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(cudaMemcpyAsync(c->prv_seeds.p, seeds + done, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            p.seeds = c->prv_seeds.as<uint64_t>();
+            p.out = c->prv_out.as<uint32_t>();
+        } else {
+            p.seeds = seeds + done;
+            p.out = packed_out + done * (size_t)lo.stride_words;
+        }
+        p.m = (uint32_t)m;
+        CUDA_TRY(cudaMemsetAsync(p.out, 0, m * stride_b, s)); // alignment padding of the record is zero, as in the packers
+        launch_prv_prove(p, s, &c->launches);
+        CUDA_TRY(cudaGetLastError());
+        if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(cudaMemcpyAsync(packed_out + done * (size_t)lo.stride_words, p.out, m * stride_b, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+    }
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, p.flag, sizeof flag, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag) return fail(SSYM_ERR_INTERNAL, flag & 1u ? "prover self-check failed: a committed polynomial exceeds its degree bound"
+                                                       : "prover hit a zero inverse / exhausted channel draw");
     return SSYM_OK;
 }
 

@@ -1,6 +1,8 @@
 // SPDX-License-Identifier: MIT
 // Kernels of the batched Stwo verifier; see stwo_kernels.cuh for the decomposition.
 #include "stwo_kernels.cuh"
+#include "channel.cuh"
+#include "deep.cuh"
 
 #include <cstdlib>
 
@@ -14,74 +16,6 @@
 namespace ssym {
 
 typedef StwoCtxLayout CX;
-
-// ------------------------------------------------------------------------------------------
-// Transcript helpers (K1).  The compression function is deliberately NOT inlined here: a
-// transcript is ~46 dependent compressions per proof, so one hot copy in the I-cache beats
-// 46 cold ones.
-// ------------------------------------------------------------------------------------------
-__device__ __noinline__ void sha_compress_call(uint32_t *h, const uint32_t *blk) {
-    uint32_t hh[8], w[16];
-#pragma unroll
-    for (int i = 0; i < 8; i++) hh[i] = h[i];
-#pragma unroll
-    for (int i = 0; i < 16; i++) w[i] = blk[i];
-    sha_compress(hh, w);
-#pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = hh[i];
-}
-
-// SHA-256 of (a[0..na) || b[0..nb)) big-endian words.
-__device__ __noinline__ void sha256_2part(const uint32_t *a, int na, const uint32_t *b, int nb, uint32_t *out) {
-    uint32_t h[8];
-    sha_iv(h);
-    const int nwords = na + nb;
-    const int nblocks = (nwords + 3 + 15) >> 4;
-    for (int blk = 0; blk < nblocks; blk++) {
-        uint32_t w[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const int i = blk * 16 + j;
-            uint32_t v = 0;
-            if (i < na) v = a[i];
-            else if (i < nwords) v = b[i - na];
-            else if (i == nwords) v = 0x80000000u;
-            else if (i == nblocks * 16 - 1) v = (uint32_t)nwords * 32u;
-            w[j] = v;
-        }
-        sha_compress_call(h, w);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = h[i];
-}
-
-struct Channel { // channel.simf:18-22 ChannelState = (u256 digest, u32 n_sent)
-    uint32_t d[8];
-    uint32_t n_sent;
-};
-__device__ __forceinline__ void channel_draw_u256(Channel &c, uint32_t *out) { // channel.simf:36-44
-    uint32_t ns = c.n_sent;
-    sha256_2part(c.d, 8, &ns, 1, out);
-    c.n_sent = c.n_sent + 1u;
-}
-__device__ __forceinline__ void channel_mix(Channel &c, const uint32_t *in, int nwords) { // channel.simf:154-173, fri/commit.simf:48-57, deep/oods.simf:23-39
-    uint32_t out[8];
-    sha256_2part(c.d, 8, in, nwords, out);
-#pragma unroll
-    for (int i = 0; i < 8; i++) c.d[i] = out[i];
-    c.n_sent = 0;
-}
-// channel_draw_qm31 = channel_draw_m31x4 (channel.simf:115-141): retry (<= 256 draws) until the first four words are < 2p
-__device__ __noinline__ QM31 channel_draw_qm31(Channel &c, bool &exhausted) {
-    uint32_t w[8];
-    bool ok = false;
-    for (int counter = 0; counter < 256 && !ok; counter++) {
-        channel_draw_u256(c, w);
-        ok = w[0] < 4294967294u && w[1] < 4294967294u && w[2] < 4294967294u && w[3] < 4294967294u;
-    }
-    exhausted = exhausted || !ok;
-    return qm31(m31_reduce(w[0]), m31_reduce(w[1]), m31_reduce(w[2]), m31_reduce(w[3]));
-}
 
 // ------------------------------------------------------------------------------------------
 // K1: the Fiat-Shamir channel of verify_proof (verifier.simf:36-51).  The channel state only ever
@@ -183,23 +117,6 @@ __device__ QM31 cp_from_partitions(QM31 c0, QM31 c1, QM31 c2, QM31 c3) {
     return res;
 }
 
-struct LineCoeffs {
-    QM31 a, b, c;
-};
-// deep_quotient_interpolant_coefficients                      deep/quotients.simf:25-35
-__device__ __noinline__ LineCoeffs interpolant_coefficients(QM31 py, QM31 sv, QM31 alpha_i) {
-    QM31 a = qm31c(cm31(0, 0), cm31_neg(cm31_dbl(sv.i)));
-    QM31 b = qm31c(cm31(0, 0), cm31_neg(cm31_dbl(py.i)));
-    QM31 a_py = qm31_mul(a, py);
-    QM31 b_val = qm31_mul(b, sv);
-    QM31 c = qm31_sub(b_val, a_py);
-    LineCoeffs r;
-    r.a = qm31_mul(alpha_i, a);
-    r.b = qm31_mul(alpha_i, b);
-    r.c = qm31_mul(alpha_i, c);
-    return r;
-}
-
 __device__ __forceinline__ QM31 qm31_shfl(QM31 v, int src) {
     return qm31(__shfl_sync(0xffffffffu, v.r.a, src), __shfl_sync(0xffffffffu, v.r.b, src), __shfl_sync(0xffffffffu, v.i.a, src),
                 __shfl_sync(0xffffffffu, v.i.b, src));
@@ -214,13 +131,6 @@ __device__ __forceinline__ QM31 qm31_warp_sum(QM31 v) {
         v = qm31_add(v, o);
     }
     return v;
-}
-
-__device__ __forceinline__ CM31 denominator_inverse(QM31 px, QM31 py, M31Point r, bool &fail) { // deep/quotients.simf:15-22
-    CM31 dx = cm31_sub_m31(px.r, r.x);
-    CM31 dy = cm31_sub_m31(py.r, r.y);
-    CM31 d = cm31_sub(cm31_mul(dx, py.i), cm31_mul(dy, px.i));
-    return cm31_inv(d, fail);
 }
 
 // sum_k b_k * v_k - (R.y * sum_a + sum_c): the batch's quotient numerator accumulator (= the fold of

@@ -139,6 +139,29 @@ class Verifier:
         check(self.lib.ssym_stwo_verify_batch(self.h, C.byref(cfg), _ptr(packed), n, _ptr(accept), _ptr(status), tptr, space))
         return accept, status, traces
 
+    def stwo_prove_batch(self, seeds, cfg: StwoConfig, out=None):
+        """Batched prover for the wide-Fibonacci AIR that verify_proof checks (ssym_stwo_prove_batch, include/ssym.h): one packed
+        proof per u64 seed, accepted by stwo_verify_batch in MODE_PROVER_CONSISTENT.  `seeds`: numpy uint64 array (host) or a CUDA
+        int64 tensor (device; the proofs then stay in HBM).  Returns an (n, stride_words) array / tensor."""
+        lo = stwo_layout(cfg)
+        if _is_device(seeds):
+            import torch
+
+            n = seeds.numel()
+            if seeds.dtype != torch.int64 or not seeds.is_contiguous():
+                raise SsymError("device seeds must be a contiguous int64 tensor (the u64 bit patterns)")
+            if out is None:
+                out = torch.empty((n, lo.stride_words), dtype=torch.int32, device=seeds.device)
+            space = MEM_DEVICE
+        else:
+            seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+            n = seeds.size
+            if out is None:
+                out = np.zeros((n, lo.stride_words), dtype=np.uint32)
+            space = MEM_HOST
+        check(self.lib.ssym_stwo_prove_batch(self.h, C.byref(cfg), _ptr(seeds), n, _ptr(out), space))
+        return out
+
     def stark101_verify_batch(self, blob, offsets, want_status: bool = False, want_trace: bool = False):
         """verify_proof (stark101/src/verifier.simf:24-42) for a batch of packed records."""
         n = (offsets.numel() if hasattr(offsets, "numel") else offsets.size) - 1
