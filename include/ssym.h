@@ -210,6 +210,11 @@ int ssym_synchronize(ssym_ctx_t *ctx);
  * ordered into the handle's stream only by ssym_join (device-side wait, no host sync) or ssym_synchronize, and the
  * caller must not reuse an input / output buffer within D consecutive calls without a join in between. */
 int ssym_set_pipeline_depth(ssym_ctx_t *ctx, int depth);
+/* Asynchronous SSYM_MEM_HOST mode for ssym_stwo_verify_batch (default off = the call returns with the results in place).
+ * With on = 1 a host-buffer call only ENQUEUES its chunked H2D copies, kernels and D2H copies and returns; consecutive calls
+ * then overlap (the H2D of call k+1 runs under the kernel tail of call k), and every output is valid after ssym_synchronize.
+ * The caller's buffers must be pinned (cudaHostAlloc / torch pin_memory) and must not be touched until then. */
+int ssym_set_host_async(ssym_ctx_t *ctx, int on);
 int ssym_join(ssym_ctx_t *ctx);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t ssym_launch_count(const ssym_ctx_t *ctx);

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -92,15 +93,17 @@ struct ssym_ctx {
     // stream and scratch, so consecutive calls overlap on the GPU (the channel kernel of call k+1 is a latency-bound
     // chain that hides behind the Merkle kernel of call k).  depth 1 = everything on the handle's stream.
     struct Lane {
-        cudaStream_t s = nullptr;
-        cudaEvent_t in = nullptr, done = nullptr;
+        cudaStream_t s = nullptr, front = nullptr; // front: high priority, for the latency-bound kernels of a pipelined call
+        cudaEvent_t in = nullptr, done = nullptr, front_done = nullptr;
         DevBuf stwo_ctx, stwo_evals, status;
         bool pending = false;
     };
-    static const int MAX_DEPTH = 4;
+    static const int MAX_DEPTH = 8;
     Lane lanes[MAX_DEPTH];
     int depth = 1;
     uint64_t calls = 0;
+    bool host_async = false;  // ssym_set_host_async: SSYM_MEM_HOST stwo calls return after enqueueing
+    uint64_t host_chunks = 0; // staging-buffer parity persists across calls so that asynchronous calls can overlap
     // domain tables (per config)
     DevBuf tab_point, tab_fold, tab_flag;
     uint32_t tab_G = 0, tab_L = 0xffffffffu;
@@ -144,7 +147,11 @@ int ssym_create(int device, ssym_ctx_t **out) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (auto &l : c->lanes) {
+        CUDA_TRY(cudaStreamCreateWithPriority(&l.front, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&l.front_done, cudaEventDisableTiming));
         CUDA_TRY(cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&l.in, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
@@ -161,6 +168,8 @@ void ssym_destroy(ssym_ctx_t *c) {
     for (auto &l : c->lanes) {
         l.stwo_ctx.release(); l.stwo_evals.release(); l.status.release();
         cudaStreamDestroy(l.s);
+        cudaStreamDestroy(l.front);
+        cudaEventDestroy(l.front_done);
         cudaEventDestroy(l.in);
         cudaEventDestroy(l.done);
     }
@@ -188,7 +197,7 @@ int ssym_set_stream(ssym_ctx_t *c, void *cuda_stream) {
     return SSYM_OK;
 }
 int ssym_set_pipeline_depth(ssym_ctx_t *c, int depth) {
-    if (!c || depth < 1 || depth > ssym_ctx::MAX_DEPTH) return fail(SSYM_ERR_USAGE, "pipeline depth must be 1..4");
+    if (!c || depth < 1 || depth > ssym_ctx::MAX_DEPTH) return fail(SSYM_ERR_USAGE, "pipeline depth must be 1..8");
     int rc = ssym_join(c);
     if (rc) return rc;
     c->depth = depth;
@@ -300,7 +309,8 @@ static int ensure_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg) {
 }
 
 static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, const uint32_t *d_packed,
-                             size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s) {
+                             size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s, bool use_front = false) {
+    static const int front_kernels = [] { const char *e = getenv("SSYM_FRONT"); return e ? atoi(e) : 2; }();
     const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers;
     for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
         const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
@@ -324,7 +334,9 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
         p.trace = d_trace ? d_trace + done : nullptr;
         p.n = (uint32_t)m;
         if (p.trace) CUDA_TRY(cudaMemsetAsync(p.trace, 0, m * sizeof(ssym_stwo_trace_t), s));
-        launch_stwo_verify(p, d_accept + done / 32, s, &c->launches, c->profiling ? &c->profiler : nullptr);
+        const bool fr = use_front && front_kernels > 0 && !p.trace && !c->profiling && n <= STWO_DEVICE_CHUNK; // one chunk: the lane's scratch is not reused inside the call
+        launch_stwo_verify(p, d_accept + done / 32, s, &c->launches, c->profiling ? &c->profiler : nullptr, fr ? lane.front : nullptr,
+                           fr ? lane.front_done : nullptr, front_kernels);
     }
     CUDA_TRY(cudaGetLastError());
     return SSYM_OK;
@@ -347,7 +359,9 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
         ssym_ctx::Lane &lane = c->lanes[c->calls++ % c->depth];
         CUDA_TRY(cudaEventRecord(lane.in, c->stream));
         CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.in, 0));
-        rc = stwo_launch_chunk(c, lane, *cfg, lo, packed, n, accept_bits, status, trace, lane.s);
+        CUDA_TRY(cudaStreamWaitEvent(lane.front, lane.in, 0));
+        if (lane.pending) CUDA_TRY(cudaStreamWaitEvent(lane.front, lane.done, 0)); // the lane's scratch is still in use by its previous batch
+        rc = stwo_launch_chunk(c, lane, *cfg, lo, packed, n, accept_bits, status, trace, lane.s, true);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(lane.done, lane.s));
         lane.pending = true;
@@ -359,19 +373,26 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     const size_t stride_b = (size_t)lo.stride_words * 4;
     size_t hc = ((n + 3) / 4 + 31) & ~(size_t)31;
     hc = std::max<size_t>(256, std::min<size_t>(hc, 2048));
+    // asynchronous calls overlap their kernel tail with the next call's copies, so they can afford chunks big enough for the copy
+    // (1 us per proof) to outlast the chunk's kernels (~0.17 ms of latency-bound channel + query kernels + 0.25 us per proof)
+    if (c->host_async) hc = std::max<size_t>(512, std::min<size_t>(((n + 1) / 2 + 31) & ~(size_t)31, 4096));
     hc = std::min(hc, (n + 31) & ~(size_t)31);
     const size_t n_words = (n + 31) / 32;
+    if (c->host_async && (c->stage[0].cap < hc * stride_b || c->stage[1].cap < hc * stride_b || c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4 ||
+                          (trace && c->d_trace.cap < n * sizeof(ssym_stwo_trace_t)))) { // growing a buffer frees it: drain the calls still using it
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    }
     CUDA_TRY(c->stage[0].ensure(hc * stride_b));
     CUDA_TRY(c->stage[1].ensure(hc * stride_b));
     CUDA_TRY(c->d_accept.ensure(n_words * 4));
     CUDA_TRY(c->d_status.ensure(n * 4));
     if (trace) CUDA_TRY(c->d_trace.ensure(n * sizeof(ssym_stwo_trace_t)));
     cudaStream_t s = c->stream;
-    size_t chunk = 0;
-    for (size_t done = 0; done < n; done += hc, chunk++) {
+    for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
         const size_t m = std::min(hc, n - done);
-        const int b = (int)(chunk & 1);
-        if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        const int b = (int)(c->host_chunks & 1);
+        if (c->host_chunks >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
         CUDA_TRY(cudaMemcpyAsync(c->stage[b].p, packed + done * (size_t)lo.stride_words, m * stride_b, cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
@@ -383,8 +404,18 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
     if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_stwo_trace_t), cudaMemcpyDeviceToHost, s));
+    if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    return SSYM_OK;
+}
+
+extern "C" int ssym_set_host_async(ssym_ctx_t *c, int on) {
+    if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
+    int rc = ssym_synchronize(c);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    c->host_async = on != 0;
     return SSYM_OK;
 }
 

@@ -144,7 +144,7 @@ __device__ __forceinline__ QM31 batch_numerator(const uint32_t *bcoef, const uin
 }
 
 #define K2_WARPS 4
-__global__ void __launch_bounds__(32 * K2_WARPS) stwo_query_kernel(StwoParams p) {
+__global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams p) { // <= 64 registers: a CTA fits the slot a Merkle CTA frees
     __shared__ __align__(16) uint32_t s_b[K2_WARPS][20 * 4];
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -528,14 +528,22 @@ void launch_stwo_tables(uint32_t G, uint32_t L, uint2 *point, uint32_t *fold_inv
     stwo_tables_kernel<<<(total + 127) / 128, 128, 0, s>>>(G, L, point, fold_inv, offs, zero_flag);
 }
 
-void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof) {
+void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof,
+                        cudaStream_t front, cudaEvent_t front_done, int front_kernels) {
     if (p.n == 0) return;
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
+    // Pipelined calls run the small latency-bound kernels (K1, optionally K2) on a high-priority `front` stream so that their
+    // CTAs are dispatched ahead of the pending Merkle CTAs of older batches: the next batch's Merkle kernel is then ready
+    // to fill the SMs the moment the current one drains.
+    const bool use_front = front && front_done && front_kernels > 0 && !prof;
+    cudaStream_t s1 = use_front ? front : s, s2 = use_front && front_kernels >= 2 ? front : s;
     if (prof) prof->begin(0, s);
-    stwo_channel_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p);
+    stwo_channel_kernel<<<(p.n + 63) / 64, 64, 0, s1>>>(p);
+    if (use_front && front_kernels < 2) { cudaEventRecord(front_done, front); cudaStreamWaitEvent(s, front_done, 0); }
     if (prof) { prof->end(0, s); prof->begin(1, s); }
     const uint32_t items = p.n * Q;
-    stwo_query_kernel<<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s>>>(p);
+    stwo_query_kernel<<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p);
+    if (use_front && front_kernels >= 2) { cudaEventRecord(front_done, front); cudaStreamWaitEvent(s, front_done, 0); }
     if (prof) { prof->end(1, s); prof->begin(2, s); }
     const uint32_t groups = (items + 31) / 32;
     const uint64_t warps = (uint64_t)groups * (L + 3);

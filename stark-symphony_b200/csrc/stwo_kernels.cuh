@@ -64,6 +64,7 @@ struct Profiler {
 
 void launch_stwo_tables(uint32_t lde_log, uint32_t n_fri_layers, uint2 *point, uint32_t *fold_inv, const uint32_t *fold_off,
                         uint32_t *zero_flag, cudaStream_t s);
-void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof);
+void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof,
+                        cudaStream_t front = nullptr, cudaEvent_t front_done = nullptr, int front_kernels = 0);
 
 } // namespace ssym

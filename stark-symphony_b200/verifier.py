@@ -78,6 +78,11 @@ class Verifier:
         """Keep up to `depth` device-resident stwo batches in flight (see ssym_set_pipeline_depth in include/ssym.h)."""
         check(self.lib.ssym_set_pipeline_depth(self.h, depth))
 
+    def set_host_async(self, on: bool) -> None:
+        """Host-buffer stwo_verify_batch calls only enqueue their copies + kernels (see ssym_set_host_async); outputs are valid
+        after synchronize().  Buffers must be pinned."""
+        check(self.lib.ssym_set_host_async(self.h, 1 if on else 0))
+
     def join(self) -> None:
         """Order all in-flight batches into the handle's stream (device-side wait only)."""
         check(self.lib.ssym_join(self.h))

@@ -400,3 +400,26 @@ def test_stark101_field_jets(ver, orc):
 def test_int32_probe_runs(ver):
     ops, ms = ver.int32_peak_probe()
     assert ops > 1e12 and ms > 0
+
+
+def test_stwo_host_async_mode_matches_sync(S, ver, orc):
+    """ssym_set_host_async: back-to-back host-buffer calls, one synchronize; same bitmaps / statuses as the synchronous call."""
+    import torch
+
+    cfg, packed = golden_stwo(S, "prod", 1)
+    batch, n, _ = negatives_batch(S, cfg, packed, extra_random=690, seed=3)
+    pinned = torch.from_numpy(batch.view(np.int32).copy()).pin_memory()
+    host = pinned.numpy().view(np.uint32)
+    acc_sync, st_sync, _ = ver.stwo_verify_batch(host, cfg, n, want_status=True)
+    rows = torch.zeros((5, (n + 31) // 32), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    sts = torch.zeros((5, n), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    ver.set_host_async(True)
+    try:
+        for k in range(5):
+            ver.stwo_verify_batch(host, cfg, n, accept_out=rows[k], status_out=sts[k])
+        ver.synchronize()
+    finally:
+        ver.set_host_async(False)
+    assert (rows == acc_sync[None, :]).all() and (sts == st_sync[None, :]).all()
+    _, o_status, _ = orc.stwo_verify_batch(ocfg(cfg), batch, n)
+    assert (st_sync == o_status).all()
