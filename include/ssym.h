@@ -204,9 +204,10 @@ const char *ssym_version(void);
  * device-resident calls on this handle; NULL restores the handle's own stream. */
 int ssym_set_stream(ssym_ctx_t *ctx, void *cuda_stream);
 int ssym_synchronize(ssym_ctx_t *ctx);
-/* Pipeline depth D (1..4, default 1) for device-resident ssym_stwo_verify_batch calls: call k runs on internal
+/* Pipeline depth D (1..8, default 1) for device-resident ssym_stwo_verify_batch calls: call k runs on internal
  * stream k % D (forked from the handle's stream at call time), so up to D consecutive batches are in flight and the
- * latency-bound channel kernel of one batch overlaps the Merkle kernel of the previous one.  With D > 1 results are
+ * latency-bound channel kernel of one batch overlaps the Merkle kernel of the previous one (the channel and query
+ * kernels of a pipelined call run on a high-priority stream so they are dispatched ahead of pending Merkle CTAs).  With D > 1 results are
  * ordered into the handle's stream only by ssym_join (device-side wait, no host sync) or ssym_synchronize, and the
  * caller must not reuse an input / output buffer within D consecutive calls without a join in between. */
 int ssym_set_pipeline_depth(ssym_ctx_t *ctx, int depth);
