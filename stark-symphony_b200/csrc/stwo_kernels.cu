@@ -17,6 +17,18 @@ namespace ssym {
 
 typedef StwoCtxLayout CX;
 
+__device__ __noinline__ QM31 qm31_mul_nl(QM31 x, QM31 y) { return qm31_mul(x, y); }
+__device__ __noinline__ QM31 qm31_inv_nl(QM31 x, bool &fail) { return qm31_inv(x, fail); }
+
+// composition_poly_eval_from_partitions                       evals/composition_poly.simf:38-44
+__device__ QM31 cp_from_partitions(QM31 c0, QM31 c1, QM31 c2, QM31 c3) {
+    QM31 res = qm31_add(c0, qm31_mul_nl(c1, qm31(0, 1, 0, 0)));
+    res = qm31_add(res, qm31_mul_nl(c2, qm31(0, 0, 1, 0)));
+    res = qm31_add(res, qm31_mul_nl(c3, qm31(0, 0, 0, 1)));
+    return res;
+}
+
+
 // ------------------------------------------------------------------------------------------
 // K1: the Fiat-Shamir channel of verify_proof (verifier.simf:36-51).  The channel state only ever
 // absorbs proof data (roots, samples, nonce): none of the field arithmetic feeds back into it, so the
@@ -50,7 +62,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
         qm31_store(tr->cp_alpha, cp_alpha);
     }
     // oods: draw the point parameter t, absorb the samples, draw the DEEP alpha    deep/oods.simf:44-64
-    qm31_store4(ctx + CX::OODS_T, channel_draw_qm31(ch, exhausted)); // channel.simf:143-144
+    const QM31 oods_t = channel_draw_qm31(ch, exhausted); // channel.simf:143-144
     channel_mix(ch, pk + lo.off_oods_trace, 80);                     // 4 trace + 16 CP samples are contiguous in the packed header
     const QM31 deep_alpha = channel_draw_qm31(ch, exhausted);
     qm31_store4(ctx + CX::DEEP_ALPHA, deep_alpha);
@@ -95,28 +107,88 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
     }
     if (exhausted) status |= SSYM_ST_DRAW_EXHAUSTED;
     if (p.cfg.mode == SSYM_MODE_REF_LITERAL && ((G - (L + 1u)) & 0xff) != 0) status |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
+
+    // ---- per-proof scalars (a thread here serves one proof per lane; the query kernel would redo them in every lane) ----
+    bool inv_zero = false;
+    QM31 px, py;
+    { // channel_draw_qm31_point channel.simf:143-151
+        const QM31 t_sq = qm31_mul_nl(oods_t, oods_t);
+        const QM31 inv = qm31_inv_nl(qm31_add(qm31_one(), t_sq), inv_zero);
+        px = qm31_mul_nl(qm31_sub(qm31_one(), t_sq), inv);
+        py = qm31_mul_nl(qm31_add(oods_t, oods_t), inv);
+    }
+    const QM31 pxy = qm31_mul_nl(px, py);
+    {
+        // composition_poly_eval_from_decomposed composition_poly.simf:47-59 (index = 4*coord + poly): F_a + y F_b + x F_c + xy F_d
+        const uint32_t *e = pk + lo.off_oods_cp;
+        QM31 sampled = qm31_zero();
+#pragma unroll 1
+        for (uint32_t poly = 0; poly < 4; poly++) {
+            const QM31 part = cp_from_partitions(qm31_load4(e + 4 * poly), qm31_load4(e + 4 * (4 + poly)), qm31_load4(e + 4 * (8 + poly)),
+                                                 qm31_load4(e + 4 * (12 + poly)));
+            const QM31 factor = poly == 1 ? py : poly == 2 ? px : pxy;
+            sampled = poly == 0 ? part : qm31_add(sampled, qm31_mul_nl(part, factor));
+        }
+        // eval_composition_poly wide_fibonacci.simf:24-62
+        QM31 acc = qm31_zero(), a = qm31_zero(), b = qm31_zero();
+        uint32_t skip_2 = 0;
+#pragma unroll 1
+        for (int col = 0; col < SSYM_NUM_COLUMNS; col++) {
+            const QM31 c = qm31_load4(pk + lo.off_oods_trace + 4 * col);
+            if (skip_2 == 2) {
+                const QM31 constraint = qm31_sub(c, qm31_add(qm31_mul_nl(b, b), qm31_mul_nl(a, a)));
+                acc = qm31_add(qm31_mul_nl(acc, cp_alpha), constraint);
+            } else {
+                skip_2++;
+            }
+            a = b;
+            b = c;
+        }
+        // vanishing_poly_eval composition_poly.simf:66-71: pi^(log_size-1)(x)
+        const uint32_t n_iter = (p.cfg.trace_log - 1u) & 0xff;
+        QM31 v = px;
+#pragma unroll 1
+        for (uint32_t counter = 0; counter < 256 && counter != n_iter; counter++) {
+            const QM31 sq = qm31_mul_nl(v, v);
+            v = qm31_sub(qm31_add(sq, sq), qm31_one());
+        }
+        const QM31 cp_eval = qm31_mul_nl(acc, qm31_inv_nl(v, inv_zero));
+        if (!qm31_eq(cp_eval, sampled)) status |= SSYM_ST_OODS_CP_MISMATCH; // deep/oods.simf:58
+        if (inv_zero) status |= SSYM_ST_OODS_INV_ZERO;
+        if (tr) {
+            qm31_store(tr->oods_x, px);
+            qm31_store(tr->oods_y, py);
+            qm31_store(tr->cp_eval, cp_eval);
+            qm31_store(tr->cp_sampled, sampled);
+        }
+    }
+    qm31_store4(ctx + CX::PX, px);
+    qm31_store4(ctx + CX::PY, py);
+    if (p.cfg.mode == SSYM_MODE_REF_LITERAL) { // all 20 columns are sampled at P (fri/answers.simf:116-125)
+        qm31_store4(ctx + CX::P2X, px);
+        qm31_store4(ctx + CX::P2Y, py);
+    } else { // the 16 CP partitions are sampled at 2*P
+        qm31_store4(ctx + CX::P2X, qm31_point_dbl_x(px));
+        qm31_store4(ctx + CX::P2Y, qm31_add(pxy, pxy));
+    }
+    { // alpha^(k+1): the running product of fri/answers.simf:52,70
+        QM31 a = deep_alpha;
+#pragma unroll 1
+        for (uint32_t k = 0; k <= 20; k++) {
+            qm31_store4(ctx + CX::ALPHA_POW + 4 * k, a);
+            a = qm31_mul_nl(a, deep_alpha);
+        }
+    }
     p.status[i] = status;
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: all field arithmetic of verify_proof, one warp per proof:
-//   phase A  OODS point from t, composition polynomial at the point vs. the recombined samples (deep/oods.simf:44-64)
+// K2: the per-query field arithmetic of verify_proof, one warp per proof (the per-proof scalars are K1's):
 //   phase B  lane k < 20: DEEP line coefficients of column k with alpha^(k+1) (deep/quotients.simf:25-35); the
 //            coefficients depend only on the proof, not on the query, so they are computed once, in parallel
 //   phase C  lane q < Q: fri_answer of query q (fri/answers.simf:97-129) and its 1+L folds (fri/layers.simf:51-78,
 //            fri/folding.simf:15-41); the Merkle halves of those functions are K3
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ QM31 qm31_mul_nl(QM31 x, QM31 y) { return qm31_mul(x, y); }
-__device__ __noinline__ QM31 qm31_inv_nl(QM31 x, bool &fail) { return qm31_inv(x, fail); }
-
-// composition_poly_eval_from_partitions                       evals/composition_poly.simf:38-44
-__device__ QM31 cp_from_partitions(QM31 c0, QM31 c1, QM31 c2, QM31 c3) {
-    QM31 res = qm31_add(c0, qm31_mul_nl(c1, qm31(0, 1, 0, 0)));
-    res = qm31_add(res, qm31_mul_nl(c2, qm31(0, 0, 1, 0)));
-    res = qm31_add(res, qm31_mul_nl(c3, qm31(0, 0, 0, 1)));
-    return res;
-}
-
 __device__ __forceinline__ QM31 qm31_shfl(QM31 v, int src) {
     return qm31(__shfl_sync(0xffffffffu, v.r.a, src), __shfl_sync(0xffffffffu, v.r.b, src), __shfl_sync(0xffffffffu, v.i.a, src),
                 __shfl_sync(0xffffffffu, v.i.b, src));
@@ -157,81 +229,16 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
     const bool literal = p.cfg.mode == SSYM_MODE_REF_LITERAL;
     uint32_t status = 0;
 
-    // ---- phase A (every lane computes the point; lanes 0..3 split the recombination) ----
-    bool inv_zero = false;
-    QM31 px, py;
-    { // channel_draw_qm31_point channel.simf:143-151
-        const QM31 t = qm31_load4(ctx + CX::OODS_T);
-        const QM31 t_sq = qm31_mul_nl(t, t);
-        const QM31 inv = qm31_inv_nl(qm31_add(qm31_one(), t_sq), inv_zero);
-        px = qm31_mul_nl(qm31_sub(qm31_one(), t_sq), inv);
-        py = qm31_mul_nl(qm31_add(t, t), inv);
-    }
-    const QM31 pxy = qm31_mul_nl(px, py);
-    {
-        // composition_poly_eval_from_decomposed composition_poly.simf:47-59 (index = 4*coord + poly): lane = poly
-        const uint32_t *e = pk + lo.off_oods_cp;
-        const uint32_t poly = lane & 3;
-        QM31 part = cp_from_partitions(qm31_load4(e + 4 * poly), qm31_load4(e + 4 * (4 + poly)), qm31_load4(e + 4 * (8 + poly)),
-                                       qm31_load4(e + 4 * (12 + poly)));
-        const QM31 factor = poly == 1 ? py : poly == 2 ? px : pxy; // F_a + y F_b + x F_c + xy F_d
-        const QM31 term = poly == 0 ? part : qm31_mul_nl(part, factor);
-        QM31 sampled = qm31_shfl(term, 0);
-        sampled = qm31_add(sampled, qm31_shfl(term, 1));
-        sampled = qm31_add(sampled, qm31_shfl(term, 2));
-        sampled = qm31_add(sampled, qm31_shfl(term, 3));
-        // eval_composition_poly wide_fibonacci.simf:24-62
-        const QM31 cp_alpha = qm31_load4(ctx + CX::CP_ALPHA);
-        QM31 acc = qm31_zero(), a = qm31_zero(), b = qm31_zero();
-        uint32_t skip_2 = 0;
-#pragma unroll 1
-        for (int col = 0; col < SSYM_NUM_COLUMNS; col++) {
-            const QM31 c = qm31_load4(pk + lo.off_oods_trace + 4 * col);
-            if (skip_2 == 2) {
-                const QM31 constraint = qm31_sub(c, qm31_add(qm31_mul_nl(b, b), qm31_mul_nl(a, a)));
-                acc = qm31_add(qm31_mul_nl(acc, cp_alpha), constraint);
-            } else {
-                skip_2++;
-            }
-            a = b;
-            b = c;
-        }
-        // vanishing_poly_eval composition_poly.simf:66-71: pi^(log_size-1)(x)
-        const uint32_t n_iter = (p.cfg.trace_log - 1u) & 0xff;
-        QM31 v = px;
-#pragma unroll 1
-        for (uint32_t counter = 0; counter < 256 && counter != n_iter; counter++) {
-            const QM31 sq = qm31_mul_nl(v, v);
-            v = qm31_sub(qm31_add(sq, sq), qm31_one());
-        }
-        const QM31 cp_eval = qm31_mul_nl(acc, qm31_inv_nl(v, inv_zero));
-        if (!qm31_eq(cp_eval, sampled)) status |= SSYM_ST_OODS_CP_MISMATCH; // deep/oods.simf:58
-        if (inv_zero) status |= SSYM_ST_OODS_INV_ZERO;
-        if (tr && lane == 0) {
-            qm31_store(tr->oods_x, px);
-            qm31_store(tr->oods_y, py);
-            qm31_store(tr->cp_eval, cp_eval);
-            qm31_store(tr->cp_sampled, sampled);
-        }
-    }
+    // the per-proof scalars come from K1: the OODS point P, the sample point of batch A, the powers of the DEEP coefficient
+    const QM31 px = qm31_load4(ctx + CX::PX), py = qm31_load4(ctx + CX::PY);
+    const QM31 p2x = qm31_load4(ctx + CX::P2X), p2y = qm31_load4(ctx + CX::P2Y);
 
     // ---- phase B: lane k computes the line coefficients of column k (aggregation order) with alpha^(k+1) ----
-    const QM31 deep_alpha = qm31_load4(ctx + CX::DEEP_ALPHA);
-    QM31 p2x = px, p2y = py; // sample point of batch A
-    if (!literal) {          // the 16 CP partitions are sampled at 2*P
-        p2x = qm31_point_dbl_x(px);
-        p2y = qm31_add(pxy, pxy);
-    }
-    QM31 sum_a_A, sum_c_A, sum_a_B, sum_c_B, batch_coeff;
+    QM31 sum_a_A, sum_c_A, sum_a_B, sum_c_B;
+    const QM31 batch_coeff = qm31_load4(ctx + CX::ALPHA_POW + 4 * 20); // alpha^21
     {
         const uint32_t k = lane < 20 ? lane : 19;
-        QM31 alpha_pow = qm31_one(), base = deep_alpha; // alpha^(k+1) by square-and-multiply (exact field ops: same value as the running product)
-#pragma unroll 1
-        for (uint32_t bit = 0; bit < 5; bit++) {
-            const QM31 t = qm31_mul_nl(alpha_pow, base);
-            if (((k + 1) >> bit) & 1u) alpha_pow = t;
-            base = qm31_mul_nl(base, base);
-        }
+        const QM31 alpha_pow = qm31_load4(ctx + CX::ALPHA_POW + 4 * k);
         // literal: columns = 4 trace then 16 CP, all at P.  prover-consistent: 16 CP at 2P, then 4 trace at P.
         const bool in_A = literal || k < 16;
         const uint32_t *sv = literal ? pk + lo.off_oods_trace + 4 * k : (k < 16 ? pk + lo.off_oods_cp + 4 * k : pk + lo.off_oods_trace + 4 * (k - 16));
@@ -242,7 +249,6 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
         sum_c_A = qm31_warp_sum(lane < 20 && in_A ? lc.c : zero);
         sum_a_B = qm31_warp_sum(lane < 20 && !in_A ? lc.a : zero);
         sum_c_B = qm31_warp_sum(lane < 20 && !in_A ? lc.c : zero);
-        batch_coeff = qm31_mul_nl(qm31_shfl(alpha_pow, 19), deep_alpha); // alpha^21
     }
     __syncwarp();
 

@@ -3,9 +3,9 @@
 // Batched verify_proof of the Stwo wide-Fibonacci verifier (stwo-verifier/src/verifier.simf:32-58)
 // as four kernels over a batch of packed proofs (layout: include/ssym.h):
 //
-//   K1 stwo_channel_kernel     one thread per proof     Fiat-Shamir channel: ~46 dependent compressions, PoW, queries
-//   K2 stwo_query_kernel       one warp per proof       all field arithmetic: OODS check, DEEP line coefficients
-//                                                      (lane = column), fri_answer + the 1+L folds (lane = query)
+//   K1 stwo_channel_kernel     one thread per proof     Fiat-Shamir channel: ~46 dependent compressions, PoW, queries; the per-proof
+//                                                      scalars: OODS point, composition-polynomial check, powers of the DEEP coefficient
+//   K2 stwo_query_kernel       one warp per proof       DEEP line coefficients (lane = column), fri_answer + the 1+L folds (lane = query)
 //   K3 stwo_merkle_kernel      one thread per hash chain  all 2*Q + (L+1)*Q Merkle decommitments
 //   K4 stwo_finalize_kernel    status words -> accept bitmap
 //
@@ -26,10 +26,14 @@ struct StwoCtxLayout {
     enum : uint32_t {
         QUERIES = 0,     // [16]   fri/queries.simf:30-43
         CP_ALPHA = 16,   // [4]    evals/commit.simf:29
-        OODS_T = 20,     // [4]    the QM31 draw the OODS point is built from, channel.simf:144
-        DEEP_ALPHA = 24, // [4]    deep/oods.simf:61
-        FRI_ALPHA = 28,  // [9][4] fri/commit.simf:42
-        WORDS = 64
+        DEEP_ALPHA = 20, // [4]    deep/oods.simf:61
+        FRI_ALPHA = 24,  // [9][4] fri/commit.simf:42
+        PX = 60,         // [4]    OODS point, channel.simf:143-151
+        PY = 64,         // [4]
+        P2X = 68,        // [4]    sample point of the 16 CP columns: P (REF_LITERAL) or 2P (PROVER_CONSISTENT, Appendix A item 1)
+        P2Y = 72,        // [4]
+        ALPHA_POW = 76,  // [21][4] deep_alpha^(k+1), k = 0..20 (k = 20: the batch coefficient of fri/answers.simf:126)
+        WORDS = 160
     };
 };
 
