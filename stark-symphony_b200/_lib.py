@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libssym.so")
+LIB_PATH = os.environ.get("SSYM_LIB") or os.path.join(HERE, "libssym.so")  # SSYM_LIB: an alternative build of the same ABI (kernel A/B runs)
 
 MEM_DEVICE, MEM_HOST = 0, 1
 MODE_REF_LITERAL, MODE_PROVER_CONSISTENT = 0, 1

@@ -33,23 +33,32 @@ __device__ __forceinline__ M31 m31_mul(M31 a, M31 b) {
     return z >= SSYM_P ? z - SSYM_P : z;
 }
 __device__ __forceinline__ M31 m31_pow2(M31 a) { return m31_mul(a, a); }
+// m31_mul for CANONICAL operands (a, b < p): the product is < 2^62, so one fold suffices.  Same value as m31_mul.
+__device__ __forceinline__ M31 m31_mul_c(M31 a, M31 b) {
+    const uint64_t x = (uint64_t)a * b;
+    const uint32_t s = ((uint32_t)x & SSYM_P) + (uint32_t)(x >> 31); // < 2^32
+    return s >= SSYM_P ? s - SSYM_P : s;
+}
 template <int N>
-__device__ __forceinline__ M31 m31_sqn(M31 a) {
+__device__ __forceinline__ M31 m31_sqn(M31 a) { // a canonical
 #pragma unroll
-    for (int i = 0; i < N; i++) a = m31_mul(a, a);
+    for (int i = 0; i < N; i++) a = m31_mul_c(a, a);
     return a;
 }
 // a^(p-2) by the reference's addition chain; *fail |= (a == 0 bitwise)   fields/m31.simf:117-132
-// (the chain maps 0 -> 0, which is the documented continuation value)
+// (the chain maps 0 -> 0, which is the documented continuation value).  Every step of the chain is an m31_mul, whose result
+// depends only on the residue of a: a is canonicalised once (p -> 0, as m31_mul(p, p) = 0) and the chain runs on the cheaper
+// canonical-operand product.
 __device__ __forceinline__ M31 m31_inv(M31 a, bool &fail) {
     fail = fail || (a == 0);
-    M31 t0 = m31_mul(m31_sqn<2>(a), a);      // a^5
-    M31 t1 = m31_mul(m31_sqn<1>(t0), t0);    // a^15
-    M31 t2 = m31_mul(m31_sqn<3>(t1), t0);    // a^125
-    M31 t3 = m31_mul(m31_sqn<1>(t2), t0);    // a^255
-    M31 t4 = m31_mul(m31_sqn<8>(t3), t3);    // a^65535
-    M31 t5 = m31_mul(m31_sqn<8>(t4), t3);    // a^16777215
-    return m31_mul(m31_sqn<7>(t5), t2);      // a^2147483645
+    a = m31_reduce(a);
+    M31 t0 = m31_mul_c(m31_sqn<2>(a), a);    // a^5
+    M31 t1 = m31_mul_c(m31_sqn<1>(t0), t0);  // a^15
+    M31 t2 = m31_mul_c(m31_sqn<3>(t1), t0);  // a^125
+    M31 t3 = m31_mul_c(m31_sqn<1>(t2), t0);  // a^255
+    M31 t4 = m31_mul_c(m31_sqn<8>(t3), t3);  // a^65535
+    M31 t5 = m31_mul_c(m31_sqn<8>(t4), t3);  // a^16777215
+    return m31_mul_c(m31_sqn<7>(t5), t2);    // a^2147483645
 }
 
 struct CM31 {
@@ -62,8 +71,12 @@ __device__ __forceinline__ CM31 cm31_sub(CM31 x, CM31 y) { return cm31(m31_sub(x
 __device__ __forceinline__ CM31 cm31_sub_m31(CM31 x, M31 y) { return cm31(m31_sub(x.a, y), x.b); }                    // cm31.simf:50-53
 __device__ __forceinline__ CM31 cm31_mul_m31(CM31 x, M31 y) { return cm31(m31_mul(x.a, y), m31_mul(x.b, y)); }        // cm31.simf:56-59
 __device__ __forceinline__ CM31 cm31_conj(CM31 x) { return cm31(x.a, m31_neg(x.b)); }                                 // cm31.simf:73-76
-__device__ __forceinline__ CM31 cm31_mul(CM31 x, CM31 y) {                                                            // cm31.simf:79-86
-    return cm31(m31_sub(m31_mul(x.a, y.a), m31_mul(x.b, y.b)), m31_add(m31_mul(x.a, y.b), m31_mul(x.b, y.a)));
+__device__ __forceinline__ M31 m31_reduce64(uint64_t x);
+// cm31.simf:79-86.  Both components are sums of m31_mul results, i.e. exact residues in canonical form for any u32 inputs: computed
+// with canonicalised operands, 64-bit accumulation and one reduction per component.
+__device__ __forceinline__ CM31 cm31_mul(CM31 x, CM31 y) {
+    const uint32_t a0 = m31_reduce(x.a), a1 = m31_reduce(x.b), b0 = m31_reduce(y.a), b1 = m31_reduce(y.b);
+    return cm31(m31_reduce64((uint64_t)a0 * b0 + (uint64_t)a1 * (SSYM_P - b1)), m31_reduce64((uint64_t)a0 * b1 + (uint64_t)a1 * b0));
 }
 __device__ __forceinline__ CM31 cm31_inv(CM31 x, bool &fail) {                                                        // cm31.simf:88-93
     CM31 cj = cm31_conj(x);
@@ -91,10 +104,32 @@ __device__ __forceinline__ QM31 qm31_neg(QM31 x) { return qm31c(cm31_neg(x.r), c
 __device__ __forceinline__ QM31 qm31_sub(QM31 x, QM31 y) { return qm31c(cm31_sub(x.r, y.r), cm31_sub(x.i, y.i)); }            // qm31.simf:49-53
 __device__ __forceinline__ QM31 qm31_mul_m31(QM31 x, M31 y) { return qm31c(cm31_mul_m31(x.r, y), cm31_mul_m31(x.i, y)); }     // qm31.simf:56-59
 __device__ __forceinline__ QM31 qm31_mul_cm31(QM31 x, CM31 y) { return qm31c(cm31_mul(x.r, y), cm31_mul(x.i, y)); }           // qm31.simf:62-65
-__device__ __forceinline__ QM31 qm31_mul(QM31 x, QM31 y) {                                                                    // qm31.simf:73-80
-    CM31 re = cm31_add(cm31_mul(x.r, y.r), cm31_mul(cm31_mul(x.i, y.i), cm31(2, 1)));
-    CM31 im = cm31_add(cm31_mul(x.r, y.i), cm31_mul(x.i, y.r));
-    return qm31c(re, im);
+// x mod p for any 64-bit x: 2^31 = 2^62 = 1 (mod p), so x = (x & p) + ((x >> 31) & p) + (x >> 62)
+__device__ __forceinline__ M31 m31_reduce64(uint64_t x) {
+    const uint32_t lo = (uint32_t)x & SSYM_P, mid = (uint32_t)(x >> 31) & SSYM_P, hi = (uint32_t)(x >> 62);
+    uint32_t s = lo + mid;                 // <= 2^32 - 2
+    s = (s & SSYM_P) + (s >> 31) + hi;     // <= p + 4
+    return s >= SSYM_P ? s - SSYM_P : s;
+}
+// qm31.simf:73-80:  re = x.r*y.r + (x.i*y.i)*(2+i),  im = x.r*y.i + x.i*y.r,  every product a cm31_mul (cm31.simf:79-86).
+// Every term of the reference formula passes through m31_mul, whose result depends only on the residues of its operands and is
+// canonical, and sums of canonical values stay canonical: the output is the exact product mod p in canonical form for ANY u32
+// inputs.  It is computed here with the operands canonicalised once, the 16 products accumulated in 64 bits (each < 2^62, at most
+// four per sum) and 6 reductions instead of 20 products + 14 modular adds.
+__device__ __forceinline__ QM31 qm31_mul(QM31 x, QM31 y) {
+    const uint32_t a0 = m31_reduce(x.r.a), a1 = m31_reduce(x.r.b), a2 = m31_reduce(x.i.a), a3 = m31_reduce(x.i.b);
+    const uint32_t b0 = m31_reduce(y.r.a), b1 = m31_reduce(y.r.b), b2 = m31_reduce(y.i.a), b3 = m31_reduce(y.i.b);
+    const uint32_t n1 = SSYM_P - b1, n3 = SSYM_P - b3; // -b1, -b3 (in [1, p]: products stay < 2^62)
+    // Y = x.i * y.i
+    const uint32_t ya = m31_reduce64((uint64_t)a2 * b2 + (uint64_t)a3 * n3);
+    const uint32_t yb = m31_reduce64((uint64_t)a2 * b3 + (uint64_t)a3 * b2);
+    // re = x.r * y.r + Y * (2 + i) = (Xa + 2 Ya - Yb, Xb + 2 Yb + Ya)
+    const uint32_t ra = m31_reduce64((uint64_t)a0 * b0 + (uint64_t)a1 * n1 + ((uint64_t)ya << 1) + (SSYM_P - yb));
+    const uint32_t rb = m31_reduce64((uint64_t)a0 * b1 + (uint64_t)a1 * b0 + ((uint64_t)yb << 1) + ya);
+    // im = x.r * y.i + x.i * y.r
+    const uint32_t ia = m31_reduce64((uint64_t)a0 * b2 + (uint64_t)a1 * n3 + (uint64_t)a2 * b0 + (uint64_t)a3 * n1);
+    const uint32_t ib = m31_reduce64((uint64_t)a0 * b3 + (uint64_t)a1 * b2 + (uint64_t)a2 * b1 + (uint64_t)a3 * b0);
+    return qm31(ra, rb, ia, ib);
 }
 __device__ __forceinline__ QM31 qm31_inv(QM31 x, bool &fail) {                                                                // qm31.simf:87-98
     CM31 ar_sq = cm31_mul(x.r, x.r);

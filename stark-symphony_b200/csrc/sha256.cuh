@@ -79,6 +79,9 @@ __device__ __forceinline__ void sha_iv(uint32_t (&h)[8]) {
 //   1  every add of the round function and of the message schedule as IMAD
 //   2  round-function adds as IMAD, message-schedule adds left to ptxas
 //   3  only the T1 chain (h + K + W + Sigma1 + Ch) as IMAD
+//   4  as 1, but a' = T1 + Sigma0 + Maj is ONE 3-input IADD3 on the ALU pipe instead of two IMADs: with everything on the FMA pipe the
+//      kernel is bound by total issue slots (ncu: 0.72 IPC), so trading two FMA-pipe instructions for one ALU-pipe instruction pays
+//   5  as 4, and the message schedule's w + sigma0 + w[-7] is an IADD3 as well
 template <int ADDMODE>
 struct ShaAdd {
     uint32_t one;
@@ -88,16 +91,21 @@ struct ShaAdd {
         return d;
     }
     __device__ __forceinline__ uint32_t t1(uint32_t a, uint32_t b) const { return ADDMODE >= 1 ? fma(a, b) : a + b; }    // T1 chain
-    __device__ __forceinline__ uint32_t rnd(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE == 2) ? fma(a, b) : a + b; } // rest of the round
-    __device__ __forceinline__ uint32_t sch(uint32_t a, uint32_t b) const { return ADDMODE == 1 ? fma(a, b) : a + b; }  // message schedule
+    __device__ __forceinline__ uint32_t rnd(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE == 2 || ADDMODE >= 4) ? fma(a, b) : a + b; } // rest of the round
+    __device__ __forceinline__ uint32_t sch(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE >= 4) ? fma(a, b) : a + b; }  // message schedule
+    // a' = t1 + Sigma0 + Maj
+    __device__ __forceinline__ uint32_t rnd3(uint32_t t1v, uint32_t s0, uint32_t mj) const { return ADDMODE >= 4 ? t1v + s0 + mj : rnd(t1v, rnd(s0, mj)); }
+    // w + sigma0 + w9 + sigma1
+    __device__ __forceinline__ uint32_t sch4(uint32_t w, uint32_t s0, uint32_t w9, uint32_t s1) const {
+        return ADDMODE == 5 ? fma(w + s0 + w9, s1) : sch(sch(w, s0), sch(w9, s1));
+    }
 };
 
 #define SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, h, kw)                        \
     {                                                                        \
         uint32_t t1_ = A.t1(A.t1(h, kw), A.t1(Sig1(e), Ch(e, f, g)));        \
-        uint32_t t2_ = A.rnd(Sig0(a), Maj(a, b, c));                         \
         (d) = A.rnd(d, t1_);                                                 \
-        (h) = A.rnd(t1_, t2_);                                               \
+        (h) = A.rnd3(t1_, Sig0(a), Maj(a, b, c));                            \
     }
 
 // One compression of `h` with the 16-word block `w` (w is consumed: it becomes the rolling schedule).
@@ -111,7 +119,7 @@ __device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int i = (t + j) & 15;
-                w[i] = A.sch(A.sch(w[i], sig0(w[(i + 1) & 15])), A.sch(w[(i + 9) & 15], sig1(w[(i + 14) & 15])));
+                w[i] = A.sch4(w[i], sig0(w[(i + 1) & 15]), w[(i + 9) & 15], sig1(w[(i + 14) & 15]));
             }
         }
         SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.t1(w[(t + 0) & 15], K.k[t + 0]));
@@ -188,7 +196,7 @@ __device__ __forceinline__ void sha_compress_rolled(uint32_t (&h)[8], uint32_t (
         if (grp) {
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                w[i] = A.sch(A.sch(w[i], sig0(w[(i + 1) & 15])), A.sch(w[(i + 9) & 15], sig1(w[(i + 14) & 15])));
+                w[i] = A.sch4(w[i], sig0(w[(i + 1) & 15]), w[(i + 9) & 15], sig1(w[(i + 14) & 15]));
         }
         const uint4 k0 = c_sha_k4.v[grp * 4 + 0], k1 = c_sha_k4.v[grp * 4 + 1], k2 = c_sha_k4.v[grp * 4 + 2], k3 = c_sha_k4.v[grp * 4 + 3];
         SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.t1(w[0], k0.x), A.t1(w[1], k0.y), A.t1(w[2], k0.z), A.t1(w[3], k0.w));

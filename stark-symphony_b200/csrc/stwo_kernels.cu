@@ -9,6 +9,9 @@
 #ifndef SSYM_DEFAULT_ADDMODE
 #define SSYM_DEFAULT_ADDMODE 1
 #endif
+#ifndef SSYM_MERKLE_MINB
+#define SSYM_MERKLE_MINB 8 // resident CTAs per SM the Merkle kernel is compiled for (8 -> 64 registers)
+#endif
 #ifndef SSYM_DEFAULT_ROLLED
 #define SSYM_DEFAULT_ROLLED 1
 #endif
@@ -339,7 +342,7 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t (&d)[8
 //   cp    : pre 0 = SHA-256(16 words)                      hash_node_m31_cp      hasher.simf:93-97
 //   fri   : pre 0 = SHA-256(e0), pre 1 = SHA-256(e1), pre 2 = sha256_pair        fri/layers.simf:40-48
 template <int ADDMODE, bool ROLLED>
-__global__ void __launch_bounds__(128) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, uint32_t one) {
+__global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, uint32_t one) {
     const ShaAdd<ADDMODE> A{one};
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -566,6 +569,8 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     case 5: SSYM_LAUNCH_MERKLE(2, true); break;
     case 6: SSYM_LAUNCH_MERKLE(3, false); break;
     case 7: SSYM_LAUNCH_MERKLE(3, true); break;
+    case 9: SSYM_LAUNCH_MERKLE(4, true); break;
+    case 11: SSYM_LAUNCH_MERKLE(5, true); break;
     default: SSYM_LAUNCH_MERKLE(0, false); break;
     }
     if (prof) { prof->end(2, s); prof->begin(3, s); }
