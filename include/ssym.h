@@ -342,6 +342,39 @@ int ssym_stwo_pack_wit(const ssym_stwo_config_t *cfg, const char *json_text, siz
  * *out_words is the capacity of `out`; on return the record length. */
 int ssym_s101_pack_wit(const char *json_text, size_t len, uint32_t *out, size_t *out_words);
 
+/* ------------------------------------------------------------------------- */
+/* Witness ingestion on the GPU                  */
+/* ------------------------------------------------------------------------- */
+
+/* Per-witness ingestion flag. */
+#define SSYM_WIT_OK 0    /* packed                                                              */
+#define SSYM_WIT_SHAPE 1 /* well-typed but ill-shaped (= *shape_reject of ssym_stwo_pack_wit)     */
+#define SSYM_WIT_PARSE 2 /* not a witness of the program's types (= SSYM_ERR_PARSE)              */
+#define SSYM_WIT_SLOW 3  /* internal: text outside the GPU tokeniser's fast path, re-parsed on the host before the call returns */
+
+/* n `.wit` JSON texts (the files `simfony run --witness` reads, simfony-cli/src/main.rs:77-81; witness i = bytes
+ * [offsets[i], offsets[i+1]) of `text`) -> n packed proofs, tokenised and packed ON THE GPU (one CTA per witness,
+ * csrc/wit_kernels.cu).  Same result as n calls of ssym_stwo_pack_wit: flags[i] = SSYM_WIT_OK / _SHAPE / _PARSE, and the
+ * record of a flagged witness is zero-filled.  Texts using grammar the generator never emits (JSON escapes, `_` separators,
+ * upper-case hex, redundant parentheses, trailing commas, decimal literals above 64 bits) and malformed ones are detected on
+ * the GPU and re-parsed by the host parser, so the accepted grammar is exactly that of ssym_stwo_pack_wit.
+ *  text / offsets / packed_out (n * stride_words) / flags (n u32) all live in `memspace`.  Synchronous. */
+int ssym_stwo_pack_wit_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const char *text, const uint64_t *offsets,
+                             size_t n, uint32_t *packed_out, uint32_t *flags, int memspace);
+
+/* The token skeleton the GPU tokeniser checks witness value `name` (0 COMMITMENTS, 1 DECOMMITMENTS, 2 OODS_EVALS,
+ * 3 FRI_COMMITMENTS, 4 FRI_DECOMMITMENTS, 5 POW_NONCE; stwo-verifier/src/main.simf:9-25) against, one byte per token
+ * ( ) [ ] , L = `list!`  N = integer literal, and for the k-th literal the packed word it lands in | width << 28 (0 u32, 1 u64, 2 u256).
+ * On entry *skel_len / *slot_cnt are the capacities, on return the lengths (SSYM_ERR_NOMEM if too small; NULL buffers query the sizes). */
+int ssym_stwo_wit_skeleton(const ssym_stwo_config_t *cfg, int name, uint8_t *skel, size_t *skel_len, uint32_t *slots, size_t *slot_cnt);
+
+/* `simfony run verifier --witness w_i` for n witness TEXTS: ssym_stwo_pack_wit_batch + ssym_stwo_verify_batch without the
+ * packed proofs ever leaving the GPU.  For SSYM_MEM_HOST the text is streamed in chunks (H2D of chunk k+1 under the
+ * tokeniser + verifier kernels of chunk k).  A witness whose flag is not SSYM_WIT_OK is rejected with SSYM_ST_SHAPE set.
+ *  accept_bits ((n+31)/32 words), status (NULL or n), flags (NULL or n) live in `memspace`.  Synchronous. */
+int ssym_stwo_verify_wit_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const char *text, const uint64_t *offsets,
+                               size_t n, uint32_t *accept_bits, uint32_t *status, uint32_t *flags, int memspace);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

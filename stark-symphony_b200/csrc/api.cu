@@ -14,6 +14,7 @@
 #include "prover_kernels.cuh"
 #include "s101_kernels.cuh"
 #include "stwo_kernels.cuh"
+#include "wit_kernels.cuh"
 
 using namespace ssym;
 
@@ -114,6 +115,14 @@ struct ssym_ctx {
     DevBuf prv_tw[2], prv_itw[2], prv_vanish, prv_flag, prv_seeds, prv_out;
     DevBuf prv_scratch[9];
     uint32_t prv_T = 0, prv_G = 0;
+    // GPU .wit ingestion: token skeleton / slot tables per config, double-buffered text + packed staging, pinned flag mirrors
+    DevBuf wit_skel, wit_slots, wit_text[2], wit_offs[2], wit_packed[2], wit_flags[2];
+    WitTables wit_tab{};
+    uint32_t wit_Q = 0, wit_L = 0xffffffffu, wit_G = 0;
+    uint32_t *wit_hflags[2] = {nullptr, nullptr};
+    uint64_t *wit_hoffs[2] = {nullptr, nullptr};
+    size_t wit_hcap = 0;
+    cudaEvent_t ev_wit_flags[2] = {nullptr, nullptr}, ev_wit_parsed[2] = {nullptr, nullptr};
     // stark101 scratch
     DevBuf s101_ctx;
     // jets staging
@@ -146,6 +155,8 @@ int ssym_create(int device, ssym_ctx_t **out) {
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wit_flags[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wit_parsed[i], cudaEventDisableTiming));
     }
     int prio_lo = 0, prio_hi = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -185,7 +196,13 @@ void ssym_destroy(ssym_ctx_t *c) {
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(c->ev_h2d[i]);
         cudaEventDestroy(c->ev_done[i]);
+        cudaEventDestroy(c->ev_wit_flags[i]);
+        cudaEventDestroy(c->ev_wit_parsed[i]);
+        c->wit_text[i].release(); c->wit_offs[i].release(); c->wit_packed[i].release(); c->wit_flags[i].release();
+        if (c->wit_hflags[i]) cudaFreeHost(c->wit_hflags[i]);
+        if (c->wit_hoffs[i]) cudaFreeHost(c->wit_hoffs[i]);
     }
+    c->wit_skel.release(); c->wit_slots.release();
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -417,6 +434,339 @@ extern "C" int ssym_set_host_async(ssym_ctx_t *c, int on) {
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     c->host_async = on != 0;
     return SSYM_OK;
+}
+
+/* ---- GPU .wit ingestion ------------------------------------------------------------------------------ */
+namespace {
+// Token skeletons and literal slots of the six witness values for one configuration; the shapes are those of the program's
+// witness types (stwo-verifier/src/main.simf:9-25, evals/verify.simf:20-36, fri/verify.simf:15-21), the same walk as
+// ssym_stwo_pack_wit (csrc/witness.cpp).
+struct WitSkeleton {
+    std::vector<uint8_t> skel;
+    std::vector<uint32_t> slots;
+    uint32_t skel_off[WIT_NAMES], skel_len[WIT_NAMES], slot_off[WIT_NAMES], slot_cnt[WIT_NAMES];
+    int cur = -1;
+    void begin(int name) { cur = name; skel_off[name] = (uint32_t)skel.size(); slot_off[name] = (uint32_t)slots.size(); }
+    void end() { skel_len[cur] = (uint32_t)skel.size() - skel_off[cur]; slot_cnt[cur] = (uint32_t)slots.size() - slot_off[cur]; }
+    void t(const char *toks) { for (; *toks; toks++) skel.push_back((uint8_t)*toks); }
+    void num(uint32_t word, uint32_t kind) { skel.push_back('N'); slots.push_back(word | (kind << 28)); }
+    void qm31(uint32_t word) { // ((a, b), (c, d))
+        t("((");
+        num(word, WIT_KIND_U32); t(","); num(word + 1, WIT_KIND_U32);
+        t("),(");
+        num(word + 2, WIT_KIND_U32); t(","); num(word + 3, WIT_KIND_U32);
+        t("))");
+    }
+    void digest_list(uint32_t word, uint32_t count) { // list![d0, d1, ...]
+        t("L[");
+        for (uint32_t k = 0; k < count; k++) { if (k) t(","); num(word + 8 * k, WIT_KIND_U256); }
+        t("]");
+    }
+};
+
+void build_wit_skeleton(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, WitSkeleton &w) {
+    const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers, G = cfg.lde_log;
+    w.begin(0); // COMMITMENTS: (u256, u256, u256)
+    w.t("(");
+    for (uint32_t i = 0; i < 3; i++) { if (i) w.t(","); w.num(lo.off_commit + 8 * i, WIT_KIND_U256); }
+    w.t(")");
+    w.end();
+    w.begin(1); // DECOMMITMENTS: [(([[u32; 1]; 4], List<u256, 32>), ([u32; 16], List<u256, 32>)); Q]
+    w.t("[");
+    for (uint32_t q = 0; q < Q; q++) {
+        if (q) w.t(",");
+        w.t("(([");
+        for (uint32_t i = 0; i < SSYM_NUM_COLUMNS; i++) { if (i) w.t(","); w.t("["); w.num(lo.off_qvals + 20 * q + i, WIT_KIND_U32); w.t("]"); }
+        w.t("],");
+        w.digest_list(lo.off_trace_sib + q * G * 8, G);
+        w.t("),([");
+        for (uint32_t i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) { if (i) w.t(","); w.num(lo.off_qvals + 20 * q + 4 + i, WIT_KIND_U32); }
+        w.t("],");
+        w.digest_list(lo.off_cp_sib + q * G * 8, G);
+        w.t("))");
+    }
+    w.t("]");
+    w.end();
+    w.begin(2); // OODS_EVALS: ([[QM31; 1]; 4], [QM31; 16])
+    w.t("([");
+    for (uint32_t i = 0; i < SSYM_NUM_COLUMNS; i++) { if (i) w.t(","); w.t("["); w.qm31(lo.off_oods_trace + 4 * i); w.t("]"); }
+    w.t("],[");
+    for (uint32_t i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) { if (i) w.t(","); w.qm31(lo.off_oods_cp + 4 * i); }
+    w.t("])");
+    w.end();
+    w.begin(3); // FRI_COMMITMENTS: (u256, [u256; L], QM31)
+    w.t("(");
+    w.num(lo.off_fri_first_root, WIT_KIND_U256);
+    w.t(",[");
+    for (uint32_t i = 0; i < L; i++) { if (i) w.t(","); w.num(lo.off_fri_inner_root + 8 * i, WIT_KIND_U256); }
+    w.t("],");
+    w.qm31(lo.off_last_coeff);
+    w.t(")");
+    w.end();
+    w.begin(4); // FRI_DECOMMITMENTS: ([(QM31, List<u256, 32>); Q], [[(QM31, List<u256, 32>); Q]; L])
+    w.t("(");
+    for (uint32_t l = 0; l <= L; l++) {
+        if (l == 1) w.t(",[");
+        else if (l > 1) w.t(",");
+        const uint32_t n_sib = G - 1 - l;
+        w.t("[");
+        for (uint32_t q = 0; q < Q; q++) {
+            if (q) w.t(",");
+            w.t("(");
+            w.qm31(lo.off_fri_wit + (l * Q + q) * 4);
+            w.t(",");
+            w.digest_list(lo.off_fri_sib[l] + q * n_sib * 8, n_sib);
+            w.t(")");
+        }
+        w.t("]");
+    }
+    w.t(L ? "])" : ",[])");
+    w.end();
+    w.begin(5); // POW_NONCE: u64
+    w.num(lo.off_pow_nonce, WIT_KIND_U64);
+    w.end();
+}
+} // namespace
+
+extern "C" int ssym_stwo_wit_skeleton(const ssym_stwo_config_t *cfg, int name, uint8_t *skel, size_t *skel_len, uint32_t *slots, size_t *slot_cnt) {
+    if (!cfg || !skel_len || !slot_cnt || name < 0 || name >= WIT_NAMES) return fail(SSYM_ERR_USAGE, "bad skeleton arguments");
+    ssym_stwo_layout_t lo;
+    int rc = ssym_stwo_layout(cfg, &lo);
+    if (rc) return rc;
+    WitSkeleton w;
+    build_wit_skeleton(*cfg, lo, w);
+    const size_t need_s = w.skel_len[name], need_n = w.slot_cnt[name];
+    const bool fits = (!skel || *skel_len >= need_s) && (!slots || *slot_cnt >= need_n);
+    if (fits && skel) memcpy(skel, w.skel.data() + w.skel_off[name], need_s);
+    if (fits && slots) memcpy(slots, w.slots.data() + w.slot_off[name], need_n * sizeof(uint32_t));
+    *skel_len = need_s;
+    *slot_cnt = need_n;
+    return fits ? SSYM_OK : fail(SSYM_ERR_NOMEM, "skeleton buffers too small");
+}
+
+static int ensure_wit_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo) {
+    if (c->wit_Q == cfg.n_queries && c->wit_L == cfg.n_fri_layers && c->wit_G == cfg.lde_log) return SSYM_OK;
+    WitSkeleton w;
+    build_wit_skeleton(cfg, lo, w);
+    CUDA_TRY(cudaStreamSynchronize(c->stream)); // the old tables may still be in use
+    CUDA_TRY(c->wit_skel.ensure(w.skel.size()));
+    CUDA_TRY(c->wit_slots.ensure(w.slots.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(c->wit_skel.p, w.skel.data(), w.skel.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->wit_slots.p, w.slots.data(), w.slots.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->wit_tab.skel = c->wit_skel.as<uint8_t>();
+    c->wit_tab.slots = c->wit_slots.as<uint32_t>();
+    for (int k = 0; k < WIT_NAMES; k++) {
+        c->wit_tab.skel_off[k] = w.skel_off[k]; c->wit_tab.skel_len[k] = w.skel_len[k];
+        c->wit_tab.slot_off[k] = w.slot_off[k]; c->wit_tab.slot_cnt[k] = w.slot_cnt[k];
+    }
+    c->wit_Q = cfg.n_queries; c->wit_L = cfg.n_fri_layers; c->wit_G = cfg.lde_log;
+    return SSYM_OK;
+}
+
+static int ensure_wit_host(ssym_ctx *c, size_t m) {
+    if (m <= c->wit_hcap) return SSYM_OK;
+    for (int b = 0; b < 2; b++) {
+        if (c->wit_hflags[b]) cudaFreeHost(c->wit_hflags[b]);
+        if (c->wit_hoffs[b]) cudaFreeHost(c->wit_hoffs[b]);
+        c->wit_hflags[b] = nullptr; c->wit_hoffs[b] = nullptr;
+    }
+    c->wit_hcap = 0;
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaHostAlloc((void **)&c->wit_hflags[b], m * sizeof(uint32_t), cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc((void **)&c->wit_hoffs[b], (m + 1) * sizeof(uint64_t), cudaHostAllocDefault));
+    }
+    c->wit_hcap = m;
+    return SSYM_OK;
+}
+
+// The witnesses the GPU tokeniser handed back (SSYM_WIT_SLOW) through the host parser; h_text(i) gives the text of witness i.
+// Patches the device record / flag of each on stream s and settles h_flags to OK / SHAPE / PARSE.
+template <class TextOf>
+static int wit_slow_path(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, uint32_t *h_flags, size_t m, TextOf h_text, uint32_t *d_packed,
+                         uint32_t *d_flags, cudaStream_t s) {
+    std::vector<uint32_t> rec;
+    for (size_t i = 0; i < m; i++) {
+        if (h_flags[i] == SSYM_WIT_OK) continue;
+        rec.assign(lo.stride_words, 0);
+        const char *txt = nullptr;
+        size_t len = 0;
+        int rc = h_text(i, &txt, &len);
+        if (rc) return rc;
+        int shape = 0;
+        rc = ssym_stwo_pack_wit(&cfg, txt, len, rec.data(), &shape); // zero-fills the record when it flags
+        h_flags[i] = rc != SSYM_OK ? SSYM_WIT_PARSE : shape ? SSYM_WIT_SHAPE : SSYM_WIT_OK;
+        CUDA_TRY(cudaMemcpyAsync(d_packed + i * (size_t)lo.stride_words, rec.data(), (size_t)lo.stride_words * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_flags + i, h_flags + i, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s)); // rec is reused
+    }
+    return SSYM_OK;
+}
+
+static const size_t WIT_CHUNK = 512; // witnesses per streamed chunk (prod: 62 MB of text, 28 MB packed)
+
+// Shared driver of ssym_stwo_pack_wit_batch / ssym_stwo_verify_wit_batch.  verify = false: packed records and flags go to packed_out / flags_out;
+// verify = true: they stay on the GPU and accept bits / status words come out.
+static int wit_batch(ssym_ctx *c, const ssym_stwo_config_t *cfg, const char *text, const uint64_t *offsets, size_t n, bool verify, uint32_t *packed_out,
+                     uint32_t *accept_bits, uint32_t *status, uint32_t *flags_out, int memspace) {
+    if (!c || !cfg || ((!text || !offsets) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    ssym_stwo_layout_t lo;
+    int rc = ssym_stwo_layout(cfg, &lo);
+    if (rc) return rc;
+    if (n == 0) return SSYM_OK;
+    if (n > 0xffffffffull / SSYM_MAX_QUERIES) return fail(SSYM_ERR_USAGE, "batch too large for one call");
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = ssym_join(c);
+    if (rc) return rc;
+    rc = ensure_tables(c, *cfg);
+    if (rc) return rc;
+    rc = ensure_wit_tables(c, *cfg, lo);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    const size_t stride_b = (size_t)lo.stride_words * 4, n_words = (n + 31) / 32;
+    const size_t hc = std::min(WIT_CHUNK, (n + 31) & ~(size_t)31);
+    rc = ensure_wit_host(c, hc);
+    if (rc) return rc;
+
+    // device mirrors of the host inputs of a device-memspace call (only the offsets, and the text of witnesses that need the host parser)
+    std::vector<uint64_t> h_offsets_dev;
+    const uint64_t *h_off = offsets;
+    if (memspace == SSYM_MEM_DEVICE) {
+        h_offsets_dev.resize(n + 1);
+        CUDA_TRY(cudaMemcpyAsync(h_offsets_dev.data(), offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        h_off = h_offsets_dev.data();
+    }
+    for (size_t i = 0; i < n; i++)
+        if (h_off[i + 1] < h_off[i]) return fail(SSYM_ERR_USAGE, "witness offsets must be non-decreasing");
+    uint32_t *d_accept = nullptr, *d_status = nullptr;
+    if (verify) {
+        if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(c->d_accept.ensure(n_words * 4));
+            CUDA_TRY(c->d_status.ensure(n * 4));
+            d_accept = c->d_accept.as<uint32_t>();
+            d_status = c->d_status.as<uint32_t>();
+        } else {
+            d_accept = accept_bits;
+            d_status = status;
+            if (!d_status) { CUDA_TRY(c->d_status.ensure(n * 4)); d_status = c->d_status.as<uint32_t>(); }
+        }
+    }
+
+    if (memspace == SSYM_MEM_HOST) { // size the staging once: growing a buffer mid-call would free memory still in use
+        uint64_t max_text = 0;
+        for (size_t beg = 0; beg < n; beg += hc) max_text = std::max(max_text, h_off[std::min(n, beg + hc)] - h_off[beg]);
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(c->wit_text[b].ensure((size_t)max_text + 16));
+            CUDA_TRY(c->wit_offs[b].ensure((hc + 1) * sizeof(uint64_t)));
+        }
+    }
+    for (int b = 0; b < 2; b++) {
+        if (!(memspace == SSYM_MEM_DEVICE && !verify)) CUDA_TRY(c->wit_packed[b].ensure(hc * stride_b));
+        if (!(memspace == SSYM_MEM_DEVICE && flags_out)) CUDA_TRY(c->wit_flags[b].ensure(hc * sizeof(uint32_t)));
+    }
+    struct Chunk { size_t beg = 0, m = 0; int b = 0; bool live = false; } prev;
+    std::vector<char> slow_text;
+    auto finish = [&](const Chunk &k) -> int {
+        const int b = k.b;
+        CUDA_TRY(cudaEventSynchronize(c->ev_wit_flags[b]));
+        uint32_t *hf = c->wit_hflags[b];
+        uint32_t *d_packed = memspace == SSYM_MEM_DEVICE && !verify ? packed_out + k.beg * (size_t)lo.stride_words : c->wit_packed[b].as<uint32_t>();
+        uint32_t *d_flags = memspace == SSYM_MEM_DEVICE && flags_out ? flags_out + k.beg : c->wit_flags[b].as<uint32_t>();
+        auto text_of = [&](size_t i, const char **txt, size_t *len) -> int {
+            const uint64_t o0 = h_off[k.beg + i], o1 = h_off[k.beg + i + 1];
+            *len = (size_t)(o1 - o0);
+            if (memspace == SSYM_MEM_HOST) { *txt = text + o0; return SSYM_OK; }
+            slow_text.resize(*len + 1);
+            CUDA_TRY(cudaMemcpyAsync(slow_text.data(), text + o0, *len, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            *txt = slow_text.data();
+            return SSYM_OK;
+        };
+        int r = getenv("SSYM_WIT_DEBUG_NOSLOW") ? SSYM_OK /* tests: expose which witnesses left the fast path */
+                                                : wit_slow_path(*cfg, lo, hf, k.m, text_of, d_packed, d_flags, s);
+        if (r) return r;
+        if (verify) {
+            r = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, d_packed, k.m, d_accept + k.beg / 32, d_status + k.beg, nullptr, s);
+            if (r) return r;
+            launch_wit_apply_flags(d_flags, d_status + k.beg, d_accept + k.beg / 32, (uint32_t)k.m, s);
+            c->launches += 1;
+        } else if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(cudaMemcpyAsync(packed_out + k.beg * (size_t)lo.stride_words, d_packed, k.m * stride_b, cudaMemcpyDeviceToHost, s));
+        }
+        if (memspace == SSYM_MEM_HOST && flags_out) memcpy(flags_out + k.beg, hf, k.m * sizeof(uint32_t));
+        CUDA_TRY(cudaEventRecord(c->ev_wit_parsed[b], s)); // staging of this parity is free again once everything above has run
+        return SSYM_OK;
+    };
+
+    for (size_t beg = 0, kidx = 0; beg < n; beg += hc, kidx++) {
+        const size_t m = std::min(hc, n - beg);
+        const int b = (int)(kidx & 1);
+        const uint64_t t0 = h_off[beg], t1 = h_off[beg + m];
+        const uint8_t *d_text;
+        const uint64_t *d_offs;
+        uint32_t *d_packed, *d_flags;
+        if (memspace == SSYM_MEM_HOST) {
+            // staging of this parity was last used by chunk kidx - 2, whose `finish` recorded ev_wit_parsed[b]
+            if (kidx >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_wit_parsed[b], 0));
+            for (size_t i = 0; i <= m; i++) c->wit_hoffs[b][i] = h_off[beg + i] - t0;
+            CUDA_TRY(cudaMemcpyAsync(c->wit_text[b].p, text + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(c->wit_offs[b].p, c->wit_hoffs[b], (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
+            CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
+            d_text = c->wit_text[b].as<uint8_t>();
+            d_offs = c->wit_offs[b].as<uint64_t>();
+        } else {
+            d_text = reinterpret_cast<const uint8_t *>(text);
+            d_offs = offsets + beg;
+        }
+        if (memspace == SSYM_MEM_DEVICE && !verify) {
+            d_packed = packed_out + beg * (size_t)lo.stride_words;
+        } else {
+            d_packed = c->wit_packed[b].as<uint32_t>();
+        }
+        if (memspace == SSYM_MEM_DEVICE && flags_out) {
+            d_flags = flags_out + beg;
+        } else {
+            d_flags = c->wit_flags[b].as<uint32_t>();
+        }
+        CUDA_TRY(cudaMemsetAsync(d_packed, 0, m * stride_b, s));
+        WitParams p;
+        p.text = d_text;
+        p.offsets = d_offs;
+        p.n = (uint32_t)m;
+        p.stride_words = lo.stride_words;
+        p.packed = d_packed;
+        p.flags = d_flags;
+        p.tab = c->wit_tab;
+        launch_wit_pack(p, s);
+        c->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(c->wit_hflags[b], d_flags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaEventRecord(c->ev_wit_flags[b], s));
+        if (prev.live) { rc = finish(prev); if (rc) return rc; }
+        prev.beg = beg; prev.m = m; prev.b = b; prev.live = true;
+    }
+    if (prev.live) { rc = finish(prev); if (rc) return rc; }
+    if (verify && memspace == SSYM_MEM_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(accept_bits, d_accept, n_words * 4, cudaMemcpyDeviceToHost, s));
+        if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    return SSYM_OK;
+}
+
+extern "C" int ssym_stwo_pack_wit_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const char *text, const uint64_t *offsets, size_t n,
+                                        uint32_t *packed_out, uint32_t *flags, int memspace) {
+    if ((!packed_out || !flags) && n) return fail(SSYM_ERR_USAGE, "NULL argument");
+    return wit_batch(c, cfg, text, offsets, n, false, packed_out, nullptr, nullptr, flags, memspace);
+}
+
+extern "C" int ssym_stwo_verify_wit_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const char *text, const uint64_t *offsets, size_t n,
+                                          uint32_t *accept_bits, uint32_t *status, uint32_t *flags, int memspace) {
+    if (!accept_bits && n) return fail(SSYM_ERR_USAGE, "NULL argument");
+    return wit_batch(c, cfg, text, offsets, n, true, nullptr, accept_bits, status, flags, memspace);
 }
 
 /* ---- Stwo prover ------------------------------------------------------------------------------------ */

@@ -82,19 +82,43 @@ __device__ __forceinline__ void sha_iv(uint32_t (&h)[8]) {
 //   4  as 1, but a' = T1 + Sigma0 + Maj is ONE 3-input IADD3 on the ALU pipe instead of two IMADs: with everything on the FMA pipe the
 //      kernel is bound by total issue slots (ncu: 0.72 IPC), so trading two FMA-pipe instructions for one ALU-pipe instruction pays
 //   5  as 4, and the message schedule's w + sigma0 + w[-7] is an IADD3 as well
+//   6  as 1, and the two plain shifts of the message schedule (x >> 3, x >> 10) are IMAD.HI by 2^29 / 2^22 on the FMA pipe
+//      (a 1:1 trade of an ALU-pipe SHF for an FMA-pipe instruction); the multipliers arrive as kernel parameters as well
+//   7  as 6, and one rotation of each big Sigma is built on the FMA pipe: rotr(x, n) = x * 2^(32-n) + hi(x * 2^(32-n))
+//      (IMAD.HI + IMAD replace one SHF)
+struct ShaMul { // opaque (kernel-parameter) constants: 1, 2^29, 2^22, 2^10, 2^7
+    uint32_t one, m29, m22, m10, m7;
+};
+__host__ __device__ inline ShaMul sha_mul_consts() { return ShaMul{1u, 1u << 29, 1u << 22, 1u << 10, 1u << 7}; }
 template <int ADDMODE>
 struct ShaAdd {
-    uint32_t one;
+    uint32_t one, m29, m22, m10, m7;
+    __device__ __forceinline__ ShaAdd(uint32_t o) : one(o), m29(0), m22(0), m10(0), m7(0) {}
+    __device__ __forceinline__ ShaAdd(const ShaMul &m) : one(m.one), m29(m.m29), m22(m.m22), m10(m.m10), m7(m.m7) {}
     __device__ __forceinline__ uint32_t fma(uint32_t a, uint32_t b) const {
         uint32_t d;
         asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
         return d;
     }
+    static __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t m) {
+        uint32_t d;
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(m));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t rot_fma(uint32_t x, uint32_t m) { // rotr(x, n) with m = 2^(32-n)
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(m), "r"(mulhi(x, m)));
+        return d;
+    }
+    __device__ __forceinline__ uint32_t ssig0(uint32_t x) const { return rotr32(x, 7) ^ rotr32(x, 18) ^ (ADDMODE >= 6 ? mulhi(x, m29) : (x >> 3)); }
+    __device__ __forceinline__ uint32_t ssig1(uint32_t x) const { return rotr32(x, 17) ^ rotr32(x, 19) ^ (ADDMODE >= 6 ? mulhi(x, m22) : (x >> 10)); }
+    __device__ __forceinline__ uint32_t bSig0(uint32_t x) const { return rotr32(x, 2) ^ rotr32(x, 13) ^ (ADDMODE >= 7 ? rot_fma(x, m10) : rotr32(x, 22)); }
+    __device__ __forceinline__ uint32_t bSig1(uint32_t x) const { return rotr32(x, 6) ^ rotr32(x, 11) ^ (ADDMODE >= 7 ? rot_fma(x, m7) : rotr32(x, 25)); }
     __device__ __forceinline__ uint32_t t1(uint32_t a, uint32_t b) const { return ADDMODE >= 1 ? fma(a, b) : a + b; }    // T1 chain
     __device__ __forceinline__ uint32_t rnd(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE == 2 || ADDMODE >= 4) ? fma(a, b) : a + b; } // rest of the round
     __device__ __forceinline__ uint32_t sch(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE >= 4) ? fma(a, b) : a + b; }  // message schedule
     // a' = t1 + Sigma0 + Maj
-    __device__ __forceinline__ uint32_t rnd3(uint32_t t1v, uint32_t s0, uint32_t mj) const { return ADDMODE >= 4 ? t1v + s0 + mj : rnd(t1v, rnd(s0, mj)); }
+    __device__ __forceinline__ uint32_t rnd3(uint32_t t1v, uint32_t s0, uint32_t mj) const { return (ADDMODE == 4 || ADDMODE == 5) ? t1v + s0 + mj : rnd(t1v, rnd(s0, mj)); }
     // w + sigma0 + w9 + sigma1
     __device__ __forceinline__ uint32_t sch4(uint32_t w, uint32_t s0, uint32_t w9, uint32_t s1) const {
         return ADDMODE == 5 ? fma(w + s0 + w9, s1) : sch(sch(w, s0), sch(w9, s1));
@@ -103,9 +127,9 @@ struct ShaAdd {
 
 #define SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, h, kw)                        \
     {                                                                        \
-        uint32_t t1_ = A.t1(A.t1(h, kw), A.t1(Sig1(e), Ch(e, f, g)));        \
+        uint32_t t1_ = A.t1(A.t1(h, kw), A.t1(A.bSig1(e), Ch(e, f, g)));     \
         (d) = A.rnd(d, t1_);                                                 \
-        (h) = A.rnd3(t1_, Sig0(a), Maj(a, b, c));                            \
+        (h) = A.rnd3(t1_, A.bSig0(a), Maj(a, b, c));                         \
     }
 
 // One compression of `h` with the 16-word block `w` (w is consumed: it becomes the rolling schedule).
@@ -119,7 +143,7 @@ __device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int i = (t + j) & 15;
-                w[i] = A.sch4(w[i], sig0(w[(i + 1) & 15]), w[(i + 9) & 15], sig1(w[(i + 14) & 15]));
+                w[i] = A.sch4(w[i], A.ssig0(w[(i + 1) & 15]), w[(i + 9) & 15], A.ssig1(w[(i + 14) & 15]));
             }
         }
         SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.t1(w[(t + 0) & 15], K.k[t + 0]));
@@ -133,7 +157,7 @@ __device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
-__device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]) { sha_compress<0>(h, w, ShaAdd<0>{1u}); }
+__device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]) { sha_compress<0>(h, w, ShaAdd<0>(1u)); }
 
 // Compression of the constant padding block that ends every 64-byte message.
 template <int ADDMODE>
@@ -196,7 +220,7 @@ __device__ __forceinline__ void sha_compress_rolled(uint32_t (&h)[8], uint32_t (
         if (grp) {
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                w[i] = A.sch4(w[i], sig0(w[(i + 1) & 15]), w[(i + 9) & 15], sig1(w[(i + 14) & 15]));
+                w[i] = A.sch4(w[i], A.ssig0(w[(i + 1) & 15]), w[(i + 9) & 15], A.ssig1(w[(i + 14) & 15]));
         }
         const uint4 k0 = c_sha_k4.v[grp * 4 + 0], k1 = c_sha_k4.v[grp * 4 + 1], k2 = c_sha_k4.v[grp * 4 + 2], k3 = c_sha_k4.v[grp * 4 + 3];
         SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.t1(w[0], k0.x), A.t1(w[1], k0.y), A.t1(w[2], k0.z), A.t1(w[3], k0.w));
@@ -235,7 +259,7 @@ __device__ __forceinline__ void sha256_64B(uint32_t (&w)[16], uint32_t (&out)[8]
     sha_compress<ADDMODE>(out, w, A);
     sha_compress_pad64<ADDMODE>(out, A);
 }
-__device__ __forceinline__ void sha256_64B(uint32_t (&w)[16], uint32_t (&out)[8]) { sha256_64B<0>(w, out, ShaAdd<0>{1u}); }
+__device__ __forceinline__ void sha256_64B(uint32_t (&w)[16], uint32_t (&out)[8]) { sha256_64B<0>(w, out, ShaAdd<0>(1u)); }
 
 // sha256_pair(left, right)
 template <int ADDMODE>
@@ -245,7 +269,7 @@ __device__ __forceinline__ void sha256_pair(const uint32_t (&l)[8], const uint32
     for (int i = 0; i < 8; i++) { w[i] = l[i]; w[8 + i] = r[i]; }
     sha256_64B<ADDMODE>(w, out, A);
 }
-__device__ __forceinline__ void sha256_pair(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8]) { sha256_pair<0>(l, r, out, ShaAdd<0>{1u}); }
+__device__ __forceinline__ void sha256_pair(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8]) { sha256_pair<0>(l, r, out, ShaAdd<0>(1u)); }
 
 // SHA-256 of a short message of `NBYTES` (multiple of 4, <= 52) given as words: one compression.
 // Covers sha256(u256) (32 B), sha256_32 (4 B), trace / QM31 leaves (16 B), channel draws (36 B),
@@ -264,7 +288,7 @@ __device__ __forceinline__ void sha256_short(const uint32_t (&m)[NWORDS], uint32
     sha_compress<ADDMODE>(out, w, A);
 }
 template <int NWORDS>
-__device__ __forceinline__ void sha256_short(const uint32_t (&m)[NWORDS], uint32_t (&out)[8]) { sha256_short<NWORDS, 0>(m, out, ShaAdd<0>{1u}); }
+__device__ __forceinline__ void sha256_short(const uint32_t (&m)[NWORDS], uint32_t (&out)[8]) { sha256_short<NWORDS, 0>(m, out, ShaAdd<0>(1u)); }
 
 // SHA-256 of an arbitrary message of `nwords` 32-bit big-endian words, word i supplied by `get(i)`.
 // One compression body in a rolled block loop: compact code for the transcript kernels, where

@@ -342,8 +342,8 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t (&d)[8
 //   cp    : pre 0 = SHA-256(16 words)                      hash_node_m31_cp      hasher.simf:93-97
 //   fri   : pre 0 = SHA-256(e0), pre 1 = SHA-256(e1), pre 2 = sha256_pair        fri/layers.simf:40-48
 template <int ADDMODE, bool ROLLED>
-__global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, uint32_t one) {
-    const ShaAdd<ADDMODE> A{one};
+__global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, ShaMul mul) {
+    const ShaAdd<ADDMODE> A(mul);
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     // warp -> (chain type rank, group); ranks are ordered longest chain first: 0 = CP, 1 = FRI layer 0, 2 = trace,
@@ -560,8 +560,8 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     static const int addmode = [] { const char *e = getenv("SSYM_ADDMODE"); return e ? atoi(e) : SSYM_DEFAULT_ADDMODE; }();
     static const int rolled = [] { const char *e = getenv("SSYM_ROLLED"); return e ? atoi(e) : SSYM_DEFAULT_ROLLED; }();
     const uint32_t grid = (uint32_t)((warps + 3) / 4);
-#define SSYM_LAUNCH_MERKLE(AM, RL) stwo_merkle_kernel<AM, RL><<<grid, 128, 0, s>>>(p, groups, 1u)
-    switch (addmode * 2 + (rolled ? 1 : 0)) { // `one` = 1 must stay opaque to ptxas
+#define SSYM_LAUNCH_MERKLE(AM, RL) stwo_merkle_kernel<AM, RL><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts())
+    switch (addmode * 2 + (rolled ? 1 : 0)) { // the multipliers (1, 2^k) must stay opaque to ptxas
     case 1: SSYM_LAUNCH_MERKLE(0, true); break;
     case 2: SSYM_LAUNCH_MERKLE(1, false); break;
     case 3: SSYM_LAUNCH_MERKLE(1, true); break;
@@ -571,6 +571,8 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     case 7: SSYM_LAUNCH_MERKLE(3, true); break;
     case 9: SSYM_LAUNCH_MERKLE(4, true); break;
     case 11: SSYM_LAUNCH_MERKLE(5, true); break;
+    case 13: SSYM_LAUNCH_MERKLE(6, true); break;
+    case 15: SSYM_LAUNCH_MERKLE(7, true); break;
     default: SSYM_LAUNCH_MERKLE(0, false); break;
     }
     if (prof) { prof->end(2, s); prof->begin(3, s); }

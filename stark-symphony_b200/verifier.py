@@ -184,16 +184,44 @@ class Verifier:
         check(self.lib.ssym_stark101_verify_batch(self.h, _ptr(blob), _ptr(offsets), n, _ptr(accept), _ptr(status), tptr, space))
         return accept, status, traces
 
+    # ---- `.wit` text in (GPU tokeniser, csrc/wit_kernels.cu) ---------------------------------------------
+    def stwo_pack_wit_batch(self, text, offsets, cfg: StwoConfig):
+        """n `.wit` JSON texts (concatenated in `text`, witness i = bytes [offsets[i], offsets[i+1])) -> (packed (n, stride_words),
+        flags (n)) tokenised and packed on the GPU; flags: WIT_OK / WIT_SHAPE / WIT_PARSE (include/ssym.h).  `text`: numpy uint8
+        array (host) or CUDA uint8 tensor; `offsets`: uint64 array / int64 tensor in the same memory space."""
+        lo = stwo_layout(cfg)
+        n = (offsets.numel() if hasattr(offsets, "numel") else offsets.size) - 1
+        space = self._space(text)
+        if space == MEM_DEVICE:
+            import torch
+
+            packed = torch.empty((n, lo.stride_words), dtype=torch.int32, device=text.device)
+            flags = torch.empty(n, dtype=torch.int32, device=text.device)
+        else:
+            packed = np.zeros((n, lo.stride_words), dtype=np.uint32)
+            flags = np.zeros(n, dtype=np.uint32)
+        check(self.lib.ssym_stwo_pack_wit_batch(self.h, C.byref(cfg), _ptr(text), _ptr(offsets), n, _ptr(packed), _ptr(flags), space))
+        return packed, flags
+
+    def stwo_verify_wit_batch(self, text, offsets, cfg: StwoConfig, want_status: bool = False, want_flags: bool = False, accept_out=None):
+        """verify_proof for n witness TEXTS: tokenise + pack + verify on the GPU, the packed proofs never leave it.
+        Returns (accept_bits, status | None, flags | None)."""
+        n = (offsets.numel() if hasattr(offsets, "numel") else offsets.size) - 1
+        space = self._space(text)
+        accept = accept_out if accept_out is not None else self._alloc(text, (n + 31) // 32)
+        status = self._alloc(text, n) if want_status else None
+        flags = self._alloc(text, n) if want_flags else None
+        check(self.lib.ssym_stwo_verify_wit_batch(self.h, C.byref(cfg), _ptr(text), _ptr(offsets), n, _ptr(accept), _ptr(status), _ptr(flags), space))
+        return accept, status, flags
+
     # ---- `simfony run`-shaped convenience ---------------------------------------------------------------
     def run_stwo_wit(self, wit_texts: Sequence[str], preset: str = "prod", mode: int = _lib.MODE_REF_LITERAL):
         """`simfony run main.simf --witness x.wit` for many witnesses: returns (accept: list[bool], status: np.ndarray)."""
         from . import witness
 
         cfg = stwo_config(preset, mode)
-        packed, bad = witness.pack_stwo_wits(wit_texts, cfg)
-        accept, status, _ = self.stwo_verify_batch(packed, cfg, len(wit_texts), want_status=True)
-        status = status.copy()
-        status[bad] |= 1 << 31
+        text, offsets = witness.concat_wit_texts(wit_texts)
+        _, status, _ = self.stwo_verify_wit_batch(text, offsets, cfg, want_status=True)
         return [bool(s == 0) for s in status], status
 
     def run_stark101_wit(self, wit_texts: Sequence[str]):

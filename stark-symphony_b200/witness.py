@@ -104,6 +104,52 @@ def pack_stwo_wits(wit_texts: Sequence[str], cfg: StwoConfig) -> Tuple[np.ndarra
     return packed, bad
 
 
+def concat_wit_texts(wit_texts: Sequence) -> Tuple[np.ndarray, np.ndarray]:
+    """[text, ...] -> (uint8 array of the concatenated texts, uint64 offsets [n + 1]) for Verifier.stwo_*_wit_batch."""
+    raws = [t.encode() if isinstance(t, str) else bytes(t) for t in wit_texts]
+    offsets = np.zeros(len(raws) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(r) for r in raws], dtype=np.uint64)
+    return np.frombuffer(b"".join(raws), dtype=np.uint8).copy() if raws else np.zeros(0, dtype=np.uint8), offsets
+
+
+def stwo_wit_from_packed(packed_one: np.ndarray, cfg: StwoConfig) -> Dict[str, Dict[str, str]]:
+    """One packed proof -> the six witnesses in the value syntax of stwo-verifier/scripts/generate_wit.py:139-243 (the inverse of the
+    packers): how proofs made by Verifier.stwo_prove_batch become `.wit` files."""
+    lo = stwo_layout(cfg)
+    w = np.asarray(packed_one, dtype=np.uint32).ravel()
+    Q, L, G = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log
+
+    def dig(off: int) -> str:
+        return "0x" + "".join(f"{int(x):08x}" for x in w[off:off + 8])
+
+    def qm(off: int) -> str:
+        return _qm31_str([int(x) for x in w[off:off + 4]])
+
+    def diglist(off: int, count: int) -> str:
+        return "list![" + ", ".join(dig(off + 8 * k) for k in range(count)) + "]"
+
+    commitments = "(" + ", ".join(dig(lo.off_commit + 8 * i) for i in range(3)) + ")"
+    items = []
+    for q in range(Q):
+        tv = "[" + ", ".join(f"[{int(w[lo.off_qvals + 20 * q + i])}]" for i in range(4)) + "]"
+        cv = "[" + ", ".join(str(int(w[lo.off_qvals + 20 * q + 4 + i])) for i in range(16)) + "]"
+        items.append(f"(({tv}, {diglist(lo.off_trace_sib + q * G * 8, G)}), ({cv}, {diglist(lo.off_cp_sib + q * G * 8, G)}))")
+    oods = "([" + ", ".join("[" + qm(lo.off_oods_trace + 4 * i) + "]" for i in range(4)) + "], [" + ", ".join(qm(lo.off_oods_cp + 4 * i) for i in range(16)) + "])"
+
+    def layer_str(l: int) -> str:
+        ns = G - 1 - l
+        return "[" + ", ".join(f"({qm(lo.off_fri_wit + (l * Q + q) * 4)}, {diglist(lo.off_fri_sib[l] + q * ns * 8, ns)})" for q in range(Q)) + "]"
+
+    fri_commitments = f"({dig(lo.off_fri_first_root)}, [" + ", ".join(dig(lo.off_fri_inner_root + 8 * i) for i in range(L)) + f"], {qm(lo.off_last_coeff)})"
+    fri_decommitments = f"({layer_str(0)}, [" + ", ".join(layer_str(l) for l in range(1, L + 1)) + "])"
+    nonce = (int(w[lo.off_pow_nonce]) << 32) | int(w[lo.off_pow_nonce + 1])
+    vals = {
+        "COMMITMENTS": commitments, "DECOMMITMENTS": "[" + ", ".join(items) + "]", "OODS_EVALS": oods,
+        "FRI_COMMITMENTS": fri_commitments, "FRI_DECOMMITMENTS": fri_decommitments, "POW_NONCE": str(nonce),
+    }
+    return {k: {"value": v, "type": ""} for k, v in vals.items()}
+
+
 def pack_stwo_proof_json(data: Dict[str, Any], cfg: StwoConfig) -> np.ndarray:
     packed, bad = pack_stwo_wits([json.dumps(stwo_wit_from_proof_json(data))], cfg)
     if bad[0]:

@@ -1,0 +1,239 @@
+"""GPU `.wit` ingestion (csrc/wit_kernels.cu, ssym_stwo_pack_wit_batch / ssym_stwo_verify_wit_batch).
+
+CPU part: the token skeleton + literal slots the GPU checks against are validated with the independent Python reader
+(oracle/witparse.py): tokenising the reference's fixtures gives exactly the skeleton, and scattering the literals through
+the slots gives exactly the packed record.  GPU part: the tokeniser against the host parser and the Python reader on the
+fixtures, on re-formatted texts, on texts outside its fast path (which it must hand to the host parser) and on malformed
+ones; then text -> accept bits end to end against the oracle."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import oracle as O
+from oracle import witparse as W
+
+NAMES = ["COMMITMENTS", "DECOMMITMENTS", "OODS_EVALS", "FRI_COMMITMENTS", "FRI_DECOMMITMENTS", "POW_NONCE"]
+
+
+@pytest.fixture(scope="module")
+def S():
+    import stark_symphony_b200 as S
+
+    S.load()
+    return S
+
+
+def skeleton(S, cfg, name):
+    lib = S.load()
+    ns, nn = C.c_size_t(0), C.c_size_t(0)
+    assert lib.ssym_stwo_wit_skeleton(C.byref(cfg), name, None, C.byref(ns), None, C.byref(nn)) == 0
+    skel = np.zeros(ns.value, dtype=np.uint8)
+    slots = np.zeros(max(nn.value, 1), dtype=np.uint32)
+    assert lib.ssym_stwo_wit_skeleton(C.byref(cfg), name, C.c_void_p(skel.ctypes.data), C.byref(ns), C.c_void_p(slots.ctypes.data), C.byref(nn)) == 0
+    return skel.tobytes().decode(), slots[: nn.value]
+
+
+@pytest.mark.parametrize("preset", ["prod", "testing"])
+def test_skeleton_matches_reference_fixture(S, preset):
+    """Tokens of the generator's output == skeleton; literals scattered through the slots == the packed record."""
+    cfg = S.stwo_config(preset, S.MODE_REF_LITERAL)
+    lo = S.stwo_layout(cfg)
+    text = open(os.path.join(GOLDEN, f"stwo_proof_{preset}.wit")).read()
+    wit = json.loads(text)
+    rec = np.zeros(lo.stride_words, dtype=np.uint32)
+    for k, name in enumerate(NAMES):
+        skel, slots = skeleton(S, cfg, k)
+        toks = W.tokenize(wit[name]["value"])
+        classes = "".join("L" if t == "list!" else "N" if t[0].isdigit() else t for t in toks)
+        assert classes == skel, name
+        lits = [int(t, 0) for t in toks if t[0].isdigit()]
+        assert len(lits) == len(slots)
+        for v, slot in zip(lits, slots):
+            off, kw = int(slot) & 0x0FFFFFFF, {0: 1, 1: 2, 2: 8}[int(slot) >> 28]
+            assert v < 1 << (32 * kw)
+            rec[off:off + kw] = [(v >> (32 * (kw - 1 - j))) & 0xFFFFFFFF for j in range(kw)]
+    expect, bad = S.witness.pack_stwo_wits([text], cfg)
+    assert not bad[0] and (rec == expect).all()
+    o_rec, o_bad = W.pack_stwo(W.load_wit(text), cfg.n_queries, cfg.n_fri_layers, cfg.lde_log)
+    assert not o_bad and (rec == o_rec).all()
+
+
+def test_skeleton_query_and_errors(S):
+    lib = S.load()
+    cfg = S.stwo_config("prod", 0)
+    ns, nn = C.c_size_t(1), C.c_size_t(1)
+    buf = np.zeros(1, dtype=np.uint8)
+    assert lib.ssym_stwo_wit_skeleton(C.byref(cfg), 4, C.c_void_p(buf.ctypes.data), C.byref(ns), None, C.byref(nn)) == -4  # SSYM_ERR_NOMEM
+    assert ns.value > 1000 and nn.value == 9 * 16 * 4 + 16 * sum(12 - l for l in range(9))
+    assert lib.ssym_stwo_wit_skeleton(C.byref(cfg), 6, None, C.byref(ns), None, C.byref(nn)) == -1
+
+
+# ---- GPU --------------------------------------------------------------------------------------------------
+def _variants(text):
+    """(label, text, on the fast path?) — every variant has a defined result under the host parser."""
+    wit = json.loads(text)
+    out = [("generator output", text, True)]
+    out.append(("pretty-printed JSON, reordered names, no type member", json.dumps({k: {"value": wit[k]["value"]} for k in reversed(NAMES)}, indent=2), True))
+    spaced = {k: {"value": "  " + re.sub(r"([(\[\]),])", r"  \1   ", v["value"]) + "  ", "type": "x"} for k, v in wit.items()}
+    out.append(("spaces around all tokens", json.dumps(spaced), True))
+    nl = {k: {"value": re.sub(r"([(\[,])", r"\1 \n\t", v["value"]), "type": "x"} for k, v in wit.items()}
+    out.append(("newlines / tabs in the value text (JSON escapes)", json.dumps(nl), False))
+    out.append(("type member before value", json.dumps({k: {"type": "u32", "value": v["value"]} for k, v in wit.items()}), True))
+    hexed = dict(wit)
+    hexed["POW_NONCE"] = {"value": hex(int(wit["POW_NONCE"]["value"]))}
+    hexed["COMMITMENTS"] = {"value": re.sub(r"0x0*", "0x", wit["COMMITMENTS"]["value"])}
+    out.append(("hex nonce, digests without leading zeros", json.dumps(hexed), True))
+    dec = dict(wit)
+    dec["COMMITMENTS"] = {"value": "(" + ", ".join(str(int(x, 16)) for x in re.findall(r"0x[0-9a-f]+", wit["COMMITMENTS"]["value"])) + ")"}
+    out.append(("decimal u256 literals", json.dumps(dec), False))
+    up = dict(wit)
+    up["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"].upper().replace("0X", "0x")}
+    out.append(("upper-case hex", json.dumps(up), False))
+    us = dict(wit)
+    us["POW_NONCE"] = {"value": wit["POW_NONCE"]["value"][0] + "_" + wit["POW_NONCE"]["value"][1:]}
+    out.append(("digit separators", json.dumps(us), False))
+    tc = dict(wit)
+    tc["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"][:-1] + ",)"}
+    out.append(("trailing comma", json.dumps(tc), False))
+    par = dict(wit)
+    par["POW_NONCE"] = {"value": "(" + wit["POW_NONCE"]["value"] + ")"}
+    out.append(("parenthesised value", json.dumps(par), False))
+    esc = json.dumps(wit).replace('"value": "(', '"value": "\\u0028', 1)
+    out.append(("JSON escape", esc, False))
+    extra = dict(wit)
+    extra["EXTRA"] = {"value": "7"}
+    out.append(("unknown extra witness", json.dumps(extra), False))
+    return out
+
+
+def _bad_variants(text):
+    """(label, text, expected flag) — witnesses `simfony run` would refuse."""
+    wit = json.loads(text)
+    out = []
+    longer = dict(wit)
+    longer["DECOMMITMENTS"] = {"value": wit["DECOMMITMENTS"]["value"].replace("list![", "list![0x01, ", 1)}
+    out.append(("one sibling too many", json.dumps(longer), 1))
+    shorter = dict(wit)
+    shorter["FRI_DECOMMITMENTS"] = {"value": re.sub(r"list!\[0x[0-9a-f]+, ", "list![", wit["FRI_DECOMMITMENTS"]["value"], count=1)}
+    out.append(("one FRI sibling too few", json.dumps(shorter), 1))
+    big = dict(wit)
+    big["OODS_EVALS"] = {"value": wit["OODS_EVALS"]["value"].replace("((1, 0)", "((4294967296, 0)", 1)}
+    assert big["OODS_EVALS"] != wit["OODS_EVALS"]
+    out.append(("u32 literal out of range", json.dumps(big), 2))
+    out.append(("missing witness", json.dumps({k: v for k, v in wit.items() if k != "POW_NONCE"}), 2))
+    out.append(("truncated file", text[: len(text) // 2], 2))
+    out.append(("not JSON", "hello", 2))
+    out.append(("empty", "", 2))
+    junk = dict(wit)
+    junk["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"].replace(", ", "; ", 1)}
+    out.append(("bad separator", json.dumps(junk), 2))
+    stray = dict(wit)
+    stray["DECOMMITMENTS"] = {"value": wit["DECOMMITMENTS"]["value"].replace("list![", "ist![", 1)}
+    out.append(("broken list! keyword", json.dumps(stray), 2))
+    arr = dict(wit)
+    arr["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"].replace("(", "[").replace(")", "]")}
+    out.append(("array where a tuple is expected", json.dumps(arr), 2))
+    return out
+
+
+def _host_reference(S, cfg, texts):
+    lo = S.stwo_layout(cfg)
+    lib = S.load()
+    packed = np.zeros((len(texts), lo.stride_words), dtype=np.uint32)
+    flags = np.zeros(len(texts), dtype=np.uint32)
+    for i, t in enumerate(texts):
+        raw = t.encode()
+        shape = C.c_int(0)
+        rc = lib.ssym_stwo_pack_wit(C.byref(cfg), raw, len(raw), C.c_void_p(packed[i].ctypes.data), C.byref(shape))
+        flags[i] = 2 if rc else 1 if shape.value else 0
+    return packed, flags
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["prod", "testing"])
+def test_gpu_tokeniser_matches_host_parser(S, preset):
+    cfg = S.stwo_config(preset, S.MODE_PROVER_CONSISTENT)
+    text = open(os.path.join(GOLDEN, f"stwo_proof_{preset}.wit")).read()
+    good, bad = _variants(text), _bad_variants(text)
+    texts = [t for _, t, _ in good] + [t for _, t, _ in bad]
+    ref_packed, ref_flags = _host_reference(S, cfg, texts)
+    assert (ref_flags[: len(good)] == 0).all(), [g[0] for g, f in zip(good, ref_flags) if f]
+    assert list(ref_flags[len(good):]) == [f for _, _, f in bad], list(zip([b[0] for b in bad], ref_flags[len(good):]))
+    # the Python reader agrees with the host parser on every well-formed variant
+    for (label, t, _), rec in zip(good, ref_packed):
+        o_rec, o_bad = W.pack_stwo(W.load_wit(t), cfg.n_queries, cfg.n_fri_layers, cfg.lde_log)
+        assert not o_bad and (o_rec == rec).all(), label
+    ver = S.Verifier(0)
+    blob, offsets = S.witness.concat_wit_texts(texts)
+    packed, flags = ver.stwo_pack_wit_batch(blob, offsets, cfg)
+    assert list(flags) == list(ref_flags)
+    assert (packed == ref_packed).all()
+    # device-resident text: same result
+    import torch
+
+    d_packed, d_flags = ver.stwo_pack_wit_batch(torch.from_numpy(blob).cuda(), torch.from_numpy(offsets.astype(np.int64)).cuda(), cfg)
+    assert (d_flags.cpu().numpy().view(np.uint32) == ref_flags).all()
+    assert (d_packed.cpu().numpy().view(np.uint32) == ref_packed).all()
+    # text -> accept bits, against the oracle on the host-packed records
+    accept, status, vflags = ver.stwo_verify_wit_batch(blob, offsets, cfg, want_status=True, want_flags=True)
+    orc = O.Oracle()
+    ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    o_accept, o_status, _ = orc.stwo_verify_batch(ocfg, ref_packed.ravel(), len(texts))
+    o_status = o_status.copy()
+    o_status[ref_flags != 0] |= 1 << 31
+    assert (status == o_status).all()
+    assert list(vflags) == list(ref_flags)
+    for i in range(len(texts)):
+        assert ((int(accept[i // 32]) >> (i % 32)) & 1) == int(o_status[i] == 0), i
+    assert (status[: len(good)] == 0).all()  # PROVER_CONSISTENT accepts the fixture in every formatting
+    acc_list, st = ver.run_stwo_wit(texts, preset, S.MODE_PROVER_CONSISTENT)
+    assert acc_list == [bool(s == 0) for s in o_status]
+    ver.close()
+
+
+@pytest.mark.gpu
+def test_gpu_tokeniser_fast_path_is_taken(S):
+    """The generator's formatting must not fall back to the host parser: SSYM_WIT_DEBUG_NOSLOW makes the slow path an error flag."""
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    text = open(os.path.join(GOLDEN, "stwo_proof_prod.wit")).read()
+    ver = S.Verifier(0)
+    os.environ["SSYM_WIT_DEBUG_NOSLOW"] = "1"
+    try:
+        good = _variants(text)
+        blob, offsets = S.witness.concat_wit_texts([t for _, t, _ in good])
+        _, flags = ver.stwo_pack_wit_batch(blob, offsets, cfg)
+        assert [int(f) == 0 for f in flags] == [fast for _, _, fast in good], list(zip([g[0] for g in good], flags))
+    finally:
+        del os.environ["SSYM_WIT_DEBUG_NOSLOW"]
+    ver.close()
+
+
+@pytest.mark.gpu
+def test_wit_batch_of_distinct_proofs_round_trip(S):
+    """Prover -> packed -> `.wit` text (generator syntax) -> GPU tokeniser == the packed proofs; spans several streamed chunks."""
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    ver = S.Verifier(0)
+    n_distinct, n = 24, 1100
+    proofs = ver.stwo_prove_batch(np.arange(100, 100 + n_distinct, dtype=np.uint64), cfg)
+    texts = [json.dumps(S.witness.stwo_wit_from_packed(proofs[i], cfg)) for i in range(n_distinct)]
+    order = [(7 * i) % n_distinct for i in range(n)]
+    bad_at = {5: '{"COMMITMENTS": 3}', 600: texts[3].replace("list![", "list![0x5, ", 1), 1099: ""}
+    batch = [bad_at.get(i, texts[order[i]]) for i in range(n)]
+    blob, offsets = S.witness.concat_wit_texts(batch)
+    packed, flags = ver.stwo_pack_wit_batch(blob, offsets, cfg)
+    expect_flags = np.zeros(n, dtype=np.uint32)
+    expect_flags[5], expect_flags[600], expect_flags[1099] = 2, 1, 2
+    assert (flags == expect_flags).all()
+    expect = proofs[order].copy()
+    expect[list(bad_at)] = 0
+    assert (packed == expect).all()
+    accept, status, _ = ver.stwo_verify_wit_batch(blob, offsets, cfg, want_status=True)
+    ok = np.array([(int(accept[i // 32]) >> (i % 32)) & 1 for i in range(n)], dtype=bool)
+    assert (ok == (expect_flags == 0)).all()
+    assert (status[expect_flags == 0] == 0).all() and (status[expect_flags != 0] >> 31 == 1).all()
+    ver.close()
