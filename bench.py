@@ -407,6 +407,31 @@ def main():
     e2e_value = total_n * e2e_steps / float(t[0].item())
     e2e_sync_value = total_n * e2e_steps / float(t[1].item())
 
+    # end to end from the reference's own input format: `.wit` JSON TEXT in pinned host memory -> accept bits
+    # (ssym_stwo_verify_wit_batch: text H2D, GPU tokeniser + packer, verifier, D2H bitmap; 122 KB of text per proof)
+    wit_raw = open(os.path.join(ROOT, "tests", "golden", "stwo_proof_prod.wit"), "rb").read()
+    n_wit = 4 * n
+    wit_pinned = torch.empty(len(wit_raw) * n_wit, dtype=torch.uint8).pin_memory()
+    wit_np = wit_pinned.numpy()
+    wit_np.reshape(n_wit, len(wit_raw))[:] = np.frombuffer(wit_raw, dtype=np.uint8)
+    wit_offsets = (np.arange(n_wit + 1, dtype=np.uint64) * np.uint64(len(wit_raw)))
+    acc_wit = torch.empty((n_wit + 31) // 32, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    wit_steps = max(2, min(args.steps, 5))
+    ver.stwo_verify_wit_batch(wit_np, wit_offsets, cfg, accept_out=acc_wit)
+    wl0 = ver.launch_count
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(wit_steps):
+        ver.stwo_verify_wit_batch(wit_np, wit_offsets, cfg, accept_out=acc_wit)
+    wit_s = time.perf_counter() - t0
+    wit_launches = ver.launch_count - wl0
+    assert (np.unpackbits(acc_wit.view(np.uint8), bitorder="little")[:n_wit] == bits[0]).all(), "text path disagrees with the packed path"
+    t = torch.tensor([wit_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wit_value = n_wit * world * wit_steps / float(t[0].item())
+
     if rank == 0:
         peaks = {}
         try:
@@ -424,7 +449,7 @@ def main():
         line = {
             "metric": "stwo_proofs_verified_per_s", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "reference fixture stwo-verifier/tests/data/proof.json (via generate_wit.py) replicated; no synthetic prover exists",
+            "data": "reference fixture stwo-verifier/tests/data/proof.json (via generate_wit.py) replicated (BASELINE configs[1]); distinct GPU-proven proofs: bench_configs.py",
             "config": {"workload": f"stwo-verifier proof.json witness (prod preset: LDE 2^13, 16 queries, 1+8 FRI layers) replicated x{n} per GPU",
                        "mode": args.mode, "batch_per_gpu": n, "accepted": accepted,
                        "l2": f"rotating {copies} distinct device copies of the batch ({copies * n * lo.stride_words * 4 / 1e6:.0f} MB > 126 MB L2)",
@@ -439,6 +464,11 @@ def main():
                             "copies inside the timed region.  `value`: the calls are enqueued back to back (ssym_set_host_async) and synchronised once, so the "
                             "H2D of step k+1 runs under the kernel tail of step k; `sync_call_value`: each call returns with its bitmap in host memory before "
                             "the next starts.  Bound by the host link: compare h2d_gbs_achieved with a plain pinned copy of the same bytes"},
+            "e2e_wit": {"value": wit_value, "unit": "proofs/s", "h2d_bytes_per_step": int(wit_np.nbytes), "d2h_bytes_per_step": int(acc_wit.nbytes),
+                        "steps": wit_steps, "proofs_per_step": n_wit, "h2d_gbs_achieved": wit_value / world * len(wit_raw) / 1e9, "gpu_launches": int(wit_launches),
+                        "note": "ssym_stwo_verify_wit_batch(SSYM_MEM_HOST): the reference's own input, `.wit` JSON text (122 KB per proof, the file `simfony run "
+                                "--witness` reads) in pinned host memory -> GPU tokeniser/packer -> verifier -> bitmap; synchronous calls, text H2D of chunk k+1 under "
+                                "the kernels of chunk k"},
             "gpu_launches": int(launches),
             "kernel_ms": kernel_ms, "serial_ms_per_step": serial_ms_per_step,
             "kernel_ms_note": "per-launch CUDA-event durations from a strictly serial pass (pipeline depth 1) of the same steps; the headline "

@@ -116,7 +116,8 @@ struct ssym_ctx {
     DevBuf prv_scratch[9];
     uint32_t prv_T = 0, prv_G = 0;
     // GPU .wit ingestion: token skeleton / slot tables per config, double-buffered text + packed staging, pinned flag mirrors
-    DevBuf wit_skel, wit_slots, wit_text[2], wit_offs[2], wit_packed[2], wit_flags[2];
+    DevBuf wit_skel, wit_slots, wit_text[2], wit_offs[2], wit_packed[2], wit_flags[2], wit_numpos[2];
+    uint32_t wit_total_slots = 0;
     WitTables wit_tab{};
     uint32_t wit_Q = 0, wit_L = 0xffffffffu, wit_G = 0;
     uint32_t *wit_hflags[2] = {nullptr, nullptr};
@@ -198,7 +199,7 @@ void ssym_destroy(ssym_ctx_t *c) {
         cudaEventDestroy(c->ev_done[i]);
         cudaEventDestroy(c->ev_wit_flags[i]);
         cudaEventDestroy(c->ev_wit_parsed[i]);
-        c->wit_text[i].release(); c->wit_offs[i].release(); c->wit_packed[i].release(); c->wit_flags[i].release();
+        c->wit_text[i].release(); c->wit_offs[i].release(); c->wit_packed[i].release(); c->wit_flags[i].release(); c->wit_numpos[i].release();
         if (c->wit_hflags[i]) cudaFreeHost(c->wit_hflags[i]);
         if (c->wit_hoffs[i]) cudaFreeHost(c->wit_hoffs[i]);
     }
@@ -559,6 +560,7 @@ static int ensure_wit_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg, const s
         c->wit_tab.skel_off[k] = w.skel_off[k]; c->wit_tab.skel_len[k] = w.skel_len[k];
         c->wit_tab.slot_off[k] = w.slot_off[k]; c->wit_tab.slot_cnt[k] = w.slot_cnt[k];
     }
+    c->wit_total_slots = (uint32_t)w.slots.size();
     c->wit_Q = cfg.n_queries; c->wit_L = cfg.n_fri_layers; c->wit_G = cfg.lde_log;
     return SSYM_OK;
 }
@@ -664,6 +666,7 @@ static int wit_batch(ssym_ctx *c, const ssym_stwo_config_t *cfg, const char *tex
     for (int b = 0; b < 2; b++) {
         if (!(memspace == SSYM_MEM_DEVICE && !verify)) CUDA_TRY(c->wit_packed[b].ensure(hc * stride_b));
         if (!(memspace == SSYM_MEM_DEVICE && flags_out)) CUDA_TRY(c->wit_flags[b].ensure(hc * sizeof(uint32_t)));
+        CUDA_TRY(c->wit_numpos[b].ensure(hc * (size_t)c->wit_total_slots * sizeof(uint32_t)));
     }
     struct Chunk { size_t beg = 0, m = 0; int b = 0; bool live = false; } prev;
     std::vector<char> slow_text;
@@ -695,7 +698,6 @@ static int wit_batch(ssym_ctx *c, const ssym_stwo_config_t *cfg, const char *tex
             CUDA_TRY(cudaMemcpyAsync(packed_out + k.beg * (size_t)lo.stride_words, d_packed, k.m * stride_b, cudaMemcpyDeviceToHost, s));
         }
         if (memspace == SSYM_MEM_HOST && flags_out) memcpy(flags_out + k.beg, hf, k.m * sizeof(uint32_t));
-        CUDA_TRY(cudaEventRecord(c->ev_wit_parsed[b], s)); // staging of this parity is free again once everything above has run
         return SSYM_OK;
     };
 
@@ -707,7 +709,7 @@ static int wit_batch(ssym_ctx *c, const ssym_stwo_config_t *cfg, const char *tex
         const uint64_t *d_offs;
         uint32_t *d_packed, *d_flags;
         if (memspace == SSYM_MEM_HOST) {
-            // staging of this parity was last used by chunk kidx - 2, whose `finish` recorded ev_wit_parsed[b]
+            // the text staging of this parity was last read by the tokeniser kernels of chunk kidx - 2
             if (kidx >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_wit_parsed[b], 0));
             for (size_t i = 0; i <= m; i++) c->wit_hoffs[b][i] = h_off[beg + i] - t0;
             CUDA_TRY(cudaMemcpyAsync(c->wit_text[b].p, text + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->copy_stream));
@@ -739,9 +741,12 @@ static int wit_batch(ssym_ctx *c, const ssym_stwo_config_t *cfg, const char *tex
         p.packed = d_packed;
         p.flags = d_flags;
         p.tab = c->wit_tab;
+        p.numpos = c->wit_numpos[b].as<uint32_t>();
+        p.total_slots = c->wit_total_slots;
         launch_wit_pack(p, s);
-        c->launches += 1;
+        c->launches += 2;
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->ev_wit_parsed[b], s)); // the text staging of this parity is free again once the two tokeniser kernels have run
         CUDA_TRY(cudaMemcpyAsync(c->wit_hflags[b], d_flags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaEventRecord(c->ev_wit_flags[b], s));
         if (prev.live) { rc = finish(prev); if (rc) return rc; }

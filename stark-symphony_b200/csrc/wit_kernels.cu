@@ -5,36 +5,9 @@
 namespace ssym {
 namespace {
 
-constexpr int WIT_THREADS = 256;
 constexpr int WIT_MAXQ = 128; // quotes per witness file handled on the GPU (the generator's output has 60)
 
-enum : uint8_t { C_BAD = 0, C_WS, C_NUM, C_STRUCT, C_L, C_LCONT };
-
 __device__ __forceinline__ bool is_ws(uint8_t c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
-
-// exclusive block scan of a pair of counters; `total` = block sums (valid in every thread)
-__device__ __forceinline__ uint2 block_excl_scan(uint2 v, uint2 *s_warp, uint2 &total) {
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint2 inc = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t x = __shfl_up_sync(0xffffffffu, inc.x, off), y = __shfl_up_sync(0xffffffffu, inc.y, off);
-        if (lane >= (uint32_t)off) { inc.x += x; inc.y += y; }
-    }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    uint2 woff = make_uint2(0, 0);
-    total = make_uint2(0, 0);
-#pragma unroll
-    for (int w = 0; w < WIT_THREADS / 32; w++) {
-        const uint2 t = s_warp[w];
-        if ((uint32_t)w < wid) { woff.x += t.x; woff.y += t.y; }
-        total.x += t.x;
-        total.y += t.y;
-    }
-    __syncthreads();
-    return make_uint2(inc.x - v.x + woff.x, inc.y - v.y + woff.y);
-}
 
 __device__ bool str_is(const uint8_t *t, uint32_t s, uint32_t e, const char *lit, uint32_t n) {
     if (e - s != n) return false;
@@ -101,23 +74,242 @@ __device__ bool json_walk(const uint8_t *t, uint32_t len, const uint32_t *q, uin
     return pos == len && k == nq && seen == (1u << WIT_NAMES) - 1;
 }
 
-// One integer literal starting at t[pos] (inside a value that ends at `end`) into its packed slot.
-__device__ bool parse_number(const uint8_t *t, uint32_t pos, uint32_t end, const uint8_t *cls, uint32_t slot, uint32_t *rec) {
+// ---- SWAR helpers (4 text bytes per 32-bit word, little endian: byte 0 = first character) ---------------------------
+// 0x80 in every byte of x that is zero (exact, no cross-byte borrow)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }
+// bit 0 of each byte (b0, b1, b2, b3) -> the 4-bit value b0 | b1 << 1 | b2 << 2 | b3 << 3
+__device__ __forceinline__ uint32_t gather4(uint32_t y) { return ((y & 0x01010101u) * 0x01020408u) >> 24; }
+__device__ __forceinline__ uint32_t word_of(const uint4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+__device__ __forceinline__ bool is_numchar(uint8_t c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'f') || c == 'x'; }
+
+// bits of the class code in the lookup table
+enum : uint8_t { K_NUM = 1, K_STR = 2, K_LC = 4, K_BAD = 8 };
+
+// A witness file seen as aligned 16-byte blocks (the text is read with 128-bit loads only; `head` = offset of its first byte in block 0)
+struct Blocks {
+    const uint4 *base;
+    uint32_t head, nblk, len;
+    __device__ __forceinline__ uint4 load(uint32_t blk) const { return blk < nblk ? __ldg(base + blk) : make_uint4(0, 0, 0, 0); }
+    // 16-bit mask of the bytes of block `blk` whose file position lies in [lo, hi)
+    __device__ __forceinline__ uint32_t valid(uint32_t blk, uint32_t lo, uint32_t hi) const {
+        const int rel0 = (int)(blk * 16u) - (int)head;
+        const int a = max(0, (int)lo - rel0), b = min(16, (int)hi - rel0);
+        return a < b ? ((1u << b) - 1u) & ~((1u << a) - 1u) : 0u;
+    }
+};
+
+constexpr int LEX_WARPS = 4;
+
+// Kernel 1: one warp per witness.  Phase 0 finds the JSON strings (quote positions; a backslash anywhere hands the file to the host parser),
+// lane 0 walks the JSON level, phase A streams every value through the warp 512 bytes at a time: bytes are classified through a lookup
+// table, token starts are numbered with a warp scan, every token is compared with the skeleton and the position of every integer
+// literal is recorded for kernel 2.
+__global__ void __launch_bounds__(32 * LEX_WARPS) wit_lex_kernel(WitParams p) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_q[LEX_WARPS][WIT_MAXQ];
+    __shared__ uint32_t s_span[LEX_WARPS][3 * WIT_NAMES];
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
+        uint8_t k = K_BAD;
+        if (is_ws((uint8_t)c)) k = 0;
+        else if (is_numchar((uint8_t)c)) k = K_NUM;
+        else if (c == '(' || c == ')' || c == '[' || c == ']' || c == ',' || c == 'l') k = K_STR;
+        else if (c == 'i' || c == 's' || c == 't' || c == '!') k = K_LC;
+        s_lut[c] = k;
+    }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * LEX_WARPS + wib;
+    if (i >= p.n) return;
+    const uint64_t b0 = p.offsets[i], b1 = p.offsets[i + 1];
+    if (b1 <= b0 || b1 - b0 >= 0x40000000ull) {
+        if (lane == 0) p.flags[i] = SSYM_WIT_SLOW;
+        return;
+    }
+    const uint8_t *t = p.text + b0;
+    Blocks B;
+    B.len = (uint32_t)(b1 - b0);
+    B.head = (uint32_t)(reinterpret_cast<uintptr_t>(t) & 15u);
+    B.base = reinterpret_cast<const uint4 *>(t - B.head);
+    B.nblk = (B.head + B.len + 15u) / 16u;
+    const uint32_t FULL = 0xffffffffu;
+    bool bad = false;
+
+    // ---- phase 0: quote positions (in order), no backslashes ----
+    uint32_t nq = 0;
+    for (uint32_t blk0 = 0; blk0 < B.nblk; blk0 += 32) {
+        const uint32_t blk = blk0 + lane;
+        const uint4 v = B.load(blk);
+        uint32_t zq[4], zb[4], any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t w = word_of(v, k);
+            zq[k] = zero_bytes(w ^ 0x22222222u); // '"'
+            zb[k] = zero_bytes(w ^ 0x5c5c5c5cu); // backslash
+            any |= zq[k] | zb[k];
+        }
+        if (__any_sync(FULL, any != 0)) {
+            const uint32_t vm = B.valid(blk, 0, B.len);
+            uint32_t qm = 0, bm = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { qm |= gather4(zq[k] >> 7) << (4 * k); bm |= gather4(zb[k] >> 7) << (4 * k); }
+            qm &= vm;
+            if (bm & vm) bad = true;
+            const uint32_t cnt = __popc(qm);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t x = __shfl_up_sync(FULL, inc, off);
+                if (lane >= (uint32_t)off) inc += x;
+            }
+            uint32_t at = nq + inc - cnt;
+            const int rel0 = (int)(blk * 16u) - (int)B.head;
+            for (uint32_t m = qm; m; m &= m - 1, at++)
+                if (at < WIT_MAXQ) s_q[wib][at] = (uint32_t)(rel0 + __ffs(m) - 1);
+            nq += __shfl_sync(FULL, inc, 31);
+        }
+    }
+    bad = __any_sync(FULL, bad) || nq > WIT_MAXQ || (nq & 1u);
+    __syncwarp();
+    if (!bad && lane == 0) {
+        uint32_t vs[WIT_NAMES], ve[WIT_NAMES];
+        if (!json_walk(t, B.len, s_q[wib], nq, vs, ve)) {
+            bad = true;
+        } else { // spans in file order
+            uint32_t order[WIT_NAMES];
+            for (int a = 0; a < WIT_NAMES; a++) order[a] = a;
+            for (int a = 1; a < WIT_NAMES; a++)
+                for (int b = a; b > 0 && vs[order[b]] < vs[order[b - 1]]; b--) { const uint32_t x = order[b]; order[b] = order[b - 1]; order[b - 1] = x; }
+            for (int a = 0; a < WIT_NAMES; a++) { s_span[wib][3 * a] = vs[order[a]]; s_span[wib][3 * a + 1] = ve[order[a]]; s_span[wib][3 * a + 2] = order[a]; }
+        }
+    }
+    bad = __any_sync(FULL, bad);
+    __syncwarp();
+    if (bad) {
+        if (lane == 0) p.flags[i] = SSYM_WIT_SLOW;
+        return;
+    }
+
+    // ---- phase A: the six values, in file order ----
+    uint32_t *numpos = p.numpos + (size_t)i * p.total_slots;
+    uint32_t n_l = 0, n_lc = 0; // `l` tokens seen (each checked to start "list!") / i s t ! characters seen: must be 4 per `l`
+    for (int sidx = 0; sidx < WIT_NAMES; sidx++) {
+        const uint32_t ss = s_span[wib][3 * sidx], se = s_span[wib][3 * sidx + 1], name = s_span[wib][3 * sidx + 2];
+        const uint8_t *skel = p.tab.skel + p.tab.skel_off[name];
+        const uint32_t skel_len = p.tab.skel_len[name], slot_cnt = p.tab.slot_cnt[name], slot_off = p.tab.slot_off[name];
+        uint32_t tokbase = 0, numbase = 0, carry = 0;
+        const uint32_t fb = (B.head + ss) / 16u, lb = (B.head + se - 1u) / 16u;
+        for (uint32_t blk0 = fb; blk0 <= lb; blk0 += 32) {
+            const uint32_t blk = blk0 + lane;
+            const uint4 v = blk <= lb ? B.load(blk) : make_uint4(0, 0, 0, 0);
+            const uint32_t vm = blk <= lb ? B.valid(blk, ss, se) : 0u;
+            uint32_t numm = 0, strm = 0, lcm = 0, badm = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = word_of(v, k);
+                const uint32_t kw = (uint32_t)s_lut[w & 0xff] | (uint32_t)s_lut[(w >> 8) & 0xff] << 8 | (uint32_t)s_lut[(w >> 16) & 0xff] << 16 |
+                                    (uint32_t)s_lut[w >> 24] << 24;
+                numm |= gather4(kw) << (4 * k);
+                strm |= gather4(kw >> 1) << (4 * k);
+                lcm |= gather4(kw >> 2) << (4 * k);
+                badm |= gather4(kw >> 3) << (4 * k);
+            }
+            numm &= vm; strm &= vm; lcm &= vm;
+            if (badm & vm) bad = true;
+            n_lc += __popc(lcm);
+            uint32_t up = __shfl_up_sync(FULL, numm >> 15, 1);
+            if (lane == 0) up = carry;
+            const uint32_t nstart = numm & ~((numm << 1) | up) & 0xffffu;
+            const uint32_t tstart = nstart | strm;
+            const uint32_t cnt = __popc(tstart) | (__popc(nstart) << 16);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t x = __shfl_up_sync(FULL, inc, off);
+                if (lane >= (uint32_t)off) inc += x;
+            }
+            const uint32_t total = __shfl_sync(FULL, inc, 31);
+            carry = __shfl_sync(FULL, numm >> 15, 31);
+            uint32_t ord = tokbase + ((inc - cnt) & 0xffffu), nidx = numbase + ((inc - cnt) >> 16);
+            const int rel0 = (int)(blk * 16u) - (int)B.head;
+            for (uint32_t m = tstart; m; m &= m - 1, ord++) {
+                const int j = __ffs(m) - 1;
+                const uint8_t ch = (uint8_t)(word_of(v, j >> 2) >> (8 * (j & 3)));
+                const bool isnum = (nstart >> j) & 1u;
+                const uint8_t act = isnum ? (uint8_t)'N' : ch == 'l' ? (uint8_t)'L' : ch;
+                if (ord >= skel_len || __ldg(skel + ord) != act) bad = true;
+                if (isnum) {
+                    if (nidx < slot_cnt) numpos[slot_off + nidx] = (uint32_t)(rel0 + j);
+                    nidx++;
+                } else if (ch == 'l') {
+                    const uint32_t at = (uint32_t)(rel0 + j);
+                    n_l++;
+                    if (!(at + 4 < se && t[at + 1] == 'i' && t[at + 2] == 's' && t[at + 3] == 't' && t[at + 4] == '!')) bad = true;
+                }
+            }
+            tokbase += total & 0xffffu;
+            numbase += total >> 16;
+        }
+        if (tokbase != skel_len || numbase != slot_cnt) bad = true;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        n_l += __shfl_xor_sync(FULL, n_l, off);
+        n_lc += __shfl_xor_sync(FULL, n_lc, off);
+    }
+    if (n_lc != 4u * n_l) bad = true;
+    bad = __any_sync(FULL, bad);
+    if (lane == 0) p.flags[i] = bad ? SSYM_WIT_SLOW : SSYM_WIT_OK;
+}
+
+// Kernel 2: one thread per integer literal.  A 64-digit hex literal for a u256 slot (a digest: 87 % of the text) is converted 4 characters
+// per operation; everything else goes through the general loop.
+__device__ __forceinline__ uint32_t hex8(uint32_t w0, uint32_t w1) { // 8 validated lower-case hex characters -> their 32-bit value
+    const uint32_t n0 = (w0 & 0x0f0f0f0fu) + 9u * ((w0 >> 6) & 0x01010101u), n1 = (w1 & 0x0f0f0f0fu) + 9u * ((w1 >> 6) & 0x01010101u);
+    const uint32_t x0 = ((n0 << 4) | (n0 >> 8)) & 0x00ff00ffu, x1 = ((n1 << 4) | (n1 >> 8)) & 0x00ff00ffu;
+    return __byte_perm(x0, x1, 0x0246);
+}
+__device__ __forceinline__ bool all_hex(uint32_t w) { // every byte in [0-9a-f]
+    const uint32_t H = 0x80808080u;
+    if (w & H) return false;
+    const uint32_t dig = ((w + 0x50505050u) & ~(w + 0x46464646u)) & H; // >= '0' and not >= ':'
+    const uint32_t let = ((w + 0x1f1f1f1fu) & ~(w + 0x19191919u)) & H; // >= 'a' and not >= 'g'
+    return (dig | let) == H;
+}
+
+__device__ bool parse_number(const uint8_t *s, uint32_t slot, uint32_t *rec) {
     const uint32_t off = slot & 0x0fffffffu, kind = slot >> 28;
     const uint32_t kw = kind == WIT_KIND_U32 ? 1u : kind == WIT_KIND_U64 ? 2u : 8u;
-    if (t[pos] == '0' && pos + 1 < end && t[pos + 1] == 'x') {
-        const uint32_t p = pos + 2;
+    if (s[0] == '0' && s[1] == 'x') {
+        const uint8_t *d = s + 2;
+        if (kw == 8) { // 64 digits and a terminator?
+            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3u);
+            const uint32_t *a = reinterpret_cast<const uint32_t *>(d - sh);
+            uint32_t A[17], W[16];
+#pragma unroll
+            for (int k = 0; k < 17; k++) A[k] = __ldg(a + k);
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                W[k] = __funnelshift_r(A[k], A[k + 1], 8 * sh);
+                ok = ok && all_hex(W[k]);
+            }
+            if (ok && !is_numchar((uint8_t)(A[16] >> (8 * sh)))) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) rec[off + k] = hex8(W[2 * k], W[2 * k + 1]);
+                return true;
+            }
+        }
         uint32_t n = 0;
-        while (p + n < end && cls[t[p + n]] == C_NUM) n++;
+        while (is_numchar(d[n])) n++;
         if (n == 0 || n > 64) return false;
         uint32_t acc = 0, rem = n;
         for (uint32_t j = 0; j < n; j++) {
-            const uint8_t c = t[p + j];
-            uint32_t d;
-            if (c >= '0' && c <= '9') d = c - '0';
-            else if (c >= 'a' && c <= 'f') d = c - 'a' + 10;
+            const uint8_t c = d[j];
+            uint32_t v;
+            if (c >= '0' && c <= '9') v = c - '0';
+            else if (c >= 'a' && c <= 'f') v = c - 'a' + 10;
             else return false; // a second 'x'
-            acc = (acc << 4) | d;
+            acc = (acc << 4) | v;
             rem--;
             if ((rem & 7u) == 0) {
                 const uint32_t widx = 7u - rem / 8u; // index in the 8-word big-endian value
@@ -129,12 +321,12 @@ __device__ bool parse_number(const uint8_t *t, uint32_t pos, uint32_t end, const
         return true;
     }
     uint64_t v = 0;
-    for (uint32_t p = pos; p < end && cls[t[p]] == C_NUM; p++) {
-        const uint8_t c = t[p];
+    for (const uint8_t *q = s; is_numchar(*q); q++) {
+        const uint8_t c = *q;
         if (c < '0' || c > '9') return false;
-        const uint32_t d = c - '0';
-        if (v > (0xffffffffffffffffull - d) / 10u) return false; // above 64 bits: host parser
-        v = v * 10u + d;
+        const uint32_t dgt = c - '0';
+        if (v > (0xffffffffffffffffull - dgt) / 10u) return false; // above 64 bits: host parser
+        v = v * 10u + dgt;
     }
     if (kw == 1) {
         if (v >> 32) return false;
@@ -146,169 +338,12 @@ __device__ bool parse_number(const uint8_t *t, uint32_t pos, uint32_t end, const
     return true;
 }
 
-struct Spans { // sorted by position
-    uint32_t start[WIT_NAMES], end[WIT_NAMES], name[WIT_NAMES];
-    uint32_t owner[WIT_NAMES], ltok[WIT_NAMES], lnum[WIT_NAMES]; // thread whose chunk holds the span start, its local counts there
-    uint32_t tokbase[WIT_NAMES], numbase[WIT_NAMES];              // global token / literal index of the span's first token
-};
-
-// One pass of a thread over its chunk [lo, hi) of the file: tokens of the value spans.  COUNT pass: token / literal counts (returned) and
-// the local counts at every span start inside the chunk.  EMIT pass: tokens are checked against the skeleton, literals are parsed.
-template <bool EMIT>
-__device__ __forceinline__ uint2 scan_values(const uint8_t *t, uint32_t lo, uint32_t hi, const uint8_t *cls, Spans &sp, const WitTables &tab, uint2 base,
-                                             uint32_t *rec, int *bad) {
-    uint32_t tok = 0, num = 0;
-    for (int s = 0; s < WIT_NAMES; s++) {
-        const uint32_t ss = sp.start[s], se = sp.end[s];
-        const uint32_t a = max(lo, ss), b = min(hi, se);
-        if (a >= b) continue;
-        uint8_t prevc = 0;
-        bool prevnum = false;
-        if (a == ss) {
-            if (!EMIT) { sp.owner[s] = threadIdx.x; sp.ltok[s] = tok; sp.lnum[s] = num; }
-        } else {
-            prevc = __ldg(t + a - 1);
-            prevnum = cls[prevc] == C_NUM;
-        }
-        const uint32_t name = sp.name[s];
-        const uint8_t *skel = tab.skel + tab.skel_off[name];
-        const uint32_t *slots = tab.slots + tab.slot_off[name];
-        const uint32_t skel_len = tab.skel_len[name], slot_cnt = tab.slot_cnt[name];
-        const uint32_t tb = EMIT ? sp.tokbase[s] : 0, nb = EMIT ? sp.numbase[s] : 0;
-        for (uint32_t pos = a; pos < b; pos++) {
-            const uint8_t c = __ldg(t + pos), k = cls[c];
-            if (k == C_NUM) {
-                if (!prevnum) {
-                    if (EMIT) {
-                        const uint32_t rel = base.x + tok - tb, nrel = base.y + num - nb;
-                        if (rel >= skel_len || skel[rel] != 'N' || nrel >= slot_cnt || !parse_number(t, pos, se, cls, slots[nrel], rec)) *bad = 1;
-                    }
-                    tok++;
-                    num++;
-                }
-                prevnum = true;
-            } else {
-                prevnum = false;
-                if (k == C_STRUCT || k == C_L) {
-                    if (EMIT) {
-                        const uint32_t rel = base.x + tok - tb;
-                        if (rel >= skel_len || skel[rel] != (k == C_L ? (uint8_t)'L' : c)) *bad = 1;
-                        if (k == C_L && !(pos + 4 < se && t[pos + 1] == 'i' && t[pos + 2] == 's' && t[pos + 3] == 't' && t[pos + 4] == '!')) *bad = 1;
-                    }
-                    tok++;
-                } else if (k == C_LCONT) { // i s t ! : only as the tail of `list!`
-                    const uint8_t need = c == 'i' ? 'l' : c == 's' ? 'i' : c == 't' ? 's' : 't';
-                    if (prevc != need) *bad = 1;
-                } else if (k != C_WS) {
-                    *bad = 1;
-                }
-            }
-            prevc = c;
-        }
-    }
-    return make_uint2(tok, num);
-}
-
-__global__ void __launch_bounds__(WIT_THREADS) wit_pack_kernel(WitParams p) {
-    __shared__ uint8_t s_cls[256];
-    __shared__ uint32_t s_q[WIT_MAXQ], s_qsorted[WIT_MAXQ];
-    __shared__ uint2 s_warp[WIT_THREADS / 32];
-    __shared__ Spans sp;
-    __shared__ uint32_t s_nq;
-    __shared__ int s_bad;
-    const uint32_t i = blockIdx.x, tid = threadIdx.x;
-    const uint64_t b0 = p.offsets[i], b1 = p.offsets[i + 1];
-    const uint8_t *t = p.text + b0;
-    uint32_t *rec = p.packed + (size_t)i * p.stride_words;
-    if (b1 < b0 || b1 - b0 >= 0x7fffffffull) {
-        if (tid == 0) p.flags[i] = SSYM_WIT_SLOW;
-        return;
-    }
-    const uint32_t len = (uint32_t)(b1 - b0);
-    {
-        const uint8_t c = (uint8_t)tid;
-        uint8_t k = C_BAD;
-        if (is_ws(c)) k = C_WS;
-        else if ((c >= '0' && c <= '9') || (c >= 'a' && c <= 'f') || c == 'x') k = C_NUM;
-        else if (c == '(' || c == ')' || c == '[' || c == ']' || c == ',') k = C_STRUCT;
-        else if (c == 'l') k = C_L;
-        else if (c == 'i' || c == 's' || c == 't' || c == '!') k = C_LCONT;
-        s_cls[tid] = k;
-    }
-    if (tid == 0) { s_nq = 0; s_bad = 0; }
-    __syncthreads();
-    const uint32_t chunk = (len + WIT_THREADS - 1) / WIT_THREADS;
-    const uint32_t lo = min(len, tid * chunk), hi = min(len, lo + chunk);
-
-    // ---- phase 0: the JSON strings.  Quote positions, no escapes. ----
-    for (uint32_t pos = lo; pos < hi; pos++) {
-        const uint8_t c = __ldg(t + pos);
-        if (c == '"') {
-            const uint32_t k = atomicAdd(&s_nq, 1u);
-            if (k < WIT_MAXQ) s_q[k] = pos;
-        } else if (c == '\\') {
-            s_bad = 1;
-        }
-    }
-    __syncthreads();
-    const uint32_t nq = s_nq;
-    if (nq > WIT_MAXQ || (nq & 1u) || s_bad) {
-        if (tid == 0) p.flags[i] = SSYM_WIT_SLOW;
-        return;
-    }
-    if (tid < nq) { // rank sort (positions are distinct)
-        const uint32_t v = s_q[tid];
-        uint32_t r = 0;
-        for (uint32_t k = 0; k < nq; k++) r += s_q[k] < v;
-        s_qsorted[r] = v;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t vs[WIT_NAMES], ve[WIT_NAMES];
-        if (!json_walk(t, len, s_qsorted, nq, vs, ve)) {
-            s_bad = 1;
-        } else { // spans in file order
-            uint32_t order[WIT_NAMES];
-            for (int a = 0; a < WIT_NAMES; a++) order[a] = a;
-            for (int a = 1; a < WIT_NAMES; a++)
-                for (int b = a; b > 0 && vs[order[b]] < vs[order[b - 1]]; b--) { const uint32_t x = order[b]; order[b] = order[b - 1]; order[b - 1] = x; }
-            for (int a = 0; a < WIT_NAMES; a++) { sp.start[a] = vs[order[a]]; sp.end[a] = ve[order[a]]; sp.name[a] = order[a]; }
-        }
-    }
-    __syncthreads();
-    if (s_bad) {
-        if (tid == 0) p.flags[i] = SSYM_WIT_SLOW;
-        return;
-    }
-
-    // ---- phase 1: count the tokens of every value, check the totals against the skeletons ----
-    int bad = 0;
-    const uint2 mine = scan_values<false>(t, lo, hi, s_cls, sp, p.tab, make_uint2(0, 0), rec, &bad);
-    if (bad) s_bad = 1;
-    uint2 total;
-    const uint2 base = block_excl_scan(mine, s_warp, total); // (has the barriers that publish sp.owner / ltok / lnum and s_bad)
-    // owners publish the global index of their span's first token
-    for (int s = 0; s < WIT_NAMES; s++)
-        if (sp.owner[s] == tid) { sp.tokbase[s] = base.x + sp.ltok[s]; sp.numbase[s] = base.y + sp.lnum[s]; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int s = 0; s < WIT_NAMES; s++) {
-            const uint32_t ntok = (s + 1 < WIT_NAMES ? sp.tokbase[s + 1] : total.x) - sp.tokbase[s];
-            const uint32_t nnum = (s + 1 < WIT_NAMES ? sp.numbase[s + 1] : total.y) - sp.numbase[s];
-            if (ntok != p.tab.skel_len[sp.name[s]] || nnum != p.tab.slot_cnt[sp.name[s]]) s_bad = 1;
-        }
-    }
-    __syncthreads();
-    if (s_bad) {
-        if (tid == 0) p.flags[i] = SSYM_WIT_SLOW;
-        return;
-    }
-
-    // ---- phase 2: check every token against the skeleton, parse and scatter the literals ----
-    scan_values<true>(t, lo, hi, s_cls, sp, p.tab, base, rec, &bad);
-    if (bad) s_bad = 1;
-    __syncthreads();
-    if (tid == 0) p.flags[i] = s_bad ? SSYM_WIT_SLOW : SSYM_WIT_OK;
+__global__ void __launch_bounds__(256) wit_numbers_kernel(WitParams p) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = (uint32_t)(g / p.total_slots), k = (uint32_t)(g % p.total_slots);
+    if (i >= p.n || p.flags[i] != SSYM_WIT_OK) return;
+    const uint8_t *t = p.text + p.offsets[i];
+    if (!parse_number(t + p.numpos[(size_t)i * p.total_slots + k], __ldg(p.tab.slots + k), p.packed + (size_t)i * p.stride_words)) p.flags[i] = SSYM_WIT_SLOW;
 }
 
 __global__ void wit_apply_flags_kernel(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n) {
@@ -321,7 +356,10 @@ __global__ void wit_apply_flags_kernel(const uint32_t *flags, uint32_t *status, 
 } // namespace
 
 void launch_wit_pack(const WitParams &p, cudaStream_t s) {
-    if (p.n) wit_pack_kernel<<<p.n, WIT_THREADS, 0, s>>>(p);
+    if (!p.n) return;
+    wit_lex_kernel<<<(p.n + LEX_WARPS - 1) / LEX_WARPS, 32 * LEX_WARPS, 0, s>>>(p);
+    const uint64_t threads = (uint64_t)p.n * p.total_slots;
+    wit_numbers_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(p);
 }
 void launch_wit_apply_flags(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n, cudaStream_t s) {
     if (n) wit_apply_flags_kernel<<<(n + 255) / 256, 256, 0, s>>>(flags, status, accept_bits, n);

@@ -2,7 +2,8 @@
 //
 // `.wit` ingestion on the GPU: the JSON text `simfony run --witness` reads
 // (simfony-cli/src/main.rs:77-81, emitted by stwo-verifier/scripts/generate_wit.py:106-245) is tokenised and packed
-// into the wire format of include/ssym.h by one CTA per witness.
+// into the wire format of include/ssym.h by two kernels: a lexer (one warp per witness, 128-bit coalesced loads, table-driven byte
+// classes, warp scans for the token numbering) and a literal converter (one thread per integer literal).
 //
 // The value grammar is fixed by the program's witness types (stwo-verifier/src/main.simf:9-25), so for a given
 // configuration the token sequence of every witness value is known in advance up to whitespace: the host builds that
@@ -37,6 +38,8 @@ struct WitParams {
     uint32_t stride_words;
     uint32_t *packed;        // n * stride_words, zero-filled by the caller
     uint32_t *flags;         // n: SSYM_WIT_OK or SSYM_WIT_SLOW (internal: host re-parse)
+    uint32_t *numpos;        // scratch, n * total_slots: file position of every integer literal (kernel 1 -> kernel 2)
+    uint32_t total_slots;    // integer literals per witness (sum of slot_cnt)
     WitTables tab;
 };
 
