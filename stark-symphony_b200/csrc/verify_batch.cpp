@@ -9,7 +9,10 @@
 // INTEGRATION.md shows the Rust binding.)
 //
 //   verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--mode {ref-literal,prover-consistent}]
-//                (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet]
+//                (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet] [--host-pack]
+//
+// Stwo witnesses are tokenised and packed ON THE GPU (ssym_stwo_verify_wit_batch: the `.wit` text is what crosses PCIe); --host-pack (and
+// --trace, which needs the packed records on the host) uses the host parser + ssym_stwo_verify_batch instead.
 #include <dirent.h>
 
 #include <algorithm>
@@ -37,7 +40,7 @@ static bool read_file(const std::string &path, std::string &out) {
 static void usage() {
     fprintf(stderr,
             "usage: verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--mode {ref-literal,prover-consistent}]\n"
-            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet]\n");
+            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet] [--host-pack]\n");
 }
 
 static std::string hex_digest(const uint32_t *w) {
@@ -56,7 +59,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> witnesses;
     size_t replicate = 1;
     int gpus = 1;
-    bool quiet = false;
+    bool quiet = false, host_pack = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](const char *what) -> std::string {
@@ -74,6 +77,7 @@ int main(int argc, char **argv) {
         else if (a == "--gpus") gpus = atoi(next("--gpus").c_str());
         else if (a == "--trace") trace_path = next("--trace");
         else if (a == "--quiet") quiet = true;
+        else if (a == "--host-pack") host_pack = true;
         else if (a == "--help" || a == "-h") { usage(); return 0; }
         else { fprintf(stderr, "Error: unknown argument %s\n", a.c_str()); usage(); return 2; }
     }
@@ -106,7 +110,27 @@ int main(int argc, char **argv) {
     std::vector<uint64_t> offsets;
     std::vector<ssym_stwo_trace_t> traces;
     std::vector<ssym_s101_trace_t> traces101;
-    if (program == "stwo") {
+    const bool gpu_ingest = program == "stwo" && !want_trace && !host_pack;
+    std::string wit_text;               // stwo, GPU ingestion: the concatenated witness texts
+    std::vector<uint64_t> wit_offsets;
+    std::vector<uint32_t> wit_flags;
+    if (gpu_ingest) {
+        if (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || ssym_stwo_layout(&cfg, &lo)) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
+        wit_offsets.push_back(0);
+        for (size_t f = 0; f < n_files; f++) {
+            std::string text;
+            if (!read_file(witnesses[f], text)) { fprintf(stderr, "Error: Failed to read witness file: %s\n", witnesses[f].c_str()); return 1; }
+            wit_text += text;
+            wit_offsets.push_back(wit_text.size());
+        }
+        const size_t one = wit_text.size();
+        wit_text.reserve(one * replicate);
+        for (size_t r = 1; r < replicate; r++) {
+            wit_text.append(wit_text, 0, one);
+            for (size_t f = 0; f < n_files; f++) wit_offsets.push_back(r * one + wit_offsets[f + 1]);
+        }
+        wit_flags.assign(n, 0);
+    } else if (program == "stwo") {
         if (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || ssym_stwo_layout(&cfg, &lo)) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
         packed.assign(n * (size_t)lo.stride_words, 0);
         for (size_t f = 0; f < n_files; f++) {
@@ -157,7 +181,13 @@ int main(int argc, char **argv) {
             ssym_ctx_t *ctx = nullptr;
             int rc = ssym_create(g, &ctx);
             if (rc == SSYM_OK) {
-                if (program == "stwo")
+                if (gpu_ingest) {
+                    std::vector<uint64_t> offs(wit_offsets.begin() + b, wit_offsets.begin() + e + 1);
+                    const uint64_t base = offs[0];
+                    for (auto &o : offs) o -= base;
+                    rc = ssym_stwo_verify_wit_batch(ctx, &cfg, wit_text.data() + base, offs.data(), e - b, accept.data() + b / 32, status.data() + b,
+                                                    wit_flags.data() + b, SSYM_MEM_HOST);
+                } else if (program == "stwo")
                     rc = ssym_stwo_verify_batch(ctx, &cfg, packed.data() + b * (size_t)lo.stride_words, e - b, accept.data() + b / 32, status.data() + b,
                                                 want_trace ? traces.data() + b : nullptr, SSYM_MEM_HOST);
                 else {
@@ -181,14 +211,15 @@ int main(int argc, char **argv) {
     size_t n_accept = 0;
     for (size_t i = 0; i < n; i++) {
         const size_t f = i % n_files;
+        if (gpu_ingest && wit_flags[i] != SSYM_WIT_OK) parse_reject[f] = 1;
         bool ok = ((accept[i / 32] >> (i % 32)) & 1) && !parse_reject[f];
         if (parse_reject[f]) status[i] |= SSYM_ST_SHAPE;
         n_accept += ok;
         if (!quiet) printf("%s %s%s\n", ok ? "accept" : "reject", witnesses[f].c_str(), ok ? "" : (" status=0x" + [&] { char b[16]; snprintf(b, sizeof b, "%08x", status[i]); return std::string(b); }()).c_str());
     }
     const double pack_s = std::chrono::duration<double>(t1 - t0).count(), gpu_s = std::chrono::duration<double>(t2 - t1).count();
-    fprintf(stderr, "verify-batch: %zu proofs, %zu accepted, %zu rejected; parse+pack %.3f s, verify (%d GPU%s, host buffers) %.3f s\n", n, n_accept,
-            n - n_accept, pack_s, gpus, gpus > 1 ? "s" : "", gpu_s);
+    fprintf(stderr, "verify-batch: %zu proofs, %zu accepted, %zu rejected; %s %.3f s, %s (%d GPU%s, host buffers) %.3f s\n", n, n_accept,
+            n - n_accept, gpu_ingest ? "read" : "parse+pack", pack_s, gpu_ingest ? "tokenise+pack+verify" : "verify", gpus, gpus > 1 ? "s" : "", gpu_s);
 
     if (want_trace) {
         std::ofstream o(trace_path);

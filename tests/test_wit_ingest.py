@@ -237,3 +237,31 @@ def test_wit_batch_of_distinct_proofs_round_trip(S):
     assert (ok == (expect_flags == 0)).all()
     assert (status[expect_flags == 0] == 0).all() and (status[expect_flags != 0] >> 31 == 1).all()
     ver.close()
+
+
+@pytest.mark.gpu
+def test_cli_gpu_ingestion_matches_host_pack(S, tmp_path):
+    """bin/verify-batch (the `simfony run --witness` counterpart): GPU ingestion (default) and --host-pack print the same verdicts."""
+    import subprocess
+
+    from conftest import ROOT
+
+    cli = os.path.join(ROOT, "stark-symphony_b200", "bin", "verify-batch")
+    good = os.path.join(GOLDEN, "stwo_proof_prod.wit")
+    text = open(good).read()
+    bad1, bad2 = tmp_path / "long_path.wit", tmp_path / "garbage.wit"
+    bad1.write_text(_bad_variants(text)[0][1])
+    bad2.write_text("{}")
+    outs = []
+    for extra in ([], ["--host-pack"]):
+        r = subprocess.run([cli, "--program", "stwo", "--mode", "prover-consistent", "--witness", good, "--replicate", "70"] + extra, capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.count("accept") == 70 and "reject" not in r.stdout, r.stderr
+        r = subprocess.run([cli, "--program", "stwo", "--mode", "prover-consistent", "--witness", good, str(bad1), str(bad2), good] + extra, capture_output=True, text=True)
+        assert r.returncode == 1 and "Error: Failed to run program" in r.stderr
+        lines = r.stdout.strip().splitlines()
+        assert [l.split()[0] for l in lines] == ["accept", "reject", "reject", "accept"]
+        assert all("status=0x8" in l for l in lines[1:3])  # SSYM_ST_SHAPE
+        outs.append(r.stdout)
+        r = subprocess.run([cli, "--program", "stwo", "--mode", "ref-literal", "--witness", good] + extra, capture_output=True, text=True)
+        assert r.returncode == 1 and r.stdout.startswith("reject")  # the reference at HEAD rejects its own fixture (DESIGN.md section 1)
+    assert outs[0] == outs[1]
