@@ -91,3 +91,55 @@ def test_gpu_prover_rejects_unsupported_config(S, ver):
     cfg.n_fri_layers = 5
     with pytest.raises(S.SsymError):
         ver.stwo_prove_batch(np.array([1], dtype=np.uint64), cfg)
+
+
+def test_config3_full_size_properties(S, ver):
+    """BASELINE config 3 at its full size (2^16 distinct proofs, 3.6 GB, proven where they are verified): size-independent properties.
+    Every honest proof is accepted; every corrupted one (nine classes, 1/12 of the batch each) is rejected and
+    the honest ones stay accepted; verification is idempotent; ragged shards give the bitmap of the whole batch."""
+    import torch
+
+    n = 1 << 16
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    lo = S.stwo_layout(cfg)
+    seeds = torch.arange(7_000_000, 7_000_000 + n, dtype=torch.int64, device="cuda")
+    proofs = ver.stwo_prove_batch(seeds, cfg)
+    accept0, status0, _ = ver.stwo_verify_batch(proofs.view(-1), cfg, n, want_status=True)
+    ver.synchronize()
+    assert int((status0 != 0).sum().item()) == 0 and bool((accept0 == -1).all().item())  # all 2^16 bits set
+    classes = S.witness.stwo_negative_classes(cfg)
+    names = list(classes)
+    rows = torch.arange(n, device="cuda")
+    cls_of_row = rows % 12  # each of the 9 corruption classes takes 1/12 of the batch, 3/12 stay honest
+    for j, name in enumerate(names):
+        word, delta = classes[name]
+        sel = rows[cls_of_row == j]
+        proofs[sel, word] += delta
+    accept1, status1, _ = ver.stwo_verify_batch(proofs.view(-1), cfg, n, want_status=True)
+    ver.synchronize()
+    st = status1.cpu().numpy().view(np.uint32)
+    cls = cls_of_row.cpu().numpy()
+    assert ((st != 0) == (cls < len(names))).all()
+    for j, name in enumerate(names):  # one status pattern per class (the corruption is at the same word of every proof)
+        pat = np.unique(st[cls == j] & ~np.uint32(0))
+        assert len(pat) >= 1 and (pat != 0).all(), name
+    bits = np.unpackbits(accept1.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert (bits == (st == 0)).all()
+    # idempotence
+    accept2, status2, _ = ver.stwo_verify_batch(proofs.view(-1), cfg, n, want_status=True)
+    ver.synchronize()
+    assert torch.equal(accept1, accept2) and torch.equal(status1, status2)
+    # ragged shards (sizes not multiples of 32 except where the bitmap requires it) == the whole batch
+    cuts = [0, 32 * 701, 32 * 701 + 32 * 13, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        acc_s, st_s, _ = ver.stwo_verify_batch(proofs[a:b].reshape(-1), cfg, b - a, want_status=True)
+        ver.synchronize()
+        assert torch.equal(st_s, status1[a:b]) and torch.equal(acc_s, accept1[a // 32:(b + 31) // 32])
+    # a sample of every class on the CPU oracle
+    from oracle import oracle as O
+
+    orc = O.Oracle()
+    oc = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    sample = proofs[:32].cpu().numpy().view(np.uint32)
+    _, o_status, _ = orc.stwo_verify_batch(oc, sample.ravel(), 32)
+    assert (o_status == st[:32]).all()
