@@ -97,6 +97,7 @@ struct ssym_ctx {
         cudaStream_t s = nullptr, front = nullptr; // front: high priority, for the latency-bound kernels of a pipelined call
         cudaEvent_t in = nullptr, done = nullptr, front_done = nullptr;
         DevBuf stwo_ctx, stwo_evals, status;
+        DevBuf dd_plan, dd_to, dd_own, dd_ckpt, dd_bins, dd_list; // shared-node Merkle schedule (StwoDedup)
         bool pending = false;
     };
     static const int MAX_DEPTH = 8;
@@ -133,7 +134,7 @@ struct ssym_ctx {
     bool fold_table_ready[2][32] = {{false}};
 };
 
-static const size_t STWO_DEVICE_CHUNK = 32768; // proofs per launch group (bounds scratch: ~3 KB / proof)
+static const size_t STWO_DEVICE_CHUNK = 8192; // proofs per launch group (bounds scratch: ~23 KB / proof)
 
 extern "C" {
 
@@ -179,6 +180,7 @@ void ssym_destroy(ssym_ctx_t *c) {
     cudaDeviceSynchronize();
     for (auto &l : c->lanes) {
         l.stwo_ctx.release(); l.stwo_evals.release(); l.status.release();
+        l.dd_plan.release(); l.dd_to.release(); l.dd_own.release(); l.dd_ckpt.release(); l.dd_bins.release(); l.dd_list.release();
         cudaStreamDestroy(l.s);
         cudaStreamDestroy(l.front);
         cudaEventDestroy(l.front_done);
@@ -351,6 +353,22 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
         }
         p.trace = d_trace ? d_trace + done : nullptr;
         p.n = (uint32_t)m;
+        memset(&p.dd, 0, sizeof p.dd);
+        if (const size_t list_entries = stwo_dedup_layout(cfg, m, p.dd)) {
+            const size_t chains = (size_t)p.dd.chains * m;
+            CUDA_TRY(lane.dd_plan.ensure(chains * sizeof(uint32_t)));
+            CUDA_TRY(lane.dd_to.ensure(chains * sizeof(uint64_t)));
+            CUDA_TRY(lane.dd_own.ensure(chains * 8 * sizeof(uint32_t)));
+            CUDA_TRY(lane.dd_ckpt.ensure(chains * 8 * sizeof(uint32_t)));
+            CUDA_TRY(lane.dd_bins.ensure(2 * STWO_DEDUP_MAX_BINS * sizeof(uint32_t)));
+            CUDA_TRY(lane.dd_list.ensure(list_entries * sizeof(uint32_t)));
+            p.dd.plan = lane.dd_plan.as<uint32_t>();
+            p.dd.ckpt_to = lane.dd_to.as<uint64_t>();
+            p.dd.own = lane.dd_own.as<uint32_t>();
+            p.dd.ckpt = lane.dd_ckpt.as<uint32_t>();
+            p.dd.bin_count = lane.dd_bins.as<uint32_t>();
+            p.dd.bin_list = lane.dd_list.as<uint32_t>();
+        }
         if (p.trace) CUDA_TRY(cudaMemsetAsync(p.trace, 0, m * sizeof(ssym_stwo_trace_t), s));
         const bool fr = use_front && front_kernels > 0 && !p.trace && !c->profiling && n <= STWO_DEVICE_CHUNK; // one chunk: the lane's scratch is not reused inside the call
         launch_stwo_verify(p, d_accept + done / 32, s, &c->launches, c->profiling ? &c->profiler : nullptr, fr ? lane.front : nullptr,

@@ -7,6 +7,8 @@
 //                                                      scalars: OODS point, composition-polynomial check, powers of the DEEP coefficient
 //   K2 stwo_query_kernel       one warp per proof       DEEP line coefficients (lane = column), fri_answer + the 1+L folds (lane = query)
 //   K3 stwo_merkle_kernel      one thread per hash chain  all 2*Q + (L+1)*Q Merkle decommitments
+//      (default: stwo_plan_kernel, stwo_merkle_shared_kernel, stwo_check_kernel, stwo_merkle_shared_kernel (round 2), stwo_resolve_kernel:
+//       the same decommitments with the nodes that several paths of a tree run through hashed once — see StwoDedup below)
 //   K4 stwo_finalize_kernel    status words -> accept bitmap
 //
 // No early exit anywhere: every check is evaluated and OR-ed into the proof's status word, so a
@@ -48,6 +50,28 @@ struct StwoTables {
     uint32_t fold_off[SSYM_MAX_FRI_LAYERS];
 };
 
+// Node sharing between the Merkle paths of one tree (SURVEY.md 8a "merkle.simf": the reference hashes every query's path to the root
+// on its own; two paths that have met run through the same nodes from there on).  With MAX_DEDUP_DEPTH >= tree depth the Merkle work of a
+// proof is planned per tree: query q follows the lowest-numbered query r < q whose path it meets first, at height h_q, and hashes only
+// the h_q levels below the meeting node.  A resolve kernel then checks, word for word, that q's node at height h_q and q's remaining
+// siblings ARE r's (if they are, q's root is r's root by construction; if not — a corrupted proof — q's path is hashed to the root after
+// all, in a second round of the same hashing kernel), so every per-query result is exactly what the per-query schedule gives.
+enum { STWO_DEDUP_MAX_DEPTH = 16, STWO_DEDUP_MAX_BINS = 64 };
+struct StwoDedup {
+    // per chain c = tree * Q + q of proof i (tree 0 = trace, 1 = composition, 2 + l = FRI layer l), index i * chains + c:
+    uint32_t *plan;      // bits 0-4 h (levels hashed in round 1), bit 6 check failed, bit 7 follower, bits 8-11 leader query, bits 16-31 checkpoint mask (bit 15 + k: height k)
+    uint64_t *ckpt_to;   // nibble k - 1: the follower query that needs this chain's node at height k
+    uint32_t *own;       // [8] round 1: the chain's last node = the root (full chains) or the node at height h (followers)
+    uint32_t *ckpt;      // [8] written by the LEADER of this chain: the leader's node at this chain's height h; after the check, round 2 puts
+                         //     the root of a follower that failed it here
+    uint32_t *bin_count; // [2][MAX_BINS] tasks per bin and round; a bin = (kind, steps) so that a warp's 32 tasks have one length; longest first
+    uint32_t *bin_list;  // chain ids (i * chains + c); bin b of round r at bin_base[r][b] .. + its capacity
+    uint32_t bin_base[2][STWO_DEDUP_MAX_BINS];
+    uint8_t bin_of[2][4][STWO_DEDUP_MAX_DEPTH + 1]; // round, kind (0 trace, 1 composition, 2 FRI, 3 = from a stored node), steps -> bin; 0xff = none
+    uint32_t n_bins[2], chains;
+    uint32_t enabled;
+};
+
 struct StwoParams {
     ssym_stwo_config_t cfg;
     ssym_stwo_layout_t lo;
@@ -58,7 +82,12 @@ struct StwoParams {
     uint32_t *status;       // n
     ssym_stwo_trace_t *trace; // n or nullptr
     uint32_t n;
+    StwoDedup dd;
 };
+
+// Fills the static part of StwoDedup (bins, capacities) for a configuration and a chunk capacity of `cap` proofs; returns the number of
+// bin_list entries needed, or 0 when the configuration is outside the planner's range (the per-query kernel is used then).
+size_t stwo_dedup_layout(const ssym_stwo_config_t &cfg, size_t cap, StwoDedup &dd);
 
 // Optional per-kernel event timing (ssym_profile_enable): begin/end bracket one kernel launch on stream s.
 struct Profiler {

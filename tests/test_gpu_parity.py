@@ -97,6 +97,44 @@ def test_stwo_negatives_match_oracle(S, ver, orc, preset, mode):
         assert status[0] == 0 and all(status[1:1 + len(names)] != 0)  # every corruption class is rejected
 
 
+def test_stwo_shared_node_schedule_matches_oracle(S, ver, orc):
+    """The Merkle paths of one tree share nodes above the height where they meet (StwoDedup, csrc/stwo_kernels.cuh): hashed once, the other
+    queries take the result only if their own node and their own remaining siblings are bit-identical.  Corrupt, for every tree and every
+    query in turn, (a) the sibling just below the root, (b) a sibling in the middle, (c) the leaf sibling, (d) the query's leaf data: the
+    whole trace (every recomputed root, every per-query mask, the first failing assert) must be what the per-query oracle gives.  Also
+    proofs whose queries collide: duplicated queries cannot be forged (the channel draws them), so their effect is covered by a proof
+    with many distinct seeds below."""
+    cfg, packed = golden_stwo(S, "prod", 1)
+    lo = S.stwo_layout(cfg)
+    G, Q, L = cfg.lde_log, cfg.n_queries, cfg.n_fri_layers
+    recs = [packed]
+    for q in range(Q):
+        for base, d in [(lo.off_trace_sib, G), (lo.off_cp_sib, G)] + [(lo.off_fri_sib[l], G - 1 - l) for l in range(L + 1)]:
+            for lvl in {d - 1, d // 2, 0}:
+                recs.append(S.witness.apply_mutation(packed, base + (q * d + lvl) * 8 + (q + lvl) % 8, 1 << ((3 * q + lvl) % 32)))
+        recs.append(S.witness.apply_mutation(packed, lo.off_qvals + 20 * q + 1, 1))       # trace leaf
+        recs.append(S.witness.apply_mutation(packed, lo.off_qvals + 20 * q + 4 + q, 1))   # composition leaf
+        for l in range(L + 1):
+            recs.append(S.witness.apply_mutation(packed, lo.off_fri_wit + (l * Q + q) * 4 + l % 4, 1))  # FRI witness = the sibling leaf
+    batch = np.concatenate(recs)
+    n = len(recs)
+    accept, status, traces = ver.stwo_verify_batch(batch, cfg, n, want_status=True, want_trace=True)
+    o_accept, o_status, o_traces = orc.stwo_verify_batch(ocfg(cfg), batch, n, want_trace=True)
+    assert status[0] == 0 and (status[1:] != 0).all()
+    assert (status == o_status).all(), [(i, hex(status[i]), hex(o_status[i])) for i in np.nonzero(status != o_status)[0][:5]]
+    assert (accept == o_accept).all()
+    for i in range(n):
+        assert trace_bytes(traces[i]) == trace_bytes(o_traces[i]), (i, diff_traces(traces[i], o_traces[i], S.StwoTrace))
+    # honest proofs of many seeds (different query patterns, incl. colliding pair indices in the small FRI layers), full traces
+    seeds = np.arange(5000, 5096, dtype=np.uint64)
+    proofs = ver.stwo_prove_batch(seeds, cfg)
+    accept, status, traces = ver.stwo_verify_batch(proofs.ravel(), cfg, len(seeds), want_status=True, want_trace=True)
+    o_accept, o_status, o_traces = orc.stwo_verify_batch(ocfg(cfg), proofs.ravel(), len(seeds), want_trace=True)
+    assert (status == 0).all() and (o_status == 0).all()
+    for i in range(len(seeds)):
+        assert trace_bytes(traces[i]) == trace_bytes(o_traces[i]), (i, diff_traces(traces[i], o_traces[i], S.StwoTrace))
+
+
 def test_stwo_device_resident_and_large_batch(S, ver, orc):
     """BASELINE config 2 shape: proof.json replicated x1024 (+ negatives sprinkled in), inputs resident in HBM."""
     import torch
