@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
 #define DD_NONE 0xffu
 #define DD_FOLLOWER 0x80u
 #define DD_INVALID 0x40u
+#define DD_SIBDIFF 0x20u
 
 // Appends chain `c` to bin `bin` of round `round`: counters privatised in shared memory, one global atomic per (CTA, bin).
 // Every thread of the CTA calls this (want = false for threads with nothing to append; up to two appends per thread).
@@ -659,6 +660,16 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
     uint32_t *dst = (round == 0 ? p.dd.own : p.dd.ckpt) + (size_t)cg * 8; // round 2 reuses the follower's checkpoint slot for its root
 #pragma unroll
     for (int k = 0; k < 8; k++) dst[k] = cur[k];
+    if (round == 0 && (pw & DD_FOLLOWER)) { // the levels this follower skips: are its siblings there the leader's?  (proof data only)
+        const uint4 *sq = reinterpret_cast<const uint4 *>(sib), *sr = reinterpret_cast<const uint4 *>(sib + ((int)((pw >> 8) & 15u) - (int)q) * (int)(depth * 8));
+        uint32_t diff = 0;
+#pragma unroll 2
+        for (uint32_t k = h; k < depth; k++) {
+            const uint4 a0 = __ldg(sq + 2 * k), a1 = __ldg(sq + 2 * k + 1), b0 = __ldg(sr + 2 * k), b1 = __ldg(sr + 2 * k + 1);
+            diff |= (a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w);
+        }
+        if (diff) p.dd.plan[cg] = pw | DD_SIBDIFF;
+    }
     }
 }
 
@@ -685,8 +696,8 @@ __global__ void __launch_bounds__(256) stwo_check_kernel(StwoParams p) {
     const uint32_t d = tree < 2 ? G : G - 1 - layer;
     const uint32_t *sib0 = pk + (tree == 0 ? lo.off_trace_sib : tree == 1 ? lo.off_cp_sib : lo.off_fri_sib[layer]);
     bool valid = true;
-    if (h >= 1) {
-        valid = eq8(p.dd.own + (size_t)cg * 8, p.dd.ckpt + (size_t)cg * 8);
+    if (h >= 1) { // its remaining siblings were compared by the chain's own thread in round 1
+        valid = !(pw & DD_SIBDIFF) && eq8(p.dd.own + (size_t)cg * 8, p.dd.ckpt + (size_t)cg * 8);
     } else if (kind == 2) { // same leaf pair: the two 16-byte leaves, in tree order (adjacent_leaves fri/layers.simf:29-37), must agree
         const uint32_t *qs = p.ctx + (size_t)i * CX::WORDS + CX::QUERIES;
         const uint32_t *ev = p.fri_evals + ((size_t)i * (L + 1) + layer) * Q * 4;
@@ -702,7 +713,7 @@ __global__ void __launch_bounds__(256) stwo_check_kernel(StwoParams p) {
     const uint4 *sq = reinterpret_cast<const uint4 *>(sib0 + q * d * 8), *sr = reinterpret_cast<const uint4 *>(sib0 + lead * d * 8);
     uint32_t diff = 0; // branch-free so that the loads of all levels are in flight together
 #pragma unroll 4
-    for (uint32_t k = h; k < d; k++) {
+    for (uint32_t k = 0; h == 0 && k < d; k++) { // (followers that met at the leaf have no thread in round 1)
         const uint4 a0 = __ldg(sq + 2 * k), a1 = __ldg(sq + 2 * k + 1), b0 = __ldg(sr + 2 * k), b1 = __ldg(sr + 2 * k + 1);
         diff |= (a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w);
     }
