@@ -440,7 +440,7 @@ def main():
     # end to end from the reference's own input format: `.wit` JSON TEXT in pinned host memory -> accept bits
     # (ssym_stwo_verify_wit_batch: text H2D, GPU tokeniser + packer, verifier, D2H bitmap; 122 KB of text per proof)
     wit_raw = open(os.path.join(ROOT, "tests", "golden", "stwo_proof_prod.wit"), "rb").read()
-    n_wit = 4 * n
+    n_wit = 8 * n  # 8 192 witnesses = 1 GB of text per step: the synchronous call's exposed first copy / last kernels stay below 10 %
     wit_pinned = torch.empty(len(wit_raw) * n_wit, dtype=torch.uint8).pin_memory()
     wit_np = wit_pinned.numpy()
     wit_np.reshape(n_wit, len(wit_raw))[:] = np.frombuffer(wit_raw, dtype=np.uint8)

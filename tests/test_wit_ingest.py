@@ -265,3 +265,35 @@ def test_cli_gpu_ingestion_matches_host_pack(S, tmp_path):
         r = subprocess.run([cli, "--program", "stwo", "--mode", "ref-literal", "--witness", good] + extra, capture_output=True, text=True)
         assert r.returncode == 1 and r.stdout.startswith("reject")  # the reference at HEAD rejects its own fixture
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_wit_batch_edge_cases(S):
+    cfg = S.stwo_config("testing", S.MODE_PROVER_CONSISTENT)
+    text = open(os.path.join(GOLDEN, "stwo_proof_testing.wit")).read()
+    ver = S.Verifier(0)
+    lo = S.stwo_layout(cfg)
+    # empty batch
+    packed, flags = ver.stwo_pack_wit_batch(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64), cfg)
+    assert packed.shape == (0, lo.stride_words) and flags.size == 0
+    # zero-length witnesses between good ones; 33 witnesses (bitmap word boundary)
+    batch = [text if i % 3 else "" for i in range(33)]
+    blob, offsets = S.witness.concat_wit_texts(batch)
+    accept, status, flags = ver.stwo_verify_wit_batch(blob, offsets, cfg, want_status=True, want_flags=True)
+    assert list(flags) == [0 if i % 3 else 2 for i in range(33)]
+    bits = np.unpackbits(accept.view(np.uint8), bitorder="little")[:33]
+    assert list(bits) == [1 if i % 3 else 0 for i in range(33)]
+    assert all((status[i] == 0) == bool(i % 3) for i in range(33))
+    # offsets must be non-decreasing
+    bad = offsets.copy()
+    bad[4] = bad[7]
+    with pytest.raises(S.SsymError):
+        ver.stwo_pack_wit_batch(blob, bad, cfg)
+    # a witness of the OTHER preset is well-formed JSON of the wrong shape: the host parser decides (shape or parse), never a crash
+    prod = open(os.path.join(GOLDEN, "stwo_proof_prod.wit")).read()
+    blob, offsets = S.witness.concat_wit_texts([text, prod, text])
+    _, flags = ver.stwo_pack_wit_batch(blob, offsets, cfg)
+    assert flags[0] == 0 and flags[2] == 0 and flags[1] in (1, 2)
+    _, ref_flags = _host_reference(S, cfg, [text, prod, text])
+    assert list(flags) == list(ref_flags)
+    ver.close()
