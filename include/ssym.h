@@ -356,7 +356,7 @@ int ssym_s101_pack_wit(const char *json_text, size_t len, uint32_t *out, size_t 
  * [offsets[i], offsets[i+1]) of `text`) -> n packed proofs, tokenised and packed ON THE GPU (one CTA per witness,
  * csrc/wit_kernels.cu).  Same result as n calls of ssym_stwo_pack_wit: flags[i] = SSYM_WIT_OK / _SHAPE / _PARSE, and the
  * record of a flagged witness is zero-filled.  Texts using grammar the generator never emits (JSON escapes, `_` separators,
- * upper-case hex, redundant parentheses, trailing commas, decimal literals above 64 bits) and malformed ones are detected on
+ * upper-case hex, redundant parentheses, trailing commas) and malformed ones are detected on
  * the GPU and re-parsed by the host parser, so the accepted grammar is exactly that of ssym_stwo_pack_wit.
  *  text / offsets / packed_out (n * stride_words) / flags (n u32) all live in `memspace`.  Synchronous. */
 int ssym_stwo_pack_wit_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const char *text, const uint64_t *offsets,
@@ -374,6 +374,14 @@ int ssym_stwo_wit_skeleton(const ssym_stwo_config_t *cfg, int name, uint8_t *ske
  *  accept_bits ((n+31)/32 words), status (NULL or n), flags (NULL or n) live in `memspace`.  Synchronous. */
 int ssym_stwo_verify_wit_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const char *text, const uint64_t *offsets,
                                size_t n, uint32_t *accept_bits, uint32_t *status, uint32_t *flags, int memspace);
+
+/* The same for stark101 witness texts (stark101/src/main.simf:12-20, stark101/scripts/generate_wit.py:13-29).  The lists of a stark101
+ * witness have no fixed length, so the GPU tokeniser works with the shape (number of FRI layers, every sibling count) of the first witness
+ * of the batch the host parser accepts; witnesses of another shape or another formatting, and malformed ones, go through the host parser
+ * (a well-typed witness of another shape is verified in a batch of its own), so every verdict is the one ssym_s101_pack_wit +
+ * ssym_stark101_verify_batch give.  flags: SSYM_WIT_OK / SSYM_WIT_PARSE. */
+int ssym_stark101_verify_wit_batch(ssym_ctx_t *ctx, const char *text, const uint64_t *offsets, size_t n, uint32_t *accept_bits,
+                                   uint32_t *status, uint32_t *flags, int memspace);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -114,6 +114,7 @@ SYMBOLS = {
     "ssym_stwo_wit_skeleton": (_I, [C.POINTER(StwoConfig), _I, _V, C.POINTER(_SZ), _V, C.POINTER(_SZ)]),
     "ssym_stwo_pack_wit_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _I]),
     "ssym_stwo_verify_wit_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _V, _I]),
+    "ssym_stark101_verify_wit_batch": (_I, [_V, _V, _V, _SZ, _V, _V, _V, _I]),
 }
 
 WIT_OK, WIT_SHAPE, WIT_PARSE = 0, 1, 2  # per-witness ingestion flags (include/ssym.h)

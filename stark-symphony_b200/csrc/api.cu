@@ -117,6 +117,7 @@ struct ssym_ctx {
     DevBuf prv_scratch[9];
     uint32_t prv_T = 0, prv_G = 0;
     // GPU .wit ingestion: token skeleton / slot tables per config, double-buffered text + packed staging, pinned flag mirrors
+    DevBuf wit101_skel, wit101_slots, wit101_templ, wit101_offs, wit101_idx, wit101_st, wit101_oblob, wit101_ooff, wit101_oacc;
     DevBuf wit_skel, wit_slots, wit_text[2], wit_offs[2], wit_packed[2], wit_flags[2], wit_numpos[2];
     uint32_t wit_total_slots = 0;
     WitTables wit_tab{};
@@ -206,6 +207,7 @@ void ssym_destroy(ssym_ctx_t *c) {
         if (c->wit_hoffs[i]) cudaFreeHost(c->wit_hoffs[i]);
     }
     c->wit_skel.release(); c->wit_slots.release();
+    c->wit101_skel.release(); c->wit101_slots.release(); c->wit101_templ.release(); c->wit101_offs.release(); c->wit101_idx.release(); c->wit101_st.release(); c->wit101_oblob.release(); c->wit101_ooff.release(); c->wit101_oacc.release();
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -463,7 +465,7 @@ namespace {
 struct WitSkeleton {
     std::vector<uint8_t> skel;
     std::vector<uint32_t> slots;
-    uint32_t skel_off[WIT_NAMES], skel_len[WIT_NAMES], slot_off[WIT_NAMES], slot_cnt[WIT_NAMES];
+    uint32_t skel_off[WIT_MAX_NAMES], skel_len[WIT_MAX_NAMES], slot_off[WIT_MAX_NAMES], slot_cnt[WIT_MAX_NAMES];
     int cur = -1;
     void begin(int name) { cur = name; skel_off[name] = (uint32_t)skel.size(); slot_off[name] = (uint32_t)slots.size(); }
     void end() { skel_len[cur] = (uint32_t)skel.size() - skel_off[cur]; slot_cnt[cur] = (uint32_t)slots.size() - slot_off[cur]; }
@@ -578,6 +580,8 @@ static int ensure_wit_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg, const s
         c->wit_tab.skel_off[k] = w.skel_off[k]; c->wit_tab.skel_len[k] = w.skel_len[k];
         c->wit_tab.slot_off[k] = w.slot_off[k]; c->wit_tab.slot_cnt[k] = w.slot_cnt[k];
     }
+    static const char *const stwo_names[WIT_NAMES] = {"COMMITMENTS", "DECOMMITMENTS", "OODS_EVALS", "FRI_COMMITMENTS", "FRI_DECOMMITMENTS", "POW_NONCE"};
+    wit_set_names(c->wit_tab, stwo_names, WIT_NAMES);
     c->wit_total_slots = (uint32_t)w.slots.size();
     c->wit_Q = cfg.n_queries; c->wit_L = cfg.n_fri_layers; c->wit_G = cfg.lde_log;
     return SSYM_OK;
@@ -790,6 +794,250 @@ extern "C" int ssym_stwo_verify_wit_batch(ssym_ctx_t *c, const ssym_stwo_config_
                                           uint32_t *accept_bits, uint32_t *status, uint32_t *flags, int memspace) {
     if (!accept_bits && n) return fail(SSYM_ERR_USAGE, "NULL argument");
     return wit_batch(c, cfg, text, offsets, n, true, nullptr, accept_bits, status, flags, memspace);
+}
+
+/* ---- stark101: `.wit` text on the GPU ------------------------------------------------------------------ */
+namespace {
+// The lists of a stark101 witness have no fixed length (List<_, 32>), so the skeleton is that of ONE shape: number of FRI layers and every
+// sibling count, taken from the first witness of the batch the host parser accepts.  Witnesses of that shape and of the generator's
+// formatting are packed on the GPU into fixed-stride records; any other goes through the host parser.
+struct S101Shape {
+    uint32_t n_layers = 0, ns[3] = {0, 0, 0}, a[SSYM_S101_MAX_LIST] = {0}, b[SSYM_S101_MAX_LIST] = {0}, total = 0;
+    bool operator==(const S101Shape &o) const {
+        return n_layers == o.n_layers && total == o.total && !memcmp(ns, o.ns, sizeof ns) && !memcmp(a, o.a, sizeof a) && !memcmp(b, o.b, sizeof b);
+    }
+};
+bool s101_shape_of(const uint32_t *rec, size_t words, S101Shape &sh) {
+    sh = S101Shape();
+    if (words < 20 || rec[0] != words || rec[1] > SSYM_S101_MAX_LIST) return false;
+    sh.total = (uint32_t)words;
+    sh.n_layers = rec[1];
+    size_t w = 20;
+    for (int i = 0; i < 3; i++) { sh.ns[i] = rec[2 + i]; if (sh.ns[i] > SSYM_S101_MAX_LIST) return false; w += 8 * sh.ns[i]; }
+    for (uint32_t l = 0; l < sh.n_layers; l++) {
+        if (w + 16 > words) return false;
+        sh.a[l] = rec[w + 11];
+        sh.b[l] = rec[w + 12];
+        if (sh.a[l] > SSYM_S101_MAX_LIST || sh.b[l] > SSYM_S101_MAX_LIST) return false;
+        w += 16 + 8 * (sh.a[l] + sh.b[l]);
+    }
+    return w == words;
+}
+// witnesses P_MT_ROOT, P_EVALS, FRI_LAYERS, FRI_LAST_LAYER (stark101/src/main.simf:12-20) in the syntax of stark101/scripts/generate_wit.py:13-29
+// (a FRI layer is written with doubled parentheses there); record layout: include/ssym.h "Packed stark101 proof"
+void build_s101_skeleton(const S101Shape &sh, WitSkeleton &w, std::vector<uint32_t> &templ) {
+    templ.assign(sh.total, 0);
+    templ[0] = sh.total;
+    templ[1] = sh.n_layers;
+    w.begin(0);
+    w.num(8, WIT_KIND_U256);
+    w.end();
+    w.begin(1);
+    w.t("(");
+    uint32_t at = 20;
+    for (int i = 0; i < 3; i++) {
+        templ[2 + i] = sh.ns[i];
+        if (i) w.t(",");
+        w.t("(");
+        w.num(16 + i, WIT_KIND_U32);
+        w.t(",");
+        w.digest_list(at, sh.ns[i]);
+        w.t(")");
+        at += 8 * sh.ns[i];
+    }
+    w.t(")");
+    w.end();
+    w.begin(2);
+    w.t("L[");
+    for (uint32_t l = 0; l < sh.n_layers; l++) {
+        if (l) w.t(",");
+        templ[at + 11] = sh.a[l];
+        templ[at + 12] = sh.b[l];
+        w.t("((");
+        w.num(at, WIT_KIND_U256); w.t(",");
+        w.num(at + 8, WIT_KIND_U32); w.t(",");
+        w.num(at + 9, WIT_KIND_U32); w.t(",");
+        w.digest_list(at + 16, sh.a[l]); w.t(",");
+        w.num(at + 10, WIT_KIND_U32); w.t(",");
+        w.digest_list(at + 16 + 8 * sh.a[l], sh.b[l]);
+        w.t("))");
+        at += 16 + 8 * (sh.a[l] + sh.b[l]);
+    }
+    w.t("]");
+    w.end();
+    w.begin(3);
+    w.num(5, WIT_KIND_U32);
+    w.end();
+}
+const size_t S101_MAX_WORDS = 20 + 8 * 3 * SSYM_S101_MAX_LIST + SSYM_S101_MAX_LIST * (16 + 8 * 2 * SSYM_S101_MAX_LIST);
+} // namespace
+
+extern "C" int ssym_stark101_verify_wit_batch(ssym_ctx_t *c, const char *text, const uint64_t *offsets, size_t n, uint32_t *accept_bits, uint32_t *status,
+                                              uint32_t *flags_out, int memspace) {
+    if (!c || !accept_bits || ((!text || !offsets) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    if (n == 0) return SSYM_OK;
+    if (n > 0x7fffffffull) return fail(SSYM_ERR_USAGE, "batch too large for one call");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ssym_join(c);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    const size_t n_words = (n + 31) / 32;
+    // host view of the offsets, and of the text where the host parser needs it
+    std::vector<uint64_t> h_off(n + 1);
+    if (memspace == SSYM_MEM_DEVICE) {
+        CUDA_TRY(cudaMemcpyAsync(h_off.data(), offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    } else {
+        memcpy(h_off.data(), offsets, (n + 1) * sizeof(uint64_t));
+    }
+    for (size_t i = 0; i < n; i++)
+        if (h_off[i + 1] < h_off[i]) return fail(SSYM_ERR_USAGE, "witness offsets must be non-decreasing");
+    std::vector<char> tmp_text;
+    auto host_text = [&](size_t i, const char **txt, size_t *len) -> int {
+        *len = (size_t)(h_off[i + 1] - h_off[i]);
+        if (memspace == SSYM_MEM_HOST) { *txt = text + h_off[i]; return SSYM_OK; }
+        tmp_text.resize(*len + 1);
+        CUDA_TRY(cudaMemcpyAsync(tmp_text.data(), text + h_off[i], *len, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        *txt = tmp_text.data();
+        return SSYM_OK;
+    };
+    // the batch's shape: the first witness the host parser accepts
+    std::vector<uint32_t> rec(S101_MAX_WORDS);
+    std::vector<uint32_t> h_flags(n, SSYM_WIT_SLOW);
+    S101Shape shape;
+    bool have_shape = false;
+    size_t first_ok = 0;
+    for (; first_ok < n && !have_shape; first_ok++) {
+        const char *txt;
+        size_t len, words = rec.size();
+        rc = host_text(first_ok, &txt, &len);
+        if (rc) return rc;
+        if (ssym_s101_pack_wit(txt, len, rec.data(), &words) == SSYM_OK && s101_shape_of(rec.data(), words, shape)) have_shape = true;
+        else h_flags[first_ok] = SSYM_WIT_PARSE;
+    }
+    uint32_t *d_accept = accept_bits, *d_status = status;
+    if (memspace == SSYM_MEM_HOST || !status) { CUDA_TRY(c->d_status.ensure(n * 4)); d_status = c->d_status.as<uint32_t>(); }
+    if (memspace == SSYM_MEM_HOST) { CUDA_TRY(c->d_accept.ensure(n_words * 4)); d_accept = c->d_accept.as<uint32_t>(); }
+    const uint32_t stride = have_shape ? shape.total : 20;
+    CUDA_TRY(c->wit_packed[0].ensure(n * (size_t)stride * 4));
+    CUDA_TRY(c->wit_flags[0].ensure(n * 4));
+    CUDA_TRY(c->wit101_offs.ensure((n + 1) * 8));
+    uint32_t *d_packed = c->wit_packed[0].as<uint32_t>(), *d_flags = c->wit_flags[0].as<uint32_t>();
+    std::vector<uint32_t> odd_blob, odd_idx;
+    std::vector<uint64_t> odd_off(1, 0);
+    if (have_shape) {
+        WitSkeleton w;
+        std::vector<uint32_t> templ;
+        build_s101_skeleton(shape, w, templ);
+        WitTables tab{};
+        CUDA_TRY(c->wit101_skel.ensure(w.skel.size()));
+        CUDA_TRY(c->wit101_slots.ensure(w.slots.size() * 4));
+        CUDA_TRY(c->wit101_templ.ensure(templ.size() * 4));
+        CUDA_TRY(cudaMemcpyAsync(c->wit101_skel.p, w.skel.data(), w.skel.size(), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->wit101_slots.p, w.slots.data(), w.slots.size() * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->wit101_templ.p, templ.data(), templ.size() * 4, cudaMemcpyHostToDevice, s));
+        tab.skel = c->wit101_skel.as<uint8_t>();
+        tab.slots = c->wit101_slots.as<uint32_t>();
+        for (int k = 0; k < 4; k++) { tab.skel_off[k] = w.skel_off[k]; tab.skel_len[k] = w.skel_len[k]; tab.slot_off[k] = w.slot_off[k]; tab.slot_cnt[k] = w.slot_cnt[k]; }
+        static const char *const names[4] = {"P_MT_ROOT", "P_EVALS", "FRI_LAYERS", "FRI_LAST_LAYER"};
+        wit_set_names(tab, names, 4);
+        const uint8_t *d_text;
+        const uint64_t *d_offs;
+        if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(c->wit_text[0].ensure((size_t)(h_off[n] - h_off[0]) + 16));
+            CUDA_TRY(c->wit_offs[0].ensure((n + 1) * 8));
+            CUDA_TRY(cudaMemcpyAsync(c->wit_text[0].p, text + h_off[0], (size_t)(h_off[n] - h_off[0]), cudaMemcpyHostToDevice, s));
+            std::vector<uint64_t> rel(n + 1);
+            for (size_t i = 0; i <= n; i++) rel[i] = h_off[i] - h_off[0];
+            CUDA_TRY(cudaMemcpyAsync(c->wit_offs[0].p, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s)); // rel is a local
+            d_text = c->wit_text[0].as<uint8_t>();
+            d_offs = c->wit_offs[0].as<uint64_t>();
+        } else {
+            d_text = reinterpret_cast<const uint8_t *>(text);
+            d_offs = offsets;
+        }
+        CUDA_TRY(c->wit_numpos[0].ensure(n * w.slots.size() * 4));
+        launch_wit_fill_template(d_packed, c->wit101_templ.as<uint32_t>(), stride, n, s);
+        WitParams p;
+        p.text = d_text; p.offsets = d_offs; p.n = (uint32_t)n; p.stride_words = stride; p.packed = d_packed; p.flags = d_flags;
+        p.numpos = c->wit_numpos[0].as<uint32_t>(); p.total_slots = (uint32_t)w.slots.size(); p.tab = tab;
+        launch_wit_pack(p, s);
+        c->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(h_flags.data(), d_flags, n * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    } else {
+        CUDA_TRY(cudaMemsetAsync(d_packed, 0, n * (size_t)stride * 4, s));
+    }
+    // everything the GPU handed back: host parser; same shape -> patched in place, another shape -> verified in a batch of its own
+    std::vector<uint32_t> zero(stride, 0); // what takes the place of an ill-typed witness: the minimal record (no layers, no siblings), as the CLI / Python packers do
+    zero[0] = 20;
+    for (size_t i = 0; i < n; i++) {
+        if (h_flags[i] == SSYM_WIT_OK) continue;
+        const uint32_t *src = zero.data();
+        if (have_shape && !getenv("SSYM_WIT_DEBUG_NOSLOW")) {
+            const char *txt;
+            size_t len, words = rec.size();
+            rc = host_text(i, &txt, &len);
+            if (rc) return rc;
+            S101Shape sh;
+            if (ssym_s101_pack_wit(txt, len, rec.data(), &words) == SSYM_OK) {
+                h_flags[i] = SSYM_WIT_OK;
+                if (s101_shape_of(rec.data(), words, sh) && sh == shape) {
+                    src = rec.data();
+                } else { // well-typed, other lengths
+                    odd_idx.push_back((uint32_t)i);
+                    odd_blob.insert(odd_blob.end(), rec.begin(), rec.begin() + words);
+                    odd_off.push_back(odd_blob.size());
+                }
+            } else {
+                h_flags[i] = SSYM_WIT_PARSE;
+            }
+        } else if (!have_shape) {
+            h_flags[i] = SSYM_WIT_PARSE;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_packed + i * (size_t)stride, src, (size_t)stride * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s)); // rec is reused
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_flags, h_flags.data(), n * 4, cudaMemcpyHostToDevice, s));
+    std::vector<uint64_t> fixed(n + 1);
+    for (size_t i = 0; i <= n; i++) fixed[i] = (uint64_t)i * stride;
+    CUDA_TRY(cudaMemcpyAsync(c->wit101_offs.p, fixed.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    rc = ssym_stark101_verify_batch(c, d_packed, c->wit101_offs.as<uint64_t>(), n, d_accept, d_status, nullptr, SSYM_MEM_DEVICE);
+    if (rc) return rc;
+    launch_wit_apply_flags(d_flags, d_status, d_accept, (uint32_t)n, s);
+    c->launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(s)); // fixed / h_flags are locals; the staging below is reused by the nested call
+    if (!odd_idx.empty()) {
+        const size_t m = odd_idx.size();
+        CUDA_TRY(c->wit101_idx.ensure(m * 4));
+        CUDA_TRY(c->wit101_st.ensure(m * 4));
+        CUDA_TRY(c->wit101_oacc.ensure(((m + 31) / 32) * 4));
+        CUDA_TRY(c->wit101_oblob.ensure(odd_blob.size() * 4));
+        CUDA_TRY(c->wit101_ooff.ensure((m + 1) * 8));
+        CUDA_TRY(cudaMemcpyAsync(c->wit101_idx.p, odd_idx.data(), m * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->wit101_oblob.p, odd_blob.data(), odd_blob.size() * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->wit101_ooff.p, odd_off.data(), (m + 1) * 8, cudaMemcpyHostToDevice, s));
+        rc = ssym_stark101_verify_batch(c, c->wit101_oblob.as<uint32_t>(), c->wit101_ooff.as<uint64_t>(), m, c->wit101_oacc.as<uint32_t>(),
+                                        c->wit101_st.as<uint32_t>(), nullptr, SSYM_MEM_DEVICE);
+        if (rc) return rc;
+        launch_wit_scatter_status(c->wit101_idx.as<uint32_t>(), c->wit101_st.as<uint32_t>(), (uint32_t)m, d_status, d_accept, s);
+        c->launches += 1;
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (memspace == SSYM_MEM_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(accept_bits, d_accept, n_words * 4, cudaMemcpyDeviceToHost, s));
+        if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s));
+        if (flags_out) memcpy(flags_out, h_flags.data(), n * 4);
+    } else if (flags_out) {
+        CUDA_TRY(cudaMemcpyAsync(flags_out, h_flags.data(), n * 4, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    return SSYM_OK;
 }
 
 /* ---- Stwo prover ------------------------------------------------------------------------------------ */

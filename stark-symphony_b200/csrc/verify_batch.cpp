@@ -11,8 +11,8 @@
 //   verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--mode {ref-literal,prover-consistent}]
 //                (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet] [--host-pack]
 //
-// Stwo witnesses are tokenised and packed ON THE GPU (ssym_stwo_verify_wit_batch: the `.wit` text is what crosses PCIe); --host-pack (and
-// --trace, which needs the packed records on the host) uses the host parser + ssym_stwo_verify_batch instead.
+// Witnesses are tokenised and packed ON THE GPU (ssym_stwo_verify_wit_batch / ssym_stark101_verify_wit_batch: the `.wit` text is what crosses
+// PCIe); --host-pack (and --trace, which needs the packed records on the host) uses the host parser + the packed-batch entry points instead.
 #include <dirent.h>
 
 #include <algorithm>
@@ -110,12 +110,12 @@ int main(int argc, char **argv) {
     std::vector<uint64_t> offsets;
     std::vector<ssym_stwo_trace_t> traces;
     std::vector<ssym_s101_trace_t> traces101;
-    const bool gpu_ingest = program == "stwo" && !want_trace && !host_pack;
+    const bool gpu_ingest = !want_trace && !host_pack;
     std::string wit_text;               // stwo, GPU ingestion: the concatenated witness texts
     std::vector<uint64_t> wit_offsets;
     std::vector<uint32_t> wit_flags;
     if (gpu_ingest) {
-        if (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || ssym_stwo_layout(&cfg, &lo)) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
+        if (program == "stwo" && (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || ssym_stwo_layout(&cfg, &lo))) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
         wit_offsets.push_back(0);
         for (size_t f = 0; f < n_files; f++) {
             std::string text;
@@ -185,8 +185,10 @@ int main(int argc, char **argv) {
                     std::vector<uint64_t> offs(wit_offsets.begin() + b, wit_offsets.begin() + e + 1);
                     const uint64_t base = offs[0];
                     for (auto &o : offs) o -= base;
-                    rc = ssym_stwo_verify_wit_batch(ctx, &cfg, wit_text.data() + base, offs.data(), e - b, accept.data() + b / 32, status.data() + b,
-                                                    wit_flags.data() + b, SSYM_MEM_HOST);
+                    rc = program == "stwo" ? ssym_stwo_verify_wit_batch(ctx, &cfg, wit_text.data() + base, offs.data(), e - b, accept.data() + b / 32,
+                                                                        status.data() + b, wit_flags.data() + b, SSYM_MEM_HOST)
+                                           : ssym_stark101_verify_wit_batch(ctx, wit_text.data() + base, offs.data(), e - b, accept.data() + b / 32,
+                                                                            status.data() + b, wit_flags.data() + b, SSYM_MEM_HOST);
                 } else if (program == "stwo")
                     rc = ssym_stwo_verify_batch(ctx, &cfg, packed.data() + b * (size_t)lo.stride_words, e - b, accept.data() + b / 32, status.data() + b,
                                                 want_trace ? traces.data() + b : nullptr, SSYM_MEM_HOST);

@@ -2,6 +2,8 @@
 // GPU `.wit` tokeniser / packer; see wit_kernels.cuh for the scheme.
 #include "wit_kernels.cuh"
 
+#include <algorithm>
+
 namespace ssym {
 namespace {
 
@@ -15,19 +17,15 @@ __device__ bool str_is(const uint8_t *t, uint32_t s, uint32_t e, const char *lit
         if (t[s + k] != (uint8_t)lit[k]) return false;
     return true;
 }
-__device__ int name_id(const uint8_t *t, uint32_t s, uint32_t e) { // stwo-verifier/src/main.simf:9-25
-    if (str_is(t, s, e, "COMMITMENTS", 11)) return 0;
-    if (str_is(t, s, e, "DECOMMITMENTS", 13)) return 1;
-    if (str_is(t, s, e, "OODS_EVALS", 10)) return 2;
-    if (str_is(t, s, e, "FRI_COMMITMENTS", 15)) return 3;
-    if (str_is(t, s, e, "FRI_DECOMMITMENTS", 17)) return 4;
-    if (str_is(t, s, e, "POW_NONCE", 9)) return 5;
+__device__ int name_id(const WitTables &tab, const uint8_t *t, uint32_t s, uint32_t e) {
+    for (uint32_t k = 0; k < tab.n_names; k++)
+        if (str_is(t, s, e, tab.name[k], tab.name_len[k])) return (int)k;
     return -1;
 }
 
 // The JSON level, by one thread: { NAME: { "value": "<text>", "type": "<text>" }, ... } (simfony-cli/src/main.rs:77-81).  `q` holds the
 // sorted positions of the `nq` quote characters (there are no backslashes in the file).  Fills the value span of every name.
-__device__ bool json_walk(const uint8_t *t, uint32_t len, const uint32_t *q, uint32_t nq, uint32_t *vstart, uint32_t *vend) {
+__device__ bool json_walk(const WitTables &tab, const uint8_t *t, uint32_t len, const uint32_t *q, uint32_t nq, uint32_t *vstart, uint32_t *vend) {
     uint32_t pos = 0, k = 0, seen = 0;
     auto skip = [&]() { while (pos < len && is_ws(t[pos])) pos++; };
     auto expect = [&](uint8_t ch) { skip(); if (pos < len && t[pos] == ch) { pos++; return true; } return false; };
@@ -60,7 +58,7 @@ __device__ bool json_walk(const uint8_t *t, uint32_t len, const uint32_t *q, uin
             break;
         }
         if (!expect('}') || !have || vs == ve) return false;
-        const int id = name_id(t, ns, ne);
+        const int id = name_id(tab, t, ns, ne);
         if (id < 0 || (seen >> id & 1)) return false;
         seen |= 1u << id;
         vstart[id] = vs;
@@ -71,7 +69,7 @@ __device__ bool json_walk(const uint8_t *t, uint32_t len, const uint32_t *q, uin
         break;
     }
     skip();
-    return pos == len && k == nq && seen == (1u << WIT_NAMES) - 1;
+    return pos == len && k == nq && seen == (1u << tab.n_names) - 1;
 }
 
 // ---- SWAR helpers (4 text bytes per 32-bit word, little endian: byte 0 = first character) ---------------------------
@@ -107,7 +105,7 @@ constexpr int LEX_WARPS = 4;
 __global__ void __launch_bounds__(32 * LEX_WARPS) wit_lex_kernel(WitParams p) {
     __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_q[LEX_WARPS][WIT_MAXQ];
-    __shared__ uint32_t s_span[LEX_WARPS][3 * WIT_NAMES];
+    __shared__ uint32_t s_span[LEX_WARPS][3 * WIT_MAX_NAMES];
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
         uint8_t k = K_BAD;
@@ -171,15 +169,16 @@ __global__ void __launch_bounds__(32 * LEX_WARPS) wit_lex_kernel(WitParams p) {
     bad = __any_sync(FULL, bad) || nq > WIT_MAXQ || (nq & 1u);
     __syncwarp();
     if (!bad && lane == 0) {
-        uint32_t vs[WIT_NAMES], ve[WIT_NAMES];
-        if (!json_walk(t, B.len, s_q[wib], nq, vs, ve)) {
+        uint32_t vs[WIT_MAX_NAMES], ve[WIT_MAX_NAMES];
+        const int NN = (int)p.tab.n_names;
+        if (!json_walk(p.tab, t, B.len, s_q[wib], nq, vs, ve)) {
             bad = true;
         } else { // spans in file order
-            uint32_t order[WIT_NAMES];
-            for (int a = 0; a < WIT_NAMES; a++) order[a] = a;
-            for (int a = 1; a < WIT_NAMES; a++)
+            uint32_t order[WIT_MAX_NAMES];
+            for (int a = 0; a < NN; a++) order[a] = a;
+            for (int a = 1; a < NN; a++)
                 for (int b = a; b > 0 && vs[order[b]] < vs[order[b - 1]]; b--) { const uint32_t x = order[b]; order[b] = order[b - 1]; order[b - 1] = x; }
-            for (int a = 0; a < WIT_NAMES; a++) { s_span[wib][3 * a] = vs[order[a]]; s_span[wib][3 * a + 1] = ve[order[a]]; s_span[wib][3 * a + 2] = order[a]; }
+            for (int a = 0; a < NN; a++) { s_span[wib][3 * a] = vs[order[a]]; s_span[wib][3 * a + 1] = ve[order[a]]; s_span[wib][3 * a + 2] = order[a]; }
         }
     }
     bad = __any_sync(FULL, bad);
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(32 * LEX_WARPS) wit_lex_kernel(WitParams p) {
     // ---- phase A: the six values, in file order ----
     uint32_t *numpos = p.numpos + (size_t)i * p.total_slots;
     uint32_t n_l = 0, n_lc = 0; // `l` tokens seen (each checked to start "list!") / i s t ! characters seen: must be 4 per `l`
-    for (int sidx = 0; sidx < WIT_NAMES; sidx++) {
+    for (int sidx = 0; sidx < (int)p.tab.n_names; sidx++) {
         const uint32_t ss = s_span[wib][3 * sidx], se = s_span[wib][3 * sidx + 1], name = s_span[wib][3 * sidx + 2];
         const uint8_t *skel = p.tab.skel + p.tab.skel_off[name];
         const uint32_t skel_len = p.tab.skel_len[name], slot_cnt = p.tab.slot_cnt[name], slot_off = p.tab.slot_off[name];
@@ -320,6 +319,34 @@ __device__ bool parse_number(const uint8_t *s, uint32_t slot, uint32_t *rec) {
         }
         return true;
     }
+    if (kw == 8) { // decimal u256 (stark101's digests): 9 digits per multiply-add over the 8 words
+        uint32_t n = 0;
+        while (is_numchar(s[n])) n++;
+        if (n > 78) return false;
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // little-endian words
+        uint32_t j = 0;
+        while (j < n) {
+            const uint32_t take = (n - j) % 9u ? (n - j) % 9u : 9u;
+            uint32_t chunk = 0, mul = 1;
+            for (uint32_t k = 0; k < take; k++, j++) {
+                const uint8_t c = s[j];
+                if (c < '0' || c > '9') return false;
+                chunk = chunk * 10u + (c - '0');
+                mul *= 10u;
+            }
+            uint64_t carry = chunk;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t x = (uint64_t)w[k] * mul + carry;
+                w[k] = (uint32_t)x;
+                carry = x >> 32;
+            }
+            if (carry) return false; // exceeds 256 bits
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) rec[off + k] = w[7 - k];
+        return true;
+    }
     uint64_t v = 0;
     for (const uint8_t *q = s; is_numchar(*q); q++) {
         const uint8_t c = *q;
@@ -332,8 +359,8 @@ __device__ bool parse_number(const uint8_t *s, uint32_t slot, uint32_t *rec) {
         if (v >> 32) return false;
         rec[off] = (uint32_t)v;
     } else {
-        rec[off + kw - 2] = (uint32_t)(v >> 32);
-        rec[off + kw - 1] = (uint32_t)v;
+        rec[off] = (uint32_t)(v >> 32);
+        rec[off + 1] = (uint32_t)v;
     }
     return true;
 }
@@ -346,6 +373,20 @@ __global__ void __launch_bounds__(256) wit_numbers_kernel(WitParams p) {
     if (!parse_number(t + p.numpos[(size_t)i * p.total_slots + k], __ldg(p.tab.slots + k), p.packed + (size_t)i * p.stride_words)) p.flags[i] = SSYM_WIT_SLOW;
 }
 
+// packed[i] = template for every i (the words of a record that are not literals: lengths, counts)
+__global__ void wit_fill_template_kernel(uint32_t *packed, const uint32_t *templ, uint32_t stride_words, uint64_t total_words) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_words; g += (uint64_t)gridDim.x * blockDim.x) packed[g] = templ[g % stride_words];
+}
+// status[idx[j]] = st[j], accept bit idx[j] = (st[j] == 0)
+__global__ void wit_scatter_status_kernel(const uint32_t *idx, const uint32_t *st, uint32_t m, uint32_t *status, uint32_t *accept_bits) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t i = idx[j];
+    if (status) status[i] = st[j];
+    if (st[j] == 0) atomicOr(&accept_bits[i >> 5], 1u << (i & 31));
+    else atomicAnd(&accept_bits[i >> 5], ~(1u << (i & 31)));
+}
+
 __global__ void wit_apply_flags_kernel(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || flags[i] == SSYM_WIT_OK) return;
@@ -355,11 +396,27 @@ __global__ void wit_apply_flags_kernel(const uint32_t *flags, uint32_t *status, 
 
 } // namespace
 
+void wit_set_names(WitTables &t, const char *const *names, uint32_t n) {
+    t.n_names = n;
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t len = 0;
+        for (; names[k][len] && len < WIT_NAME_CHARS; len++) t.name[k][len] = names[k][len];
+        t.name_len[k] = (uint8_t)len;
+    }
+}
+
 void launch_wit_pack(const WitParams &p, cudaStream_t s) {
     if (!p.n) return;
     wit_lex_kernel<<<(p.n + LEX_WARPS - 1) / LEX_WARPS, 32 * LEX_WARPS, 0, s>>>(p);
     const uint64_t threads = (uint64_t)p.n * p.total_slots;
     wit_numbers_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(p);
+}
+void launch_wit_fill_template(uint32_t *packed, const uint32_t *templ, uint32_t stride_words, size_t n, cudaStream_t s) {
+    const uint64_t total = (uint64_t)n * stride_words;
+    if (total) wit_fill_template_kernel<<<(uint32_t)std::min<uint64_t>((total + 255) / 256, 148 * 16), 256, 0, s>>>(packed, templ, stride_words, total);
+}
+void launch_wit_scatter_status(const uint32_t *idx, const uint32_t *st, uint32_t m, uint32_t *status, uint32_t *accept_bits, cudaStream_t s) {
+    if (m) wit_scatter_status_kernel<<<(m + 127) / 128, 128, 0, s>>>(idx, st, m, status, accept_bits);
 }
 void launch_wit_apply_flags(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n, cudaStream_t s) {
     if (n) wit_apply_flags_kernel<<<(n + 255) / 256, 256, 0, s>>>(flags, status, accept_bits, n);

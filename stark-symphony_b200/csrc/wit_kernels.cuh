@@ -21,22 +21,27 @@
 
 namespace ssym {
 
-enum { WIT_NAMES = 6 };
+enum { WIT_NAMES = 6 /* stwo-verifier/src/main.simf:9-25 */, WIT_MAX_NAMES = 8, WIT_NAME_CHARS = 20 };
 enum { WIT_KIND_U32 = 0, WIT_KIND_U64 = 1, WIT_KIND_U256 = 2 };
 
 struct WitTables {
     const uint8_t *skel;   // token skeletons of the six witness values, concatenated
     const uint32_t *slots; // per integer literal: packed word offset | kind << 28
-    uint32_t skel_off[WIT_NAMES], skel_len[WIT_NAMES];
-    uint32_t slot_off[WIT_NAMES], slot_cnt[WIT_NAMES];
+    uint32_t skel_off[WIT_MAX_NAMES], skel_len[WIT_MAX_NAMES];
+    uint32_t slot_off[WIT_MAX_NAMES], slot_cnt[WIT_MAX_NAMES];
+    // the program's witness names (main.simf): every one must be present exactly once, in any order
+    uint32_t n_names;
+    uint8_t name_len[WIT_MAX_NAMES];
+    char name[WIT_MAX_NAMES][WIT_NAME_CHARS];
 };
+void wit_set_names(WitTables &t, const char *const *names, uint32_t n);
 
 struct WitParams {
     const uint8_t *text;     // concatenated witness texts (device)
     const uint64_t *offsets; // n + 1 byte offsets into text (device)
     uint32_t n;
     uint32_t stride_words;
-    uint32_t *packed;        // n * stride_words, zero-filled by the caller
+    uint32_t *packed;        // n * stride_words, pre-filled by the caller with everything that is not a literal (zeros for Stwo)
     uint32_t *flags;         // n: SSYM_WIT_OK or SSYM_WIT_SLOW (internal: host re-parse)
     uint32_t *numpos;        // scratch, n * total_slots: file position of every integer literal (kernel 1 -> kernel 2)
     uint32_t total_slots;    // integer literals per witness (sum of slot_cnt)
@@ -44,6 +49,8 @@ struct WitParams {
 };
 
 void launch_wit_pack(const WitParams &p, cudaStream_t s);
+void launch_wit_fill_template(uint32_t *packed, const uint32_t *templ, uint32_t stride_words, size_t n, cudaStream_t s);
+void launch_wit_scatter_status(const uint32_t *idx, const uint32_t *st, uint32_t m, uint32_t *status, uint32_t *accept_bits, cudaStream_t s);
 // status[i] |= SSYM_ST_SHAPE and accept bit i cleared for every witness with a non-zero flag
 void launch_wit_apply_flags(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n, cudaStream_t s);
 

@@ -214,6 +214,16 @@ class Verifier:
         check(self.lib.ssym_stwo_verify_wit_batch(self.h, C.byref(cfg), _ptr(text), _ptr(offsets), n, _ptr(accept), _ptr(status), _ptr(flags), space))
         return accept, status, flags
 
+    def stark101_verify_wit_batch(self, text, offsets, want_status: bool = False, want_flags: bool = False):
+        """verify_proof (stark101) for n witness TEXTS, tokenised and packed on the GPU (ssym_stark101_verify_wit_batch)."""
+        n = (offsets.numel() if hasattr(offsets, "numel") else offsets.size) - 1
+        space = self._space(text)
+        accept = self._alloc(text, (n + 31) // 32)
+        status = self._alloc(text, n) if want_status else None
+        flags = self._alloc(text, n) if want_flags else None
+        check(self.lib.ssym_stark101_verify_wit_batch(self.h, _ptr(text), _ptr(offsets), n, _ptr(accept), _ptr(status), _ptr(flags), space))
+        return accept, status, flags
+
     # ---- `simfony run`-shaped convenience ---------------------------------------------------------------
     def run_stwo_wit(self, wit_texts: Sequence[str], preset: str = "prod", mode: int = _lib.MODE_REF_LITERAL):
         """`simfony run main.simf --witness x.wit` for many witnesses: returns (accept: list[bool], status: np.ndarray)."""
@@ -227,10 +237,8 @@ class Verifier:
     def run_stark101_wit(self, wit_texts: Sequence[str]):
         from . import witness
 
-        blob, offsets, bad = witness.pack_stark101_wits(wit_texts)
-        accept, status, _ = self.stark101_verify_batch(blob, offsets, want_status=True)
-        status = status.copy()
-        status[bad] |= 1 << 31
+        text, offsets = witness.concat_wit_texts(wit_texts)
+        _, status, _ = self.stark101_verify_wit_batch(text, offsets, want_status=True)
         return [bool(s == 0) for s in status], status
 
     # ---- element-wise jets --------------------------------------------------------------------------------

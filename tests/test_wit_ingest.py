@@ -90,7 +90,7 @@ def _variants(text):
     out.append(("hex nonce, digests without leading zeros", json.dumps(hexed), True))
     dec = dict(wit)
     dec["COMMITMENTS"] = {"value": "(" + ", ".join(str(int(x, 16)) for x in re.findall(r"0x[0-9a-f]+", wit["COMMITMENTS"]["value"])) + ")"}
-    out.append(("decimal u256 literals", json.dumps(dec), False))
+    out.append(("decimal u256 literals", json.dumps(dec), True))
     up = dict(wit)
     up["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"].upper().replace("0X", "0x")}
     out.append(("upper-case hex", json.dumps(up), False))
@@ -265,6 +265,14 @@ def test_cli_gpu_ingestion_matches_host_pack(S, tmp_path):
         r = subprocess.run([cli, "--program", "stwo", "--mode", "ref-literal", "--witness", good] + extra, capture_output=True, text=True)
         assert r.returncode == 1 and r.stdout.startswith("reject")  # the reference at HEAD rejects its own fixture
     assert outs[0] == outs[1]
+    s101 = os.path.join(GOLDEN, "stark101_proof.wit")
+    bad3 = tmp_path / "s101_bad.wit"
+    bad3.write_text(open(s101).read().replace("2133065320", "2133065321"))  # wrong last layer: well-typed, rejected by fri.simf:90
+    for extra in ([], ["--host-pack"]):
+        r = subprocess.run([cli, "--program", "stark101", "--witness", s101, str(bad3), s101, "--replicate", "11"] + extra, capture_output=True, text=True)
+        lines = r.stdout.strip().splitlines()
+        assert r.returncode == 1 and [l.split()[0] for l in lines] == ["accept", "reject", "accept"] * 11, r.stderr
+        assert all("status=0x00000100" in l for l in lines[1::3])  # SSYM_S101_ST_LAST
 
 
 @pytest.mark.gpu
@@ -296,4 +304,69 @@ def test_wit_batch_edge_cases(S):
     assert flags[0] == 0 and flags[2] == 0 and flags[1] in (1, 2)
     _, ref_flags = _host_reference(S, cfg, [text, prod, text])
     assert list(flags) == list(ref_flags)
+    ver.close()
+
+
+def _s101_variants(text):
+    wit = json.loads(text)
+    names = ["P_MT_ROOT", "P_EVALS", "FRI_LAYERS", "FRI_LAST_LAYER"]
+    out = [("generator output", text, True)]
+    out.append(("pretty-printed, reordered, no type member", json.dumps({k: {"value": wit[k]["value"]} for k in reversed(names)}, indent=1), True))
+    out.append(("spaces around tokens", json.dumps({k: {"value": " " + re.sub(r"([(\[\]),])", r" \1  ", v["value"]) + " "} for k, v in wit.items()}), True))
+    hexed = dict(wit)
+    hexed["P_MT_ROOT"] = {"value": hex(int(wit["P_MT_ROOT"]["value"]))}
+    hexed["FRI_LAST_LAYER"] = {"value": hex(int(wit["FRI_LAST_LAYER"]["value"]))}
+    out.append(("hex root and last layer", json.dumps(hexed), True))
+    single = dict(wit)
+    single["FRI_LAYERS"] = {"value": wit["FRI_LAYERS"]["value"].replace("((", "(").replace("))", ")")}
+    out.append(("FRI layers without the doubled parentheses", json.dumps(single), False))
+    fewer = dict(wit)  # one FRI layer dropped: well-typed, another shape (and a proof the verifier rejects)
+    fewer["FRI_LAYERS"] = {"value": "list![" + wit["FRI_LAYERS"]["value"][len("list!["):].split(")), ((", 1)[1].join(["((", ""])}
+    out.append(("another shape: first FRI layer dropped", json.dumps(fewer), False))
+    shorter = dict(wit)
+    shorter["P_EVALS"] = {"value": re.sub(r"list!\[\d+, ", "list![", wit["P_EVALS"]["value"], count=1)}
+    out.append(("another shape: one trace sibling dropped", json.dumps(shorter), False))
+    bad = [("garbage", "{]", 2), ("missing witness", json.dumps({k: v for k, v in wit.items() if k != "P_EVALS"}), 2),
+           ("u32 out of range", json.dumps({**wit, "FRI_LAST_LAYER": {"value": str(1 << 32)}}), 2),
+           ("u256 out of range", json.dumps({**wit, "P_MT_ROOT": {"value": str(1 << 256)}}), 2), ("empty", "", 2)]
+    return out, bad
+
+
+@pytest.mark.gpu
+def test_stark101_wit_on_gpu(S):
+    """stark101 witness texts tokenised on the GPU (ssym_stark101_verify_wit_batch) against host parser + packed verify + oracle."""
+    text = open(os.path.join(GOLDEN, "stark101_proof.wit")).read()
+    good, bad = _s101_variants(text)
+    ver = S.Verifier(0)
+    orc = O.Oracle()
+    for lead_with_odd in (False, True):  # the batch's shape comes from its first parseable witness: also lead with the other shape
+        items = good + [(l, t, False) for l, t, _ in bad]
+        if lead_with_odd:
+            items = [items[5]] + items[:5] + items[6:]
+        texts = [t for _, t, _ in items] + [text] * 40
+        blob, offsets, hostbad = S.witness.pack_stark101_wits(texts)
+        o_accept, o_status, _ = orc.s101_verify_batch(blob, offsets)
+        o_status = o_status.copy()
+        o_status[hostbad] |= 1 << 31
+        tblob, toffs = S.witness.concat_wit_texts(texts)
+        accept, status, flags = ver.stark101_verify_wit_batch(tblob, toffs, want_status=True, want_flags=True)
+        assert (status == o_status).all(), [(items[i][0] if i < len(items) else "fixture", hex(status[i]), hex(o_status[i])) for i in np.nonzero(status != o_status)[0][:6]]
+        assert list(flags) == [2 if b else 0 for b in hostbad]
+        bits = np.unpackbits(accept.view(np.uint8), bitorder="little")[: len(texts)]
+        assert (bits == (o_status == 0)).all()
+        assert status[len(items):].tolist() == [0] * 40 and (status[[i for i, it in enumerate(items) if it[0] == "generator output"]] == 0).all()
+        import torch
+
+        d_acc, d_st, d_fl = ver.stark101_verify_wit_batch(torch.from_numpy(tblob).cuda(), torch.from_numpy(toffs.astype(np.int64)).cuda(), want_status=True, want_flags=True)
+        assert (d_st.cpu().numpy().view(np.uint32) == o_status).all() and (d_acc.cpu().numpy().view(np.uint32) == accept).all()
+        acc_list, st = ver.run_stark101_wit(texts)
+        assert acc_list == [bool(x == 0) for x in o_status]
+    # which variants stay on the GPU
+    os.environ["SSYM_WIT_DEBUG_NOSLOW"] = "1"
+    try:
+        tblob, toffs = S.witness.concat_wit_texts([t for _, t, _ in good])
+        _, _, flags = ver.stark101_verify_wit_batch(tblob, toffs, want_flags=True)
+        assert [int(f) == 0 for f in flags] == [fast for _, _, fast in good], list(zip([g[0] for g in good], flags))
+    finally:
+        del os.environ["SSYM_WIT_DEBUG_NOSLOW"]
     ver.close()
