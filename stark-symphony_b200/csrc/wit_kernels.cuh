@@ -9,8 +9,7 @@
 // configuration the token sequence of every witness value is known in advance up to whitespace: the host builds that
 // "skeleton" (one byte per token: ( ) [ ] , L = `list!`  N = integer literal) plus, for the k-th integer literal, the
 // packed word it lands in and its width (u32 / u64 / u256).  The kernel checks the text against the skeleton and scatters
-// the literals.  Anything the fast path does not cover (JSON escapes, `_` digit separators, upper-case hex, decimal literals
-// above 64 bits, redundant parentheses, trailing commas, a list of another length, any malformed text) sets the witness's
+// the literals.  Anything the fast path does not cover (JSON escapes, `_` digit separators, upper-case hex, redundant parentheses, trailing commas, a list of another length, any malformed text) sets the witness's
 // flag to WIT_SLOW and the host re-parses exactly that witness with the full grammar (csrc/witness.cpp), so the result is
 // always the one ssym_stwo_pack_wit gives.
 #pragma once
