@@ -154,6 +154,31 @@ def main():
                            "oracle_1_thread_proofs_per_s": 1 / cpu_per}
     print(f"stark101 x{n}: {ms:8.3f} ms  {n / ms / 1e3:8.2f} M proofs/s  (oracle, 1 thread: {1 / cpu_per:8.0f} proofs/s)", flush=True)
     del d_blob, d_off
+    # the same batch as `.wit` TEXT (the file `make run` hands to simfony), tokenised on the GPU: device resident and from pinned host memory
+    raw = open(os.path.join(golden, "stark101_proof.wit"), "rb").read()
+    t_pinned = torch.empty(len(raw) * n, dtype=torch.uint8).pin_memory()
+    t_np = t_pinned.numpy()
+    t_np.reshape(n, len(raw))[:] = np.frombuffer(raw, dtype=np.uint8)
+    t_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(len(raw))
+    d_text, d_toff = t_pinned.cuda(), torch.from_numpy(t_off.view(np.int64)).cuda()
+    best_dev, best_host = 1e30, 1e30
+    for rep in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        acc_t, _, _ = ver.stark101_verify_wit_batch(d_text, d_toff)
+        torch.cuda.synchronize()
+        if rep:
+            best_dev = min(best_dev, time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        acc_h, _, _ = ver.stark101_verify_wit_batch(t_np, t_off)
+        if rep:
+            best_host = min(best_host, time.perf_counter() - t0)
+    assert (np.unpackbits(acc_h.view(np.uint8), bitorder="little")[:n] == 1).all() and bool((acc_t == -1).all().item())
+    results["stark101"]["from_wit_text"] = {"text_bytes_per_proof": len(raw), "device_resident_proofs_per_s": n / best_dev, "host_pinned_proofs_per_s": n / best_host,
+                                            "host_text_gb_per_s": n * len(raw) / best_host / 1e9,
+                                            "note": "ssym_stark101_verify_wit_batch, synchronous call, wall clock (one H2D of the whole text, no chunk overlap)"}
+    print(f"stark101 x{n} from .wit text: {n / best_dev / 1e6:.2f} M proofs/s device resident, {n / best_host / 1e6:.2f} M proofs/s from pinned host text", flush=True)
+    del d_text, d_toff, t_pinned
 
     # ---- Stwo at larger batches -------------------------------------------------------------------------------
     cfg = S.stwo_config("prod", S.MODE_REF_LITERAL)

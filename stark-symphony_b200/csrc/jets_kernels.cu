@@ -39,11 +39,114 @@ __global__ void __launch_bounds__(256) m31_binary_kernel(const uint32_t *a, cons
     }
     for (size_t i = nv * 4 + tid; i < n; i += stride) out[i] = m31_op<OP>(a[i], OP == JET_M31_NEG ? 0u : b[i]);
 }
+// Inverses K at a time (Montgomery's trick): the prefix products of the K residues, ONE addition-chain inversion (fields/m31.simf:117-132) of
+// their product, and a back-substitution — 3 (K - 1) + 37 products instead of 37 K.  The inverse of a non-zero residue is unique, so every
+// output is the canonical value the per-element chain gives; a zero residue is taken out of the product and gets the chain's 0.
+// On entry v[k] = canonical residues; on return their inverses (0 for 0).
+template <int K>
+__device__ __forceinline__ void m31_batch_inv(uint32_t (&v)[K]) {
+    uint32_t pfx[K], nz[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        nz[k] = v[k] ? v[k] : 1u;
+        pfx[k] = k ? m31_mul_c(pfx[k - 1], nz[k]) : nz[0];
+    }
+    bool dummy = false;
+    uint32_t inv = m31_inv(pfx[K - 1], dummy); // product of non-zero residues: never zero
+#pragma unroll
+    for (int k = K - 1; k >= 1; k--) {
+        const uint32_t mine = m31_mul_c(inv, pfx[k - 1]);
+        inv = m31_mul_c(inv, nz[k]);
+        v[k] = v[k] ? mine : 0u;
+    }
+    v[0] = v[0] ? inv : 0u;
+}
+
 __global__ void __launch_bounds__(256) m31_inv_kernel(const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    constexpr int K = 16;
+    const size_t nv = n / K, stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(a);
+    uint4 *o4 = reinterpret_cast<uint4 *>(out);
+    const bool fail_vec = (reinterpret_cast<uintptr_t>(fail) & 15u) == 0;
+    for (size_t i = tid; i < nv; i += stride) {
+        uint32_t raw[K], v[K];
+#pragma unroll
+        for (int j = 0; j < K / 4; j++) {
+            const uint4 x = __ldg(a4 + (K / 4) * i + j);
+            raw[4 * j] = x.x; raw[4 * j + 1] = x.y; raw[4 * j + 2] = x.z; raw[4 * j + 3] = x.w;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) v[k] = m31_reduce(raw[k]);
+        m31_batch_inv<K>(v);
+#pragma unroll
+        for (int j = 0; j < K / 4; j++) o4[(K / 4) * i + j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (fail) { // assert!(false) of m31.simf:118-122: the input is bitwise 0
+            uint32_t f[K / 4];
+#pragma unroll
+            for (int j = 0; j < K / 4; j++) {
+                f[j] = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) f[j] |= (raw[4 * j + k] == 0 ? 1u : 0u) << (8 * k);
+            }
+            if (fail_vec) reinterpret_cast<uint4 *>(fail)[i] = make_uint4(f[0], f[1], f[2], f[3]);
+            else
+                for (int k = 0; k < K; k++) fail[K * i + k] = raw[k] == 0;
+        }
+    }
+    for (size_t i = nv * K + tid; i < n; i += stride) {
         bool f = false;
         out[i] = m31_inv(a[i], f);
+        if (fail) fail[i] = f;
+    }
+}
+
+// cm31_inv (cm31.simf:88-93) / qm31_inv (qm31.simf:87-98) K elements per thread: both end in ONE m31 inversion of a norm, batched as above.
+template <bool QM>
+__global__ void __launch_bounds__(256) ext_inv_kernel(const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n) {
+    constexpr int K = 8;
+    const size_t nv = n / K, stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = tid; i < nv; i += stride) {
+        QM31 x[K];
+        CM31 den[K];
+        uint32_t norm[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (QM) {
+                x[k] = qm31_load4(a + 4 * (K * i + k));
+                const CM31 ar_sq = cm31_mul(x[k].r, x[k].r), ai_sq = cm31_mul(x[k].i, x[k].i);
+                den[k] = cm31_add(ar_sq, cm31_neg(cm31_add(cm31_add(ai_sq, ai_sq), cm31(m31_neg(ai_sq.b), ai_sq.a))));
+            } else {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a) + K * i + k);
+                den[k] = cm31(v.x, v.y);
+            }
+            norm[k] = m31_add(m31_pow2(den[k].a), m31_pow2(den[k].b)); // canonical
+        }
+        uint32_t ninv[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) ninv[k] = norm[k];
+        m31_batch_inv<K>(ninv);
+        uint64_t fbits = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const CM31 dinv = cm31_mul_m31(cm31_conj(den[k]), ninv[k]);
+            fbits |= (uint64_t)(norm[k] == 0 ? 1u : 0u) << (8 * k);
+            if (QM) qm31_store4(out + 4 * (K * i + k), qm31c(cm31_mul(x[k].r, dinv), cm31_mul(cm31_neg(x[k].i), dinv)));
+            else reinterpret_cast<uint2 *>(out)[K * i + k] = make_uint2(dinv.a, dinv.b);
+        }
+        if (fail) {
+            if ((reinterpret_cast<uintptr_t>(fail) & 7u) == 0) reinterpret_cast<uint64_t *>(fail)[i] = fbits;
+            else
+                for (int k = 0; k < K; k++) fail[K * i + k] = (uint8_t)(fbits >> (8 * k));
+        }
+    }
+    for (size_t i = nv * K + tid; i < n; i += stride) {
+        bool f = false;
+        if (QM) qm31_store4(out + 4 * i, qm31_inv(qm31_load4(a + 4 * i), f));
+        else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a) + i);
+            const CM31 r = cm31_inv(cm31(v.x, v.y), f);
+            reinterpret_cast<uint2 *>(out)[i] = make_uint2(r.a, r.b);
+        }
         if (fail) fail[i] = f;
     }
 }
@@ -89,13 +192,13 @@ int launch_field_jet(int op, const uint32_t *a, const uint32_t *b, uint32_t *out
     case JET_M31_SUB: m31_binary_kernel<JET_M31_SUB><<<g4, 256, 0, s>>>(a, b, out, n); break;
     case JET_M31_MUL: m31_binary_kernel<JET_M31_MUL><<<g4, 256, 0, s>>>(a, b, out, n); break;
     case JET_M31_NEG: m31_binary_kernel<JET_M31_NEG><<<g4, 256, 0, s>>>(a, a, out, n); break;
-    case JET_M31_INV: m31_inv_kernel<<<g1, 256, 0, s>>>(a, out, fail, n); break;
+    case JET_M31_INV: m31_inv_kernel<<<stream_grid((n + 15) / 16, 256), 256, 0, s>>>(a, out, fail, n); break;
     case JET_CM31_MUL: ext_kernel<JET_CM31_MUL><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
-    case JET_CM31_INV: ext_kernel<JET_CM31_INV><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_CM31_INV: ext_inv_kernel<false><<<stream_grid((n + 7) / 8, 256), 256, 0, s>>>(a, out, fail, n); break;
     case JET_QM31_ADD: ext_kernel<JET_QM31_ADD><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
     case JET_QM31_SUB: ext_kernel<JET_QM31_SUB><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
     case JET_QM31_MUL: ext_kernel<JET_QM31_MUL><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
-    case JET_QM31_INV: ext_kernel<JET_QM31_INV><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
+    case JET_QM31_INV: ext_inv_kernel<true><<<stream_grid((n + 7) / 8, 256), 256, 0, s>>>(a, out, fail, n); break;
     case JET_QM31_MUL_M31: ext_kernel<JET_QM31_MUL_M31><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
     case JET_QM31_MUL_CM31: ext_kernel<JET_QM31_MUL_CM31><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
     default: return -1;
