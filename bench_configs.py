@@ -49,6 +49,7 @@ def apply_negatives(torch, proofs, plan, first_index):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, required=True, choices=[3, 5])
+    ap.add_argument("--gpus", type=int, default=None, help="informational (the world size comes from torchrun), accepted for symmetry with bench.py")
     ap.add_argument("--log-n", type=int, default=None)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
