@@ -56,6 +56,10 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # libraries (NCCL's version banner) write to fd 1: keep stdout for the single JSON line, as bench.py does
+    sys.stdout.flush()
+    B._REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
