@@ -143,3 +143,37 @@ def test_config3_full_size_properties(S, ver):
     sample = proofs[:32].cpu().numpy().view(np.uint32)
     _, o_status, _ = orc.stwo_verify_batch(oc, sample.ravel(), 32)
     assert (o_status == st[:32]).all()
+
+
+@pytest.mark.parametrize("T,G,Q", [(5, 7, 8), (4, 9, 16), (6, 8, 3), (2, 4, 5)])
+def test_other_configurations_end_to_end(S, ver, orc, T, G, Q):
+    """Configurations config.simf has no preset for (other trace / LDE sizes, query counts that are not powers of two): GPU prover == CPU
+    reference prover, GPU verifier == oracle on honest and corrupted proofs with full traces (shared-node Merkle schedule included), and
+    proof -> `.wit` text -> GPU tokeniser == the packed proof."""
+    import json
+
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers = T, G, Q, T - 1
+    lo = S.stwo_layout(cfg)
+    seeds = np.arange(300, 340, dtype=np.uint64)
+    gpu = ver.stwo_prove_batch(seeds, cfg)
+    ref = orc.stwo_prove_batch(ocfg(cfg), seeds, threads=8)
+    assert (gpu == ref).all()
+    rng = np.random.default_rng(T * 100 + G)
+    batch = gpu.copy()
+    for k in range(8, 40):  # one random word corrupted in every proof from the 9th on
+        batch[k, rng.integers(0, lo.stride_words)] ^= np.uint32(1 << rng.integers(0, 32))
+    for mode in (S.MODE_PROVER_CONSISTENT, S.MODE_REF_LITERAL):
+        cfg.mode = mode
+        accept, status, traces = ver.stwo_verify_batch(batch.ravel(), cfg, len(seeds), want_status=True, want_trace=True)
+        o_accept, o_status, o_traces = orc.stwo_verify_batch(ocfg(cfg), batch.ravel(), len(seeds), want_trace=True)
+        assert (status == o_status).all() and (accept == o_accept).all()
+        for i in range(len(seeds)):
+            assert bytes(memoryview(traces[i]).cast("B")) == bytes(memoryview(o_traces[i]).cast("B")), (mode, i)
+        if mode == S.MODE_PROVER_CONSISTENT:
+            assert (status[:8] == 0).all()
+    cfg.mode = S.MODE_PROVER_CONSISTENT
+    texts = [json.dumps(S.witness.stwo_wit_from_packed(gpu[i], cfg)) for i in range(6)]
+    blob, offsets = S.witness.concat_wit_texts(texts)
+    packed, flags = ver.stwo_pack_wit_batch(blob, offsets, cfg)
+    assert (flags == 0).all() and (packed == gpu[:6]).all()
