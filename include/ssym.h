@@ -216,6 +216,13 @@ int ssym_set_pipeline_depth(ssym_ctx_t *ctx, int depth);
  * then overlap (the H2D of call k+1 runs under the kernel tail of call k), and every output is valid after ssym_synchronize.
  * The caller's buffers must be pinned (cudaHostAlloc / torch pin_memory) and must not be touched until then. */
 int ssym_set_host_async(ssym_ctx_t *ctx, int on);
+/* Merkle schedule of ssym_stwo_verify_batch.  The reference hashes every query's path to the root on its own (merkle.simf:39-44); paths of
+ * one tree that have met run through the same nodes from there on.  policy 0: one hash chain per query, as the reference; 2: every distinct
+ * node is hashed once and a query takes over another's nodes only after a bitwise comparison of everything its own computation would have
+ * read (per-query roots, fail masks and verdicts are identical by construction; csrc/stwo_kernels.cuh StwoDedup); 1 (default): policy 2
+ * under SSYM_MODE_PROVER_CONSISTENT, policy 0 under SSYM_MODE_REF_LITERAL, where no FRI path can share (finding F1) and planning does not
+ * pay.  The default can also be set with the environment variable SSYM_MERKLE_DEDUP. */
+int ssym_set_merkle_sharing(ssym_ctx_t *ctx, int policy);
 int ssym_join(ssym_ctx_t *ctx);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t ssym_launch_count(const ssym_ctx_t *ctx);

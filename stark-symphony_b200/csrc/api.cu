@@ -100,6 +100,8 @@ struct ssym_ctx {
         DevBuf dd_plan, dd_to, dd_own, dd_ckpt, dd_bins, dd_list; // shared-node Merkle schedule (StwoDedup)
         bool pending = false;
     };
+    // Merkle schedule (ssym_set_merkle_sharing): 0 per-query kernel, 1 shared nodes where it pays (PROVER_CONSISTENT), 2 shared nodes always
+    int merkle_sharing = [] { const char *e = getenv("SSYM_MERKLE_DEDUP"); return e ? atoi(e) : 1; }();
     static const int MAX_DEPTH = 8;
     Lane lanes[MAX_DEPTH];
     int depth = 1;
@@ -356,7 +358,8 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
         p.trace = d_trace ? d_trace + done : nullptr;
         p.n = (uint32_t)m;
         memset(&p.dd, 0, sizeof p.dd);
-        if (const size_t list_entries = stwo_dedup_layout(cfg, m, p.dd)) {
+        const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && cfg.mode == SSYM_MODE_PROVER_CONSISTENT);
+        if (const size_t list_entries = share ? stwo_dedup_layout(cfg, m, p.dd) : 0) {
             const size_t chains = (size_t)p.dd.chains * m;
             CUDA_TRY(lane.dd_plan.ensure(chains * sizeof(uint32_t)));
             CUDA_TRY(lane.dd_to.ensure(chains * sizeof(uint64_t)));
@@ -445,6 +448,14 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    return SSYM_OK;
+}
+
+extern "C" int ssym_set_merkle_sharing(ssym_ctx_t *c, int policy) {
+    if (!c || policy < 0 || policy > 2) return fail(SSYM_ERR_USAGE, "merkle sharing policy must be 0, 1 or 2");
+    int rc = ssym_synchronize(c);
+    if (rc) return rc;
+    c->merkle_sharing = policy;
     return SSYM_OK;
 }
 

@@ -890,10 +890,7 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     if (prof) { prof->end(0, s); prof->begin(1, s); }
     const uint32_t items = p.n * Q;
     stwo_query_kernel<<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p);
-    // SSYM_MERKLE_DEDUP: 0 = always the per-query Merkle kernel, 1 (default) = the shared-node schedule where it pays: PROVER_CONSISTENT (measured
-    // +17 % on accepted proofs; under REF_LITERAL no FRI path can share, the trace / composition trees alone do not cover the planning), 2 = always
-    static const int dedup = [] { const char *e = getenv("SSYM_MERKLE_DEDUP"); return e ? atoi(e) : 1; }();
-    if (p.dd.enabled && (dedup == 2 || (dedup == 1 && p.cfg.mode == SSYM_MODE_PROVER_CONSISTENT))) {
+    if (p.dd.enabled) { // decided by the caller (ssym_set_merkle_sharing)
         // shared-node schedule: plan (on the front stream with K1 / K2 when pipelined), hash the distinct nodes, check the followers, hash
         // what did not match, resolve every query
         stwo_plan_kernel<<<(p.n * (L + 2) * 16 + 511) / 512, 512, 0, s2>>>(p);

@@ -83,6 +83,11 @@ class Verifier:
         after synchronize().  Buffers must be pinned."""
         check(self.lib.ssym_set_host_async(self.h, 1 if on else 0))
 
+    def set_merkle_sharing(self, policy: int) -> None:
+        """0: one hash chain per query (the reference's schedule); 2: paths of a tree share the nodes above their meeting point; 1 (default):
+        2 under MODE_PROVER_CONSISTENT, 0 under MODE_REF_LITERAL (ssym_set_merkle_sharing, include/ssym.h)."""
+        check(self.lib.ssym_set_merkle_sharing(self.h, int(policy)))
+
     def join(self) -> None:
         """Order all in-flight batches into the handle's stream (device-side wait only)."""
         check(self.lib.ssym_join(self.h))

@@ -135,6 +135,25 @@ def test_stwo_shared_node_schedule_matches_oracle(S, ver, orc):
         assert trace_bytes(traces[i]) == trace_bytes(o_traces[i]), (i, diff_traces(traces[i], o_traces[i], S.StwoTrace))
 
 
+@pytest.mark.parametrize("policy", [0, 2])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_stwo_both_merkle_schedules_in_both_modes(S, orc, policy, mode):
+    """ssym_set_merkle_sharing: the per-query kernel and the shared-node schedule, each under both semantics (the default policy picks one per
+    mode), give the oracle's traces on the fixture, its negatives and random corruptions."""
+    v = S.Verifier(0)
+    v.set_merkle_sharing(policy)
+    cfg, packed = golden_stwo(S, "prod", mode)
+    batch, n, names = negatives_batch(S, cfg, packed, extra_random=120, seed=7 + policy)
+    accept, status, traces = v.stwo_verify_batch(batch, cfg, n, want_status=True, want_trace=True)
+    o_accept, o_status, o_traces = orc.stwo_verify_batch(ocfg(cfg), batch, n, want_trace=True)
+    assert (status == o_status).all() and (accept == o_accept).all()
+    for i in range(n):
+        assert trace_bytes(traces[i]) == trace_bytes(o_traces[i]), (i, diff_traces(traces[i], o_traces[i], S.StwoTrace))
+    with pytest.raises(S.SsymError):
+        v.set_merkle_sharing(3)
+    v.close()
+
+
 def test_stwo_device_resident_and_large_batch(S, ver, orc):
     """BASELINE config 2 shape: proof.json replicated x1024 (+ negatives sprinkled in), inputs resident in HBM."""
     import torch
