@@ -203,6 +203,10 @@ const char *ssym_version(void);
 /* Use a caller-owned stream (e.g. torch's current stream) for all subsequent
  * device-resident calls on this handle; NULL restores the handle's own stream. */
 int ssym_set_stream(ssym_ctx_t *ctx, void *cuda_stream);
+/* Page-locked host memory for SSYM_MEM_HOST buffers (packed proofs, witness text): copies from it run at the link rate and, in the
+ * asynchronous host mode, truly overlap.  Plain malloc'ed buffers are accepted everywhere too, only slower.  Returns NULL on failure. */
+void *ssym_pinned_alloc(size_t bytes);
+void ssym_pinned_free(void *ptr);
 int ssym_synchronize(ssym_ctx_t *ctx);
 /* Pipeline depth D (1..8, default 1) for device-resident ssym_stwo_verify_batch calls: call k runs on internal
  * stream k % D (forked from the handle's stream at call time), so up to D consecutive batches are in flight and the

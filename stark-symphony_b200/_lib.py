@@ -74,6 +74,8 @@ SYMBOLS = {
     "ssym_last_error": (C.c_char_p, []),
     "ssym_version": (C.c_char_p, []),
     "ssym_set_stream": (_I, [_V, _V]),
+    "ssym_pinned_alloc": (_V, [_SZ]),
+    "ssym_pinned_free": (None, [_V]),
     "ssym_synchronize": (_I, [_V]),
     "ssym_set_pipeline_depth": (_I, [_V, _I]),
     "ssym_join": (_I, [_V]),

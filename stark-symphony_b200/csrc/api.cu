@@ -215,6 +215,15 @@ void ssym_destroy(ssym_ctx_t *c) {
     delete c;
 }
 
+void *ssym_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { g_last_error = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+void ssym_pinned_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 int ssym_set_stream(ssym_ctx_t *c, void *cuda_stream) {
     if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
     c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;

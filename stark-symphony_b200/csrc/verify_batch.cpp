@@ -14,6 +14,7 @@
 // Witnesses are tokenised and packed ON THE GPU (ssym_stwo_verify_wit_batch / ssym_stark101_verify_wit_batch: the `.wit` text is what crosses
 // PCIe); --host-pack (and --trace, which needs the packed records on the host) uses the host parser + the packed-batch entry points instead.
 #include <dirent.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <chrono>
@@ -111,22 +112,30 @@ int main(int argc, char **argv) {
     std::vector<ssym_stwo_trace_t> traces;
     std::vector<ssym_s101_trace_t> traces101;
     const bool gpu_ingest = !want_trace && !host_pack;
-    std::string wit_text;               // stwo, GPU ingestion: the concatenated witness texts
+    char *wit_text = nullptr;           // GPU ingestion: the concatenated witness texts, read straight into page-locked memory
     std::vector<uint64_t> wit_offsets;
     std::vector<uint32_t> wit_flags;
     if (gpu_ingest) {
         if (program == "stwo" && (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || ssym_stwo_layout(&cfg, &lo))) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
         wit_offsets.push_back(0);
         for (size_t f = 0; f < n_files; f++) {
-            std::string text;
-            if (!read_file(witnesses[f], text)) { fprintf(stderr, "Error: Failed to read witness file: %s\n", witnesses[f].c_str()); return 1; }
-            wit_text += text;
-            wit_offsets.push_back(wit_text.size());
+            struct stat st;
+            if (stat(witnesses[f].c_str(), &st) != 0 || !S_ISREG(st.st_mode)) { fprintf(stderr, "Error: Failed to read witness file: %s\n", witnesses[f].c_str()); return 1; }
+            wit_offsets.push_back(wit_offsets.back() + (uint64_t)st.st_size);
         }
-        const size_t one = wit_text.size();
-        wit_text.reserve(one * replicate);
+        const size_t one = wit_offsets.back();
+        wit_text = static_cast<char *>(ssym_pinned_alloc(one * replicate + 16));
+        bool pinned = wit_text != nullptr;
+        if (!pinned) wit_text = static_cast<char *>(malloc(one * replicate + 16)); // no GPU / no pinned memory: ssym_create reports it below
+        if (!wit_text) { fprintf(stderr, "Error: out of memory\n"); return 1; }
+        for (size_t f = 0; f < n_files; f++) {
+            FILE *fp = fopen(witnesses[f].c_str(), "rb");
+            const size_t want = (size_t)(wit_offsets[f + 1] - wit_offsets[f]);
+            if (!fp || fread(wit_text + wit_offsets[f], 1, want, fp) != want) { fprintf(stderr, "Error: Failed to read witness file: %s\n", witnesses[f].c_str()); return 1; }
+            fclose(fp);
+        }
         for (size_t r = 1; r < replicate; r++) {
-            wit_text.append(wit_text, 0, one);
+            memcpy(wit_text + r * one, wit_text, one);
             for (size_t f = 0; f < n_files; f++) wit_offsets.push_back(r * one + wit_offsets[f + 1]);
         }
         wit_flags.assign(n, 0);
@@ -185,9 +194,9 @@ int main(int argc, char **argv) {
                     std::vector<uint64_t> offs(wit_offsets.begin() + b, wit_offsets.begin() + e + 1);
                     const uint64_t base = offs[0];
                     for (auto &o : offs) o -= base;
-                    rc = program == "stwo" ? ssym_stwo_verify_wit_batch(ctx, &cfg, wit_text.data() + base, offs.data(), e - b, accept.data() + b / 32,
+                    rc = program == "stwo" ? ssym_stwo_verify_wit_batch(ctx, &cfg, wit_text + base, offs.data(), e - b, accept.data() + b / 32,
                                                                         status.data() + b, wit_flags.data() + b, SSYM_MEM_HOST)
-                                           : ssym_stark101_verify_wit_batch(ctx, wit_text.data() + base, offs.data(), e - b, accept.data() + b / 32,
+                                           : ssym_stark101_verify_wit_batch(ctx, wit_text + base, offs.data(), e - b, accept.data() + b / 32,
                                                                             status.data() + b, wit_flags.data() + b, SSYM_MEM_HOST);
                 } else if (program == "stwo")
                     rc = ssym_stwo_verify_batch(ctx, &cfg, packed.data() + b * (size_t)lo.stride_words, e - b, accept.data() + b / 32, status.data() + b,
