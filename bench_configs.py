@@ -202,7 +202,7 @@ def main():
             dt, done = B.oracle_run(orc, ocfg, flat, sample_n, threads, total)
             line["cpu_baseline"] = {"value": done / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
                                     "sample": f"{done} proofs (cycling the first {sample_n} proofs of the batch) on {threads} threads, {dt:.2f} s wall; oracle/ssym_oracle.c"}
-        print(json.dumps(line), flush=True)
+        B.emit(line)
         if args.out:
             with open(args.out, "w") as f:
                 json.dump(line, f)

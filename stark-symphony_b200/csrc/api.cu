@@ -404,18 +404,27 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     rc = ensure_tables(c, *cfg);
     if (rc) return rc;
     if (memspace == SSYM_MEM_DEVICE) {
-        if (c->depth == 1) return stwo_launch_chunk(c, c->lanes[0], *cfg, lo, packed, n, accept_bits, status, trace, c->stream);
-        // pipelined: fork from the handle's stream into lane k % depth; joined by ssym_join / ssym_synchronize
-        ssym_ctx::Lane &lane = c->lanes[c->calls++ % c->depth];
-        CUDA_TRY(cudaEventRecord(lane.in, c->stream));
-        CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.in, 0));
-        CUDA_TRY(cudaStreamWaitEvent(lane.front, lane.in, 0));
-        if (lane.pending) CUDA_TRY(cudaStreamWaitEvent(lane.front, lane.done, 0)); // the lane's scratch is still in use by its previous batch
-        rc = stwo_launch_chunk(c, lane, *cfg, lo, packed, n, accept_bits, status, trace, lane.s, true);
-        if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(lane.done, lane.s));
-        lane.pending = true;
-        return SSYM_OK;
+        const bool multi = n > STWO_DEVICE_CHUNK;
+        if ((c->depth == 1 && !multi) || c->profiling) return stwo_launch_chunk(c, c->lanes[0], *cfg, lo, packed, n, accept_bits, status, trace, c->stream);
+        // Pipelined: every chunk of at most STWO_DEVICE_CHUNK proofs forks from the handle's stream into the next lane (own stream, own scratch, the
+        // latency-bound kernels on the lane's high-priority stream), so the channel kernel of one chunk hides behind the Merkle kernels of the
+        // previous one.  depth > 1: consecutive CALLS overlap too and the caller joins (ssym_join / ssym_synchronize).  depth == 1: only the
+        // chunks of this one large call overlap, and they are ordered back into the handle's stream before the call returns.
+        const int D = std::max(c->depth, multi ? 4 : 1);
+        for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
+            const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
+            ssym_ctx::Lane &lane = c->lanes[c->calls++ % D];
+            CUDA_TRY(cudaEventRecord(lane.in, c->stream));
+            CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.in, 0));
+            CUDA_TRY(cudaStreamWaitEvent(lane.front, lane.in, 0));
+            if (lane.pending) CUDA_TRY(cudaStreamWaitEvent(lane.front, lane.done, 0)); // the lane's scratch is still in use by its previous batch
+            rc = stwo_launch_chunk(c, lane, *cfg, lo, packed + done * (size_t)lo.stride_words, m, accept_bits + done / 32, status ? status + done : nullptr,
+                                   trace ? trace + done : nullptr, lane.s, true);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(lane.done, lane.s));
+            lane.pending = true;
+        }
+        return c->depth == 1 ? ssym_join(c) : SSYM_OK;
     }
     if (memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
 
