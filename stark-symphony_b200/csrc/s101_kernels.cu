@@ -212,7 +212,8 @@ __device__ __forceinline__ void s101_load_digest(const uint32_t *src, uint32_t (
 
 // Path slots: 0..2 = trace decommitments of f(x), f(gx), f(g^2 x) (air.simf:39-56); 3 + 2l, 4 + 2l = cpa / cpb of
 // FRI layer l (fri.simf:78-80).  merkle_verify_32 here has no `path == 1` assert (stark101/src/merkle.simf:39-43).
-__global__ void __launch_bounds__(128) s101_merkle_kernel(S101Params p, uint32_t groups) {
+__global__ void __launch_bounds__(128, 8) s101_merkle_kernel(S101Params p, uint32_t groups, ShaMul mul) {
+    const ShaAdd<1> A(mul); // adds on the FMA pipe, rounds rolled 4 x 16, ONE hashing loop: the core of stwo_merkle_kernel (sha256.cuh)
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t slot = warp / groups, group = warp % groups;
     const uint32_t i = group * 32 + lane;
@@ -248,23 +249,32 @@ __global__ void __launch_bounds__(128) s101_merkle_kernel(S101Params p, uint32_t
         fail_bit = is_b ? SSYM_S101_ST_LAYER_MERKLE_B : SSYM_S101_ST_LAYER_MERKLE_A;
         mask_bit = is_b ? 4u : 2u;
     }
-    uint32_t cur[8];
-    {
-        const uint32_t m[1] = {value};
-        sha256_short<1>(m, cur); // sha256_32
-    }
-#pragma unroll 1
-    for (uint32_t lvl = 0; lvl < n_sib; lvl++) {
-        uint32_t s[8], w[16];
-        s101_load_digest(sib + 8 * lvl, s);
-        const bool cur_left = (path & 1u) == 0;
+    uint32_t cur[8], nxt[8]; // nxt: the next sibling, loaded one level ahead
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            w[k] = cur_left ? cur[k] : s[k];
-            w[8 + k] = cur_left ? s[k] : cur[k];
+    for (int k = 0; k < 8; k++) cur[k] = nxt[k] = 0;
+#pragma unroll 1
+    for (uint32_t step = 0; step <= n_sib; step++) {
+        uint32_t w[16];
+        if (step == 0) { // sha256_32(value): the leaf (merkle.simf:39, sha256.simf:17-21)
+            w[0] = value;
+            w[1] = 0x80000000u;
+#pragma unroll
+            for (int k = 2; k < 15; k++) w[k] = 0;
+            w[15] = 32u;
+            if (n_sib) s101_load_digest(sib, nxt);
+        } else {
+            const bool cur_left = (path & 1u) == 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                w[k] = cur_left ? cur[k] : nxt[k];
+                w[8 + k] = cur_left ? nxt[k] : cur[k];
+            }
+            if (step < n_sib) s101_load_digest(sib + 8 * step, nxt);
+            path >>= 1;
         }
-        sha256_64B(w, cur);
-        path >>= 1;
+        sha_iv(cur);
+        sha_compress_rolled<1>(cur, w, A);
+        if (step) sha_compress_pad64_rolled<1>(cur, A);
     }
     bool ok = true;
 #pragma unroll
@@ -304,7 +314,7 @@ void launch_s101_verify(const S101Params &p, uint32_t *accept_bits, cudaStream_t
     const uint32_t groups = (p.n + 31) / 32;
     const uint32_t slots = 3 + 2 * p.max_layers;
     const uint64_t warps = (uint64_t)groups * slots;
-    s101_merkle_kernel<<<(uint32_t)((warps + 3) / 4), 128, 0, s>>>(p, groups);
+    s101_merkle_kernel<<<(uint32_t)((warps + 3) / 4), 128, 0, s>>>(p, groups, sha_mul_consts());
     if (prof) { prof->end(5, s); prof->begin(6, s); }
     s101_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
     if (prof) prof->end(6, s);
