@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
 #define DD_FOLLOWER 0x80u
 #define DD_INVALID 0x40u
 #define DD_SIBDIFF 0x20u
+#define DD_SAMELEAF 0x1000u // follower whose leaf position IS its leader's (h = 0): nothing to hash in round 1
 
 // Appends chain `c` to bin `bin` of round `round`: counters privatised in shared memory, one global atomic per (CTA, bin).
 // Every thread of the CTA calls this (want = false for threads with nothing to append; up to two appends per thread).
@@ -525,7 +526,11 @@ __global__ void __launch_bounds__(512) stwo_plan_kernel(StwoParams p) {
         const uint32_t hr = __shfl_sync(gmask, h, r, 16), lr = __shfl_sync(gmask, follower ? lead : DD_NONE, r, 16);
         if (act && lr == q && hr >= 1) { mask |= 1u << (hr - 1); to |= (uint64_t)r << (4 * (hr - 1)); }
     }
-    const uint32_t word = h | (follower ? DD_FOLLOWER : 0u) | ((lead & 15u) << 8) | (mask << 16);
+    // A follower stops one level BELOW the meeting node (lv = h - 1 levels): there its node must be the leader's sibling and its sibling the
+    // leader's node, which makes the meeting node — and everything above it — the leader's.  Checkpoint bit / nibble k = the leader's node at height k.
+    const bool same_leaf = follower && h == 0;
+    const uint32_t lv = follower ? (h ? h - 1 : 0u) : h;
+    const uint32_t word = lv | (follower ? DD_FOLLOWER : 0u) | (same_leaf ? DD_SAMELEAF : 0u) | ((lead & 15u) << 8) | (mask << 16);
     const uint32_t CH = p.dd.chains;
     uint32_t bin[2] = {0, 0}, chain[2] = {0, 0}, n_app = 0;
     if (act) {
@@ -535,16 +540,15 @@ __global__ void __launch_bounds__(512) stwo_plan_kernel(StwoParams p) {
             const uint32_t c = i * CH + tree * Q + q;
             p.dd.plan[c] = word;
             p.dd.ckpt_to[c] = to;
-            const uint32_t b = p.dd.bin_of[0][kind][h];
-            if (b != DD_NONE) { bin[n_app] = b; chain[n_app] = c; n_app++; }
+            if (!same_leaf) { bin[n_app] = p.dd.bin_of[0][kind][lv]; chain[n_app] = c; n_app++; }
         }
     }
     dd_append<2>(p.dd, 0, bin, chain, n_app, s_cnt, s_base);
 }
 
 // One thread per task, a warp = 32 tasks of one bin = one (kind, number of steps): no divergence; bins are ordered longest first.
-// Round 1: chain c from its leaf up to its meeting height h (plan), storing the nodes its followers need.  Round 2: the followers whose
-// check failed, from their node at height h (or, for h = 0, from their leaf) to the root with their own siblings.
+// Round 1: chain c from its leaf up lv levels (plan: a follower stops one level below its meeting node), storing the nodes its followers need.
+// Round 2: the followers whose check failed, from their node at height lv (same-leaf followers: from their leaf) to the root with their own siblings.
 template <int ADDMODE>
 __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kernel(StwoParams p, uint32_t round, ShaMul mul) {
     const ShaAdd<ADDMODE> A(mul);
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
     const uint32_t cg = p.dd.bin_list[p.dd.bin_base[round][bin] + off];
     const uint32_t i = cg / CH, c = cg % CH, tree = c / Q, q = c % Q;
     const uint32_t pw = p.dd.plan[cg];
-    const uint32_t h = pw & 31u, ckmask = round == 0 ? pw >> 16 : 0u;
+    const uint32_t lv = pw & 31u, ckmask = round == 0 ? pw >> 16 : 0u;
     const uint64_t ckto = round == 0 ? p.dd.ckpt_to[cg] : 0ull;
     const ssym_stwo_layout_t &lo = p.lo;
     const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
@@ -596,13 +600,15 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
         path = fq >> 1;
     }
     const uint32_t *evp = p.fri_evals + ((size_t)i * (L + 1) * Q + layer * Q + q) * 4;
-    const uint32_t start = round == 0 ? 0u : h, end = round == 0 ? h : depth; // levels [start, end)
-    if (start) n_pre = 0;
+    // levels [start, end): round 1 = [0, lv); round 2 = from the stored node at height lv (or, for a same-leaf follower, from the leaf) to the root
+    const bool from_node = round != 0 && !(pw & DD_SAMELEAF);
+    const uint32_t start = from_node ? lv : 0u, end = round == 0 ? lv : depth;
+    if (from_node) n_pre = 0;
 
     uint32_t cur[8], nxt[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) cur[k] = nxt[k] = 0;
-    if (start) {
+    if (from_node) {
         load_digest(p.dd.own + (size_t)cg * 8, cur);
         load_digest(sib + 8 * start, nxt);
         path >>= start;
@@ -639,8 +645,8 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
             if (step + 1 == n_pre && end) load_digest(sib, nxt);
         } else {
             const uint32_t lvl = start + step - n_pre;
-            if (lvl && ((ckmask >> (lvl - 1)) & 1u)) { // a follower needs this node (height lvl)
-                uint32_t *dst = p.dd.ckpt + ((size_t)i * CH + tree * Q + (uint32_t)((ckto >> (4 * (lvl - 1))) & 15u)) * 8;
+            if ((ckmask >> lvl) & 1u) { // a follower needs this node (height lvl)
+                uint32_t *dst = p.dd.ckpt + ((size_t)i * CH + tree * Q + (uint32_t)((ckto >> (4 * lvl)) & 15u)) * 8;
 #pragma unroll
                 for (int k = 0; k < 8; k++) dst[k] = cur[k];
             }
@@ -660,11 +666,12 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
     uint32_t *dst = (round == 0 ? p.dd.own : p.dd.ckpt) + (size_t)cg * 8; // round 2 reuses the follower's checkpoint slot for its root
 #pragma unroll
     for (int k = 0; k < 8; k++) dst[k] = cur[k];
-    if (round == 0 && (pw & DD_FOLLOWER)) { // the levels this follower skips: are its siblings there the leader's?  (proof data only)
+    if (round == 0 && (pw & DD_FOLLOWER)) { // proof data only: my node (height lv) must be the leader's sibling there, and above it my siblings the leader's
         const uint4 *sq = reinterpret_cast<const uint4 *>(sib), *sr = reinterpret_cast<const uint4 *>(sib + ((int)((pw >> 8) & 15u) - (int)q) * (int)(depth * 8));
-        uint32_t diff = 0;
+        const uint4 l0 = __ldg(sr + 2 * lv), l1 = __ldg(sr + 2 * lv + 1);
+        uint32_t diff = (cur[0] ^ l0.x) | (cur[1] ^ l0.y) | (cur[2] ^ l0.z) | (cur[3] ^ l0.w) | (cur[4] ^ l1.x) | (cur[5] ^ l1.y) | (cur[6] ^ l1.z) | (cur[7] ^ l1.w);
 #pragma unroll 2
-        for (uint32_t k = h; k < depth; k++) {
+        for (uint32_t k = lv + 1; k < depth; k++) {
             const uint4 a0 = __ldg(sq + 2 * k), a1 = __ldg(sq + 2 * k + 1), b0 = __ldg(sr + 2 * k), b1 = __ldg(sr + 2 * k + 1);
             diff |= (a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w);
         }
@@ -679,8 +686,9 @@ __device__ __forceinline__ bool eq8(const uint32_t *a, const uint32_t *b) {
     return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 }
 
-// One thread per chain: a follower keeps its leader's result only if its own node at the meeting height (for h = 0: its own leaf data) and
-// every one of its remaining siblings is bit-identical to the leader's; otherwise (corrupted proofs only) it is queued for round 2.
+// One thread per chain: a follower keeps its leader's result only if, one level below the meeting node, its node is the leader's sibling and its
+// sibling the leader's node (same-leaf followers: its leaf data is the leader's), and every sibling above is bit-identical to the leader's;
+// otherwise (corrupted proofs only) it is queued for round 2.
 __global__ void __launch_bounds__(256) stwo_check_kernel(StwoParams p) {
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
     const uint32_t CH = p.dd.chains;
@@ -689,15 +697,16 @@ __global__ void __launch_bounds__(256) stwo_check_kernel(StwoParams p) {
     const uint32_t pw = p.dd.plan[cg];
     if (!(pw & DD_FOLLOWER)) return;
     const uint32_t i = cg / CH, c = cg % CH, tree = c / Q, q = c % Q;
-    const uint32_t h = pw & 31u, lead = (pw >> 8) & 15u;
+    const uint32_t lv = pw & 31u, lead = (pw >> 8) & 15u;
+    const bool same_leaf = (pw & DD_SAMELEAF) != 0;
     const ssym_stwo_layout_t &lo = p.lo;
     const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
     const uint32_t kind = tree < 2 ? tree : 2u, layer = tree < 2 ? 0u : tree - 2u;
     const uint32_t d = tree < 2 ? G : G - 1 - layer;
     const uint32_t *sib0 = pk + (tree == 0 ? lo.off_trace_sib : tree == 1 ? lo.off_cp_sib : lo.off_fri_sib[layer]);
     bool valid = true;
-    if (h >= 1) { // its remaining siblings were compared by the chain's own thread in round 1
-        valid = !(pw & DD_SIBDIFF) && eq8(p.dd.own + (size_t)cg * 8, p.dd.ckpt + (size_t)cg * 8);
+    if (!same_leaf) { // round 1 compared its node with the leader's sibling and its upper siblings with the leader's; here: its sibling at lv = the leader's node
+        valid = !(pw & DD_SIBDIFF) && eq8(sib0 + (q * d + lv) * 8, p.dd.ckpt + (size_t)cg * 8);
     } else if (kind == 2) { // same leaf pair: the two 16-byte leaves, in tree order (adjacent_leaves fri/layers.simf:29-37), must agree
         const uint32_t *qs = p.ctx + (size_t)i * CX::WORDS + CX::QUERIES;
         const uint32_t *ev = p.fri_evals + ((size_t)i * (L + 1) + layer) * Q * 4;
@@ -713,14 +722,14 @@ __global__ void __launch_bounds__(256) stwo_check_kernel(StwoParams p) {
     const uint4 *sq = reinterpret_cast<const uint4 *>(sib0 + q * d * 8), *sr = reinterpret_cast<const uint4 *>(sib0 + lead * d * 8);
     uint32_t diff = 0; // branch-free so that the loads of all levels are in flight together
 #pragma unroll 4
-    for (uint32_t k = 0; h == 0 && k < d; k++) { // (followers that met at the leaf have no thread in round 1)
+    for (uint32_t k = 0; same_leaf && k < d; k++) { // (followers that met at the leaf have no thread in round 1)
         const uint4 a0 = __ldg(sq + 2 * k), a1 = __ldg(sq + 2 * k + 1), b0 = __ldg(sr + 2 * k), b1 = __ldg(sr + 2 * k + 1);
         diff |= (a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w);
     }
     valid = valid && diff == 0;
     if (!valid) {
         p.dd.plan[cg] = pw | DD_INVALID;
-        const uint32_t bin = p.dd.bin_of[1][h ? 3u : kind][h ? d - h : d];
+        const uint32_t bin = p.dd.bin_of[1][same_leaf ? kind : 3u][same_leaf ? d : d - lv];
         const uint32_t slot = atomicAdd(&p.dd.bin_count[STWO_DEDUP_MAX_BINS + bin], 1u);
         p.dd.bin_list[p.dd.bin_base[1][bin] + slot] = cg;
     }
@@ -761,22 +770,22 @@ size_t stwo_dedup_layout(const ssym_stwo_config_t &cfg, size_t cap, StwoDedup &d
     dd.enabled = 0;
     dd.chains = (L + 3) * Q;
     if (G > STWO_DEDUP_MAX_DEPTH || Q > 16) return 0;
-    // Bins (kind, steps), ordered by decreasing number of compressions.  Round 1: kind 0 trace (1 + 2h), 1 composition (2 + 2h), 2 FRI (4 + 2h),
-    // h = 1..depth.  Round 2: kind 3 = from a stored node, r = depth - h levels (2r); kinds 0..2 = whole paths of followers that met at the leaf.
+    // Bins (kind, levels), ordered by decreasing number of compressions.  Round 1: kind 0 trace (1 + 2 lv), 1 composition (2 + 2 lv), 2 FRI (4 + 2 lv),
+    // lv = 0..depth.  Round 2: kind 3 = from a stored node at height lv, depth - lv levels; kinds 0..2 = whole paths of followers that met at the leaf.
     struct B { uint32_t kind, steps, work, capacity; };
     size_t total = 0;
     for (uint32_t round = 0; round < 2; round++) {
         B bins[STWO_DEDUP_MAX_BINS];
         uint32_t nb = 0;
         for (uint32_t kind = 0; kind < 4; kind++)
-            for (uint32_t steps = 1; steps <= G; steps++) {
+            for (uint32_t steps = 0; steps <= G; steps++) {
                 // trees that can put a chain here
                 uint32_t trees = 0;
                 for (uint32_t tree = 0; tree < L + 3; tree++) {
                     const uint32_t tk = tree < 2 ? tree : 2u, d = tree < 2 ? G : G - 1 - (tree - 2);
-                    if (round == 0) trees += (kind == tk && steps <= d) ? 1u : 0u;          // h = steps
-                    else if (kind == 3) trees += (steps < d) ? 1u : 0u;                   // h = d - steps >= 1
-                    else trees += (kind == tk && steps == d) ? 1u : 0u;                   // h = 0: the whole path
+                    if (round == 0) trees += (kind == tk && steps <= d) ? 1u : 0u;             // lv = steps
+                    else if (kind == 3) trees += (steps >= 1 && steps <= d) ? 1u : 0u;      // lv = d - steps
+                    else trees += (kind == tk && steps == d) ? 1u : 0u;                      // same leaf: the whole path
                 }
                 if (!trees || (round == 0 && kind == 3)) continue;
                 const uint32_t pre = kind == 0 ? 1u : kind == 1 ? 2u : kind == 2 ? 4u : 0u;

@@ -51,18 +51,21 @@ struct StwoTables {
 };
 
 // Node sharing between the Merkle paths of one tree (SURVEY.md 8a "merkle.simf": the reference hashes every query's path to the root
-// on its own; two paths that have met run through the same nodes from there on).  With MAX_DEDUP_DEPTH >= tree depth the Merkle work of a
-// proof is planned per tree: query q follows the lowest-numbered query r < q whose path it meets first, at height h_q, and hashes only
-// the h_q levels below the meeting node.  A resolve kernel then checks, word for word, that q's node at height h_q and q's remaining
-// siblings ARE r's (if they are, q's root is r's root by construction; if not — a corrupted proof — q's path is hashed to the root after
-// all, in a second round of the same hashing kernel), so every per-query result is exactly what the per-query schedule gives.
+// on its own; two paths that have met run through the same nodes from there on).  With STWO_DEDUP_MAX_DEPTH >= tree depth the Merkle work of a
+// proof is planned per tree: query q follows the lowest-numbered query r < q whose path it meets first, at height h_q, and hashes only the
+// h_q - 1 levels below the two children of the meeting node.  There q's node must be r's sibling and q's sibling r's node: then the meeting
+// node has bit-identical inputs on both paths, and if q's siblings above it are r's too, q's root IS r's root.  All of this is checked word for
+// word (followers compare proof data in their own thread, a check kernel compares the one hashed node); a follower that fails any comparison
+// — a corrupted proof — is hashed to the root after all, in a second round of the same hashing kernel, so every per-query result is exactly
+// what the per-query schedule gives.
 enum { STWO_DEDUP_MAX_DEPTH = 16, STWO_DEDUP_MAX_BINS = 64 };
 struct StwoDedup {
     // per chain c = tree * Q + q of proof i (tree 0 = trace, 1 = composition, 2 + l = FRI layer l), index i * chains + c:
-    uint32_t *plan;      // bits 0-4 h (levels hashed in round 1), bit 6 check failed, bit 7 follower, bits 8-11 leader query, bits 16-31 checkpoint mask (bit 15 + k: height k)
-    uint64_t *ckpt_to;   // nibble k - 1: the follower query that needs this chain's node at height k
-    uint32_t *own;       // [8] round 1: the chain's last node = the root (full chains) or the node at height h (followers)
-    uint32_t *ckpt;      // [8] written by the LEADER of this chain: the leader's node at this chain's height h; after the check, round 2 puts
+    uint32_t *plan;      // bits 0-4 lv (levels hashed in round 1), bit 5 sibling mismatch, bit 6 check failed, bit 7 follower, bits 8-11 leader query,
+                         // bit 12 same leaf as the leader, bits 16-31 checkpoint mask (bit 16 + k: this chain's node at height k is wanted)
+    uint64_t *ckpt_to;   // nibble k: the follower query that needs this chain's node at height k
+    uint32_t *own;       // [8] round 1: the chain's last node = the root (full chains) or the node at height lv (followers)
+    uint32_t *ckpt;      // [8] written by the LEADER of this chain: the leader's node at this chain's height lv; after the check, round 2 puts
                          //     the root of a follower that failed it here
     uint32_t *bin_count; // [2][MAX_BINS] tasks per bin and round; a bin = (kind, steps) so that a warp's 32 tasks have one length; longest first
     uint32_t *bin_list;  // chain ids (i * chains + c); bin b of round r at bin_base[r][b] .. + its capacity
