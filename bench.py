@@ -88,7 +88,7 @@ def cpu_baseline(cfg, packed, n, budget_s=15.0):
     from oracle import oracle as O
 
     orc = O.Oracle()
-    ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
     threads = cpu_threads()
     t1, _ = oracle_run(orc, ocfg, packed, n, 1, 8)
     per_proof = t1 / 8
@@ -382,7 +382,7 @@ def main():
         from oracle import oracle as O
 
         orc = O.Oracle()
-        ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+        ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
         _, o_status, _ = orc.stwo_verify_batch(ocfg, host_batch, 4)
         assert (st[:4] == o_status).all() and (st == st[0]).all(), "GPU status differs from the oracle"
         assert accepted == (total_n if args.mode == "prover-consistent" else 0)

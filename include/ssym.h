@@ -57,7 +57,8 @@ extern "C" {
 #define SSYM_MODE_REF_LITERAL 0
 #define SSYM_MODE_PROVER_CONSISTENT 1
 
-#define SSYM_NUM_COLUMNS 4        /* config.simf:14 NUM_COLUMNS                     */
+#define SSYM_NUM_COLUMNS 4        /* config.simf:14 NUM_COLUMNS at reference HEAD (the default)   */
+#define SSYM_MAX_COLUMNS 16       /* largest supported NUM_COLUMNS (a power of two, config.simf:12-14) */
 #define SSYM_NUM_CP_PARTITIONS 16 /* evals/composition_poly.simf:13                 */
 #define SSYM_MAX_QUERIES 16       /* config.simf:42 NUM_FRI_QUERIES (prod)          */
 #define SSYM_MAX_FRI_LAYERS 9     /* first layer + NUM_FRI_LAYERS (config.simf:47)  */
@@ -68,9 +69,15 @@ typedef struct ssym_stwo_config {
     uint32_t n_queries;    /* NUM_FRI_QUERIES     config.simf:25,43  (1..16)        */
     uint32_t n_fri_layers; /* NUM_FRI_LAYERS      config.simf:29,47  (inner, 0..8)  */
     uint32_t mode;         /* SSYM_MODE_*                                           */
-    uint32_t reserved;
+    uint32_t n_columns;    /* NUM_COLUMNS         config.simf:14     (4, 8 or 16; 0 = 4, the value at reference HEAD).
+                            * The AIR stays the wide-Fibonacci one (constraints/wide_fibonacci.simf:24-62: column i >= 2 is
+                            * constrained by c_i = c_{i-1}^2 + c_{i-2}^2), only its width changes: the `CONFIG:` comments of the
+                            * reference (fri/answers.simf:118, evals/verify.simf, hasher.simf:85-90) name the macros to re-point. */
     uint64_t pow_target;   /* POW_TARGET_64       config.simf:32,51 */
 } ssym_stwo_config_t;
+
+/* NUM_COLUMNS of a configuration (n_columns == 0 means the reference's 4). */
+#define SSYM_STWO_COLUMNS(cfg) ((cfg)->n_columns ? (cfg)->n_columns : (uint32_t)SSYM_NUM_COLUMNS)
 
 /* The two presets of config.simf (TESTING / production). */
 int ssym_stwo_config_preset(const char *name /* "prod" | "testing" */, uint32_t mode,
@@ -78,10 +85,10 @@ int ssym_stwo_config_preset(const char *name /* "prod" | "testing" */, uint32_t 
 
 /* Packed wire format of one Stwo proof (all little-endian u32 words; digests as
  * 8 words, most significant first).  Sections, in order, each starting on a
- * 32-byte boundary (Q = n_queries, L = n_fri_layers, G = lde_log):
- *   header   : commit[3][8] | oods_trace[4][4] | oods_cp[16][4] | fri_first_root[8]
+ * 32-byte boundary (Q = n_queries, L = n_fri_layers, G = lde_log, C = NUM_COLUMNS):
+ *   header   : commit[3][8] | oods_trace[C][4] | oods_cp[16][4] | fri_first_root[8]
  *              | fri_inner_root[L][8] | last_coeff[4] | pow_nonce {hi, lo}
- *   qvals    : per query { trace_vals[4], cp_vals[16] }
+ *   qvals    : per query { trace_vals[C], cp_vals[16] }
  *   trace_sib: [Q][G][8]         (leaf -> root order, merkle.simf:39-44)
  *   cp_sib   : [Q][G][8]
  *   fri_wit  : [L+1][Q][4]

@@ -27,7 +27,7 @@ class StwoConfig(C.Structure):
         ("n_queries", C.c_uint32),
         ("n_fri_layers", C.c_uint32),
         ("mode", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("n_columns", C.c_uint32),
         ("pow_target", C.c_uint64),
     ]
 
@@ -81,9 +81,10 @@ PRESETS = {
 }
 
 
-def make_config(preset: str, mode: int) -> StwoConfig:
+def make_config(preset: str, mode: int, n_columns: int = 4) -> StwoConfig:
+    """A preset of config.simf:10-51 with NUM_COLUMNS = n_columns (config.simf:14; 4 at reference HEAD)."""
     p = PRESETS[preset]
-    return StwoConfig(p["trace_log"], p["lde_log"], p["n_queries"], p["n_fri_layers"], mode, 0, p["pow_target"])
+    return StwoConfig(p["trace_log"], p["lde_log"], p["n_queries"], p["n_fri_layers"], mode, n_columns, p["pow_target"])
 
 
 def build(force: bool = False) -> str:

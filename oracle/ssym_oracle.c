@@ -360,9 +360,9 @@ static Ctx8 hasher_add_qm31(QM31 v, Ctx8 c) { /* hasher.simf:57-64 */
     c = sha_256_ctx_8_add_4(c, v.i.b);
     return c;
 }
-static u256 hash_node_m31_trace(const M31 *evals /* NUM_COLUMNS x 1 */) { /* hasher.simf:85-90 */
+static u256 hash_node_m31_trace(const M31 *evals /* NUM_COLUMNS x 1 */, uint32_t n_columns) { /* hasher.simf:85-90 */
     Ctx8 c = sha_256_ctx_8_init();
-    for (int i = 0; i < SSYM_NUM_COLUMNS; i++) c = sha_256_ctx_8_add_4(c, evals[i]);
+    for (uint32_t i = 0; i < n_columns; i++) c = sha_256_ctx_8_add_4(c, evals[i]);
     return sha_256_ctx_8_finalize(c);
 }
 static u256 hash_node_m31_cp(const M31 *evals /* 16 */) { /* hasher.simf:93-97 */
@@ -505,10 +505,10 @@ static QM31 vanishing_poly_eval(uint8_t log_size, QM31Point p) { /* composition_
 }
 
 /* ---- constraints/wide_fibonacci.simf -------------------------------------- */
-static QM31 eval_composition_poly(uint8_t log_size, QM31Point p, const QM31 oods_trace[4], QM31 random_coeff) { /* wide_fibonacci.simf:24-62 */
+static QM31 eval_composition_poly(uint8_t log_size, QM31Point p, const QM31 *oods_trace /* NUM_COLUMNS */, uint32_t n_columns, QM31 random_coeff) { /* wide_fibonacci.simf:24-62 */
     QM31 acc = qm31_zero(), a = qm31_zero(), b = qm31_zero();
     uint8_t skip_2 = 0;
-    for (int col = 0; col < SSYM_NUM_COLUMNS; col++) { /* eval_column, left-to-right fold */
+    for (uint32_t col = 0; col < n_columns; col++) { /* eval_column, left-to-right fold */
         QM31 c = oods_trace[col];
         if (skip_2 == 2) {
             QM31 constraint = qm31_sub(c, qm31_add(qm31_pow2(b), qm31_pow2(a)));
@@ -523,10 +523,10 @@ static QM31 eval_composition_poly(uint8_t log_size, QM31Point p, const QM31 oods
 }
 
 /* ---- deep/oods.simf -------------------------------------------------------- */
-static void channel_mix_oods_evals(ChannelState *s, const QM31 oods_trace[4], const QM31 oods_cp[16]) { /* deep/oods.simf:23-39 */
+static void channel_mix_oods_evals(ChannelState *s, const QM31 *oods_trace /* NUM_COLUMNS */, uint32_t n_columns, const QM31 oods_cp[16]) { /* deep/oods.simf:23-39 */
     Ctx8 c = sha_256_ctx_8_init();
     c = sha_256_ctx_8_add_32(c, s->digest);
-    for (int i = 0; i < SSYM_NUM_COLUMNS; i++) c = hasher_add_qm31(oods_trace[i], c);
+    for (uint32_t i = 0; i < n_columns; i++) c = hasher_add_qm31(oods_trace[i], c);
     for (int i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) c = hasher_add_qm31(oods_cp[i], c);
     s->digest = sha_256_ctx_8_finalize(c);
     s->n_sent = 0;
@@ -577,14 +577,14 @@ static QM31 line_fold(uint32_t position, QM31 f_p, QM31 f_neg_p, uint8_t log_siz
 
 /* ---- fri/answers.simf --------------------------------------------------------- */
 /* REF_LITERAL: fri/answers.simf:97-129. */
-static QM31 fri_answer_literal(uint32_t query, const M31 trace_evals[4], const M31 cp_evals[16], QM31 random_coeff,
-                               QM31Point oods_point, const QM31 oods_trace[4], const QM31 oods_cp[16], uint8_t log_size_ex) {
+static QM31 fri_answer_literal(uint32_t query, const M31 *trace_evals /* NUM_COLUMNS */, uint32_t n_columns, const M31 cp_evals[16], QM31 random_coeff,
+                               QM31Point oods_point, const QM31 *oods_trace, const QM31 oods_cp[16], uint8_t log_size_ex) {
     CircleDomain domain = circle_domain(log_size_ex);
     uint32_t position = bit_reverse_position(query, log_size_ex);
     M31Point dp = circle_position_to_m31_point(domain, position);
     CM31 den_inv = deep_quotient_denominator_inverse(oods_point, dp);
     QM31 acc = qm31(0, 0, 0, 0), alpha_i = random_coeff;
-    for (int c = 0; c < SSYM_NUM_COLUMNS; c++) { /* trace_quotient_numerator_aggregate, offset 0 */
+    for (uint32_t c = 0; c < n_columns; c++) { /* trace_quotient_numerator_aggregate, offset 0 */
         LineCoeffs k = deep_quotient_interpolant_coefficients(oods_point, oods_trace[c], alpha_i);
         acc = qm31_add(acc, deep_quotient_nominator(k, dp, trace_evals[c]));
         alpha_i = qm31_mul(alpha_i, random_coeff);
@@ -594,11 +594,11 @@ static QM31 fri_answer_literal(uint32_t query, const M31 trace_evals[4], const M
         acc = qm31_add(acc, deep_quotient_nominator(k, dp, cp_evals[c]));
         alpha_i = qm31_mul(alpha_i, random_coeff);
     }
-    return qm31_mul(qm31_mul_cm31(acc, den_inv), alpha_i); /* batch_coeff = alpha^21 */
+    return qm31_mul(qm31_mul_cm31(acc, den_inv), alpha_i); /* batch_coeff = alpha^(NUM_COLUMNS + 17) */
 }
 /* PROVER_CONSISTENT: SURVEY.md Appendix A item 1 (the behaviour of the prover that produced tests/data/proof.json). */
-static QM31 fri_answer_prover(uint32_t query, const M31 trace_evals[4], const M31 cp_evals[16], QM31 random_coeff,
-                              QM31Point oods_point, const QM31 oods_trace[4], const QM31 oods_cp[16], uint8_t log_size_ex) {
+static QM31 fri_answer_prover(uint32_t query, const M31 *trace_evals /* NUM_COLUMNS */, uint32_t n_columns, const M31 cp_evals[16], QM31 random_coeff,
+                              QM31Point oods_point, const QM31 *oods_trace, const QM31 oods_cp[16], uint8_t log_size_ex) {
     CircleDomain domain = circle_domain(log_size_ex);
     uint32_t position = bit_reverse_position(query, log_size_ex);
     M31Point dp = circle_position_to_m31_point(domain, position);
@@ -612,7 +612,7 @@ static QM31 fri_answer_prover(uint32_t query, const M31 trace_evals[4], const M3
         num_a = qm31_add(num_a, deep_quotient_nominator(k, dp, cp_evals[c]));
         alpha_i = qm31_mul(alpha_i, random_coeff);
     }
-    for (int c = 0; c < SSYM_NUM_COLUMNS; c++) {
+    for (uint32_t c = 0; c < n_columns; c++) {
         LineCoeffs k = deep_quotient_interpolant_coefficients(oods_point, oods_trace[c], alpha_i);
         num_b = qm31_add(num_b, deep_quotient_nominator(k, dp, trace_evals[c]));
         alpha_i = qm31_mul(alpha_i, random_coeff);
@@ -626,19 +626,20 @@ static QM31 fri_answer_prover(uint32_t query, const M31 trace_evals[4], const M3
 static uint32_t align8(uint32_t w) { return (w + 7u) & ~7u; } /* 32-byte sections */
 
 EXPORT int oracle_stwo_layout(const ssym_stwo_config_t *cfg, ssym_stwo_layout_t *o) {
-    uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log;
+    uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg);
     if (Q < 1 || Q > SSYM_MAX_QUERIES || L + 1 > SSYM_MAX_FRI_LAYERS || G < L + 1 || G > 30) return -1;
+    if (C != 4 && C != 8 && C != 16) return -1;
     memset(o, 0, sizeof *o);
     uint32_t w = 0, alg = 0;
     o->off_commit = w; w += 24;
-    o->off_oods_trace = w; w += 16;
+    o->off_oods_trace = w; w += 4 * C;
     o->off_oods_cp = w; w += 64;
     o->off_fri_first_root = w; w += 8;
     o->off_fri_inner_root = w; w += 8 * L;
     o->off_last_coeff = w; w += 4;
     o->off_pow_nonce = w; w += 2;
     alg += w; w = align8(w);
-    o->off_qvals = w; w += Q * 20; alg += Q * 20; w = align8(w);
+    o->off_qvals = w; w += Q * (C + 16); alg += Q * (C + 16); w = align8(w);
     o->off_trace_sib = w; w += Q * G * 8; alg += Q * G * 8;
     o->off_cp_sib = w; w += Q * G * 8; alg += Q * G * 8;
     o->off_fri_wit = w; w += (L + 1) * Q * 4; alg += (L + 1) * Q * 4; w = align8(w);
@@ -662,13 +663,13 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     ssym_stwo_layout_t lo;
     memset(tr, 0, sizeof *tr);
     if (oracle_stwo_layout(cfg, &lo) != 0) { tr->status = SSYM_ST_SHAPE; return; }
-    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log;
+    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
     uint32_t status = 0;
 
     u256 commitments[3];
     for (int i = 0; i < 3; i++) commitments[i] = load_u256(pk + lo.off_commit + 8 * i);
-    QM31 oods_trace[4], oods_cp[16];
-    for (int i = 0; i < 4; i++) oods_trace[i] = qm31_from_w(pk + lo.off_oods_trace + 4 * i);
+    QM31 oods_trace[SSYM_MAX_COLUMNS], oods_cp[16];
+    for (uint32_t i = 0; i < C; i++) oods_trace[i] = qm31_from_w(pk + lo.off_oods_trace + 4 * i);
     for (int i = 0; i < 16; i++) oods_cp[i] = qm31_from_w(pk + lo.off_oods_cp + 4 * i);
 
     /* verifier.simf:36 */
@@ -692,8 +693,8 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
         oods_point.x = qm31_mul(qm31_sub(qm31_one(), t_sq), inv);
         oods_point.y = qm31_mul(qm31_add(t, t), inv);
     }
-    channel_mix_oods_evals(&state, oods_trace, oods_cp);
-    QM31 cp_eval = eval_composition_poly((uint8_t)cfg->trace_log, oods_point, oods_trace, cp_alpha);
+    channel_mix_oods_evals(&state, oods_trace, C, oods_cp);
+    QM31 cp_eval = eval_composition_poly((uint8_t)cfg->trace_log, oods_point, oods_trace, C, cp_alpha);
     if (t_fail) status |= SSYM_ST_OODS_INV_ZERO;
     QM31 sampled = composition_poly_eval_from_decomposed(oods_cp, oods_point);
     if (!qm31_eq(cp_eval, sampled)) status |= SSYM_ST_OODS_CP_MISMATCH; /* deep/oods.simf:58 */
@@ -747,16 +748,16 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     uint32_t domain_size = jet_left_shift_32((uint8_t)G, 1); /* evals/verify.simf:119 */
     for (uint32_t q = 0; q < Q; q++) {
         tr->queries[q] = queries[q];
-        const uint32_t *qv = pk + lo.off_qvals + 20 * q;
+        const uint32_t *qv = pk + lo.off_qvals + QV * q;
         /* verify_trace_evals evals/verify.simf:50-58 */
         t_fail = 0;
-        u256 r = merkle_verify_32(hash_node_m31_trace(qv), jet_add_32(queries[q], domain_size),
+        u256 r = merkle_verify_32(hash_node_m31_trace(qv, C), jet_add_32(queries[q], domain_size),
                                   pk + lo.off_trace_sib + q * G * 8, G, commitments[1]);
         if (t_fail) { status |= SSYM_ST_TRACE_MERKLE; tr->mask_trace |= 1u << q; }
         store_u256(tr->trace_root[q], r);
         /* verify_cp_evals evals/verify.simf:60-68 */
         t_fail = 0;
-        r = merkle_verify_32(hash_node_m31_cp(qv + 4), jet_add_32(queries[q], domain_size),
+        r = merkle_verify_32(hash_node_m31_cp(qv + C), jet_add_32(queries[q], domain_size),
                              pk + lo.off_cp_sib + q * G * 8, G, commitments[2]);
         if (t_fail) { status |= SSYM_ST_CP_MERKLE; tr->mask_cp |= 1u << q; }
         store_u256(tr->cp_root[q], r);
@@ -766,11 +767,11 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     QM31 evals[SSYM_MAX_QUERIES];
     uint32_t fq[SSYM_MAX_QUERIES];
     for (uint32_t q = 0; q < Q; q++) {
-        const uint32_t *qv = pk + lo.off_qvals + 20 * q;
+        const uint32_t *qv = pk + lo.off_qvals + QV * q;
         t_fail = 0;
         evals[q] = (cfg->mode == SSYM_MODE_REF_LITERAL)
-                       ? fri_answer_literal(queries[q], qv, qv + 4, deep_alpha, oods_point, oods_trace, oods_cp, (uint8_t)G)
-                       : fri_answer_prover(queries[q], qv, qv + 4, deep_alpha, oods_point, oods_trace, oods_cp, (uint8_t)G);
+                       ? fri_answer_literal(queries[q], qv, C, qv + C, deep_alpha, oods_point, oods_trace, oods_cp, (uint8_t)G)
+                       : fri_answer_prover(queries[q], qv, C, qv + C, deep_alpha, oods_point, oods_trace, oods_cp, (uint8_t)G);
         if (t_fail) { status |= SSYM_ST_ANSWER_INV_ZERO; tr->mask_answer_inv |= 1u << q; }
         qm31_to_w(evals[q], tr->fri_answer[q]);
         fq[q] = queries[q];
@@ -906,7 +907,7 @@ EXPORT void oracle_sha256(const uint32_t *in, uint32_t *o) { store_u256(o, sha25
 EXPORT void oracle_sha256_32(uint32_t in, uint32_t *o) { store_u256(o, sha256_32(in)); }
 EXPORT void oracle_sha256_pair(const uint32_t *l, const uint32_t *r, uint32_t *o) { store_u256(o, sha256_pair(load_u256(l), load_u256(r))); }
 EXPORT void oracle_sha256_bytes(const uint8_t *data, size_t len, uint32_t *o) { Ctx8 c = sha_256_ctx_8_init(); for (size_t i = 0; i < len; i++) ctx_add_byte(&c, data[i]); store_u256(o, sha_256_ctx_8_finalize(c)); }
-EXPORT void oracle_hash_node_m31_trace(const uint32_t *e, uint32_t *o) { store_u256(o, hash_node_m31_trace(e)); }
+EXPORT void oracle_hash_node_m31_trace(const uint32_t *e, uint32_t *o) { store_u256(o, hash_node_m31_trace(e, SSYM_NUM_COLUMNS)); }
 EXPORT void oracle_hash_node_m31_cp(const uint32_t *e, uint32_t *o) { store_u256(o, hash_node_m31_cp(e)); }
 EXPORT void oracle_hash_node_qm31(const uint32_t *e, uint32_t *o) { store_u256(o, hash_node_qm31(qm31_from_w(e))); }
 /* merkle.simf:39-44; returns 1 iff both asserts hold */
@@ -949,7 +950,7 @@ EXPORT void oracle_eval_composition_poly(uint32_t log_size, const uint32_t *poin
     QM31 tr[4];
     for (int i = 0; i < 4; i++) tr[i] = qm31_from_w(oods_trace + 4 * i);
     t_fail = 0;
-    qm31_to_w(eval_composition_poly((uint8_t)log_size, qp_from_w(point), tr, qm31_from_w(coeff)), o);
+    qm31_to_w(eval_composition_poly((uint8_t)log_size, qp_from_w(point), tr, SSYM_NUM_COLUMNS, qm31_from_w(coeff)), o);
     if (fail) *fail = t_fail;
 }
 EXPORT void oracle_channel_mix_oods_evals(uint32_t *st, const uint32_t *oods_trace, const uint32_t *oods_cp) {
@@ -957,7 +958,7 @@ EXPORT void oracle_channel_mix_oods_evals(uint32_t *st, const uint32_t *oods_tra
     QM31 tr[4], cp[16];
     for (int i = 0; i < 4; i++) tr[i] = qm31_from_w(oods_trace + 4 * i);
     for (int i = 0; i < 16; i++) cp[i] = qm31_from_w(oods_cp + 4 * i);
-    channel_mix_oods_evals(&s, tr, cp);
+    channel_mix_oods_evals(&s, tr, SSYM_NUM_COLUMNS, cp);
     st_to_w(s, st);
 }
 /* deep/oods.simf:44-64; returns 1 iff the CP assert (:58) holds and no inverse-of-zero occurred */
@@ -969,8 +970,8 @@ EXPORT int oracle_oods(uint32_t *st, uint32_t log_size, const uint32_t *oods_tra
     for (int i = 0; i < 16; i++) cp[i] = qm31_from_w(oods_cp + 4 * i);
     t_fail = 0;
     QM31Point p = channel_draw_qm31_point(&s);
-    channel_mix_oods_evals(&s, tr, cp);
-    QM31 cp_eval = eval_composition_poly((uint8_t)log_size, p, tr, qm31_from_w(cp_alpha));
+    channel_mix_oods_evals(&s, tr, SSYM_NUM_COLUMNS, cp);
+    QM31 cp_eval = eval_composition_poly((uint8_t)log_size, p, tr, SSYM_NUM_COLUMNS, qm31_from_w(cp_alpha));
     QM31 sampled = composition_poly_eval_from_decomposed(cp, p);
     ORACLE_ASSERT(qm31_eq(cp_eval, sampled));
     qm31_to_w(channel_draw_qm31(&s), deep_alpha);
@@ -1014,8 +1015,8 @@ EXPORT void oracle_fri_answer(uint32_t mode, uint32_t query, const uint32_t *tra
     for (int i = 0; i < 16; i++) cp[i] = qm31_from_w(oods_cp + 4 * i);
     t_fail = 0;
     QM31 r = mode == SSYM_MODE_REF_LITERAL
-                 ? fri_answer_literal(query, trace_evals, cp_evals, qm31_from_w(coeff), qp_from_w(point), tr, cp, (uint8_t)log_size_ex)
-                 : fri_answer_prover(query, trace_evals, cp_evals, qm31_from_w(coeff), qp_from_w(point), tr, cp, (uint8_t)log_size_ex);
+                 ? fri_answer_literal(query, trace_evals, SSYM_NUM_COLUMNS, cp_evals, qm31_from_w(coeff), qp_from_w(point), tr, cp, (uint8_t)log_size_ex)
+                 : fri_answer_prover(query, trace_evals, SSYM_NUM_COLUMNS, cp_evals, qm31_from_w(coeff), qp_from_w(point), tr, cp, (uint8_t)log_size_ex);
     qm31_to_w(r, o);
     if (fail) *fail = t_fail;
 }

@@ -11,10 +11,12 @@
  * reference VERIFIER: every proof it emits must be accepted by oracle_stwo_verify_one in PROVER_CONSISTENT mode (the
  * semantics under which the shipped fixtures verify), i.e. pass stwo-verifier/src/verifier.simf:32-58
  * with F1-F3 resolved.  The statement proven is the one the verifier checks:
- *   - 4 trace columns over the canonic coset of size 2^trace_log, each row c2 = c0^2 + c1^2, c3 = c1^2 + c2^2
- *     (constraints/wide_fibonacci.simf:24-62, all masks at offset 0), c0 = 1, c1 = SplitMix64(seed, row) mod p;
+ *   - C = NUM_COLUMNS (config.simf:14; 4 at reference HEAD, also 8 and 16) trace columns over the canonic coset of size 2^trace_log,
+ *     each row c_i = c_{i-1}^2 + c_{i-2}^2 for i >= 2 (constraints/wide_fibonacci.simf:24-62, all masks at offset 0),
+ *     c0 = 1, c1 = SplitMix64(seed, row) mod p;
  *   - commitments = (SHA-256(""), trace root, composition root) mixed as in evals/commit.simf:20-35;
- *   - composition polynomial CP = (alpha*C2 + C3) / vanishing(trace_log) split into 16 M31 columns
+ *   - composition polynomial CP = (sum_{i>=2} alpha^(C-1-i) K_i) / vanishing(trace_log), K_i = c_i - c_{i-1}^2 - c_{i-2}^2 (the Horner fold of
+ *     eval_column, wide_fibonacci.simf:33-52; alpha*K2 + K3 for C = 4), split into 16 M31 columns
  *     (index 4*coord + poly; poly = low two bits of the circle-FFT coefficient index, so that
  *     F(P) = Fa(2P) + y Fb(2P) + x Fc(2P) + xy Fd(2P), evals/composition_poly.simf:47-59) sampled at the doubled point;
  *   - DEEP quotient = fri_answer (fri/answers.simf:97-129 with Appendix A item 1) on the whole LDE domain;
@@ -173,10 +175,17 @@ static uint64_t pr_splitmix(uint64_t seed, uint64_t row) {
     return z;
 }
 
+/* one trace row: c0 = 1, c1 = SplitMix64(seed, row) mod p, c_i = c_{i-1}^2 + c_{i-2}^2 */
+static void pr_trace_row(uint64_t seed, uint32_t row, uint32_t n_columns, uint32_t *out) {
+    out[0] = 1;
+    out[1] = (uint32_t)(pr_splitmix(seed, row) >> 33) % M31_MODULUS;
+    for (uint32_t i = 2; i < n_columns; i++) out[i] = fadd(fmul(out[i - 1], out[i - 1]), fmul(out[i - 2], out[i - 2]));
+}
+
 EXPORT int oracle_stwo_prove_one(const ssym_stwo_config_t *cfg, uint64_t seed, uint32_t *out) {
     ssym_stwo_layout_t lo;
     if (oracle_stwo_layout(cfg, &lo) != 0) return -1;
-    const uint32_t T = cfg->trace_log, G = cfg->lde_log, Q = cfg->n_queries, L = cfg->n_fri_layers;
+    const uint32_t T = cfg->trace_log, G = cfg->lde_log, Q = cfg->n_queries, L = cfg->n_fri_layers, C = SSYM_STWO_COLUMNS(cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
     if (T < 2 || G <= T || L != T - 1) return -1;
     const PrTables *tb = pr_tables(T, G);
     if (!tb) return -1;
@@ -185,21 +194,21 @@ EXPORT int oracle_stwo_prove_one(const ssym_stwo_config_t *cfg, uint64_t seed, u
     int keep_fail = t_fail;
 
     /* 1. trace -> coefficients -> LDE */
-    uint32_t *tcoef[4], *tlde[4];
-    for (int c = 0; c < 4; c++) { tcoef[c] = (uint32_t *)malloc(4u * NT); tlde[c] = (uint32_t *)calloc(NG, 4); }
+    uint32_t *tcoef[SSYM_MAX_COLUMNS], *tlde[SSYM_MAX_COLUMNS];
+    for (uint32_t c = 0; c < C; c++) { tcoef[c] = (uint32_t *)malloc(4u * NT); tlde[c] = (uint32_t *)calloc(NG, 4); }
     for (uint32_t r = 0; r < NT; r++) {
-        uint32_t c0 = 1, c1 = (uint32_t)(pr_splitmix(seed, r) >> 33) % M31_MODULUS;
-        uint32_t c2 = fadd(fmul(c0, c0), fmul(c1, c1)), c3 = fadd(fmul(c1, c1), fmul(c2, c2));
-        tcoef[0][r] = c0; tcoef[1][r] = c1; tcoef[2][r] = c2; tcoef[3][r] = c3;
+        uint32_t row[SSYM_MAX_COLUMNS];
+        pr_trace_row(seed, r, C, row);
+        for (uint32_t c = 0; c < C; c++) tcoef[c][r] = row[c];
     }
-    for (int c = 0; c < 4; c++) {
+    for (uint32_t c = 0; c < C; c++) {
         pr_ifft(&tb->tr, tcoef[c]);
         memcpy(tlde[c], tcoef[c], 4u * NT);
         pr_fft(&tb->lde, tlde[c]);
     }
     /* 2. trace tree (hasher.simf:85-90 leaves) */
     uint32_t *tree_t = (uint32_t *)malloc(32u * 2 * NG), *tree_c = (uint32_t *)malloc(32u * 2 * NG);
-    for (uint32_t q = 0; q < NG; q++) { uint32_t w[4] = {tlde[0][q], tlde[1][q], tlde[2][q], tlde[3][q]}; pr_sha_words(w, 4, tree_t + 8 * (size_t)(NG + q)); }
+    for (uint32_t q = 0; q < NG; q++) { uint32_t w[SSYM_MAX_COLUMNS]; for (uint32_t c = 0; c < C; c++) w[c] = tlde[c][q]; pr_sha_words(w, C, tree_t + 8 * (size_t)(NG + q)); }
     pr_tree_build(tree_t, G);
     /* 3. channel: evals/commit.simf:20-35 */
     u256 commitments[3];
@@ -209,14 +218,19 @@ EXPORT int oracle_stwo_prove_one(const ssym_stwo_config_t *cfg, uint64_t seed, u
     channel_mix_u256(&st, commitments[0]);
     channel_mix_u256(&st, commitments[1]);
     QM31 cp_alpha = channel_draw_qm31(&st);
-    uint32_t al[4]; qm31_to_w(cp_alpha, al);
+    uint32_t al[SSYM_MAX_COLUMNS][4]; /* al[j] = the four coordinates of cp_alpha^j: constraint i is weighted by alpha^(C-1-i) */
+    { QM31 pw = qm31_one(); for (uint32_t j = 0; j + 2 < C; j++) { qm31_to_w(qcanon(pw), al[j]); pw = qm31_mul(pw, cp_alpha); } }
     /* 4. composition polynomial on the LDE domain, per QM31 coordinate; interpolate; split by the low two coefficient-index bits */
     uint32_t *cpc[4], *cplde[16];
     for (int k = 0; k < 4; k++) cpc[k] = (uint32_t *)malloc(4u * NG);
     for (uint32_t q = 0; q < NG; q++) {
-        uint32_t c0 = tlde[0][q], c1 = tlde[1][q], c2 = tlde[2][q], c3 = tlde[3][q];
-        uint32_t k2 = fsub(c2, fadd(fmul(c1, c1), fmul(c0, c0))), k3 = fsub(c3, fadd(fmul(c2, c2), fmul(c1, c1)));
-        for (int k = 0; k < 4; k++) cpc[k][q] = fmul(fadd(fmul(al[k], k2), k == 0 ? k3 : 0), tb->vanish_inv[q]);
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (uint32_t i = 2; i < C; i++) {
+            uint32_t a = tlde[i - 2][q], b = tlde[i - 1][q];
+            uint32_t ki = fsub(tlde[i][q], fadd(fmul(b, b), fmul(a, a)));
+            for (int k = 0; k < 4; k++) acc[k] = fadd(acc[k], fmul(al[C - 1 - i][k], ki));
+        }
+        for (int k = 0; k < 4; k++) cpc[k][q] = fmul(acc[k], tb->vanish_inv[q]);
     }
     int degree_ok = 1;
     for (int k = 0; k < 4; k++) {
@@ -242,28 +256,28 @@ EXPORT int oracle_stwo_prove_one(const ssym_stwo_config_t *cfg, uint64_t seed, u
     QM31 tw[32];
     tw[0] = P.y; tw[1] = P.x;
     for (uint32_t k = 2; k < 32; k++) tw[k] = qm31_point_dbl_x(tw[k - 1]);
-    QM31 oods_trace[4], oods_cp[16];
-    for (int c = 0; c < 4; c++) oods_trace[c] = pr_eval_at(tcoef[c], 1, T, tw);
+    QM31 oods_trace[SSYM_MAX_COLUMNS], oods_cp[16];
+    for (uint32_t c = 0; c < C; c++) oods_trace[c] = pr_eval_at(tcoef[c], 1, T, tw);
     QM31 tw2[32];
     tw2[0] = P2.x;
     for (uint32_t k = 1; k < 32; k++) tw2[k] = qm31_point_dbl_x(tw2[k - 1]);
     for (int k = 0; k < 4; k++)
         for (int p = 0; p < 4; p++) oods_cp[4 * k + p] = pr_eval_at(cpc[k] + p, 4, T - 1, tw2); /* m < 2^(T-1) covers 4m+p <= 2^T */
-    channel_mix_oods_evals(&st, oods_trace, oods_cp);
+    channel_mix_oods_evals(&st, oods_trace, C, oods_cp);
     QM31 deep_alpha = channel_draw_qm31(&st);
     /* 6. DEEP quotient on the whole LDE domain = fri_answer of every position (Appendix A item 1) */
     QM31 *h = (QM31 *)malloc(sizeof(QM31) * NG);
     {
-        LineCoeffs ka[16], kb[4];
+        LineCoeffs ka[16], kb[SSYM_MAX_COLUMNS];
         QM31 alpha_i = deep_alpha;
         QM31 sa_a = qm31_zero(), sa_c = qm31_zero(), sb_a = qm31_zero(), sb_c = qm31_zero();
         for (int c = 0; c < 16; c++) { ka[c] = deep_quotient_interpolant_coefficients(P2, oods_cp[c], alpha_i); sa_a = qm31_add(sa_a, ka[c].a); sa_c = qm31_add(sa_c, ka[c].c); alpha_i = qm31_mul(alpha_i, deep_alpha); }
-        for (int c = 0; c < 4; c++) { kb[c] = deep_quotient_interpolant_coefficients(P, oods_trace[c], alpha_i); sb_a = qm31_add(sb_a, kb[c].a); sb_c = qm31_add(sb_c, kb[c].c); alpha_i = qm31_mul(alpha_i, deep_alpha); }
+        for (uint32_t c = 0; c < C; c++) { kb[c] = deep_quotient_interpolant_coefficients(P, oods_trace[c], alpha_i); sb_a = qm31_add(sb_a, kb[c].a); sb_c = qm31_add(sb_c, kb[c].c); alpha_i = qm31_mul(alpha_i, deep_alpha); }
         for (uint32_t q = 0; q < NG; q++) {
             M31Point dp = tb->lde.pt[q];
             QM31 na = qm31_zero(), nb = qm31_zero();
             for (int c = 0; c < 16; c++) na = qm31_add(na, qm31_mul_m31(ka[c].b, cplde[c][q]));
-            for (int c = 0; c < 4; c++) nb = qm31_add(nb, qm31_mul_m31(kb[c].b, tlde[c][q]));
+            for (uint32_t c = 0; c < C; c++) nb = qm31_add(nb, qm31_mul_m31(kb[c].b, tlde[c][q]));
             na = qm31_sub(na, qm31_add(qm31_mul_m31(sa_a, dp.y), sa_c));
             nb = qm31_sub(nb, qm31_add(qm31_mul_m31(sb_a, dp.y), sb_c));
             h[q] = qcanon(qm31_add(qm31_mul_cm31(na, deep_quotient_denominator_inverse(P2, dp)), qm31_mul_cm31(nb, deep_quotient_denominator_inverse(P, dp))));
@@ -313,16 +327,16 @@ EXPORT int oracle_stwo_prove_one(const ssym_stwo_config_t *cfg, uint64_t seed, u
         for (uint32_t j = 0; j < 8 && q + j < Q; j++) queries[q + j] = w.w[j] & (NG - 1);
     }
     for (int i = 0; i < 3; i++) store_u256(out + lo.off_commit + 8 * i, commitments[i]);
-    for (int c = 0; c < 4; c++) qm31_to_w(oods_trace[c], out + lo.off_oods_trace + 4 * c);
+    for (uint32_t c = 0; c < C; c++) qm31_to_w(oods_trace[c], out + lo.off_oods_trace + 4 * c);
     for (int c = 0; c < 16; c++) qm31_to_w(oods_cp[c], out + lo.off_oods_cp + 4 * c);
     qm31_to_w(last_coeff, out + lo.off_last_coeff);
     out[lo.off_pow_nonce] = (uint32_t)(nonce >> 32);
     out[lo.off_pow_nonce + 1] = (uint32_t)nonce;
     for (uint32_t qi = 0; qi < Q; qi++) {
         uint32_t q = queries[qi];
-        uint32_t *qv = out + lo.off_qvals + 20 * qi;
-        for (int c = 0; c < 4; c++) qv[c] = tlde[c][q];
-        for (int c = 0; c < 16; c++) qv[4 + c] = cplde[c][q];
+        uint32_t *qv = out + lo.off_qvals + QV * qi;
+        for (uint32_t c = 0; c < C; c++) qv[c] = tlde[c][q];
+        for (int c = 0; c < 16; c++) qv[C + c] = cplde[c][q];
         uint32_t node = NG + q;
         for (uint32_t lev = 0; lev < G; lev++, node >>= 1) {
             memcpy(out + lo.off_trace_sib + (qi * G + lev) * 8, tree_t + 8 * (size_t)(node ^ 1), 32);
@@ -337,7 +351,8 @@ EXPORT int oracle_stwo_prove_one(const ssym_stwo_config_t *cfg, uint64_t seed, u
             fq >>= 1;
         }
     }
-    for (int c = 0; c < 4; c++) { free(tcoef[c]); free(tlde[c]); free(cpc[c]); }
+    for (uint32_t c = 0; c < C; c++) { free(tcoef[c]); free(tlde[c]); }
+    for (int k = 0; k < 4; k++) free(cpc[k]);
     for (int c = 0; c < 16; c++) free(cplde[c]);
     for (uint32_t l = 0; l <= L; l++) free(ftree[l]);
     for (uint32_t l = 0; l <= L + 1; l++) free(fev[l]);
@@ -358,8 +373,5 @@ EXPORT int oracle_stwo_prove_batch(const ssym_stwo_config_t *cfg, const uint64_t
 }
 
 /* The trace row of a seed (what both provers commit to), for tests. */
-EXPORT void oracle_stwo_trace_row(uint64_t seed, uint32_t row, uint32_t out[4]) {
-    uint32_t c0 = 1, c1 = (uint32_t)(pr_splitmix(seed, row) >> 33) % M31_MODULUS;
-    uint32_t c2 = fadd(fmul(c0, c0), fmul(c1, c1)), c3 = fadd(fmul(c1, c1), fmul(c2, c2));
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
+EXPORT void oracle_stwo_trace_row(uint64_t seed, uint32_t row, uint32_t out[4]) { pr_trace_row(seed, row, SSYM_NUM_COLUMNS, out); }
+EXPORT void oracle_stwo_trace_row_n(uint64_t seed, uint32_t row, uint32_t n_columns, uint32_t *out) { pr_trace_row(seed, row, n_columns, out); }

@@ -154,12 +154,12 @@ def _align8(w: int) -> int:
     return (w + 7) & ~7
 
 
-def stwo_layout(n_queries: int, n_fri_layers: int, lde_log: int) -> Dict[str, Any]:
-    Q, L, G = n_queries, n_fri_layers, lde_log
+def stwo_layout(n_queries: int, n_fri_layers: int, lde_log: int, n_columns: int = 4) -> Dict[str, Any]:
+    Q, L, G, NC = n_queries, n_fri_layers, lde_log, n_columns
     lo: Dict[str, Any] = {}
     w = 0
     lo["commit"] = w; w += 24
-    lo["oods_trace"] = w; w += 16
+    lo["oods_trace"] = w; w += 4 * NC
     lo["oods_cp"] = w; w += 64
     lo["fri_first_root"] = w; w += 8
     lo["fri_inner_root"] = w; w += 8 * L
@@ -167,7 +167,7 @@ def stwo_layout(n_queries: int, n_fri_layers: int, lde_log: int) -> Dict[str, An
     lo["pow_nonce"] = w; w += 2
     alg = w
     w = _align8(w)
-    lo["qvals"] = w; w += Q * 20; alg += Q * 20; w = _align8(w)
+    lo["qvals"] = w; w += Q * (NC + 16); alg += Q * (NC + 16); w = _align8(w)
     lo["trace_sib"] = w; w += Q * G * 8; alg += Q * G * 8
     lo["cp_sib"] = w; w += Q * G * 8; alg += Q * G * 8
     lo["fri_wit"] = w; w += (L + 1) * Q * 4; alg += (L + 1) * Q * 4; w = _align8(w)
@@ -181,10 +181,10 @@ def stwo_layout(n_queries: int, n_fri_layers: int, lde_log: int) -> Dict[str, An
     return lo
 
 
-def pack_stwo(wit: Dict[str, Any], n_queries: int, n_fri_layers: int, lde_log: int) -> Tuple[np.ndarray, bool]:
-    """Pack the six witnesses of stwo-verifier/src/main.simf:9-25.  Returns (words, shape_reject)."""
-    Q, L, G = n_queries, n_fri_layers, lde_log
-    lo = stwo_layout(Q, L, G)
+def pack_stwo(wit: Dict[str, Any], n_queries: int, n_fri_layers: int, lde_log: int, n_columns: int = 4) -> Tuple[np.ndarray, bool]:
+    """Pack the six witnesses of stwo-verifier/src/main.simf:9-25 (n_columns = NUM_COLUMNS, config.simf:14).  Returns (words, shape_reject)."""
+    Q, L, G, NC = n_queries, n_fri_layers, lde_log, n_columns
+    lo = stwo_layout(Q, L, G, NC)
     out = np.zeros(lo["stride_words"], dtype=np.uint32)
     shape_reject = False
 
@@ -197,7 +197,7 @@ def pack_stwo(wit: Dict[str, Any], n_queries: int, n_fri_layers: int, lde_log: i
     for i, r in enumerate(_tuple(wit["COMMITMENTS"], 3)):
         put(lo["commit"] + 8 * i, u256_words(r))
     oods_trace, oods_cp = _tuple(wit["OODS_EVALS"], 2)
-    for i, col in enumerate(_array(oods_trace, 4)):
+    for i, col in enumerate(_array(oods_trace, NC)):
         put(lo["oods_trace"] + 4 * i, _qm31(_array(col, 1)[0]))
     for i, v in enumerate(_array(oods_cp, 16)):
         put(lo["oods_cp"] + 4 * i, _qm31(v))
@@ -211,8 +211,8 @@ def pack_stwo(wit: Dict[str, Any], n_queries: int, n_fri_layers: int, lde_log: i
 
     for q, dec in enumerate(_array(wit["DECOMMITMENTS"], Q)):
         (tvals, tproof), (cvals, cproof) = (_tuple(x, 2) for x in _tuple(dec, 2))
-        put(lo["qvals"] + 20 * q, [_uint(_array(c, 1)[0], 32) for c in _array(tvals, 4)])
-        put(lo["qvals"] + 20 * q + 4, [_uint(v, 32) for v in _array(cvals, 16)])
+        put(lo["qvals"] + (NC + 16) * q, [_uint(_array(c, 1)[0], 32) for c in _array(tvals, NC)])
+        put(lo["qvals"] + (NC + 16) * q + NC, [_uint(v, 32) for v in _array(cvals, 16)])
         for name, proof in (("trace_sib", tproof), ("cp_sib", cproof)):
             proof = _list32(proof)
             if len(proof) != G:

@@ -23,7 +23,7 @@ class SsymError(RuntimeError):
 
 class StwoConfig(C.Structure):
     _fields_ = [("trace_log", C.c_uint32), ("lde_log", C.c_uint32), ("n_queries", C.c_uint32), ("n_fri_layers", C.c_uint32),
-                ("mode", C.c_uint32), ("reserved", C.c_uint32), ("pow_target", C.c_uint64)]
+                ("mode", C.c_uint32), ("n_columns", C.c_uint32), ("pow_target", C.c_uint64)]
 
 
 class StwoLayout(C.Structure):

@@ -123,7 +123,7 @@ struct ssym_ctx {
     DevBuf wit_skel, wit_slots, wit_text[2], wit_offs[2], wit_packed[2], wit_flags[2], wit_numpos[2];
     uint32_t wit_total_slots = 0;
     WitTables wit_tab{};
-    uint32_t wit_Q = 0, wit_L = 0xffffffffu, wit_G = 0;
+    uint32_t wit_Q = 0, wit_L = 0xffffffffu, wit_G = 0, wit_C = 0;
     uint32_t *wit_hflags[2] = {nullptr, nullptr};
     uint64_t *wit_hoffs[2] = {nullptr, nullptr};
     size_t wit_hcap = 0;
@@ -274,9 +274,9 @@ int ssym_stwo_config_preset(const char *name, uint32_t mode, ssym_stwo_config_t 
     out->mode = mode;
     out->pow_target = 0x07ffffffffffffffull; // config.simf:32,51
     if (!strcmp(name, "prod")) { // config.simf:34-52
-        out->trace_log = 9; out->lde_log = 13; out->n_queries = 16; out->n_fri_layers = 8;
+        out->trace_log = 9; out->lde_log = 13; out->n_queries = 16; out->n_fri_layers = 8; out->n_columns = SSYM_NUM_COLUMNS;
     } else if (!strcmp(name, "testing")) { // config.simf:16-33
-        out->trace_log = 3; out->lde_log = 4; out->n_queries = 1; out->n_fri_layers = 2;
+        out->trace_log = 3; out->lde_log = 4; out->n_queries = 1; out->n_fri_layers = 2; out->n_columns = SSYM_NUM_COLUMNS;
     } else {
         return fail(SSYM_ERR_USAGE, "unknown preset (prod | testing)");
     }
@@ -287,20 +287,21 @@ static uint32_t align8(uint32_t w) { return (w + 7u) & ~7u; }
 
 int ssym_stwo_layout(const ssym_stwo_config_t *cfg, ssym_stwo_layout_t *o) {
     if (!cfg || !o) return fail(SSYM_ERR_USAGE, "NULL argument");
-    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log;
+    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg);
     if (Q < 1 || Q > SSYM_MAX_QUERIES || L + 1 > SSYM_MAX_FRI_LAYERS || G < L + 1 || G > 30 || cfg->mode > 1 || cfg->trace_log > 255)
         return fail(SSYM_ERR_USAGE, "unsupported Stwo configuration");
+    if (C != 4 && C != 8 && C != 16) return fail(SSYM_ERR_USAGE, "n_columns must be 4, 8 or 16 (0 = 4)");
     memset(o, 0, sizeof *o);
     uint32_t w = 0, alg = 0;
     o->off_commit = w; w += 24;
-    o->off_oods_trace = w; w += 16;
+    o->off_oods_trace = w; w += 4 * C;
     o->off_oods_cp = w; w += 64;
     o->off_fri_first_root = w; w += 8;
     o->off_fri_inner_root = w; w += 8 * L;
     o->off_last_coeff = w; w += 4;
     o->off_pow_nonce = w; w += 2;
     alg += w; w = align8(w);
-    o->off_qvals = w; w += Q * 20; alg += Q * 20; w = align8(w);
+    o->off_qvals = w; w += Q * (C + 16); alg += Q * (C + 16); w = align8(w);
     o->off_trace_sib = w; w += Q * G * 8; alg += Q * G * 8;
     o->off_cp_sib = w; w += Q * G * 8; alg += Q * G * 8;
     o->off_fri_wit = w; w += (L + 1) * Q * 4; alg += (L + 1) * Q * 4; w = align8(w);
@@ -515,31 +516,31 @@ struct WitSkeleton {
 };
 
 void build_wit_skeleton(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, WitSkeleton &w) {
-    const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers, G = cfg.lde_log;
+    const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers, G = cfg.lde_log, C = SSYM_STWO_COLUMNS(&cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
     w.begin(0); // COMMITMENTS: (u256, u256, u256)
     w.t("(");
     for (uint32_t i = 0; i < 3; i++) { if (i) w.t(","); w.num(lo.off_commit + 8 * i, WIT_KIND_U256); }
     w.t(")");
     w.end();
-    w.begin(1); // DECOMMITMENTS: [(([[u32; 1]; 4], List<u256, 32>), ([u32; 16], List<u256, 32>)); Q]
+    w.begin(1); // DECOMMITMENTS: [(([[u32; 1]; C], List<u256, 32>), ([u32; 16], List<u256, 32>)); Q]
     w.t("[");
     for (uint32_t q = 0; q < Q; q++) {
         if (q) w.t(",");
         w.t("(([");
-        for (uint32_t i = 0; i < SSYM_NUM_COLUMNS; i++) { if (i) w.t(","); w.t("["); w.num(lo.off_qvals + 20 * q + i, WIT_KIND_U32); w.t("]"); }
+        for (uint32_t i = 0; i < C; i++) { if (i) w.t(","); w.t("["); w.num(lo.off_qvals + QV * q + i, WIT_KIND_U32); w.t("]"); }
         w.t("],");
         w.digest_list(lo.off_trace_sib + q * G * 8, G);
         w.t("),([");
-        for (uint32_t i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) { if (i) w.t(","); w.num(lo.off_qvals + 20 * q + 4 + i, WIT_KIND_U32); }
+        for (uint32_t i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) { if (i) w.t(","); w.num(lo.off_qvals + QV * q + C + i, WIT_KIND_U32); }
         w.t("],");
         w.digest_list(lo.off_cp_sib + q * G * 8, G);
         w.t("))");
     }
     w.t("]");
     w.end();
-    w.begin(2); // OODS_EVALS: ([[QM31; 1]; 4], [QM31; 16])
+    w.begin(2); // OODS_EVALS: ([[QM31; 1]; C], [QM31; 16])
     w.t("([");
-    for (uint32_t i = 0; i < SSYM_NUM_COLUMNS; i++) { if (i) w.t(","); w.t("["); w.qm31(lo.off_oods_trace + 4 * i); w.t("]"); }
+    for (uint32_t i = 0; i < C; i++) { if (i) w.t(","); w.t("["); w.qm31(lo.off_oods_trace + 4 * i); w.t("]"); }
     w.t("],[");
     for (uint32_t i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) { if (i) w.t(","); w.qm31(lo.off_oods_cp + 4 * i); }
     w.t("])");
@@ -595,7 +596,7 @@ extern "C" int ssym_stwo_wit_skeleton(const ssym_stwo_config_t *cfg, int name, u
 }
 
 static int ensure_wit_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo) {
-    if (c->wit_Q == cfg.n_queries && c->wit_L == cfg.n_fri_layers && c->wit_G == cfg.lde_log) return SSYM_OK;
+    if (c->wit_Q == cfg.n_queries && c->wit_L == cfg.n_fri_layers && c->wit_G == cfg.lde_log && c->wit_C == SSYM_STWO_COLUMNS(&cfg)) return SSYM_OK;
     WitSkeleton w;
     build_wit_skeleton(cfg, lo, w);
     CUDA_TRY(cudaStreamSynchronize(c->stream)); // the old tables may still be in use
@@ -612,7 +613,7 @@ static int ensure_wit_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg, const s
     static const char *const stwo_names[WIT_NAMES] = {"COMMITMENTS", "DECOMMITMENTS", "OODS_EVALS", "FRI_COMMITMENTS", "FRI_DECOMMITMENTS", "POW_NONCE"};
     wit_set_names(c->wit_tab, stwo_names, WIT_NAMES);
     c->wit_total_slots = (uint32_t)w.slots.size();
-    c->wit_Q = cfg.n_queries; c->wit_L = cfg.n_fri_layers; c->wit_G = cfg.lde_log;
+    c->wit_Q = cfg.n_queries; c->wit_L = cfg.n_fri_layers; c->wit_G = cfg.lde_log; c->wit_C = SSYM_STWO_COLUMNS(&cfg);
     return SSYM_OK;
 }
 
@@ -1083,6 +1084,7 @@ extern "C" int ssym_stwo_prove_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cf
     const uint32_t T = cfg->trace_log, G = cfg->lde_log, L = cfg->n_fri_layers;
     if (T < 2 || G <= T || G > SSYM_PRV_MAX_LOG || L != T - 1)
         return fail(SSYM_ERR_USAGE, "prover needs 2 <= trace_log < lde_log <= 13 and n_fri_layers == trace_log - 1 (both presets of config.simf do)");
+    if (SSYM_STWO_COLUMNS(cfg) != SSYM_NUM_COLUMNS) return fail(SSYM_ERR_USAGE, "the GPU prover is built for NUM_COLUMNS = 4 (config.simf:14)");
     if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
     if (n == 0) return SSYM_OK;
     CUDA_TRY(cudaSetDevice(c->device));

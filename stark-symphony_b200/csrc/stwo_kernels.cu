@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
     uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
     ssym_stwo_trace_t *tr = p.trace ? p.trace + i : nullptr;
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
+    const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg), NCOL = C + SSYM_NUM_CP_PARTITIONS; // columns entering the DEEP quotient
     uint32_t status = 0;
     bool exhausted = false;
 
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
     }
     // oods: draw the point parameter t, absorb the samples, draw the DEEP alpha    deep/oods.simf:44-64
     const QM31 oods_t = channel_draw_qm31(ch, exhausted); // channel.simf:143-144
-    channel_mix(ch, pk + lo.off_oods_trace, 80);                     // 4 trace + 16 CP samples are contiguous in the packed header
+    channel_mix(ch, pk + lo.off_oods_trace, 4 * NCOL);               // C trace + 16 CP samples are contiguous in the packed header
     const QM31 deep_alpha = channel_draw_qm31(ch, exhausted);
     qm31_store4(ctx + CX::DEEP_ALPHA, deep_alpha);
     if (tr) {
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
         QM31 acc = qm31_zero(), a = qm31_zero(), b = qm31_zero();
         uint32_t skip_2 = 0;
 #pragma unroll 1
-        for (int col = 0; col < SSYM_NUM_COLUMNS; col++) {
+        for (uint32_t col = 0; col < C; col++) {
             const QM31 c = qm31_load4(pk + lo.off_oods_trace + 4 * col);
             if (skip_2 == 2) {
                 const QM31 constraint = qm31_sub(c, qm31_add(qm31_mul_nl(b, b), qm31_mul_nl(a, a)));
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
     }
     qm31_store4(ctx + CX::PX, px);
     qm31_store4(ctx + CX::PY, py);
-    if (p.cfg.mode == SSYM_MODE_REF_LITERAL) { // all 20 columns are sampled at P (fri/answers.simf:116-125)
+    if (p.cfg.mode == SSYM_MODE_REF_LITERAL) { // all C + 16 columns are sampled at P (fri/answers.simf:116-125)
         qm31_store4(ctx + CX::P2X, px);
         qm31_store4(ctx + CX::P2Y, py);
     } else { // the 16 CP partitions are sampled at 2*P
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
     { // alpha^(k+1): the running product of fri/answers.simf:52,70
         QM31 a = deep_alpha;
 #pragma unroll 1
-        for (uint32_t k = 0; k <= 20; k++) {
+        for (uint32_t k = 0; k <= NCOL; k++) {
             qm31_store4(ctx + CX::ALPHA_POW + 4 * k, a);
             a = qm31_mul_nl(a, deep_alpha);
         }
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p) {
 
 // ------------------------------------------------------------------------------------------
 // K2: the per-query field arithmetic of verify_proof, one warp per proof (the per-proof scalars are K1's):
-//   phase B  lane k < 20: DEEP line coefficients of column k with alpha^(k+1) (deep/quotients.simf:25-35); the
+//   phase B  lane k < C + 16: DEEP line coefficients of column k with alpha^(k+1) (deep/quotients.simf:25-35); the
 //            coefficients depend only on the proof, not on the query, so they are computed once, in parallel
 //   phase C  lane q < Q: fri_answer of query q (fri/answers.simf:97-129) and its 1+L folds (fri/layers.simf:51-78,
 //            fri/folding.simf:15-41); the Merkle halves of those functions are K3
@@ -222,8 +223,11 @@ __device__ __forceinline__ QM31 batch_numerator(const uint32_t *bcoef, const uin
 }
 
 #define K2_WARPS 4
+template <int C> // NUM_COLUMNS (config.simf:14): the DEEP quotient runs over NCOL = C + 16 <= 32 columns, one lane each
 __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams p) { // <= 64 registers: a CTA fits the slot a Merkle CTA frees
-    __shared__ __align__(16) uint32_t s_b[K2_WARPS][20 * 4];
+    constexpr int NCOL = C + SSYM_NUM_CP_PARTITIONS;
+    static_assert(NCOL <= 32 && C % 4 == 0, "one lane per column; the per-query values are read as uint4");
+    __shared__ __align__(16) uint32_t s_b[K2_WARPS][NCOL * 4];
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * K2_WARPS + wib;
@@ -241,20 +245,21 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
 
     // ---- phase B: lane k computes the line coefficients of column k (aggregation order) with alpha^(k+1) ----
     QM31 sum_a_A, sum_c_A, sum_a_B, sum_c_B;
-    const QM31 batch_coeff = qm31_load4(ctx + CX::ALPHA_POW + 4 * 20); // alpha^21
+    const QM31 batch_coeff = qm31_load4(ctx + CX::ALPHA_POW + 4 * NCOL); // alpha^(NCOL + 1)
     {
-        const uint32_t k = lane < 20 ? lane : 19;
+        const uint32_t k = lane < NCOL ? lane : NCOL - 1;
         const QM31 alpha_pow = qm31_load4(ctx + CX::ALPHA_POW + 4 * k);
-        // literal: columns = 4 trace then 16 CP, all at P.  prover-consistent: 16 CP at 2P, then 4 trace at P.
+        // literal: columns = C trace then 16 CP, all at P (the trace samples and the CP samples are contiguous in the header).
+        // prover-consistent: 16 CP at 2P, then C trace at P.
         const bool in_A = literal || k < 16;
         const uint32_t *sv = literal ? pk + lo.off_oods_trace + 4 * k : (k < 16 ? pk + lo.off_oods_cp + 4 * k : pk + lo.off_oods_trace + 4 * (k - 16));
         const LineCoeffs lc = interpolant_coefficients(in_A ? p2y : py, qm31_load4(sv), alpha_pow);
-        if (lane < 20) qm31_store4(&s_b[wib][4 * lane], lc.b);
+        if (lane < NCOL) qm31_store4(&s_b[wib][4 * lane], lc.b);
         const QM31 zero = qm31_zero();
-        sum_a_A = qm31_warp_sum(lane < 20 && in_A ? lc.a : zero);
-        sum_c_A = qm31_warp_sum(lane < 20 && in_A ? lc.c : zero);
-        sum_a_B = qm31_warp_sum(lane < 20 && !in_A ? lc.a : zero);
-        sum_c_B = qm31_warp_sum(lane < 20 && !in_A ? lc.c : zero);
+        sum_a_A = qm31_warp_sum(lane < NCOL && in_A ? lc.a : zero);
+        sum_c_A = qm31_warp_sum(lane < NCOL && in_A ? lc.c : zero);
+        sum_a_B = qm31_warp_sum(lane < NCOL && !in_A ? lc.a : zero);
+        sum_c_B = qm31_warp_sum(lane < NCOL && !in_A ? lc.c : zero);
     }
     __syncwarp();
 
@@ -264,11 +269,11 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
         const uint32_t query = ctx[CX::QUERIES + q];
         const uint2 rp = p.tab.point[query]; // domain point of the query, fri/answers.simf:108-110
         const M31Point R = m31_point(rp.x, rp.y);
-        uint32_t vals[20];
+        uint32_t vals[NCOL];
         {
-            const uint4 *v4 = reinterpret_cast<const uint4 *>(pk + lo.off_qvals + 20 * q); // 80-byte records: 16-byte aligned
+            const uint4 *v4 = reinterpret_cast<const uint4 *>(pk + lo.off_qvals + NCOL * q); // 4 * NCOL-byte records: 16-byte aligned
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
+            for (int k = 0; k < NCOL / 4; k++) {
                 const uint4 v = __ldg(v4 + k);
                 vals[4 * k] = v.x; vals[4 * k + 1] = v.y; vals[4 * k + 2] = v.z; vals[4 * k + 3] = v.w;
             }
@@ -277,13 +282,13 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
         bool inv_fail = false;
         if (literal) {
             const CM31 den_inv = denominator_inverse(px, py, R, inv_fail);
-            const QM31 acc = batch_numerator(s_b[wib], vals, 20, sum_a_A, sum_c_A, R.y);
+            const QM31 acc = batch_numerator(s_b[wib], vals, NCOL, sum_a_A, sum_c_A, R.y);
             eval = qm31_mul(qm31_mul_cm31(acc, den_inv), batch_coeff); // fri/answers.simf:126
         } else {
             const CM31 den_a = denominator_inverse(p2x, p2y, R, inv_fail);
             const CM31 den_b = denominator_inverse(px, py, R, inv_fail);
-            const QM31 num_a = batch_numerator(s_b[wib], vals + 4, 16, sum_a_A, sum_c_A, R.y);
-            const QM31 num_b = batch_numerator(s_b[wib] + 64, vals, 4, sum_a_B, sum_c_B, R.y);
+            const QM31 num_a = batch_numerator(s_b[wib], vals + C, 16, sum_a_A, sum_c_A, R.y);
+            const QM31 num_b = batch_numerator(s_b[wib] + 64, vals, C, sum_a_B, sum_c_B, R.y);
             eval = qm31_add(qm31_mul_cm31(num_a, den_a), qm31_mul_cm31(num_b, den_b));
         }
         if (inv_fail) {
@@ -364,8 +369,9 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
     uint32_t n_sib, n_pre, path, fail_bit, layer = 0;
     bool fri_even = true;
     int kind; // 0 trace, 1 cp, 2 fri
+    const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg); // trace leaf = C words (hasher.simf:85-90): 4 / 8 in one block, 16 = a 64-byte message like the CP leaf
     if (rank == 0 || rank == 2) {
-        msg = pk + lo.off_qvals + 20 * q + (rank == 0 ? 4 : 0);
+        msg = pk + lo.off_qvals + (C + SSYM_NUM_CP_PARTITIONS) * q + (rank == 0 ? C : 0);
         if (rank == 2) {
             kind = 0;
             sib = pk + lo.off_trace_sib + q * G * 8;
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
         uint32_t w[16];
         bool two_blocks = true; // 64-byte message: data block + the constant padding block
         if (step < n_pre) {
-            if (kind == 1) {
+            if (kind == 1 || (kind == 0 && C == 16)) { // a 64-byte leaf: 16 composition values, or 16 trace columns
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(msg) + k);
@@ -417,10 +423,14 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
                 const bool take_eval = kind == 2 && ((step == 0) == fri_even);
                 const uint4 v = take_eval ? *reinterpret_cast<const uint4 *>(evp) : __ldg(reinterpret_cast<const uint4 *>(msg));
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-                w[4] = 0x80000000u;
+                uint4 v2 = make_uint4(0x80000000u, 0u, 0u, 0u); // FIPS 180-4 padding right after a 16-byte message ...
+                const bool wide = kind == 0 && C == 8;          // ... or after the 32 bytes of an 8-column trace leaf
+                if (wide) v2 = __ldg(reinterpret_cast<const uint4 *>(msg) + 1);
+                w[4] = v2.x; w[5] = v2.y; w[6] = v2.z; w[7] = v2.w;
+                w[8] = wide ? 0x80000000u : 0u;
 #pragma unroll
-                for (int k = 5; k < 15; k++) w[k] = 0;
-                w[15] = 128u;
+                for (int k = 9; k < 15; k++) w[k] = 0;
+                w[15] = wide ? 256u : 128u;
                 two_blocks = false;
                 if (kind == 2 && step == 1) {
 #pragma unroll
@@ -581,9 +591,10 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
     uint32_t n_pre, path, layer = 0, depth;
     bool fri_even = true;
     int kind;
+    const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg);
     if (tree < 2) {
         kind = (int)tree;
-        msg = pk + lo.off_qvals + 20 * q + (tree == 1 ? 4 : 0);
+        msg = pk + lo.off_qvals + (C + SSYM_NUM_CP_PARTITIONS) * q + (tree == 1 ? C : 0);
         sib = pk + (tree == 0 ? lo.off_trace_sib : lo.off_cp_sib) + q * G * 8;
         n_pre = 1;
         path = query;
@@ -619,7 +630,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
         uint32_t w[16];
         bool two_blocks = true;
         if (step < n_pre) {
-            if (kind == 1) {
+            if (kind == 1 || (kind == 0 && C == 16)) { // a 64-byte leaf: 16 composition values, or 16 trace columns
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(msg) + k);
@@ -632,10 +643,14 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kern
                 const bool take_eval = kind == 2 && ((step == 0) == fri_even);
                 const uint4 v = take_eval ? *reinterpret_cast<const uint4 *>(evp) : __ldg(reinterpret_cast<const uint4 *>(msg));
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-                w[4] = 0x80000000u;
+                uint4 v2 = make_uint4(0x80000000u, 0u, 0u, 0u); // FIPS 180-4 padding right after a 16-byte message ...
+                const bool wide = kind == 0 && C == 8;          // ... or after the 32 bytes of an 8-column trace leaf
+                if (wide) v2 = __ldg(reinterpret_cast<const uint4 *>(msg) + 1);
+                w[4] = v2.x; w[5] = v2.y; w[6] = v2.z; w[7] = v2.w;
+                w[8] = wide ? 0x80000000u : 0u;
 #pragma unroll
-                for (int k = 5; k < 15; k++) w[k] = 0;
-                w[15] = 128u;
+                for (int k = 9; k < 15; k++) w[k] = 0;
+                w[15] = wide ? 256u : 128u;
                 two_blocks = false;
                 if (kind == 2 && step == 1) {
 #pragma unroll
@@ -716,8 +731,9 @@ __global__ void __launch_bounds__(256) stwo_check_kernel(StwoParams p) {
         const uint32_t *b0 = even_l ? ev + 4 * lead : wl, *b1 = even_l ? wl : ev + 4 * lead;
         for (int j = 0; j < 4; j++) valid = valid && a0[j] == b0[j] && a1[j] == b1[j];
     } else {
-        const uint32_t nw = kind == 0 ? 4u : 16u, o = kind == 0 ? 0u : 4u;
-        for (uint32_t j = 0; j < nw; j++) valid = valid && pk[lo.off_qvals + 20 * q + o + j] == pk[lo.off_qvals + 20 * lead + o + j];
+        const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
+        const uint32_t nw = kind == 0 ? C : 16u, o = kind == 0 ? 0u : C;
+        for (uint32_t j = 0; j < nw; j++) valid = valid && pk[lo.off_qvals + QV * q + o + j] == pk[lo.off_qvals + QV * lead + o + j];
     }
     const uint4 *sq = reinterpret_cast<const uint4 *>(sib0 + q * d * 8), *sr = reinterpret_cast<const uint4 *>(sib0 + lead * d * 8);
     uint32_t diff = 0; // branch-free so that the loads of all levels are in flight together
@@ -788,7 +804,7 @@ size_t stwo_dedup_layout(const ssym_stwo_config_t &cfg, size_t cap, StwoDedup &d
                     else trees += (kind == tk && steps == d) ? 1u : 0u;                      // same leaf: the whole path
                 }
                 if (!trees || (round == 0 && kind == 3)) continue;
-                const uint32_t pre = kind == 0 ? 1u : kind == 1 ? 2u : kind == 2 ? 4u : 0u;
+                const uint32_t pre = kind == 0 ? (SSYM_STWO_COLUMNS(&cfg) == 16 ? 2u : 1u) : kind == 1 ? 2u : kind == 2 ? 4u : 0u;
                 if (nb == STWO_DEDUP_MAX_BINS) return 0;
                 bins[nb++] = B{kind, steps, pre + 2u * steps, (uint32_t)(trees * Q * cap)};
             }
@@ -898,7 +914,11 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     if (use_front && front_kernels < 2) { cudaEventRecord(front_done, front); cudaStreamWaitEvent(s, front_done, 0); }
     if (prof) { prof->end(0, s); prof->begin(1, s); }
     const uint32_t items = p.n * Q;
-    stwo_query_kernel<<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p);
+    switch (SSYM_STWO_COLUMNS(&p.cfg)) { // ssym_stwo_layout admits 4, 8, 16
+    case 8: stwo_query_kernel<8><<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p); break;
+    case 16: stwo_query_kernel<16><<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p); break;
+    default: stwo_query_kernel<SSYM_NUM_COLUMNS><<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p); break;
+    }
     if (p.dd.enabled) { // decided by the caller (ssym_set_merkle_sharing)
         // shared-node schedule: plan (on the front stream with K1 / K2 when pipelined), hash the distinct nodes, check the followers, hash
         // what did not match, resolve every query

@@ -34,8 +34,8 @@ struct StwoCtxLayout {
         PY = 64,         // [4]
         P2X = 68,        // [4]    sample point of the 16 CP columns: P (REF_LITERAL) or 2P (PROVER_CONSISTENT, Appendix A item 1)
         P2Y = 72,        // [4]
-        ALPHA_POW = 76,  // [21][4] deep_alpha^(k+1), k = 0..20 (k = 20: the batch coefficient of fri/answers.simf:126)
-        WORDS = 160
+        ALPHA_POW = 76,  // [C + 17][4] deep_alpha^(k+1), k = 0..C+16 (the last: the batch coefficient of fri/answers.simf:126); C <= 16
+        WORDS = 76 + 4 * (SSYM_MAX_COLUMNS + SSYM_NUM_CP_PARTITIONS + 1)
     };
 };
 

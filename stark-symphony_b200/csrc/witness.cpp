@@ -289,7 +289,7 @@ extern "C" int ssym_stwo_pack_wit(const ssym_stwo_config_t *cfg, const char *jso
     ssym_stwo_layout_t lo;
     int rc = ssym_stwo_layout(cfg, &lo);
     if (rc) return rc;
-    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log;
+    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
     memset(out, 0, (size_t)lo.stride_words * 4);
     bool reject = false;
     try {
@@ -297,8 +297,8 @@ extern "C" int ssym_stwo_pack_wit(const ssym_stwo_config_t *cfg, const char *jso
         const Val &com = tuple_of(need(w, "COMMITMENTS"), 3, "COMMITMENTS"); // evals/commit.simf:16
         for (int i = 0; i < 3; i++) put_u256(out + lo.off_commit + 8 * i, com.items[i], "COMMITMENTS");
         const Val &oods = tuple_of(need(w, "OODS_EVALS"), 2, "OODS_EVALS"); // deep/oods.simf:20
-        const Val &ot = array_of(oods.items[0], SSYM_NUM_COLUMNS, "OODS trace evals");
-        for (int i = 0; i < SSYM_NUM_COLUMNS; i++) put_qm31(out + lo.off_oods_trace + 4 * i, array_of(ot.items[i], 1, "ColEvalsQM31").items[0], "OODS trace eval");
+        const Val &ot = array_of(oods.items[0], C, "OODS trace evals");
+        for (uint32_t i = 0; i < C; i++) put_qm31(out + lo.off_oods_trace + 4 * i, array_of(ot.items[i], 1, "ColEvalsQM31").items[0], "OODS trace eval");
         const Val &oc = array_of(oods.items[1], SSYM_NUM_CP_PARTITIONS, "OODS CP evals");
         for (int i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) put_qm31(out + lo.off_oods_cp + 4 * i, oc.items[i], "OODS CP eval");
         const Val &fc = tuple_of(need(w, "FRI_COMMITMENTS"), 3, "FRI_COMMITMENTS"); // fri/commit.simf:19-23
@@ -312,10 +312,10 @@ extern "C" int ssym_stwo_pack_wit(const ssym_stwo_config_t *cfg, const char *jso
         for (uint32_t q = 0; q < Q; q++) {
             const Val &d = tuple_of(dec.items[q], 2, "Decommitment");
             const Val &td = tuple_of(d.items[0], 2, "TraceDecommitment"), &cd = tuple_of(d.items[1], 2, "CpDecommitment");
-            const Val &tv = array_of(td.items[0], SSYM_NUM_COLUMNS, "TraceEvalsM31");
-            for (int i = 0; i < SSYM_NUM_COLUMNS; i++) out[lo.off_qvals + 20 * q + i] = u32_of(array_of(tv.items[i], 1, "ColEvalsM31").items[0], "trace eval");
+            const Val &tv = array_of(td.items[0], C, "TraceEvalsM31");
+            for (uint32_t i = 0; i < C; i++) out[lo.off_qvals + QV * q + i] = u32_of(array_of(tv.items[i], 1, "ColEvalsM31").items[0], "trace eval");
             const Val &cv = array_of(cd.items[0], SSYM_NUM_CP_PARTITIONS, "CPEvalM31");
-            for (int i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) out[lo.off_qvals + 20 * q + 4 + i] = u32_of(cv.items[i], "cp eval");
+            for (int i = 0; i < SSYM_NUM_CP_PARTITIONS; i++) out[lo.off_qvals + QV * q + C + i] = u32_of(cv.items[i], "cp eval");
             const Val *proofs[2] = {&list32(td.items[1], "trace MerkleProof32"), &list32(cd.items[1], "cp MerkleProof32")};
             const uint32_t offs[2] = {lo.off_trace_sib, lo.off_cp_sib};
             for (int t = 0; t < 2; t++) {

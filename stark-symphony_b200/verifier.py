@@ -14,10 +14,12 @@ from . import _lib
 from ._lib import MEM_DEVICE, MEM_HOST, S101Trace, SsymError, StwoConfig, StwoLayout, StwoTrace, check, load
 
 
-def stwo_config(preset: str = "prod", mode: int = _lib.MODE_REF_LITERAL) -> StwoConfig:
-    """The two presets of stwo-verifier/src/config.simf:10-51."""
+def stwo_config(preset: str = "prod", mode: int = _lib.MODE_REF_LITERAL, n_columns: int = 4) -> StwoConfig:
+    """The two presets of stwo-verifier/src/config.simf:10-51; n_columns = NUM_COLUMNS (config.simf:14: 4 at reference HEAD; 8 and 16 widen
+    the same wide-Fibonacci AIR)."""
     cfg = StwoConfig()
     check(load().ssym_stwo_config_preset(preset.encode(), mode, C.byref(cfg)))
+    cfg.n_columns = n_columns
     return cfg
 
 

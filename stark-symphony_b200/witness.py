@@ -118,6 +118,8 @@ def stwo_wit_from_packed(packed_one: np.ndarray, cfg: StwoConfig) -> Dict[str, D
     lo = stwo_layout(cfg)
     w = np.asarray(packed_one, dtype=np.uint32).ravel()
     Q, L, G = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log
+    NC = cfg.n_columns or 4  # NUM_COLUMNS, config.simf:14
+    QV = NC + 16
 
     def dig(off: int) -> str:
         return "0x" + "".join(f"{int(x):08x}" for x in w[off:off + 8])
@@ -131,10 +133,10 @@ def stwo_wit_from_packed(packed_one: np.ndarray, cfg: StwoConfig) -> Dict[str, D
     commitments = "(" + ", ".join(dig(lo.off_commit + 8 * i) for i in range(3)) + ")"
     items = []
     for q in range(Q):
-        tv = "[" + ", ".join(f"[{int(w[lo.off_qvals + 20 * q + i])}]" for i in range(4)) + "]"
-        cv = "[" + ", ".join(str(int(w[lo.off_qvals + 20 * q + 4 + i])) for i in range(16)) + "]"
+        tv = "[" + ", ".join(f"[{int(w[lo.off_qvals + QV * q + i])}]" for i in range(NC)) + "]"
+        cv = "[" + ", ".join(str(int(w[lo.off_qvals + QV * q + NC + i])) for i in range(16)) + "]"
         items.append(f"(({tv}, {diglist(lo.off_trace_sib + q * G * 8, G)}), ({cv}, {diglist(lo.off_cp_sib + q * G * 8, G)}))")
-    oods = "([" + ", ".join("[" + qm(lo.off_oods_trace + 4 * i) + "]" for i in range(4)) + "], [" + ", ".join(qm(lo.off_oods_cp + 4 * i) for i in range(16)) + "])"
+    oods = "([" + ", ".join("[" + qm(lo.off_oods_trace + 4 * i) + "]" for i in range(NC)) + "], [" + ", ".join(qm(lo.off_oods_cp + 4 * i) for i in range(16)) + "])"
 
     def layer_str(l: int) -> str:
         ns = G - 1 - l
@@ -205,7 +207,7 @@ def stwo_negative_classes(cfg: StwoConfig) -> Dict[str, Tuple[int, int]]:
         "oods_trace_plus_1": (lo.off_oods_trace + 4 * 2 + 1, 1),
         "pow_nonce_plus_1": (lo.off_pow_nonce + 1, 1),
         "last_coeff_plus_1": (lo.off_last_coeff + 1, 1),
-        "queried_value_plus_p": (lo.off_qvals + 20 * q + 2, 2147483647),
+        "queried_value_plus_p": (lo.off_qvals + ((cfg.n_columns or 4) + 16) * q + 2, 2147483647),
     }
 
 

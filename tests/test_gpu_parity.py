@@ -36,7 +36,7 @@ def golden_stwo(S, preset, mode):
 def ocfg(cfg):
     from oracle import oracle as O
 
-    return O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    return O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
 
 
 def trace_bytes(t):

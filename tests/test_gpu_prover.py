@@ -24,7 +24,7 @@ def ver(S):
 def ocfg(cfg):
     from oracle import oracle as O
 
-    return O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    return O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
 
 
 def first_diff(a, b, lo):
@@ -139,7 +139,7 @@ def test_config3_full_size_properties(S, ver):
     from oracle import oracle as O
 
     orc = O.Oracle()
-    oc = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    oc = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
     sample = proofs[:32].cpu().numpy().view(np.uint32)
     _, o_status, _ = orc.stwo_verify_batch(oc, sample.ravel(), 32)
     assert (o_status == st[:32]).all()

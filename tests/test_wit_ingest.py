@@ -182,7 +182,7 @@ def test_gpu_tokeniser_matches_host_parser(S, preset):
     # text -> accept bits, against the oracle on the host-packed records
     accept, status, vflags = ver.stwo_verify_wit_batch(blob, offsets, cfg, want_status=True, want_flags=True)
     orc = O.Oracle()
-    ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, 0, cfg.pow_target)
+    ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
     o_accept, o_status, _ = orc.stwo_verify_batch(ocfg, ref_packed.ravel(), len(texts))
     o_status = o_status.copy()
     o_status[ref_flags != 0] |= 1 << 31
