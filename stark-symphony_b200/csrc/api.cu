@@ -1084,7 +1084,6 @@ extern "C" int ssym_stwo_prove_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cf
     const uint32_t T = cfg->trace_log, G = cfg->lde_log, L = cfg->n_fri_layers;
     if (T < 2 || G <= T || G > SSYM_PRV_MAX_LOG || L != T - 1)
         return fail(SSYM_ERR_USAGE, "prover needs 2 <= trace_log < lde_log <= 13 and n_fri_layers == trace_log - 1 (both presets of config.simf do)");
-    if (SSYM_STWO_COLUMNS(cfg) != SSYM_NUM_COLUMNS) return fail(SSYM_ERR_USAGE, "the GPU prover is built for NUM_COLUMNS = 4 (config.simf:14)");
     if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
     if (n == 0) return SSYM_OK;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1121,7 +1120,8 @@ extern "C" int ssym_stwo_prove_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cf
     for (uint32_t l = 0; l <= L; l++) { p.ftree_off[l] = to; to += 8u * 2u * (uint32_t)(NG >> l); }
     p.ftree_stride = to;
     // words of scratch per proof, per buffer
-    const size_t per[9] = {PrvCtx::WORDS, 4 * NT, 4 * NG, 8 * NT, 16 * NG, 16 * NG, 16 * NG, p.fev_stride, p.ftree_stride};
+    const size_t NC = SSYM_STWO_COLUMNS(cfg);
+    const size_t per[9] = {PrvCtx::WORDS, NC * NT, NC * NG, 8 * NT, 16 * NG, 16 * NG, 16 * NG, p.fev_stride, p.ftree_stride};
     size_t per_total = 0;
     for (size_t w : per) per_total += w * 4;
     size_t chunk = std::max<size_t>(1, std::min<size_t>({n, (size_t)4096, ((size_t)8 << 30) / per_total}));

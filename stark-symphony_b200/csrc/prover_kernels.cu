@@ -105,21 +105,26 @@ void launch_prv_vanish(uint32_t trace_log, uint32_t lde_log, const uint2 *point,
 // ------------------------------------------------------------------------------------------
 // P1: trace -> coefficients -> LDE
 // ------------------------------------------------------------------------------------------
+// One CTA per (proof, group of four columns): the shared-memory FFTs hold 4 columns x 2^G words; a group re-runs the row recurrence
+// from c0, c1 up to its own columns (at most 14 squarings per row).
 __global__ void __launch_bounds__(512) prv_trace_kernel(PrvParams p) {
     extern __shared__ uint32_t sm[];
-    const uint32_t T = p.cfg.trace_log, G = p.cfg.lde_log, NT = 1u << T, NG = 1u << G;
-    const uint32_t i = blockIdx.x;
+    const uint32_t T = p.cfg.trace_log, G = p.cfg.lde_log, NT = 1u << T, NG = 1u << G, C = SSYM_STWO_COLUMNS(&p.cfg);
+    const uint32_t i = blockIdx.x, c_first = 4 * blockIdx.y;
     const uint64_t seed = p.seeds[i];
-    for (uint32_t r = threadIdx.x; r < NT; r += blockDim.x) { // row: c2 = c0^2 + c1^2, c3 = c1^2 + c2^2 (wide_fibonacci.simf:24-62)
+    for (uint32_t r = threadIdx.x; r < NT; r += blockDim.x) { // row: c_k = c_{k-1}^2 + c_{k-2}^2 (wide_fibonacci.simf:24-62)
         const uint32_t raw = (uint32_t)(prv_splitmix(seed, r) >> 33);
-        const uint32_t c0 = 1u, c1 = raw == SSYM_P ? 0u : raw;
-        const uint32_t c1s = m31_mul(c1, c1);
-        const uint32_t c2 = m31_add(m31_mul(c0, c0), c1s), c3 = m31_add(c1s, m31_mul(c2, c2));
-        sm[r] = c0; sm[NG + r] = c1; sm[2 * NG + r] = c2; sm[3 * NG + r] = c3;
+        uint32_t a = 1u, b = raw == SSYM_P ? 0u : raw; // c0, c1
+        for (uint32_t k = 0; k < c_first + 4; k++) {    // a = c_k
+            if (k >= c_first) sm[(k - c_first) * NG + r] = a;
+            const uint32_t nx = m31_add(m31_mul(b, b), m31_mul(a, a));
+            a = b;
+            b = nx;
+        }
     }
     __syncthreads();
     cfft_block<true>(sm, 4, NG, T, p.tr.itw);
-    uint32_t *tc = p.tcoef + (size_t)i * 4 * NT;
+    uint32_t *tc = p.tcoef + ((size_t)i * C + c_first) * NT;
     for (uint32_t idx = threadIdx.x; idx < 4 * NG; idx += blockDim.x) {
         const uint32_t c = idx >> G, j = idx & (NG - 1);
         uint32_t v = 0;
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(512) prv_trace_kernel(PrvParams p) {
     }
     __syncthreads();
     cfft_block<false>(sm, 4, NG, G, p.lde.tw);
-    uint32_t *tl = p.tlde + (size_t)i * 4 * NG;
+    uint32_t *tl = p.tlde + ((size_t)i * C + c_first) * NG;
     for (uint32_t idx = threadIdx.x; idx < 4 * NG; idx += blockDim.x) tl[idx] = sm[idx];
 }
 
@@ -143,10 +148,24 @@ __global__ void __launch_bounds__(128) prv_leaf_trace_kernel(PrvParams p, uint32
     const uint32_t G = p.cfg.lde_log, NG = 1u << G;
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= p.m << G) return;
-    const uint32_t i = gid >> G, q = gid & (NG - 1);
-    const uint32_t *tl = p.tlde + (size_t)i * 4 * NG + q;
+    const uint32_t i = gid >> G, q = gid & (NG - 1), C = SSYM_STWO_COLUMNS(&p.cfg);
+    const uint32_t *tl = p.tlde + (size_t)i * C * NG + q;
     uint32_t d[8];
-    hash_16B(make_uint4(tl[0], tl[NG], tl[2 * NG], tl[3 * NG]), d, A);
+    if (C == 4) {
+        hash_16B(make_uint4(tl[0], tl[NG], tl[2 * NG], tl[3 * NG]), d, A);
+    } else { // hash_node_m31_trace (hasher.simf:85-90) over C words: 8 -> one block with the padding behind the data, 16 -> a 64-byte message
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) w[k] = (uint32_t)k < C ? tl[(size_t)k * NG] : 0u;
+        if (C == 16) {
+            sha256_64B_rolled<1>(w, d, A);
+        } else {
+            w[8] = 0x80000000u;
+            w[15] = 256u;
+            sha_iv(d);
+            sha_compress_rolled<1>(d, w, A);
+        }
+    }
     store_digest(p.tree_t + ((size_t)i * 2 * NG + NG + q) * 8, d);
 }
 __global__ void __launch_bounds__(128) prv_leaf_cp_kernel(PrvParams p, uint32_t one) { // hash_node_m31_cp hasher.simf:93-97
@@ -259,7 +278,7 @@ __global__ void __launch_bounds__(64) prv_ch_oods_point_kernel(PrvParams p) {
     ch_store(ch, pc);
     if (ex || iz) atomicOr(p.flag, 2u);
 }
-// mix the samples (deep/oods.simf:23-39), draw the DEEP coefficient, line coefficients of the 20 columns (deep/quotients.simf:25-35)
+// mix the samples (deep/oods.simf:23-39), draw the DEEP coefficient, line coefficients of the C + 16 columns (deep/quotients.simf:25-35)
 __global__ void __launch_bounds__(64) prv_ch_deep_kernel(PrvParams p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.m) return;
@@ -268,14 +287,15 @@ __global__ void __launch_bounds__(64) prv_ch_deep_kernel(PrvParams p) {
     Channel ch;
     ch_load(ch, pc);
     bool ex = false;
-    channel_mix(ch, out + p.lo.off_oods_trace, 80);
+    const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg);
+    channel_mix(ch, out + p.lo.off_oods_trace, 4 * (C + 16));
     const QM31 deep_alpha = channel_draw_qm31(ch, ex);
     qm31_store4(pc + PC::DEEP_ALPHA, deep_alpha);
     const QM31 py = qm31_load4(pc + PC::PY), p2y = qm31_load4(pc + PC::P2Y);
     QM31 alpha_i = deep_alpha;
     QM31 sa_a = qm31_zero(), sa_c = qm31_zero(), sb_a = qm31_zero(), sb_c = qm31_zero();
 #pragma unroll 1
-    for (uint32_t k = 0; k < 20; k++) { // aggregation order of Appendix A item 1: 16 CP columns at 2P, then 4 trace columns at P
+    for (uint32_t k = 0; k < C + 16; k++) { // aggregation order of Appendix A item 1: 16 CP columns at 2P, then the C trace columns at P
         const bool in_a = k < 16;
         const QM31 sv = qm31_load4(in_a ? out + p.lo.off_oods_cp + 4 * k : out + p.lo.off_oods_trace + 4 * (k - 16));
         const LineCoeffs lc = interpolant_coefficients(in_a ? p2y : py, sv, alpha_i);
@@ -314,15 +334,28 @@ __global__ void __launch_bounds__(64) prv_ch_fri_kernel(PrvParams p, uint32_t la
 __global__ void __launch_bounds__(512) prv_cp_kernel(PrvParams p) {
     extern __shared__ uint32_t sm[]; // [0, NG): evaluations / coefficients of this coordinate; [NG, 5 NG): the four sub-polynomial columns
     const uint32_t T = p.cfg.trace_log, G = p.cfg.lde_log, NT = 1u << T, NG = 1u << G;
-    const uint32_t i = blockIdx.x, coord = blockIdx.y;
-    const uint32_t alpha = p.pctx[(size_t)i * PC::WORDS + PC::CP_ALPHA + coord];
-    const uint32_t *tl = p.tlde + (size_t)i * 4 * NG;
+    const uint32_t i = blockIdx.x, coord = blockIdx.y, C = SSYM_STWO_COLUMNS(&p.cfg);
+    __shared__ uint32_t s_al[SSYM_MAX_COLUMNS]; // s_al[j] = this coordinate of cp_alpha^j: constraint k carries alpha^(C-1-k) in the Horner fold
+    if (threadIdx.x == 0) {
+        const QM31 alpha = qm31_load4(p.pctx + (size_t)i * PC::WORDS + PC::CP_ALPHA);
+        QM31 pw = qm31_one();
+        for (uint32_t j = 0; j + 2 < C; j++) {
+            s_al[j] = coord == 0 ? pw.r.a : coord == 1 ? pw.r.b : coord == 2 ? pw.i.a : pw.i.b;
+            pw = qm31_mul_pn(pw, alpha);
+        }
+    }
+    __syncthreads();
+    const uint32_t *tl = p.tlde + (size_t)i * C * NG;
     for (uint32_t q = threadIdx.x; q < NG; q += blockDim.x) {
-        const uint32_t c0 = tl[q], c1 = tl[NG + q], c2 = tl[2 * NG + q], c3 = tl[3 * NG + q];
-        const uint32_t c1s = m31_mul(c1, c1), c2s = m31_mul(c2, c2);
-        const uint32_t k2 = m31_sub(c2, m31_add(c1s, m31_mul(c0, c0))), k3 = m31_sub(c3, m31_add(c2s, c1s));
-        // (cp_alpha * C2 + C3) / vanishing, this QM31 coordinate (wide_fibonacci.simf:24-62)
-        sm[q] = m31_mul(m31_add(m31_mul(alpha, k2), coord == 0 ? k3 : 0u), __ldg(p.vanish_inv + q));
+        // (sum_k alpha^(C-1-k) (c_k - c_{k-1}^2 - c_{k-2}^2)) / vanishing, this QM31 coordinate (wide_fibonacci.simf:24-62)
+        uint32_t a = tl[q], b = tl[NG + q], as = m31_mul(a, a), bs = m31_mul(b, b), acc = 0;
+        for (uint32_t k = 2; k < C; k++) {
+            const uint32_t ck = tl[(size_t)k * NG + q];
+            acc = m31_add(acc, m31_mul(s_al[C - 1 - k], m31_sub(ck, m31_add(bs, as))));
+            as = bs;
+            bs = m31_mul(ck, ck);
+        }
+        sm[q] = m31_mul(acc, __ldg(p.vanish_inv + q));
     }
     __syncthreads();
     cfft_block<true>(sm, 1, NG, G, p.lde.itw);
@@ -358,14 +391,15 @@ __global__ void __launch_bounds__(32 * PRV_OODS_WARPS) prv_oods_kernel(PrvParams
     const uint32_t T = p.cfg.trace_log, NT = 1u << T;
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t wid = blockIdx.x * PRV_OODS_WARPS + wib;
-    if (wid >= p.m * 20) return; // warp-uniform
-    const uint32_t i = wid / 20, col = wid % 20;
+    const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg), NCOL = C + 16;
+    if (wid >= p.m * NCOL) return; // warp-uniform
+    const uint32_t i = wid / NCOL, col = wid % NCOL;
     const uint32_t *pc = p.pctx + (size_t)i * PC::WORDS;
     const uint32_t *c, *tw;
     uint32_t stride, bits;
-    if (col < 4) { c = p.tcoef + ((size_t)i * 4 + col) * NT; stride = 1; bits = T; tw = pc + PC::TW; }
+    if (col < C) { c = p.tcoef + ((size_t)i * C + col) * NT; stride = 1; bits = T; tw = pc + PC::TW; }
     else { // CP column k = 4 * coord + poly: coefficients c[4m + poly] of the coordinate, factors pi^k(2P.x) = TW[2 + k]
-        const uint32_t k = col - 4;
+        const uint32_t k = col - C;
         c = p.cpcoef + ((size_t)i * 4 + (k >> 2)) * 2 * NT + (k & 3); stride = 4; bits = T - 1; tw = pc + PC::TW + 8;
     }
     const uint32_t blk_bits = bits > 5 ? bits - 5 : 0, lane_bits = bits - blk_bits;
@@ -388,7 +422,7 @@ __global__ void __launch_bounds__(32 * PRV_OODS_WARPS) prv_oods_kernel(PrvParams
     }
     if (lane == 0) {
         uint32_t *out = p.out + (size_t)i * p.lo.stride_words;
-        qm31_store4(col < 4 ? out + p.lo.off_oods_trace + 4 * col : out + p.lo.off_oods_cp + 4 * (col - 4), v);
+        qm31_store4(col < C ? out + p.lo.off_oods_trace + 4 * col : out + p.lo.off_oods_cp + 4 * (col - C), v);
     }
 }
 
@@ -403,12 +437,13 @@ __global__ void __launch_bounds__(128) prv_quotient_kernel(PrvParams p) {
     const uint32_t *pc = p.pctx + (size_t)i * PC::WORDS;
     const uint2 rp = __ldg(p.point + q);
     const M31Point R = m31_point(rp.x, rp.y);
-    const uint32_t *cl = p.cplde + (size_t)i * 16 * NG + q, *tl = p.tlde + (size_t)i * 4 * NG + q;
+    const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg);
+    const uint32_t *cl = p.cplde + (size_t)i * 16 * NG + q, *tl = p.tlde + (size_t)i * C * NG + q;
     QM31 na = qm31_zero(), nb = qm31_zero();
 #pragma unroll 4
     for (int k = 0; k < 16; k++) na = qm31_add(na, qm31_mul_m31(qm31_load4(pc + PC::KB + 4 * k), cl[(size_t)k * NG]));
-#pragma unroll
-    for (int k = 0; k < 4; k++) nb = qm31_add(nb, qm31_mul_m31(qm31_load4(pc + PC::KB + 4 * (16 + k)), tl[(size_t)k * NG]));
+#pragma unroll 4
+    for (uint32_t k = 0; k < C; k++) nb = qm31_add(nb, qm31_mul_m31(qm31_load4(pc + PC::KB + 4 * (16 + k)), tl[(size_t)k * NG]));
     na = qm31_sub(na, qm31_add(qm31_mul_m31(qm31_load4(pc + PC::SUMS), R.y), qm31_load4(pc + PC::SUMS + 4)));
     nb = qm31_sub(nb, qm31_add(qm31_mul_m31(qm31_load4(pc + PC::SUMS + 8), R.y), qm31_load4(pc + PC::SUMS + 12)));
     bool iz = false;
@@ -481,8 +516,9 @@ __global__ void __launch_bounds__(128) prv_decommit_kernel(PrvParams p) {
     const uint32_t i = wid / Q, qi = wid % Q;
     const uint32_t q = p.pctx[(size_t)i * PC::WORDS + PC::QUERIES + qi];
     uint32_t *out = p.out + (size_t)i * p.lo.stride_words;
-    if (lane < 20)
-        out[p.lo.off_qvals + 20 * qi + lane] = lane < 4 ? p.tlde[((size_t)i * 4 + lane) * NG + q] : p.cplde[((size_t)i * 16 + (lane - 4)) * NG + q];
+    const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg);
+    if (lane < C + 16)
+        out[p.lo.off_qvals + (C + 16) * qi + lane] = lane < C ? p.tlde[((size_t)i * C + lane) * NG + q] : p.cplde[((size_t)i * 16 + (lane - C)) * NG + q];
     if (lane <= L) { // the sibling evaluation of layer `lane` (adjacent_leaves fri/layers.simf:29-37)
         const uint32_t fq = q >> lane;
         *reinterpret_cast<uint4 *>(out + p.lo.off_fri_wit + (lane * Q + qi) * 4) =
@@ -514,7 +550,7 @@ __global__ void __launch_bounds__(128) prv_decommit_kernel(PrvParams p) {
 // ------------------------------------------------------------------------------------------
 int launch_prv_prove(const PrvParams &p, cudaStream_t s, uint64_t *launch_counter) {
     if (p.m == 0) return 0;
-    const uint32_t T = p.cfg.trace_log, G = p.cfg.lde_log, L = p.cfg.n_fri_layers, Q = p.cfg.n_queries, NG = 1u << G;
+    const uint32_t T = p.cfg.trace_log, G = p.cfg.lde_log, L = p.cfg.n_fri_layers, Q = p.cfg.n_queries, NG = 1u << G, C = SSYM_STWO_COLUMNS(&p.cfg);
     (void)T;
     int launches = 0;
     cudaFuncSetAttribute(prv_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (4 << SSYM_PRV_MAX_LOG));
@@ -528,7 +564,7 @@ int launch_prv_prove(const PrvParams &p, cudaStream_t s, uint64_t *launch_counte
             launches++;
         }
     };
-    prv_trace_kernel<<<p.m, 512, 4 * sizeof(uint32_t) * NG, s>>>(p);
+    prv_trace_kernel<<<dim3(p.m, C / 4), 512, 4 * sizeof(uint32_t) * NG, s>>>(p);
     prv_leaf_trace_kernel<<<blocks((uint64_t)p.m << G), 128, 0, s>>>(p, one);
     launches += 2;
     tree(p.tree_t, (size_t)2 * NG * 8, 0, G);
@@ -538,7 +574,7 @@ int launch_prv_prove(const PrvParams &p, cudaStream_t s, uint64_t *launch_counte
     launches += 3;
     tree(p.tree_c, (size_t)2 * NG * 8, 0, G);
     prv_ch_oods_point_kernel<<<per_proof_blocks, 64, 0, s>>>(p);
-    prv_oods_kernel<<<(p.m * 20 + PRV_OODS_WARPS - 1) / PRV_OODS_WARPS, 32 * PRV_OODS_WARPS, 0, s>>>(p);
+    prv_oods_kernel<<<(p.m * (C + 16) + PRV_OODS_WARPS - 1) / PRV_OODS_WARPS, 32 * PRV_OODS_WARPS, 0, s>>>(p);
     prv_ch_deep_kernel<<<per_proof_blocks, 64, 0, s>>>(p);
     prv_quotient_kernel<<<blocks((uint64_t)p.m << G), 128, 0, s>>>(p);
     launches += 4;

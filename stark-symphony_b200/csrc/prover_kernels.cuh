@@ -32,11 +32,11 @@ struct PrvCtx { // per-proof prover context, u32 words
         PX = 16, PY = 20, P2X = 24, P2Y = 28, // OODS point P and 2P
         TW = 32,         // [14][4]  P.y, P.x, pi(P.x), pi^2(P.x), ...  (basis factors of the circle-FFT basis at P)
         DEEP_ALPHA = 88, // [4]
-        KB = 92,         // [20][4]  line coefficient b of column k with alpha^(k+1): 16 CP columns (at 2P), then 4 trace columns (at P)
-        SUMS = 172,      // [4][4]   sum a / sum c of batch A (CP), sum a / sum c of batch B (trace)
-        FRI_ALPHA = 188, // [9][4]
-        QUERIES = 224,   // [16]
-        WORDS = 256
+        KB = 92,         // [16 + C][4]  line coefficient b of column k with alpha^(k+1): 16 CP columns (at 2P), then the C <= 16 trace columns (at P)
+        SUMS = 220,      // [4][4]   sum a / sum c of batch A (CP), sum a / sum c of batch B (trace)
+        FRI_ALPHA = 236, // [9][4]
+        QUERIES = 272,   // [16]
+        WORDS = 288
     };
 };
 
@@ -58,8 +58,8 @@ struct PrvParams {
     const uint64_t *seeds;      // m
     uint32_t *out;              // m packed records
     uint32_t *pctx;             // m * PrvCtx::WORDS
-    uint32_t *tcoef;            // m * 4 * 2^T
-    uint32_t *tlde;             // m * 4 * 2^G
+    uint32_t *tcoef;            // m * C * 2^T   (C = NUM_COLUMNS)
+    uint32_t *tlde;             // m * C * 2^G
     uint32_t *cpcoef;           // m * 4 * 2^(T+1)
     uint32_t *cplde;            // m * 16 * 2^G
     uint32_t *tree_t, *tree_c;  // m * 2^(G+1) * 8

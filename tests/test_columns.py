@@ -184,6 +184,45 @@ def test_gpu_wit_ingestion_of_wide_proofs(S, ver, orc, nc):
 
 
 @pytest.mark.gpu
-def test_gpu_prover_says_it_is_four_columns_only(S, ver):
-    with pytest.raises(S.SsymError):
-        ver.stwo_prove_batch(np.arange(2, dtype=np.uint64), S.stwo_config("prod", 1, n_columns=8))
+@pytest.mark.parametrize("nc", WIDTHS)
+@pytest.mark.parametrize("preset,seeds", [("testing", list(range(24)) + [2**64 - 1]), ("prod", [0, 1, 0xDEADBEEF, 2**63 + 5])])
+def test_gpu_prover_matches_reference_prover_on_wide_traces(S, ver, orc, preset, seeds, nc):
+    cfg = S.stwo_config(preset, S.MODE_PROVER_CONSISTENT, n_columns=nc)
+    seeds = np.array(seeds, dtype=np.uint64)
+    gpu = ver.stwo_prove_batch(seeds, cfg)
+    ref = orc.stwo_prove_batch(ocfg(cfg), seeds, threads=8)
+    assert (gpu == ref).all(), np.argwhere(gpu != ref)[:4]
+    accept, status, _ = ver.stwo_verify_batch(gpu.ravel(), cfg, len(seeds), want_status=True)
+    assert (status == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nc", WIDTHS)
+def test_wide_batch_device_resident_with_negatives(S, ver, orc, nc):
+    """2048 distinct GPU-proven wide proofs, every 8th corrupted: bitmap == the corruption pattern, a sample of statuses == the oracle."""
+    import torch
+
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT, n_columns=nc)
+    lo = S.stwo_layout(cfg)
+    n = 2048
+    seeds = torch.arange(7000, 7000 + n, dtype=torch.int64, device="cuda")
+    proofs = ver.stwo_prove_batch(seeds, cfg)
+    torch.cuda.synchronize()
+    assert proofs.shape == (n, lo.stride_words)
+    classes = list(S.witness.stwo_negative_classes(cfg).values())
+    bad_rows = list(range(0, n, 8))
+    for j, row in enumerate(bad_rows):
+        word, delta = classes[j % len(classes)]
+        proofs[row, word] += delta
+    accept, status, _ = ver.stwo_verify_batch(proofs.view(-1), cfg, n, want_status=True)
+    ver.synchronize()
+    status = status.cpu().numpy().view(np.uint32)
+    expect_bad = np.zeros(n, dtype=bool)
+    expect_bad[bad_rows] = True
+    assert ((status != 0) == expect_bad).all(), np.flatnonzero((status != 0) != expect_bad)[:10]
+    bits = accept.cpu().numpy().view(np.uint32)
+    got = np.array([(bits[i // 32] >> (i % 32)) & 1 for i in range(n)], dtype=bool)
+    assert (got == ~expect_bad).all()
+    sample = proofs[:24].cpu().numpy().view(np.uint32)
+    _, o_status, _ = orc.stwo_verify_batch(ocfg(cfg), sample.ravel(), 24)
+    assert (o_status == status[:24]).all()
