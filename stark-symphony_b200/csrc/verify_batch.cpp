@@ -40,7 +40,7 @@ static bool read_file(const std::string &path, std::string &out) {
 
 static void usage() {
     fprintf(stderr,
-            "usage: verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--mode {ref-literal,prover-consistent}]\n"
+            "usage: verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--columns {4,8,16}] [--mode {ref-literal,prover-consistent}]\n"
             "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet] [--host-pack]\n");
 }
 
@@ -60,6 +60,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> witnesses;
     size_t replicate = 1;
     int gpus = 1;
+    uint32_t columns = SSYM_NUM_COLUMNS; // NUM_COLUMNS of the program the witnesses were made for (config.simf:14)
     bool quiet = false, host_pack = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -76,6 +77,7 @@ int main(int argc, char **argv) {
         } else if (a == "--witness-dir") witness_dir = next("--witness-dir");
         else if (a == "--replicate") replicate = strtoull(next("--replicate").c_str(), nullptr, 10);
         else if (a == "--gpus") gpus = atoi(next("--gpus").c_str());
+        else if (a == "--columns") columns = (uint32_t)strtoul(next("--columns").c_str(), nullptr, 10);
         else if (a == "--trace") trace_path = next("--trace");
         else if (a == "--quiet") quiet = true;
         else if (a == "--host-pack") host_pack = true;
@@ -116,7 +118,7 @@ int main(int argc, char **argv) {
     std::vector<uint64_t> wit_offsets;
     std::vector<uint32_t> wit_flags;
     if (gpu_ingest) {
-        if (program == "stwo" && (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || ssym_stwo_layout(&cfg, &lo))) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
+        if (program == "stwo" && (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || (cfg.n_columns = columns, ssym_stwo_layout(&cfg, &lo)))) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
         wit_offsets.push_back(0);
         for (size_t f = 0; f < n_files; f++) {
             struct stat st;
@@ -140,7 +142,7 @@ int main(int argc, char **argv) {
         }
         wit_flags.assign(n, 0);
     } else if (program == "stwo") {
-        if (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || ssym_stwo_layout(&cfg, &lo)) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
+        if (ssym_stwo_config_preset(preset.c_str(), mode_id, &cfg) || (cfg.n_columns = columns, ssym_stwo_layout(&cfg, &lo))) { fprintf(stderr, "Error: %s\n", ssym_last_error()); return 2; }
         packed.assign(n * (size_t)lo.stride_words, 0);
         for (size_t f = 0; f < n_files; f++) {
             std::string text;

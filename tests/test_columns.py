@@ -226,3 +226,33 @@ def test_wide_batch_device_resident_with_negatives(S, ver, orc, nc):
     sample = proofs[:24].cpu().numpy().view(np.uint32)
     _, o_status, _ = orc.stwo_verify_batch(ocfg(cfg), sample.ravel(), 24)
     assert (o_status == status[:24]).all()
+
+
+@pytest.mark.gpu
+def test_cli_columns_option(S, orc, tmp_path):
+    """bin/verify-batch --columns N: `.wit` files written from 8-column proofs verify with --columns 8 (GPU ingestion and --host-pack alike) and
+    are refused as ill-typed without it, as `simfony run` refuses a witness that does not match the program's types."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    cli = os.path.join(ROOT, "stark-symphony_b200", "bin", "verify-batch")
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT, n_columns=8)
+    pk = orc.stwo_prove_batch(ocfg(cfg), [21, 22])
+    bad = S.witness.apply_mutation(pk[1], *S.witness.stwo_negative_classes(cfg)["oods_trace_plus_1"])
+    paths = []
+    for name, rec in (("a", pk[0]), ("b", bad), ("c", pk[1])):
+        path = tmp_path / f"{name}.wit"
+        path.write_text(json.dumps(S.witness.stwo_wit_from_packed(rec, cfg)))
+        paths.append(str(path))
+    outs = []
+    for extra in ([], ["--host-pack"]):
+        r = subprocess.run([cli, "--program", "stwo", "--mode", "prover-consistent", "--columns", "8", "--witness"] + paths + extra, capture_output=True, text=True)
+        assert r.returncode == 1 and [l.split()[0] for l in r.stdout.strip().splitlines()] == ["accept", "reject", "accept"], r.stderr
+        outs.append(r.stdout)
+        r = subprocess.run([cli, "--program", "stwo", "--mode", "prover-consistent", "--witness", paths[0]] + extra, capture_output=True, text=True)
+        assert r.returncode == 1 and r.stdout.startswith("reject") and "status=0x8" in r.stdout
+    assert outs[0] == outs[1]
+    r = subprocess.run([cli, "--program", "stwo", "--columns", "5", "--witness", paths[0]], capture_output=True, text=True)
+    assert r.returncode == 2 and "n_columns" in r.stderr
