@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--columns", type=int, default=4, choices=[4, 8, 16], help="NUM_COLUMNS of the AIR (config.simf:14); 4 = reference HEAD")
     args = ap.parse_args()
     # libraries (NCCL's version banner) write to fd 1: keep stdout for the single JSON line, as bench.py does
     sys.stdout.flush()
@@ -77,8 +78,8 @@ def main():
     n_total = 1 << log_n
     begin, end = sharding.shard_range(n_total, rank, world)
     n = end - begin
-    cfg_pc = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
-    cfg_lit = S.stwo_config("prod", S.MODE_REF_LITERAL)
+    cfg_pc = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT, n_columns=args.columns)
+    cfg_lit = S.stwo_config("prod", S.MODE_REF_LITERAL, n_columns=args.columns)
     lo = S.stwo_layout(cfg_pc)
     ver = S.Verifier(local_rank)
     stream = torch.cuda.Stream()
@@ -159,7 +160,7 @@ def main():
         sample = proofs[:sample_n].cpu().numpy().view(np.uint32)
         checks = {}
         for name, mode in (("prover-consistent", O.MODE_PROVER_CONSISTENT), ("ref-literal", O.MODE_REF_LITERAL)):
-            _, o_status, _ = orc.stwo_verify_batch(O.make_config("prod", mode), sample.ravel(), sample_n)
+            _, o_status, _ = orc.stwo_verify_batch(O.make_config("prod", mode, args.columns), sample.ravel(), sample_n)
             assert (o_status == results[name]["status_sample"][:sample_n]).all(), f"{name}: GPU statuses differ from the oracle"
             checks[name] = f"{sample_n} statuses bit-identical to the oracle"
         peaks = {}
@@ -170,7 +171,10 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         mk_ms, mk_n = prof.get("stwo_merkle", (0.0, 0))
         kernel_ms = {k: v[0] for k, v in prof.items()}
-        lit_ops = n * B.MERKLE_COMPRESSIONS_PER_PROOF * B.LITERAL_OPS_PER_COMPRESSION / (mk_ms * 1e-3) if mk_ms else 0.0
+        # a 16-column trace leaf is a 64-byte message: one more compression per trace decommitment
+        merkle_compressions = B.MERKLE_COMPRESSIONS_PER_PROOF + (cfg_pc.n_queries if args.columns == 16 else 0)
+        alg_bytes = lo.algorithmic_bytes
+        lit_ops = n * merkle_compressions * B.LITERAL_OPS_PER_COMPRESSION / (mk_ms * 1e-3) if mk_ms else 0.0
         r = results["prover-consistent"]
         line = {
             "metric": "stwo_proofs_verified_per_s", "value": r["proofs_per_s"], "unit": "proofs/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
@@ -178,14 +182,14 @@ def main():
             "data": "synthetic: distinct proofs of the wide-Fibonacci AIR, one per seed, generated on the GPU by ssym_stwo_prove_batch",
             "config": {"workload": (f"BASELINE config 3: 2^{log_n} distinct synthetic Stwo proofs + corrupted negatives (6 classes x 1/8 of the batch), 1 B200" if args.config == 3 else
                                     f"BASELINE config 5: 2^{log_n} distinct synthetic Stwo proofs sharded by index over {world} B200, accept-bitmap gather"),
-                       "mode": "prover-consistent", "proofs_total": n_total, "proofs_per_gpu": n, "negatives": int(expect_bad.sum()),
+                       "mode": "prover-consistent", "n_columns": args.columns, "proofs_total": n_total, "proofs_per_gpu": n, "negatives": int(expect_bad.sum()),
                        "l2": f"one pass reads {n * lo.stride_words * 4 / 1e9:.2f} GB per GPU (>> 126 MB L2)"},
             "accepted": r["accepted"], "gpu_launches": int(r["gpu_launches"]),
             "ref_literal": {"proofs_per_s": results["ref-literal"]["proofs_per_s"], "ms_per_pass": results["ref-literal"]["ms_per_pass"], "accepted": results["ref-literal"]["accepted"]},
-            "merkle_hashes_per_s": r["proofs_per_s"] * B.MERKLE_COMPRESSIONS_PER_PROOF / 2.0,
+            "merkle_hashes_per_s": r["proofs_per_s"] * merkle_compressions / 2.0,
             "kernel_ms_per_pass": kernel_ms,
-            "roofline": {"bound": "hbm", "kernel": "stwo_merkle_kernel", "achieved": n * B.ALG_BYTES_PER_PROOF / (mk_ms * 1e-3) / 1e9 if mk_ms else None, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": (n * B.ALG_BYTES_PER_PROOF / (mk_ms * 1e-3) / 1e9 / hbm_peak) if mk_ms else None, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "stwo_merkle_kernel", "achieved": n * alg_bytes / (mk_ms * 1e-3) / 1e9 if mk_ms else None, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": (n * alg_bytes / (mk_ms * 1e-3) / 1e9 / hbm_peak) if mk_ms else None, "traffic": None,
                          "note": "INT32-ALU bound kernel (170 int-ops per byte): see roofline_int32"},
             "roofline_int32": {"bound": "int32_alu", "kernel": "stwo_merkle_kernel", "achieved": lit_ops / 1e12, "peak": int32_ops / 1e12, "unit": "Tops/s",
                                "frac": lit_ops / int32_ops if int32_ops else None, "launches": mk_n, "total_ms": mk_ms},
@@ -195,7 +199,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             threads = B.cpu_threads()
-            ocfg = O.make_config("prod", O.MODE_PROVER_CONSISTENT)
+            ocfg = O.make_config("prod", O.MODE_PROVER_CONSISTENT, args.columns)
             flat = np.ascontiguousarray(sample.ravel())
             t1, _ = B.oracle_run(orc, ocfg, flat, sample_n, 1, 8)
             total = int(max(threads * 8, min(15.0 / (t1 / 8), 64 * sample_n)))
