@@ -85,6 +85,10 @@ SYMBOLS = {
     "ssym_profile_enable": (_I, [_V, _I]),
     "ssym_profile_read": (_I, [_V, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ssym_stwo_verify_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _V, _V, _I]),
+    "ssym_stwo_compact_bound": (_SZ, [C.POINTER(StwoConfig), _SZ]),
+    "ssym_stwo_compact_pack": (_I, [C.POINTER(StwoConfig), _V, _SZ, _V, _SZ, _V]),
+    "ssym_stwo_compact_expand": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _I]),
+    "ssym_stwo_verify_compact_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _I]),
     "ssym_stark101_verify_batch": (_I, [_V, _V, _V, _SZ, _V, _V, _V, _I]),
     "ssym_stwo_prove_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _I]),
     "ssym_m31_add": (_I, [_V, _V, _V, _V, _SZ, _I]),

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/ssym.h"
+#include "compact_kernels.cuh"
 #include "jets_kernels.cuh"
 #include "prover_kernels.cuh"
 #include "s101_kernels.cuh"
@@ -114,6 +115,7 @@ struct ssym_ctx {
     uint32_t fold_off[SSYM_MAX_FRI_LAYERS] = {0};
     // host-memspace staging
     DevBuf stage[2], d_accept, d_status, d_trace, d_offsets;
+    DevBuf cstage[2], coffs[2], cflags[2]; // compact transport: compact chunk, its offsets, malformed-record flags (stage[] holds the expanded chunk)
     // prover: twiddle tables per (trace_log, lde_log) and per-chunk scratch
     DevBuf prv_tw[2], prv_itw[2], prv_vanish, prv_flag, prv_seeds, prv_out;
     DevBuf prv_scratch[9];
@@ -205,6 +207,7 @@ void ssym_destroy(ssym_ctx_t *c) {
         cudaEventDestroy(c->ev_wit_flags[i]);
         cudaEventDestroy(c->ev_wit_parsed[i]);
         c->wit_text[i].release(); c->wit_offs[i].release(); c->wit_packed[i].release(); c->wit_flags[i].release(); c->wit_numpos[i].release();
+        c->cstage[i].release(); c->coffs[i].release(); c->cflags[i].release();
         if (c->wit_hflags[i]) cudaFreeHost(c->wit_hflags[i]);
         if (c->wit_hoffs[i]) cudaFreeHost(c->wit_hoffs[i]);
     }
@@ -484,6 +487,193 @@ extern "C" int ssym_set_host_async(ssym_ctx_t *c, int on) {
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     c->host_async = on != 0;
+    return SSYM_OK;
+}
+
+/* ---- compact transport form (include/ssym.h) ------------------------------------------------------------ */
+extern "C" size_t ssym_stwo_compact_bound(const ssym_stwo_config_t *cfg, size_t n) {
+    ssym_stwo_layout_t lo;
+    CompactShape sh;
+    if (!cfg || ssym_stwo_layout(cfg, &lo) || compact_shape(*cfg, lo, sh)) return 0;
+    return n * (size_t)(sh.off_tab + 8u * sh.slots);
+}
+
+extern "C" int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint32_t *out, size_t out_cap_words,
+                                      uint64_t *offsets) {
+    if (!cfg || !offsets || ((!packed || !out) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    ssym_stwo_layout_t lo;
+    int rc = ssym_stwo_layout(cfg, &lo);
+    if (rc) return rc;
+    CompactShape sh;
+    if (compact_shape(*cfg, lo, sh)) return fail(SSYM_ERR_INTERNAL, "packed layout is not contiguous in slot order");
+    const uint32_t HASH = 1024; // > 2 * the slots of one tree (Q * G <= 480)
+    std::vector<uint32_t> rec(sh.off_tab + 8u * sh.slots), bucket(HASH);
+    size_t pos = 0;
+    offsets[0] = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t *pk = packed + i * (size_t)lo.stride_words;
+        std::fill(rec.begin(), rec.begin() + sh.off_tab, 0u);
+        memcpy(rec.data() + COMPACT_HDR_WORDS, pk, sh.fixed_words * 4);
+        memcpy(rec.data() + sh.off_wit, pk + lo.off_fri_wit, sh.wit_words * 4);
+        uint8_t *idx8 = reinterpret_cast<uint8_t *>(rec.data() + sh.off_idx);
+        uint16_t *idx16 = reinterpret_cast<uint16_t *>(rec.data() + sh.off_idx);
+        uint32_t *tab = rec.data() + sh.off_tab;
+        uint32_t D = 0;
+        for (uint32_t t = 0; t < sh.trees; t++) {
+            const uint32_t first = D;
+            rec[4 + t] = first;
+            std::fill(bucket.begin(), bucket.end(), 0u);
+            for (uint32_t sl = sh.slot_first[t]; sl < sh.slot_first[t + 1]; sl++) {
+                const uint32_t *d = pk + (sl < sh.head_slots ? lo.off_trace_sib + 8 * sl : lo.off_fri_sib[0] + 8 * (sl - sh.head_slots));
+                uint32_t h = (d[0] * 0x9E3779B1u) ^ (d[3] * 0x85EBCA77u) ^ d[7];
+                h = (h ^ (h >> 15)) & (HASH - 1);
+                uint32_t e;
+                for (;; h = (h + 1) & (HASH - 1)) { // linear probing; a hit only after comparing all 32 bytes
+                    if (!bucket[h]) { e = D++; bucket[h] = e + 1; memcpy(tab + 8 * (size_t)e, d, 32); break; }
+                    e = bucket[h] - 1;
+                    if (!memcmp(tab + 8 * (size_t)e, d, 32)) break;
+                }
+                if (sh.idx_bytes == 1) idx8[sl] = (uint8_t)(e - first);
+                else idx16[sl] = (uint16_t)(e - first);
+            }
+        }
+        const uint32_t words = sh.off_tab + 8u * D;
+        rec[0] = words; rec[1] = D; rec[2] = SSYM_COMPACT_MAGIC;
+        if (out_cap_words - pos < words) return fail(SSYM_ERR_NOMEM, "compact output buffer too small (ssym_stwo_compact_bound gives the worst case)");
+        memcpy(out + pos, rec.data(), (size_t)words * 4);
+        pos += words;
+        offsets[i + 1] = pos;
+    }
+    return SSYM_OK;
+}
+
+static int compact_prepare(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, ssym_stwo_layout_t &lo, CompactShape &sh) {
+    int rc = ssym_stwo_layout(cfg, &lo);
+    if (rc) return rc;
+    if (compact_shape(*cfg, lo, sh)) return fail(SSYM_ERR_INTERNAL, "packed layout is not contiguous in slot order");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return SSYM_OK;
+}
+
+extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets, size_t n,
+                                        uint32_t *packed_out, uint32_t *flags, int memspace) {
+    if (!c || !cfg || ((!blob || !offsets || !packed_out) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    ssym_stwo_layout_t lo;
+    CompactShape sh;
+    int rc = compact_prepare(c, cfg, lo, sh);
+    if (rc || n == 0) return rc;
+    if (n > 0xffffffffull) return fail(SSYM_ERR_USAGE, "batch too large for one call");
+    cudaStream_t s = c->stream;
+    CompactParams p;
+    p.sh = sh; p.lo = lo; p.base = 0; p.n = (uint32_t)n;
+    if (memspace == SSYM_MEM_DEVICE) {
+        p.blob = blob; p.offsets = offsets; p.packed = packed_out; p.flags = flags;
+        launch_stwo_expand(p, s);
+        c->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        return SSYM_OK;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(SSYM_ERR_USAGE, "offsets must be non-decreasing");
+    const size_t words = offsets[n] - offsets[0], out_b = n * (size_t)lo.stride_words * 4;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(c->cstage[0].ensure(words * 4 + 16));
+    CUDA_TRY(c->coffs[0].ensure((n + 1) * sizeof(uint64_t)));
+    CUDA_TRY(c->cflags[0].ensure(n * sizeof(uint32_t)));
+    CUDA_TRY(c->stage[0].ensure(out_b));
+    CUDA_TRY(cudaMemcpyAsync(c->cstage[0].p, blob + offsets[0], words * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->coffs[0].p, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    p.blob = c->cstage[0].as<uint32_t>(); p.offsets = c->coffs[0].as<uint64_t>(); p.base = offsets[0];
+    p.packed = c->stage[0].as<uint32_t>(); p.flags = c->cflags[0].as<uint32_t>();
+    launch_stwo_expand(p, s);
+    c->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(packed_out, p.packed, out_b, cudaMemcpyDeviceToHost, s));
+    if (flags) CUDA_TRY(cudaMemcpyAsync(flags, p.flags, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    return SSYM_OK;
+}
+
+extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets, size_t n,
+                                              uint32_t *accept_bits, uint32_t *status, int memspace) {
+    if (!c || !cfg || !accept_bits || ((!blob || !offsets) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    ssym_stwo_layout_t lo;
+    CompactShape sh;
+    int rc = compact_prepare(c, cfg, lo, sh);
+    if (rc || n == 0) return rc;
+    if (n > 0xffffffffull / SSYM_MAX_QUERIES) return fail(SSYM_ERR_USAGE, "batch too large for one call");
+    rc = ensure_tables(c, *cfg);
+    if (rc) return rc;
+    const size_t stride_b = (size_t)lo.stride_words * 4, max_rec_b = (size_t)(sh.off_tab + 8u * sh.slots) * 4;
+    cudaStream_t s = c->stream;
+    CompactParams p;
+    p.sh = sh; p.lo = lo;
+    if (memspace == SSYM_MEM_DEVICE) { // expand a chunk into HBM scratch, verify it, next chunk (in order on the handle's stream)
+        const size_t cap = std::min(n, STWO_DEVICE_CHUNK);
+        CUDA_TRY(c->stage[0].ensure(cap * stride_b));
+        CUDA_TRY(c->cflags[0].ensure(cap * sizeof(uint32_t)));
+        for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
+            const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
+            p.blob = blob; p.offsets = offsets + done; p.base = 0; p.n = (uint32_t)m;
+            p.packed = c->stage[0].as<uint32_t>(); p.flags = c->cflags[0].as<uint32_t>();
+            launch_stwo_expand(p, s);
+            rc = stwo_launch_chunk(c, c->lanes[0], *cfg, lo, p.packed, m, accept_bits + done / 32, status ? status + done : nullptr, nullptr, s);
+            if (rc) return rc;
+            launch_compact_apply_flags(p.flags, status ? status + done : nullptr, accept_bits + done / 32, (uint32_t)m, s);
+            c->launches += 2;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return SSYM_OK;
+    }
+    // Host buffers: the compact bytes cross the link (double-buffered on the copy stream under the kernels of the previous chunk), the
+    // expanded chunk only ever exists in HBM.
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > max_rec_b / 4) return fail(SSYM_ERR_USAGE, "bad compact offsets");
+    size_t hc = ((n + 3) / 4 + 31) & ~(size_t)31;
+    hc = std::max<size_t>(256, std::min<size_t>(hc, 2048));
+    if (c->host_async) hc = std::max<size_t>(512, std::min<size_t>(((n + 1) / 2 + 31) & ~(size_t)31, 4096));
+    hc = std::min(hc, (n + 31) & ~(size_t)31);
+    const size_t n_words = (n + 31) / 32;
+    bool grow = c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4;
+    for (int b = 0; b < 2; b++)
+        grow = grow || c->stage[b].cap < hc * stride_b || c->cstage[b].cap < hc * max_rec_b || c->coffs[b].cap < (hc + 1) * sizeof(uint64_t) ||
+               c->cflags[b].cap < hc * sizeof(uint32_t);
+    if (c->host_async && grow) { // growing a buffer frees it: drain the calls still using it
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    }
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(c->stage[b].ensure(hc * stride_b));
+        CUDA_TRY(c->cstage[b].ensure(hc * max_rec_b));
+        CUDA_TRY(c->coffs[b].ensure((hc + 1) * sizeof(uint64_t)));
+        CUDA_TRY(c->cflags[b].ensure(hc * sizeof(uint32_t)));
+    }
+    CUDA_TRY(c->d_accept.ensure(n_words * 4));
+    CUDA_TRY(c->d_status.ensure(n * 4));
+    for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
+        const size_t m = std::min(hc, n - done);
+        const int b = (int)(c->host_chunks & 1);
+        if (c->host_chunks >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(c->cstage[b].p, blob + offsets[done], (offsets[done + m] - offsets[done]) * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(c->coffs[b].p, offsets + done, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
+        p.blob = c->cstage[b].as<uint32_t>(); p.offsets = c->coffs[b].as<uint64_t>(); p.base = offsets[done]; p.n = (uint32_t)m;
+        p.packed = c->stage[b].as<uint32_t>(); p.flags = c->cflags[b].as<uint32_t>();
+        launch_stwo_expand(p, s);
+        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, s);
+        if (rc) return rc;
+        launch_compact_apply_flags(p.flags, c->d_status.as<uint32_t>() + done, c->d_accept.as<uint32_t>() + done / 32, (uint32_t)m, s);
+        c->launches += 2;
+        CUDA_TRY(cudaEventRecord(c->ev_done[b], s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     return SSYM_OK;
 }
 

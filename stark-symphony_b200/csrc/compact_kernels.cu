@@ -1,0 +1,98 @@
+// SPDX-License-Identifier: MIT
+#include "compact_kernels.cuh"
+
+namespace ssym {
+
+int compact_shape(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, CompactShape &sh) {
+    const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers, G = cfg.lde_log;
+    sh.trees = L + 3;
+    uint32_t s = 0;
+    for (uint32_t t = 0; t < sh.trees; t++) {
+        sh.slot_first[t] = s;
+        s += Q * (t < 2 ? G : G - 1 - (t - 2));
+    }
+    for (uint32_t t = sh.trees; t <= COMPACT_MAX_TREES; t++) sh.slot_first[t] = s;
+    sh.slots = s;
+    sh.head_slots = 2 * Q * G;
+    sh.idx_bytes = Q * G <= 256 ? 1 : 2;
+    sh.fixed_words = lo.off_trace_sib;
+    sh.wit_words = lo.off_fri_sib[0] - lo.off_fri_wit;
+    sh.off_wit = COMPACT_HDR_WORDS + sh.fixed_words;
+    sh.off_idx = sh.off_wit + sh.wit_words;
+    sh.off_tab = sh.off_idx + ((sh.slots * sh.idx_bytes + 31u) / 32u) * 8u;
+    // the packed sibling sections are contiguous in slot order (trace | composition) and (FRI layer 0 | 1 | ...)
+    if (lo.off_cp_sib != lo.off_trace_sib + Q * G * 8 || lo.off_fri_wit != lo.off_cp_sib + Q * G * 8 || (sh.fixed_words & 7u) || (sh.wit_words & 7u)) return -1;
+    return 0;
+}
+
+namespace {
+
+__global__ void __launch_bounds__(256) stwo_expand_kernel(CompactParams p) {
+    __shared__ uint32_t s_hdr[COMPACT_HDR_WORDS];
+    __shared__ int s_ok;
+    const CompactShape &sh = p.sh;
+    const uint32_t i = blockIdx.x;
+    const uint64_t o0 = p.offsets[i], o1 = p.offsets[i + 1];
+    const uint32_t *rec = p.blob + (o0 - p.base);
+    uint32_t *out = p.packed + (size_t)i * p.lo.stride_words;
+    if (threadIdx.x == 0) {
+        bool ok = o0 >= p.base && o1 >= o0 + sh.off_tab && ((o0 - p.base) & 7u) == 0 && o1 - o0 <= 0xffffffffull;
+        if (ok) {
+            for (int k = 0; k < COMPACT_HDR_WORDS; k++) s_hdr[k] = rec[k];
+            const uint32_t D = s_hdr[1];
+            ok = s_hdr[0] == (uint32_t)(o1 - o0) && s_hdr[2] == SSYM_COMPACT_MAGIC && D <= sh.slots && s_hdr[0] == sh.off_tab + 8u * D && s_hdr[4] == 0;
+            for (uint32_t t = 0; ok && t < sh.trees; t++) ok = s_hdr[4 + t] <= (t + 1 < sh.trees ? s_hdr[5 + t] : D);
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    bool bad = !s_ok;
+    if (!bad) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(rec + COMPACT_HDR_WORDS);
+        uint4 *dst = reinterpret_cast<uint4 *>(out);
+        for (uint32_t k = threadIdx.x; k < sh.fixed_words / 4; k += blockDim.x) dst[k] = __ldg(src + k);
+        src = reinterpret_cast<const uint4 *>(rec + sh.off_wit);
+        dst = reinterpret_cast<uint4 *>(out + p.lo.off_fri_wit);
+        for (uint32_t k = threadIdx.x; k < sh.wit_words / 4; k += blockDim.x) dst[k] = __ldg(src + k);
+        const uint32_t D = s_hdr[1];
+        const uint8_t *idx8 = reinterpret_cast<const uint8_t *>(rec + sh.off_idx);
+        const uint16_t *idx16 = reinterpret_cast<const uint16_t *>(rec + sh.off_idx);
+        const uint4 *tab = reinterpret_cast<const uint4 *>(rec + sh.off_tab);
+        for (uint32_t s = threadIdx.x; s < sh.slots; s += blockDim.x) {
+            uint32_t t = 0;
+            while (t + 1 < sh.trees && s >= sh.slot_first[t + 1]) t++;
+            const uint32_t e = s_hdr[4 + t] + (sh.idx_bytes == 1 ? (uint32_t)idx8[s] : (uint32_t)idx16[s]);
+            const uint32_t lim = t + 1 < sh.trees ? s_hdr[5 + t] : D;
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (e < lim) { a = __ldg(tab + 2 * e); b = __ldg(tab + 2 * e + 1); }
+            else bad = true;
+            uint4 *d = reinterpret_cast<uint4 *>(out + (s < sh.head_slots ? p.lo.off_trace_sib + 8 * s : p.lo.off_fri_sib[0] + 8 * (s - sh.head_slots)));
+            d[0] = a;
+            d[1] = b;
+        }
+    }
+    const int any_bad = __syncthreads_or(bad); // malformed: the record expands to zeros and is flagged
+    if (any_bad) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out);
+        for (uint32_t k = threadIdx.x; k < p.lo.stride_words / 4; k += blockDim.x) dst[k] = make_uint4(0, 0, 0, 0);
+    }
+    if (p.flags && threadIdx.x == 0) p.flags[i] = any_bad ? 1u : 0u;
+}
+
+__global__ void compact_apply_flags_kernel(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || flags[i] == 0) return;
+    if (status) status[i] |= SSYM_ST_SHAPE;
+    atomicAnd(&accept_bits[i >> 5], ~(1u << (i & 31)));
+}
+
+} // namespace
+
+void launch_stwo_expand(const CompactParams &p, cudaStream_t s) {
+    if (p.n) stwo_expand_kernel<<<p.n, 256, 0, s>>>(p);
+}
+void launch_compact_apply_flags(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n, cudaStream_t s) {
+    if (n) compact_apply_flags_kernel<<<(n + 255) / 256, 256, 0, s>>>(flags, status, accept_bits, n);
+}
+
+} // namespace ssym

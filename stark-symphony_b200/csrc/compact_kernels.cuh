@@ -1,0 +1,42 @@
+// SPDX-License-Identifier: MIT
+//
+// Compact transport form of packed Stwo proofs (include/ssym.h "compact transport form"): per tree, every distinct sibling digest
+// once + one index per path slot.  The host link carries the compact bytes; stwo_expand_kernel rebuilds the packed records in HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ssym.h"
+
+namespace ssym {
+
+enum { COMPACT_HDR_WORDS = 16, COMPACT_MAX_TREES = SSYM_MAX_FRI_LAYERS + 2 };
+
+// Section geometry of a compact record for one configuration (host-computed, passed by value).
+struct CompactShape {
+    uint32_t trees;                              // T = n_fri_layers + 3
+    uint32_t slots;                              // sibling slots of a proof, all trees
+    uint32_t slot_first[COMPACT_MAX_TREES + 1];  // first slot of tree t; [T] = slots
+    uint32_t head_slots;                         // slots of the trace + composition trees (contiguous from off_trace_sib); the rest from off_fri_sib[0]
+    uint32_t idx_bytes;                          // 1 or 2
+    uint32_t fixed_words;                        // packed [0, off_trace_sib)
+    uint32_t wit_words;                          // packed [off_fri_wit, off_fri_sib[0])
+    uint32_t off_wit, off_idx, off_tab;          // word offsets inside the compact record (the fixed part starts at COMPACT_HDR_WORDS)
+};
+int compact_shape(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, CompactShape &sh);
+
+struct CompactParams {
+    CompactShape sh;
+    ssym_stwo_layout_t lo;
+    const uint32_t *blob;    // record i at blob + (offsets[i] - base)
+    const uint64_t *offsets; // n + 1, device
+    uint64_t base;
+    uint32_t *packed;        // n * stride_words
+    uint32_t *flags;         // n or nullptr
+    uint32_t n;
+};
+void launch_stwo_expand(const CompactParams &p, cudaStream_t s);
+// status[i] |= SSYM_ST_SHAPE, accept bit i cleared, where flags[i] != 0
+void launch_compact_apply_flags(const uint32_t *flags, uint32_t *status, uint32_t *accept_bits, uint32_t n, cudaStream_t s);
+
+} // namespace ssym

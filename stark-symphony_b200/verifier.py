@@ -151,6 +151,24 @@ class Verifier:
         check(self.lib.ssym_stwo_verify_batch(self.h, C.byref(cfg), _ptr(packed), n, _ptr(accept), _ptr(status), tptr, space))
         return accept, status, traces
 
+    def stwo_compact_expand(self, blob, offsets, cfg: StwoConfig, want_flags: bool = False):
+        """Compact records (witness.compact_stwo) -> packed records, on the GPU (ssym_stwo_compact_expand).  Returns (packed (n, stride_words), flags | None)."""
+        lo = stwo_layout(cfg)
+        n = (offsets.numel() if hasattr(offsets, "numel") else offsets.size) - 1
+        packed = self._alloc(blob, (n, lo.stride_words))
+        flags = self._alloc(blob, n) if want_flags else None
+        check(self.lib.ssym_stwo_compact_expand(self.h, C.byref(cfg), _ptr(blob), _ptr(offsets), n, _ptr(packed), _ptr(flags), self._space(blob)))
+        return packed, flags
+
+    def stwo_verify_compact_batch(self, blob, offsets, cfg: StwoConfig, want_status: bool = False, accept_out=None, status_out=None):
+        """stwo_verify_batch on compact records (include/ssym.h "compact transport form"): with host arrays, the compact bytes are what
+        crosses the host link.  Returns (accept_bits, status | None)."""
+        n = (offsets.numel() if hasattr(offsets, "numel") else offsets.size) - 1
+        accept = accept_out if accept_out is not None else self._alloc(blob, (n + 31) // 32)
+        status = status_out if status_out is not None else (self._alloc(blob, n) if want_status else None)
+        check(self.lib.ssym_stwo_verify_compact_batch(self.h, C.byref(cfg), _ptr(blob), _ptr(offsets), n, _ptr(accept), _ptr(status), self._space(blob)))
+        return accept, status
+
     def stwo_prove_batch(self, seeds, cfg: StwoConfig, out=None):
         """Batched prover for the wide-Fibonacci AIR that verify_proof checks (ssym_stwo_prove_batch, include/ssym.h): one packed
         proof per u64 seed, accepted by stwo_verify_batch in MODE_PROVER_CONSISTENT.  `seeds`: numpy uint64 array (host) or a CUDA

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
-from typing import Any, Dict, List, Sequence, Tuple
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -187,6 +187,23 @@ def pack_stark101_proof_json(proof: Dict[str, Any]) -> np.ndarray:
     if bad[0]:
         raise SsymError("malformed stark101 proof JSON")
     return blob
+
+
+def compact_stwo(packed: np.ndarray, cfg: StwoConfig, out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Packed records -> the compact transport form (ssym_stwo_compact_pack, include/ssym.h): per tree every distinct sibling once plus
+    one index per path slot; lossless for any record.  Returns (blob of u32 words, u64 word offsets [n + 1]); `out` may be a
+    preallocated (e.g. pinned) uint32 array of at least ssym_stwo_compact_bound words."""
+    lib = load()
+    lo = stwo_layout(cfg)
+    flat = np.ascontiguousarray(np.asarray(packed, dtype=np.uint32).ravel())
+    if flat.size % lo.stride_words:
+        raise SsymError("packed length is not a multiple of the proof stride")
+    n = flat.size // lo.stride_words
+    bound = int(lib.ssym_stwo_compact_bound(C.byref(cfg), n))
+    buf = out if out is not None else np.zeros(bound, dtype=np.uint32)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    check(lib.ssym_stwo_compact_pack(C.byref(cfg), C.c_void_p(flat.ctypes.data), n, C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(offsets.ctypes.data)))
+    return (buf if out is not None else buf[:int(offsets[n])].copy()), offsets
 
 
 # ---- corrupted-proof generators (fault injection; the reference has no negative tests) -----------------------

@@ -1,0 +1,190 @@
+"""Compact transport form of packed Stwo proofs (include/ssym.h): the reference's witness carries one full authentication path per query
+(merkle.simf:39-44, evals/verify.simf:20-36, fri/layers.simf:18-24); the compact record keeps every distinct sibling of a tree once.
+The host packer is pinned here by an independent numpy expander (CPU); the GPU expander and ssym_stwo_verify_compact_batch are compared
+with the packed path and the oracle (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import oracle as O
+
+MAGIC = 0x31435353
+
+
+@pytest.fixture(scope="module")
+def S():
+    import stark_symphony_b200 as S
+
+    S.load()
+    return S
+
+
+def ocfg(cfg):
+    return O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
+
+
+def numpy_expand(S, cfg, blob, offsets):
+    """Independent restatement of the record format: compact -> packed."""
+    lo = S.stwo_layout(cfg)
+    Q, L, G = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log
+    depths = [G, G] + [G - 1 - l for l in range(L + 1)]
+    n = len(offsets) - 1
+    out = np.zeros((n, lo.stride_words), dtype=np.uint32)
+    idx_bytes = 1 if Q * G <= 256 else 2
+    fixed, wit = lo.off_trace_sib, lo.off_fri_sib[0] - lo.off_fri_wit
+    slots = Q * sum(depths)
+    idx_words = (slots * idx_bytes + 31) // 32 * 8
+    for i in range(n):
+        rec = blob[int(offsets[i]):int(offsets[i + 1])]
+        assert rec[0] == len(rec) and rec[2] == MAGIC and len(rec) % 8 == 0
+        D = int(rec[1])
+        off_wit = 16 + fixed
+        off_idx = off_wit + wit
+        off_tab = off_idx + idx_words
+        assert len(rec) == off_tab + 8 * D
+        out[i, :fixed] = rec[16:16 + fixed]
+        out[i, lo.off_fri_wit:lo.off_fri_wit + wit] = rec[off_wit:off_idx]
+        idx = rec[off_idx:off_tab].view(np.uint8 if idx_bytes == 1 else np.uint16)
+        tab = rec[off_tab:].reshape(D, 8)
+        s = 0
+        for t, d in enumerate(depths):
+            base = int(rec[4 + t])
+            for k in range(Q * d):
+                dst = lo.off_trace_sib + 8 * s if s < 2 * Q * G else lo.off_fri_sib[0] + 8 * (s - 2 * Q * G)
+                out[i, dst:dst + 8] = tab[base + int(idx[s])]
+                s += 1
+    return out
+
+
+def _records(S, orc, cfg, rng):
+    """honest proofs, corrupted ones, and pure noise (no two siblings equal: the worst case)."""
+    pk = orc.stwo_prove_batch(ocfg(cfg), list(range(90, 96)), threads=4)
+    lo = S.stwo_layout(cfg)
+    recs = [pk[i] for i in range(6)]
+    recs += [S.witness.apply_mutation(pk[0], w, d) for (w, d) in S.witness.stwo_negative_classes(cfg).values()]
+    noise = rng.integers(0, 2**32, size=lo.stride_words, dtype=np.uint64).astype(np.uint32)
+    recs.append(noise)
+    return np.stack(recs)
+
+
+@pytest.mark.parametrize("preset,nc", [("testing", 4), ("prod", 4), ("prod", 16)])
+def test_compact_pack_is_lossless_and_smaller(S, orc, preset, nc):
+    cfg = S.stwo_config(preset, S.MODE_PROVER_CONSISTENT, n_columns=nc)
+    lo = S.stwo_layout(cfg)
+    recs = _records(S, orc, cfg, np.random.default_rng(1))
+    blob, offsets = S.witness.compact_stwo(recs, cfg)
+    assert offsets[0] == 0 and offsets[-1] == blob.size and (np.diff(offsets.astype(np.int64)) % 8 == 0).all()
+    assert (numpy_expand(S, cfg, blob, offsets) == recs).all()
+    sizes = np.diff(offsets.astype(np.int64)) * 4
+    bound = S.load().ssym_stwo_compact_bound(__import__("ctypes").byref(cfg), 1) * 4
+    assert sizes[-1] == bound  # noise: nothing to share
+    if preset == "prod":
+        assert (sizes[:6] < 0.80 * lo.stride_words * 4).all(), sizes[:6]  # honest proofs: >= 20 % fewer bytes on the link
+    # the shipped fixture
+    if nc == 4:
+        text = open(os.path.join(GOLDEN, f"stwo_proof_{preset}.wit")).read()
+        packed, bad = S.witness.pack_stwo_wits([text], cfg)
+        b2, o2 = S.witness.compact_stwo(packed, cfg)
+        assert not bad[0] and (numpy_expand(S, cfg, b2, o2)[0] == packed).all()
+
+
+def test_compact_pack_errors(S, orc):
+    import ctypes as C
+
+    cfg = S.stwo_config("testing", 1)
+    pk = orc.stwo_prove_batch(ocfg(cfg), [1, 2])
+    small = np.zeros(40, dtype=np.uint32)
+    with pytest.raises(S.SsymError):
+        S.witness.compact_stwo(pk, cfg, out=small)
+    blob, offsets = S.witness.compact_stwo(pk[:0], cfg)
+    assert blob.size == 0 and list(offsets) == [0]
+    assert S.load().ssym_stwo_compact_bound(C.byref(S.stwo_config("prod", 0, n_columns=5)), 3) == 0
+
+
+# ---- GPU ----------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ver(S):
+    return S.Verifier(0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,nc", [("testing", 4), ("prod", 4), ("prod", 8)])
+def test_gpu_expand_and_verify_compact(S, ver, orc, preset, nc):
+    import torch
+
+    cfg = S.stwo_config(preset, S.MODE_PROVER_CONSISTENT, n_columns=nc)
+    recs = _records(S, orc, cfg, np.random.default_rng(2))
+    n = len(recs)
+    blob, offsets = S.witness.compact_stwo(recs, cfg)
+    # host buffers
+    packed, flags = ver.stwo_compact_expand(blob, offsets, cfg, want_flags=True)
+    assert (packed == recs).all() and not flags.any()
+    # device buffers
+    d_blob, d_off = torch.from_numpy(blob.view(np.int32)).cuda(), torch.from_numpy(offsets.view(np.int64)).cuda()
+    d_packed, d_flags = ver.stwo_compact_expand(d_blob, d_off, cfg, want_flags=True)
+    ver.synchronize()
+    assert (d_packed.cpu().numpy().view(np.uint32) == recs).all() and not d_flags.cpu().numpy().any()
+    for mode in (S.MODE_PROVER_CONSISTENT, S.MODE_REF_LITERAL):
+        cfg.mode = mode
+        ref_accept, ref_status, _ = ver.stwo_verify_batch(recs.ravel(), cfg, n, want_status=True)
+        _, o_status, _ = orc.stwo_verify_batch(ocfg(cfg), recs.ravel(), n)
+        assert (ref_status == o_status).all()
+        accept, status = ver.stwo_verify_compact_batch(blob, offsets, cfg, want_status=True)
+        assert (status == ref_status).all() and (accept == ref_accept).all()
+        d_accept, d_status = ver.stwo_verify_compact_batch(d_blob, d_off, cfg, want_status=True)
+        ver.synchronize()
+        assert (d_status.cpu().numpy().view(np.uint32) == ref_status).all() and (d_accept.cpu().numpy().view(np.uint32) == ref_accept).all()
+        if mode == S.MODE_PROVER_CONSISTENT:
+            assert (status[:6] == 0).all() and (status[6:] != 0).all()
+
+
+@pytest.mark.gpu
+def test_gpu_malformed_compact_records_are_rejected(S, ver, orc):
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    lo = S.stwo_layout(cfg)
+    pk = orc.stwo_prove_batch(ocfg(cfg), [5, 6, 7, 8, 9, 10], threads=4)
+    blob, offsets = S.witness.compact_stwo(pk, cfg)
+    blob = blob.copy()
+    o = [int(x) for x in offsets]
+    blob[o[1] + 2] ^= 1                  # magic
+    blob[o[2] + 1] += 1                  # table size does not match the record length
+    blob[o[3] + 5] = blob[o[3] + 1] + 1  # a tree's table starts beyond the table
+    fixed, wit = lo.off_trace_sib, lo.off_fri_sib[0] - lo.off_fri_wit
+    idx = blob[o[4] + 16 + fixed + wit:].view(np.uint8)
+    idx[3] = 255                         # an index outside the trace tree's table
+    packed, flags = ver.stwo_compact_expand(blob, offsets, cfg, want_flags=True)
+    assert list(flags) == [0, 1, 1, 1, 1, 0]
+    assert (packed[[0, 5]] == pk[[0, 5]]).all() and not packed[1:5].any()
+    accept, status = ver.stwo_verify_compact_batch(blob, offsets, cfg, want_status=True)
+    assert status[0] == 0 and status[5] == 0 and (status[1:5] >> 31 == 1).all() and int(accept[0]) & 63 == 0b100001
+    bad_off = offsets.copy()
+    bad_off[2] = bad_off[1] - 8
+    with pytest.raises(S.SsymError):
+        ver.stwo_verify_compact_batch(blob, bad_off, cfg)
+
+
+@pytest.mark.gpu
+def test_gpu_compact_host_path_chunks_and_async(S, ver, orc):
+    """3000 records (several double-buffered chunks), every 7th corrupted; synchronous and enqueue-only calls give the packed path's bitmap."""
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    n = 3000
+    proofs = ver.stwo_prove_batch(np.arange(n, dtype=np.uint64) + 40000, cfg)
+    classes = list(S.witness.stwo_negative_classes(cfg).values())
+    for j, row in enumerate(range(3, n, 7)):
+        w, d = classes[j % len(classes)]
+        proofs[row, w] = np.uint32((int(proofs[row, w]) + d) & 0xFFFFFFFF)
+    blob, offsets = S.witness.compact_stwo(proofs, cfg)
+    ref_accept, ref_status, _ = ver.stwo_verify_batch(proofs.ravel(), cfg, n, want_status=True)
+    accept, status = ver.stwo_verify_compact_batch(blob, offsets, cfg, want_status=True)
+    assert (status == ref_status).all() and (accept == ref_accept).all()
+    expect_bad = np.zeros(n, dtype=bool)
+    expect_bad[3::7] = True
+    assert ((status != 0) == expect_bad).all()
+    ver.set_host_async(True)
+    outs = [ver.stwo_verify_compact_batch(blob, offsets, cfg, want_status=True) for _ in range(3)]
+    ver.synchronize()
+    ver.set_host_async(False)
+    for a, st in outs:
+        assert (st == ref_status).all() and (a == ref_accept).all()
