@@ -9,8 +9,8 @@ only exchange is the accept-bitmap gather.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 1024] [--mode ref-literal|prover-consistent]
 
 `value`  : whole-job proofs/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).
-`e2e`    : the same metric through the C-ABI with HOST (pinned) buffers: H2D of the packed batch + D2H of the bitmap
-           inside the timed region.
+`e2e`    : the same metric through the C-ABI with HOST (pinned) buffers: H2D of the batch (compact transport form) + D2H of the
+           bitmap inside the timed region; `e2e_packed`: the same on fixed-stride packed records; `e2e_wit`: from `.wit` text.
 `roofline` / `roofline_int32` : the dominant kernel (stwo_merkle_kernel) against HBM and against the measured INT32 rate.
 `cpu_baseline` : the C oracle (a port of the .simf programs; the reference binary cannot be built here) on the host cores.
 """
@@ -437,6 +437,48 @@ def main():
     e2e_value = total_n * e2e_steps / float(t[0].item())
     e2e_sync_value = total_n * e2e_steps / float(t[1].item())
 
+    # the same, with the batch in the compact transport form (include/ssym.h: per tree every distinct sibling once + one index per path
+    # slot; made by the host packer ssym_stwo_compact_pack, lossless): fewer bytes cross the link, the GPU expands them into HBM
+    bound_words = int(S.load().ssym_stwo_compact_bound(C.byref(cfg), n))
+    c_pinned = torch.empty(bound_words, dtype=torch.int32).pin_memory()
+    c_blob_full, c_off_np = S.witness.compact_stwo(host_batch, cfg, out=c_pinned.numpy().view(np.uint32))
+    c_words = int(c_off_np[n])
+    c_blob = c_blob_full[:c_words]
+    c_off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+    c_off.numpy()[:] = c_off_np.view(np.int64)
+    c_off_view = c_off.numpy().view(np.uint64)
+    acc_c = torch.empty((n + 31) // 32, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    for _ in range(3):
+        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_c)
+    assert (acc_c == acc_host).all(), "compact path disagrees with the packed path"
+    cl0 = ver.launch_count
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_c)
+    c_sync_s = time.perf_counter() - t0
+    c_launches = (ver.launch_count - cl0) // e2e_steps
+    ver.set_host_async(True)
+    for k in range(3):
+        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_rows_np[k])
+    ver.synchronize()
+    acc_rows_np[:] = 0xA5A5A5A5
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_rows_np[k])
+    ver.synchronize()
+    c_s = time.perf_counter() - t0
+    ver.set_host_async(False)
+    assert (acc_rows_np == acc_host[None, :]).all(), "asynchronous compact results differ from the synchronous packed call"
+    t = torch.tensor([c_s, c_sync_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c_value = total_n * e2e_steps / float(t[0].item())
+    c_sync_value = total_n * e2e_steps / float(t[1].item())
+
     # end to end from the reference's own input format: `.wit` JSON TEXT in pinned host memory -> accept bits
     # (ssym_stwo_verify_wit_batch: text H2D, GPU tokeniser + packer, verifier, D2H bitmap; 122 KB of text per proof)
     wit_raw = open(os.path.join(ROOT, "tests", "golden", "stwo_proof_prod.wit"), "rb").read()
@@ -492,7 +534,17 @@ def main():
                                    "so fewer compressions are executed than the reference's per-query count"},
             "merkle_hashes_per_s": value * MERKLE_COMPRESSIONS_PER_PROOF / 2.0,
             "sha256_compressions_per_s": value * COMPRESSIONS_PER_PROOF,
-            "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n * lo.stride_words * 4), "d2h_bytes_per_step": int(acc_host.nbytes),
+            "e2e": {"value": c_value, "unit": "proofs/s", "h2d_bytes_per_step": int(c_words * 4 + c_off.numpy().nbytes), "d2h_bytes_per_step": int(acc_c.nbytes),
+                    "steps": e2e_steps, "h2d_gbs_achieved": c_value / world * (c_words * 4 + c_off.numpy().nbytes) / n / 1e9, "h2d_gbs_plain_copy": h2d_gbs,
+                    "sync_call_value": c_sync_value, "bytes_per_proof": c_words * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
+                    "gpu_launches_per_step": int(c_launches),
+                    "note": "ssym_stwo_verify_compact_batch(SSYM_MEM_HOST) on pinned host buffers holding the batch in the compact transport form "
+                            "(include/ssym.h: per Merkle tree every distinct 32-byte sibling once + one index per path slot; produced by the host packer "
+                            "ssym_stwo_compact_pack, lossless for any record, expanded on the GPU by stwo_expand_kernel): chunked double-buffered H2D -> "
+                            "expand -> verifier kernels -> D2H bitmap, every step's copies inside the timed region.  `value`: calls enqueued back to back "
+                            "(ssym_set_host_async), one synchronize; `sync_call_value`: each call returns with its bitmap in host memory.  Bound by the "
+                            "host link; `e2e_packed` is the same measurement on the fixed-stride packed records (25 % more bytes)"},
+            "e2e_packed": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n * lo.stride_words * 4), "d2h_bytes_per_step": int(acc_host.nbytes),
                     "steps": e2e_steps, "h2d_gbs_achieved": e2e_value / world * lo.stride_words * 4 / 1e9, "h2d_gbs_plain_copy": h2d_gbs,
                     "sync_call_value": e2e_sync_value,
                     "note": "ssym_stwo_verify_batch(SSYM_MEM_HOST) on pinned host buffers: chunked double-buffered H2D -> kernels -> D2H bitmap, every step's "
