@@ -89,7 +89,9 @@ struct ssym_ctx {
     EventProfiler profiler;
     bool profiling = false;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // host-buffer staging: HOST_BUFS chunks in flight (copy of chunk k + 1.. under the kernels of chunk k), chunk k on lane k % HOST_BUFS
+    static const int HOST_BUFS = 4;
+    cudaEvent_t ev_h2d[HOST_BUFS] = {nullptr, nullptr, nullptr, nullptr}, ev_done[HOST_BUFS] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;
     // Pipeline lanes: call k of ssym_stwo_verify_batch(SSYM_MEM_DEVICE) runs on lane k % depth, each lane with its own
     // stream and scratch, so consecutive calls overlap on the GPU (the channel kernel of call k+1 is a latency-bound
@@ -114,8 +116,8 @@ struct ssym_ctx {
     uint32_t tab_G = 0, tab_L = 0xffffffffu;
     uint32_t fold_off[SSYM_MAX_FRI_LAYERS] = {0};
     // host-memspace staging
-    DevBuf stage[2], d_accept, d_status, d_trace, d_offsets;
-    DevBuf cstage[2], coffs[2], cflags[2]; // compact transport: compact chunk, its offsets, malformed-record flags (stage[] holds the expanded chunk)
+    DevBuf stage[HOST_BUFS], d_accept, d_status, d_trace, d_offsets;
+    DevBuf cstage[HOST_BUFS], coffs[HOST_BUFS], cflags[HOST_BUFS]; // compact transport: compact chunk, its offsets, malformed-record flags (stage[] holds the expanded chunk)
     // prover: twiddle tables per (trace_log, lde_log) and per-chunk scratch
     DevBuf prv_tw[2], prv_itw[2], prv_vanish, prv_flag, prv_seeds, prv_out;
     DevBuf prv_scratch[9];
@@ -159,9 +161,11 @@ int ssym_create(int device, ssym_ctx_t **out) {
     c->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ssym_ctx::HOST_BUFS; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wit_flags[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wit_parsed[i], cudaEventDisableTiming));
     }
@@ -192,7 +196,12 @@ void ssym_destroy(ssym_ctx_t *c) {
         cudaEventDestroy(l.in);
         cudaEventDestroy(l.done);
     }
-    DevBuf *bufs[] = {&c->tab_point, &c->tab_fold, &c->tab_flag, &c->stage[0], &c->stage[1],
+    for (int i = 0; i < ssym_ctx::HOST_BUFS; i++) {
+        c->stage[i].release(); c->cstage[i].release(); c->coffs[i].release(); c->cflags[i].release();
+        cudaEventDestroy(c->ev_h2d[i]);
+        cudaEventDestroy(c->ev_done[i]);
+    }
+    DevBuf *bufs[] = {&c->tab_point, &c->tab_fold, &c->tab_flag,
                       &c->d_accept, &c->d_status, &c->d_trace, &c->d_offsets, &c->s101_ctx};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : c->tmp) b.release();
@@ -202,12 +211,9 @@ void ssym_destroy(ssym_ctx_t *c) {
     for (auto &row : c->fold_table)
         for (DevBuf &b : row) b.release();
     for (int i = 0; i < 2; i++) {
-        cudaEventDestroy(c->ev_h2d[i]);
-        cudaEventDestroy(c->ev_done[i]);
         cudaEventDestroy(c->ev_wit_flags[i]);
         cudaEventDestroy(c->ev_wit_parsed[i]);
         c->wit_text[i].release(); c->wit_offs[i].release(); c->wit_packed[i].release(); c->wit_flags[i].release(); c->wit_numpos[i].release();
-        c->cstage[i].release(); c->coffs[i].release(); c->cflags[i].release();
         if (c->wit_hflags[i]) cudaFreeHost(c->wit_hflags[i]);
         if (c->wit_hoffs[i]) cudaFreeHost(c->wit_hoffs[i]);
     }
@@ -396,6 +402,21 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
     return SSYM_OK;
 }
 
+// Host-buffer calls run chunk k's kernels on lane (k % HOST_BUFS)'s own stream: the latency-bound channel kernel of one chunk then overlaps the Merkle
+// kernel of the other instead of queueing behind it (a 256-proof chunk is 0.15 ms of channel kernel + 0.1 ms of everything else).
+// host_fork orders both lane streams after what the handle's stream holds (e.g. the previous call's D2H of the shared result buffers);
+// host_join orders the handle's stream after the chunks.
+static int host_fork(ssym_ctx *c) {
+    CUDA_TRY(cudaEventRecord(c->lanes[0].in, c->stream));
+    for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) CUDA_TRY(cudaStreamWaitEvent(c->lanes[b].s, c->lanes[0].in, 0));
+    return SSYM_OK;
+}
+static int host_join(ssym_ctx *c, const bool (&used)[ssym_ctx::HOST_BUFS]) {
+    for (int b = 0; b < ssym_ctx::HOST_BUFS; b++)
+        if (used[b]) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done[b], 0));
+    return SSYM_OK;
+}
+
 extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n,
                                       uint32_t *accept_bits, uint32_t *status, ssym_stwo_trace_t *trace, int memspace) {
     if (!c || !cfg || !accept_bits || (!packed && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
@@ -441,29 +462,37 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     if (c->host_async) hc = std::max<size_t>(512, std::min<size_t>(((n + 1) / 2 + 31) & ~(size_t)31, 4096));
     hc = std::min(hc, (n + 31) & ~(size_t)31);
     const size_t n_words = (n + 31) / 32;
-    if (c->host_async && (c->stage[0].cap < hc * stride_b || c->stage[1].cap < hc * stride_b || c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4 ||
+    bool grow_stage = false;
+    for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) grow_stage = grow_stage || c->stage[b].cap < hc * stride_b;
+    if (c->host_async && (grow_stage || c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4 ||
                           (trace && c->d_trace.cap < n * sizeof(ssym_stwo_trace_t)))) { // growing a buffer frees it: drain the calls still using it
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     }
-    CUDA_TRY(c->stage[0].ensure(hc * stride_b));
-    CUDA_TRY(c->stage[1].ensure(hc * stride_b));
+    for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) CUDA_TRY(c->stage[b].ensure(hc * stride_b));
     CUDA_TRY(c->d_accept.ensure(n_words * 4));
     CUDA_TRY(c->d_status.ensure(n * 4));
     if (trace) CUDA_TRY(c->d_trace.ensure(n * sizeof(ssym_stwo_trace_t)));
     cudaStream_t s = c->stream;
+    rc = host_fork(c);
+    if (rc) return rc;
+    bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
     for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
         const size_t m = std::min(hc, n - done);
-        const int b = (int)(c->host_chunks & 1);
-        if (c->host_chunks >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        const int b = (int)(c->host_chunks % ssym_ctx::HOST_BUFS);
+        cudaStream_t ls = c->profiling ? s : c->lanes[b].s; // per-kernel event timing wants one strictly serial stream
+        if (c->host_chunks >= (uint64_t)ssym_ctx::HOST_BUFS) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
         CUDA_TRY(cudaMemcpyAsync(c->stage[b].p, packed + done * (size_t)lo.stride_words, m * stride_b, cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
-        CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
+        CUDA_TRY(cudaStreamWaitEvent(ls, c->ev_h2d[b], 0));
         rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, c->stage[b].as<uint32_t>(), m, c->d_accept.as<uint32_t>() + done / 32,
-                               c->d_status.as<uint32_t>() + done, trace ? c->d_trace.as<ssym_stwo_trace_t>() + done : nullptr, s);
+                               c->d_status.as<uint32_t>() + done, trace ? c->d_trace.as<ssym_stwo_trace_t>() + done : nullptr, ls);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(c->ev_done[b], s));
+        CUDA_TRY(cudaEventRecord(c->ev_done[b], ls));
+        used[b] = true;
     }
+    rc = host_join(c, used);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
     if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_stwo_trace_t), cudaMemcpyDeviceToHost, s));
@@ -637,14 +666,14 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     hc = std::min(hc, (n + 31) & ~(size_t)31);
     const size_t n_words = (n + 31) / 32;
     bool grow = c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4;
-    for (int b = 0; b < 2; b++)
+    for (int b = 0; b < ssym_ctx::HOST_BUFS; b++)
         grow = grow || c->stage[b].cap < hc * stride_b || c->cstage[b].cap < hc * max_rec_b || c->coffs[b].cap < (hc + 1) * sizeof(uint64_t) ||
                c->cflags[b].cap < hc * sizeof(uint32_t);
     if (c->host_async && grow) { // growing a buffer frees it: drain the calls still using it
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) {
         CUDA_TRY(c->stage[b].ensure(hc * stride_b));
         CUDA_TRY(c->cstage[b].ensure(hc * max_rec_b));
         CUDA_TRY(c->coffs[b].ensure((hc + 1) * sizeof(uint64_t)));
@@ -652,23 +681,30 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     }
     CUDA_TRY(c->d_accept.ensure(n_words * 4));
     CUDA_TRY(c->d_status.ensure(n * 4));
+    rc = host_fork(c);
+    if (rc) return rc;
+    bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
     for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
         const size_t m = std::min(hc, n - done);
-        const int b = (int)(c->host_chunks & 1);
-        if (c->host_chunks >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        const int b = (int)(c->host_chunks % ssym_ctx::HOST_BUFS);
+        cudaStream_t ls = c->profiling ? s : c->lanes[b].s;
+        if (c->host_chunks >= (uint64_t)ssym_ctx::HOST_BUFS) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
         CUDA_TRY(cudaMemcpyAsync(c->cstage[b].p, blob + offsets[done], (offsets[done + m] - offsets[done]) * 4, cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_TRY(cudaMemcpyAsync(c->coffs[b].p, offsets + done, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
-        CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
+        CUDA_TRY(cudaStreamWaitEvent(ls, c->ev_h2d[b], 0));
         p.blob = c->cstage[b].as<uint32_t>(); p.offsets = c->coffs[b].as<uint64_t>(); p.base = offsets[done]; p.n = (uint32_t)m;
         p.packed = c->stage[b].as<uint32_t>(); p.flags = c->cflags[b].as<uint32_t>();
-        launch_stwo_expand(p, s);
-        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, s);
+        launch_stwo_expand(p, ls);
+        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls);
         if (rc) return rc;
-        launch_compact_apply_flags(p.flags, c->d_status.as<uint32_t>() + done, c->d_accept.as<uint32_t>() + done / 32, (uint32_t)m, s);
+        launch_compact_apply_flags(p.flags, c->d_status.as<uint32_t>() + done, c->d_accept.as<uint32_t>() + done / 32, (uint32_t)m, ls);
         c->launches += 2;
-        CUDA_TRY(cudaEventRecord(c->ev_done[b], s));
+        CUDA_TRY(cudaEventRecord(c->ev_done[b], ls));
+        used[b] = true;
     }
+    rc = host_join(c, used);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
     if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize

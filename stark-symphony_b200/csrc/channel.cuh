@@ -20,7 +20,7 @@ static __device__ __noinline__ void sha_compress_call(uint32_t *h, const uint32_
     for (int i = 0; i < 8; i++) hh[i] = h[i];
 #pragma unroll
     for (int i = 0; i < 16; i++) w[i] = blk[i];
-    sha_compress(hh, w);
+    sha_compress_rolled<0>(hh, w, ShaAdd<0>(1u)); // 4 x 16 rounds: the body stays resident in the instruction cache of an SM that runs one warp of this
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] = hh[i];
 }
