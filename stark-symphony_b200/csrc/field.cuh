@@ -131,6 +131,28 @@ __device__ __forceinline__ QM31 qm31_mul(QM31 x, QM31 y) {
     const uint32_t ib = m31_reduce64((uint64_t)a0 * b3 + (uint64_t)a1 * b2 + (uint64_t)a2 * b1 + (uint64_t)a3 * b0);
     return qm31(ra, rb, ia, ib);
 }
+// circle_fold / line_fold without the twiddle lookup (fri/folding.simf:21-26, 35-40):
+//     f0 = e0 + e1,  f1 = (e0 - e1) * inv,  result = f0 + alpha * f1          (qm31_add, qm31_sub, qm31_mul_m31, qm31_mul, qm31_add)
+// for ANY u32 inputs.  Every step of the reference formula is exact modulo p on the residues of its operands except that the
+// 32-bit adds wrap first ((a + b) mod 2^32, a + (p - b) mod 2^32: m31.simf:22-37) — so the wrapped sums are formed literally and
+// everything after them is residue arithmetic with a canonical result: alpha * ((e0 - e1) * inv) = (alpha * inv) * (e0 - e1), the 16
+// products and the wrapped f0 accumulated in 64 bits, 6 reductions in all (the step-by-step form has 20 products, 4 + 8 + 4 + 6 + 4).
+__device__ __forceinline__ QM31 qm31_fold(QM31 e0, QM31 e1, M31 inv, QM31 alpha) {
+    const uint32_t s0 = e0.r.a + e1.r.a, s1 = e0.r.b + e1.r.b, s2 = e0.i.a + e1.i.a, s3 = e0.i.b + e1.i.b; // f0 before its reduction
+    const uint32_t b0 = m31_reduce(e0.r.a + (SSYM_P - e1.r.a)), b1 = m31_reduce(e0.r.b + (SSYM_P - e1.r.b));
+    const uint32_t b2 = m31_reduce(e0.i.a + (SSYM_P - e1.i.a)), b3 = m31_reduce(e0.i.b + (SSYM_P - e1.i.b));
+    const uint32_t ic = m31_reduce(inv);
+    const uint32_t a0 = m31_mul_c(m31_reduce(alpha.r.a), ic), a1 = m31_mul_c(m31_reduce(alpha.r.b), ic);
+    const uint32_t a2 = m31_mul_c(m31_reduce(alpha.i.a), ic), a3 = m31_mul_c(m31_reduce(alpha.i.b), ic);
+    const uint32_t n1 = SSYM_P - b1, n3 = SSYM_P - b3;
+    const uint32_t ya = m31_reduce64((uint64_t)a2 * b2 + (uint64_t)a3 * n3);
+    const uint32_t yb = m31_reduce64((uint64_t)a2 * b3 + (uint64_t)a3 * b2);
+    const uint32_t ra = m31_reduce64((uint64_t)a0 * b0 + (uint64_t)a1 * n1 + ((uint64_t)ya << 1) + (SSYM_P - yb) + s0);
+    const uint32_t rb = m31_reduce64((uint64_t)a0 * b1 + (uint64_t)a1 * b0 + ((uint64_t)yb << 1) + ya + s1);
+    const uint32_t ia = m31_reduce64((uint64_t)a0 * b2 + (uint64_t)a1 * n3 + (uint64_t)a2 * b0 + (uint64_t)a3 * n1 + s2); // < 2^64 - 2^34 + 2^32
+    const uint32_t ib = m31_reduce64((uint64_t)a0 * b3 + (uint64_t)a1 * b2 + (uint64_t)a2 * b1 + (uint64_t)a3 * b0 + s3);
+    return qm31(ra, rb, ia, ib);
+}
 __device__ __forceinline__ QM31 qm31_inv(QM31 x, bool &fail) {                                                                // qm31.simf:87-98
     CM31 ar_sq = cm31_mul(x.r, x.r);
     CM31 ai_sq = cm31_mul(x.i, x.i);

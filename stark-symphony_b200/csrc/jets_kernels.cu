@@ -260,10 +260,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint32_t *position, con
         } else {
             inv = fold_twiddle_inv<CIRCLE>(position_i, log_size, f);
         }
-        const QM31 a = qm31_load4(f_p + 4 * i), b = qm31_load4(f_neg_p + 4 * i);
-        const QM31 f0 = qm31_add(a, b);
-        const QM31 f1 = qm31_mul_m31(qm31_sub(a, b), inv);
-        qm31_store4(out + 4 * i, qm31_add(f0, qm31_mul(qm31_load4(alpha + 4 * i), f1)));
+        qm31_store4(out + 4 * i, qm31_fold(qm31_load4(f_p + 4 * i), qm31_load4(f_neg_p + 4 * i), inv, qm31_load4(alpha + 4 * i)));
         if (fail) fail[i] = f;
     }
 }

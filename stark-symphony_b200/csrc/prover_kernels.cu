@@ -466,8 +466,7 @@ __global__ void __launch_bounds__(128) prv_fold_kernel(PrvParams p, uint32_t lay
     const QM31 e0 = qm31_load4(src), e1 = qm31_load4(src + 4);
     const uint32_t inv = __ldg(p.lde.itw + ((1u << G) - (1u << n)) + j);
     const QM31 alpha = qm31_load4(p.pctx + (size_t)i * PC::WORDS + PC::FRI_ALPHA + 4 * layer);
-    const QM31 f0 = qm31_add(e0, e1), f1 = qm31_mul_m31(qm31_sub(e0, e1), inv);
-    qm31_store4(p.fev + (size_t)i * p.fev_stride + p.fev_off[layer + 1] + 4 * j, qm31_add(f0, qm31_mul(alpha, f1)));
+    qm31_store4(p.fev + (size_t)i * p.fev_stride + p.fev_off[layer + 1] + 4 * j, qm31_fold(e0, e1, inv, alpha));
 }
 
 // ------------------------------------------------------------------------------------------

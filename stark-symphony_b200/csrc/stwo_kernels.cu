@@ -310,9 +310,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
                 status |= SSYM_ST_FOLD_INV_ZERO;
                 if (tr) atomicOr(&tr->mask_fold_inv[l], 1u << q);
             }
-            const QM31 f0 = qm31_add(e0, e1);
-            const QM31 f1 = qm31_mul_m31(qm31_sub(e0, e1), inv);
-            eval = qm31_add(f0, qm31_mul(qm31_load4(ctx + CX::FRI_ALPHA + 4 * l), f1));
+            eval = qm31_fold(e0, e1, inv, qm31_load4(ctx + CX::FRI_ALPHA + 4 * l)); // circle_fold / line_fold, fri/folding.simf:15-41
             if (tr) qm31_store(tr->folded[l][q], eval);
             fq >>= 1; // divide_32(position, 2)
         }
