@@ -39,10 +39,17 @@ __device__ __forceinline__ M31 m31_mul_c(M31 a, M31 b) {
     const uint32_t s = ((uint32_t)x & SSYM_P) + (uint32_t)(x >> 31); // < 2^32
     return s >= SSYM_P ? s - SSYM_P : s;
 }
+// The same product with one operand pre-doubled: (2a) * b = 2ab puts floor(ab / 2^31) in the high word and 2 * (ab mod 2^31) in the low
+// word, so the Mersenne fold is one shift-and-add (LEA.HI) instead of and + funnel shift + add.  a, b canonical; same value as m31_mul.
+__device__ __forceinline__ M31 m31_mul_d(uint32_t a_doubled, M31 b) {
+    const uint64_t x = (uint64_t)a_doubled * b;
+    const uint32_t s = (uint32_t)(x >> 32) + ((uint32_t)x >> 1); // < 2^32
+    return s >= SSYM_P ? s - SSYM_P : s;
+}
 template <int N>
 __device__ __forceinline__ M31 m31_sqn(M31 a) { // a canonical
 #pragma unroll
-    for (int i = 0; i < N; i++) a = m31_mul_c(a, a);
+    for (int i = 0; i < N; i++) a = m31_mul_d(a << 1, a);
     return a;
 }
 // a^(p-2) by the reference's addition chain; *fail |= (a == 0 bitwise)   fields/m31.simf:117-132
@@ -52,13 +59,15 @@ __device__ __forceinline__ M31 m31_sqn(M31 a) { // a canonical
 __device__ __forceinline__ M31 m31_inv(M31 a, bool &fail) {
     fail = fail || (a == 0);
     a = m31_reduce(a);
-    M31 t0 = m31_mul_c(m31_sqn<2>(a), a);    // a^5
-    M31 t1 = m31_mul_c(m31_sqn<1>(t0), t0);  // a^15
-    M31 t2 = m31_mul_c(m31_sqn<3>(t1), t0);  // a^125
-    M31 t3 = m31_mul_c(m31_sqn<1>(t2), t0);  // a^255
-    M31 t4 = m31_mul_c(m31_sqn<8>(t3), t3);  // a^65535
-    M31 t5 = m31_mul_c(m31_sqn<8>(t4), t3);  // a^16777215
-    return m31_mul_c(m31_sqn<7>(t5), t2);    // a^2147483645
+    M31 t0 = m31_mul_d(a << 1, m31_sqn<2>(a));    // a^5
+    const uint32_t t0d = t0 << 1;
+    M31 t1 = m31_mul_d(t0d, m31_sqn<1>(t0));       // a^15
+    M31 t2 = m31_mul_d(t0d, m31_sqn<3>(t1));       // a^125
+    M31 t3 = m31_mul_d(t0d, m31_sqn<1>(t2));       // a^255
+    const uint32_t t3d = t3 << 1;
+    M31 t4 = m31_mul_d(t3d, m31_sqn<8>(t3));       // a^65535
+    M31 t5 = m31_mul_d(t3d, m31_sqn<8>(t4));       // a^16777215
+    return m31_mul_d(t2 << 1, m31_sqn<7>(t5));     // a^2147483645
 }
 
 struct CM31 {

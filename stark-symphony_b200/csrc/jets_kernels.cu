@@ -6,6 +6,8 @@
 // The field kernels are HBM-bound: 128-bit loads/stores, grid-stride over 148 x 8 CTAs.
 #include "jets_kernels.cuh"
 
+#include <cstdlib>
+
 #include "field.cuh"
 #include "sha256.cuh"
 
@@ -39,58 +41,71 @@ __global__ void __launch_bounds__(256) m31_binary_kernel(const uint32_t *a, cons
     }
     for (size_t i = nv * 4 + tid; i < n; i += stride) out[i] = m31_op<OP>(a[i], OP == JET_M31_NEG ? 0u : b[i]);
 }
+#ifndef M31_INV_K
+#define M31_INV_K 16 // elements inverted per thread with one addition chain (SSYM_M31_INV_K: 8 / 16 / 32)
+#endif
 // Inverses K at a time (Montgomery's trick): the prefix products of the K residues, ONE addition-chain inversion (fields/m31.simf:117-132) of
 // their product, and a back-substitution — 3 (K - 1) + 37 products instead of 37 K.  The inverse of a non-zero residue is unique, so every
 // output is the canonical value the per-element chain gives; a zero residue is taken out of the product and gets the chain's 0.
 // On entry v[k] = canonical residues; on return their inverses (0 for 0).
 template <int K>
 __device__ __forceinline__ void m31_batch_inv(uint32_t (&v)[K]) {
-    uint32_t pfx[K], nz[K];
+    uint32_t pfx[K], zmask = 0; // v[k] is overwritten by 2 * (the residue, or 1 for a zero): the pre-doubled operand of m31_mul_d
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        nz[k] = v[k] ? v[k] : 1u;
-        pfx[k] = k ? m31_mul_c(pfx[k - 1], nz[k]) : nz[0];
+        const bool z = v[k] == 0;
+        zmask |= (z ? 1u : 0u) << k;
+        v[k] = z ? 2u : v[k] << 1;
+        pfx[k] = k ? m31_mul_d(v[k], pfx[k - 1]) : v[0] >> 1;
     }
     bool dummy = false;
     uint32_t inv = m31_inv(pfx[K - 1], dummy); // product of non-zero residues: never zero
 #pragma unroll
     for (int k = K - 1; k >= 1; k--) {
-        const uint32_t mine = m31_mul_c(inv, pfx[k - 1]);
-        inv = m31_mul_c(inv, nz[k]);
-        v[k] = v[k] ? mine : 0u;
+        const uint32_t mine = m31_mul_d(inv << 1, pfx[k - 1]);
+        inv = m31_mul_d(v[k], inv);
+        v[k] = (zmask >> k) & 1u ? 0u : mine;
     }
-    v[0] = v[0] ? inv : 0u;
+    v[0] = zmask & 1u ? 0u : inv;
 }
 
-__global__ void __launch_bounds__(256) m31_inv_kernel(const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n) {
-    constexpr int K = 16;
+template <int K>
+__global__ void __launch_bounds__(256, K == 16 ? 4 : 1) m31_inv_kernel(const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n) {
+    static_assert(K == 8 || K == 16 || K == 32, "the fail bytes of one thread are stored as uint2 / uint4");
     const size_t nv = n / K, stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint4 *a4 = reinterpret_cast<const uint4 *>(a);
     uint4 *o4 = reinterpret_cast<uint4 *>(out);
     const bool fail_vec = (reinterpret_cast<uintptr_t>(fail) & 15u) == 0;
     for (size_t i = tid; i < nv; i += stride) {
-        uint32_t raw[K], v[K];
+        uint32_t v[K], fmask = 0; // fmask bit k: element k is bitwise 0 = the assert!(false) of m31.simf:118-122
 #pragma unroll
         for (int j = 0; j < K / 4; j++) {
             const uint4 x = __ldg(a4 + (K / 4) * i + j);
-            raw[4 * j] = x.x; raw[4 * j + 1] = x.y; raw[4 * j + 2] = x.z; raw[4 * j + 3] = x.w;
+            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
         }
 #pragma unroll
-        for (int k = 0; k < K; k++) v[k] = m31_reduce(raw[k]);
+        for (int k = 0; k < K; k++) {
+            fmask |= (v[k] == 0 ? 1u : 0u) << k;
+            v[k] = m31_reduce(v[k]);
+        }
         m31_batch_inv<K>(v);
 #pragma unroll
         for (int j = 0; j < K / 4; j++) o4[(K / 4) * i + j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (fail) { // assert!(false) of m31.simf:118-122: the input is bitwise 0
-            uint32_t f[K / 4];
+        if (fail) {
+            uint32_t f[K / 4]; // one byte per element
 #pragma unroll
             for (int j = 0; j < K / 4; j++) {
-                f[j] = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) f[j] |= (raw[4 * j + k] == 0 ? 1u : 0u) << (8 * k);
+                const uint32_t m = (fmask >> (4 * j)) & 15u;
+                f[j] = (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21);
             }
-            if (fail_vec) reinterpret_cast<uint4 *>(fail)[i] = make_uint4(f[0], f[1], f[2], f[3]);
-            else
-                for (int k = 0; k < K; k++) fail[K * i + k] = raw[k] == 0;
+            if (fail_vec && K == 8) {
+                reinterpret_cast<uint2 *>(fail)[i] = make_uint2(f[0], f[K / 4 - 1]);
+            } else if (fail_vec) {
+#pragma unroll
+                for (int j = 0; j < K / 16; j++) reinterpret_cast<uint4 *>(fail)[(K / 16) * i + j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+                for (int k = 0; k < K; k++) fail[K * i + k] = (uint8_t)((fmask >> k) & 1u);
+            }
         }
     }
     for (size_t i = nv * K + tid; i < n; i += stride) {
@@ -192,7 +207,13 @@ int launch_field_jet(int op, const uint32_t *a, const uint32_t *b, uint32_t *out
     case JET_M31_SUB: m31_binary_kernel<JET_M31_SUB><<<g4, 256, 0, s>>>(a, b, out, n); break;
     case JET_M31_MUL: m31_binary_kernel<JET_M31_MUL><<<g4, 256, 0, s>>>(a, b, out, n); break;
     case JET_M31_NEG: m31_binary_kernel<JET_M31_NEG><<<g4, 256, 0, s>>>(a, a, out, n); break;
-    case JET_M31_INV: m31_inv_kernel<<<stream_grid((n + 15) / 16, 256), 256, 0, s>>>(a, out, fail, n); break;
+    case JET_M31_INV: {
+        static const int k = [] { const char *e = getenv("SSYM_M31_INV_K"); return e ? atoi(e) : M31_INV_K; }();
+        if (k == 32) m31_inv_kernel<32><<<stream_grid((n + 31) / 32, 256), 256, 0, s>>>(a, out, fail, n);
+        else if (k == 8) m31_inv_kernel<8><<<stream_grid((n + 7) / 8, 256), 256, 0, s>>>(a, out, fail, n);
+        else m31_inv_kernel<16><<<stream_grid((n + 15) / 16, 256), 256, 0, s>>>(a, out, fail, n);
+        break;
+    }
     case JET_CM31_MUL: ext_kernel<JET_CM31_MUL><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
     case JET_CM31_INV: ext_inv_kernel<false><<<stream_grid((n + 7) / 8, 256), 256, 0, s>>>(a, out, fail, n); break;
     case JET_QM31_ADD: ext_kernel<JET_QM31_ADD><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;
