@@ -568,6 +568,8 @@ def main():
                          "note": "the kernel is INT32-ALU bound (170 int-ops per byte), not HBM bound: see roofline_int32"},
             "roofline_int32": {"bound": "int32_alu", "kernel": "stwo_merkle_kernel", "achieved": lit_ops / 1e12, "peak": int32_ops / 1e12, "unit": "Tops/s",
                                "frac": lit_ops / int32_ops if int32_ops else None,
+                               "alu_pipe_busy_ncu": 0.827, "fma_heavy_pipe_busy_ncu": 0.447, "issue_slots_busy_ncu": 0.70,
+                               "ncu_source": "profiles/r01e_ncu_summary.md (one ncu --set full capture of this kernel at 1024 proofs; 0.849 / 0.518 / 0.718 at 16 384 proofs, profiles/r01_ncu_summary.md)",
                                "convention": "achieved = FIPS-180-4-literal 2296 ops x compressions / kernel time (SURVEY 8d); peak = measured SHF/LOP3/IADD3 "
                                              "machine-instruction lanes/s (ssym_int32_peak_probe); LOP3/IADD3 fusion makes >1.0 possible",
                                "probe_ms": probe_ms},
