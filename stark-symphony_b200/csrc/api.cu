@@ -991,6 +991,8 @@ static int wit_batch(ssym_ctx *c, const ssym_stwo_config_t *cfg, const char *tex
             if (kidx >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_wit_parsed[b], 0));
             for (size_t i = 0; i <= m; i++) c->wit_hoffs[b][i] = h_off[beg + i] - t0;
             CUDA_TRY(cudaMemcpyAsync(c->wit_text[b].p, text + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->copy_stream));
+            // the lexer reads aligned 16-byte blocks: the (ignored) bytes behind the last witness are defined, not whatever the buffer held
+            CUDA_TRY(cudaMemsetAsync(static_cast<uint8_t *>(c->wit_text[b].p) + (size_t)(t1 - t0), 0, 16, c->copy_stream));
             CUDA_TRY(cudaMemcpyAsync(c->wit_offs[b].p, c->wit_hoffs[b], (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->copy_stream));
             CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
             CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d[b], 0));
@@ -1205,6 +1207,7 @@ extern "C" int ssym_stark101_verify_wit_batch(ssym_ctx_t *c, const char *text, c
             CUDA_TRY(c->wit_text[0].ensure((size_t)(h_off[n] - h_off[0]) + 16));
             CUDA_TRY(c->wit_offs[0].ensure((n + 1) * 8));
             CUDA_TRY(cudaMemcpyAsync(c->wit_text[0].p, text + h_off[0], (size_t)(h_off[n] - h_off[0]), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemsetAsync(static_cast<uint8_t *>(c->wit_text[0].p) + (size_t)(h_off[n] - h_off[0]), 0, 16, s)); // defined pad behind the last witness
             std::vector<uint64_t> rel(n + 1);
             for (size_t i = 0; i <= n; i++) rel[i] = h_off[i] - h_off[0];
             CUDA_TRY(cudaMemcpyAsync(c->wit_offs[0].p, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));

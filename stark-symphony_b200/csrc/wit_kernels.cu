@@ -87,7 +87,18 @@ enum : uint8_t { K_NUM = 1, K_STR = 2, K_LC = 4, K_BAD = 8 };
 struct Blocks {
     const uint4 *base;
     uint32_t head, nblk, len;
-    __device__ __forceinline__ uint4 load(uint32_t blk) const { return blk < nblk ? __ldg(base + blk) : make_uint4(0, 0, 0, 0); }
+    uint32_t safe_blk;  // blocks [0, safe_blk) lie entirely inside the text buffer; the one block that may straddle its end is read byte by byte
+    uint32_t safe_bytes; // bytes from `base` to the end of the text buffer (saturated)
+    __device__ __noinline__ uint4 load_tail(uint32_t blk) const {
+        uint32_t w[4] = {0, 0, 0, 0};
+        const uint8_t *b = reinterpret_cast<const uint8_t *>(base + blk);
+        for (uint32_t k = 0; k < 16 && blk * 16u + k < safe_bytes; k++) w[k >> 2] |= (uint32_t)b[k] << (8 * (k & 3));
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ __forceinline__ uint4 load(uint32_t blk) const {
+        if (blk >= nblk) return make_uint4(0, 0, 0, 0);
+        return blk < safe_blk ? __ldg(base + blk) : load_tail(blk);
+    }
     // 16-bit mask of the bytes of block `blk` whose file position lies in [lo, hi)
     __device__ __forceinline__ uint32_t valid(uint32_t blk, uint32_t lo, uint32_t hi) const {
         const int rel0 = (int)(blk * 16u) - (int)head;
@@ -129,6 +140,11 @@ __global__ void __launch_bounds__(32 * LEX_WARPS) wit_lex_kernel(WitParams p) {
     B.head = (uint32_t)(reinterpret_cast<uintptr_t>(t) & 15u);
     B.base = reinterpret_cast<const uint4 *>(t - B.head);
     B.nblk = (B.head + B.len + 15u) / 16u;
+    { // the buffer holds p.offsets[p.n] bytes: nothing behind them is read (the last block of the last witness usually straddles the end)
+        const uint64_t room = p.offsets[p.n] - b0 + B.head;
+        B.safe_bytes = room > 0xffffffffull ? 0xffffffffu : (uint32_t)room;
+        B.safe_blk = B.safe_bytes / 16u;
+    }
     const uint32_t FULL = 0xffffffffu;
     bool bad = false;
 
@@ -275,13 +291,13 @@ __device__ __forceinline__ bool all_hex(uint32_t w) { // every byte in [0-9a-f]
     return (dig | let) == H;
 }
 
-__device__ bool parse_number(const uint8_t *s, uint32_t slot, uint32_t *rec) {
+__device__ bool parse_number(const uint8_t *s, const uint8_t *text_end, uint32_t slot, uint32_t *rec) {
     const uint32_t off = slot & 0x0fffffffu, kind = slot >> 28;
     const uint32_t kw = kind == WIT_KIND_U32 ? 1u : kind == WIT_KIND_U64 ? 2u : 8u;
     if (s[0] == '0' && s[1] == 'x') {
         const uint8_t *d = s + 2;
-        if (kw == 8) { // 64 digits and a terminator?
-            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3u);
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3u);
+        if (kw == 8 && d - sh + 68 <= text_end) { // 64 digits and a terminator?  (17 aligned words, all inside the text buffer)
             const uint32_t *a = reinterpret_cast<const uint32_t *>(d - sh);
             uint32_t A[17], W[16];
 #pragma unroll
@@ -370,7 +386,8 @@ __global__ void __launch_bounds__(256) wit_numbers_kernel(WitParams p) {
     const uint32_t i = (uint32_t)(g / p.total_slots), k = (uint32_t)(g % p.total_slots);
     if (i >= p.n || p.flags[i] != SSYM_WIT_OK) return;
     const uint8_t *t = p.text + p.offsets[i];
-    if (!parse_number(t + p.numpos[(size_t)i * p.total_slots + k], __ldg(p.tab.slots + k), p.packed + (size_t)i * p.stride_words)) p.flags[i] = SSYM_WIT_SLOW;
+    if (!parse_number(t + p.numpos[(size_t)i * p.total_slots + k], p.text + p.offsets[p.n], __ldg(p.tab.slots + k), p.packed + (size_t)i * p.stride_words))
+        p.flags[i] = SSYM_WIT_SLOW;
 }
 
 // packed[i] = template for every i (the words of a record that are not literals: lengths, counts)

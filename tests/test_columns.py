@@ -214,6 +214,7 @@ def test_wide_batch_device_resident_with_negatives(S, ver, orc, nc):
     for j, row in enumerate(bad_rows):
         word, delta = classes[j % len(classes)]
         proofs[row, word] += delta
+    torch.cuda.synchronize()  # the corruptions run on torch's stream, the verifier on the handle's own
     accept, status, _ = ver.stwo_verify_batch(proofs.view(-1), cfg, n, want_status=True)
     ver.synchronize()
     status = status.cpu().numpy().view(np.uint32)

@@ -66,6 +66,7 @@ def test_gpu_prover_device_resident_batch_verifies(S, ver, orc):
     for j, row in enumerate(bad_rows):
         word, delta = classes[j % len(classes)]
         proofs[row, word] += delta
+    torch.cuda.synchronize()  # the corruptions run on torch's stream, the verifier on the handle's own
     accept, status, _ = ver.stwo_verify_batch(proofs.view(-1), cfg, n, want_status=True)
     ver.synchronize()
     status = status.cpu().numpy().view(np.uint32)
