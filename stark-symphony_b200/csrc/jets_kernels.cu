@@ -116,37 +116,53 @@ __global__ void __launch_bounds__(256, K == 16 ? 4 : 1) m31_inv_kernel(const uin
 }
 
 // cm31_inv (cm31.simf:88-93) / qm31_inv (qm31.simf:87-98) K elements per thread: both end in ONE m31 inversion of a norm, batched as above.
+// Every step of the reference formulas goes through m31_add / m31_mul, whose results are canonical and depend only on the residues of their
+// operands — except the negations of RAW inputs (cm31_conj of the input in cm31_inv, cm31_neg(x.i) in qm31_inv): (p - a) mod 2^32 wraps for a > p
+// and is then 2 off the negated residue (m31.simf:29-32), so those two are formed literally.  Everything else runs on operands canonicalised
+// once, with the products of each component accumulated in 64 bits and one reduction per component:
+//   qm31_inv(x): u + v i = x.i^2;  den = x.r^2 - (2 + i)(u + v i);  n = |den|^2;  den_inv = conj(den) / n;  result = (x.r den_inv, -x.i den_inv)
 template <bool QM>
-__global__ void __launch_bounds__(256) ext_inv_kernel(const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n) {
+__global__ void __launch_bounds__(256, QM ? 3 : 4) ext_inv_kernel(const uint32_t *a, uint32_t *out, uint8_t *fail, size_t n) {
     constexpr int K = 8;
     const size_t nv = n / K, stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = tid; i < nv; i += stride) {
-        QM31 x[K];
-        CM31 den[K];
-        uint32_t norm[K];
+        uint32_t da[K], db[K], norm[K]; // den = da + db i (canonical), its norm
+        uint32_t ncb[K];                // CM31 input: the literal conj, m31(p - b mod 2^32)
 #pragma unroll
         for (int k = 0; k < K; k++) {
             if (QM) {
-                x[k] = qm31_load4(a + 4 * (K * i + k));
-                const CM31 ar_sq = cm31_mul(x[k].r, x[k].r), ai_sq = cm31_mul(x[k].i, x[k].i);
-                den[k] = cm31_add(ar_sq, cm31_neg(cm31_add(cm31_add(ai_sq, ai_sq), cm31(m31_neg(ai_sq.b), ai_sq.a))));
+                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(a) + K * i + k);
+                const uint32_t a0 = m31_reduce(x.x), a1 = m31_reduce(x.y), a2 = m31_reduce(x.z), a3 = m31_reduce(x.w);
+                const uint32_t u = m31_reduce64((uint64_t)a2 * a2 + (uint64_t)a3 * (SSYM_P - a3)); // Re x.i^2
+                const uint32_t v = m31_reduce64((uint64_t)(a2 << 1) * a3);                            // Im x.i^2
+                da[k] = m31_reduce64((uint64_t)a0 * a0 + (uint64_t)a1 * (SSYM_P - a1) + ((uint64_t)(SSYM_P - u) << 1) + v);
+                db[k] = m31_reduce64((uint64_t)(a0 << 1) * a1 + ((uint64_t)(SSYM_P - v) << 1) + (SSYM_P - u));
             } else {
                 const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a) + K * i + k);
-                den[k] = cm31(v.x, v.y);
+                da[k] = m31_reduce(v.x);
+                db[k] = m31_reduce(v.y);
+                ncb[k] = m31_reduce(SSYM_P - v.y);
             }
-            norm[k] = m31_add(m31_pow2(den[k].a), m31_pow2(den[k].b)); // canonical
+            norm[k] = m31_reduce64((uint64_t)da[k] * da[k] + (uint64_t)db[k] * db[k]);
         }
-        uint32_t ninv[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) ninv[k] = norm[k];
-        m31_batch_inv<K>(ninv);
         uint64_t fbits = 0;
 #pragma unroll
+        for (int k = 0; k < K; k++) fbits |= (uint64_t)(norm[k] == 0 ? 1u : 0u) << (8 * k);
+        m31_batch_inv<K>(norm);
+#pragma unroll
         for (int k = 0; k < K; k++) {
-            const CM31 dinv = cm31_mul_m31(cm31_conj(den[k]), ninv[k]);
-            fbits |= (uint64_t)(norm[k] == 0 ? 1u : 0u) << (8 * k);
-            if (QM) qm31_store4(out + 4 * (K * i + k), qm31c(cm31_mul(x[k].r, dinv), cm31_mul(cm31_neg(x[k].i), dinv)));
-            else reinterpret_cast<uint2 *>(out)[K * i + k] = make_uint2(dinv.a, dinv.b);
+            const uint32_t nd = norm[k] << 1;
+            const uint32_t d0 = m31_mul_d(nd, da[k]), d1 = m31_mul_d(nd, QM ? SSYM_P - db[k] : ncb[k]); // conj(den) / n; p - db in [1, p]: the product stays < 2^63
+            if (QM) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(a) + K * i + k); // L1 / L2 hit: loaded a few hundred instructions ago
+                const uint32_t a0 = m31_reduce(x.x), a1 = m31_reduce(x.y), nd1 = SSYM_P - d1;
+                const uint32_t n2 = m31_reduce(SSYM_P - x.z), n3 = m31_reduce(SSYM_P - x.w); // cm31_neg(x.i) on the raw words, then the residues
+                reinterpret_cast<uint4 *>(out)[K * i + k] =
+                    make_uint4(m31_reduce64((uint64_t)a0 * d0 + (uint64_t)a1 * nd1), m31_reduce64((uint64_t)a0 * d1 + (uint64_t)a1 * d0),
+                               m31_reduce64((uint64_t)n2 * d0 + (uint64_t)(SSYM_P - n3) * d1), m31_reduce64((uint64_t)n2 * d1 + (uint64_t)n3 * d0));
+            } else {
+                reinterpret_cast<uint2 *>(out)[K * i + k] = make_uint2(d0, d1);
+            }
         }
         if (fail) {
             if ((reinterpret_cast<uintptr_t>(fail) & 7u) == 0) reinterpret_cast<uint64_t *>(fail)[i] = fbits;
