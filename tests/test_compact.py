@@ -188,3 +188,24 @@ def test_gpu_compact_host_path_chunks_and_async(S, ver, orc):
     ver.set_host_async(False)
     for a, st in outs:
         assert (st == ref_status).all() and (a == ref_accept).all()
+
+
+def test_compact_pack_fuzz_with_many_duplicates(S):
+    """Records whose siblings come from a pool of a few digests (duplicates inside a tree, across trees, runs of equal slots, all-equal
+    trees): the packer's tables stay per tree, indices fit their byte, and the independent expander gives every record back."""
+    rng = np.random.default_rng(7)
+    for preset, nc in (("testing", 4), ("prod", 4), ("prod", 16)):
+        cfg = S.stwo_config(preset, 0, n_columns=nc)
+        lo = S.stwo_layout(cfg)
+        recs = rng.integers(0, 2**32, size=(12, lo.stride_words), dtype=np.uint64).astype(np.uint32)
+        first, last = lo.off_trace_sib, lo.stride_words
+        for i, pool_size in enumerate((1, 1, 2, 3, 5, 8, 17, 40, 100, 255, 256, 300)):
+            pool = rng.integers(0, 2**32, size=(pool_size, 8), dtype=np.uint64).astype(np.uint32)
+            if i == 1:
+                pool[:] = 0
+            for off in list(range(lo.off_trace_sib, lo.off_fri_wit, 8)) + list(range(lo.off_fri_sib[0], last, 8)):
+                recs[i, off:off + 8] = pool[rng.integers(0, pool_size)]
+        blob, offsets = S.witness.compact_stwo(recs, cfg)
+        assert (numpy_expand(S, cfg, blob, offsets) == recs).all()
+        sizes = np.diff(offsets.astype(np.int64))
+        assert (sizes[:-1] <= sizes[-1]).all() and sizes[0] < sizes[-1]
