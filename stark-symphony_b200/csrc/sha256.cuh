@@ -230,6 +230,42 @@ __device__ __forceinline__ void sha_compress_rolled(uint32_t (&h)[8], uint32_t (
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
+// NP independent compressions in lockstep (same rolled structure, the rounds of the NP states interleaved in one instruction stream):
+// a lone warp per scheduler is bound by the dependency chain of a compression (ncu: 0.34 instructions per cycle, every issue followed by
+// ~1.2 cycles of fixed-latency wait); a second independent chain fills those slots.  Used by the transcript kernel.
+template <int ADDMODE, int NP>
+__device__ __forceinline__ void sha_compress_rolled_n(uint32_t (&h)[NP][8], uint32_t (&w)[NP][16], const ShaAdd<ADDMODE> A) {
+    uint32_t v[NP][8];
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[p][k] = h[p][k];
+#pragma unroll 1
+    for (int grp = 0; grp < 4; grp++) {
+        if (grp) {
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+#pragma unroll
+                for (int p = 0; p < NP; p++) w[p][i] = A.sch4(w[p][i], A.ssig0(w[p][(i + 1) & 15]), w[p][(i + 9) & 15], A.ssig1(w[p][(i + 14) & 15]));
+        }
+        const uint4 kq[4] = {c_sha_k4.v[grp * 4 + 0], c_sha_k4.v[grp * 4 + 1], c_sha_k4.v[grp * 4 + 2], c_sha_k4.v[grp * 4 + 3]};
+#pragma unroll
+        for (int t = 0; t < 16; t++) { // round t of the group: the working variables rotate through v[][(j - t) & 7]
+            const uint4 k4 = kq[t >> 2];
+            const uint32_t kt = (t & 3) == 0 ? k4.x : (t & 3) == 1 ? k4.y : (t & 3) == 2 ? k4.z : k4.w;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                uint32_t &a = v[p][(0 - t) & 7], &b = v[p][(1 - t) & 7], &c = v[p][(2 - t) & 7], &d = v[p][(3 - t) & 7];
+                uint32_t &e = v[p][(4 - t) & 7], &f = v[p][(5 - t) & 7], &g = v[p][(6 - t) & 7], &hh = v[p][(7 - t) & 7];
+                SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.t1(w[p][t], kt));
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) h[p][k] += v[p][k];
+}
 template <int ADDMODE>
 __device__ __forceinline__ void sha_compress_pad64_rolled(uint32_t (&h)[8], const ShaAdd<ADDMODE> A) {
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
