@@ -134,9 +134,13 @@ __device__ __noinline__ void stwo_scalars(const StwoParams &p, uint32_t i, QM31 
 
 // One thread runs the transcripts of NP proofs in lockstep (the steps of the program are the same for every proof of a configuration; only a
 // felt draw that has to be repeated — probability 2^-29 — makes one proof wait for the other).
+#ifndef K1_ADDMODE
+#define K1_ADDMODE 1 // adds as IMAD, as in the Merkle kernels.  Plain adds (0: 3-input IADD3s, shorter chains) make a lone launch 4 % faster (0.123 vs
+                     // 0.129 ms), but in the pipelined loop this kernel runs under Merkle kernels that are bound by the ALU pipe, where every ALU slot counts
+#endif
 template <int NP>
 __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul mul) {
-    const ShaAdd<1> A(mul);
+    const ShaAdd<K1_ADDMODE> A(mul);
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * NP;
     if (p.dd.enabled && blockIdx.x == 0) // the bin counters of stwo_plan_kernel / stwo_check_kernel, later in this stream
         for (uint32_t t = threadIdx.x; t < 2 * STWO_DEDUP_MAX_BINS; t += blockDim.x) p.dd.bin_count[t] = 0;
@@ -190,6 +194,11 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
         const uint32_t nwords = 8 + n, nblocks = (nwords + 3 + 15) >> 4;
 #pragma unroll 1
         for (uint32_t b = 0; b < nblocks; b++) {
+            if (nwords == 16 && b == 1) { // the 12 digest-sized mixes: the second block is the constant padding block of a 64-byte message
+#pragma unroll
+                for (int k = 0; k < NP; k++) sha_compress_pad64_rolled<K1_ADDMODE>(h[k], A);
+                break;
+            }
             uint32_t w[NP][16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
                     w[k][j] = v;
                 }
             }
-            sha_compress_rolled_n<1, NP>(h, w, A);
+            sha_compress_rolled_n<K1_ADDMODE, NP>(h, w, A);
         }
         // ---- what the step does with the hash ----
         if (!draw) { // channel_mix_*: the digest moves, the counter restarts
