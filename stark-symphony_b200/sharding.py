@@ -17,6 +17,15 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, end
 
 
+def shard_compact(blob, offsets, rank: int, world: int):
+    """This rank's slice of a batch held in the compact transport form (witness.compact_stwo): (blob words, offsets rebased to 0) of the
+    proofs shard_range gives it.  Views, no copies: records are contiguous and self-describing, so the blob shards by proof index too."""
+    n = len(offsets) - 1
+    begin, end = shard_range(n, rank, world)
+    lo, hi = int(offsets[begin]), int(offsets[end])
+    return blob[lo:hi], offsets[begin:end + 1] - offsets[begin]
+
+
 def shard_words(n: int, world: int) -> int:
     """Bitmap words every rank contributes to the gather (fixed size: all_gather needs equal shapes)."""
     per = ((n + world - 1) // world + 31) // 32 * 32

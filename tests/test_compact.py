@@ -209,3 +209,24 @@ def test_compact_pack_fuzz_with_many_duplicates(S):
         assert (numpy_expand(S, cfg, blob, offsets) == recs).all()
         sizes = np.diff(offsets.astype(np.int64))
         assert (sizes[:-1] <= sizes[-1]).all() and sizes[0] < sizes[-1]
+
+
+def test_compact_blob_shards_by_proof_index(S, orc):
+    """sharding.shard_compact: every rank's slice expands to exactly its shard_range of the packed batch."""
+    from importlib import import_module
+
+    sh = import_module("stark_symphony_b200.sharding")
+    cfg = S.stwo_config("testing", 1)
+    n = 70
+    pk = orc.stwo_prove_batch(ocfg(cfg), list(range(n)), threads=4)
+    blob, offsets = S.witness.compact_stwo(pk, cfg)
+    for world in (1, 2, 3, 8):
+        seen = 0
+        for rank in range(world):
+            b, e = sh.shard_range(n, rank, world)
+            sb, so = sh.shard_compact(blob, offsets, rank, world)
+            assert so[0] == 0 and len(so) == e - b + 1 and so[-1] == sb.size
+            if e > b:
+                assert (numpy_expand(S, cfg, sb, so) == pk[b:e]).all()
+            seen += e - b
+        assert seen == n
