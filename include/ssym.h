@@ -274,7 +274,8 @@ int ssym_stwo_verify_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const
  *   packed fri_wit section, padded to 8 words
  *   one index per sibling slot, in packed order (trace [Q][G], composition [Q][G], FRI layer l [Q][G-1-l]), relative to the
  *     tree's first table entry; 1 byte each if Q * G <= 256, else 2; padded to 8 words
- *   D digests of 8 words */
+ *   D digests of 8 words
+ * Record offsets are multiples of 8 words (ssym_stwo_compact_pack produces them so); a blob in device memory is 16-byte aligned. */
 #define SSYM_COMPACT_MAGIC 0x31435353u /* "SSC1" */
 /* Words an n-proof compact blob can need at most (no two siblings equal). */
 size_t ssym_stwo_compact_bound(const ssym_stwo_config_t *cfg, size_t n);

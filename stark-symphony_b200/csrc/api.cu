@@ -597,6 +597,7 @@ extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t 
     CompactParams p;
     p.sh = sh; p.lo = lo; p.base = 0; p.n = (uint32_t)n;
     if (memspace == SSYM_MEM_DEVICE) {
+        if (reinterpret_cast<uintptr_t>(blob) & 15u) return fail(SSYM_ERR_USAGE, "a device compact blob must be 16-byte aligned");
         p.blob = blob; p.offsets = offsets; p.packed = packed_out; p.flags = flags;
         launch_stwo_expand(p, s);
         c->launches += 1;
@@ -607,6 +608,7 @@ extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t 
         if (offsets[i + 1] < offsets[i]) return fail(SSYM_ERR_USAGE, "offsets must be non-decreasing");
     const size_t words = offsets[n] - offsets[0], out_b = n * (size_t)lo.stride_words * 4;
     CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream)); // an enqueue-only host call may still be filling the staging buffers
     CUDA_TRY(c->cstage[0].ensure(words * 4 + 16));
     CUDA_TRY(c->coffs[0].ensure((n + 1) * sizeof(uint64_t)));
     CUDA_TRY(c->cflags[0].ensure(n * sizeof(uint32_t)));
@@ -640,6 +642,7 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     CompactParams p;
     p.sh = sh; p.lo = lo;
     if (memspace == SSYM_MEM_DEVICE) { // expand a chunk into HBM scratch, verify it, next chunk (in order on the handle's stream)
+        if (reinterpret_cast<uintptr_t>(blob) & 15u) return fail(SSYM_ERR_USAGE, "a device compact blob must be 16-byte aligned");
         const size_t cap = std::min(n, STWO_DEVICE_CHUNK);
         CUDA_TRY(c->stage[0].ensure(cap * stride_b));
         CUDA_TRY(c->cflags[0].ensure(cap * sizeof(uint32_t)));
