@@ -53,6 +53,28 @@ def load_workload(S, batch, mode_name):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on all host cores
 # ---------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Multi-GPU runs feed every GPU from pinned host memory at link rate: pin this rank to the CPUs of its GPU's NUMA node before any
+    buffer is allocated (first-touch then places the pinned pages next to the GPU's PCIe root).  Returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo_, _, hi_ = part.partition("-")
+            cpus.update(range(int(lo_), int(hi_ or lo_) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -257,7 +279,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libssym has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 and not os.environ.get("SSYM_NO_NUMA_BIND") else None
     if world > 1:
+        log(f"rank {rank}: GPU {local_rank} NUMA node {numa_node}, {len(os.sched_getaffinity(0))} CPUs")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
@@ -526,7 +550,8 @@ def main():
                        "mode": args.mode, "batch_per_gpu": n, "accepted": accepted,
                        "l2": f"rotating {copies} distinct device copies of the batch ({copies * n * lo.stride_words * 4 / 1e6:.0f} MB > 126 MB L2)",
                        "pipeline": f"{depth} batches in flight per GPU (ssym_set_pipeline_depth); per-kernel times below are per launch, kernels of consecutive steps overlap" if depth > 1 else "serial steps",
-                       "parallelism": f"proof-sharded x{world} (one process per GPU, no data-path collective), one NCCL all_gather of the accept bitmaps of all steps inside the timed region" if world > 1 else "single GPU"},
+                       "parallelism": f"proof-sharded x{world} (one process per GPU, no data-path collective), one NCCL all_gather of the accept bitmaps of all steps inside the timed region" if world > 1 else "single GPU",
+                       "numa": (f"every rank pinned to the CPUs of its GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else "no NUMA binding")},
             "other_mode": {"mode": "prover-consistent" if args.mode == "ref-literal" else "ref-literal", "value": other_value, "unit": "proofs/s",
                            "steps": other_steps, "accepted_per_gpu": other_accepted,
                            "note": "same pipelined loop, same batch, the other semantics switch; under prover-consistent the fixture is ACCEPTED and the Merkle paths "
