@@ -564,11 +564,11 @@ def main():
                     "sync_call_value": c_sync_value, "bytes_per_proof": c_words * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
                     "gpu_launches_per_step": int(c_launches),
                     "note": "ssym_stwo_verify_compact_batch(SSYM_MEM_HOST) on pinned host buffers holding the batch in the compact transport form "
-                            "(include/ssym.h: per Merkle tree every distinct 32-byte sibling once + one index per path slot; produced by the host packer "
+                            "(include/ssym.h: per Merkle tree every distinct 32-byte sibling once + one bit per path slot + one back reference per repeated slot; produced by the host packer "
                             "ssym_stwo_compact_pack, lossless for any record, expanded on the GPU by stwo_expand_kernel): chunked double-buffered H2D -> "
                             "expand -> verifier kernels -> D2H bitmap, every step's copies inside the timed region.  `value`: calls enqueued back to back "
                             "(ssym_set_host_async), one synchronize; `sync_call_value`: each call returns with its bitmap in host memory.  Bound by the "
-                            "host link; `e2e_packed` is the same measurement on the fixed-stride packed records (25 % more bytes)"},
+                            "host link; `e2e_packed` is the same measurement on the fixed-stride packed records (36 % more bytes)"},
             "e2e_packed": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n * lo.stride_words * 4), "d2h_bytes_per_step": int(acc_host.nbytes),
                     "steps": e2e_steps, "h2d_gbs_achieved": e2e_value / world * lo.stride_words * 4 / 1e9, "h2d_gbs_plain_copy": h2d_gbs,
                     "sync_call_value": e2e_sync_value,

@@ -264,26 +264,26 @@ int ssym_stwo_verify_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const
 /* ---- compact transport form of packed Stwo proofs ---------------------------
  * 92 % of a packed proof is authentication paths, and the reference's witness repeats every node that several of a
  * tree's paths run through (merkle.simf:39-44 takes one full path per query).  The compact record stores, per tree, each
- * distinct 32-byte sibling once plus one index per path slot; expanding it gives back the packed record bit for bit,
+ * distinct 32-byte sibling once plus one bit per path slot and one index per repeated slot; expanding it gives back the packed record bit for bit,
  * for ANY packed record (equal digests are found by comparing data, nothing is assumed about the proof being honest).
  * It is what host buffers should hold when the host link is the bottleneck (DESIGN.md "Host buffers").
- * Record (u32 words, a multiple of 8):
- *   [0] record length in words   [1] D = digests in the table   [2] SSYM_COMPACT_MAGIC   [3] 0
- *   [4 .. 4+T) first table entry of tree t (T = n_fri_layers + 3: trace, composition, FRI layers 0..L)   [.. 16) 0
+ * Record (u32 words, a multiple of 8; S = sibling slots of a proof in packed order: trace [Q][G], composition [Q][G], FRI layer l [Q][G-1-l]):
+ *   [0] record length in words   [1] D = digests in the table   [2] SSYM_COMPACT_MAGIC   [3] R = S - D back references   [4 .. 8) 0
  *   packed words [0, off_trace_sib)                  (header + per-query values)
  *   packed fri_wit section, padded to 8 words
- *   one index per sibling slot, in packed order (trace [Q][G], composition [Q][G], FRI layer l [Q][G-1-l]), relative to the
- *     tree's first table entry; 1 byte each if Q * G <= 256, else 2; padded to 8 words
+ *   S bits, slot s = bit s & 31 of word s >> 5: 1 = the slot's sibling is the next digest of the table (digests are stored in the order
+ *     of their first slot), 0 = it repeats an earlier sibling of the same tree; padded to 8 words
+ *   R back references in slot order: the digest's position among its tree's table entries; 1 byte each if Q * G <= 256, else 2; padded to 8 words
  *   D digests of 8 words
  * Record offsets are multiples of 8 words (ssym_stwo_compact_pack produces them so); a blob in device memory is 16-byte aligned. */
-#define SSYM_COMPACT_MAGIC 0x31435353u /* "SSC1" */
+#define SSYM_COMPACT_MAGIC 0x32435353u /* "SSC2" */
 /* Words an n-proof compact blob can need at most (no two siblings equal). */
 size_t ssym_stwo_compact_bound(const ssym_stwo_config_t *cfg, size_t n);
 /* Host function: n packed records -> compact records, concatenated in `out`; offsets[0..n] (u32-word offsets, offsets[0] = 0). */
 int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint32_t *out,
                            size_t out_cap_words, uint64_t *offsets);
 /* GPU: compact -> packed (n * layout.stride_words words).  flags: NULL or n words, 1 where a record is malformed (wrong length /
- * magic / an index outside its tree's table); such a record expands to zeros.  blob holds offsets[n] words. */
+ * magic / counts that do not match the bitmap / a back reference that does not point to an earlier digest of its tree); such a record expands to zeros.  blob holds offsets[n] words. */
 int ssym_stwo_compact_expand(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets,
                              size_t n, uint32_t *packed_out, uint32_t *flags, int memspace);
 /* ssym_stwo_verify_batch on compact records: expanded on the GPU, then verified; a malformed record is rejected with

@@ -524,7 +524,7 @@ extern "C" size_t ssym_stwo_compact_bound(const ssym_stwo_config_t *cfg, size_t 
     ssym_stwo_layout_t lo;
     CompactShape sh;
     if (!cfg || ssym_stwo_layout(cfg, &lo) || compact_shape(*cfg, lo, sh)) return 0;
-    return n * (size_t)(sh.off_tab + 8u * sh.slots);
+    return n * (size_t)sh.max_words;
 }
 
 extern "C" int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint32_t *out, size_t out_cap_words,
@@ -536,38 +536,47 @@ extern "C" int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint3
     CompactShape sh;
     if (compact_shape(*cfg, lo, sh)) return fail(SSYM_ERR_INTERNAL, "packed layout is not contiguous in slot order");
     const uint32_t HASH = 1024; // > 2 * the slots of one tree (Q * G <= 480)
-    std::vector<uint32_t> rec(sh.off_tab + 8u * sh.slots), bucket(HASH);
+    std::vector<uint32_t> rec(sh.max_words), bucket(HASH), tab(8u * (size_t)sh.slots);
+    std::vector<uint16_t> refs(sh.slots);
     size_t pos = 0;
     offsets[0] = 0;
     for (size_t i = 0; i < n; i++) {
         const uint32_t *pk = packed + i * (size_t)lo.stride_words;
-        std::fill(rec.begin(), rec.begin() + sh.off_tab, 0u);
+        std::fill(rec.begin(), rec.begin() + sh.off_refs, 0u);
         memcpy(rec.data() + COMPACT_HDR_WORDS, pk, sh.fixed_words * 4);
         memcpy(rec.data() + sh.off_wit, pk + lo.off_fri_wit, sh.wit_words * 4);
-        uint8_t *idx8 = reinterpret_cast<uint8_t *>(rec.data() + sh.off_idx);
-        uint16_t *idx16 = reinterpret_cast<uint16_t *>(rec.data() + sh.off_idx);
-        uint32_t *tab = rec.data() + sh.off_tab;
-        uint32_t D = 0;
+        uint32_t *bitmap = rec.data() + sh.off_bitmap;
+        uint32_t D = 0, R = 0;
         for (uint32_t t = 0; t < sh.trees; t++) {
-            const uint32_t first = D;
-            rec[4 + t] = first;
+            const uint32_t first = D; // the tree's first table entry
             std::fill(bucket.begin(), bucket.end(), 0u);
             for (uint32_t sl = sh.slot_first[t]; sl < sh.slot_first[t + 1]; sl++) {
                 const uint32_t *d = pk + (sl < sh.head_slots ? lo.off_trace_sib + 8 * sl : lo.off_fri_sib[0] + 8 * (sl - sh.head_slots));
                 uint32_t h = (d[0] * 0x9E3779B1u) ^ (d[3] * 0x85EBCA77u) ^ d[7];
                 h = (h ^ (h >> 15)) & (HASH - 1);
-                uint32_t e;
                 for (;; h = (h + 1) & (HASH - 1)) { // linear probing; a hit only after comparing all 32 bytes
-                    if (!bucket[h]) { e = D++; bucket[h] = e + 1; memcpy(tab + 8 * (size_t)e, d, 32); break; }
-                    e = bucket[h] - 1;
-                    if (!memcmp(tab + 8 * (size_t)e, d, 32)) break;
+                    if (!bucket[h]) { // first time in this tree: the next table entry
+                        bucket[h] = D + 1;
+                        memcpy(tab.data() + 8 * (size_t)D, d, 32);
+                        D++;
+                        bitmap[sl >> 5] |= 1u << (sl & 31u);
+                        break;
+                    }
+                    const uint32_t e = bucket[h] - 1;
+                    if (!memcmp(tab.data() + 8 * (size_t)e, d, 32)) { refs[R++] = (uint16_t)(e - first); break; }
                 }
-                if (sh.idx_bytes == 1) idx8[sl] = (uint8_t)(e - first);
-                else idx16[sl] = (uint16_t)(e - first);
             }
         }
-        const uint32_t words = sh.off_tab + 8u * D;
-        rec[0] = words; rec[1] = D; rec[2] = SSYM_COMPACT_MAGIC;
+        const uint32_t refs_words = compact_refs_words(sh, R), words = sh.off_refs + refs_words + 8u * D;
+        std::fill(rec.begin() + sh.off_refs, rec.begin() + sh.off_refs + refs_words, 0u);
+        if (sh.idx_bytes == 1) {
+            uint8_t *r8 = reinterpret_cast<uint8_t *>(rec.data() + sh.off_refs);
+            for (uint32_t k = 0; k < R; k++) r8[k] = (uint8_t)refs[k];
+        } else {
+            memcpy(rec.data() + sh.off_refs, refs.data(), (size_t)R * 2);
+        }
+        memcpy(rec.data() + sh.off_refs + refs_words, tab.data(), (size_t)D * 32);
+        rec[0] = words; rec[1] = D; rec[2] = SSYM_COMPACT_MAGIC; rec[3] = R;
         if (out_cap_words - pos < words) return fail(SSYM_ERR_NOMEM, "compact output buffer too small (ssym_stwo_compact_bound gives the worst case)");
         memcpy(out + pos, rec.data(), (size_t)words * 4);
         pos += words;
@@ -637,7 +646,7 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     if (n > 0xffffffffull / SSYM_MAX_QUERIES) return fail(SSYM_ERR_USAGE, "batch too large for one call");
     rc = ensure_tables(c, *cfg);
     if (rc) return rc;
-    const size_t stride_b = (size_t)lo.stride_words * 4, max_rec_b = (size_t)(sh.off_tab + 8u * sh.slots) * 4;
+    const size_t stride_b = (size_t)lo.stride_words * 4, max_rec_b = (size_t)sh.max_words * 4;
     cudaStream_t s = c->stream;
     CompactParams p;
     p.sh = sh; p.lo = lo;

@@ -17,9 +17,12 @@ int compact_shape(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, C
     sh.idx_bytes = Q * G <= 256 ? 1 : 2;
     sh.fixed_words = lo.off_trace_sib;
     sh.wit_words = lo.off_fri_sib[0] - lo.off_fri_wit;
+    sh.bitmap_words = (sh.slots + 31u) / 32u;
     sh.off_wit = COMPACT_HDR_WORDS + sh.fixed_words;
-    sh.off_idx = sh.off_wit + sh.wit_words;
-    sh.off_tab = sh.off_idx + ((sh.slots * sh.idx_bytes + 31u) / 32u) * 8u;
+    sh.off_bitmap = sh.off_wit + sh.wit_words;
+    sh.off_refs = sh.off_bitmap + ((sh.bitmap_words + 7u) / 8u) * 8u;
+    sh.max_words = sh.off_refs + 8u * sh.slots;
+    if (sh.bitmap_words > COMPACT_MAX_BITMAP_WORDS) return -1;
     // the packed sibling sections are contiguous in slot order (trace | composition) and (FRI layer 0 | 1 | ...)
     if (lo.off_cp_sib != lo.off_trace_sib + Q * G * 8 || lo.off_fri_wit != lo.off_cp_sib + Q * G * 8 || (sh.fixed_words & 7u) || (sh.wit_words & 7u)) return -1;
     return 0;
@@ -29,6 +32,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) stwo_expand_kernel(CompactParams p) {
     __shared__ uint32_t s_hdr[COMPACT_HDR_WORDS];
+    __shared__ uint32_t s_bm[COMPACT_MAX_BITMAP_WORDS], s_pre[COMPACT_MAX_BITMAP_WORDS + 1]; // bitmap words, new digests before each word
     __shared__ int s_ok;
     const CompactShape &sh = p.sh;
     const uint32_t i = blockIdx.x;
@@ -36,17 +40,33 @@ __global__ void __launch_bounds__(256) stwo_expand_kernel(CompactParams p) {
     const uint32_t *rec = p.blob + (o0 - p.base);
     uint32_t *out = p.packed + (size_t)i * p.lo.stride_words;
     if (threadIdx.x == 0) {
-        bool ok = o0 >= p.base && o1 >= o0 + sh.off_tab && ((o0 - p.base) & 7u) == 0 && o1 - o0 <= 0xffffffffull;
+        bool ok = o0 >= p.base && o1 >= o0 + sh.off_refs && ((o0 - p.base) & 7u) == 0 && o1 - o0 <= 0xffffffffull;
         if (ok) {
             for (int k = 0; k < COMPACT_HDR_WORDS; k++) s_hdr[k] = rec[k];
-            const uint32_t D = s_hdr[1];
-            ok = s_hdr[0] == (uint32_t)(o1 - o0) && s_hdr[2] == SSYM_COMPACT_MAGIC && D <= sh.slots && s_hdr[0] == sh.off_tab + 8u * D && s_hdr[4] == 0;
-            for (uint32_t t = 0; ok && t < sh.trees; t++) ok = s_hdr[4 + t] <= (t + 1 < sh.trees ? s_hdr[5 + t] : D);
+            const uint32_t D = s_hdr[1], R = s_hdr[3];
+            ok = s_hdr[0] == (uint32_t)(o1 - o0) && s_hdr[2] == SSYM_COMPACT_MAGIC && D <= sh.slots && R == sh.slots - D &&
+                 s_hdr[0] == sh.off_refs + compact_refs_words(sh, R) + 8u * D;
         }
         s_ok = ok;
     }
     __syncthreads();
     bool bad = !s_ok;
+    if (!bad) {
+        for (uint32_t k = threadIdx.x; k < sh.bitmap_words; k += blockDim.x) {
+            uint32_t w = rec[sh.off_bitmap + k];
+            if (k == sh.bitmap_words - 1 && (sh.slots & 31u)) w &= (1u << (sh.slots & 31u)) - 1u; // bits behind the last slot do not count
+            s_bm[k] = w;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (uint32_t k = 0; k < sh.bitmap_words; k++) { s_pre[k] = acc; acc += __popc(s_bm[k]); }
+            s_pre[sh.bitmap_words] = acc;
+            if (acc != s_hdr[1]) s_ok = 0; // the bitmap does not announce D digests
+        }
+        __syncthreads();
+        bad = !s_ok;
+    }
     if (!bad) {
         const uint4 *src = reinterpret_cast<const uint4 *>(rec + COMPACT_HDR_WORDS);
         uint4 *dst = reinterpret_cast<uint4 *>(out);
@@ -54,17 +74,23 @@ __global__ void __launch_bounds__(256) stwo_expand_kernel(CompactParams p) {
         src = reinterpret_cast<const uint4 *>(rec + sh.off_wit);
         dst = reinterpret_cast<uint4 *>(out + p.lo.off_fri_wit);
         for (uint32_t k = threadIdx.x; k < sh.wit_words / 4; k += blockDim.x) dst[k] = __ldg(src + k);
-        const uint32_t D = s_hdr[1];
-        const uint8_t *idx8 = reinterpret_cast<const uint8_t *>(rec + sh.off_idx);
-        const uint16_t *idx16 = reinterpret_cast<const uint16_t *>(rec + sh.off_idx);
-        const uint4 *tab = reinterpret_cast<const uint4 *>(rec + sh.off_tab);
+        const uint32_t R = s_hdr[3];
+        const uint8_t *ref8 = reinterpret_cast<const uint8_t *>(rec + sh.off_refs);
+        const uint16_t *ref16 = reinterpret_cast<const uint16_t *>(rec + sh.off_refs);
+        const uint4 *tab = reinterpret_cast<const uint4 *>(rec + sh.off_refs + compact_refs_words(sh, R));
         for (uint32_t s = threadIdx.x; s < sh.slots; s += blockDim.x) {
-            uint32_t t = 0;
-            while (t + 1 < sh.trees && s >= sh.slot_first[t + 1]) t++;
-            const uint32_t e = s_hdr[4 + t] + (sh.idx_bytes == 1 ? (uint32_t)idx8[s] : (uint32_t)idx16[s]);
-            const uint32_t lim = t + 1 < sh.trees ? s_hdr[5 + t] : D;
+            const uint32_t w = s_bm[s >> 5], before = s_pre[s >> 5] + __popc(w & ((1u << (s & 31u)) - 1u)); // new digests before slot s
+            uint32_t e = before; // a new digest: the next table entry
+            bool ok = true;
+            if (!((w >> (s & 31u)) & 1u)) { // a repeat: back reference number (s - before), relative to the first table entry of the slot's tree
+                uint32_t t = 0;
+                while (t + 1 < sh.trees && s >= sh.slot_first[t + 1]) t++;
+                const uint32_t f = sh.slot_first[t], tree_first = s_pre[f >> 5] + __popc(s_bm[f >> 5] & ((1u << (f & 31u)) - 1u));
+                e = tree_first + (sh.idx_bytes == 1 ? (uint32_t)ref8[s - before] : (uint32_t)ref16[s - before]);
+                ok = e < before; // an earlier digest of the same tree (e >= tree_first by construction)
+            }
             uint4 a = make_uint4(0, 0, 0, 0), b = a;
-            if (e < lim) { a = __ldg(tab + 2 * e); b = __ldg(tab + 2 * e + 1); }
+            if (ok) { a = __ldg(tab + 2 * e); b = __ldg(tab + 2 * e + 1); }
             else bad = true;
             uint4 *d = reinterpret_cast<uint4 *>(out + (s < sh.head_slots ? p.lo.off_trace_sib + 8 * s : p.lo.off_fri_sib[0] + 8 * (s - sh.head_slots)));
             d[0] = a;

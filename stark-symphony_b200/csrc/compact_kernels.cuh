@@ -1,7 +1,7 @@
 // SPDX-License-Identifier: MIT
 //
 // Compact transport form of packed Stwo proofs (include/ssym.h "compact transport form"): per tree, every distinct sibling digest
-// once + one index per path slot.  The host link carries the compact bytes; stwo_expand_kernel rebuilds the packed records in HBM.
+// once + one bit per path slot + one index per repeated slot.  The host link carries the compact bytes; stwo_expand_kernel rebuilds the packed records in HBM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -10,7 +10,7 @@
 
 namespace ssym {
 
-enum { COMPACT_HDR_WORDS = 16, COMPACT_MAX_TREES = SSYM_MAX_FRI_LAYERS + 2 };
+enum { COMPACT_HDR_WORDS = 8, COMPACT_MAX_TREES = SSYM_MAX_FRI_LAYERS + 2, COMPACT_MAX_BITMAP_WORDS = 256 };
 
 // Section geometry of a compact record for one configuration (host-computed, passed by value).
 struct CompactShape {
@@ -21,9 +21,13 @@ struct CompactShape {
     uint32_t idx_bytes;                          // 1 or 2
     uint32_t fixed_words;                        // packed [0, off_trace_sib)
     uint32_t wit_words;                          // packed [off_fri_wit, off_fri_sib[0])
-    uint32_t off_wit, off_idx, off_tab;          // word offsets inside the compact record (the fixed part starts at COMPACT_HDR_WORDS)
+    uint32_t bitmap_words;                       // ceil(slots / 32)
+    uint32_t off_wit, off_bitmap, off_refs;      // word offsets inside the compact record (the fixed part starts at COMPACT_HDR_WORDS); the
+                                                 // table follows the R back references: off_refs + compact_refs_words(R)
+    uint32_t max_words;                          // a record with no repeated sibling
 };
 int compact_shape(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, CompactShape &sh);
+__host__ __device__ inline uint32_t compact_refs_words(const CompactShape &sh, uint32_t refs) { return ((refs * sh.idx_bytes + 31u) / 32u) * 8u; }
 
 struct CompactParams {
     CompactShape sh;

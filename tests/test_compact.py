@@ -10,7 +10,7 @@ import pytest
 from conftest import GOLDEN
 from oracle import oracle as O
 
-MAGIC = 0x31435353
+MAGIC = 0x32435353
 
 
 @pytest.fixture(scope="module")
@@ -26,7 +26,7 @@ def ocfg(cfg):
 
 
 def numpy_expand(S, cfg, blob, offsets):
-    """Independent restatement of the record format: compact -> packed."""
+    """Independent restatement of the record format (include/ssym.h): compact -> packed."""
     lo = S.stwo_layout(cfg)
     Q, L, G = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log
     depths = [G, G] + [G - 1 - l for l in range(L + 1)]
@@ -35,25 +35,37 @@ def numpy_expand(S, cfg, blob, offsets):
     idx_bytes = 1 if Q * G <= 256 else 2
     fixed, wit = lo.off_trace_sib, lo.off_fri_sib[0] - lo.off_fri_wit
     slots = Q * sum(depths)
-    idx_words = (slots * idx_bytes + 31) // 32 * 8
+    bitmap_words = ((slots + 31) // 32 + 7) // 8 * 8
     for i in range(n):
         rec = blob[int(offsets[i]):int(offsets[i + 1])]
         assert rec[0] == len(rec) and rec[2] == MAGIC and len(rec) % 8 == 0
-        D = int(rec[1])
-        off_wit = 16 + fixed
-        off_idx = off_wit + wit
-        off_tab = off_idx + idx_words
+        D, R = int(rec[1]), int(rec[3])
+        assert D + R == slots
+        off_wit = 8 + fixed
+        off_bitmap = off_wit + wit
+        off_refs = off_bitmap + bitmap_words
+        refs_words = (R * idx_bytes + 31) // 32 * 8
+        off_tab = off_refs + refs_words
         assert len(rec) == off_tab + 8 * D
-        out[i, :fixed] = rec[16:16 + fixed]
-        out[i, lo.off_fri_wit:lo.off_fri_wit + wit] = rec[off_wit:off_idx]
-        idx = rec[off_idx:off_tab].view(np.uint8 if idx_bytes == 1 else np.uint16)
+        out[i, :fixed] = rec[8:8 + fixed]
+        out[i, lo.off_fri_wit:lo.off_fri_wit + wit] = rec[off_wit:off_bitmap]
+        bits = np.unpackbits(rec[off_bitmap:off_refs].view(np.uint8), bitorder="little")
+        assert int(bits[:slots].sum()) == D
+        refs = rec[off_refs:off_tab].view(np.uint8 if idx_bytes == 1 else np.uint16)
         tab = rec[off_tab:].reshape(D, 8)
-        s = 0
+        s = new = ref = 0
         for t, d in enumerate(depths):
-            base = int(rec[4 + t])
+            tree_first = new
             for k in range(Q * d):
+                if bits[s]:
+                    e = new
+                    new += 1
+                else:
+                    e = tree_first + int(refs[ref])
+                    ref += 1
+                    assert e < new
                 dst = lo.off_trace_sib + 8 * s if s < 2 * Q * G else lo.off_fri_sib[0] + 8 * (s - 2 * Q * G)
-                out[i, dst:dst + 8] = tab[base + int(idx[s])]
+                out[i, dst:dst + 8] = tab[e]
                 s += 1
     return out
 
@@ -149,11 +161,14 @@ def test_gpu_malformed_compact_records_are_rejected(S, ver, orc):
     blob = blob.copy()
     o = [int(x) for x in offsets]
     blob[o[1] + 2] ^= 1                  # magic
-    blob[o[2] + 1] += 1                  # table size does not match the record length
-    blob[o[3] + 5] = blob[o[3] + 1] + 1  # a tree's table starts beyond the table
+    blob[o[2] + 1] += 1                  # D does not match the record length
     fixed, wit = lo.off_trace_sib, lo.off_fri_sib[0] - lo.off_fri_wit
-    idx = blob[o[4] + 16 + fixed + wit:].view(np.uint8)
-    idx[3] = 255                         # an index outside the trace tree's table
+    off_bitmap = 8 + fixed + wit
+    blob[o[3] + off_bitmap] ^= 2         # one more / one fewer "new digest" bit than D says
+    slots = cfg.n_queries * (2 * cfg.lde_log + sum(cfg.lde_log - 1 - l for l in range(cfg.n_fri_layers + 1)))
+    off_refs = off_bitmap + ((slots + 31) // 32 + 7) // 8 * 8
+    refs = blob[o[4] + off_refs:].view(np.uint8)
+    refs[0] = 255                        # a back reference that does not point to an earlier digest of its tree
     packed, flags = ver.stwo_compact_expand(blob, offsets, cfg, want_flags=True)
     assert list(flags) == [0, 1, 1, 1, 1, 0]
     assert (packed[[0, 5]] == pk[[0, 5]]).all() and not packed[1:5].any()
