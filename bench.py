@@ -461,7 +461,7 @@ def main():
     e2e_value = total_n * e2e_steps / float(t[0].item())
     e2e_sync_value = total_n * e2e_steps / float(t[1].item())
 
-    # the same, with the batch in the compact transport form (include/ssym.h: per tree every distinct sibling once + one index per path
+    # the same, with the batch in the compact transport form (include/ssym.h: per tree every distinct sibling once, one bit per path
     # slot; made by the host packer ssym_stwo_compact_pack, lossless): fewer bytes cross the link, the GPU expands them into HBM
     bound_words = int(S.load().ssym_stwo_compact_bound(C.byref(cfg), n))
     c_pinned = torch.empty(bound_words, dtype=torch.int32).pin_memory()

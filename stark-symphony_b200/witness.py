@@ -191,7 +191,7 @@ def pack_stark101_proof_json(proof: Dict[str, Any]) -> np.ndarray:
 
 def compact_stwo(packed: np.ndarray, cfg: StwoConfig, out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
     """Packed records -> the compact transport form (ssym_stwo_compact_pack, include/ssym.h): per tree every distinct sibling once plus
-    one index per path slot; lossless for any record.  Returns (blob of u32 words, u64 word offsets [n + 1]); `out` may be a
+    one bit per path slot and one back reference per repeated slot; lossless for any record.  Returns (blob of u32 words, u64 word offsets [n + 1]); `out` may be a
     preallocated (e.g. pinned) uint32 array of at least ssym_stwo_compact_bound words."""
     lib = load()
     lo = stwo_layout(cfg)
