@@ -1,0 +1,108 @@
+"""Differential fuzz of the host witness parser (csrc/witness.cpp behind ssym_stwo_pack_wit) against the independent Python reader
+(oracle/witparse.py) on mutated `.wit` texts of the TESTING preset: token-level rewrites that keep the value (spacing, hex / decimal /
+underscores, redundant parentheses, trailing commas) and ones that break it (dropped / duplicated / swapped tokens, out-of-range literals).
+Both implementations must agree on accept / reject and, when accepted, on every packed word — the grammar is the one `simfony run --witness`
+reads (simfony-cli/src/main.rs:77-81; values as emitted by stwo-verifier/scripts/generate_wit.py:139-243)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from conftest import GOLDEN
+from oracle import witparse as W
+
+TOKEN = re.compile(r"0x[0-9a-fA-F]+|[0-9]+|list!|[()\[\],]")
+
+
+@pytest.fixture(scope="module")
+def S():
+    import stark_symphony_b200 as S
+
+    S.load()
+    return S
+
+
+@pytest.fixture(scope="module")
+def base():
+    return json.loads(open(os.path.join(GOLDEN, "stwo_proof_testing.wit")).read())
+
+
+def _python_result(text, cfg):
+    try:
+        rec, rej = W.pack_stwo(W.load_wit(text), cfg.n_queries, cfg.n_fri_layers, cfg.lde_log, cfg.n_columns or 4)
+        return ("shape", None) if rej else ("ok", rec)
+    except (W.WitnessTypeError, ValueError, KeyError, IndexError, TypeError, RecursionError):
+        return ("reject", None)
+
+
+def _render(tokens, seps):
+    return "".join(s + t for s, t in zip(seps, tokens)) + seps[-1]
+
+
+@st.composite
+def mutated_value(draw, value):
+    toks = TOKEN.findall(value)
+    toks = list(toks)
+    n_mut = draw(st.integers(0, 3))
+    for _ in range(n_mut):
+        kind = draw(st.sampled_from(["respell", "paren", "trail", "drop", "dup", "swap", "big", "junk"]))
+        i = draw(st.integers(0, len(toks) - 1))
+        t = toks[i]
+        if t[0].isdigit() and not re.fullmatch(r"0x[0-9a-fA-F]+|[0-9]+", t):
+            continue  # a junk token from an earlier mutation
+        if kind == "respell" and t[0].isdigit():
+            v = int(t, 0)
+            form = draw(st.sampled_from(["dec", "hex", "hex0", "us", "HEX"]))
+            toks[i] = {"dec": str(v), "hex": hex(v), "hex0": "0x" + "0" * draw(st.integers(1, 3)) + format(v, "x"),
+                       "us": (str(v)[0] + "_" + str(v)[1:]) if len(str(v)) > 1 else str(v), "HEX": "0x" + format(v, "X")}[form]
+        elif kind == "paren" and t[0].isdigit():
+            toks[i:i + 1] = ["(", t, ")"]
+        elif kind == "trail" and t in (")", "]") and i > 0 and toks[i - 1] not in ("(", "[", ","):
+            toks.insert(i, ",")
+        elif kind == "drop":
+            del toks[i]
+            if not toks:
+                toks = ["0"]
+        elif kind == "dup":
+            toks.insert(i, t)
+        elif kind == "swap" and i + 1 < len(toks):
+            toks[i], toks[i + 1] = toks[i + 1], toks[i]
+        elif kind == "big" and t[0].isdigit():
+            toks[i] = str(int(t, 0) + draw(st.sampled_from([2**32, 2**64, 2**256])))
+        elif kind == "junk":
+            toks.insert(i, draw(st.sampled_from([";", "list", "!", "x", "0x", "-1", "1.5", "{"])))
+    seps = [draw(st.sampled_from(["", " ", "  ", "\\n", "\\t "])) for _ in range(len(toks) + 1)]
+    return _render(toks, seps)
+
+
+@st.composite
+def mutated_wit(draw, base):
+    names = list(base)
+    victim = draw(st.sampled_from(names))
+    wit = {k: {"value": v["value"], "type": v.get("type", "")} for k, v in base.items()}
+    wit[victim]["value"] = draw(mutated_value(base[victim]["value"]))
+    if draw(st.booleans()):
+        wit = {k: wit[k] for k in draw(st.permutations(names))}
+    if draw(st.integers(0, 9)) == 0:
+        del wit[draw(st.sampled_from(names))]
+    text = json.dumps(wit, indent=draw(st.sampled_from([None, 0, 2])))
+    return text.replace("\\\\n", "\\n").replace("\\\\t", "\\t")  # the separators above are JSON escapes inside the value string
+
+
+@settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(data=st.data())
+def test_host_parser_agrees_with_python_reader(S, base, data):
+    cfg = S.stwo_config("testing", 0)
+    text = data.draw(mutated_wit(base))
+    packed, bad = S.witness.pack_stwo_wits([text], cfg)
+    kind, rec = _python_result(text, cfg)
+    if kind == "ok":
+        assert not bad[0], text[:300]
+        assert (packed == rec).all()
+    else:
+        assert bad[0], (kind, text[:300])
+        assert not packed.any()
