@@ -106,3 +106,26 @@ def test_host_parser_agrees_with_python_reader(S, base, data):
     else:
         assert bad[0], (kind, text[:300])
         assert not packed.any()
+
+
+@pytest.fixture(scope="module")
+def base101():
+    return json.loads(open(os.path.join(GOLDEN, "stark101_proof.wit")).read())
+
+
+@settings(max_examples=200, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(data=st.data())
+def test_stark101_host_parser_agrees_with_python_reader(S, base101, data):
+    """The same for the stark101 witnesses (stark101/src/main.simf:12-20, lists of 0..31 items: dropping or duplicating a sibling or a whole FRI
+    layer stays well-typed and must pack identically in both implementations)."""
+    text = data.draw(mutated_wit(base101))
+    blob, offsets, bad = S.witness.pack_stark101_wits([text])
+    try:
+        rec = W.pack_stark101(W.load_wit(text))
+    except (W.WitnessTypeError, ValueError, KeyError, IndexError, TypeError, RecursionError):
+        rec = None
+    if rec is None:
+        assert bad[0], text[:300]
+    else:
+        assert not bad[0], text[:300]
+        assert len(blob) == len(rec) and (blob == rec).all()
