@@ -129,3 +129,76 @@ def test_stark101_host_parser_agrees_with_python_reader(S, base101, data):
     else:
         assert not bad[0], text[:300]
         assert len(blob) == len(rec) and (blob == rec).all()
+
+
+# ---- GPU tokeniser (csrc/wit_kernels.cu) against the host parser on the same kind of mutations --------------------------------
+def _random_mutation(rng, value):
+    toks = TOKEN.findall(value)
+    for _ in range(int(rng.integers(0, 4))):
+        kind = rng.choice(["respell", "paren", "trail", "drop", "dup", "swap", "big", "junk"])
+        i = int(rng.integers(0, len(toks)))
+        t = toks[i]
+        if t[0].isdigit() and not re.fullmatch(r"0x[0-9a-fA-F]+|[0-9]+", t):
+            continue
+        if kind == "respell" and t[0].isdigit():
+            v = int(t, 0)
+            toks[i] = [str(v), hex(v), "0x00" + format(v, "x"), (str(v)[0] + "_" + str(v)[1:]) if len(str(v)) > 1 else str(v), "0x" + format(v, "X")][int(rng.integers(0, 5))]
+        elif kind == "paren" and t[0].isdigit():
+            toks[i:i + 1] = ["(", t, ")"]
+        elif kind == "trail" and t in (")", "]") and i > 0 and toks[i - 1] not in ("(", "[", ","):
+            toks.insert(i, ",")
+        elif kind == "drop" and len(toks) > 1:
+            del toks[i]
+        elif kind == "dup":
+            toks.insert(i, t)
+        elif kind == "swap" and i + 1 < len(toks):
+            toks[i], toks[i + 1] = toks[i + 1], toks[i]
+        elif kind == "big" and t[0].isdigit():
+            toks[i] = str(int(t, 0) + [2**32, 2**64, 2**256][int(rng.integers(0, 3))])
+        elif kind == "junk":
+            toks.insert(i, [";", "list", "!", "x", "0x", "-1", "1.5", "{"][int(rng.integers(0, 8))])
+    seps = [["", " ", "  ", "\\n", "\\t "][int(rng.integers(0, 5))] for _ in range(len(toks) + 1)]
+    return _render(toks, seps)
+
+
+def _random_wit(rng, base):
+    names = list(base)
+    wit = {k: {"value": v["value"], "type": v.get("type", "")} for k, v in base.items()}
+    victim = names[int(rng.integers(0, len(names)))]
+    wit[victim]["value"] = _random_mutation(rng, base[victim]["value"])
+    if rng.integers(0, 2):
+        wit = {k: wit[k] for k in rng.permutation(names)}
+    if rng.integers(0, 10) == 0:
+        del wit[names[int(rng.integers(0, len(names)))]]
+    text = json.dumps(wit, indent=[None, 0, 2][int(rng.integers(0, 3))])
+    return text.replace("\\\\n", "\\n").replace("\\\\t", "\\t")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,n", [("testing", 1500), ("prod", 96)])
+def test_gpu_tokeniser_agrees_with_host_parser_on_mutations(S, preset, n):
+    """One batch of randomly mutated witnesses through ssym_stwo_pack_wit_batch: record and flag (ok / shape / parse) of every witness equal
+    what ssym_stwo_pack_wit gives — whichever of them the GPU kept on its fast path and whichever it handed to the host parser."""
+    rng = np.random.default_rng(2025)
+    cfg = S.stwo_config(preset, 0)
+    lo = S.stwo_layout(cfg)
+    base = json.loads(open(os.path.join(GOLDEN, f"stwo_proof_{preset}.wit")).read())
+    texts = [_random_wit(rng, base) for _ in range(n)]
+    ver = S.Verifier(0)
+    blob, offsets = S.witness.concat_wit_texts(texts)
+    g_packed, g_flags = ver.stwo_pack_wit_batch(blob, offsets, cfg)
+    ver.close()
+    lib = S.load()
+    import ctypes as C
+
+    n_ok = 0
+    for i, text in enumerate(texts):
+        raw = text.encode()
+        out = np.zeros(lo.stride_words, dtype=np.uint32)
+        shape = C.c_int(0)
+        rc = lib.ssym_stwo_pack_wit(C.byref(cfg), raw, len(raw), C.c_void_p(out.ctypes.data), C.byref(shape))
+        want = 2 if rc != 0 else (1 if shape.value else 0)
+        assert int(g_flags[i]) == want, (i, int(g_flags[i]), want, text[:200])
+        assert (g_packed[i] == out).all(), i
+        n_ok += want == 0
+    assert 0 < n_ok < n  # the batch mixes accepted and refused witnesses
