@@ -245,3 +245,52 @@ def test_compact_blob_shards_by_proof_index(S, orc):
                 assert (numpy_expand(S, cfg, sb, so) == pk[b:e]).all()
             seen += e - b
         assert seen == n
+
+
+@pytest.mark.gpu
+def test_gpu_expand_survives_corrupted_compact_records(S, ver, orc):
+    """Random corruptions of the header, the bitmap, the back references and the record lengths of valid compact records: the GPU either flags the
+    record (zeros out) or expands it to exactly what the independent expander gives; nothing else (run under compute-sanitizer memcheck too)."""
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    lo = S.stwo_layout(cfg)
+    pk = orc.stwo_prove_batch(ocfg(cfg), [77], threads=1)
+    n = 400
+    blob1, off1 = S.witness.compact_stwo(pk, cfg)
+    w = int(off1[1])
+    blob = np.tile(blob1, n)
+    offsets = (np.arange(n + 1, dtype=np.uint64) * np.uint64(w))
+    rng = np.random.default_rng(11)
+    fixed, wit = lo.off_trace_sib, lo.off_fri_sib[0] - lo.off_fri_wit
+    off_bitmap = 8 + fixed + wit
+    slots = cfg.n_queries * (2 * cfg.lde_log + sum(cfg.lde_log - 1 - l for l in range(cfg.n_fri_layers + 1)))
+    off_refs = off_bitmap + ((slots + 31) // 32 + 7) // 8 * 8
+    R = int(blob1[3])
+    for i in range(1, n):
+        base = i * w
+        kind = i % 5
+        if kind == 0:
+            blob[base + int(rng.integers(0, 4))] = np.uint32(rng.integers(0, 2**32))            # header word
+        elif kind == 1:
+            blob[base + off_bitmap + int(rng.integers(0, (slots + 31) // 32))] ^= np.uint32(1 << int(rng.integers(0, 32)))  # a bitmap bit
+        elif kind == 2:
+            blob[base + off_refs:base + off_refs + (R + 3) // 4].view(np.uint8)[int(rng.integers(0, R))] = np.uint8(rng.integers(0, 256))  # a back reference
+        elif kind == 3:
+            blob[base + 1], blob[base + 3] = blob[base + 3], blob[base + 1]                        # D and R swapped
+        else:
+            blob[base + off_refs + (R + 31) // 32 * 8 + int(rng.integers(0, 64))] ^= np.uint32(1)  # a digest word: still a valid record
+    packed, flags = ver.stwo_compact_expand(blob, offsets, cfg, want_flags=True)
+    assert flags[0] == 0 and (packed[0] == pk[0]).all()
+    seen = set()
+    for i in range(n):
+        rec = blob[i * w:(i + 1) * w]
+        try:
+            want = numpy_expand(S, cfg, rec, np.array([0, w], dtype=np.uint64))[0]
+        except (AssertionError, IndexError, ValueError):
+            want = None
+        if flags[i]:
+            assert not packed[i].any()
+            assert want is None, i  # the GPU refuses nothing the format allows
+        else:
+            assert want is not None and (packed[i] == want).all(), i
+        seen.add(int(flags[i]))
+    assert seen == {0, 1}
