@@ -94,12 +94,12 @@ static void pr_domain_build(PrDomain *d, uint32_t n) {
     }
 }
 
-static PrTables *g_pr_tables[8];
+static PrTables *g_pr_tables[128]; /* one entry per (trace_log, lde_log) ever used: fewer than 128 pairs with lde_log <= 16 */
 static pthread_mutex_t g_pr_lock = PTHREAD_MUTEX_INITIALIZER;
 static const PrTables *pr_tables(uint32_t trace_log, uint32_t lde_log) {
     pthread_mutex_lock(&g_pr_lock);
     PrTables *t = NULL;
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 128; i++) {
         if (g_pr_tables[i] && g_pr_tables[i]->trace_log == trace_log && g_pr_tables[i]->lde_log == lde_log) { t = g_pr_tables[i]; break; }
         if (!g_pr_tables[i]) {
             t = (PrTables *)calloc(1, sizeof *t);
