@@ -80,7 +80,9 @@ static const uint32_t SHA_K[64] = {
     0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
-static uint64_t g_compressions; /* instrumentation: counts compression-function calls */
+/* instrumentation (per thread, so that the multi-threaded CPU baseline does not bounce a shared cache line): compression-function calls and
+ * M31 operations of the calling thread — the per-proof work figures of SURVEY.md section 8d come from these */
+static _Thread_local uint64_t g_compressions, g_m31_mul, g_m31_add, g_m31_inv;
 
 static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
@@ -151,10 +153,11 @@ static int eq_256(u256 a, u256 b) { return memcmp(a.w, b.w, sizeof a.w) == 0; }
 typedef uint32_t M31;
 
 static M31 m31(uint32_t v) { return jet_modulo_32(v, M31_MODULUS); }                 /* m31.simf:17-19 */
-static M31 m31_add(M31 a, M31 b) { return m31(jet_add_32(a, b)); }                  /* m31.simf:22-26 */
+static M31 m31_add(M31 a, M31 b) { g_m31_add++; return m31(jet_add_32(a, b)); }     /* m31.simf:22-26 */
 static M31 m31_neg(M31 a) { return jet_subtract_32(M31_MODULUS, a); }               /* m31.simf:29-32 (unreduced) */
 static M31 m31_sub(M31 a, M31 b) { return m31_add(a, m31_neg(b)); }                 /* m31.simf:35-37 */
 static M31 m31_mul(M31 a, M31 b) {                                                  /* m31.simf:40-45 */
+    g_m31_mul++;
     return (uint32_t)jet_modulo_64(jet_multiply_32(a, b), M31_MODULUS);
 }
 static M31 m31_exp(M31 a, M31 b) { /* m31.simf:57-80: square-and-multiply, <= 65536 steps */
@@ -174,6 +177,7 @@ static M31 m31_pow8(M31 a) { return m31_pow2(m31_pow4(a)); } /* m31.simf:93-95 *
 static M31 m31_pow16(M31 a) { return m31_pow4(m31_pow4(a)); } /* m31.simf:98-100 */
 static int m31_eq(M31 a, M31 b) { return a == b; }          /* m31.simf:103-105 (bitwise) */
 static M31 m31_inv(M31 a) {                                 /* m31.simf:117-132 */
+    g_m31_inv++;
     if (a == 0) { /* is_zero_32 -> assert!(false); 0 */
         t_fail = 1;
         return 0;
@@ -860,6 +864,9 @@ EXPORT void oracle_stwo_verify_batch(const ssym_stwo_config_t *cfg, const uint32
 
 EXPORT uint64_t oracle_compression_count(void) { return g_compressions; }
 EXPORT void oracle_compression_reset(void) { g_compressions = 0; }
+/* M31 operations of the calling thread since the last reset: out = {mul (those inside inversions included), add / sub, inversions} */
+EXPORT void oracle_field_op_counts(uint64_t out[3]) { out[0] = g_m31_mul; out[1] = g_m31_add; out[2] = g_m31_inv; }
+EXPORT void oracle_field_op_reset(void) { g_m31_mul = g_m31_add = g_m31_inv = 0; }
 
 /* ------------------------------------------------------------------------- */
 /* Function-level exports for the known-answer tests (ctypes)                 */

@@ -167,3 +167,25 @@ def test_stark101_negatives(orc):
     offs = np.arange(len(recs) + 1, dtype=np.uint64) * n
     accept, status, _ = orc.s101_verify_batch(blob, offs)
     assert status[0] == 0 and all(status[1:] != 0) and accept[0] == 1
+
+
+def test_work_per_proof_matches_survey_8d(orc):
+    """The per-proof work figures builder and judge use (3 806 compressions, 65 486 M31 multiplications, 55 220 reduced
+    additions, 162 inversions for the prod fixture under the literal semantics) are what the restated program executes."""
+    import ctypes as C
+
+    from oracle import witparse as W
+
+    orc.lib.oracle_compression_count.restype = C.c_uint64
+    expect = {("prod", O.MODE_REF_LITERAL): (3806, 65486, 55220, 162), ("prod", O.MODE_PROVER_CONSISTENT): (3806, 66718, 55908, 178),
+              ("testing", O.MODE_REF_LITERAL): (70, 3782, 3119, 6)}
+    for (preset, mode), want in expect.items():
+        p = O.PRESETS[preset]
+        packed, rej = W.pack_stwo(W.load_wit(open(os.path.join(GOLDEN, f"stwo_proof_{preset}.wit")).read()), p["n_queries"], p["n_fri_layers"], p["lde_log"])
+        assert not rej
+        orc.lib.oracle_compression_reset()
+        orc.lib.oracle_field_op_reset()
+        orc.stwo_verify_batch(O.make_config(preset, mode), packed, 1)
+        ops = (C.c_uint64 * 3)()
+        orc.lib.oracle_field_op_counts(ops)
+        assert (int(orc.lib.oracle_compression_count()), int(ops[0]), int(ops[1]), int(ops[2])) == want, (preset, mode)
