@@ -2,20 +2,26 @@
 """Headline benchmark: Stwo proofs verified per second on N B200s (BASELINE.json metric).
 
 Workload (BASELINE.json configs[1]): the reference's own `stwo-verifier/tests/data/proof.json` witness (prod preset:
-LDE 2^13, 16 queries, 1+8 FRI layers, 54 488 B packed, 3 806 SHA-256 compressions) replicated x1024 per GPU.
-A step = one pass of verify_proof over that batch.  Weak scaling: every rank verifies its own 1024-proof shard and the
-only exchange is the accept-bitmap gather.
+LDE 2^13, 16 queries, 1+8 FRI layers, 54 488 B packed, 3 806 SHA-256 compressions) replicated x1024 per GPU = one PASS.
+A STEP = `--passes` (default 256) passes of verify_proof over that 1024-proof batch, issued back to back through the C-ABI
+(`config.passes_per_step`): with the driver's `--steps 20` the timed region is about a second instead of 4 ms, so first-use
+effects, rank start skew and the one NCCL gather cannot move the number.  Weak scaling: every rank verifies its own
+shard; the only exchange is the accept-bitmap gather.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 1024] [--mode ref-literal|prover-consistent]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 1024] [--passes 256] [--mode ref-literal|prover-consistent]
 
-`value`  : whole-job proofs/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).
-`e2e`    : the same metric through the C-ABI with HOST (pinned) buffers: H2D of the batch (compact transport form) + D2H of the
-           bitmap inside the timed region; `e2e_packed`: the same on fixed-stride packed records; `e2e_wit`: from `.wit` text.
-`roofline` / `roofline_int32` : the dominant kernel (stwo_merkle_kernel) against HBM and against the measured INT32 rate.
-`cpu_baseline` : the C oracle (a port of the .simf programs; the reference binary cannot be built here) on the host cores.
+`value`    : whole-job proofs/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`      : the same metric through the C-ABI with HOST (pinned) buffers: H2D of every pass's batch (compact transport form) + D2H of
+             its bitmap inside the timed region; `e2e_packed`: the same on fixed-stride packed records; `e2e_wit`: from `.wit` text.
+`roofline` : the dominant kernel against the resource that binds it, the INT32 ALU pipe: ALU-pipe warp instructions per launch (ncu,
+             profiles/step_pipe_counts.json) / CUDA-event launch duration / measured ALU issue rate; HBM figures beside it.
+`cpu_baseline` : the C oracle (a port of the .simf programs; the reference binary cannot be built here) on the host cores;
+             `cpu_baseline_fast`: the same port with SHA-NI / word-wise absorbs / Mersenne folding.
+`configs`  : bounded runs of BASELINE configs 1, 3, 4, 5 (bench_sub.py), each with its own parity check.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import sys
@@ -30,7 +36,12 @@ COMPRESSIONS_PER_PROOF = 3806      # SURVEY.md section 8d (46 channel + 880 trac
 MERKLE_COMPRESSIONS_PER_PROOF = 3760
 LITERAL_OPS_PER_COMPRESSION = 2296  # FIPS 180-4 literal: 64*26 + 48*13 + 8
 LITERAL_OPS_PER_PROOF = 3806 * 2296 + 65486 * 6 + 55220 * 4
-NCU_DRAM_BYTES_PER_LAUNCH = 58_279_936  # stwo_merkle_kernel at 1024 proofs: 58.09 MB read + 0.19 MB written (profiles/r01_ncu_summary.md)
+METRIC = "stwo_proofs_verified_per_s"
+
+
+def workload_name(n):
+    """One string for both arms (the driver compares `config.workload` of the two lines)."""
+    return f"stwo-verifier proof.json witness (prod preset: LDE 2^13, 16 queries, 1+8 FRI layers) replicated x{n} per GPU"
 
 
 def log(*a):
@@ -48,6 +59,28 @@ def load_workload(S, batch, mode_name):
     lo = S.stwo_layout(cfg)
     assert lo.algorithmic_bytes == ALG_BYTES_PER_PROOF
     return cfg, lo, np.tile(packed, batch)
+
+
+def csrc_sha16():
+    d = os.path.join(ROOT, "stark-symphony_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_pipe_counts(mode_name):
+    """ncu-measured warp-instruction counts per kernel launch (profiles/step_pipe_counts.json, written by profiles/pipe_counts.py)."""
+    try:
+        doc = json.load(open(os.path.join(ROOT, "profiles", "step_pipe_counts.json")))
+        m = doc["modes"][mode_name]
+        return {"kernels": m["kernels"], "proofs_per_launch": m["proofs_per_launch"], "source": m["source"],
+                "matches_build": doc.get("csrc_sha16") == csrc_sha16(), "csrc_sha16": doc.get("csrc_sha16")}
+    except Exception as e:  # pragma: no cover
+        log(f"profiles/step_pipe_counts.json unavailable: {e}")
+        return None
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -83,7 +116,7 @@ def cpu_threads():
 
 
 def oracle_run(orc, ocfg, packed, n, threads, proofs_total):
-    """Verify `proofs_total` proofs (cycling through the n-proof batch) on `threads` threads; returns seconds."""
+    """Verify `proofs_total` proofs (cycling through the n-proof batch) on `threads` threads; returns (seconds, proofs done)."""
     from oracle import oracle as O
 
     per = (proofs_total + threads - 1) // threads
@@ -106,19 +139,27 @@ def oracle_run(orc, ocfg, packed, n, threads, proofs_total):
     return time.perf_counter() - t0, per * threads
 
 
-def cpu_baseline(cfg, packed, n, budget_s=15.0):
+def cpu_baseline(cfg, packed, n, budget_s=3.0, fast=False):
     from oracle import oracle as O
 
     orc = O.Oracle()
     ocfg = O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
     threads = cpu_threads()
-    t1, _ = oracle_run(orc, ocfg, packed, n, 1, 8)
-    per_proof = t1 / 8
-    total = int(max(threads * 8, min(budget_s / per_proof, 64 * n)))
-    dt, done = oracle_run(orc, ocfg, packed, n, threads, total)
+    level = orc.set_fast(fast)
+    try:
+        t1, _ = oracle_run(orc, ocfg, packed, n, 1, 8)
+        per_proof = t1 / 8
+        total = int(max(threads * 8, min(budget_s * threads / per_proof, 256 * n)))
+        dt, done = oracle_run(orc, ocfg, packed, n, threads, total)
+    finally:
+        orc.set_fast(False)
+    how = ("oracle/ssym_oracle.c -O3, the literal port: byte-at-a-time SHA-256 absorbs, scalar compression, `%` reductions" if not fast else
+           "oracle/ssym_oracle.c -O3 in fast mode (oracle_set_fast_sha): 4-byte absorbs, block-wise padding, Mersenne folding, "
+           + ("SHA-NI compressions" if level == 2 else "scalar compressions (this host has no SHA-NI)") + "; bit-identical results "
+           "(tests/test_oracle_fixtures.py::test_fast_sha_mode_is_bit_identical)")
     return {"value": done / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
-            "sample": f"{done} proofs (cycling the same {n}-proof batch) on {threads} threads, {dt:.2f} s wall; oracle/ssym_oracle.c -O3, "
-                      "plain C SHA-256 (the reference's `simfony run` cannot be built here: no Rust, un-vendored crates)",
+            "sample": f"{done} proofs (cycling the same {n}-proof batch) on {threads} threads, {dt:.2f} s wall; {how} "
+                      "(the reference's `simfony run` cannot be built here: no Rust, un-vendored crates)",
             "compressions_per_s": done * COMPRESSIONS_PER_PROOF / dt}
 
 
@@ -142,8 +183,8 @@ def run_reference(args):
     threads = cpu_threads()
     t1, _ = oracle_run(orc, ocfg, packed, n, 1, 8)
     per_proof = t1 / 8
-    budget = 100.0
-    m = int(max(threads, min(n, budget * threads / ((args.steps + args.warmup) * per_proof))))
+    budget = 60.0
+    m = int(max(threads, min(n * args.passes, budget * threads / ((args.steps + args.warmup) * per_proof))))
     for _ in range(args.warmup):
         oracle_run(orc, ocfg, packed, n, threads, m)
     t0 = time.perf_counter()
@@ -153,13 +194,25 @@ def run_reference(args):
         done += d
     dt = time.perf_counter() - t0
     value = done / dt
-    sample = f"{done // args.steps} proofs per step (of the {n}-proof batch) x {args.steps} steps on {threads} threads"
+    sample = (f"{done // args.steps} proofs per step (a bounded sample of the step's {args.passes} x {n} proofs) x {args.steps} steps on {threads} threads; "
+              "oracle/ssym_oracle.c, the literal port (byte-at-a-time SHA-256)")
+    # the same sample with the fast CPU path, for context (not the arm's value)
+    fast = None
+    try:
+        level = orc.set_fast(True)
+        dtf, df = oracle_run(orc, ocfg, packed, n, threads, m * 4)
+        fast = {"value": df / dtf, "unit": "proofs/s", "cores": threads, "kind": "port", "sha_ni": level == 2,
+                "sample": f"{df} proofs on {threads} threads, fast mode of the same port (SHA-NI / word-wise absorbs / Mersenne folding)"}
+    finally:
+        orc.set_fast(False)
     line = {
-        "impl": "reference", "metric": "stwo_proofs_verified_per_s", "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-        "data": "reference fixture stwo-verifier/tests/data/proof.json replicated",
-        "config": {"workload": f"stwo-verifier proof.json witness (prod preset) replicated x{n}", "mode": args.mode, "batch_per_gpu": n},
+        "data": "reference fixture stwo-verifier/tests/data/proof.json (via generate_wit.py) replicated (BASELINE configs[1])",
+        "config": {"workload": workload_name(n), "mode": args.mode, "batch_per_gpu": n, "passes_per_step": args.passes,
+                   "sampled_proofs_per_step": done // args.steps},
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline_fast": fast,
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,10 +224,13 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """NVML SM clock / throttle reasons / power, sampled every `interval` s on a side thread (>= 0.2 s: eight ranks polling NVML at
+    50 Hz showed up in the round-1 scaling numbers)."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
 
-    def __init__(self, torch_device_index):
+    def __init__(self, torch_device_index, interval=0.2):
         self.samples, self.reasons, self.power = [], set(), []
+        self.interval = interval
         self.stop = threading.Event()
         self.ok = False
         self.max_mhz = None
@@ -197,22 +253,24 @@ class ClockSampler:
             log(f"clock sampling unavailable: {e}")
         self.thread = threading.Thread(target=self.run, daemon=True)
 
-    def run(self):
+    def sample(self):
         nv = self.nv
-        while not self.stop.is_set():
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            self.stop.wait(0.02)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop.wait(self.interval):
+            self.sample()
 
     def __enter__(self):
         if self.ok:
@@ -243,6 +301,23 @@ def emit(line):
 _REAL_STDOUT = None
 
 
+def max_over_ranks(torch, dist, world, values):
+    t = torch.tensor(list(values), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu()]
+
+
+def gather_ranks(torch, dist, world, values):
+    """-> list over ranks of the per-rank value lists."""
+    t = torch.tensor(list(values), dtype=torch.float64, device="cuda")
+    if world == 1:
+        return [[float(x) for x in t.cpu()]]
+    out = torch.zeros((world, t.numel()), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(out.view(-1), t)
+    return [[float(x) for x in row] for row in out.cpu()]
+
+
 def main():
     # Libraries (NCCL's "NCCL version ..." banner, for one) write to fd 1: keep stdout clean for the single JSON line.
     global _REAL_STDOUT
@@ -251,21 +326,23 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None)
-    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="proofs per GPU per step (BASELINE config: 1024)")
+    ap.add_argument("--batch", type=int, default=1024, help="proofs per GPU per pass (BASELINE config: 1024)")
+    ap.add_argument("--passes", type=int, default=256, help="passes over the batch per step (one C-ABI call each); sizes the timed region")
+    ap.add_argument("--e2e-passes", type=int, default=64, help="passes per step of the host-buffer (e2e) legs")
     ap.add_argument("--mode", default="ref-literal", choices=["ref-literal", "prover-consistent"])
     ap.add_argument("--copies", type=int, default=8, help="distinct device copies of the batch rotated through (defeats L2 reuse)")
-    ap.add_argument("--pipeline", type=int, default=8, help="batches in flight per GPU (ssym_set_pipeline_depth); 1 = strictly serial steps")
+    ap.add_argument("--pipeline", type=int, default=8, help="batches in flight per GPU (ssym_set_pipeline_depth); 1 = strictly serial passes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the bounded runs of BASELINE configs 1, 3, 4, 5")
+    ap.add_argument("--headline-only", action="store_true", help="device-resident headline loop only (profiling runs)")
     args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    args.passes = max(1, args.passes)
     if args.impl == "reference":
-        args.steps = args.steps or 20
-        args.warmup = 3 if args.warmup is None else args.warmup
         return run_reference(args)
-    args.steps = args.steps or 2000
-    args.warmup = max(3, 50 if args.warmup is None else args.warmup)
 
     import numpy as np
     import torch
@@ -286,122 +363,78 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
     import stark_symphony_b200 as S
-    from importlib import import_module
 
-    sharding = import_module("stark_symphony_b200.sharding")
-
-    n = args.batch
+    n, R = args.batch, args.passes
     cfg, lo, host_batch = load_workload(S, n, args.mode)
     ver = S.Verifier(local_rank)
     stream = torch.cuda.Stream()  # a real (non-default) stream: the library and the timing events share it
     torch.cuda.set_stream(stream)
     ver.set_stream(stream.cuda_stream)
 
-    # R distinct device copies of the batch, rotated: R * n * 54.5 KB > 126 MB L2, so no step finds its input in L2
+    # `copies` distinct device copies of the batch, rotated: copies * n * 54.5 KB > 126 MB L2, so no pass finds its input in L2
     depth = max(1, min(8, args.pipeline))
     copies = max(1, args.copies, depth)
     dev = [torch.from_numpy(host_batch.view(np.int32)).cuda() for _ in range(copies)]
     ver.set_pipeline_depth(depth)
-    # outputs: one bitmap row per step (never reused inside the timed region), one status buffer per in-flight batch
+    # outputs: one bitmap row per pass of the timed region (never reused inside it), one status buffer per in-flight batch
     words = (n + 31) // 32
-    rows = max(args.steps, args.warmup)
+    rows = max(args.steps, args.warmup) * R
     accept_all = torch.zeros((rows, words), dtype=torch.int32, device="cuda")
     gathered = torch.zeros((world, rows, words), dtype=torch.int32, device="cuda") if world > 1 else None
     statuses = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(depth)]
     total_n = n * world
 
-    def step(k):
-        """One pass of verify_proof over one batch (asynchronous; with depth > 1 up to `depth` batches are in flight)."""
-        ver.stwo_verify_batch(dev[k % copies], cfg, n, accept_out=accept_all[k], status_out=statuses[k % depth])
+    def step(k, c=cfg, acc=accept_all, sts=statuses):
+        """One step = R passes of verify_proof over the 1024-proof batch (asynchronous; up to `depth` passes in flight)."""
+        for p in range(k * R, (k + 1) * R):
+            ver.stwo_verify_batch(dev[p % copies], c, n, accept_out=acc[p % acc.shape[0]], status_out=sts[p % depth])
 
-    def finish():
+    def finish(ev_join=None):
         """Order all in-flight batches into the timing stream, then the job's only exchange: the accept-bitmap gather."""
         ver.join()
+        if ev_join is not None:
+            ev_join.record(stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), accept_all.view(-1))
 
-    int32_ops, probe_ms = ver.int32_peak_probe()
-    for k in range(args.warmup):
+    int32_lanes, probe_ms = ver.int32_peak_probe()
+    for k in range(args.warmup):  # >= 3 steps = >= 3 R passes >> 2 x depth: every lane's scratch exists, NCCL is connected
         step(k)
     finish()
     torch.cuda.synchronize()
     launches0 = ver.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     with ClockSampler(local_rank) as clocks:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        clocks.sample() if clocks.ok else None
+        h0 = time.perf_counter()
+        ev[0].record(stream)
         for k in range(args.steps):
             step(k)
-        finish()
-        e1.record(stream)
+        h1 = time.perf_counter()
+        finish(ev[1])
+        ev[2].record(stream)
         torch.cuda.synchronize()
+        h2 = time.perf_counter()
         if world > 1:
             dist.barrier()
-        ms = e0.elapsed_time(e1)
     launches = ver.launch_count - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = total_n * args.steps / (ms_max * 1e-3)
+    ms = ev[0].elapsed_time(ev[2])
+    per_rank = gather_ranks(torch, dist, world, [ms, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), (h1 - h0) * 1e3, (h2 - h0) * 1e3])
+    ms_max = max(r[0] for r in per_rank)
+    value = total_n * R * args.steps / (ms_max * 1e-3)
+    pass_ms = ms_max / (args.steps * R)
 
-    # The same pipelined loop under the other semantics (DESIGN.md section 1): PROVER_CONSISTENT accepts the fixture, and accepted proofs are
-    # where the shared-node Merkle schedule applies (paths of one tree that have met are hashed once).
-    other_mode = S.MODE_PROVER_CONSISTENT if args.mode == "ref-literal" else S.MODE_REF_LITERAL
-    cfg_other = S.stwo_config("prod", other_mode)
-    other_steps = max(3, min(args.steps, 500))
-
-    accept_other = torch.zeros((other_steps, words), dtype=torch.int32, device="cuda")
-    statuses_other = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(depth)]
-
-    def step_other(k):
-        ver.stwo_verify_batch(dev[k % copies], cfg_other, n, accept_out=accept_other[k % other_steps], status_out=statuses_other[k % depth])
-
-    for k in range(min(args.warmup, 10)):
-        step_other(k)
-    ver.join()
-    torch.cuda.synchronize()
-    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    o0.record(stream)
-    for k in range(other_steps):
-        step_other(k)
-    ver.join()
-    o1.record(stream)
-    torch.cuda.synchronize()
-    t = torch.tensor([o0.elapsed_time(o1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    other_value = total_n * other_steps / (float(t.item()) * 1e-3)
-    other_accepted = int(np.unpackbits(accept_other[other_steps - 1].cpu().numpy().view(np.uint8), bitorder="little")[:n].sum())
-    assert other_accepted == (n if other_mode == S.MODE_PROVER_CONSISTENT else 0)
-
-    # Per-kernel durations for the roofline: the same steps issued strictly serially (depth 1), with CUDA events around
-    # every kernel on the launching stream (ssym_profile_enable), so each kernel is timed alone on the GPU.
-    ver.set_pipeline_depth(1)
-    ver.profile_read()
-    ver.profile_enable(True)
-    serial_steps = max(3, min(args.steps, 200))
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    for k in range(serial_steps):
-        step(k)
-    e3.record(stream)
-    torch.cuda.synchronize()
-    serial_ms_per_step = e2.elapsed_time(e3) / serial_steps
-    ver.profile_enable(False)
-    prof = ver.profile_read()
-    ver.set_pipeline_depth(depth)
-
-    # correctness of what was timed (outside the timed region): every rank's statuses against the oracle on a slice
-    status = statuses[(args.steps - 1) % depth]
-    st = status.cpu().numpy().view(np.uint32)
-    last = (gathered[:, args.steps - 1, :] if world > 1 else accept_all[args.steps - 1]).contiguous().cpu().numpy()
+    # correctness of what was timed (outside the timed region): every pass's bitmap, every rank's statuses against the oracle
+    st = statuses[(args.steps * R - 1) % depth].cpu().numpy().view(np.uint32)
+    used_rows = accept_all[: args.steps * R].cpu().numpy()
+    assert (used_rows == used_rows[0]).all(), "passes disagree"
+    last_row = args.steps * R - 1
+    last = (gathered[:, last_row, :] if world > 1 else accept_all[last_row]).contiguous().cpu().numpy()
     bits = np.concatenate([np.unpackbits(r.view(np.uint8), bitorder="little")[:n] for r in last.reshape(world, words)])
     accepted = int(bits.sum())
-    first_rows = accept_all[: args.steps].cpu().numpy()
-    assert (first_rows == first_rows[0]).all(), "steps disagree"
     if rank == 0:
         from oracle import oracle as O
 
@@ -411,122 +444,200 @@ def main():
         assert (st[:4] == o_status).all() and (st == st[0]).all(), "GPU status differs from the oracle"
         assert accepted == (total_n if args.mode == "prover-consistent" else 0)
 
-    # end to end: host (pinned) buffers through the same C-ABI call, copies inside the timed region
+    line = {
+        "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "reference fixture stwo-verifier/tests/data/proof.json (via generate_wit.py) replicated (BASELINE configs[1]); distinct GPU-proven proofs: configs.c3 / c5",
+        "config": {"workload": workload_name(n), "mode": args.mode, "batch_per_gpu": n, "passes_per_step": R, "proofs_per_step": total_n * R,
+                   "ms_per_pass": pass_ms, "accepted": accepted,
+                   "step": f"one step = {R} passes of verify_proof over the {n}-proof batch, one ssym_stwo_verify_batch call per pass (timed region = steps x passes calls)",
+                   "l2": f"rotating {copies} distinct device copies of the batch ({copies * n * lo.stride_words * 4 / 1e6:.0f} MB > 126 MB L2)",
+                   "pipeline": f"{depth} batches in flight per GPU (ssym_set_pipeline_depth); per-kernel times below are per launch, kernels of consecutive passes overlap" if depth > 1 else "serial passes",
+                   "parallelism": f"proof-sharded x{world} (one process per GPU, no data-path collective), one NCCL all_gather of the accept bitmaps of all passes inside the timed region" if world > 1 else "single GPU",
+                   "numa": (f"every rank pinned to the CPUs of its GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else "no NUMA binding")},
+        "merkle_hashes_per_s": value * MERKLE_COMPRESSIONS_PER_PROOF / 2.0,
+        "sha256_compressions_per_s": value * COMPRESSIONS_PER_PROOF,
+        "gpu_launches": int(launches),
+        "timing_per_rank": {"columns": ["timed_ms (events: first launch -> after gather)", "compute_ms (first launch -> all batches joined)",
+                                        "allgather_ms (device)", "launch_loop_ms (host: issuing all calls)", "host_wall_ms (launch -> synchronized)"],
+                            "ranks": per_rank,
+                            "note": "the headline uses max over ranks of column 0; a launch loop as long as the timed region means the host, not the GPU, sets the rate"},
+        "clocks": clocks.summary(),
+    }
+    if args.headline_only:
+        if rank == 0:
+            emit(line)
+        ver.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- the same pipelined loop under the other semantics ---------------------------------------------
+    # PROVER_CONSISTENT accepts the fixture, and accepted proofs are where the shared-node Merkle schedule applies.
+    other_mode = S.MODE_PROVER_CONSISTENT if args.mode == "ref-literal" else S.MODE_REF_LITERAL
+    other_name = "prover-consistent" if args.mode == "ref-literal" else "ref-literal"
+    cfg_other = S.stwo_config("prod", other_mode)
+    other_steps = max(3, args.steps // 4)
+    accept_other = torch.zeros((R, words), dtype=torch.int32, device="cuda")
+    statuses_other = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(depth)]
+    for k in range(2):
+        step(k, cfg_other, accept_other, statuses_other)
+    ver.join()
+    torch.cuda.synchronize()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    o0.record(stream)
+    for k in range(other_steps):
+        step(k, cfg_other, accept_other, statuses_other)
+    ver.join()
+    o1.record(stream)
+    torch.cuda.synchronize()
+    other_ms = max_over_ranks(torch, dist, world, [o0.elapsed_time(o1)])[0]
+    other_value = total_n * R * other_steps / (other_ms * 1e-3)
+    other_accepted = int(np.unpackbits(accept_other[R - 1].cpu().numpy().view(np.uint8), bitorder="little")[:n].sum())
+    assert other_accepted == (n if other_mode == S.MODE_PROVER_CONSISTENT else 0)
+
+    # ---- per-kernel durations for the roofline: the same passes issued strictly serially (depth 1), CUDA events around every kernel ----
+    ver.set_pipeline_depth(1)
+    prof_by_mode = {}
+    serial_ms = {}
+    for name, c in ((args.mode, cfg), (other_name, cfg_other)):
+        ver.profile_read()
+        ver.profile_enable(True)
+        serial_passes = 200
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for p in range(serial_passes):
+            ver.stwo_verify_batch(dev[p % copies], c, n, accept_out=accept_other[p % R], status_out=statuses_other[0])
+        e3.record(stream)
+        torch.cuda.synchronize()
+        serial_ms[name] = e2.elapsed_time(e3) / serial_passes
+        ver.profile_enable(False)
+        prof_by_mode[name] = ver.profile_read()
+    ver.set_pipeline_depth(depth)
+    prof = prof_by_mode[args.mode]
+
+    # ---- end to end: host (pinned) buffers through the same C-ABI calls, copies inside the timed region ---------------------------
+    ver.set_stream(None)
+    Re = max(1, args.e2e_passes)
+    e2e_steps = args.steps
+    acc_host = torch.empty(words, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    acc_rows = torch.zeros((Re, words), dtype=torch.int32).pin_memory()
+    acc_rows_np = acc_rows.numpy().view(np.uint32)
     pinned = torch.empty(host_batch.size, dtype=torch.int32).pin_memory()
     pinned.numpy()[:] = host_batch.view(np.int32)
     host_view = pinned.numpy().view(np.uint32)
-    acc_host = torch.empty((n + 31) // 32, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    ver.set_stream(None)
-    pin_t = torch.empty(host_batch.size, dtype=torch.int32, device="cuda")
-    pin_t.copy_(pinned, non_blocking=True)
-    torch.cuda.synchronize()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for _ in range(5):
-        pin_t.copy_(pinned, non_blocking=True)
-    c1.record()
-    torch.cuda.synchronize()
-    h2d_gbs = 5 * host_batch.nbytes / (c0.elapsed_time(c1) * 1e-3) / 1e9  # plain pinned H2D copy of the same batch: the PCIe ceiling of e2e
-    del pin_t
-    e2e_steps = max(5, min(args.steps, 100))
-    for _ in range(3):
-        ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc_host)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc_host)  # synchronous: returns with the bitmap in host memory
-    e2e_sync_s = time.perf_counter() - t0
-    # throughput mode of the same call (ssym_set_host_async): each call enqueues its H2D + kernels + D2H and returns, one synchronize
-    # at the end; every step has its own pinned bitmap row, and the rows are checked after the timed region
-    acc_rows = torch.zeros((e2e_steps, (n + 31) // 32), dtype=torch.int32).pin_memory()
-    acc_rows_np = acc_rows.numpy().view(np.uint32)
-    ver.set_host_async(True)
-    for k in range(3):
-        ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc_rows_np[k])
-    ver.synchronize()
-    acc_rows_np[:] = 0xA5A5A5A5
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc_rows_np[k])
-    ver.synchronize()
-    e2e_s = time.perf_counter() - t0
-    ver.set_host_async(False)
-    assert (acc_rows_np == acc_host[None, :]).all(), "asynchronous host-buffer results differ from the synchronous call"
-    t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_n * e2e_steps / float(t[0].item())
-    e2e_sync_value = total_n * e2e_steps / float(t[1].item())
 
-    # the same, with the batch in the compact transport form (include/ssym.h: per tree every distinct sibling once, one bit per path
-    # slot; made by the host packer ssym_stwo_compact_pack, lossless): fewer bytes cross the link, the GPU expands them into HBM
+    # compact transport form (include/ssym.h): produced by the host packer OUTSIDE the timed region; its cost is reported
     bound_words = int(S.load().ssym_stwo_compact_bound(C.byref(cfg), n))
     c_pinned = torch.empty(bound_words, dtype=torch.int32).pin_memory()
+    S.witness.compact_stwo(host_batch, cfg, out=c_pinned.numpy().view(np.uint32))  # warm (page faults of the output)
+    t0 = time.perf_counter()
     c_blob_full, c_off_np = S.witness.compact_stwo(host_batch, cfg, out=c_pinned.numpy().view(np.uint32))
+    pack_s = time.perf_counter() - t0
     c_words = int(c_off_np[n])
     c_blob = c_blob_full[:c_words]
     c_off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
     c_off.numpy()[:] = c_off_np.view(np.int64)
     c_off_view = c_off.numpy().view(np.uint64)
-    acc_c = torch.empty((n + 31) // 32, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    for _ in range(3):
-        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_c)
-    assert (acc_c == acc_host).all(), "compact path disagrees with the packed path"
-    cl0 = ver.launch_count
+
+    def host_leg(call, nbytes):
+        """-> (async proofs/s, sync proofs/s, launches per pass, plain-copy GB/s alone, plain-copy GB/s with all ranks copying) for one host-buffer entry point."""
+        for _ in range(3):
+            call(acc_host)
+        ref_bits = acc_host.copy()
+        l0 = ver.launch_count
+        sync_passes = max(8, Re // 4)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(sync_passes):
+            call(acc_host)  # synchronous: returns with the bitmap in host memory
+        sync_s = time.perf_counter() - t0
+        per_pass = (ver.launch_count - l0) // sync_passes
+        # throughput mode of the same call (ssym_set_host_async): each call enqueues its H2D + kernels + D2H and returns; one synchronize per step;
+        # every pass of a step has its own pinned bitmap row, checked after the timed region
+        ver.set_host_async(True)
+        for k in range(4):
+            call(acc_rows_np[k % Re])
+        ver.synchronize()
+        acc_rows_np[:] = 0xA5A5A5A5
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for p in range(Re):
+                call(acc_rows_np[p])
+            ver.synchronize()
+        async_s = time.perf_counter() - t0
+        ver.set_host_async(False)
+        assert (acc_rows_np == ref_bits[None, :]).all(), "asynchronous host-buffer results differ from the synchronous call"
+        a, s_ = max_over_ranks(torch, dist, world, [async_s, sync_s])
+        return total_n * Re * e2e_steps / a, total_n * sync_passes / s_, int(per_pass), ref_bits
+
+    def plain_copy_gbs(src_tensor, nbytes, concurrent):
+        """Plain pinned H2D copies of the same bytes: the link ceiling of a host leg.  concurrent: all ranks copy at the same time (barrier)."""
+        dst = torch.empty(src_tensor.numel(), dtype=src_tensor.dtype, device="cuda")
+        reps = max(4, int(0.25 / (nbytes / 50e9)))
+        dst.copy_(src_tensor, non_blocking=True)
+        torch.cuda.synchronize()
+        if concurrent and world > 1:
+            dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(reps):
+            dst.copy_(src_tensor, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return reps * nbytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
+
+    c_bytes = c_words * 4 + c_off.numpy().nbytes
+    c_value, c_sync, c_launches, bits_c = host_leg(lambda acc: ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc), c_bytes)
+    p_bytes = n * lo.stride_words * 4
+    p_value, p_sync, p_launches, bits_p = host_leg(lambda acc: ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc), p_bytes)
+    assert (bits_c == bits_p).all() and (np.unpackbits(bits_p.view(np.uint8), bitorder="little")[:n] == bits[:n]).all(), "host legs disagree with the device leg"
+    copy_alone = plain_copy_gbs(c_pinned[:c_words], c_words * 4, False)
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_c)
-    c_sync_s = time.perf_counter() - t0
-    c_launches = (ver.launch_count - cl0) // e2e_steps
-    ver.set_host_async(True)
-    for k in range(3):
-        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_rows_np[k])
-    ver.synchronize()
-    acc_rows_np[:] = 0xA5A5A5A5
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc_rows_np[k])
-    ver.synchronize()
-    c_s = time.perf_counter() - t0
-    ver.set_host_async(False)
-    assert (acc_rows_np == acc_host[None, :]).all(), "asynchronous compact results differ from the synchronous packed call"
-    t = torch.tensor([c_s, c_sync_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    c_value = total_n * e2e_steps / float(t[0].item())
-    c_sync_value = total_n * e2e_steps / float(t[1].item())
+    copy_conc = plain_copy_gbs(c_pinned[:c_words], c_words * 4, True)
+    conc_ranks = gather_ranks(torch, dist, world, [copy_alone, copy_conc])
 
     # end to end from the reference's own input format: `.wit` JSON TEXT in pinned host memory -> accept bits
     # (ssym_stwo_verify_wit_batch: text H2D, GPU tokeniser + packer, verifier, D2H bitmap; 122 KB of text per proof)
     wit_raw = open(os.path.join(ROOT, "tests", "golden", "stwo_proof_prod.wit"), "rb").read()
-    n_wit = 8 * n  # 8 192 witnesses = 1 GB of text per step: the synchronous call's exposed first copy / last kernels stay below 10 %
+    n_wit = 8 * n  # 8 192 witnesses = 1 GB of text per call: the synchronous call's exposed first copy / last kernels stay below 10 %
     wit_pinned = torch.empty(len(wit_raw) * n_wit, dtype=torch.uint8).pin_memory()
     wit_np = wit_pinned.numpy()
     wit_np.reshape(n_wit, len(wit_raw))[:] = np.frombuffer(wit_raw, dtype=np.uint8)
     wit_offsets = (np.arange(n_wit + 1, dtype=np.uint64) * np.uint64(len(wit_raw)))
     acc_wit = torch.empty((n_wit + 31) // 32, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    wit_steps = max(2, min(args.steps, 5))
+    wit_calls = 8
     ver.stwo_verify_wit_batch(wit_np, wit_offsets, cfg, accept_out=acc_wit)
     wl0 = ver.launch_count
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(wit_steps):
+    for _ in range(wit_calls):
         ver.stwo_verify_wit_batch(wit_np, wit_offsets, cfg, accept_out=acc_wit)
-    wit_s = time.perf_counter() - t0
+    wit_s = max_over_ranks(torch, dist, world, [time.perf_counter() - t0])[0]
     wit_launches = ver.launch_count - wl0
     assert (np.unpackbits(acc_wit.view(np.uint8), bitorder="little")[:n_wit] == bits[0]).all(), "text path disagrees with the packed path"
-    t = torch.tensor([wit_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wit_value = n_wit * world * wit_steps / float(t[0].item())
+    wit_value = n_wit * world * wit_calls / wit_s
+    del wit_pinned, wit_np
+
+    # ---- bounded runs of BASELINE configs 1, 3, 4 (single GPU only) and 5 (every N) -------------------------------------------------
+    sub = {}
+    if not args.no_configs:
+        import bench_sub
+
+        ver.set_stream(stream.cuda_stream)
+        ver.set_pipeline_depth(1)
+        sub = bench_sub.run_all(S, ver, stream, rank, world, int32_lanes, single_gpu_configs=(world == 1))
+        ver.set_pipeline_depth(depth)
 
     if rank == 0:
         peaks = {}
@@ -536,72 +647,84 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json (driver-measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        mk_ms, mk_n = prof.get("stwo_merkle", (0.0, 0))
+        mk_name = "stwo_merkle"
+        mk_ms, mk_n = prof.get(mk_name, (0.0, 0))
         mk_avg_ms = mk_ms / max(mk_n, 1)
         kernel_ms = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
         share = mk_ms / max(sum(v[0] for v in prof.values()), 1e-9)
         hbm_achieved = n * ALG_BYTES_PER_PROOF / (mk_avg_ms * 1e-3) / 1e9 if mk_avg_ms else 0.0
         lit_ops = n * MERKLE_COMPRESSIONS_PER_PROOF * LITERAL_OPS_PER_COMPRESSION / (mk_avg_ms * 1e-3) if mk_avg_ms else 0.0
-        line = {
-            "metric": "stwo_proofs_verified_per_s", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "reference fixture stwo-verifier/tests/data/proof.json (via generate_wit.py) replicated (BASELINE configs[1]); distinct GPU-proven proofs: bench_configs.py",
-            "config": {"workload": f"stwo-verifier proof.json witness (prod preset: LDE 2^13, 16 queries, 1+8 FRI layers) replicated x{n} per GPU",
-                       "mode": args.mode, "batch_per_gpu": n, "accepted": accepted,
-                       "l2": f"rotating {copies} distinct device copies of the batch ({copies * n * lo.stride_words * 4 / 1e6:.0f} MB > 126 MB L2)",
-                       "pipeline": f"{depth} batches in flight per GPU (ssym_set_pipeline_depth); per-kernel times below are per launch, kernels of consecutive steps overlap" if depth > 1 else "serial steps",
-                       "parallelism": f"proof-sharded x{world} (one process per GPU, no data-path collective), one NCCL all_gather of the accept bitmaps of all steps inside the timed region" if world > 1 else "single GPU",
-                       "numa": (f"every rank pinned to the CPUs of its GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else "no NUMA binding")},
-            "other_mode": {"mode": "prover-consistent" if args.mode == "ref-literal" else "ref-literal", "value": other_value, "unit": "proofs/s",
-                           "steps": other_steps, "accepted_per_gpu": other_accepted,
+        warp_peak = int32_lanes / 32.0  # ALU-pipe warp instructions per second, measured (ssym_int32_peak_probe)
+        counts = load_pipe_counts(args.mode)
+        roof = {"bound": "int32_alu", "kernel": "stwo_merkle_kernel", "unit": "G warp-instructions/s (ALU pipe)", "peak": warp_peak / 1e9,
+                "peak_source": f"ssym_int32_peak_probe, measured in this run: {int32_lanes / 1e12:.2f} T SHF/LOP3/IADD3 lanes/s = 148 SMs x 64 lanes x clock ({probe_ms:.2f} ms probe)",
+                "avg_launch_ms": mk_avg_ms, "kernel_share_of_step": share}
+        if counts and "stwo_merkle_kernel" in counts["kernels"] and mk_avg_ms:
+            scale = n / counts["proofs_per_launch"]
+            k3 = counts["kernels"]["stwo_merkle_kernel"]
+            alu = k3["alu_pipe_warp_inst"] * scale
+            step_alu = sum(k.get("alu_pipe_warp_inst", 0.0) for k in counts["kernels"].values()) * scale
+            roof.update({
+                "achieved": alu / (mk_avg_ms * 1e-3) / 1e9, "frac": alu / (mk_avg_ms * 1e-3) / warp_peak,
+                "alu_pipe_warp_inst_per_launch": alu, "warp_inst_per_launch": k3.get("warp_inst", 0.0) * scale,
+                "fmaheavy_pipe_warp_inst_per_launch": k3.get("fmaheavy_pipe_warp_inst", 0.0) * scale,
+                "whole_step_frac": step_alu / (pass_ms * 1e-3) / warp_peak,
+                "whole_step_note": "ALU-pipe warp instructions of ALL kernels of one pass / the headline's ms_per_pass (pipelined) / the same peak",
+                "serial_step_frac": step_alu / (serial_ms[args.mode] * 1e-3) / warp_peak,
+                "traffic": k3.get("dram_read_bytes", 0.0) * scale + k3.get("dram_write_bytes", 0.0) * scale,
+                "counts_source": f"profiles/step_pipe_counts.json <- {counts['source']} (ncu, per launch at {counts['proofs_per_launch']} proofs; instruction counts are clock- and profiler-independent)",
+                "counts_match_build": counts["matches_build"],
+            })
+        else:
+            roof.update({"achieved": None, "frac": None, "traffic": None, "counts_source": "profiles/step_pipe_counts.json missing"})
+        roof["hbm"] = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak if hbm_peak else None,
+                       "algorithmic_bytes_per_launch": n * ALG_BYTES_PER_PROOF, "peak_source": peak_src,
+                       "note": "not the binding resource: 170 integer ops per byte"}
+        roof["literal_ops"] = {"achieved": lit_ops / 1e12, "peak": int32_lanes / 1e12, "unit": "Tops/s", "frac": lit_ops / int32_lanes if int32_lanes else None,
+                               "convention": "SURVEY 8d: FIPS-180-4-literal 2296 ops x compressions / kernel time over measured instruction lanes/s; LOP3/IADD3 fusion and "
+                                             "adds issued on the FMA pipe make > 1.0 possible — `frac` above is the instruction-level figure"}
+        line.update({
+            "other_mode": {"mode": other_name, "value": other_value, "unit": "proofs/s", "steps": other_steps, "accepted_per_gpu": other_accepted,
+                           "kernel_ms": {k: v[0] / max(v[1], 1) for k, v in prof_by_mode[other_name].items()}, "serial_ms_per_pass": serial_ms[other_name],
                            "note": "same pipelined loop, same batch, the other semantics switch; under prover-consistent the fixture is ACCEPTED and the Merkle paths "
                                    "of a tree share the nodes above the height where they meet (hashed once, results per query identical: DESIGN.md section 4), "
                                    "so fewer compressions are executed than the reference's per-query count"},
-            "merkle_hashes_per_s": value * MERKLE_COMPRESSIONS_PER_PROOF / 2.0,
-            "sha256_compressions_per_s": value * COMPRESSIONS_PER_PROOF,
-            "e2e": {"value": c_value, "unit": "proofs/s", "h2d_bytes_per_step": int(c_words * 4 + c_off.numpy().nbytes), "d2h_bytes_per_step": int(acc_c.nbytes),
-                    "steps": e2e_steps, "h2d_gbs_achieved": c_value / world * (c_words * 4 + c_off.numpy().nbytes) / n / 1e9, "h2d_gbs_plain_copy": h2d_gbs,
-                    "sync_call_value": c_sync_value, "bytes_per_proof": c_words * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
-                    "gpu_launches_per_step": int(c_launches),
+            "e2e": {"value": c_value, "unit": "proofs/s", "h2d_bytes_per_step": int(c_bytes * Re), "d2h_bytes_per_step": int(acc_host.nbytes * Re),
+                    "steps": e2e_steps, "passes_per_step": Re, "h2d_gbs_achieved": c_value / world * c_bytes / n / 1e9,
+                    "h2d_gbs_plain_copy": copy_alone, "h2d_gbs_plain_copy_concurrent": min(r[1] for r in conc_ranks),
+                    "h2d_gbs_plain_copy_concurrent_per_rank": [r[1] for r in conc_ranks], "h2d_gbs_plain_copy_concurrent_aggregate": sum(r[1] for r in conc_ranks),
+                    "frac_of_concurrent_copy": (c_value / world * c_bytes / n / 1e9) / max(min(r[1] for r in conc_ranks), 1e-9),
+                    "sync_call_value": c_sync, "bytes_per_proof": c_words * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
+                    "gpu_launches_per_pass": c_launches,
+                    "host_pack": {"proofs_per_s_per_core": n / pack_s, "seconds_per_1024": pack_s, "inside_timed_region": False,
+                                  "note": "ssym_stwo_compact_pack (one host thread) turns packed records into the compact form BEFORE the clock starts; a producer that "
+                                          "emits compact records directly pays nothing, one that holds packed records pays this per core"},
+                    "e2e_packed_value": p_value,
                     "note": "ssym_stwo_verify_compact_batch(SSYM_MEM_HOST) on pinned host buffers holding the batch in the compact transport form "
-                            "(include/ssym.h: per Merkle tree every distinct 32-byte sibling once + one bit per path slot + one back reference per repeated slot; produced by the host packer "
-                            "ssym_stwo_compact_pack, lossless for any record, expanded on the GPU by stwo_expand_kernel): chunked double-buffered H2D -> "
-                            "expand -> verifier kernels -> D2H bitmap, every step's copies inside the timed region.  `value`: calls enqueued back to back "
-                            "(ssym_set_host_async), one synchronize; `sync_call_value`: each call returns with its bitmap in host memory.  Bound by the "
-                            "host link; `e2e_packed` is the same measurement on the fixed-stride packed records (36 % more bytes)"},
-            "e2e_packed": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n * lo.stride_words * 4), "d2h_bytes_per_step": int(acc_host.nbytes),
-                    "steps": e2e_steps, "h2d_gbs_achieved": e2e_value / world * lo.stride_words * 4 / 1e9, "h2d_gbs_plain_copy": h2d_gbs,
-                    "sync_call_value": e2e_sync_value,
-                    "note": "ssym_stwo_verify_batch(SSYM_MEM_HOST) on pinned host buffers: chunked double-buffered H2D -> kernels -> D2H bitmap, every step's "
-                            "copies inside the timed region.  `value`: the calls are enqueued back to back (ssym_set_host_async) and synchronised once, so the "
-                            "H2D of step k+1 runs under the kernel tail of step k; `sync_call_value`: each call returns with its bitmap in host memory before "
-                            "the next starts.  Bound by the host link: compare h2d_gbs_achieved with a plain pinned copy of the same bytes"},
-            "e2e_wit": {"value": wit_value, "unit": "proofs/s", "h2d_bytes_per_step": int(wit_np.nbytes), "d2h_bytes_per_step": int(acc_wit.nbytes),
-                        "steps": wit_steps, "proofs_per_step": n_wit, "h2d_gbs_achieved": wit_value / world * len(wit_raw) / 1e9, "gpu_launches": int(wit_launches),
+                            "(include/ssym.h: per Merkle tree every distinct 32-byte sibling once + one bit per path slot + one back reference per repeated slot; lossless "
+                            "for any record, expanded on the GPU by stwo_expand_kernel): chunked multi-buffered H2D -> expand -> verifier kernels -> D2H bitmap, every "
+                            "pass's copies inside the timed region.  PACKING IS OUTSIDE THE CLOCK (host_pack).  `value`: calls enqueued back to back "
+                            "(ssym_set_host_async), one synchronize per step; `sync_call_value`: each call returns with its bitmap in host memory.  Bound by the host link; "
+                            "`e2e_packed` is the same measurement on the reference-shaped fixed-stride packed records (no host packing at all)"},
+            "e2e_packed": {"value": p_value, "unit": "proofs/s", "h2d_bytes_per_step": int(p_bytes * Re), "d2h_bytes_per_step": int(acc_host.nbytes * Re),
+                           "steps": e2e_steps, "passes_per_step": Re, "h2d_gbs_achieved": p_value / world * lo.stride_words * 4 / 1e9, "h2d_gbs_plain_copy": copy_alone,
+                           "sync_call_value": p_sync, "gpu_launches_per_pass": p_launches,
+                           "note": "ssym_stwo_verify_batch(SSYM_MEM_HOST) on pinned host buffers holding fixed-stride packed records (the witness's values one to one): chunked "
+                                   "multi-buffered H2D -> kernels -> D2H bitmap inside the timed region"},
+            "e2e_wit": {"value": wit_value, "unit": "proofs/s", "h2d_bytes_per_step": int(len(wit_raw) * n_wit), "d2h_bytes_per_step": int(acc_wit.nbytes),
+                        "steps": wit_calls, "proofs_per_step": n_wit, "h2d_gbs_achieved": wit_value / world * len(wit_raw) / 1e9, "gpu_launches": int(wit_launches),
                         "note": "ssym_stwo_verify_wit_batch(SSYM_MEM_HOST): the reference's own input, `.wit` JSON text (122 KB per proof, the file `simfony run "
                                 "--witness` reads) in pinned host memory -> GPU tokeniser/packer -> verifier -> bitmap; synchronous calls, text H2D of chunk k+1 under "
                                 "the kernels of chunk k"},
-            "gpu_launches": int(launches),
-            "kernel_ms": kernel_ms, "serial_ms_per_step": serial_ms_per_step,
-            "kernel_ms_note": "per-launch CUDA-event durations from a strictly serial pass (pipeline depth 1) of the same steps; the headline "
-                              "`value` keeps `pipeline` batches in flight so kernels of consecutive steps overlap",
-            "roofline": {"bound": "hbm", "kernel": "stwo_merkle_kernel", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": hbm_achieved / hbm_peak if hbm_peak else None,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == 1024 else None, "traffic_source": "profiles/r01_ncu_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture, 1024 proofs per launch)",
-                         "algorithmic_bytes_per_launch": n * ALG_BYTES_PER_PROOF, "peak_source": peak_src,
-                         "kernel_share_of_step": share, "avg_launch_ms": mk_avg_ms,
-                         "note": "the kernel is INT32-ALU bound (170 int-ops per byte), not HBM bound: see roofline_int32"},
-            "roofline_int32": {"bound": "int32_alu", "kernel": "stwo_merkle_kernel", "achieved": lit_ops / 1e12, "peak": int32_ops / 1e12, "unit": "Tops/s",
-                               "frac": lit_ops / int32_ops if int32_ops else None,
-                               "alu_pipe_busy_ncu": 0.827, "fma_heavy_pipe_busy_ncu": 0.447, "issue_slots_busy_ncu": 0.70,
-                               "ncu_source": "profiles/r01e_ncu_summary.md (one ncu --set full capture of this kernel at 1024 proofs; 0.849 / 0.518 / 0.718 at 16 384 proofs, profiles/r01_ncu_summary.md)",
-                               "convention": "achieved = FIPS-180-4-literal 2296 ops x compressions / kernel time (SURVEY 8d); peak = measured SHF/LOP3/IADD3 "
-                                             "machine-instruction lanes/s (ssym_int32_peak_probe); LOP3/IADD3 fusion makes >1.0 possible",
-                               "probe_ms": probe_ms},
-            "clocks": clocks.summary(),
-        }
+            "kernel_ms": kernel_ms, "serial_ms_per_pass": serial_ms[args.mode],
+            "kernel_ms_note": "per-launch CUDA-event durations from a strictly serial run (pipeline depth 1) of 200 passes; the headline "
+                              "`value` keeps `pipeline` batches in flight so kernels of consecutive passes overlap",
+            "roofline": roof,
+            "configs": sub,
+        })
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, host_batch, n)
+            line["cpu_baseline_fast"] = cpu_baseline(cfg, host_batch, n, budget_s=2.0, fast=True)
         emit(line)
     ver.close()
     if world > 1:

@@ -1,0 +1,283 @@
+#!/usr/bin/env python3
+"""Bounded runs of BASELINE.json configs 1, 3, 4 and 5, attached by bench.py to its JSON line as `configs.{c1_stark101, c3_distinct_negatives,
+c4_micro, c5_sharded}` (the driver's record should carry them, not only builder-run files).  Sizes are reduced so that all four
+finish in well under a minute; `bench_micro.py` / `bench_configs.py` run the full sizes (2^16 / 2^20 proofs, 2^28 elements).
+
+Every sub-record: inputs resident in HBM and larger than L2 (or stated otherwise), CUDA events on the launching stream, >= 3 warm-up launches,
+best of 5; a parity check against the oracle (test infrastructure) outside the timed region; the fraction of the resource that binds it.
+
+  python bench_sub.py            # the four sub-records on one GPU, as JSON
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+P = 2147483647
+# ALU-pipe lane-instructions per SHA-256 compression of the shared rolled / IMAD hashing loop (ncu: 103 994 368 ALU-pipe warp instructions for
+# 1024 x 3760 compressions, profiles/step_pipe_counts.json): used where a kernel built on that loop has no ncu count of its own (marked "estimate")
+ALU_LANES_PER_COMPRESSION = 103994368 * 32 / (1024 * 3760)
+
+
+def timed(torch, fn, stream, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def c1_stark101(S, ver, stream, torch, orc, int32_lanes, log_n=15):
+    """BASELINE config 1: the stark101 Fibonacci-square proof (the reference's `make proof` fixture) replicated x2^log_n + negatives, device resident."""
+    golden = os.path.join(ROOT, "tests", "golden")
+    blob, _, bad = S.witness.pack_stark101_wits([open(os.path.join(golden, "stark101_proof.wit")).read()])
+    assert not bad[0]
+    n = 1 << log_n
+    all_blob = np.tile(blob, n)
+    bad_rows = list(range(7, n, 97))
+    for r in bad_rows:
+        all_blob[r * len(blob) + 5] += 1  # wrong last layer
+    offsets = np.arange(n + 1, dtype=np.uint64) * len(blob)
+    d_blob = torch.from_numpy(all_blob.view(np.int32)).cuda()
+    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    ms = timed(torch, lambda: ver.stark101_verify_batch(d_blob, d_off), stream)
+    accept, status, _ = ver.stark101_verify_batch(d_blob, d_off, want_status=True)
+    ver.synchronize()
+    bits = np.unpackbits(accept.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    expect = np.ones(n, dtype=bool)
+    expect[bad_rows] = False
+    assert (bits == expect).all()
+    m = 128
+    _, o_status, _ = orc.s101_verify_batch(all_blob[: m * len(blob)], offsets[: m + 1])
+    assert (status[:m].cpu().numpy().view(np.uint32) == o_status).all()
+    comp = n * 480 / (ms * 1e-3)
+    return {"workload": f"BASELINE config 1: stark101 proof (p = 3*2^30+1, 1023-step trace, blowup 8) replicated x{n} + {len(bad_rows)} corrupted, device resident",
+            "proofs": n, "ms": ms, "value": n / (ms * 1e-3), "unit": "proofs/s", "compressions_per_s": comp, "packed_bytes_per_proof": int(len(blob) * 4),
+            "input_mb": all_blob.nbytes / 1e6, "gb_per_s": all_blob.nbytes / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "int32_alu", "frac": comp * ALU_LANES_PER_COMPRESSION / int32_lanes, "basis": "estimate: 480 compressions/proof x ALU-pipe lane-instructions "
+                         "per compression of the shared hashing loop (ncu count of stwo_merkle_kernel) / measured ALU lanes/s; the transcript's field divisions are not counted"},
+            "parity": f"accept bits as constructed ({len(bad_rows)} rejected); first {m} status words bit-identical to the oracle"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def c3_distinct_negatives(S, ver, stream, torch, orc, int32_lanes, log_n=14):
+    """BASELINE config 3: 2^log_n DISTINCT synthetic Stwo proofs (GPU prover, one per seed) + corrupted negatives (6 classes x 1/8), both semantics."""
+    import bench_configs as BC
+
+    n = 1 << log_n
+    cfg_pc = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    cfg_lit = S.stwo_config("prod", S.MODE_REF_LITERAL)
+    lo = S.stwo_layout(cfg_pc)
+    seeds = torch.arange(0, n, dtype=torch.int64, device="cuda")
+    proofs = torch.empty((n, lo.stride_words), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ver.stwo_prove_batch(seeds, cfg_pc, out=proofs)
+    torch.cuda.synchronize()
+    prove_s = time.perf_counter() - t0
+    expect_bad = BC.apply_negatives(torch, proofs, BC.negatives_plan(S, cfg_pc), 0)
+    accept = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    out = {}
+    from oracle import oracle as O
+
+    m = 64
+    sample = proofs[:m].cpu().numpy().view(np.uint32)
+    for name, cfg, omode in (("prover-consistent", cfg_pc, O.MODE_PROVER_CONSISTENT), ("ref-literal", cfg_lit, O.MODE_REF_LITERAL)):
+        ms = timed(torch, lambda: ver.stwo_verify_batch(proofs.view(-1), cfg, n, accept_out=accept, status_out=status), stream)
+        st = status.cpu().numpy().view(np.uint32)
+        if name == "prover-consistent":
+            assert ((st != 0) == expect_bad).all(), "wrong verdicts"
+        else:
+            assert (st != 0).all()
+        _, o_status, _ = orc.stwo_verify_batch(O.make_config("prod", omode), sample.ravel(), m)
+        assert (o_status == st[:m]).all(), f"{name}: GPU statuses differ from the oracle"
+        out[name] = {"ms": ms, "proofs_per_s": n / (ms * 1e-3)}
+    v = out["ref-literal"]["proofs_per_s"]
+    return {"workload": f"BASELINE config 3: 2^{log_n} distinct synthetic Stwo proofs of the wide-Fibonacci AIR (GPU prover, seed = index) + corrupted negatives "
+                        f"(6 classes x 1/8 of the batch), 1 B200, one call per pass ({n * lo.stride_words * 4 / 1e6:.0f} MB > L2)",
+            "proofs": n, "negatives": int(expect_bad.sum()), "value": out["prover-consistent"]["proofs_per_s"], "unit": "proofs/s", "mode": "prover-consistent",
+            "ref_literal_value": v, "ms": out["prover-consistent"]["ms"], "ref_literal_ms": out["ref-literal"]["ms"],
+            "prover_proofs_per_s": n / prove_s,
+            "roofline": {"bound": "int32_alu", "frac": v * 3760 * ALU_LANES_PER_COMPRESSION / int32_lanes, "mode": "ref-literal (per-query Merkle kernel: the executed "
+                         "compressions are the reference's 3 760 per proof)", "basis": "ALU-pipe lane-instructions per compression (ncu) x compressions/s / measured ALU lanes/s; whole call, "
+                         "transcript and field kernels included in the time but not in the numerator"},
+            "parity": f"verdicts: exactly the {int(expect_bad.sum())} corrupted proofs rejected (prover-consistent), all rejected (ref-literal); first {m} status words of both modes bit-identical to the oracle"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def c4_micro(S, ver, stream, torch, orc, int32_lanes, log_elems=26, log_paths=18):
+    """BASELINE config 4: field / fold jets over 2^log_elems random canonical elements (HBM roofline) + Merkle-path sweep (INT32 roofline)."""
+    from oracle import oracle as O
+
+    peak, peak_src = hbm_peak()
+    g = torch.Generator(device="cuda").manual_seed(0)  # Philox, seed 0
+    N = 1 << log_elems
+
+    def rnd(words):
+        return torch.randint(0, P, (N * words,), dtype=torch.int32, device="cuda", generator=g)
+
+    a1, b1, a4, b4 = rnd(1), rnd(1), rnd(4), rnd(4)
+    pos = torch.randint(0, 1 << 20, (N,), dtype=torch.int32, device="cuda", generator=g) & ~1
+    field = []
+    for name, fn, bytes_per in (
+        ("m31_mul", lambda: ver.m31_mul(a1, b1), 12), ("m31_inv", lambda: ver.m31_inv(a1), 9), ("qm31_mul", lambda: ver.qm31_mul(a4, b4), 48),
+        ("qm31_inv", lambda: ver.qm31_inv(a4), 33), ("circle_fold", lambda: ver.circle_fold(pos, a4, b4, a4, 20), 69), ("line_fold", lambda: ver.line_fold(pos, a4, b4, a4, 20), 69),
+    ):
+        ms = timed(torch, fn, stream)
+        gbs = N * bytes_per / (ms * 1e-3) / 1e9
+        field.append({"op": name, "ms": ms, "elements_per_s": N / (ms * 1e-3), "bytes_per_element": bytes_per, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak})
+    out = ver.qm31_mul(a4, b4).cpu().numpy().view(np.uint32)
+    ha, hb = a4[:64].cpu().numpy().view(np.uint32), b4[:64].cpu().numpy().view(np.uint32)
+    for i in range(16):
+        assert list(out[4 * i:4 * i + 4]) == list(orc.qm31_mul(ha[4 * i:4 * i + 4], hb[4 * i:4 * i + 4]))
+    inv, _ = ver.m31_inv(a1)
+    h1, hi = a1[:16].cpu().numpy().view(np.uint32), inv[:16].cpu().numpy().view(np.uint32)
+    assert all(int(h1[i]) * int(hi[i]) % P == 1 for i in range(16) if h1[i])
+    o2, _ = ver.circle_fold(pos, a4, b4, a4, 20)
+    o2 = o2.cpu().numpy().view(np.uint32)
+    hp = pos[:8].cpu().numpy().view(np.uint32)
+    for i in range(8):
+        w, _ = orc.circle_fold(int(hp[i]), ha[4 * i:4 * i + 4], hb[4 * i:4 * i + 4], 20, ha[4 * i:4 * i + 4])
+        assert list(o2[4 * i:4 * i + 4]) == list(w)
+    del a1, b1, a4, b4, pos, out, o2, inv
+    torch.cuda.empty_cache()
+    M = 1 << log_paths
+    leaf = torch.randint(-2**31, 2**31 - 1, (M * 8,), dtype=torch.int32, device="cuda", generator=g)
+    sweep = []
+    for depth in (16, 28):
+        sib = torch.randint(-2**31, 2**31 - 1, (M * depth * 8,), dtype=torch.int32, device="cuda", generator=g)
+        auth = (torch.randint(0, 1 << depth, (M,), dtype=torch.int64, device="cuda", generator=g) + (1 << depth)).to(torch.int32)
+        roots, _, _ = ver.merkle_root_from_path(leaf, auth, sib, depth)  # tree-free construction: the computed roots become the expected ones
+        ms = timed(torch, lambda: ver.merkle_root_from_path(leaf, auth, sib, depth, expected_root=roots), stream)
+        _, _, ok = ver.merkle_root_from_path(leaf, auth, sib, depth, expected_root=roots)
+        assert int((ok.cpu().numpy().view(np.uint32) != 0xFFFFFFFF).sum()) == 0
+        hl, hs, ha_ = leaf[:8].cpu().numpy().view(np.uint32), sib[: depth * 8].cpu().numpy().view(np.uint32), int(auth[0].item()) & 0xFFFFFFFF
+        _, croot, fpath = orc.merkle_verify_32(O.words_u256(hl), ha_, [O.words_u256(hs[8 * k:8 * k + 8]) for k in range(depth)], 0)
+        assert fpath == 1 and list(O.u256_words(croot)) == list(roots[:8].cpu().numpy().view(np.uint32))
+        comp = 2 * M * depth / (ms * 1e-3)
+        sweep.append({"depth": depth, "paths": M, "ms": ms, "pair_hashes_per_s": comp / 2, "compressions_per_s": comp,
+                      "gb_per_s": M * (32 * depth + 68) / (ms * 1e-3) / 1e9, "alu_pipe_frac": comp * ALU_LANES_PER_COMPRESSION / int32_lanes})
+        del sib, auth, roots
+        torch.cuda.empty_cache()
+    best = max(f["frac_of_hbm_peak"] for f in field)
+    return {"workload": f"BASELINE config 4 (bounded): M31/QM31 mul/inv and circle/line fold over 2^{log_elems} elements; Merkle-path sweep, 2^{log_paths} paths, depth 16 and 28",
+            "field": field, "merkle_sweep": sweep, "hbm_peak_gbs": peak, "hbm_peak_source": peak_src,
+            "value": max(s["pair_hashes_per_s"] for s in sweep), "unit": "Merkle pair hashes/s",
+            "roofline": {"bound": "hbm (field jets) / int32_alu (Merkle sweep)", "frac_hbm_best": best, "frac_int32_alu": max(s["alu_pipe_frac"] for s in sweep)},
+            "parity": "qm31_mul, m31_inv, circle_fold spot-checked against the oracle; every swept path verifies; one path per depth re-derived by the oracle"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def c5_sharded(S, ver, stream, torch, orc, int32_lanes, rank, world, log_n=17):
+    """BASELINE config 5 (bounded): 2^log_n distinct proofs sharded by proof index over the N ranks, accept-bitmap all-gather inside the timed region."""
+    import torch.distributed as dist
+    from importlib import import_module
+
+    sharding = import_module("stark_symphony_b200.sharding")
+    n_total = 1 << log_n
+    begin, end = sharding.shard_range(n_total, rank, world)
+    n = end - begin
+    cfg_pc = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    lo = S.stwo_layout(cfg_pc)
+    seeds = torch.arange(begin, end, dtype=torch.int64, device="cuda")
+    proofs = torch.empty((n, lo.stride_words), dtype=torch.int32, device="cuda")
+    ver.stwo_prove_batch(seeds, cfg_pc, out=proofs)
+    # one corrupted proof per 1000 (global index), so that the gathered bitmap is not trivially all ones
+    idx = torch.arange(begin, end, device="cuda")
+    bad_rows = torch.nonzero(idx % 1000 == 999).view(-1)
+    word, delta = S.witness.stwo_negative_classes(cfg_pc)["fri_witness_plus_1"]
+    proofs[bad_rows, word] += delta
+    words = sharding.shard_words(n_total, world)
+    accept = torch.zeros(words, dtype=torch.int32, device="cuda")
+    status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    gathered = torch.zeros(words * world, dtype=torch.int32, device="cuda")
+
+    def one_pass():
+        ver.stwo_verify_batch(proofs.view(-1), cfg_pc, n, accept_out=accept, status_out=status)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, accept)  # the job's only exchange: 4 bytes per 32 proofs
+
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        one_pass()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = min(best, float(t.item()))
+    bits = (gathered if world > 1 else accept).cpu().numpy()
+    accepted = sharding.expected_accept_count(bits, words * 32 * world)
+    expected = n_total - len([i for i in range(n_total) if i % 1000 == 999])
+    assert accepted == expected, (accepted, expected)
+    if rank == 0:
+        from oracle import oracle as O
+
+        m = 32
+        _, o_status, _ = orc.stwo_verify_batch(O.make_config("prod", O.MODE_PROVER_CONSISTENT), proofs[:m].cpu().numpy().view(np.uint32).ravel(), m)
+        assert (o_status == status[:m].cpu().numpy().view(np.uint32)).all()
+    return {"workload": f"BASELINE config 5 (bounded): 2^{log_n} distinct synthetic Stwo proofs sharded by proof index over {world} B200, accept-bitmap all-gather",
+            "proofs_total": n_total, "proofs_per_gpu": n, "n_gpus": world, "scaling": "strong", "ms": best, "value": n_total / (best * 1e-3), "unit": "proofs/s",
+            "mode": "prover-consistent (shared-node Merkle schedule)", "accepted": accepted,
+            "parity": f"gathered bitmap: exactly the {n_total - expected} corrupted proofs rejected across all ranks; rank 0's first 32 status words bit-identical to the oracle"}
+
+
+def run_all(S, ver, stream, rank, world, int32_lanes, single_gpu_configs=True):
+    import torch
+
+    orc = None
+    if rank == 0 or single_gpu_configs:
+        from oracle import oracle as O
+
+        orc = O.Oracle()
+    out = {}
+    t0 = time.perf_counter()
+    if single_gpu_configs:
+        out["c1_stark101"] = c1_stark101(S, ver, stream, torch, orc, int32_lanes)
+        out["c3_distinct_negatives"] = c3_distinct_negatives(S, ver, stream, torch, orc, int32_lanes)
+        out["c4_micro"] = c4_micro(S, ver, stream, torch, orc, int32_lanes)
+    out["c5_sharded"] = c5_sharded(S, ver, stream, torch, orc, int32_lanes, rank, world)
+    out["seconds"] = time.perf_counter() - t0
+    return out
+
+
+if __name__ == "__main__":
+    import torch
+
+    import stark_symphony_b200 as S
+
+    ver = S.Verifier(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ver.set_stream(stream.cuda_stream)
+    lanes, _ = ver.int32_peak_probe()
+    print(json.dumps(run_all(S, ver, stream, 0, 1, lanes), indent=1))

@@ -207,8 +207,17 @@ int ssym_create(int device, ssym_ctx_t **out);
 void ssym_destroy(ssym_ctx_t *ctx);
 const char *ssym_last_error(void);
 const char *ssym_version(void);
-/* Use a caller-owned stream (e.g. torch's current stream) for all subsequent
- * device-resident calls on this handle; NULL restores the handle's own stream. */
+/* Stream ordering (read this before passing device buffers).  SSYM_MEM_DEVICE calls are ASYNCHRONOUS and run on the handle's stream,
+ * which by default is a stream of its own created with cudaStreamNonBlocking: work on it is NOT ordered after the caller's other
+ * streams, not even after the legacy default stream.  A caller that fills the input buffers with kernels or copies on its own stream
+ * (torch, thrust, ...) must therefore either
+ *   - hand that stream to the handle: ssym_set_stream(ctx, stream) — every later device-resident call is then enqueued on it (after
+ *     the producers already in it, before whatever the caller enqueues next); cudaStreamLegacy / cudaStreamPerThread name the default
+ *     streams; or
+ *   - synchronise the producers itself (cudaStreamSynchronize / an event the handle's stream cannot see is NOT enough) and call
+ *     ssym_synchronize(ctx) before reading the outputs.
+ * The Python binding does the first automatically for torch tensors (Verifier._space: torch's current stream).  NULL restores the
+ * handle's own stream.  SSYM_MEM_HOST calls are synchronous unless ssym_set_host_async is on. */
 int ssym_set_stream(ssym_ctx_t *ctx, void *cuda_stream);
 /* Page-locked host memory for SSYM_MEM_HOST buffers (packed proofs, witness text): copies from it run at the link rate and, in the
  * asynchronous host mode, truly overlap.  Plain malloc'ed buffers are accepted everywhere too, only slower.  Returns NULL on failure. */
@@ -256,7 +265,9 @@ int ssym_profile_read(ssym_ctx_t *ctx, double *ms_per_kernel, uint64_t *launches
  *  status      : NULL or n status words (SSYM_ST_*)
  *  trace       : NULL or n ssym_stwo_trace_t
  * All four pointers live in `memspace`.  Asynchronous on the handle's stream
- * for SSYM_MEM_DEVICE; synchronous for SSYM_MEM_HOST (copies included). */
+ * for SSYM_MEM_DEVICE — see "Stream ordering" at ssym_set_stream: the inputs must have been produced on (or ordered into) that stream,
+ * and with ssym_set_pipeline_depth > 1 the outputs are ordered into it only by ssym_join / ssym_synchronize; synchronous for
+ * SSYM_MEM_HOST (copies included). */
 int ssym_stwo_verify_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const uint32_t *packed,
                            size_t n, uint32_t *accept_bits, uint32_t *status,
                            ssym_stwo_trace_t *trace, int memspace);

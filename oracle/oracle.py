@@ -387,3 +387,8 @@ class Oracle:
 
     def compression_count(self) -> int: return int(self.lib.oracle_compression_count())
     def compression_reset(self) -> None: self.lib.oracle_compression_reset()
+
+    def set_fast(self, on: bool) -> int:
+        """CPU-baseline speed switch (process-wide): word-wise absorbs, block-wise padding, Mersenne folding and, where the host has them, SHA-NI
+        compressions instead of the literal byte-at-a-time port.  Same results bit for bit.  Returns 2 (SHA-NI in use), 1 (word-wise only) or 0 (off)."""
+        return int(self.lib.oracle_set_fast_sha(1 if on else 0))

@@ -86,7 +86,58 @@ static _Thread_local uint64_t g_compressions, g_m31_mul, g_m31_add, g_m31_inv;
 
 static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
+/* CPU-baseline speed switch (bench.py `cpu_baseline_fast`): 0 = the literal port (byte-at-a-time absorb, scalar compression — the default, and what
+ * every test pins); 1 = the same functions with 4-byte absorbs and, where the host CPU has them, the SHA-NI compression instructions.  Same digests
+ * (tests/test_oracle_fixtures.py::test_fast_sha_mode_is_bit_identical); only the time differs. */
+static int g_fast_sha;
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>
+static int cpu_has_sha_ni(void) {
+    unsigned a, b, c, d;
+    if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return 0;
+    return (b >> 29) & 1;
+}
+__attribute__((target("sha,sse4.1,ssse3"))) static void sha_compress_shani(uint32_t h[8], const uint8_t blk[64]) {
+    const __m128i bswap = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i t = _mm_loadu_si128((const __m128i *)&h[0]), s1 = _mm_loadu_si128((const __m128i *)&h[4]);
+    t = _mm_shuffle_epi32(t, 0xB1);             /* CDAB */
+    s1 = _mm_shuffle_epi32(s1, 0x1B);           /* EFGH */
+    __m128i s0 = _mm_alignr_epi8(t, s1, 8);     /* ABEF */
+    s1 = _mm_blend_epi16(s1, t, 0xF0);          /* CDGH */
+    const __m128i save0 = s0, save1 = s1;
+    __m128i m[4];
+    for (int i = 0; i < 4; i++) m[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(blk + 16 * i)), bswap);
+    for (int r = 0; r < 16; r++) {              /* 4 rounds per iteration */
+        __m128i w = m[r & 3];
+        __m128i k = _mm_add_epi32(w, _mm_loadu_si128((const __m128i *)&SHA_K[4 * r]));
+        s1 = _mm_sha256rnds2_epu32(s1, s0, k);
+        s0 = _mm_sha256rnds2_epu32(s0, s1, _mm_shuffle_epi32(k, 0x0E));
+        if (r < 12) {                           /* schedule W[4r+16 .. 4r+19] into the slot of W[4r .. 4r+3] */
+            __m128i x = _mm_sha256msg1_epu32(m[r & 3], m[(r + 1) & 3]);
+            x = _mm_add_epi32(x, _mm_alignr_epi8(m[(r + 3) & 3], m[(r + 2) & 3], 4));
+            m[r & 3] = _mm_sha256msg2_epu32(x, m[(r + 3) & 3]);
+        }
+    }
+    s0 = _mm_add_epi32(s0, save0);
+    s1 = _mm_add_epi32(s1, save1);
+    t = _mm_shuffle_epi32(s0, 0x1B);            /* FEBA */
+    s1 = _mm_shuffle_epi32(s1, 0xB1);           /* DCHG */
+    _mm_storeu_si128((__m128i *)&h[0], _mm_blend_epi16(t, s1, 0xF0)); /* DCBA */
+    _mm_storeu_si128((__m128i *)&h[4], _mm_alignr_epi8(s1, t, 8));    /* HGFE */
+}
+#else
+static int cpu_has_sha_ni(void) { return 0; }
+static void sha_compress_shani(uint32_t h[8], const uint8_t blk[64]) { (void)h; (void)blk; }
+#endif
+static int g_sha_ni = -1;
+
 static void sha_compress(uint32_t h[8], const uint8_t blk[64]) {
+    if (g_fast_sha && g_sha_ni > 0) {
+        sha_compress_shani(h, blk);
+        g_compressions++;
+        return;
+    }
     uint32_t w[64];
     for (int i = 0; i < 16; i++)
         w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
@@ -122,6 +173,13 @@ static void ctx_add_byte(Ctx8 *c, uint8_t b) {
     if (c->len % 64 == 0) sha_compress(c->h, c->buf);
 }
 static Ctx8 sha_256_ctx_8_add_4(Ctx8 c, uint32_t v) {
+    if (g_fast_sha && c.len % 4 == 0) { /* word-wise absorb: same bytes, one store */
+        const uint32_t be = __builtin_bswap32(v);
+        memcpy(c.buf + c.len % 64, &be, 4);
+        c.len += 4;
+        if (c.len % 64 == 0) sha_compress(c.h, c.buf);
+        return c;
+    }
     for (int i = 3; i >= 0; i--) ctx_add_byte(&c, (uint8_t)(v >> (8 * i)));
     return c;
 }
@@ -130,11 +188,35 @@ static Ctx8 sha_256_ctx_8_add_8(Ctx8 c, uint64_t v) {
     return c;
 }
 static Ctx8 sha_256_ctx_8_add_32(Ctx8 c, u256 v) {
+    if (g_fast_sha && c.len % 4 == 0 && c.len % 64 <= 32) { /* the 32 bytes fit the current block */
+        uint32_t be[8];
+        for (int i = 0; i < 8; i++) be[i] = __builtin_bswap32(v.w[i]);
+        memcpy(c.buf + c.len % 64, be, 32);
+        c.len += 32;
+        if (c.len % 64 == 0) sha_compress(c.h, c.buf);
+        return c;
+    }
     for (int i = 0; i < 8; i++) c = sha_256_ctx_8_add_4(c, v.w[i]);
     return c;
 }
 static u256 sha_256_ctx_8_finalize(Ctx8 c) {
     uint64_t bits = c.len * 8;
+    if (g_fast_sha) { /* FIPS 180-4 padding written block-wise */
+        size_t at = c.len % 64;
+        c.buf[at++] = 0x80;
+        if (at > 56) {
+            memset(c.buf + at, 0, 64 - at);
+            sha_compress(c.h, c.buf);
+            at = 0;
+        }
+        memset(c.buf + at, 0, 56 - at);
+        const uint64_t be = __builtin_bswap64(bits);
+        memcpy(c.buf + 56, &be, 8);
+        sha_compress(c.h, c.buf);
+        u256 r;
+        memcpy(r.w, c.h, sizeof r.w);
+        return r;
+    }
     ctx_add_byte(&c, 0x80);
     while (c.len % 64 != 56) ctx_add_byte(&c, 0);
     for (int i = 7; i >= 0; i--) ctx_add_byte(&c, (uint8_t)(bits >> (8 * i)));
@@ -152,12 +234,20 @@ static int eq_256(u256 a, u256 b) { return memcmp(a.w, b.w, sizeof a.w) == 0; }
 #define M31_MODULUS 2147483647u
 typedef uint32_t M31;
 
-static M31 m31(uint32_t v) { return jet_modulo_32(v, M31_MODULUS); }                 /* m31.simf:17-19 */
+/* exact x mod (2^31 - 1) for any 64-bit x by Mersenne folding: the fast-mode (oracle_set_fast_sha) replacement of the literal `%` */
+static inline uint32_t m31_fold64(uint64_t x) {
+    x = (x & M31_MODULUS) + (x >> 31); /* < 2^34 */
+    x = (x & M31_MODULUS) + (x >> 31); /* <= 2^31 + 6 */
+    x = (x & M31_MODULUS) + (x >> 31); /* <= 2^31 - 1 */
+    return x == M31_MODULUS ? 0 : (uint32_t)x;
+}
+static M31 m31(uint32_t v) { return g_fast_sha ? m31_fold64(v) : jet_modulo_32(v, M31_MODULUS); }                 /* m31.simf:17-19 */
 static M31 m31_add(M31 a, M31 b) { g_m31_add++; return m31(jet_add_32(a, b)); }     /* m31.simf:22-26 */
 static M31 m31_neg(M31 a) { return jet_subtract_32(M31_MODULUS, a); }               /* m31.simf:29-32 (unreduced) */
 static M31 m31_sub(M31 a, M31 b) { return m31_add(a, m31_neg(b)); }                 /* m31.simf:35-37 */
 static M31 m31_mul(M31 a, M31 b) {                                                  /* m31.simf:40-45 */
     g_m31_mul++;
+    if (g_fast_sha) return m31_fold64(jet_multiply_32(a, b));
     return (uint32_t)jet_modulo_64(jet_multiply_32(a, b), M31_MODULUS);
 }
 static M31 m31_exp(M31 a, M31 b) { /* m31.simf:57-80: square-and-multiply, <= 65536 steps */
@@ -862,6 +952,13 @@ EXPORT void oracle_stwo_verify_batch(const ssym_stwo_config_t *cfg, const uint32
     }
 }
 
+/* 0 = literal port (default); 1 = word-wise absorb + SHA-NI where available.  Returns 2 if SHA-NI is in use, 1 if only the word-wise absorb, 0 if off.
+ * Process-wide: set it before starting worker threads. */
+EXPORT int oracle_set_fast_sha(int on) {
+    if (g_sha_ni < 0) g_sha_ni = cpu_has_sha_ni();
+    g_fast_sha = on != 0;
+    return g_fast_sha ? (g_sha_ni > 0 ? 2 : 1) : 0;
+}
 EXPORT uint64_t oracle_compression_count(void) { return g_compressions; }
 EXPORT void oracle_compression_reset(void) { g_compressions = 0; }
 /* M31 operations of the calling thread since the last reset: out = {mul (those inside inversions included), add / sub, inversions} */

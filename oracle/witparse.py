@@ -49,46 +49,58 @@ def parse_value(text: str) -> Any:
     return val
 
 
-def _parse_seq(toks: List[str], pos: int, close: str) -> Tuple[List[Any], int]:
+class _Trailing(list):
+    """Items of a sequence that ended in a trailing comma (`(x,)` is a 1-tuple, `(x)` a parenthesised value)."""
+
+
+def _parse_seq(toks: List[str], pos: int, close: str, depth: int = 0) -> Tuple[List[Any], int]:
     items: List[Any] = []
     if pos < len(toks) and toks[pos] == close:
         return items, pos + 1
     while True:
-        v, pos = _parse(toks, pos)
+        v, pos = _parse(toks, pos, depth)
         items.append(v)
         if pos >= len(toks):
             raise WitnessTypeError("unterminated sequence")
         if toks[pos] == ",":
             pos += 1
             if pos < len(toks) and toks[pos] == close:  # trailing comma
-                return items, pos + 1
+                return _Trailing(items), pos + 1
             continue
         if toks[pos] == close:
             return items, pos + 1
         raise WitnessTypeError(f"expected , or {close}, got {toks[pos]}")
 
 
-def _parse(toks: List[str], pos: int) -> Tuple[Any, int]:
+MAX_NESTING = 64  # same bound as csrc/witness.cpp
+
+
+def _parse(toks: List[str], pos: int, depth: int = 0) -> Tuple[Any, int]:
     if pos >= len(toks):
         raise WitnessTypeError("unexpected end")
+    depth += 1
+    if depth > MAX_NESTING:
+        raise WitnessTypeError("nesting too deep")
     t = toks[pos]
     if t == "(":
-        items, pos = _parse_seq(toks, pos + 1, ")")
-        if len(items) == 1:  # parenthesised value
-            return items[0], pos
+        items, pos = _parse_seq(toks, pos + 1, ")", depth)
+        if len(items) == 1:
+            if isinstance(items, _Trailing):  # `(x,)`: a 1-tuple, a value of none of the witness types
+                raise WitnessTypeError("1-tuple")
+            return items[0], pos  # parenthesised value
         return tuple(items), pos
     if t == "[":
-        items, pos = _parse_seq(toks, pos + 1, "]")
+        items, pos = _parse_seq(toks, pos + 1, "]", depth)
         return list(items), pos
     if t == "list!":
         if pos + 1 >= len(toks) or toks[pos + 1] != "[":
             raise WitnessTypeError("list! must be followed by [")
-        items, pos = _parse_seq(toks, pos + 2, "]")
+        items, pos = _parse_seq(toks, pos + 2, "]", depth)
         return ListValue(items), pos
     if t == "qm31":  # constructor used in .simf literals (fields/qm31.simf:20-22)
         if toks[pos + 1] != "(":
             raise WitnessTypeError("qm31 needs (")
-        items, pos = _parse_seq(toks, pos + 2, ")")
+        items, pos = _parse_seq(toks, pos + 2, ")", depth)
         if len(items) != 4:
             raise WitnessTypeError("qm31 takes 4 values")
         return ((items[0], items[1]), (items[2], items[3])), pos
@@ -97,14 +109,24 @@ def _parse(toks: List[str], pos: int) -> Tuple[Any, int]:
     raise WitnessTypeError(f"unexpected token {t}")
 
 
+def _no_duplicates(pairs):
+    keys = [k for k, _ in pairs]
+    if len(set(keys)) != len(keys):
+        raise WitnessTypeError("duplicate member")
+    return dict(pairs)
+
+
 def load_wit(text: str) -> Dict[str, Any]:
-    obj = json.loads(text)
+    """NAME -> {"value": str, "type": str}, both members required, no repeated names or members (serde's WitnessValues, simfony-cli/src/main.rs:77-81)."""
+    obj = json.loads(text, object_pairs_hook=_no_duplicates)
     if not isinstance(obj, dict):
         raise WitnessTypeError("witness file must be a JSON object")
     out = {}
     for name, entry in obj.items():
-        if not isinstance(entry, dict) or "value" not in entry:
+        if not isinstance(entry, dict) or not isinstance(entry.get("value"), str):
             raise WitnessTypeError(f"witness {name} has no value")
+        if not isinstance(entry.get("type"), str):
+            raise WitnessTypeError(f"witness {name} has no type")
         out[name] = parse_value(entry["value"])
     return out
 

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSYM_LIB") or os.path.join(HERE, "libssym.so")  # SSYM_LIB: an alternative build of the same ABI (kernel A/B runs)
 
 MEM_DEVICE, MEM_HOST = 0, 1
+OK, ERR_USAGE, ERR_CUDA, ERR_PARSE, ERR_NOMEM, ERR_INTERNAL = 0, -1, -2, -3, -4, -5  # include/ssym.h
 MODE_REF_LITERAL, MODE_PROVER_CONSISTENT = 0, 1
 MAX_QUERIES, MAX_FRI_LAYERS, S101_MAX_LIST = 16, 9, 31
 

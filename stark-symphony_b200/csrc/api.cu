@@ -351,14 +351,37 @@ static int ensure_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg) {
     return SSYM_OK;
 }
 
+// Scratch of one lane for chunks of up to m proofs.  Growing a buffer is a cudaFree + cudaMalloc (device-synchronising), so callers size EVERY
+// lane they will rotate through before the first launch of a call: no later call of the same shape allocates (a pipelined loop would otherwise
+// stall once per lane, at calls 1..depth-1).
+static int ensure_lane_scratch(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, size_t m, bool own_status) {
+    const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers;
+    m = std::min(m, STWO_DEVICE_CHUNK);
+    CUDA_TRY(lane.stwo_ctx.ensure(m * StwoCtxLayout::WORDS * sizeof(uint32_t)));
+    CUDA_TRY(lane.stwo_evals.ensure(m * (size_t)(L + 1) * Q * 4 * sizeof(uint32_t)));
+    if (own_status) CUDA_TRY(lane.status.ensure(m * sizeof(uint32_t)));
+    const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && cfg.mode == SSYM_MODE_PROVER_CONSISTENT);
+    StwoDedup dd;
+    memset(&dd, 0, sizeof dd);
+    if (const size_t list_entries = share ? stwo_dedup_layout(cfg, m, dd) : 0) {
+        const size_t chains = (size_t)dd.chains * m;
+        CUDA_TRY(lane.dd_plan.ensure(chains * sizeof(uint32_t)));
+        CUDA_TRY(lane.dd_to.ensure(chains * sizeof(uint64_t)));
+        CUDA_TRY(lane.dd_own.ensure(chains * 8 * sizeof(uint32_t)));
+        CUDA_TRY(lane.dd_ckpt.ensure(chains * 8 * sizeof(uint32_t)));
+        CUDA_TRY(lane.dd_bins.ensure(2 * STWO_DEDUP_MAX_BINS * sizeof(uint32_t)));
+        CUDA_TRY(lane.dd_list.ensure(list_entries * sizeof(uint32_t)));
+    }
+    return SSYM_OK;
+}
+
 static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, const uint32_t *d_packed,
                              size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s, bool use_front = false) {
     static const int front_kernels = [] { const char *e = getenv("SSYM_FRONT"); return e ? atoi(e) : 2; }();
-    const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers;
+    int rc = ensure_lane_scratch(c, lane, cfg, n, d_status_out == nullptr);
+    if (rc) return rc;
     for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
         const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
-        CUDA_TRY(lane.stwo_ctx.ensure(m * StwoCtxLayout::WORDS * sizeof(uint32_t)));
-        CUDA_TRY(lane.stwo_evals.ensure(m * (size_t)(L + 1) * Q * 4 * sizeof(uint32_t)));
         StwoParams p;
         p.cfg = cfg;
         p.lo = lo;
@@ -368,24 +391,12 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
         p.packed = d_packed + done * (size_t)lo.stride_words;
         p.ctx = lane.stwo_ctx.as<uint32_t>();
         p.fri_evals = lane.stwo_evals.as<uint32_t>();
-        if (d_status_out) {
-            p.status = d_status_out + done;
-        } else {
-            CUDA_TRY(lane.status.ensure(m * sizeof(uint32_t)));
-            p.status = lane.status.as<uint32_t>();
-        }
+        p.status = d_status_out ? d_status_out + done : lane.status.as<uint32_t>();
         p.trace = d_trace ? d_trace + done : nullptr;
         p.n = (uint32_t)m;
         memset(&p.dd, 0, sizeof p.dd);
         const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && cfg.mode == SSYM_MODE_PROVER_CONSISTENT);
-        if (const size_t list_entries = share ? stwo_dedup_layout(cfg, m, p.dd) : 0) {
-            const size_t chains = (size_t)p.dd.chains * m;
-            CUDA_TRY(lane.dd_plan.ensure(chains * sizeof(uint32_t)));
-            CUDA_TRY(lane.dd_to.ensure(chains * sizeof(uint64_t)));
-            CUDA_TRY(lane.dd_own.ensure(chains * 8 * sizeof(uint32_t)));
-            CUDA_TRY(lane.dd_ckpt.ensure(chains * 8 * sizeof(uint32_t)));
-            CUDA_TRY(lane.dd_bins.ensure(2 * STWO_DEDUP_MAX_BINS * sizeof(uint32_t)));
-            CUDA_TRY(lane.dd_list.ensure(list_entries * sizeof(uint32_t)));
+        if (share && stwo_dedup_layout(cfg, m, p.dd)) {
             p.dd.plan = lane.dd_plan.as<uint32_t>();
             p.dd.ckpt_to = lane.dd_to.as<uint64_t>();
             p.dd.own = lane.dd_own.as<uint32_t>();
@@ -430,12 +441,20 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     if (rc) return rc;
     if (memspace == SSYM_MEM_DEVICE) {
         const bool multi = n > STWO_DEVICE_CHUNK;
-        if ((c->depth == 1 && !multi) || c->profiling) return stwo_launch_chunk(c, c->lanes[0], *cfg, lo, packed, n, accept_bits, status, trace, c->stream);
+        if ((c->depth == 1 && !multi) || c->profiling) {
+            rc = ssym_join(c); // lane 0's scratch may still belong to a pipelined call
+            if (rc) return rc;
+            return stwo_launch_chunk(c, c->lanes[0], *cfg, lo, packed, n, accept_bits, status, trace, c->stream);
+        }
         // Pipelined: every chunk of at most STWO_DEVICE_CHUNK proofs forks from the handle's stream into the next lane (own stream, own scratch, the
         // latency-bound kernels on the lane's high-priority stream), so the channel kernel of one chunk hides behind the Merkle kernels of the
         // previous one.  depth > 1: consecutive CALLS overlap too and the caller joins (ssym_join / ssym_synchronize).  depth == 1: only the
         // chunks of this one large call overlap, and they are ordered back into the handle's stream before the call returns.
         const int D = std::max(c->depth, multi ? 4 : 1);
+        for (int k = 0; k < D; k++) { // the first call of a shape sizes the scratch of ALL the lanes it and its successors rotate through
+            rc = ensure_lane_scratch(c, c->lanes[k], *cfg, n, status == nullptr);
+            if (rc) return rc;
+        }
         for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
             const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
             ssym_ctx::Lane &lane = c->lanes[c->calls++ % D];
@@ -452,6 +471,8 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
         return c->depth == 1 ? ssym_join(c) : SSYM_OK;
     }
     if (memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    rc = ssym_join(c); // host chunks run on the lanes' streams with the lanes' scratch
+    if (rc) return rc;
 
     // Host buffers: double-buffered H2D on the copy stream overlapped with the kernels of the previous chunk.
     const size_t stride_b = (size_t)lo.stride_words * 4;
@@ -590,7 +611,7 @@ static int compact_prepare(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, ssym_st
     if (rc) return rc;
     if (compact_shape(*cfg, lo, sh)) return fail(SSYM_ERR_INTERNAL, "packed layout is not contiguous in slot order");
     CUDA_TRY(cudaSetDevice(c->device));
-    return SSYM_OK;
+    return ssym_join(c); // stage[] / lanes[] scratch is shared with pipelined ssym_stwo_verify_batch calls
 }
 
 extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets, size_t n,
@@ -1328,6 +1349,8 @@ extern "C" int ssym_stwo_prove_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cf
     if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
     if (n == 0) return SSYM_OK;
     CUDA_TRY(cudaSetDevice(c->device));
+    rc = ssym_join(c);
+    if (rc) return rc;
     rc = ensure_tables(c, *cfg);
     if (rc) return rc;
     cudaStream_t s = c->stream;
@@ -1417,6 +1440,10 @@ extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, c
     if (n == 0) return SSYM_OK;
     if (n > 0x7fffffffull) return fail(SSYM_ERR_USAGE, "batch too large for one call");
     CUDA_TRY(cudaSetDevice(c->device));
+    {
+        int rc = ssym_join(c); // lanes[0].status / stage[0] are shared with the Stwo calls
+        if (rc) return rc;
+    }
     cudaStream_t s = c->stream;
     CUDA_TRY(c->s101_ctx.ensure(n * S101_CTX_WORDS * sizeof(uint32_t)));
     S101Params p;

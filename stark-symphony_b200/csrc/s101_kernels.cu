@@ -103,9 +103,13 @@ __global__ void __launch_bounds__(64) s101_transcript_kernel(S101Params p) {
     const uint32_t *rec = p.blob + p.offsets[i];
     uint32_t *ctx = p.ctx + (size_t)i * S101_CTX_WORDS;
     ssym_s101_trace_t *tr = p.trace ? p.trace + i : nullptr;
-    const uint32_t total = rec[0], n_layers = rec[1];
-    const uint32_t ns0 = rec[2], ns1 = rec[3], ns2 = rec[4];
-    bool shape_ok = n_layers <= SSYM_S101_MAX_LIST && ns0 <= SSYM_S101_MAX_LIST && ns1 <= SSYM_S101_MAX_LIST && ns2 <= SSYM_S101_MAX_LIST && total >= 20;
+    // The record's own length word is trusted only after it has been compared with the offsets array (a device-resident caller may hand over
+    // anything): nothing of the record is read before that, and every later read stays below `total`.
+    const uint64_t len = p.offsets[i + 1] - p.offsets[i];
+    bool shape_ok = p.offsets[i + 1] >= p.offsets[i] && len >= 20 && len <= 0xffffffffull && rec[0] == (uint32_t)len;
+    const uint32_t total = shape_ok ? rec[0] : 0, n_layers = shape_ok ? rec[1] : 0;
+    const uint32_t ns0 = shape_ok ? rec[2] : 0, ns1 = shape_ok ? rec[3] : 0, ns2 = shape_ok ? rec[4] : 0;
+    shape_ok = shape_ok && n_layers <= SSYM_S101_MAX_LIST && ns0 <= SSYM_S101_MAX_LIST && ns1 <= SSYM_S101_MAX_LIST && ns2 <= SSYM_S101_MAX_LIST;
     uint32_t w = 20 + 8 * (ns0 + ns1 + ns2);
     if (shape_ok) {
         for (uint32_t l = 0; l < n_layers; l++) {

@@ -42,7 +42,7 @@ __device__ bool json_walk(const WitTables &tab, const uint8_t *t, uint32_t len, 
     for (;;) {
         uint32_t ns, ne;
         if (!string(ns, ne) || !expect(':') || !expect('{')) return false;
-        bool have = false;
+        bool have = false, have_type = false;
         uint32_t vs = 0, ve = 0;
         for (;;) {
             uint32_t ks, ke, s, e;
@@ -52,12 +52,17 @@ __device__ bool json_walk(const WitTables &tab, const uint8_t *t, uint32_t len, 
                 have = true;
                 vs = s;
                 ve = e;
+            } else if (str_is(t, ks, ke, "type", 4)) {
+                if (have_type) return false;
+                have_type = true;
+            } else {
+                return false; // a member serde's WitnessValues does not know: the host parser decides
             }
             skip();
             if (pos < len && t[pos] == ',') { pos++; continue; }
             break;
         }
-        if (!expect('}') || !have || vs == ve) return false;
+        if (!expect('}') || !have || !have_type || vs == ve) return false; // both members are required (the host parser reports the error)
         const int id = name_id(tab, t, ns, ne);
         if (id < 0 || (seen >> id & 1)) return false;
         seen |= 1u << id;

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -33,9 +34,18 @@ struct Val {
 };
 
 // ---- value grammar ----------------------------------------------------------------------------------
+// Witness text is untrusted: nesting is bounded (the deepest value of either program nests 7 levels), so a hostile text cannot overflow the stack.
+constexpr int MAX_NESTING = 64;
+struct DepthGuard {
+    int &d;
+    explicit DepthGuard(int &d_) : d(d_) { if (++d > MAX_NESTING) throw ParseError{"nesting too deep"}; }
+    ~DepthGuard() { --d; }
+};
+
 struct ValueParser {
     const char *s;
     size_t n, pos = 0;
+    int depth = 0;
     ValueParser(const char *s_, size_t n_) : s(s_), n(n_) {}
     void ws() {
         while (pos < n && (s[pos] == ' ' || s[pos] == '\n' || s[pos] == '\t' || s[pos] == '\r')) pos++;
@@ -74,13 +84,16 @@ struct ValueParser {
         if (!digits) throw ParseError{"empty integer literal"};
         return v;
     }
-    std::vector<Val> seq(char close) {
+    std::vector<Val> seq(char close, bool *trailing_comma = nullptr) {
         std::vector<Val> items;
         if (eat(close)) return items;
         for (;;) {
             items.push_back(value());
             if (eat(',')) {
-                if (eat(close)) return items; // trailing comma
+                if (eat(close)) { // trailing comma
+                    if (trailing_comma) *trailing_comma = true;
+                    return items;
+                }
                 continue;
             }
             if (eat(close)) return items;
@@ -88,13 +101,19 @@ struct ValueParser {
         }
     }
     Val value() {
+        DepthGuard guard(depth);
         ws();
         if (pos >= n) throw ParseError{"unexpected end of value"};
         char c = s[pos];
         if (c == '(') {
             pos++;
-            std::vector<Val> items = seq(')');
-            if (items.size() == 1) return items[0]; // parenthesised value
+            bool trailing = false;
+            std::vector<Val> items = seq(')', &trailing);
+            if (items.size() == 1) {
+                // `(x)` is a parenthesised expression; `(x,)` is a 1-tuple, which is a value of none of the programs' witness types
+                if (trailing) throw ParseError{"1-tuple is not a value of any witness type"};
+                return items[0];
+            }
             Val v;
             v.kind = Val::TUPLE;
             v.items = std::move(items);
@@ -130,6 +149,7 @@ struct ValueParser {
 struct Json {
     const char *s;
     size_t n, pos = 0;
+    int depth = 0;
     Json(const char *s_, size_t n_) : s(s_), n(n_) {}
     void ws() {
         while (pos < n && (s[pos] == ' ' || s[pos] == '\n' || s[pos] == '\t' || s[pos] == '\r')) pos++;
@@ -161,8 +181,10 @@ struct Json {
                     if (pos + 4 > n) throw ParseError{"JSON: bad \\u escape"};
                     unsigned cp = 0;
                     for (int i = 0; i < 4; i++) {
-                        char h = s[pos++];
-                        cp = cp * 16 + (h >= '0' && h <= '9' ? h - '0' : (h | 32) - 'a' + 10);
+                        const char h = s[pos++];
+                        const bool dec = h >= '0' && h <= '9', hexl = (h | 32) >= 'a' && (h | 32) <= 'f';
+                        if (!dec && !hexl) throw ParseError{"JSON: bad \\u escape"};
+                        cp = cp * 16 + (dec ? h - '0' : (h | 32) - 'a' + 10);
                     }
                     if (cp > 0x7f) throw ParseError{"JSON: non-ASCII escape in witness"};
                     out += (char)cp;
@@ -179,6 +201,7 @@ struct Json {
         return out;
     }
     void skip_value() {
+        DepthGuard guard(depth);
         ws();
         if (pos >= n) throw ParseError{"JSON: unexpected end"};
         char c = s[pos];
@@ -207,13 +230,25 @@ struct Json {
             std::string name = str();
             expect(':');
             expect('{');
-            bool have = false;
+            // serde's WitnessValues (simfony-cli/src/main.rs:77-81): both members are strings and both are required; a repeated member or
+            // witness name is an error there, not "last one wins"
+            bool have = false, have_type = false;
+            if (out.count(name)) throw ParseError{"duplicate witness " + name};
             if (!peek('}')) {
                 for (;;) {
                     std::string key = str();
                     expect(':');
-                    if (key == "value") { out[name] = str(); have = true; }
-                    else skip_value();
+                    if (key == "value") {
+                        if (have) throw ParseError{"witness " + name + " has two \"value\" members"};
+                        out[name] = str();
+                        have = true;
+                    } else if (key == "type") {
+                        if (have_type) throw ParseError{"witness " + name + " has two \"type\" members"};
+                        str(); // shapes come from the program, not from this text (stark101's FRI_LAYERS type string is malformed upstream)
+                        have_type = true;
+                    } else {
+                        skip_value();
+                    }
                     ws();
                     if (pos < n && s[pos] == ',') { pos++; continue; }
                     break;
@@ -221,11 +256,14 @@ struct Json {
             }
             expect('}');
             if (!have) throw ParseError{"witness " + name + " has no \"value\""};
+            if (!have_type) throw ParseError{"witness " + name + " has no \"type\""};
             ws();
             if (pos < n && s[pos] == ',') { pos++; continue; }
             expect('}');
             break;
         }
+        ws();
+        if (pos != n) throw ParseError{"JSON: trailing characters after the witness object"};
         return out;
     }
 };
@@ -339,6 +377,12 @@ extern "C" int ssym_stwo_pack_wit(const ssym_stwo_config_t *cfg, const char *jso
     } catch (const ParseError &) {
         memset(out, 0, (size_t)lo.stride_words * 4);
         return SSYM_ERR_PARSE;
+    } catch (const std::bad_alloc &) { // nothing may escape the extern "C" boundary: a hostile witness is a reject, not a crash
+        memset(out, 0, (size_t)lo.stride_words * 4);
+        return SSYM_ERR_NOMEM;
+    } catch (...) {
+        memset(out, 0, (size_t)lo.stride_words * 4);
+        return SSYM_ERR_PARSE;
     }
     if (reject) memset(out, 0, (size_t)lo.stride_words * 4);
     if (shape_reject) *shape_reject = reject ? 1 : 0;
@@ -390,6 +434,10 @@ extern "C" int ssym_s101_pack_wit(const char *json_text, size_t len, uint32_t *o
         memcpy(out, rec.data(), rec.size() * 4);
         *out_words = rec.size();
     } catch (const ParseError &) {
+        return SSYM_ERR_PARSE;
+    } catch (const std::bad_alloc &) {
+        return SSYM_ERR_NOMEM;
+    } catch (...) {
         return SSYM_ERR_PARSE;
     }
     return SSYM_OK;

@@ -54,6 +54,8 @@ class Verifier:
         check(self.lib.ssym_create(device, C.byref(h)))
         self.h = h
         self.device = device
+        self._explicit_stream = False  # set_stream() was called: the caller manages ordering
+        self._auto_stream = None       # the stream handle last installed by _space()
 
     def close(self) -> None:
         if getattr(self, "h", None):
@@ -70,8 +72,10 @@ class Verifier:
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         """Run device-resident calls on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream)."""
         if cuda_stream == 0:
-            raise SsymError("pass a non-default stream handle (e.g. torch.cuda.Stream().cuda_stream); None restores the handle's own stream")
+            raise SsymError("pass a non-default stream handle (e.g. torch.cuda.Stream().cuda_stream); None restores the default behaviour")
         check(self.lib.ssym_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        self._explicit_stream = cuda_stream is not None
+        self._auto_stream = None
 
     def synchronize(self) -> None:
         check(self.lib.ssym_synchronize(self.h))
@@ -119,9 +123,25 @@ class Verifier:
             return torch.empty(shape, dtype=tdt, device=like.device)  # every output element is written by the kernels
         return np.zeros(shape, dtype=dtype)
 
-    @staticmethod
-    def _space(x) -> int:
-        return MEM_DEVICE if _is_device(x) else MEM_HOST
+    CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle that names the default stream in API calls
+
+    def _space(self, x) -> int:
+        """Memory space of a buffer.  For device buffers this is also where the stream-ordering contract of include/ssym.h ("Stream ordering")
+        is made safe by default: unless set_stream() was called, the handle is pointed at torch's CURRENT stream for x's device, so the
+        call is ordered after whatever produced its inputs and before whatever the caller enqueues next."""
+        if not _is_device(x):
+            return MEM_HOST
+        if not self._explicit_stream:
+            try:
+                import torch
+
+                handle = int(torch.cuda.current_stream(x.device).cuda_stream) or self.CUDA_STREAM_LEGACY
+            except Exception:  # not a torch tensor: the caller owns the ordering (ssym_set_stream)
+                handle = None
+            if handle is not None and handle != self._auto_stream:
+                check(self.lib.ssym_set_stream(self.h, C.c_void_p(handle)))
+                self._auto_stream = handle
+        return MEM_DEVICE
 
     # ---- whole proofs --------------------------------------------------------------------------------
     def stwo_verify_batch(self, packed, cfg: StwoConfig, n: Optional[int] = None, want_status: bool = False, want_trace: bool = False,
@@ -182,7 +202,7 @@ class Verifier:
                 raise SsymError("device seeds must be a contiguous int64 tensor (the u64 bit patterns)")
             if out is None:
                 out = torch.empty((n, lo.stride_words), dtype=torch.int32, device=seeds.device)
-            space = MEM_DEVICE
+            space = self._space(seeds)
         else:
             seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
             n = seeds.size

@@ -6,6 +6,7 @@ reference's own fixtures (no reference source is copied):
 
   stwo_proof_prod.wit      = stwo-verifier/scripts/generate_wit.py tests/data/proof.json      (Makefile:10-11 `make proof-wit`)
   stwo_proof_testing.wit   = stwo-verifier/scripts/generate_wit.py tests/data/proof_test.json
+  stwo_proof.json, stwo_proof_test.json = the two upstream proof-JSON fixtures themselves (stwo-verifier/tests/data/, data files)
   stark101_proof.json      = `python -m fibsquare`  (stark101/Makefile:14-15 `make proof`, deterministic: prover.py:27 seed)
   stark101_proof.wit       = stark101/scripts/generate_wit.py stark101_proof.json
   simf_literals.json       = the witness literals embedded in stwo-verifier/src/verifier.simf:62-108
@@ -61,6 +62,8 @@ def main():
     for name, src in (("prod", "proof.json"), ("testing", "proof_test.json")):
         out = run([sys.executable, os.path.join(stwo, "scripts", "generate_wit.py"), os.path.join(stwo, "tests", "data", src)])
         open(os.path.join(HERE, f"stwo_proof_{name}.wit"), "w").write(out)
+        # the upstream proof JSON itself (data, not source): the input of the proof-JSON boundary test (tests/test_abi_and_host.py)
+        shutil.copy(os.path.join(stwo, "tests", "data", src), os.path.join(HERE, f"stwo_{src}"))
 
     s101_json = os.path.join(HERE, "stark101_proof.json")
     if not skip_prover or not os.path.exists(s101_json):

@@ -121,6 +121,29 @@ def test_stark101_wit_packer_matches_python_reader(S):
     assert bad[0]
 
 
+@pytest.mark.parametrize("preset,src", [("testing", "stwo_proof_test.json"), ("prod", "stwo_proof.json")])
+def test_stwo_proof_json_path_equals_reference_generator(S, preset, src):
+    """The upstream proof-JSON boundary: witness.stwo_wit_from_proof_json mirrors stwo-verifier/scripts/generate_wit.py:106-245, so
+    on the reference's two fixtures every witness value must equal, character for character, what the reference's generator wrote
+    (tests/golden/*.wit are its output), and pack_stwo_proof_json must equal the packed golden witness."""
+    data = json.load(open(os.path.join(GOLDEN, src)))
+    golden_text = open(os.path.join(GOLDEN, f"stwo_proof_{preset}.wit")).read()
+    golden = json.loads(golden_text)
+    ours = S.witness.stwo_wit_from_proof_json(data)
+    assert set(ours) == set(golden) == {"COMMITMENTS", "DECOMMITMENTS", "OODS_EVALS", "FRI_COMMITMENTS", "FRI_DECOMMITMENTS", "POW_NONCE"}
+    for name in golden:
+        assert ours[name]["value"] == golden[name]["value"], name
+    cfg = S.stwo_config(preset, 0)
+    want, bad = S.witness.pack_stwo_wits([golden_text], cfg)
+    assert not bad[0]
+    assert (S.witness.pack_stwo_proof_json(data, cfg) == want).all()
+    p = O.PRESETS[preset]
+    ref, rej = W.pack_stwo(W.load_wit(json.dumps(ours)), p["n_queries"], p["n_fri_layers"], p["lde_log"])
+    assert not rej and (ref == want).all()
+    with pytest.raises(S.SsymError):  # the other preset's shape
+        S.witness.pack_stwo_proof_json(data, S.stwo_config("prod" if preset == "testing" else "testing", 0))
+
+
 def test_value_grammar_corner_cases():
     assert W.parse_value("(1, (2, 3), [4, 5], list![], list![6,], 0x10, 1_000)") == (1, (2, 3), [4, 5], [], [6], 16, 1000)
     assert W.parse_value("((7))") == 7

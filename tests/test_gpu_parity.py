@@ -261,6 +261,31 @@ def test_stark101_replicated_device(S, ver):
     assert (bits == expect).all()
 
 
+def test_stark101_device_records_that_lie_about_their_length(S, ver):
+    """Device-resident records are untrusted too: a record whose length word disagrees with the offsets array, or one shorter than the
+    fixed header, is SHAPE-rejected without a single read outside its own [offsets[i], offsets[i+1]) range (memcheck-clean under
+    tools/sanitize.sh).  Its neighbours are unaffected."""
+    import torch
+
+    blob, _, _ = golden_s101(S)
+    L = len(blob)
+    recs = [blob.copy() for _ in range(6)]
+    recs[1][0] = L + 4096            # declares more words than it has
+    recs[2][0] = 0xFFFFFFFF          # ... far more
+    recs[3] = blob[:12].copy()       # shorter than the header; its length word still says L
+    recs[4][0] = L - 8               # declares fewer
+    all_blob = np.concatenate(recs)
+    offsets = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.uint64)
+    d_blob = torch.from_numpy(all_blob.view(np.int32)).cuda()  # exact-size allocation: an over-read would leave the buffer
+    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    accept, status, _ = ver.stark101_verify_batch(d_blob, d_off, want_status=True)
+    ver.synchronize()
+    st = status.cpu().numpy().view(np.uint32)
+    assert st[0] == 0 and st[5] == 0
+    assert all(st[i] != 0 for i in (1, 2, 3, 4))
+    assert int(accept.cpu().numpy().view(np.uint32)[0]) & 0x3F == 0b100001
+
+
 # ---- jets ---------------------------------------------------------------------------------------------------
 def rand_u32(rng, n, canonical_frac=0.5):
     P = 2147483647

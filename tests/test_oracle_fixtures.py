@@ -189,3 +189,47 @@ def test_work_per_proof_matches_survey_8d(orc):
         ops = (C.c_uint64 * 3)()
         orc.lib.oracle_field_op_counts(ops)
         assert (int(orc.lib.oracle_compression_count()), int(ops[0]), int(ops[1]), int(ops[2])) == want, (preset, mode)
+
+
+def test_fast_sha_mode_is_bit_identical(orc):
+    """bench.py's `cpu_baseline_fast` leg runs the oracle with word-wise absorbs / SHA-NI / Mersenne folding (oracle_set_fast_sha): every trace byte,
+    every digest and every field value must equal the literal port's, on the fixtures, on corrupted records, and on non-canonical field inputs."""
+    import hashlib
+
+    P = 2**31 - 1
+    try:
+        for n in list(range(0, 130)) + [1000]:
+            data = bytes((7 * i + n) & 0xFF for i in range(n))
+            for fast in (False, True):
+                orc.set_fast(fast)
+                out = (O.C.c_uint32 * 8)()
+                orc.lib.oracle_sha256_bytes(data, n, out)
+                assert b"".join(int(x).to_bytes(4, "big") for x in out) == hashlib.sha256(data).digest(), (n, fast)
+        orc.set_fast(True)
+        edge = [0, 1, P - 1, P, P + 1, 2 * P, 2 * P + 1, 2**32 - 1]
+        rng = np.random.default_rng(5)
+        vals = edge + [int(x) for x in rng.integers(0, 2**32, size=300, dtype=np.uint64)]
+        for a in vals[:40]:
+            assert orc.lib.oracle_m31(a) == a % P
+            for b in vals[:40]:
+                assert orc.lib.oracle_m31_mul(a, b) == (a * b) % P and orc.lib.oracle_m31_add(a, b) == ((a + b) % 2**32) % P
+        for preset in ("testing", "prod"):
+            packed = load_stwo(preset)
+            recs = [packed]
+            rng = np.random.default_rng(11)
+            for _ in range(6):
+                r = packed.copy()
+                r[int(rng.integers(0, len(r)))] ^= np.uint32(1 << int(rng.integers(0, 32)))
+                recs.append(r)
+            batch = np.concatenate(recs)
+            for mode in (O.MODE_REF_LITERAL, O.MODE_PROVER_CONSISTENT):
+                cfg = O.make_config(preset, mode)
+                orc.set_fast(False)
+                a0, s0, t0 = orc.stwo_verify_batch(cfg, batch, len(recs), want_trace=True)
+                assert orc.set_fast(True) >= 1
+                a1, s1, t1 = orc.stwo_verify_batch(cfg, batch, len(recs), want_trace=True)
+                assert (a0 == a1).all() and (s0 == s1).all()
+                for i in range(len(recs)):
+                    assert bytes(memoryview(t0[i]).cast("B")) == bytes(memoryview(t1[i]).cast("B")), (preset, mode, i)
+    finally:
+        orc.set_fast(False)

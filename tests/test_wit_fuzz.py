@@ -202,3 +202,89 @@ def test_gpu_tokeniser_agrees_with_host_parser_on_mutations(S, preset, n):
         assert (g_packed[i] == out).all(), i
         n_ok += want == 0
     assert 0 < n_ok < n  # the batch mixes accepted and refused witnesses
+
+
+# ---- hostile and JSON-level cases (untrusted text must be a reject, never a crash; accept <=> serde would parse it) ------------
+def _json_level_cases(base):
+    good = {k: {"value": v["value"], "type": v.get("type", "")} for k, v in base.items()}
+    text = json.dumps(good)
+    first = next(iter(good))
+    no_type = json.dumps({k: ({"value": v["value"]} if k == first else v) for k, v in good.items()})
+    type_not_string = json.dumps({k: ({"value": v["value"], "type": 5} if k == first else v) for k, v in good.items()})
+    dup_value = text.replace('"value":', '"value": "0", "value":', 1)
+    dup_type = text.replace('"type":', '"type": "u32", "type":', 1)
+    dup_name = text[:-1] + ", " + json.dumps({first: good[first]})[1:]
+    return {
+        "good": (text, True), "trailing garbage": (text + " x", False), "trailing object": (text + "{}", False), "trailing whitespace": (text + " \n\t", True),
+        "no type": (no_type, False), "type not a string": (type_not_string, False), "two values": (dup_value, False), "two types": (dup_type, False),
+        "two witnesses of one name": (dup_name, False),
+        "bad unicode escape": (text.replace('"value": "', '"value": "\\u00zz', 1), False),
+        "ascii unicode escape": (text.replace('"value": "', '"value": "\\u0020', 1), True),
+        "unknown member": (text.replace('"type":', '"note": [1, {"a": [2]}], "type":', 1), True),
+    }
+
+
+def test_json_level_strictness_matches_python_reader(S, base):
+    cfg = S.stwo_config("testing", 0)
+    for name, (text, ok) in _json_level_cases(base).items():
+        packed, bad = S.witness.pack_stwo_wits([text], cfg)
+        kind, rec = _python_result(text, cfg)
+        assert (not bad[0]) == ok, name
+        assert (kind == "ok") == ok, name
+        if ok:
+            assert (packed == rec).all(), name
+
+
+def test_one_tuple_is_not_a_parenthesised_value(S, base):
+    """`(x)` is a parenthesised expression (accepted, = x); `(x,)` is a 1-tuple and no witness type of either program is one."""
+    cfg = S.stwo_config("testing", 0)
+    wit = {k: dict(v) for k, v in base.items()}
+    nonce = wit["POW_NONCE"]["value"].strip()
+    for form, ok in ((f"({nonce})", True), (f"(({nonce}))", True), (f"({nonce},)", False), (f"(({nonce}),)", False)):
+        wit["POW_NONCE"]["value"] = form
+        text = json.dumps(wit)
+        _, bad = S.witness.pack_stwo_wits([text], cfg)
+        assert (not bad[0]) == ok, form
+        assert (_python_result(text, cfg)[0] == "ok") == ok, form
+
+
+@pytest.mark.parametrize("depth", [60, 70, 1000, 2_000_000])
+def test_hostile_nesting_is_a_parse_error_not_a_crash(S, base, base101, depth):
+    """A value of `depth` opening brackets, and the same nesting in a JSON member the parser skips: ParseError beyond 64 levels, at any depth,
+    in both programs' entry points (2 000 000 '(' used to overflow the stack of ssym_s101_pack_wit)."""
+    import ctypes as C
+
+    lib = S.load()
+    cfg = S.stwo_config("testing", 0)
+    lo = S.stwo_layout(cfg)
+    for opener, closer in (("(", ")"), ("[", "]"), ("list![", "]")):
+        wit = {k: dict(v) for k, v in base.items()}
+        wit["POW_NONCE"]["value"] = opener * depth + "1" + closer * depth
+        raw = json.dumps(wit).encode()
+        out = np.zeros(lo.stride_words, dtype=np.uint32)
+        shape = C.c_int(0)
+        rc = lib.ssym_stwo_pack_wit(C.byref(cfg), raw, len(raw), C.c_void_p(out.ctypes.data), C.byref(shape))
+        if opener == "(" and depth < 64:
+            assert rc == 0  # redundant parentheses within the bound are a parenthesised value
+        else:
+            assert rc == S.ERR_PARSE and not out.any()
+    # nesting inside a member that is skipped (no closing brackets at all for the deepest case: still no crash)
+    wit = json.dumps({k: dict(v) for k, v in base101.items()})
+    deep = wit.replace('"type":', '"skipped": ' + "[" * depth + "]" * (depth if depth < 10**6 else 0) + ', "type":', 1).encode()
+    rec = np.zeros(4096, dtype=np.uint32)
+    words = C.c_size_t(rec.size)
+    rc = lib.ssym_s101_pack_wit(deep, len(deep), C.c_void_p(rec.ctypes.data), C.byref(words))
+    assert rc == (0 if depth < 64 else S.ERR_PARSE)
+
+
+def test_huge_list_is_rejected_without_escaping_exceptions(S, base101):
+    """A list! of two million items is well-formed text but not a List<_, 32>: rejected (parse error), nothing escapes the extern "C" boundary."""
+    import ctypes as C
+
+    lib = S.load()
+    wit = {k: dict(v) for k, v in base101.items()}
+    wit["FRI_LAYERS"]["value"] = "list![" + "1," * 2_000_000 + "1]"
+    raw = json.dumps(wit).encode()
+    rec = np.zeros(4096, dtype=np.uint32)
+    words = C.c_size_t(rec.size)
+    assert lib.ssym_s101_pack_wit(raw, len(raw), C.c_void_p(rec.ctypes.data), C.byref(words)) in (S.ERR_PARSE, S.ERR_NOMEM)

@@ -74,40 +74,46 @@ def test_skeleton_query_and_errors(S):
 
 
 # ---- GPU --------------------------------------------------------------------------------------------------
+def _dumps(wit, **kw):
+    """json.dumps of NAME -> {"value": ...} with the "type" member serde's WitnessValues requires (simfony-cli/src/main.rs:77-81) added where a
+    variant did not carry one."""
+    return json.dumps({k: ({"type": "", **v} if isinstance(v, dict) else v) for k, v in wit.items()}, **kw)
+
+
 def _variants(text):
     """(label, text, on the fast path?) — every variant has a defined result under the host parser."""
     wit = json.loads(text)
     out = [("generator output", text, True)]
-    out.append(("pretty-printed JSON, reordered names, no type member", json.dumps({k: {"value": wit[k]["value"]} for k in reversed(NAMES)}, indent=2), True))
+    out.append(("pretty-printed JSON, reordered names", _dumps({k: {"value": wit[k]["value"]} for k in reversed(NAMES)}, indent=2), True))
     spaced = {k: {"value": "  " + re.sub(r"([(\[\]),])", r"  \1   ", v["value"]) + "  ", "type": "x"} for k, v in wit.items()}
-    out.append(("spaces around all tokens", json.dumps(spaced), True))
+    out.append(("spaces around all tokens", _dumps(spaced), True))
     nl = {k: {"value": re.sub(r"([(\[,])", r"\1 \n\t", v["value"]), "type": "x"} for k, v in wit.items()}
-    out.append(("newlines / tabs in the value text (JSON escapes)", json.dumps(nl), False))
-    out.append(("type member before value", json.dumps({k: {"type": "u32", "value": v["value"]} for k, v in wit.items()}), True))
+    out.append(("newlines / tabs in the value text (JSON escapes)", _dumps(nl), False))
+    out.append(("type member before value", _dumps({k: {"type": "u32", "value": v["value"]} for k, v in wit.items()}), True))
     hexed = dict(wit)
     hexed["POW_NONCE"] = {"value": hex(int(wit["POW_NONCE"]["value"]))}
     hexed["COMMITMENTS"] = {"value": re.sub(r"0x0*", "0x", wit["COMMITMENTS"]["value"])}
-    out.append(("hex nonce, digests without leading zeros", json.dumps(hexed), True))
+    out.append(("hex nonce, digests without leading zeros", _dumps(hexed), True))
     dec = dict(wit)
     dec["COMMITMENTS"] = {"value": "(" + ", ".join(str(int(x, 16)) for x in re.findall(r"0x[0-9a-f]+", wit["COMMITMENTS"]["value"])) + ")"}
-    out.append(("decimal u256 literals", json.dumps(dec), True))
+    out.append(("decimal u256 literals", _dumps(dec), True))
     up = dict(wit)
     up["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"].upper().replace("0X", "0x")}
-    out.append(("upper-case hex", json.dumps(up), False))
+    out.append(("upper-case hex", _dumps(up), False))
     us = dict(wit)
     us["POW_NONCE"] = {"value": wit["POW_NONCE"]["value"][0] + "_" + wit["POW_NONCE"]["value"][1:]}
-    out.append(("digit separators", json.dumps(us), False))
+    out.append(("digit separators", _dumps(us), False))
     tc = dict(wit)
     tc["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"][:-1] + ",)"}
-    out.append(("trailing comma", json.dumps(tc), False))
+    out.append(("trailing comma", _dumps(tc), False))
     par = dict(wit)
     par["POW_NONCE"] = {"value": "(" + wit["POW_NONCE"]["value"] + ")"}
-    out.append(("parenthesised value", json.dumps(par), False))
-    esc = json.dumps(wit).replace('"value": "(', '"value": "\\u0028', 1)
+    out.append(("parenthesised value", _dumps(par), False))
+    esc = _dumps(wit).replace('"value": "(', '"value": "\\u0028', 1)
     out.append(("JSON escape", esc, False))
     extra = dict(wit)
     extra["EXTRA"] = {"value": "7"}
-    out.append(("unknown extra witness", json.dumps(extra), False))
+    out.append(("unknown extra witness", _dumps(extra), False))
     return out
 
 
@@ -117,27 +123,29 @@ def _bad_variants(text):
     out = []
     longer = dict(wit)
     longer["DECOMMITMENTS"] = {"value": wit["DECOMMITMENTS"]["value"].replace("list![", "list![0x01, ", 1)}
-    out.append(("one sibling too many", json.dumps(longer), 1))
+    out.append(("one sibling too many", _dumps(longer), 1))
     shorter = dict(wit)
     shorter["FRI_DECOMMITMENTS"] = {"value": re.sub(r"list!\[0x[0-9a-f]+, ", "list![", wit["FRI_DECOMMITMENTS"]["value"], count=1)}
-    out.append(("one FRI sibling too few", json.dumps(shorter), 1))
+    out.append(("one FRI sibling too few", _dumps(shorter), 1))
     big = dict(wit)
     big["OODS_EVALS"] = {"value": wit["OODS_EVALS"]["value"].replace("((1, 0)", "((4294967296, 0)", 1)}
     assert big["OODS_EVALS"] != wit["OODS_EVALS"]
-    out.append(("u32 literal out of range", json.dumps(big), 2))
-    out.append(("missing witness", json.dumps({k: v for k, v in wit.items() if k != "POW_NONCE"}), 2))
+    out.append(("u32 literal out of range", _dumps(big), 2))
+    out.append(("missing witness", _dumps({k: v for k, v in wit.items() if k != "POW_NONCE"}), 2))
+    out.append(("no type member", json.dumps({k: {"value": v["value"]} for k, v in wit.items()}), 2))
+    out.append(("trailing bytes after the object", text + "0", 2))
     out.append(("truncated file", text[: len(text) // 2], 2))
     out.append(("not JSON", "hello", 2))
     out.append(("empty", "", 2))
     junk = dict(wit)
     junk["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"].replace(", ", "; ", 1)}
-    out.append(("bad separator", json.dumps(junk), 2))
+    out.append(("bad separator", _dumps(junk), 2))
     stray = dict(wit)
     stray["DECOMMITMENTS"] = {"value": wit["DECOMMITMENTS"]["value"].replace("list![", "ist![", 1)}
-    out.append(("broken list! keyword", json.dumps(stray), 2))
+    out.append(("broken list! keyword", _dumps(stray), 2))
     arr = dict(wit)
     arr["COMMITMENTS"] = {"value": wit["COMMITMENTS"]["value"].replace("(", "[").replace(")", "]")}
-    out.append(("array where a tuple is expected", json.dumps(arr), 2))
+    out.append(("array where a tuple is expected", _dumps(arr), 2))
     return out
 
 
@@ -314,24 +322,24 @@ def _s101_variants(text):
     wit = json.loads(text)
     names = ["P_MT_ROOT", "P_EVALS", "FRI_LAYERS", "FRI_LAST_LAYER"]
     out = [("generator output", text, True)]
-    out.append(("pretty-printed, reordered, no type member", json.dumps({k: {"value": wit[k]["value"]} for k in reversed(names)}, indent=1), True))
-    out.append(("spaces around tokens", json.dumps({k: {"value": " " + re.sub(r"([(\[\]),])", r" \1  ", v["value"]) + " "} for k, v in wit.items()}), True))
+    out.append(("pretty-printed, reordered", _dumps({k: {"value": wit[k]["value"]} for k in reversed(names)}, indent=1), True))
+    out.append(("spaces around tokens", _dumps({k: {"value": " " + re.sub(r"([(\[\]),])", r" \1  ", v["value"]) + " "} for k, v in wit.items()}), True))
     hexed = dict(wit)
     hexed["P_MT_ROOT"] = {"value": hex(int(wit["P_MT_ROOT"]["value"]))}
     hexed["FRI_LAST_LAYER"] = {"value": hex(int(wit["FRI_LAST_LAYER"]["value"]))}
-    out.append(("hex root and last layer", json.dumps(hexed), True))
+    out.append(("hex root and last layer", _dumps(hexed), True))
     single = dict(wit)
     single["FRI_LAYERS"] = {"value": wit["FRI_LAYERS"]["value"].replace("((", "(").replace("))", ")")}
-    out.append(("FRI layers without the doubled parentheses", json.dumps(single), False))
+    out.append(("FRI layers without the doubled parentheses", _dumps(single), False))
     fewer = dict(wit)  # one FRI layer dropped: well-typed, another shape (and a proof the verifier rejects)
     fewer["FRI_LAYERS"] = {"value": "list![" + wit["FRI_LAYERS"]["value"][len("list!["):].split(")), ((", 1)[1].join(["((", ""])}
-    out.append(("another shape: first FRI layer dropped", json.dumps(fewer), False))
+    out.append(("another shape: first FRI layer dropped", _dumps(fewer), False))
     shorter = dict(wit)
     shorter["P_EVALS"] = {"value": re.sub(r"list!\[\d+, ", "list![", wit["P_EVALS"]["value"], count=1)}
-    out.append(("another shape: one trace sibling dropped", json.dumps(shorter), False))
-    bad = [("garbage", "{]", 2), ("missing witness", json.dumps({k: v for k, v in wit.items() if k != "P_EVALS"}), 2),
-           ("u32 out of range", json.dumps({**wit, "FRI_LAST_LAYER": {"value": str(1 << 32)}}), 2),
-           ("u256 out of range", json.dumps({**wit, "P_MT_ROOT": {"value": str(1 << 256)}}), 2), ("empty", "", 2)]
+    out.append(("another shape: one trace sibling dropped", _dumps(shorter), False))
+    bad = [("garbage", "{]", 2), ("no type member", json.dumps({k: {"value": v["value"]} for k, v in wit.items()}), 2), ("missing witness", _dumps({k: v for k, v in wit.items() if k != "P_EVALS"}), 2),
+           ("u32 out of range", _dumps({**wit, "FRI_LAST_LAYER": {"value": str(1 << 32)}}), 2),
+           ("u256 out of range", _dumps({**wit, "P_MT_ROOT": {"value": str(1 << 256)}}), 2), ("empty", "", 2)]
     return out, bad
 
 
