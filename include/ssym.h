@@ -149,8 +149,39 @@ typedef struct ssym_stwo_trace {
     uint32_t mask_fri[SSYM_MAX_FRI_LAYERS];
     uint32_t mask_fold_inv[SSYM_MAX_FRI_LAYERS];
     uint32_t mask_last_query, mask_last_eval;
-    uint32_t pad_[3];
+    uint32_t draw_retries; /* felt draws that had to be repeated (channel.simf:115-141: a word >= 2p, probability 2^-29 each) */
+    uint32_t pad_[2];
 } ssym_stwo_trace_t;
+
+/* ------------------------------------------------------------------------- */
+/* Cost model                                               */
+/* ------------------------------------------------------------------------- */
+
+/* What the reference PROGRAM executes for one proof — the dynamic counterpart of the static `Node bounds` that `simfony run`
+ * prints (simfony-cli/src/main.rs:142-154,193-203) — counted at the level of the functions that carry the cost:
+ *  - the sha_256_ctx_8_* jets (calls per jet, message bytes, compression-function invocations inside them);
+ *  - the M31 operations (fields/m31.simf): m31_mul = 1 multiply_32 + 1 modulo_64, m31_add (counting the add inside m31_sub) = 1 add_32 +
+ *    1 modulo_32, m31_neg = 1 subtract_32, m31_inv = 1 is_zero_32 + 37 m31_mul (those 37 are INCLUDED in m31_mul);
+ *  - eq_256 (Merkle root comparisons), index -> point conversions (groups/m31_point.simf:58-106: 32 doublings + one point addition per
+ *    set bit of the index, which is what makes m31_mul / m31_add depend on the drawn queries).
+ * The O(queries x layers) control jets (eq_32, and_32, shifts, divide_32 / divides_32 of the index algebra) are not modelled.
+ * The numbers are those of a proof on which no inversion meets zero (status bits OODS_INV_ZERO / ANSWER_INV_ZERO / FOLD_INV_ZERO clear);
+ * the reference's early exit at the first failed assert is NOT modelled: this is the cost of running verify_proof to its end.
+ * Closed form in csrc/cost.cpp, function by function from the .simf sources; tests/test_cost_model.py compares every field with the
+ * oracle's per-thread counters on the fixtures, on random configurations and on random queries. */
+#define SSYM_COST_FIELDS 14
+typedef struct ssym_cost {
+    uint64_t sha_compressions;
+    uint64_t sha_init, sha_add_4, sha_add_8, sha_add_32, sha_finalize; /* calls of sha_256_ctx_8_{init,add_4,add_8,add_32,finalize} */
+    uint64_t sha_bytes;
+    uint64_t m31_mul, m31_add, m31_neg, m31_inv;
+    uint64_t eq_256;
+    uint64_t point_from_index;
+    uint64_t draw_retries;
+} ssym_cost_t;
+/* Cost of verify_proof (stwo-verifier/src/verifier.simf:32-58) for one proof of configuration `cfg` whose transcript drew `queries`
+ * (cfg->n_queries words, e.g. ssym_stwo_trace_t.queries) and repeated `draw_retries` felt draws.  Host-only, no GPU involved. */
+int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *queries, uint32_t draw_retries, ssym_cost_t *out);
 
 /* ------------------------------------------------------------------------- */
 /* stark101 (stark101/src/verifier.simf:17-42)                                 */

@@ -60,7 +60,7 @@ class StwoTrace(C.Structure):
         ("mask_trace", C.c_uint32), ("mask_cp", C.c_uint32), ("mask_answer_inv", C.c_uint32),
         ("mask_fri", C.c_uint32 * 9), ("mask_fold_inv", C.c_uint32 * 9),
         ("mask_last_query", C.c_uint32), ("mask_last_eval", C.c_uint32),
-        ("pad_", C.c_uint32 * 3),
+        ("draw_retries", C.c_uint32), ("pad_", C.c_uint32 * 2),
     ]
 
 

@@ -83,6 +83,10 @@ static const uint32_t SHA_K[64] = {
 /* instrumentation (per thread, so that the multi-threaded CPU baseline does not bounce a shared cache line): compression-function calls and
  * M31 operations of the calling thread — the per-proof work figures of SURVEY.md section 8d come from these */
 static _Thread_local uint64_t g_compressions, g_m31_mul, g_m31_add, g_m31_inv;
+/* cost-model counters (tests/test_cost_model.py checks the product's closed-form model, csrc/cost.cpp, against these): calls of the
+ * sha_256_ctx_8_* jets, message bytes, unreduced negations (= subtract_32), eq_256, index -> point conversions, repeated felt draws */
+static _Thread_local uint64_t g_sha_init, g_sha_add_4, g_sha_add_8, g_sha_add_32, g_sha_finalize, g_sha_bytes, g_m31_neg, g_eq_256, g_point_from_index,
+    g_draw_retries;
 
 static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
@@ -165,6 +169,7 @@ static Ctx8 sha_256_ctx_8_init(void) {
     static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
     memcpy(c.h, iv, sizeof iv);
     c.len = 0;
+    g_sha_init++;
     return c;
 }
 static void ctx_add_byte(Ctx8 *c, uint8_t b) {
@@ -173,6 +178,7 @@ static void ctx_add_byte(Ctx8 *c, uint8_t b) {
     if (c->len % 64 == 0) sha_compress(c->h, c->buf);
 }
 static Ctx8 sha_256_ctx_8_add_4(Ctx8 c, uint32_t v) {
+    g_sha_add_4++;
     if (g_fast_sha && c.len % 4 == 0) { /* word-wise absorb: same bytes, one store */
         const uint32_t be = __builtin_bswap32(v);
         memcpy(c.buf + c.len % 64, &be, 4);
@@ -184,11 +190,15 @@ static Ctx8 sha_256_ctx_8_add_4(Ctx8 c, uint32_t v) {
     return c;
 }
 static Ctx8 sha_256_ctx_8_add_8(Ctx8 c, uint64_t v) {
+    g_sha_add_8++;
     for (int i = 7; i >= 0; i--) ctx_add_byte(&c, (uint8_t)(v >> (8 * i)));
     return c;
 }
 static Ctx8 sha_256_ctx_8_add_32(Ctx8 c, u256 v) {
+    g_sha_add_32++;
+    g_sha_add_4 -= 8; /* the literal path below feeds the eight words through sha_256_ctx_8_add_4: those are not jet calls of the program */
     if (g_fast_sha && c.len % 4 == 0 && c.len % 64 <= 32) { /* the 32 bytes fit the current block */
+        g_sha_add_4 += 8;
         uint32_t be[8];
         for (int i = 0; i < 8; i++) be[i] = __builtin_bswap32(v.w[i]);
         memcpy(c.buf + c.len % 64, be, 32);
@@ -201,6 +211,8 @@ static Ctx8 sha_256_ctx_8_add_32(Ctx8 c, u256 v) {
 }
 static u256 sha_256_ctx_8_finalize(Ctx8 c) {
     uint64_t bits = c.len * 8;
+    g_sha_finalize++;
+    g_sha_bytes += c.len;
     if (g_fast_sha) { /* FIPS 180-4 padding written block-wise */
         size_t at = c.len % 64;
         c.buf[at++] = 0x80;
@@ -224,7 +236,7 @@ static u256 sha_256_ctx_8_finalize(Ctx8 c) {
     memcpy(r.w, c.h, sizeof r.w);
     return r;
 }
-static int eq_256(u256 a, u256 b) { return memcmp(a.w, b.w, sizeof a.w) == 0; }
+static int eq_256(u256 a, u256 b) { g_eq_256++; return memcmp(a.w, b.w, sizeof a.w) == 0; }
 
 /* ========================================================================= */
 /* stwo-verifier                                                              */
@@ -243,7 +255,7 @@ static inline uint32_t m31_fold64(uint64_t x) {
 }
 static M31 m31(uint32_t v) { return g_fast_sha ? m31_fold64(v) : jet_modulo_32(v, M31_MODULUS); }                 /* m31.simf:17-19 */
 static M31 m31_add(M31 a, M31 b) { g_m31_add++; return m31(jet_add_32(a, b)); }     /* m31.simf:22-26 */
-static M31 m31_neg(M31 a) { return jet_subtract_32(M31_MODULUS, a); }               /* m31.simf:29-32 (unreduced) */
+static M31 m31_neg(M31 a) { g_m31_neg++; return jet_subtract_32(M31_MODULUS, a); }               /* m31.simf:29-32 (unreduced) */
 static M31 m31_sub(M31 a, M31 b) { return m31_add(a, m31_neg(b)); }                 /* m31.simf:35-37 */
 static M31 m31_mul(M31 a, M31 b) {                                                  /* m31.simf:40-45 */
     g_m31_mul++;
@@ -360,6 +372,7 @@ static M31Point m31_point_dbl(M31Point p) { /* m31_point.simf:49-55 */
 }
 static M31Point circle_point_index_to_m31_point(uint32_t index) { /* m31_point.simf:58-106: 32 LSB-first steps */
     M31Point res = m31_point_mk(1, 0), cur = m31_point_mk(2, 1268011823u);
+    g_point_from_index++;
     for (int bit = 0; bit < 32; bit++) {
         if ((index >> bit) & 1) res = m31_point_add(res, cur);
         cur = m31_point_dbl(cur);
@@ -512,6 +525,7 @@ static void channel_draw_m31xn(ChannelState *s, int n, M31 *out) { /* channel.si
     u256 v;
     for (int counter = 0; counter < 256; counter++) {
         v = channel_draw_u256(s);
+        if (counter) g_draw_retries++;
         if (is_uniform_n(v.w, n)) {
             for (int i = 0; i < n; i++) out[i] = m31(v.w[i]);
             return;
@@ -759,6 +773,7 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     if (oracle_stwo_layout(cfg, &lo) != 0) { tr->status = SSYM_ST_SHAPE; return; }
     const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
     uint32_t status = 0;
+    const uint64_t retries0 = g_draw_retries;
 
     u256 commitments[3];
     for (int i = 0; i < 3; i++) commitments[i] = load_u256(pk + lo.off_commit + 8 * i);
@@ -906,6 +921,7 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     }
     tr->status = status;
     tr->first_fail = first_fail_code(cfg, tr);
+    tr->draw_retries = (uint32_t)(g_draw_retries - retries0);
 }
 
 /* First failing assert in the reference's program order (verifier.simf:32-58), derived from the masks. */
@@ -964,6 +980,16 @@ EXPORT void oracle_compression_reset(void) { g_compressions = 0; }
 /* M31 operations of the calling thread since the last reset: out = {mul (those inside inversions included), add / sub, inversions} */
 EXPORT void oracle_field_op_counts(uint64_t out[3]) { out[0] = g_m31_mul; out[1] = g_m31_add; out[2] = g_m31_inv; }
 EXPORT void oracle_field_op_reset(void) { g_m31_mul = g_m31_add = g_m31_inv = 0; }
+/* Everything the cost model predicts, in the field order of ssym_cost_t (include/ssym.h), for the calling thread since the last reset. */
+EXPORT void oracle_cost_counts(uint64_t out[SSYM_COST_FIELDS]) {
+    const uint64_t v[SSYM_COST_FIELDS] = {g_compressions, g_sha_init, g_sha_add_4, g_sha_add_8, g_sha_add_32, g_sha_finalize, g_sha_bytes,
+                                          g_m31_mul, g_m31_add, g_m31_neg, g_m31_inv, g_eq_256, g_point_from_index, g_draw_retries};
+    memcpy(out, v, sizeof v);
+}
+EXPORT void oracle_cost_reset(void) {
+    g_compressions = g_sha_init = g_sha_add_4 = g_sha_add_8 = g_sha_add_32 = g_sha_finalize = g_sha_bytes = 0;
+    g_m31_mul = g_m31_add = g_m31_neg = g_m31_inv = g_eq_256 = g_point_from_index = g_draw_retries = 0;
+}
 
 /* ------------------------------------------------------------------------- */
 /* Function-level exports for the known-answer tests (ctypes)                 */

@@ -52,7 +52,7 @@ class StwoTrace(C.Structure):
         ("mask_trace", C.c_uint32), ("mask_cp", C.c_uint32), ("mask_answer_inv", C.c_uint32),
         ("mask_fri", C.c_uint32 * MAX_FRI_LAYERS), ("mask_fold_inv", C.c_uint32 * MAX_FRI_LAYERS),
         ("mask_last_query", C.c_uint32), ("mask_last_eval", C.c_uint32),
-        ("pad_", C.c_uint32 * 3),
+        ("draw_retries", C.c_uint32), ("pad_", C.c_uint32 * 2),
     ]
 
 
@@ -124,6 +124,19 @@ SYMBOLS = {
     "ssym_stwo_verify_wit_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _V, _I]),
     "ssym_stark101_verify_wit_batch": (_I, [_V, _V, _V, _SZ, _V, _V, _V, _I]),
 }
+
+COST_FIELDS = ("sha_compressions", "sha_init", "sha_add_4", "sha_add_8", "sha_add_32", "sha_finalize", "sha_bytes", "m31_mul", "m31_add", "m31_neg",
+               "m31_inv", "eq_256", "point_from_index", "draw_retries")  # ssym_cost_t, include/ssym.h
+
+
+class Cost(C.Structure):
+    _fields_ = [(name, C.c_uint64) for name in COST_FIELDS]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name in COST_FIELDS}
+
+
+SYMBOLS["ssym_stwo_cost"] = (_I, [C.POINTER(StwoConfig), _V, _U32, C.POINTER(Cost)])
 
 WIT_OK, WIT_SHAPE, WIT_PARSE = 0, 1, 2  # per-witness ingestion flags (include/ssym.h)
 

@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libssym.so")
 CLI = os.path.join(HERE, "bin", "verify-batch")
 
 CU_SOURCES = ["stwo_kernels.cu", "prover_kernels.cu", "s101_kernels.cu", "jets_kernels.cu", "wit_kernels.cu", "compact_kernels.cu", "api.cu"]
-CPP_SOURCES = ["witness.cpp"]
+CPP_SOURCES = ["witness.cpp", "cost.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
               "-Xptxas", "-v"]
 

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
     const uint32_t *pk[NP];
     uint32_t *ctx[NP];
     ssym_stwo_trace_t *tr[NP];
-    uint32_t status[NP], n_sent[NP], tries[NP], d[NP][8]; // channel_init channel.simf:31-33: ChannelState = (digest, n_sent) = (0, 0)
+    uint32_t status[NP], n_sent[NP], tries[NP], retries[NP], d[NP][8]; // channel_init channel.simf:31-33: ChannelState = (digest, n_sent) = (0, 0)
     bool exhausted[NP], settled[NP];
     QM31 felt[NP], oods_t[NP], deep_alpha[NP], cp_alpha[NP];
 #pragma unroll
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
         pk[k] = p.packed + (size_t)idx[k] * lo.stride_words;
         ctx[k] = p.ctx + (size_t)idx[k] * CX::WORDS;
         tr[k] = p.trace && live[k] ? p.trace + idx[k] : nullptr;
-        status[k] = 0; n_sent[k] = 0; tries[k] = 0;
+        status[k] = 0; n_sent[k] = 0; tries[k] = 0; retries[k] = 0;
         exhausted[k] = false; settled[k] = false;
         felt[k] = oods_t[k] = deep_alpha[k] = cp_alpha[k] = qm31_zero();
 #pragma unroll
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
                 const bool ok = h[k][0] < 4294967294u && h[k][1] < 4294967294u && h[k][2] < 4294967294u && h[k][3] < 4294967294u;
                 tries[k]++;
                 if (ok || tries[k] == 256) {
+                    retries[k] += tries[k] - 1u;
                     settled[k] = true;
                     exhausted[k] = exhausted[k] || !ok;
                     felt[k] = qm31(m31_reduce(h[k][0]), m31_reduce(h[k][1]), m31_reduce(h[k][2]), m31_reduce(h[k][3]));
@@ -315,6 +316,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
         uint32_t st = status[k];
         if (exhausted[k]) st |= SSYM_ST_DRAW_EXHAUSTED;
         if (p.cfg.mode == SSYM_MODE_REF_LITERAL && ((G - (L + 1u)) & 0xff) != 0) st |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
+        if (tr[k]) tr[k]->draw_retries = retries[k];
         stwo_scalars(p, idx[k], oods_t[k], cp_alpha[k], deep_alpha[k], st);
     }
 }

@@ -9,7 +9,11 @@
 // INTEGRATION.md shows the Rust binding.)
 //
 //   verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--mode {ref-literal,prover-consistent}]
-//                (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet] [--host-pack]
+//                (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--cost] [--quiet] [--host-pack]
+//
+// --cost (stwo): after verifying, prints what the reference PROGRAM executes per proof — sha_256_ctx_8_* jet calls and compressions, M31
+// multiplications / additions / inversions, eq_256 — from the cost model of include/ssym.h (ssym_stwo_cost) fed with the queries each
+// transcript drew; the dynamic counterpart of the `Node bounds` line `simfony run` prints (simfony-cli/src/main.rs:193-203).
 //
 // Witnesses are tokenised and packed ON THE GPU (ssym_stwo_verify_wit_batch / ssym_stark101_verify_wit_batch: the `.wit` text is what crosses
 // PCIe); --host-pack (and --trace, which needs the packed records on the host) uses the host parser + the packed-batch entry points instead.
@@ -41,7 +45,7 @@ static bool read_file(const std::string &path, std::string &out) {
 static void usage() {
     fprintf(stderr,
             "usage: verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--columns {4,8,16}] [--mode {ref-literal,prover-consistent}]\n"
-            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--quiet] [--host-pack]\n");
+            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--cost] [--quiet] [--host-pack]\n");
 }
 
 static std::string hex_digest(const uint32_t *w) {
@@ -61,7 +65,7 @@ int main(int argc, char **argv) {
     size_t replicate = 1;
     int gpus = 1;
     uint32_t columns = SSYM_NUM_COLUMNS; // NUM_COLUMNS of the program the witnesses were made for (config.simf:14)
-    bool quiet = false, host_pack = false;
+    bool quiet = false, host_pack = false, want_cost = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](const char *what) -> std::string {
@@ -80,6 +84,7 @@ int main(int argc, char **argv) {
         else if (a == "--columns") columns = (uint32_t)strtoul(next("--columns").c_str(), nullptr, 10);
         else if (a == "--trace") trace_path = next("--trace");
         else if (a == "--quiet") quiet = true;
+        else if (a == "--cost") want_cost = true;
         else if (a == "--host-pack") host_pack = true;
         else if (a == "--help" || a == "-h") { usage(); return 0; }
         else { fprintf(stderr, "Error: unknown argument %s\n", a.c_str()); usage(); return 2; }
@@ -103,7 +108,8 @@ int main(int argc, char **argv) {
     const size_t n_files = witnesses.size(), n = n_files * replicate;
     std::vector<uint8_t> parse_reject(n_files, 0); // ill-typed or ill-shaped witness: simfony would refuse it -> reject
     std::vector<uint32_t> accept((n + 31) / 32, 0), status(n, 0);
-    const bool want_trace = !trace_path.empty();
+    if (want_cost && program != "stwo") { fprintf(stderr, "Error: --cost models the stwo program only\n"); return 2; }
+    const bool want_trace = !trace_path.empty() || want_cost; // the cost model needs the queries each transcript drew
     auto t0 = std::chrono::steady_clock::now();
 
     ssym_stwo_config_t cfg{};
@@ -234,7 +240,31 @@ int main(int argc, char **argv) {
     fprintf(stderr, "verify-batch: %zu proofs, %zu accepted, %zu rejected; %s %.3f s, %s (%d GPU%s, host buffers) %.3f s\n", n, n_accept,
             n - n_accept, gpu_ingest ? "read" : "parse+pack", pack_s, gpu_ingest ? "tokenise+pack+verify" : "verify", gpus, gpus > 1 ? "s" : "", gpu_s);
 
-    if (want_trace) {
+    if (want_cost) {
+        static const char *const names[SSYM_COST_FIELDS] = {"sha_compressions", "sha_init", "sha_add_4", "sha_add_8", "sha_add_32", "sha_finalize", "sha_bytes",
+                                                            "m31_mul", "m31_add", "m31_neg", "m31_inv", "eq_256", "point_from_index", "draw_retries"};
+        uint64_t total[SSYM_COST_FIELDS] = {0};
+        for (size_t i = 0; i < n; i++) {
+            ssym_cost_t c;
+            if (parse_reject[i % n_files] || ssym_stwo_cost(&cfg, traces[i].queries, traces[i].draw_retries, &c) != SSYM_OK) continue;
+            const uint64_t *v = reinterpret_cast<const uint64_t *>(&c);
+            if (!quiet) printf("cost %s", witnesses[i % n_files].c_str());
+            for (int k = 0; k < SSYM_COST_FIELDS; k++) {
+                total[k] += v[k];
+                if (!quiet) printf(" %s=%llu", names[k], (unsigned long long)v[k]);
+            }
+            if (!quiet) printf("\n");
+        }
+        fprintf(stderr, "verify-batch: program cost over %zu proofs (what verify_proof executes, run to its end):", n);
+        for (int k = 0; k < SSYM_COST_FIELDS; k++) fprintf(stderr, " %s=%llu", names[k], (unsigned long long)total[k]);
+        // the jets underneath the field functions (fields/m31.simf:22-45,117-132)
+        fprintf(stderr, "\nverify-batch: as jets: multiply_32=%llu modulo_64=%llu add_32=%llu modulo_32=%llu subtract_32=%llu is_zero_32=%llu eq_256=%llu "
+                        "sha_256_ctx_8_{init=%llu,add_4=%llu,add_8=%llu,add_32=%llu,finalize=%llu}\n",
+                (unsigned long long)total[7], (unsigned long long)total[7], (unsigned long long)total[8], (unsigned long long)total[8], (unsigned long long)total[9],
+                (unsigned long long)total[10], (unsigned long long)total[11], (unsigned long long)total[1], (unsigned long long)total[2], (unsigned long long)total[3],
+                (unsigned long long)total[4], (unsigned long long)total[5]);
+    }
+    if (!trace_path.empty()) {
         std::ofstream o(trace_path);
         o << "[\n";
         for (size_t i = 0; i < n; i++) {

@@ -287,6 +287,36 @@ def test_cli_gpu_ingestion_matches_host_pack(S, tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_cost_output_equals_oracle_counters(S, tmp_path):
+    """verify-batch --cost: the per-proof program cost printed by the CLI — the closed-form model of csrc/cost.cpp fed with
+    the queries the GPU transcript drew — equals the oracle's counters for that proof, field by field, in both semantics and both presets."""
+    import ctypes as C
+    import subprocess
+
+    from conftest import ROOT
+    from test_oracle_fixtures import load_stwo
+
+    cli = os.path.join(ROOT, "stark-symphony_b200", "bin", "verify-batch")
+    orc = O.Oracle()
+    for preset in ("testing", "prod"):
+        for mode_name, mode in (("ref-literal", O.MODE_REF_LITERAL), ("prover-consistent", O.MODE_PROVER_CONSISTENT)):
+            wit = os.path.join(GOLDEN, f"stwo_proof_{preset}.wit")
+            r = subprocess.run([cli, "--program", "stwo", "--preset", preset, "--mode", mode_name, "--witness", wit, "--replicate", "3", "--cost"], capture_output=True, text=True)
+            assert r.returncode == (0 if mode == O.MODE_PROVER_CONSISTENT else 1), r.stderr
+            lines = [l for l in r.stdout.splitlines() if l.startswith("cost ")]
+            assert len(lines) == 3 and len(set(lines)) == 1
+            got = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in lines[0].split()[2:]}
+            want = (C.c_uint64 * 14)()
+            orc.lib.oracle_cost_reset()
+            orc.stwo_verify_batch(O.make_config(preset, mode), load_stwo(preset), 1)
+            orc.lib.oracle_cost_counts(want)
+            assert [got[k] for k in S._lib.COST_FIELDS] == [int(x) for x in want], (preset, mode_name)
+            assert "as jets: multiply_32=" in r.stderr
+    r = subprocess.run([cli, "--program", "stark101", "--witness", os.path.join(GOLDEN, "stark101_proof.wit"), "--cost"], capture_output=True, text=True)
+    assert r.returncode == 2 and "models the stwo program only" in r.stderr
+
+
+@pytest.mark.gpu
 def test_wit_batch_edge_cases(S):
     cfg = S.stwo_config("testing", S.MODE_PROVER_CONSISTENT)
     text = open(os.path.join(GOLDEN, "stwo_proof_testing.wit")).read()
