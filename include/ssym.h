@@ -267,6 +267,12 @@ int ssym_set_pipeline_depth(ssym_ctx_t *ctx, int depth);
  * then overlap (the H2D of call k+1 runs under the kernel tail of call k), and every output is valid after ssym_synchronize.
  * The caller's buffers must be pinned (cudaHostAlloc / torch pin_memory) and must not be touched until then. */
 int ssym_set_host_async(ssym_ctx_t *ctx, int on);
+/* Witness texts the GPU tokeniser does not keep on its fast path (JSON escapes, `_` separators, upper-case hex, redundant parentheses,
+ * another list length, anything malformed) are re-read by the host parser, whose verdict is the call's (default, on = 1).  on = 0
+ * makes ssym_stwo_*_wit_batch / ssym_stark101_verify_wit_batch GPU-only: such a witness keeps the flag SSYM_WIT_SLOW and is reported as
+ * rejected without any host parsing — a strict mode for inputs known to come from the reference's generators, and how the tests see
+ * which formattings stay on the GPU. */
+int ssym_set_wit_host_fallback(ssym_ctx_t *ctx, int on);
 /* Merkle schedule of ssym_stwo_verify_batch.  The reference hashes every query's path to the root on its own (merkle.simf:39-44); paths of
  * one tree that have met run through the same nodes from there on.  policy 0: one hash chain per query, as the reference; 2: every distinct
  * node is hashed once and a query takes over another's nodes only after a bitwise comparison of everything its own computation would have
@@ -441,7 +447,8 @@ int ssym_s101_pack_wit(const char *json_text, size_t len, uint32_t *out, size_t 
 #define SSYM_WIT_OK 0    /* packed                                                              */
 #define SSYM_WIT_SHAPE 1 /* well-typed but ill-shaped (= *shape_reject of ssym_stwo_pack_wit)     */
 #define SSYM_WIT_PARSE 2 /* not a witness of the program's types (= SSYM_ERR_PARSE)              */
-#define SSYM_WIT_SLOW 3  /* internal: text outside the GPU tokeniser's fast path, re-parsed on the host before the call returns */
+#define SSYM_WIT_SLOW 3  /* text outside the GPU tokeniser's fast path: re-parsed on the host before the call returns, so never seen by callers unless
+                            ssym_set_wit_host_fallback(ctx, 0) */
 
 /* n `.wit` JSON texts (the files `simfony run --witness` reads, simfony-cli/src/main.rs:77-81; witness i = bytes
  * [offsets[i], offsets[i+1]) of `text`) -> n packed proofs, tokenised and packed ON THE GPU (one CTA per witness,

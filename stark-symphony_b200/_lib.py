@@ -81,6 +81,7 @@ SYMBOLS = {
     "ssym_set_pipeline_depth": (_I, [_V, _I]),
     "ssym_join": (_I, [_V]),
     "ssym_set_host_async": (_I, [_V, _I]),
+    "ssym_set_wit_host_fallback": (_I, [_V, _I]),
     "ssym_set_merkle_sharing": (_I, [_V, _I]),
     "ssym_launch_count": (C.c_uint64, [_V]),
     "ssym_profile_enable": (_I, [_V, _I]),

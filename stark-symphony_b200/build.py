@@ -51,7 +51,12 @@ def _compile(src: str) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> str:
+    """tuning=True adds -DSSYM_TUNING: every kernel variant of the experiments DESIGN.md section 4 reports (SSYM_ADDMODE, SSYM_ROLLED, SSYM_CHANNEL_NP,
+    SSYM_FRONT, SSYM_M31_INV_K environment switches).  The release library has none of them."""
+    if tuning and "-DSSYM_TUNING" not in NVCC_FLAGS:
+        NVCC_FLAGS.append("-DSSYM_TUNING")
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
     stale = force or not os.path.exists(LIB) or not os.path.exists(CLI) or min(os.path.getmtime(LIB), os.path.getmtime(CLI)) < _deps_mtime()
@@ -72,4 +77,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tuning="--tuning" in sys.argv))

@@ -110,6 +110,7 @@ struct ssym_ctx {
     int depth = 1;
     uint64_t calls = 0;
     bool host_async = false;  // ssym_set_host_async: SSYM_MEM_HOST stwo calls return after enqueueing
+    bool wit_host_fallback = true; // ssym_set_wit_host_fallback: witnesses the GPU tokeniser hands back are re-read by the host parser
     uint64_t host_chunks = 0; // staging-buffer parity persists across calls so that asynchronous calls can overlap
     // domain tables (per config)
     DevBuf tab_point, tab_fold, tab_flag;
@@ -377,7 +378,11 @@ static int ensure_lane_scratch(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stw
 
 static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, const uint32_t *d_packed,
                              size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s, bool use_front = false) {
+#ifdef SSYM_TUNING // experiment builds only: which of K1 / K2 run on the lane's high-priority stream (0 none, 1 K1, 2 both)
     static const int front_kernels = [] { const char *e = getenv("SSYM_FRONT"); return e ? atoi(e) : 2; }();
+#else
+    const int front_kernels = 2;
+#endif
     int rc = ensure_lane_scratch(c, lane, cfg, n, d_status_out == nullptr);
     if (rc) return rc;
     for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
@@ -528,6 +533,12 @@ extern "C" int ssym_set_merkle_sharing(ssym_ctx_t *c, int policy) {
     int rc = ssym_synchronize(c);
     if (rc) return rc;
     c->merkle_sharing = policy;
+    return SSYM_OK;
+}
+
+extern "C" int ssym_set_wit_host_fallback(ssym_ctx_t *c, int on) {
+    if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
+    c->wit_host_fallback = on != 0;
     return SSYM_OK;
 }
 
@@ -997,8 +1008,8 @@ static int wit_batch(ssym_ctx *c, const ssym_stwo_config_t *cfg, const char *tex
             *txt = slow_text.data();
             return SSYM_OK;
         };
-        int r = getenv("SSYM_WIT_DEBUG_NOSLOW") ? SSYM_OK /* tests: expose which witnesses left the fast path */
-                                                : wit_slow_path(*cfg, lo, hf, k.m, text_of, d_packed, d_flags, s);
+        int r = c->wit_host_fallback ? wit_slow_path(*cfg, lo, hf, k.m, text_of, d_packed, d_flags, s)
+                                     : SSYM_OK; /* ssym_set_wit_host_fallback(0): a witness off the fast path keeps its SSYM_WIT_SLOW flag */
         if (r) return r;
         if (verify) {
             r = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, d_packed, k.m, d_accept + k.beg / 32, d_status + k.beg, nullptr, s);
@@ -1270,7 +1281,7 @@ extern "C" int ssym_stark101_verify_wit_batch(ssym_ctx_t *c, const char *text, c
     for (size_t i = 0; i < n; i++) {
         if (h_flags[i] == SSYM_WIT_OK) continue;
         const uint32_t *src = zero.data();
-        if (have_shape && !getenv("SSYM_WIT_DEBUG_NOSLOW")) {
+        if (have_shape && c->wit_host_fallback) {
             const char *txt;
             size_t len, words = rec.size();
             rc = host_text(i, &txt, &len);

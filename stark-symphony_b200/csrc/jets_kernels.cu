@@ -224,10 +224,13 @@ int launch_field_jet(int op, const uint32_t *a, const uint32_t *b, uint32_t *out
     case JET_M31_MUL: m31_binary_kernel<JET_M31_MUL><<<g4, 256, 0, s>>>(a, b, out, n); break;
     case JET_M31_NEG: m31_binary_kernel<JET_M31_NEG><<<g4, 256, 0, s>>>(a, a, out, n); break;
     case JET_M31_INV: {
+#ifdef SSYM_TUNING // experiment builds only: batch size of the shared inversion (8 / 16 / 32 elements per addition chain)
         static const int k = [] { const char *e = getenv("SSYM_M31_INV_K"); return e ? atoi(e) : M31_INV_K; }();
         if (k == 32) m31_inv_kernel<32><<<stream_grid((n + 31) / 32, 256), 256, 0, s>>>(a, out, fail, n);
         else if (k == 8) m31_inv_kernel<8><<<stream_grid((n + 7) / 8, 256), 256, 0, s>>>(a, out, fail, n);
-        else m31_inv_kernel<16><<<stream_grid((n + 15) / 16, 256), 256, 0, s>>>(a, out, fail, n);
+        else
+#endif
+            m31_inv_kernel<M31_INV_K><<<stream_grid((n + M31_INV_K - 1) / M31_INV_K, 256), 256, 0, s>>>(a, out, fail, n);
         break;
     }
     case JET_CM31_MUL: ext_kernel<JET_CM31_MUL><<<g1, 256, 0, s>>>(a, b, out, fail, n); break;

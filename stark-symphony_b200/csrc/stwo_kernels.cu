@@ -1043,9 +1043,12 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     {
         // NP = 2 (two transcripts per thread in lockstep) raises a warp's issue rate from 0.34 to 0.46 per cycle, but a batch of 1024 proofs has
         // fewer warps than the GPU has schedulers: the launch takes 0.211 ms instead of 0.143 ms.  A knob for very large batches only.
+#ifdef SSYM_TUNING // experiment builds only (build.py --tuning): SSYM_CHANNEL_NP=2 runs two transcripts per thread
         static const int np = [] { const char *e = getenv("SSYM_CHANNEL_NP"); return e ? atoi(e) : 1; }();
         if (np == 2 && p.n > 1) stwo_channel_kernel<2><<<((p.n + 1) / 2 + 63) / 64, 64, 0, s1>>>(p, sha_mul_consts());
-        else stwo_channel_kernel<1><<<(p.n + 63) / 64, 64, 0, s1>>>(p, sha_mul_consts());
+        else
+#endif
+            stwo_channel_kernel<1><<<(p.n + 63) / 64, 64, 0, s1>>>(p, sha_mul_consts());
     }
     if (use_front && front_kernels < 2) { cudaEventRecord(front_done, front); cudaStreamWaitEvent(s, front_done, 0); }
     if (prof) { prof->end(0, s); prof->begin(1, s); }
@@ -1077,11 +1080,13 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     if (prof) { prof->end(1, s); prof->begin(2, s); }
     const uint32_t groups = (items + 31) / 32;
     const uint64_t warps = (uint64_t)groups * (L + 3);
-    // tuning knobs (sha256.cuh): which adds go to the FMA pipe, and whether the 64 rounds are rolled into 4 x 16
-    static const int addmode = [] { const char *e = getenv("SSYM_ADDMODE"); return e ? atoi(e) : SSYM_DEFAULT_ADDMODE; }();
-    static const int rolled = [] { const char *e = getenv("SSYM_ROLLED"); return e ? atoi(e) : SSYM_DEFAULT_ROLLED; }();
     const uint32_t grid = (uint32_t)((warps + 3) / 4);
 #define SSYM_LAUNCH_MERKLE(AM, RL) stwo_merkle_kernel<AM, RL><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts())
+#ifdef SSYM_TUNING
+    // experiment builds only (build.py --tuning; sha256.cuh): which adds go to the FMA pipe, and whether the 64 rounds are rolled into 4 x 16.
+    // The release library contains the one variant DESIGN.md section 4 arrives at.
+    static const int addmode = [] { const char *e = getenv("SSYM_ADDMODE"); return e ? atoi(e) : SSYM_DEFAULT_ADDMODE; }();
+    static const int rolled = [] { const char *e = getenv("SSYM_ROLLED"); return e ? atoi(e) : SSYM_DEFAULT_ROLLED; }();
     switch (addmode * 2 + (rolled ? 1 : 0)) { // the multipliers (1, 2^k) must stay opaque to ptxas
     case 1: SSYM_LAUNCH_MERKLE(0, true); break;
     case 2: SSYM_LAUNCH_MERKLE(1, false); break;
@@ -1096,6 +1101,9 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     case 15: SSYM_LAUNCH_MERKLE(7, true); break;
     default: SSYM_LAUNCH_MERKLE(0, false); break;
     }
+#else
+    SSYM_LAUNCH_MERKLE(SSYM_DEFAULT_ADDMODE, SSYM_DEFAULT_ROLLED != 0);
+#endif
     if (prof) { prof->end(2, s); prof->begin(3, s); }
     stwo_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
     if (prof) prof->end(3, s);

@@ -89,6 +89,11 @@ class Verifier:
         after synchronize().  Buffers must be pinned."""
         check(self.lib.ssym_set_host_async(self.h, 1 if on else 0))
 
+    def set_wit_host_fallback(self, on: bool) -> None:
+        """on=False: `.wit` texts the GPU tokeniser does not keep on its fast path are flagged WIT_SLOW (= rejected) instead of being re-read
+        by the host parser (ssym_set_wit_host_fallback, include/ssym.h)."""
+        check(self.lib.ssym_set_wit_host_fallback(self.h, 1 if on else 0))
+
     def set_merkle_sharing(self, policy: int) -> None:
         """0: one hash chain per query (the reference's schedule); 2: paths of a tree share the nodes above their meeting point; 1 (default):
         2 under MODE_PROVER_CONSISTENT, 0 under MODE_REF_LITERAL (ssym_set_merkle_sharing, include/ssym.h)."""

@@ -206,18 +206,19 @@ def test_gpu_tokeniser_matches_host_parser(S, preset):
 
 @pytest.mark.gpu
 def test_gpu_tokeniser_fast_path_is_taken(S):
-    """The generator's formatting must not fall back to the host parser: SSYM_WIT_DEBUG_NOSLOW makes the slow path an error flag."""
+    """The generator's formatting must not fall back to the host parser: with ssym_set_wit_host_fallback(0) a witness that leaves the fast path
+    keeps its flag."""
     cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
     text = open(os.path.join(GOLDEN, "stwo_proof_prod.wit")).read()
     ver = S.Verifier(0)
-    os.environ["SSYM_WIT_DEBUG_NOSLOW"] = "1"
+    ver.set_wit_host_fallback(False)
     try:
         good = _variants(text)
         blob, offsets = S.witness.concat_wit_texts([t for _, t, _ in good])
         _, flags = ver.stwo_pack_wit_batch(blob, offsets, cfg)
         assert [int(f) == 0 for f in flags] == [fast for _, _, fast in good], list(zip([g[0] for g in good], flags))
     finally:
-        del os.environ["SSYM_WIT_DEBUG_NOSLOW"]
+        ver.set_wit_host_fallback(True)
     ver.close()
 
 
@@ -403,11 +404,11 @@ def test_stark101_wit_on_gpu(S):
         acc_list, st = ver.run_stark101_wit(texts)
         assert acc_list == [bool(x == 0) for x in o_status]
     # which variants stay on the GPU
-    os.environ["SSYM_WIT_DEBUG_NOSLOW"] = "1"
+    ver.set_wit_host_fallback(False)
     try:
         tblob, toffs = S.witness.concat_wit_texts([t for _, t, _ in good])
         _, _, flags = ver.stark101_verify_wit_batch(tblob, toffs, want_flags=True)
         assert [int(f) == 0 for f in flags] == [fast for _, _, fast in good], list(zip([g[0] for g in good], flags))
     finally:
-        del os.environ["SSYM_WIT_DEBUG_NOSLOW"]
+        ver.set_wit_host_fallback(True)
     ver.close()

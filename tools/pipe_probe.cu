@@ -1,4 +1,4 @@
-// Scratch microbenchmark: can IMAD (FMA pipe) co-issue with SHF/LOP3 (ALU pipe) on sm_100?
+// Pipe microbenchmark (nvcc -arch=sm_100a tools/pipe_probe.cu; cited by DESIGN.md section 4): can IMAD (FMA pipe) co-issue with SHF/LOP3 (ALU pipe) on sm_100?
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
