@@ -677,6 +677,11 @@ def main():
             })
         else:
             roof.update({"achieved": None, "frac": None, "traffic": None, "counts_source": "profiles/step_pipe_counts.json missing"})
+        other_counts = load_pipe_counts(other_name)
+        other_frac = None
+        if other_counts:
+            o_alu = sum(k.get("alu_pipe_warp_inst", 0.0) for k in other_counts["kernels"].values()) * n / other_counts["proofs_per_launch"]
+            other_frac = o_alu / (other_ms / (other_steps * R) * 1e-3) / warp_peak
         roof["hbm"] = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak if hbm_peak else None,
                        "algorithmic_bytes_per_launch": n * ALG_BYTES_PER_PROOF, "peak_source": peak_src,
                        "note": "not the binding resource: 170 integer ops per byte"}
@@ -686,6 +691,7 @@ def main():
         line.update({
             "other_mode": {"mode": other_name, "value": other_value, "unit": "proofs/s", "steps": other_steps, "accepted_per_gpu": other_accepted,
                            "kernel_ms": {k: v[0] / max(v[1], 1) for k, v in prof_by_mode[other_name].items()}, "serial_ms_per_pass": serial_ms[other_name],
+                           "whole_step_frac_int32_alu": other_frac,
                            "note": "same pipelined loop, same batch, the other semantics switch; under prover-consistent the fixture is ACCEPTED and the Merkle paths "
                                    "of a tree share the nodes above the height where they meet (hashed once, results per query identical: DESIGN.md section 4), "
                                    "so fewer compressions are executed than the reference's per-query count"},

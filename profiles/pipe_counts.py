@@ -6,7 +6,7 @@
       python bench.py --steps 1 --warmup 1 --passes 4 --pipeline 1 --no-cpu-baseline --no-configs --headline-only [--mode prover-consistent]
   python profiles/pipe_counts.py profiles/r02_step_metrics.csv [profiles/r02_shared_step_metrics.csv] --proofs 1024[,8192] -o profiles/step_pipe_counts.json
 
-Per kernel (name without template / argument list): the MEDIAN over its launches of warp instructions executed, ALU-pipe and FMA-heavy-pipe warp
+Per kernel (name without template / argument list): the MEDIAN over the captured passes of warp instructions executed, ALU-pipe and FMA-heavy-pipe warp
 instructions, DRAM bytes, and the (cold-cache, serialised) duration under ncu.  Instruction counts do not depend on clocks or on the profiler, which
 is why they may be measured once per build and divided by the CUDA-event time of a live run; durations under ncu are only good for shares."""
 import argparse
@@ -53,13 +53,23 @@ def parse(path):
     by_kernel = defaultdict(list)
     for (_, name, grid, block), m in sorted(per_launch.items()):
         by_kernel[kernel_base(name)].append(dict(m, full_name=name, grid=grid, block=block))
+    # A pass launches stwo_finalize_kernel exactly once; a kernel launched several times per pass (the two rounds of stwo_merkle_shared_kernel)
+    # is reported as its per-pass TOTAL, so that "sum over kernels" is the pass.
+    passes = max(1, len(by_kernel.get("stwo_finalize_kernel", [])) or 1)
     out = {}
     for k, launches in by_kernel.items():
-        rec = {"launches_seen": len(launches), "full_name": launches[0]["full_name"], "grid": launches[-1]["grid"], "block": launches[-1]["block"]}
+        per_pass = max(1, round(len(launches) / passes))
+        rec = {"launches_seen": len(launches), "launches_per_pass": per_pass, "full_name": launches[0]["full_name"], "grid": launches[0]["grid"],
+               "block": launches[0]["block"]}
         for key in METRICS.values():
             vals = [l[key] for l in launches if key in l]
-            if vals:
+            if not vals:
+                continue
+            if per_pass == 1:
                 rec[key] = statistics.median(vals)
+            else:  # launches of one pass are consecutive: median over passes of the per-pass sum
+                sums = [sum(vals[j:j + per_pass]) for j in range(0, len(vals) - per_pass + 1, per_pass)]
+                rec[key] = statistics.median(sums)
         out[k] = rec
     return out
 

@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(64) s101_transcript_kernel(S101Params p) {
     uint32_t *ctx = p.ctx + (size_t)i * S101_CTX_WORDS;
     ssym_s101_trace_t *tr = p.trace ? p.trace + i : nullptr;
     // The record's own length word is trusted only after it has been compared with the offsets array (a device-resident caller may hand over
-    // anything): nothing of the record is read before that, and every later read stays below `total`.
+    // anything): nothing of the record is read before that, and every later read stays below `total` <= the record's slot.  (A record may be
+    // shorter than its slot: the `.wit` path packs into fixed-stride slots.)
     const uint64_t len = p.offsets[i + 1] - p.offsets[i];
-    bool shape_ok = p.offsets[i + 1] >= p.offsets[i] && len >= 20 && len <= 0xffffffffull && rec[0] == (uint32_t)len;
+    bool shape_ok = p.offsets[i + 1] >= p.offsets[i] && len >= 20 && len <= 0xffffffffull && rec[0] <= (uint32_t)len;
     const uint32_t total = shape_ok ? rec[0] : 0, n_layers = shape_ok ? rec[1] : 0;
     const uint32_t ns0 = shape_ok ? rec[2] : 0, ns1 = shape_ok ? rec[3] : 0, ns2 = shape_ok ? rec[4] : 0;
     shape_ok = shape_ok && n_layers <= SSYM_S101_MAX_LIST && ns0 <= SSYM_S101_MAX_LIST && ns1 <= SSYM_S101_MAX_LIST && ns2 <= SSYM_S101_MAX_LIST;
