@@ -530,18 +530,29 @@ def main():
     pinned.numpy()[:] = host_batch.view(np.int32)
     host_view = pinned.numpy().view(np.uint32)
 
-    # compact transport form (include/ssym.h): produced by the host packer OUTSIDE the timed region; its cost is reported
+    # compact transport form (include/ssym.h), version 3: produced OUTSIDE the timed region by ssym_stwo_compact_pack_gpu (the GPU finds the
+    # siblings that are nodes of other queries' paths, the host assembles the records); its cost is reported.  Records with derived siblings are
+    # bound to the semantics they were packed under, so each mode gets its own blob.
     bound_words = int(S.load().ssym_stwo_compact_bound(C.byref(cfg), n))
-    c_pinned = torch.empty(bound_words, dtype=torch.int32).pin_memory()
-    S.witness.compact_stwo(host_batch, cfg, out=c_pinned.numpy().view(np.uint32))  # warm (page faults of the output)
+
+    def pack_compact(c):
+        pinned_buf = torch.empty(bound_words, dtype=torch.int32).pin_memory()
+        S.witness.compact_stwo(host_batch, c, out=pinned_buf.numpy().view(np.uint32), ver=ver)  # warm (page faults of the output)
+        t0 = time.perf_counter()
+        full, off_np = S.witness.compact_stwo(host_batch, c, out=pinned_buf.numpy().view(np.uint32), ver=ver)
+        secs = time.perf_counter() - t0
+        words = int(off_np[n])
+        off_t = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+        off_t.numpy()[:] = off_np.view(np.int64)
+        return {"pinned": pinned_buf, "blob": full[:words], "words": words, "off": off_t, "off_view": off_t.numpy().view(np.uint64), "pack_s": secs,
+                "derived_per_proof": int(full[4]) if int(full[2]) == 0x33435353 else 0}
+
+    cp = pack_compact(cfg)
+    cp_other = pack_compact(cfg_other)
     t0 = time.perf_counter()
-    c_blob_full, c_off_np = S.witness.compact_stwo(host_batch, cfg, out=c_pinned.numpy().view(np.uint32))
-    pack_s = time.perf_counter() - t0
-    c_words = int(c_off_np[n])
-    c_blob = c_blob_full[:c_words]
-    c_off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
-    c_off.numpy()[:] = c_off_np.view(np.int64)
-    c_off_view = c_off.numpy().view(np.uint64)
+    S.witness.compact_stwo(host_batch, cfg)  # version 2: host only (no hashing), for comparison
+    pack_v2_s = time.perf_counter() - t0
+    c_pinned, c_blob, c_words, c_off, c_off_view, pack_s = cp["pinned"], cp["blob"], cp["words"], cp["off"], cp["off_view"], cp["pack_s"]
 
     def host_leg(call, nbytes):
         """-> (async proofs/s, sync proofs/s, launches per pass, plain-copy GB/s alone, plain-copy GB/s with all ranks copying) for one host-buffer entry point."""
@@ -597,6 +608,9 @@ def main():
 
     c_bytes = c_words * 4 + c_off.numpy().nbytes
     c_value, c_sync, c_launches, bits_c = host_leg(lambda acc: ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc), c_bytes)
+    co_bytes = cp_other["words"] * 4 + cp_other["off"].numpy().nbytes
+    co_value, co_sync, _, bits_co = host_leg(lambda acc: ver.stwo_verify_compact_batch(cp_other["blob"], cp_other["off_view"], cfg_other, accept_out=acc), co_bytes)
+    assert int(np.unpackbits(bits_co.view(np.uint8), bitorder="little")[:n].sum()) == (n if other_mode == S.MODE_PROVER_CONSISTENT else 0)
     p_bytes = n * lo.stride_words * 4
     p_value, p_sync, p_launches, bits_p = host_leg(lambda acc: ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc), p_bytes)
     assert (bits_c == bits_p).all() and (np.unpackbits(bits_p.view(np.uint8), bitorder="little")[:n] == bits[:n]).all(), "host legs disagree with the device leg"
@@ -702,13 +716,23 @@ def main():
                     "frac_of_concurrent_copy": (c_value / world * c_bytes / n / 1e9) / max(min(r[1] for r in conc_ranks), 1e-9),
                     "sync_call_value": c_sync, "bytes_per_proof": c_words * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
                     "gpu_launches_per_pass": c_launches,
-                    "host_pack": {"proofs_per_s_per_core": n / pack_s, "seconds_per_1024": pack_s, "inside_timed_region": False,
-                                  "note": "ssym_stwo_compact_pack (one host thread) turns packed records into the compact form BEFORE the clock starts; a producer that "
-                                          "emits compact records directly pays nothing, one that holds packed records pays this per core"},
+                    "derived_siblings_per_proof": cp["derived_per_proof"],
+                    "host_pack": {"proofs_per_s": n / pack_s, "seconds_per_1024": pack_s, "inside_timed_region": False,
+                                  "version2_host_only_proofs_per_s_per_core": n / pack_v2_s,
+                                  "note": "ssym_stwo_compact_pack_gpu turns packed records into version 3 compact records BEFORE the clock starts: H2D of the packed "
+                                          "records, the verifier's kernels in scan mode (which siblings are nodes of other paths), D2H of one byte per sibling slot, "
+                                          "assembly on one host thread.  A producer that emits compact records directly (a prover: it holds the trees) pays nothing; "
+                                          "version 2 records (no hashing, host only: ssym_stwo_compact_pack) cost `version2_host_only_proofs_per_s_per_core`"},
+                    "other_mode": {"mode": other_name, "value": co_value, "sync_call_value": co_sync, "bytes_per_proof": cp_other["words"] * 4 / n,
+                                   "derived_siblings_per_proof": cp_other["derived_per_proof"], "h2d_gbs_achieved": co_value / world * co_bytes / n / 1e9,
+                                   "note": "the same leg under the other semantics.  Which siblings can be left out depends on the proof being consistent with the "
+                                           "verifier: under ref-literal the fixture's FRI evaluations are not the ones its FRI trees were built from (finding F1, "
+                                           "DESIGN.md section 1), so only the trace and composition trees have derivable siblings; under prover-consistent all "
+                                           "eleven trees do and the record is the size of upstream stwo's minimal decommitment"},
                     "e2e_packed_value": p_value,
                     "note": "ssym_stwo_verify_compact_batch(SSYM_MEM_HOST) on pinned host buffers holding the batch in the compact transport form "
-                            "(include/ssym.h: per Merkle tree every distinct 32-byte sibling once + one bit per path slot + one back reference per repeated slot; lossless "
-                            "for any record, expanded on the GPU by stwo_expand_kernel): chunked multi-buffered H2D -> expand -> verifier kernels -> D2H bitmap, every "
+                            "(include/ssym.h, version 3: per Merkle tree every distinct 32-byte sibling once, none at all where another query's path computes it; "
+                            "lossless for any record; expanded on the GPU by stwo_expand_kernel + the Merkle kernel itself): chunked multi-buffered H2D -> expand -> verifier kernels -> D2H bitmap, every "
                             "pass's copies inside the timed region.  PACKING IS OUTSIDE THE CLOCK (host_pack).  `value`: calls enqueued back to back "
                             "(ssym_set_host_async), one synchronize per step; `sync_call_value`: each call returns with its bitmap in host memory.  Bound by the host link; "
                             "`e2e_packed` is the same measurement on the reference-shaped fixed-stride packed records (no host packing at all)"},

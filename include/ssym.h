@@ -56,6 +56,15 @@ extern "C" {
  *                     the prover of tests/data/proof.json behaves. */
 #define SSYM_MODE_REF_LITERAL 0
 #define SSYM_MODE_PROVER_CONSISTENT 1
+/* Flag, OR-ed into either of the two: the queries fri_generate_queries draws are SORTED and DE-DUPLICATED before use — the step
+ * fri/queries.simf:41 says the reference leaves out "to simplify the implementation" (upstream stwo's Queries::generate collects them into
+ * an ordered set).  U <= n_queries positions remain.  The witness types are fixed-size arrays, so the shapes do not change: slot j of
+ * DECOMMITMENTS / of every FRI layer decommitment belongs to the j-th smallest distinct query for j < U, and slots j >= U are not looked at
+ * (a prover zero-fills them; the compact transport form stores their repeated digests once).  Every per-query check — decommitments, DEEP
+ * quotient, folds, last layer — runs for j < U only.  This is configuration the reference announces but does not define; its results are
+ * pinned by the oracle (which implements the same rule) and by the two provers, not by a reference vector. */
+#define SSYM_MODE_QUERY_DEDUP 2
+#define SSYM_MODE_SEMANTICS(mode) ((mode) & 1u)
 
 #define SSYM_NUM_COLUMNS 4        /* config.simf:14 NUM_COLUMNS at reference HEAD (the default)   */
 #define SSYM_MAX_COLUMNS 16       /* largest supported NUM_COLUMNS (a power of two, config.simf:12-14) */
@@ -150,7 +159,8 @@ typedef struct ssym_stwo_trace {
     uint32_t mask_fold_inv[SSYM_MAX_FRI_LAYERS];
     uint32_t mask_last_query, mask_last_eval;
     uint32_t draw_retries; /* felt draws that had to be repeated (channel.simf:115-141: a word >= 2p, probability 2^-29 each) */
-    uint32_t pad_[2];
+    uint32_t n_queries_used; /* U: = n_queries, or the number of distinct queries under SSYM_MODE_QUERY_DEDUP (queries[0..U) sorted, the rest 0) */
+    uint32_t pad_[1];
 } ssym_stwo_trace_t;
 
 /* ------------------------------------------------------------------------- */
@@ -180,8 +190,9 @@ typedef struct ssym_cost {
     uint64_t draw_retries;
 } ssym_cost_t;
 /* Cost of verify_proof (stwo-verifier/src/verifier.simf:32-58) for one proof of configuration `cfg` whose transcript drew `queries`
- * (cfg->n_queries words, e.g. ssym_stwo_trace_t.queries) and repeated `draw_retries` felt draws.  Host-only, no GPU involved. */
-int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *queries, uint32_t draw_retries, ssym_cost_t *out);
+ * (the first `n_queries_used` words are used — ssym_stwo_trace_t.queries / .n_queries_used; = cfg->n_queries without SSYM_MODE_QUERY_DEDUP) and
+ * repeated `draw_retries` felt draws.  Host-only, no GPU involved. */
+int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *queries, uint32_t n_queries_used, uint32_t draw_retries, ssym_cost_t *out);
 
 /* ------------------------------------------------------------------------- */
 /* stark101 (stark101/src/verifier.simf:17-42)                                 */
@@ -324,12 +335,34 @@ int ssym_stwo_verify_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const
  *   R back references in slot order: the digest's position among its tree's table entries; 1 byte each if Q * G <= 256, else 2; padded to 8 words
  *   D digests of 8 words
  * Record offsets are multiples of 8 words (ssym_stwo_compact_pack produces them so); a blob in device memory is 16-byte aligned. */
-#define SSYM_COMPACT_MAGIC 0x32435353u /* "SSC2" */
+#define SSYM_COMPACT_MAGIC 0x32435353u  /* "SSC2" */
+#define SSYM_COMPACT_MAGIC3 0x33435353u /* "SSC3": version 3, below */
 /* Words an n-proof compact blob can need at most (no two siblings equal). */
 size_t ssym_stwo_compact_bound(const ssym_stwo_config_t *cfg, size_t n);
 /* Host function: n packed records -> compact records, concatenated in `out`; offsets[0..n] (u32-word offsets, offsets[0] = 0). */
 int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint32_t *out,
                            size_t out_cap_words, uint64_t *offsets);
+/* Version 3 ("SSC3"): siblings another query computes are left out.  Where two paths of a tree meet, the sibling each of them needs at that
+ * level is the node the OTHER path has just computed — upstream stwo's decommitments leave those out (its `hash_witness` is minimal; the fork
+ * that wrote the reference's fixtures expanded them, stwo-verifier/scripts/generate_wit.py:38-42,150-160).  A version 3 record marks such a
+ * slot "derived" and stores one byte, the query whose path supplies the node:
+ *   [2] SSYM_COMPACT_MAGIC3   [4] X = derived slots (S = D + R + X)   [5] the semantics (0 / 1) the record was packed under   [6 .. 8) 0
+ *   a second S-bit bitmap behind the first (1 = derived; never set together with "new"); the X partner bytes behind the R back references.
+ * What a derived slot expands to is DEFINED as the node verify_proof computes on that path from this very record — from the queries its
+ * transcript draws, the queried values (trace / composition trees) or the evaluations of fri_answer and the folds (FRI trees), and the
+ * siblings below — so expansion is a function of the record and of the semantics alone, and ssym_stwo_compact_pack_hinted only marks a slot
+ * whose stored digest IS that node (ssym_stwo_compact_hints compares them on the GPU): lossless for any record, honest or not.  For the FRI
+ * trees this ties a record to the semantics it was packed under ([5]); under another one it is reported malformed.  Under REF_LITERAL the
+ * fixtures' FRI paths do not verify (finding F1), so only their trace / composition trees have derivable siblings.  Requires 32 % Q == 0
+ * (the Merkle kernel resolves a derived sibling with a warp shuffle between the Q chains of a tree); otherwise X = 0.
+ * ssym_stwo_compact_hints: hints[i * S + s] = the lowest query whose node equals sibling slot s of proof i, or 0xff (S = the slots of a proof
+ * in record order).  ssym_stwo_compact_pack_hinted: as ssym_stwo_compact_pack, hints == NULL gives version 2 records.
+ * ssym_stwo_compact_pack_gpu = the two together for packed records in HOST memory (the GPU does the hashing, the host the assembly). */
+int ssym_stwo_compact_hints(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint8_t *hints, int memspace);
+int ssym_stwo_compact_pack_hinted(const ssym_stwo_config_t *cfg, const uint32_t *packed, const uint8_t *hints, size_t n, uint32_t *out,
+                                  size_t out_cap_words, uint64_t *offsets);
+int ssym_stwo_compact_pack_gpu(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint32_t *out,
+                               size_t out_cap_words, uint64_t *offsets);
 /* GPU: compact -> packed (n * layout.stride_words words).  flags: NULL or n words, 1 where a record is malformed (wrong length /
  * magic / counts that do not match the bitmap / a back reference that does not point to an earlier digest of its tree); such a record expands to zeros.  blob holds offsets[n] words. */
 int ssym_stwo_compact_expand(ssym_ctx_t *ctx, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets,

@@ -18,6 +18,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 u32p = C.POINTER(C.c_uint32)
 MODE_REF_LITERAL = 0
 MODE_PROVER_CONSISTENT = 1
+MODE_QUERY_DEDUP = 2  # flag OR-ed into either: sorted, de-duplicated queries (include/ssym.h)
 
 
 class StwoConfig(C.Structure):
@@ -60,7 +61,7 @@ class StwoTrace(C.Structure):
         ("mask_trace", C.c_uint32), ("mask_cp", C.c_uint32), ("mask_answer_inv", C.c_uint32),
         ("mask_fri", C.c_uint32 * 9), ("mask_fold_inv", C.c_uint32 * 9),
         ("mask_last_query", C.c_uint32), ("mask_last_eval", C.c_uint32),
-        ("draw_retries", C.c_uint32), ("pad_", C.c_uint32 * 2),
+        ("draw_retries", C.c_uint32), ("n_queries_used", C.c_uint32), ("pad_", C.c_uint32 * 1),
     ]
 
 

@@ -771,7 +771,9 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     ssym_stwo_layout_t lo;
     memset(tr, 0, sizeof *tr);
     if (oracle_stwo_layout(cfg, &lo) != 0) { tr->status = SSYM_ST_SHAPE; return; }
-    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
+    const uint32_t QL = cfg->n_queries; /* query SLOTS of the record (layout) */
+    uint32_t Q = QL;                    /* queries verified: U <= QL under SSYM_MODE_QUERY_DEDUP */
+    const uint32_t L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg), QV = C + SSYM_NUM_CP_PARTITIONS;
     uint32_t status = 0;
     const uint64_t retries0 = g_draw_retries;
 
@@ -854,6 +856,18 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
         u256 w = channel_draw_u256(&state);
         for (uint32_t j = 0; j < 8 && q + j < Q; j++) queries[q + j] = w.w[j] & query_mask;
     }
+    /* SSYM_MODE_QUERY_DEDUP (include/ssym.h): sort, drop duplicates; slot j < U belongs to the j-th smallest distinct query, slots >= U are ignored */
+    const uint32_t Q_drawn = Q;
+    if (cfg->mode & SSYM_MODE_QUERY_DEDUP) {
+        for (uint32_t a = 1; a < Q_drawn; a++) /* insertion sort */
+            for (uint32_t b = a; b > 0 && queries[b] < queries[b - 1]; b--) { uint32_t t_ = queries[b]; queries[b] = queries[b - 1]; queries[b - 1] = t_; }
+        uint32_t u = 0;
+        for (uint32_t a = 0; a < Q_drawn; a++)
+            if (a == 0 || queries[a] != queries[u - 1]) queries[u++] = queries[a];
+        for (uint32_t a = u; a < Q_drawn; a++) queries[a] = 0;
+        Q = u;
+    }
+    tr->n_queries_used = Q;
     uint32_t domain_size = jet_left_shift_32((uint8_t)G, 1); /* evals/verify.simf:119 */
     for (uint32_t q = 0; q < Q; q++) {
         tr->queries[q] = queries[q];
@@ -878,7 +892,7 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     for (uint32_t q = 0; q < Q; q++) {
         const uint32_t *qv = pk + lo.off_qvals + QV * q;
         t_fail = 0;
-        evals[q] = (cfg->mode == SSYM_MODE_REF_LITERAL)
+        evals[q] = (SSYM_MODE_SEMANTICS(cfg->mode) == SSYM_MODE_REF_LITERAL)
                        ? fri_answer_literal(queries[q], qv, C, qv + C, deep_alpha, oods_point, oods_trace, oods_cp, (uint8_t)G)
                        : fri_answer_prover(queries[q], qv, C, qv + C, deep_alpha, oods_point, oods_trace, oods_cp, (uint8_t)G);
         if (t_fail) { status |= SSYM_ST_ANSWER_INV_ZERO; tr->mask_answer_inv |= 1u << q; }
@@ -891,7 +905,7 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
     for (uint32_t l = 0; l <= L; l++) {
         uint32_t n_sib = G - 1 - l;
         for (uint32_t q = 0; q < Q; q++) { /* fri_verify_query fri/layers.simf:51-69 */
-            QM31 witness = qm31_from_w(pk + lo.off_fri_wit + (l * Q + q) * 4);
+            QM31 witness = qm31_from_w(pk + lo.off_fri_wit + (l * QL + q) * 4);
             uint32_t position;
             QM31 e0, e1;
             if (jet_divides_32(2, fq[q])) { position = fq[q]; e0 = evals[q]; e1 = witness; } /* adjacent_leaves layers.simf:29-37 */
@@ -914,9 +928,9 @@ EXPORT void oracle_stwo_verify_one(const ssym_stwo_config_t *cfg, const uint32_t
         }
         log_size_ex = jet_subtract_8(log_size_ex, 1); /* fri/verify.simf:76 */
     }
-    if (cfg->mode == SSYM_MODE_REF_LITERAL && log_size_ex != 0) status |= SSYM_ST_FINAL_LOG; /* fri/verify.simf:127 */
+    if (SSYM_MODE_SEMANTICS(cfg->mode) == SSYM_MODE_REF_LITERAL && log_size_ex != 0) status |= SSYM_ST_FINAL_LOG; /* fri/verify.simf:127 */
     for (uint32_t q = 0; q < Q; q++) { /* fri_verify_last_layer fri/layers.simf:73-78 */
-        if (cfg->mode == SSYM_MODE_REF_LITERAL && fq[q] != 0) { status |= SSYM_ST_LAST_QUERY; tr->mask_last_query |= 1u << q; }
+        if (SSYM_MODE_SEMANTICS(cfg->mode) == SSYM_MODE_REF_LITERAL && fq[q] != 0) { status |= SSYM_ST_LAST_QUERY; tr->mask_last_query |= 1u << q; }
         if (!qm31_eq(evals[q], last_coeff)) { status |= SSYM_ST_LAST_EVAL; tr->mask_last_eval |= 1u << q; }
     }
     tr->status = status;

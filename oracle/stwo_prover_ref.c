@@ -326,13 +326,21 @@ EXPORT int oracle_stwo_prove_one(const ssym_stwo_config_t *cfg, uint64_t seed, u
         u256 w = channel_draw_u256(&st);
         for (uint32_t j = 0; j < 8 && q + j < Q; j++) queries[q + j] = w.w[j] & (NG - 1);
     }
+    uint32_t U = Q;
+    if (cfg->mode & SSYM_MODE_QUERY_DEDUP) { /* include/ssym.h: sorted distinct queries in the first U slots, the other slots zero-filled */
+        for (uint32_t a = 1; a < Q; a++)
+            for (uint32_t b = a; b > 0 && queries[b] < queries[b - 1]; b--) { uint32_t t_ = queries[b]; queries[b] = queries[b - 1]; queries[b - 1] = t_; }
+        U = 0;
+        for (uint32_t a = 0; a < Q; a++)
+            if (a == 0 || queries[a] != queries[U - 1]) queries[U++] = queries[a];
+    }
     for (int i = 0; i < 3; i++) store_u256(out + lo.off_commit + 8 * i, commitments[i]);
     for (uint32_t c = 0; c < C; c++) qm31_to_w(oods_trace[c], out + lo.off_oods_trace + 4 * c);
     for (int c = 0; c < 16; c++) qm31_to_w(oods_cp[c], out + lo.off_oods_cp + 4 * c);
     qm31_to_w(last_coeff, out + lo.off_last_coeff);
     out[lo.off_pow_nonce] = (uint32_t)(nonce >> 32);
     out[lo.off_pow_nonce + 1] = (uint32_t)nonce;
-    for (uint32_t qi = 0; qi < Q; qi++) {
+    for (uint32_t qi = 0; qi < U; qi++) { /* slots >= U stay zero (the record was cleared on entry) */
         uint32_t q = queries[qi];
         uint32_t *qv = out + lo.off_qvals + QV * qi;
         for (uint32_t c = 0; c < C; c++) qv[c] = tlde[c][q];

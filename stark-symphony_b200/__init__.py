@@ -13,10 +13,10 @@ Host-side mirror of the reference's interface for its verification hot path:
 All compute goes through libssym.so (hand-written sm_100a CUDA behind the C-ABI of include/ssym.h).
 Nothing in this package imports oracle/: that directory is the tests' checker only.
 """
-from ._lib import (ERR_CUDA, ERR_INTERNAL, ERR_NOMEM, ERR_PARSE, ERR_USAGE, MEM_DEVICE, MEM_HOST, MODE_PROVER_CONSISTENT, MODE_REF_LITERAL, S101Trace, SsymError, StwoConfig, StwoLayout, StwoTrace,
+from ._lib import (ERR_CUDA, ERR_INTERNAL, ERR_NOMEM, ERR_PARSE, ERR_USAGE, MEM_DEVICE, MEM_HOST, MODE_PROVER_CONSISTENT, MODE_QUERY_DEDUP, MODE_REF_LITERAL, S101Trace, SsymError, StwoConfig, StwoLayout, StwoTrace,
                    load)
 from .verifier import Verifier, stwo_config, stwo_layout
 from . import witness
 
 __all__ = ["Verifier", "stwo_config", "stwo_layout", "witness", "StwoConfig", "StwoLayout", "StwoTrace", "S101Trace", "SsymError", "load",
-           "MEM_DEVICE", "MEM_HOST", "MODE_REF_LITERAL", "MODE_PROVER_CONSISTENT", "ERR_USAGE", "ERR_CUDA", "ERR_PARSE", "ERR_NOMEM", "ERR_INTERNAL"]
+           "MEM_DEVICE", "MEM_HOST", "MODE_REF_LITERAL", "MODE_PROVER_CONSISTENT", "MODE_QUERY_DEDUP", "ERR_USAGE", "ERR_CUDA", "ERR_PARSE", "ERR_NOMEM", "ERR_INTERNAL"]

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("SSYM_LIB") or os.path.join(HERE, "libssym.so")  # SSY
 MEM_DEVICE, MEM_HOST = 0, 1
 OK, ERR_USAGE, ERR_CUDA, ERR_PARSE, ERR_NOMEM, ERR_INTERNAL = 0, -1, -2, -3, -4, -5  # include/ssym.h
 MODE_REF_LITERAL, MODE_PROVER_CONSISTENT = 0, 1
+MODE_QUERY_DEDUP = 2  # flag: sorted, de-duplicated queries (fri/queries.simf:41; include/ssym.h)
 MAX_QUERIES, MAX_FRI_LAYERS, S101_MAX_LIST = 16, 9, 31
 
 u32p = C.POINTER(C.c_uint32)
@@ -52,7 +53,7 @@ class StwoTrace(C.Structure):
         ("mask_trace", C.c_uint32), ("mask_cp", C.c_uint32), ("mask_answer_inv", C.c_uint32),
         ("mask_fri", C.c_uint32 * MAX_FRI_LAYERS), ("mask_fold_inv", C.c_uint32 * MAX_FRI_LAYERS),
         ("mask_last_query", C.c_uint32), ("mask_last_eval", C.c_uint32),
-        ("draw_retries", C.c_uint32), ("pad_", C.c_uint32 * 2),
+        ("draw_retries", C.c_uint32), ("n_queries_used", C.c_uint32), ("pad_", C.c_uint32 * 1),
     ]
 
 
@@ -90,6 +91,9 @@ SYMBOLS = {
     "ssym_stwo_compact_bound": (_SZ, [C.POINTER(StwoConfig), _SZ]),
     "ssym_stwo_compact_pack": (_I, [C.POINTER(StwoConfig), _V, _SZ, _V, _SZ, _V]),
     "ssym_stwo_compact_expand": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _I]),
+    "ssym_stwo_compact_hints": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _I]),
+    "ssym_stwo_compact_pack_hinted": (_I, [C.POINTER(StwoConfig), _V, _V, _SZ, _V, _SZ, _V]),
+    "ssym_stwo_compact_pack_gpu": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _SZ, _V]),
     "ssym_stwo_verify_compact_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _I]),
     "ssym_stark101_verify_batch": (_I, [_V, _V, _V, _SZ, _V, _V, _V, _I]),
     "ssym_stwo_prove_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _I]),
@@ -137,7 +141,7 @@ class Cost(C.Structure):
         return {name: int(getattr(self, name)) for name in COST_FIELDS}
 
 
-SYMBOLS["ssym_stwo_cost"] = (_I, [C.POINTER(StwoConfig), _V, _U32, C.POINTER(Cost)])
+SYMBOLS["ssym_stwo_cost"] = (_I, [C.POINTER(StwoConfig), _V, _U32, _U32, C.POINTER(Cost)])
 
 WIT_OK, WIT_SHAPE, WIT_PARSE = 0, 1, 2  # per-witness ingestion flags (include/ssym.h)
 

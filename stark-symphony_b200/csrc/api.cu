@@ -119,6 +119,7 @@ struct ssym_ctx {
     // host-memspace staging
     DevBuf stage[HOST_BUFS], d_accept, d_status, d_trace, d_offsets;
     DevBuf cstage[HOST_BUFS], coffs[HOST_BUFS], cflags[HOST_BUFS]; // compact transport: compact chunk, its offsets, malformed-record flags (stage[] holds the expanded chunk)
+    DevBuf cderive[HOST_BUFS];                                      // ... and the derive table of the chunk (version 3 records), one byte per sibling slot
     // prover: twiddle tables per (trace_log, lde_log) and per-chunk scratch
     DevBuf prv_tw[2], prv_itw[2], prv_vanish, prv_flag, prv_seeds, prv_out;
     DevBuf prv_scratch[9];
@@ -198,7 +199,7 @@ void ssym_destroy(ssym_ctx_t *c) {
         cudaEventDestroy(l.done);
     }
     for (int i = 0; i < ssym_ctx::HOST_BUFS; i++) {
-        c->stage[i].release(); c->cstage[i].release(); c->coffs[i].release(); c->cflags[i].release();
+        c->stage[i].release(); c->cstage[i].release(); c->coffs[i].release(); c->cflags[i].release(); c->cderive[i].release();
         cudaEventDestroy(c->ev_h2d[i]);
         cudaEventDestroy(c->ev_done[i]);
     }
@@ -279,7 +280,7 @@ int ssym_profile_read(ssym_ctx_t *c, double *ms, uint64_t *cnt) {
 
 /* ---- configuration / layout -------------------------------------------------------------------- */
 int ssym_stwo_config_preset(const char *name, uint32_t mode, ssym_stwo_config_t *out) {
-    if (!name || !out || mode > 1) return fail(SSYM_ERR_USAGE, "bad preset arguments");
+    if (!name || !out || mode > 3) return fail(SSYM_ERR_USAGE, "bad preset arguments");
     memset(out, 0, sizeof *out);
     out->mode = mode;
     out->pow_target = 0x07ffffffffffffffull; // config.simf:32,51
@@ -298,7 +299,7 @@ static uint32_t align8(uint32_t w) { return (w + 7u) & ~7u; }
 int ssym_stwo_layout(const ssym_stwo_config_t *cfg, ssym_stwo_layout_t *o) {
     if (!cfg || !o) return fail(SSYM_ERR_USAGE, "NULL argument");
     const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, C = SSYM_STWO_COLUMNS(cfg);
-    if (Q < 1 || Q > SSYM_MAX_QUERIES || L + 1 > SSYM_MAX_FRI_LAYERS || G < L + 1 || G > 30 || cfg->mode > 1 || cfg->trace_log > 255)
+    if (Q < 1 || Q > SSYM_MAX_QUERIES || L + 1 > SSYM_MAX_FRI_LAYERS || G < L + 1 || G > 30 || cfg->mode > 3 || cfg->trace_log > 255)
         return fail(SSYM_ERR_USAGE, "unsupported Stwo configuration");
     if (C != 4 && C != 8 && C != 16) return fail(SSYM_ERR_USAGE, "n_columns must be 4, 8 or 16 (0 = 4)");
     memset(o, 0, sizeof *o);
@@ -361,7 +362,7 @@ static int ensure_lane_scratch(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stw
     CUDA_TRY(lane.stwo_ctx.ensure(m * StwoCtxLayout::WORDS * sizeof(uint32_t)));
     CUDA_TRY(lane.stwo_evals.ensure(m * (size_t)(L + 1) * Q * 4 * sizeof(uint32_t)));
     if (own_status) CUDA_TRY(lane.status.ensure(m * sizeof(uint32_t)));
-    const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && cfg.mode == SSYM_MODE_PROVER_CONSISTENT);
+    const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && SSYM_MODE_SEMANTICS(cfg.mode) == SSYM_MODE_PROVER_CONSISTENT);
     StwoDedup dd;
     memset(&dd, 0, sizeof dd);
     if (const size_t list_entries = share ? stwo_dedup_layout(cfg, m, dd) : 0) {
@@ -376,8 +377,10 @@ static int ensure_lane_scratch(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stw
     return SSYM_OK;
 }
 
+// derive / derive_mode: the compact form's table of left-out siblings (StwoParams::derive); only for calls of at most STWO_DEVICE_CHUNK proofs
 static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, const uint32_t *d_packed,
-                             size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s, bool use_front = false) {
+                             size_t n, uint32_t *d_accept, uint32_t *d_status_out, ssym_stwo_trace_t *d_trace, cudaStream_t s, bool use_front = false,
+                             uint8_t *derive = nullptr, uint32_t derive_stride = 0, uint32_t derive_mode = 0) {
 #ifdef SSYM_TUNING // experiment builds only: which of K1 / K2 run on the lane's high-priority stream (0 none, 1 K1, 2 both)
     static const int front_kernels = [] { const char *e = getenv("SSYM_FRONT"); return e ? atoi(e) : 2; }();
 #else
@@ -399,8 +402,12 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
         p.status = d_status_out ? d_status_out + done : lane.status.as<uint32_t>();
         p.trace = d_trace ? d_trace + done : nullptr;
         p.n = (uint32_t)m;
+        p.derive = derive ? derive + done * (size_t)derive_stride : nullptr;
+        p.derive_stride = derive_stride;
+        p.derive_mode = derive ? derive_mode : 0;
+        p.packed_rw = const_cast<uint32_t *>(p.packed);
         memset(&p.dd, 0, sizeof p.dd);
-        const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && cfg.mode == SSYM_MODE_PROVER_CONSISTENT);
+        const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && SSYM_MODE_SEMANTICS(cfg.mode) == SSYM_MODE_PROVER_CONSISTENT);
         if (share && stwo_dedup_layout(cfg, m, p.dd)) {
             p.dd.plan = lane.dd_plan.as<uint32_t>();
             p.dd.ckpt_to = lane.dd_to.as<uint64_t>();
@@ -561,6 +568,11 @@ extern "C" size_t ssym_stwo_compact_bound(const ssym_stwo_config_t *cfg, size_t 
 
 extern "C" int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint32_t *out, size_t out_cap_words,
                                       uint64_t *offsets) {
+    return ssym_stwo_compact_pack_hinted(cfg, packed, nullptr, n, out, out_cap_words, offsets);
+}
+
+extern "C" int ssym_stwo_compact_pack_hinted(const ssym_stwo_config_t *cfg, const uint32_t *packed, const uint8_t *hints, size_t n, uint32_t *out,
+                                             size_t out_cap_words, uint64_t *offsets) {
     if (!cfg || !offsets || ((!packed || !out) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
     ssym_stwo_layout_t lo;
     int rc = ssym_stwo_layout(cfg, &lo);
@@ -570,15 +582,21 @@ extern "C" int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint3
     const uint32_t HASH = 1024; // > 2 * the slots of one tree (Q * G <= 480)
     std::vector<uint32_t> rec(sh.max_words), bucket(HASH), tab(8u * (size_t)sh.slots);
     std::vector<uint16_t> refs(sh.slots);
+    std::vector<uint8_t> partners(sh.slots);
+    // hints (ssym_stwo_compact_hints): byte s of proof i = a query whose path reaches, at the slot's level, a node equal to the slot's sibling.
+    // Such a digest need not be shipped (version 3 record).  Only usable where the Merkle kernel can resolve it: 32 % Q == 0.
+    const bool v3 = hints != nullptr && (32u % cfg->n_queries) == 0;
+    const uint32_t refs_at = v3 ? sh.off_refs3 : sh.off_refs;
     size_t pos = 0;
     offsets[0] = 0;
     for (size_t i = 0; i < n; i++) {
         const uint32_t *pk = packed + i * (size_t)lo.stride_words;
-        std::fill(rec.begin(), rec.begin() + sh.off_refs, 0u);
+        const uint8_t *hint = v3 ? hints + i * (size_t)sh.slots : nullptr;
+        std::fill(rec.begin(), rec.begin() + refs_at, 0u);
         memcpy(rec.data() + COMPACT_HDR_WORDS, pk, sh.fixed_words * 4);
         memcpy(rec.data() + sh.off_wit, pk + lo.off_fri_wit, sh.wit_words * 4);
-        uint32_t *bitmap = rec.data() + sh.off_bitmap;
-        uint32_t D = 0, R = 0;
+        uint32_t *bitmap = rec.data() + sh.off_bitmap, *bitmap2 = rec.data() + sh.off_bitmap2;
+        uint32_t D = 0, R = 0, X = 0;
         for (uint32_t t = 0; t < sh.trees; t++) {
             const uint32_t first = D; // the tree's first table entry
             std::fill(bucket.begin(), bucket.end(), 0u);
@@ -587,8 +605,13 @@ extern "C" int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint3
                 uint32_t h = (d[0] * 0x9E3779B1u) ^ (d[3] * 0x85EBCA77u) ^ d[7];
                 h = (h ^ (h >> 15)) & (HASH - 1);
                 for (;; h = (h + 1) & (HASH - 1)) { // linear probing; a hit only after comparing all 32 bytes
-                    if (!bucket[h]) { // first time in this tree: the next table entry
-                        bucket[h] = D + 1;
+                    if (!bucket[h]) { // first time in this tree
+                        if (hint && hint[sl] < cfg->n_queries) { // ... and another path computes it: derived, nothing stored (a later equal sibling is derived too)
+                            partners[X++] = hint[sl];
+                            bitmap2[sl >> 5] |= 1u << (sl & 31u);
+                            break;
+                        }
+                        bucket[h] = D + 1; // the next table entry
                         memcpy(tab.data() + 8 * (size_t)D, d, 32);
                         D++;
                         bitmap[sl >> 5] |= 1u << (sl & 31u);
@@ -599,16 +622,18 @@ extern "C" int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint3
                 }
             }
         }
-        const uint32_t refs_words = compact_refs_words(sh, R), words = sh.off_refs + refs_words + 8u * D;
-        std::fill(rec.begin() + sh.off_refs, rec.begin() + sh.off_refs + refs_words, 0u);
+        const uint32_t refs_words = compact_refs_words(sh, R, X), words = refs_at + refs_words + 8u * D;
+        std::fill(rec.begin() + refs_at, rec.begin() + refs_at + refs_words, 0u);
+        uint8_t *r8 = reinterpret_cast<uint8_t *>(rec.data() + refs_at);
         if (sh.idx_bytes == 1) {
-            uint8_t *r8 = reinterpret_cast<uint8_t *>(rec.data() + sh.off_refs);
             for (uint32_t k = 0; k < R; k++) r8[k] = (uint8_t)refs[k];
         } else {
-            memcpy(rec.data() + sh.off_refs, refs.data(), (size_t)R * 2);
+            memcpy(r8, refs.data(), (size_t)R * 2);
         }
-        memcpy(rec.data() + sh.off_refs + refs_words, tab.data(), (size_t)D * 32);
-        rec[0] = words; rec[1] = D; rec[2] = SSYM_COMPACT_MAGIC; rec[3] = R;
+        memcpy(r8 + (size_t)R * sh.idx_bytes, partners.data(), X); // version 3: the partner queries of the derived slots
+        memcpy(rec.data() + refs_at + refs_words, tab.data(), (size_t)D * 32);
+        rec[0] = words; rec[1] = D; rec[2] = v3 ? SSYM_COMPACT_MAGIC3 : SSYM_COMPACT_MAGIC; rec[3] = R;
+        if (v3) { rec[4] = X; rec[5] = SSYM_MODE_SEMANTICS(cfg->mode); }
         if (out_cap_words - pos < words) return fail(SSYM_ERR_NOMEM, "compact output buffer too small (ssym_stwo_compact_bound gives the worst case)");
         memcpy(out + pos, rec.data(), (size_t)words * 4);
         pos += words;
@@ -625,6 +650,16 @@ static int compact_prepare(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, ssym_st
     return ssym_join(c); // stage[] / lanes[] scratch is shared with pipelined ssym_stwo_verify_batch calls
 }
 
+// A version 3 record leaves out the siblings another query's path computes (include/ssym.h).  host_has_derived: does any record of
+// blob[offsets[0] .. offsets[m]) (host memory) carry such slots?  Records without them take exactly the version 2 path.
+static bool host_has_derived(const uint32_t *blob, const uint64_t *offsets, size_t m) {
+    for (size_t i = 0; i < m; i++) {
+        const uint32_t *r = blob + offsets[i];
+        if (offsets[i + 1] - offsets[i] >= COMPACT_HDR_WORDS && r[2] == SSYM_COMPACT_MAGIC3 && r[4] != 0) return true;
+    }
+    return false;
+}
+
 extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets, size_t n,
                                         uint32_t *packed_out, uint32_t *flags, int memspace) {
     if (!c || !cfg || ((!blob || !offsets || !packed_out) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
@@ -635,36 +670,128 @@ extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t 
     if (rc || n == 0) return rc;
     if (n > 0xffffffffull) return fail(SSYM_ERR_USAGE, "batch too large for one call");
     cudaStream_t s = c->stream;
+    const bool can_derive = (32u % cfg->n_queries) == 0;
     CompactParams p;
-    p.sh = sh; p.lo = lo; p.base = 0; p.n = (uint32_t)n;
-    if (memspace == SSYM_MEM_DEVICE) {
-        if (reinterpret_cast<uintptr_t>(blob) & 15u) return fail(SSYM_ERR_USAGE, "a device compact blob must be 16-byte aligned");
-        p.blob = blob; p.offsets = offsets; p.packed = packed_out; p.flags = flags;
+    p.sh = sh; p.lo = lo; p.base = 0; p.mode = SSYM_MODE_SEMANTICS(cfg->mode); p.derive = nullptr;
+    const size_t stride_b = (size_t)lo.stride_words * 4;
+    if (memspace == SSYM_MEM_HOST) {
+        for (size_t i = 0; i < n; i++)
+            if (offsets[i + 1] < offsets[i]) return fail(SSYM_ERR_USAGE, "offsets must be non-decreasing");
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream)); // an enqueue-only host call may still be filling the staging buffers
+    } else if (reinterpret_cast<uintptr_t>(blob) & 15u) {
+        return fail(SSYM_ERR_USAGE, "a device compact blob must be 16-byte aligned");
+    }
+    // Chunks of at most STWO_DEVICE_CHUNK records: expand what the record holds; where records left siblings out, run the verifier's
+    // own transcript / field / Merkle kernels over the chunk — the Merkle kernel writes every derived sibling into the packed record.
+    const size_t cap = std::min(n, STWO_DEVICE_CHUNK);
+    if (can_derive) {
+        rc = ensure_tables(c, *cfg);
+        if (rc) return rc;
+        CUDA_TRY(c->cderive[0].ensure(cap * (size_t)sh.slots));
+        CUDA_TRY(c->d_accept.ensure(((cap + 31) / 32) * 4));
+        CUDA_TRY(c->d_status.ensure(cap * 4));
+    }
+    CUDA_TRY(c->cflags[0].ensure(cap * sizeof(uint32_t)));
+    if (memspace == SSYM_MEM_HOST) {
+        size_t max_words = 0;
+        for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) max_words = std::max<size_t>(max_words, offsets[std::min(n, done + STWO_DEVICE_CHUNK)] - offsets[done]);
+        CUDA_TRY(c->cstage[0].ensure(max_words * 4 + 16));
+        CUDA_TRY(c->coffs[0].ensure((cap + 1) * sizeof(uint64_t)));
+        CUDA_TRY(c->stage[0].ensure(cap * stride_b));
+    }
+    for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
+        const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
+        bool derived = can_derive;
+        if (memspace == SSYM_MEM_HOST) {
+            derived = can_derive && host_has_derived(blob, offsets + done, m);
+            const size_t words = offsets[done + m] - offsets[done];
+            CUDA_TRY(cudaMemcpyAsync(c->cstage[0].p, blob + offsets[done], words * 4, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(c->coffs[0].p, offsets + done, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            p.blob = c->cstage[0].as<uint32_t>(); p.offsets = c->coffs[0].as<uint64_t>(); p.base = offsets[done];
+            p.packed = c->stage[0].as<uint32_t>();
+        } else {
+            p.blob = blob; p.offsets = offsets + done; p.base = 0;
+            p.packed = packed_out + done * (size_t)lo.stride_words;
+        }
+        p.flags = memspace == SSYM_MEM_DEVICE && flags ? flags + done : c->cflags[0].as<uint32_t>();
+        p.n = (uint32_t)m;
+        p.derive = derived ? c->cderive[0].as<uint8_t>() : nullptr;
         launch_stwo_expand(p, s);
         c->launches += 1;
-        CUDA_TRY(cudaGetLastError());
-        return SSYM_OK;
+        if (derived) {
+            rc = stwo_launch_chunk(c, c->lanes[0], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>(), c->d_status.as<uint32_t>(), nullptr, s, false, p.derive,
+                                   sh.slots, 1);
+            if (rc) return rc;
+        }
+        if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(cudaMemcpyAsync(packed_out + done * (size_t)lo.stride_words, p.packed, m * stride_b, cudaMemcpyDeviceToHost, s));
+            if (flags) CUDA_TRY(cudaMemcpyAsync(flags + done, p.flags, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s)); // the staging buffers are reused by the next chunk
+        }
     }
-    for (size_t i = 0; i < n; i++)
-        if (offsets[i + 1] < offsets[i]) return fail(SSYM_ERR_USAGE, "offsets must be non-decreasing");
-    const size_t words = offsets[n] - offsets[0], out_b = n * (size_t)lo.stride_words * 4;
-    CUDA_TRY(cudaStreamSynchronize(s));
-    CUDA_TRY(cudaStreamSynchronize(c->copy_stream)); // an enqueue-only host call may still be filling the staging buffers
-    CUDA_TRY(c->cstage[0].ensure(words * 4 + 16));
-    CUDA_TRY(c->coffs[0].ensure((n + 1) * sizeof(uint64_t)));
-    CUDA_TRY(c->cflags[0].ensure(n * sizeof(uint32_t)));
-    CUDA_TRY(c->stage[0].ensure(out_b));
-    CUDA_TRY(cudaMemcpyAsync(c->cstage[0].p, blob + offsets[0], words * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(c->coffs[0].p, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    p.blob = c->cstage[0].as<uint32_t>(); p.offsets = c->coffs[0].as<uint64_t>(); p.base = offsets[0];
-    p.packed = c->stage[0].as<uint32_t>(); p.flags = c->cflags[0].as<uint32_t>();
-    launch_stwo_expand(p, s);
-    c->launches += 1;
-    CUDA_TRY(cudaMemcpyAsync(packed_out, p.packed, out_b, cudaMemcpyDeviceToHost, s));
-    if (flags) CUDA_TRY(cudaMemcpyAsync(flags, p.flags, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     return SSYM_OK;
+}
+
+// Which siblings of packed records are nodes of other queries' paths (the Merkle kernel in scan mode, after the transcript and field kernels
+// gave it the queries and the FRI evaluations).
+extern "C" int ssym_stwo_compact_hints(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint8_t *hints, int memspace) {
+    if (!c || !cfg || ((!packed || !hints) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    ssym_stwo_layout_t lo;
+    CompactShape sh;
+    int rc = compact_prepare(c, cfg, lo, sh);
+    if (rc || n == 0) return rc;
+    cudaStream_t s = c->stream;
+    if ((32u % cfg->n_queries) != 0) { // the Merkle kernel cannot resolve derived siblings for this query count: nothing is derivable
+        if (memspace == SSYM_MEM_HOST) memset(hints, 0xff, n * (size_t)sh.slots);
+        else CUDA_TRY(cudaMemsetAsync(hints, 0xff, n * (size_t)sh.slots, s));
+        return SSYM_OK;
+    }
+    rc = ensure_tables(c, *cfg);
+    if (rc) return rc;
+    const size_t cap = std::min(n, STWO_DEVICE_CHUNK), stride_b = (size_t)lo.stride_words * 4;
+    CUDA_TRY(c->d_accept.ensure(((cap + 31) / 32) * 4));
+    CUDA_TRY(c->d_status.ensure(cap * 4));
+    if (memspace == SSYM_MEM_HOST) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+        CUDA_TRY(c->stage[0].ensure(cap * stride_b));
+        CUDA_TRY(c->cderive[0].ensure(cap * (size_t)sh.slots));
+    }
+    for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
+        const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
+        const uint32_t *d_packed = packed + done * (size_t)lo.stride_words;
+        uint8_t *d_hints = hints + done * (size_t)sh.slots;
+        if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(cudaMemcpyAsync(c->stage[0].p, d_packed, m * stride_b, cudaMemcpyHostToDevice, s));
+            d_packed = c->stage[0].as<uint32_t>();
+            d_hints = c->cderive[0].as<uint8_t>();
+        }
+        CUDA_TRY(cudaMemsetAsync(d_hints, 0xff, m * (size_t)sh.slots, s)); // slots of unused queries (SSYM_MODE_QUERY_DEDUP) are never written
+        rc = stwo_launch_chunk(c, c->lanes[0], *cfg, lo, d_packed, m, c->d_accept.as<uint32_t>(), c->d_status.as<uint32_t>(), nullptr, s, false, d_hints, sh.slots, 2);
+        if (rc) return rc;
+        if (memspace == SSYM_MEM_HOST) {
+            CUDA_TRY(cudaMemcpyAsync(hints + done * (size_t)sh.slots, d_hints, m * (size_t)sh.slots, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SSYM_OK;
+}
+
+extern "C" int ssym_stwo_compact_pack_gpu(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *packed, size_t n, uint32_t *out, size_t out_cap_words,
+                                          uint64_t *offsets) {
+    if (!c || !cfg || !offsets || ((!packed || !out) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
+    ssym_stwo_layout_t lo;
+    CompactShape sh;
+    int rc = compact_prepare(c, cfg, lo, sh);
+    if (rc) return rc;
+    std::vector<uint8_t> hints(n * (size_t)sh.slots);
+    rc = ssym_stwo_compact_hints(c, cfg, packed, n, hints.data(), SSYM_MEM_HOST);
+    if (rc) return rc;
+    return ssym_stwo_compact_pack_hinted(cfg, packed, hints.data(), n, out, out_cap_words, offsets);
 }
 
 extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets, size_t n,
@@ -679,20 +806,24 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     rc = ensure_tables(c, *cfg);
     if (rc) return rc;
     const size_t stride_b = (size_t)lo.stride_words * 4, max_rec_b = (size_t)sh.max_words * 4;
+    const bool can_derive = (32u % cfg->n_queries) == 0;
     cudaStream_t s = c->stream;
     CompactParams p;
-    p.sh = sh; p.lo = lo;
+    p.sh = sh; p.lo = lo; p.mode = SSYM_MODE_SEMANTICS(cfg->mode); p.derive = nullptr;
     if (memspace == SSYM_MEM_DEVICE) { // expand a chunk into HBM scratch, verify it, next chunk (in order on the handle's stream)
         if (reinterpret_cast<uintptr_t>(blob) & 15u) return fail(SSYM_ERR_USAGE, "a device compact blob must be 16-byte aligned");
         const size_t cap = std::min(n, STWO_DEVICE_CHUNK);
         CUDA_TRY(c->stage[0].ensure(cap * stride_b));
         CUDA_TRY(c->cflags[0].ensure(cap * sizeof(uint32_t)));
+        if (can_derive) CUDA_TRY(c->cderive[0].ensure(cap * (size_t)sh.slots));
         for (size_t done = 0; done < n; done += STWO_DEVICE_CHUNK) {
             const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
             p.blob = blob; p.offsets = offsets + done; p.base = 0; p.n = (uint32_t)m;
             p.packed = c->stage[0].as<uint32_t>(); p.flags = c->cflags[0].as<uint32_t>();
+            p.derive = can_derive ? c->cderive[0].as<uint8_t>() : nullptr; // the records are in device memory: whether any has derived slots is not known here
             launch_stwo_expand(p, s);
-            rc = stwo_launch_chunk(c, c->lanes[0], *cfg, lo, p.packed, m, accept_bits + done / 32, status ? status + done : nullptr, nullptr, s);
+            rc = stwo_launch_chunk(c, c->lanes[0], *cfg, lo, p.packed, m, accept_bits + done / 32, status ? status + done : nullptr, nullptr, s, false, p.derive,
+                                   sh.slots, 1);
             if (rc) return rc;
             launch_compact_apply_flags(p.flags, status ? status + done : nullptr, accept_bits + done / 32, (uint32_t)m, s);
             c->launches += 2;
@@ -709,10 +840,11 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     if (c->host_async) hc = std::max<size_t>(512, std::min<size_t>(((n + 1) / 2 + 31) & ~(size_t)31, 4096));
     hc = std::min(hc, (n + 31) & ~(size_t)31);
     const size_t n_words = (n + 31) / 32;
+    const bool derived = can_derive && host_has_derived(blob, offsets, n);
     bool grow = c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4;
     for (int b = 0; b < ssym_ctx::HOST_BUFS; b++)
         grow = grow || c->stage[b].cap < hc * stride_b || c->cstage[b].cap < hc * max_rec_b || c->coffs[b].cap < (hc + 1) * sizeof(uint64_t) ||
-               c->cflags[b].cap < hc * sizeof(uint32_t);
+               c->cflags[b].cap < hc * sizeof(uint32_t) || (derived && c->cderive[b].cap < hc * (size_t)sh.slots);
     if (c->host_async && grow) { // growing a buffer frees it: drain the calls still using it
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
@@ -722,6 +854,7 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
         CUDA_TRY(c->cstage[b].ensure(hc * max_rec_b));
         CUDA_TRY(c->coffs[b].ensure((hc + 1) * sizeof(uint64_t)));
         CUDA_TRY(c->cflags[b].ensure(hc * sizeof(uint32_t)));
+        if (derived) CUDA_TRY(c->cderive[b].ensure(hc * (size_t)sh.slots));
     }
     CUDA_TRY(c->d_accept.ensure(n_words * 4));
     CUDA_TRY(c->d_status.ensure(n * 4));
@@ -739,8 +872,10 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
         CUDA_TRY(cudaStreamWaitEvent(ls, c->ev_h2d[b], 0));
         p.blob = c->cstage[b].as<uint32_t>(); p.offsets = c->coffs[b].as<uint64_t>(); p.base = offsets[done]; p.n = (uint32_t)m;
         p.packed = c->stage[b].as<uint32_t>(); p.flags = c->cflags[b].as<uint32_t>();
+        p.derive = derived ? c->cderive[b].as<uint8_t>() : nullptr; // no version 3 record in the call: exactly the version 2 path (and any Merkle schedule)
         launch_stwo_expand(p, ls);
-        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls);
+        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls, false,
+                               p.derive, sh.slots, 1);
         if (rc) return rc;
         launch_compact_apply_flags(p.flags, c->d_status.as<uint32_t>() + done, c->d_accept.as<uint32_t>() + done / 32, (uint32_t)m, ls);
         c->launches += 2;

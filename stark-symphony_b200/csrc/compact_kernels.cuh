@@ -24,10 +24,15 @@ struct CompactShape {
     uint32_t bitmap_words;                       // ceil(slots / 32)
     uint32_t off_wit, off_bitmap, off_refs;      // word offsets inside the compact record (the fixed part starts at COMPACT_HDR_WORDS); the
                                                  // table follows the R back references: off_refs + compact_refs_words(R)
-    uint32_t max_words;                          // a record with no repeated sibling
+    uint32_t off_bitmap2, off_refs3;             // version 3 records: the "derived" bitmap, and where their references start (one bitmap further)
+    uint32_t max_words;                          // a record with no repeated sibling (version 3: the larger of the two)
+    uint32_t n_queries;                          // Q (partner numbers of derived slots are < Q)
 };
 int compact_shape(const ssym_stwo_config_t &cfg, const ssym_stwo_layout_t &lo, CompactShape &sh);
-__host__ __device__ inline uint32_t compact_refs_words(const CompactShape &sh, uint32_t refs) { return ((refs * sh.idx_bytes + 31u) / 32u) * 8u; }
+// words of the reference section: R back references of idx_bytes each, then (version 3) X partner bytes
+__host__ __device__ inline uint32_t compact_refs_words(const CompactShape &sh, uint32_t refs, uint32_t derived = 0) {
+    return ((refs * sh.idx_bytes + derived + 31u) / 32u) * 8u;
+}
 
 struct CompactParams {
     CompactShape sh;
@@ -38,6 +43,9 @@ struct CompactParams {
     uint32_t *packed;        // n * stride_words
     uint32_t *flags;         // n or nullptr
     uint32_t n;
+    uint8_t *derive;         // nullptr, or n * sh.slots bytes: the derive table of StwoParams (0xff, or the partner query of a derived slot); a
+                             // version 3 record with derived slots is malformed without it
+    uint32_t mode;           // semantics (0 / 1) of the call: a record with derived slots must have been packed under the same
 };
 void launch_stwo_expand(const CompactParams &p, cudaStream_t s);
 // status[i] |= SSYM_ST_SHAPE, accept bit i cleared, where flags[i] != 0

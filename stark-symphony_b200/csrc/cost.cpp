@@ -104,12 +104,14 @@ Cost fold(uint32_t index) { // fri/folding.simf:15-41 (circle and line folds cos
 
 } // namespace
 
-extern "C" int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *queries, uint32_t draw_retries, ssym_cost_t *out) {
+extern "C" int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *queries, uint32_t n_queries_used, uint32_t draw_retries, ssym_cost_t *out) {
     ssym_stwo_layout_t lo;
     if (!cfg || !queries || !out) return SSYM_ERR_USAGE;
     int rc = ssym_stwo_layout(cfg, &lo); // validates the configuration
     if (rc) return rc;
-    const uint32_t Q = cfg->n_queries, L = cfg->n_fri_layers, G = cfg->lde_log, T = cfg->trace_log, C = SSYM_STWO_COLUMNS(cfg), NCOL = C + SSYM_NUM_CP_PARTITIONS;
+    const uint32_t QD = cfg->n_queries; // queries DRAWN; Q of them are verified (all, or the distinct ones under SSYM_MODE_QUERY_DEDUP)
+    if (n_queries_used > QD || (!(cfg->mode & SSYM_MODE_QUERY_DEDUP) && n_queries_used != QD)) return SSYM_ERR_USAGE;
+    const uint32_t Q = n_queries_used, L = cfg->n_fri_layers, G = cfg->lde_log, T = cfg->trace_log, C = SSYM_STWO_COLUMNS(cfg), NCOL = C + SSYM_NUM_CP_PARTITIONS;
     Cost c;
     // evals_commit                                    evals/commit.simf:20-35
     c += channel_mix_u256() * 3 + channel_draw_qm31();
@@ -126,7 +128,7 @@ extern "C" int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *que
     // check_proof_of_work                             pow.simf:22-35
     c += channel_mix_u64();
     // fri_generate_queries                            fri/queries.simf:30-43
-    c += channel_draw_u256() * ((Q + 7) / 8);
+    c += channel_draw_u256() * ((QD + 7) / 8);
     // repeated felt draws (channel.simf:125-137): each is one more channel_draw_u256
     c += channel_draw_u256() * draw_retries + unit(RETRY, draw_retries);
     // evals_verify                                    evals/verify.simf:50-78: trace leaf + path, composition leaf + path, per query
@@ -135,7 +137,7 @@ extern "C" int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *que
         // fri_answer                                  fri/answers.simf:97-129 / SURVEY Appendix A item 1
         c += point_from_index(circle_position_to_point_index(G, bit_reverse_position(queries[q], G)));
         c += numerator_aggregate_column() * NCOL;
-        if (cfg->mode == SSYM_MODE_REF_LITERAL) c += denominator_inverse() + qm31_mul_cm31() + qm31_mul();
+        if (SSYM_MODE_SEMANTICS(cfg->mode) == SSYM_MODE_REF_LITERAL) c += denominator_inverse() + qm31_mul_cm31() + qm31_mul();
         else c += qm31_point_dbl_x() + qm31_mul() + qm31_add() /* 2P */ + denominator_inverse() * 2 + qm31_mul_cm31() * 2 + qm31_add();
         // fri_verify                                  fri/verify.simf:114-129, fri/layers.simf:29-69
         uint32_t fq = queries[q];

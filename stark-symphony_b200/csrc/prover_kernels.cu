@@ -502,6 +502,22 @@ __global__ void __launch_bounds__(64) prv_final_kernel(PrvParams p) {
         channel_draw_u256(ch, w);
         for (uint32_t j = 0; j < 8 && q0 + j < Q; j++) pc[PC::QUERIES + q0 + j] = w[j] & mask;
     }
+    uint32_t used = Q;
+    if (p.cfg.mode & SSYM_MODE_QUERY_DEDUP) { // include/ssym.h: sorted distinct queries in slots [0, U), the other slots zero-filled
+        uint32_t *qs = pc + PC::QUERIES;
+        for (uint32_t a = 1; a < Q; a++) {
+            const uint32_t v = qs[a];
+            uint32_t b = a;
+            for (; b > 0 && qs[b - 1] > v; b--) qs[b] = qs[b - 1];
+            qs[b] = v;
+        }
+        used = 0;
+        for (uint32_t a = 0; a < Q; a++) {
+            const uint32_t v = qs[a];
+            if (a == 0 || v != qs[used - 1]) qs[used++] = v;
+        }
+    }
+    pc[PC::N_USED] = used;
     ch_store(ch, pc);
 }
 
@@ -516,6 +532,24 @@ __global__ void __launch_bounds__(128) prv_decommit_kernel(PrvParams p) {
     const uint32_t q = p.pctx[(size_t)i * PC::WORDS + PC::QUERIES + qi];
     uint32_t *out = p.out + (size_t)i * p.lo.stride_words;
     const uint32_t C = SSYM_STWO_COLUMNS(&p.cfg);
+    if (qi >= p.pctx[(size_t)i * PC::WORDS + PC::N_USED]) { // an unused slot (SSYM_MODE_QUERY_DEDUP): zeros, as the reference prover writes
+        if (lane < C + 16) out[p.lo.off_qvals + (C + 16) * qi + lane] = 0;
+        if (lane <= L) *reinterpret_cast<uint4 *>(out + p.lo.off_fri_wit + (lane * Q + qi) * 4) = make_uint4(0, 0, 0, 0);
+        const uint32_t n_slots = 2 * G + (L + 1) * (G - 1) - L * (L + 1) / 2;
+        for (uint32_t job = lane; job < n_slots; job += 32) {
+            uint32_t *dst;
+            if (job < 2 * G) {
+                dst = out + (job < G ? p.lo.off_trace_sib : p.lo.off_cp_sib) + (qi * G + (job < G ? job : job - G)) * 8;
+            } else {
+                uint32_t r = job - 2 * G, l = 0;
+                while (r >= G - 1 - l) { r -= G - 1 - l; l++; }
+                dst = out + p.lo.off_fri_sib[l] + (qi * (G - l - 1) + r) * 8;
+            }
+            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
     if (lane < C + 16)
         out[p.lo.off_qvals + (C + 16) * qi + lane] = lane < C ? p.tlde[((size_t)i * C + lane) * NG + q] : p.cplde[((size_t)i * 16 + (lane - C)) * NG + q];
     if (lane <= L) { // the sibling evaluation of layer `lane` (adjacent_leaves fri/layers.simf:29-37)

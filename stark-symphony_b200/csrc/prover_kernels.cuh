@@ -36,7 +36,8 @@ struct PrvCtx { // per-proof prover context, u32 words
         SUMS = 220,      // [4][4]   sum a / sum c of batch A (CP), sum a / sum c of batch B (trace)
         FRI_ALPHA = 236, // [9][4]
         QUERIES = 272,   // [16]
-        WORDS = 288
+        N_USED = 288,    // [1] slots the decommitments fill: n_queries, or the distinct queries under SSYM_MODE_QUERY_DEDUP
+        WORDS = 292
     };
 };
 

@@ -125,9 +125,12 @@ struct ShaAdd {
     }
 };
 
+// T1 is associated as ((h + K + W) + Ch) + Sigma1: Sigma1(e) (two dependent ALU operations) is the last term to arrive, so only ONE addition sits
+// between it and the new e — the dependent chain of a round is SHF, LOP3, IMAD, IMAD instead of SHF, LOP3, IMAD, IMAD, IMAD.  Same operation
+// count; it matters where a lone warp runs a chain of compressions (the transcript kernel), not in the throughput-bound Merkle kernels.
 #define SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, h, kw)                        \
     {                                                                        \
-        uint32_t t1_ = A.t1(A.t1(h, kw), A.t1(A.bSig1(e), Ch(e, f, g)));     \
+        uint32_t t1_ = A.t1(A.t1(A.t1(h, kw), Ch(e, f, g)), A.bSig1(e));     \
         (d) = A.rnd(d, t1_);                                                 \
         (h) = A.rnd3(t1_, A.bSig0(a), Maj(a, b, c));                         \
     }

@@ -53,7 +53,7 @@ enum TxState : uint32_t {
 // The per-proof scalars of verify_proof (a thread serves one proof here; the query kernel would redo them in every lane): the OODS point
 // (channel.simf:143-151), the composition-polynomial check (deep/oods.simf:52-58), the sample point of the CP columns, the powers of the
 // DEEP coefficient.  Adds its failures to `status` and stores the proof's status word.
-__device__ __noinline__ void stwo_scalars(const StwoParams &p, uint32_t i, QM31 oods_t, QM31 cp_alpha, QM31 deep_alpha, uint32_t status) {
+__device__ __noinline__ uint32_t stwo_scalars(const StwoParams &p, uint32_t i, QM31 oods_t, QM31 cp_alpha, QM31 deep_alpha, uint32_t status) {
     const ssym_stwo_layout_t &lo = p.lo;
     const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
     uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
@@ -114,7 +114,7 @@ __device__ __noinline__ void stwo_scalars(const StwoParams &p, uint32_t i, QM31 
     }
     qm31_store4(ctx + CX::PX, px);
     qm31_store4(ctx + CX::PY, py);
-    if (p.cfg.mode == SSYM_MODE_REF_LITERAL) { // all C + 16 columns are sampled at P (fri/answers.simf:116-125)
+    if (SSYM_MODE_SEMANTICS(p.cfg.mode) == SSYM_MODE_REF_LITERAL) { // all C + 16 columns are sampled at P (fri/answers.simf:116-125)
         qm31_store4(ctx + CX::P2X, px);
         qm31_store4(ctx + CX::P2Y, py);
     } else { // the 16 CP partitions are sampled at 2*P
@@ -129,7 +129,7 @@ __device__ __noinline__ void stwo_scalars(const StwoParams &p, uint32_t i, QM31 
             a = qm31_mul_nl(a, deep_alpha);
         }
     }
-    p.status[i] = status;
+    return status;
 }
 
 // One thread runs the transcripts of NP proofs in lockstep (the steps of the program are the same for every proof of a configuration; only a
@@ -313,11 +313,286 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
 #pragma unroll 1
     for (int k = 0; k < NP; k++) {
         if (!live[k]) continue;
+        uint32_t used = Q;
+        if (p.cfg.mode & SSYM_MODE_QUERY_DEDUP) { // include/ssym.h: sort the drawn queries, keep the distinct ones in slots [0, U), zero the rest
+            uint32_t *qs = ctx[k] + CX::QUERIES;
+            for (uint32_t a = 1; a < Q; a++) { // insertion sort of <= 16 words in the proof's own context
+                const uint32_t v = qs[a];
+                uint32_t b = a;
+                for (; b > 0 && qs[b - 1] > v; b--) qs[b] = qs[b - 1];
+                qs[b] = v;
+            }
+            used = 0;
+            for (uint32_t a = 0; a < Q; a++) {
+                const uint32_t v = qs[a];
+                if (a == 0 || v != qs[used - 1]) qs[used++] = v;
+            }
+            for (uint32_t a = used; a < Q; a++) qs[a] = 0;
+            if (tr[k])
+                for (uint32_t a = 0; a < Q; a++) tr[k]->queries[a] = qs[a];
+        }
+        ctx[k][CX::N_USED] = used;
+        if (tr[k]) tr[k]->n_queries_used = used;
         uint32_t st = status[k];
         if (exhausted[k]) st |= SSYM_ST_DRAW_EXHAUSTED;
-        if (p.cfg.mode == SSYM_MODE_REF_LITERAL && ((G - (L + 1u)) & 0xff) != 0) st |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
+        if (SSYM_MODE_SEMANTICS(p.cfg.mode) == SSYM_MODE_REF_LITERAL && ((G - (L + 1u)) & 0xff) != 0) st |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
         if (tr[k]) tr[k]->draw_retries = retries[k];
-        stwo_scalars(p, idx[k], oods_t[k], cp_alpha[k], deep_alpha[k], st);
+        p.status[idx[k]] = stwo_scalars(p, idx[k], oods_t[k], cp_alpha[k], deep_alpha[k], st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, warp-specialised (the default).  A transcript is one dependent chain, and a lone warp issues at most one instruction every ~2 cycles per pipe
+// (ncu on the one-thread-per-proof kernel above: 0.34 instructions per cycle, 1.15 cycles of fixed-latency wait per issue): its latency is its
+// instruction count.  So the instruction stream of 32 transcripts is cut across THREE warps of one CTA, on three schedulers:
+//   warp R  the 64 rounds of every compression and nothing else: K[t] + W[t] comes from shared memory                 (~1000 instructions / compression)
+//   warp S  the state machine of the transcript (what is hashed next, draws, retries, PoW, queries) and the message schedule: it assembles each block
+//           and produces K + W for rounds 16 g .. 16 g + 15 one group AHEAD of warp R (double-buffered; one named barrier per group)
+//   warp F  the per-proof scalars (stwo_scalars: OODS point, composition-polynomial check, powers of the DEEP coefficient) as soon as the DEEP
+//           coefficient is drawn, i.e. while the 31 compressions of fri_commit / PoW / queries are still running
+// Same values, same order of hash inputs; lane l of every warp serves proof 32 * blockIdx.x + l.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#define K1_BAR_RS 1 // warps R + S: group produced / group consumed / digest ready / control ready
+#define K1_BAR_F_GO 2   // S arrives, F waits: the three drawn elements the scalars need are in shared memory
+#define K1_BAR_F_DONE 3 // F arrives, S waits: the scalars' status bits are in shared memory
+
+__global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMul mul) {
+    __shared__ uint32_t s_kw[2][16][32]; // K + W of one 16-round group per buffer, [round][lane]
+    __shared__ uint32_t s_dig[8][32];    // digest of the finished message (R -> S)
+    __shared__ uint32_t s_ctl[4];        // {blocks of the next message, second block is the constant padding block, done}
+    __shared__ uint32_t s_felt[12][32];  // oods_t, cp_alpha, deep_alpha (S -> F)
+    __shared__ uint32_t s_fbits[32];     // status bits of the scalars (F -> S)
+    const ShaAdd<K1_ADDMODE> A(mul);
+    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * 32 + lane;
+    const bool live = i < p.n;
+    const uint32_t idx = live ? i : p.n - 1; // idle lanes of the last CTA replay the last proof and store nothing
+    if (p.dd.enabled && blockIdx.x == 0) // the bin counters of stwo_plan_kernel / stwo_check_kernel, later in this stream
+        for (uint32_t t = threadIdx.x; t < 2 * STWO_DEDUP_MAX_BINS; t += blockDim.x) p.dd.bin_count[t] = 0;
+
+    if (role == 0) { // ---- warp R: rounds ------------------------------------------------------------------------------------
+        uint32_t h[8];
+        for (;;) {
+            named_bar_sync(K1_BAR_RS, 64); // control ready
+            const uint32_t nblocks = s_ctl[0], pad64 = s_ctl[1];
+            if (s_ctl[2]) break;
+            sha_iv(h);
+#pragma unroll 1
+            for (uint32_t b = 0; b < nblocks; b++) {
+                if (pad64 && b == 1) { sha_compress_pad64_rolled<K1_ADDMODE>(h, A); continue; }
+                uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll 1
+                for (uint32_t grp = 0; grp < 4; grp++) {
+                    named_bar_sync(K1_BAR_RS, 64); // group `grp` produced (and group grp - 1 consumed: its buffer may be overwritten)
+                    const uint32_t(*kw)[32] = s_kw[grp & 1];
+                    SSYM_SHA_ROUND4(A, a, bb, c, d, e, f, g, hh, kw[0][lane], kw[1][lane], kw[2][lane], kw[3][lane]);
+                    SSYM_SHA_ROUND4(A, e, f, g, hh, a, bb, c, d, kw[4][lane], kw[5][lane], kw[6][lane], kw[7][lane]);
+                    SSYM_SHA_ROUND4(A, a, bb, c, d, e, f, g, hh, kw[8][lane], kw[9][lane], kw[10][lane], kw[11][lane]);
+                    SSYM_SHA_ROUND4(A, e, f, g, hh, a, bb, c, d, kw[12][lane], kw[13][lane], kw[14][lane], kw[15][lane]);
+                }
+                h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) s_dig[k][lane] = h[k];
+            named_bar_sync(K1_BAR_RS, 64); // digest ready
+        }
+        return;
+    }
+    if (role == 2) { // ---- warp F: the per-proof scalars ----------------------------------------------------------------------
+        named_bar_sync(K1_BAR_F_GO, 64);
+        const QM31 oods_t = qm31(s_felt[0][lane], s_felt[1][lane], s_felt[2][lane], s_felt[3][lane]);
+        const QM31 cp_alpha = qm31(s_felt[4][lane], s_felt[5][lane], s_felt[6][lane], s_felt[7][lane]);
+        const QM31 deep_alpha = qm31(s_felt[8][lane], s_felt[9][lane], s_felt[10][lane], s_felt[11][lane]);
+        uint32_t bits = 0;
+        if (live) bits = stwo_scalars(p, idx, oods_t, cp_alpha, deep_alpha, 0u);
+        s_fbits[lane] = bits;
+        __threadfence_block();
+        named_bar_arrive(K1_BAR_F_DONE, 64);
+        return;
+    }
+    // ---- warp S: state machine + message schedule ---------------------------------------------------------------------------
+    const ssym_stwo_layout_t &lo = p.lo;
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
+    const uint32_t NCOL = SSYM_STWO_COLUMNS(&p.cfg) + SSYM_NUM_CP_PARTITIONS;
+    const uint32_t *pk = p.packed + (size_t)idx * lo.stride_words;
+    uint32_t *ctx = p.ctx + (size_t)idx * CX::WORDS;
+    ssym_stwo_trace_t *tr = p.trace && live ? p.trace + idx : nullptr;
+    uint32_t status = 0, n_sent = 0, tries = 0, retries = 0, d[8]; // channel_init channel.simf:31-33
+    bool exhausted = false, settled = false;
+    QM31 felt = qm31_zero();
+#pragma unroll
+    for (int j = 0; j < 8; j++) d[j] = 0;
+    uint32_t state = TX_MIX_CONST, layer = 0, q0 = 0;
+    const uint32_t query_mask = shl32(G & 0xff, 1u) - 1u;
+#pragma unroll 1
+    while (state != TX_DONE) {
+        uint32_t off = 0, n = 1;
+        bool draw = false;
+        switch (state) {
+        case TX_MIX_CONST: off = lo.off_commit; n = 8; break;
+        case TX_MIX_TRACE: off = lo.off_commit + 8; n = 8; break;
+        case TX_MIX_CP: off = lo.off_commit + 16; n = 8; break;
+        case TX_MIX_OODS: off = lo.off_oods_trace; n = 4 * NCOL; break;
+        case TX_MIX_FRI_ROOT: off = layer == 0 ? lo.off_fri_first_root : lo.off_fri_inner_root + 8 * (layer - 1); n = 8; break;
+        case TX_MIX_LAST: off = lo.off_last_coeff; n = 4; break;
+        case TX_MIX_NONCE: off = lo.off_pow_nonce; n = 2; break;
+        default: draw = true; break;
+        }
+        const uint32_t nwords = 8 + n, nblocks = (nwords + 3 + 15) >> 4;
+        const bool pad64 = nwords == 16; // the 12 digest-sized mixes: the second block is the constant padding block of a 64-byte message
+        if (lane == 0) { s_ctl[0] = nblocks; s_ctl[1] = pad64 ? 1u : 0u; s_ctl[2] = 0u; }
+        named_bar_sync(K1_BAR_RS, 64); // control ready
+#pragma unroll 1
+        for (uint32_t b = 0; b < nblocks; b++) {
+            if (pad64 && b == 1) continue;
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t m = b * 16 + j;
+                uint32_t v = 0;
+                if (m < 8) v = d[j & 7]; // only in block 0, where m == j
+                else if (m < nwords) v = draw ? n_sent : __ldg(pk + off + (m - 8));
+                else if (m == nwords) v = 0x80000000u;
+                else if (m == nblocks * 16 - 1) v = nwords * 32u;
+                w[j] = v;
+            }
+#pragma unroll 1
+            for (uint32_t grp = 0; grp < 4; grp++) {
+                if (grp) {
+#pragma unroll
+                    for (int t = 0; t < 16; t++) w[t] = A.sch4(w[t], A.ssig0(w[(t + 1) & 15]), w[(t + 9) & 15], A.ssig1(w[(t + 14) & 15]));
+                }
+                uint32_t(*kw)[32] = s_kw[grp & 1];
+#pragma unroll
+                for (int t4 = 0; t4 < 4; t4++) {
+                    const uint4 k4 = c_sha_k4.v[grp * 4 + t4];
+                    kw[4 * t4 + 0][lane] = A.t1(w[4 * t4 + 0], k4.x);
+                    kw[4 * t4 + 1][lane] = A.t1(w[4 * t4 + 1], k4.y);
+                    kw[4 * t4 + 2][lane] = A.t1(w[4 * t4 + 2], k4.z);
+                    kw[4 * t4 + 3][lane] = A.t1(w[4 * t4 + 3], k4.w);
+                }
+                named_bar_sync(K1_BAR_RS, 64); // group produced
+            }
+        }
+        named_bar_sync(K1_BAR_RS, 64); // digest ready
+        uint32_t h[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) h[k] = s_dig[k][lane];
+        // ---- what the step does with the hash (as in the one-thread kernel above) ----
+        if (!draw) { // channel_mix_*: the digest moves, the counter restarts
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = h[j];
+            n_sent = 0;
+            if (state == TX_MIX_CP && tr)
+                for (int j = 0; j < 8; j++) tr->digest_commit[j] = d[j];
+            if (state == TX_MIX_LAST && tr)
+                for (int j = 0; j < 8; j++) tr->digest_fri[j] = d[j];
+            if (state == TX_MIX_NONCE) { // check_proof_of_work pow.simf:22-35
+                const uint64_t value = ((uint64_t)__byte_perm(d[7], 0, 0x0123) << 32) | __byte_perm(d[6], 0, 0x0123);
+                if (!(value < p.cfg.pow_target)) status |= SSYM_ST_POW_FAIL;
+                if (tr) {
+                    for (int j = 0; j < 8; j++) tr->digest_pow[j] = d[j];
+                    tr->pow_value[0] = (uint32_t)(value >> 32);
+                    tr->pow_value[1] = (uint32_t)value;
+                }
+            }
+            switch (state) {
+            case TX_MIX_CONST: state = TX_MIX_TRACE; break;
+            case TX_MIX_TRACE: state = TX_DRAW_CP_ALPHA; break;
+            case TX_MIX_CP: state = TX_DRAW_OODS_T; break;
+            case TX_MIX_OODS: state = TX_DRAW_DEEP_ALPHA; break;
+            case TX_MIX_FRI_ROOT: state = TX_DRAW_FRI_ALPHA; break;
+            case TX_MIX_LAST: state = TX_MIX_NONCE; break;
+            default: state = TX_DRAW_QUERIES; break; // TX_MIX_NONCE
+            }
+            continue;
+        }
+        if (state == TX_DRAW_QUERIES) { // fri_generate_queries fri/queries.simf:30-43: 8 queries per draw, masked to the LDE domain
+            n_sent = n_sent + 1u;
+            for (uint32_t j = 0; live && j < 8 && q0 + j < Q; j++) {
+                ctx[CX::QUERIES + q0 + j] = h[j] & query_mask;
+                if (tr) tr->queries[q0 + j] = h[j] & query_mask;
+            }
+            q0 += 8;
+            if (q0 >= Q) state = TX_DONE;
+            continue;
+        }
+        // channel_draw_qm31 (channel.simf:115-141): retry (<= 256 draws) until the first four words are < 2p.  The step is uniform over the warp:
+        // a settled proof hashes along (its hash is not looked at) while another repeats its draw.
+        if (!settled) {
+            const bool ok = h[0] < 4294967294u && h[1] < 4294967294u && h[2] < 4294967294u && h[3] < 4294967294u;
+            tries++;
+            if (ok || tries == 256) {
+                retries += tries - 1u;
+                settled = true;
+                exhausted = exhausted || !ok;
+                felt = qm31(m31_reduce(h[0]), m31_reduce(h[1]), m31_reduce(h[2]), m31_reduce(h[3]));
+            }
+            n_sent = n_sent + 1u; // channel_draw_u256 channel.simf:36-44
+        }
+        if (!__all_sync(0xffffffffu, settled)) continue;
+        settled = false;
+        tries = 0;
+        switch (state) {
+        case TX_DRAW_CP_ALPHA:
+            if (live) qm31_store4(ctx + CX::CP_ALPHA, felt);
+            if (tr) qm31_store(tr->cp_alpha, felt);
+            s_felt[4][lane] = felt.r.a; s_felt[5][lane] = felt.r.b; s_felt[6][lane] = felt.i.a; s_felt[7][lane] = felt.i.b;
+            break;
+        case TX_DRAW_OODS_T: // channel.simf:143-144
+            s_felt[0][lane] = felt.r.a; s_felt[1][lane] = felt.r.b; s_felt[2][lane] = felt.i.a; s_felt[3][lane] = felt.i.b;
+            break;
+        case TX_DRAW_DEEP_ALPHA:
+            if (live) qm31_store4(ctx + CX::DEEP_ALPHA, felt);
+            if (tr) {
+                for (int j = 0; j < 8; j++) tr->digest_oods[j] = d[j];
+                qm31_store(tr->deep_alpha, felt);
+            }
+            s_felt[8][lane] = felt.r.a; s_felt[9][lane] = felt.r.b; s_felt[10][lane] = felt.i.a; s_felt[11][lane] = felt.i.b;
+            __threadfence_block();
+            named_bar_arrive(K1_BAR_F_GO, 64); // warp F starts on the scalars; this warp goes on with fri_commit
+            break;
+        default: // TX_DRAW_FRI_ALPHA
+            if (live) qm31_store4(ctx + CX::FRI_ALPHA + 4 * layer, felt);
+            if (tr) qm31_store(tr->fri_alpha[layer], felt);
+            break;
+        }
+        switch (state) {
+        case TX_DRAW_CP_ALPHA: state = TX_MIX_CP; break;
+        case TX_DRAW_OODS_T: state = TX_MIX_OODS; break;
+        case TX_DRAW_DEEP_ALPHA: state = TX_MIX_FRI_ROOT; break;
+        default: layer++; state = layer <= L ? TX_MIX_FRI_ROOT : TX_MIX_LAST; break;
+        }
+    }
+    if (lane == 0) s_ctl[2] = 1u;
+    named_bar_sync(K1_BAR_RS, 64); // releases warp R
+    uint32_t used = Q;
+    if (live && (p.cfg.mode & SSYM_MODE_QUERY_DEDUP)) { // include/ssym.h: sort the drawn queries, keep the distinct ones in slots [0, U), zero the rest
+        uint32_t *qs = ctx + CX::QUERIES;
+        for (uint32_t a = 1; a < Q; a++) {
+            const uint32_t v = qs[a];
+            uint32_t b = a;
+            for (; b > 0 && qs[b - 1] > v; b--) qs[b] = qs[b - 1];
+            qs[b] = v;
+        }
+        used = 0;
+        for (uint32_t a = 0; a < Q; a++) {
+            const uint32_t v = qs[a];
+            if (a == 0 || v != qs[used - 1]) qs[used++] = v;
+        }
+        for (uint32_t a = used; a < Q; a++) qs[a] = 0;
+        if (tr)
+            for (uint32_t a = 0; a < Q; a++) tr->queries[a] = qs[a];
+    }
+    if (exhausted) status |= SSYM_ST_DRAW_EXHAUSTED;
+    if (SSYM_MODE_SEMANTICS(p.cfg.mode) == SSYM_MODE_REF_LITERAL && ((G - (L + 1u)) & 0xff) != 0) status |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
+    named_bar_sync(K1_BAR_F_DONE, 64); // the scalars are done (long ago)
+    if (live) {
+        ctx[CX::N_USED] = used;
+        if (tr) { tr->n_queries_used = used; tr->draw_retries = retries; }
+        p.status[idx] = status | s_fbits[lane];
     }
 }
 
@@ -368,7 +643,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
     const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
     const uint32_t *ctx = p.ctx + (size_t)i * CX::WORDS;
     ssym_stwo_trace_t *tr = p.trace ? p.trace + i : nullptr;
-    const bool literal = p.cfg.mode == SSYM_MODE_REF_LITERAL;
+    const bool literal = SSYM_MODE_SEMANTICS(p.cfg.mode) == SSYM_MODE_REF_LITERAL;
     uint32_t status = 0;
 
     // the per-proof scalars come from K1: the OODS point P, the sample point of batch A, the powers of the DEEP coefficient
@@ -396,7 +671,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
     __syncwarp();
 
     // ---- phase C: lane q = query q ----
-    if (lane < Q) {
+    if (lane < ctx[CX::N_USED]) { // U = Q unless SSYM_MODE_QUERY_DEDUP
         const uint32_t q = lane;
         const uint32_t query = ctx[CX::QUERIES + q];
         const uint2 rp = p.tab.point[query]; // domain point of the query, fri/answers.simf:108-110
@@ -479,7 +754,10 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t (&d)[8
 //   trace : pre 0 = SHA-256(4 words)                       hash_node_m31_trace   hasher.simf:85-90
 //   cp    : pre 0 = SHA-256(16 words)                      hash_node_m31_cp      hasher.simf:93-97
 //   fri   : pre 0 = SHA-256(e0), pre 1 = SHA-256(e1), pre 2 = sha256_pair        fri/layers.simf:40-48
-template <int ADDMODE, bool ROLLED>
+// KMODE 0: the kernel of every packed batch.  KMODE 1 / 2 (compact transport form, version 3; StwoParams::derive): the siblings a record left out
+// are the nodes of other queries' paths — the 16 (Q) chains of one tree of one proof sit in one warp and step through the levels together, so a
+// derived sibling is a warp shuffle away; KMODE 2 finds, for the packer, which siblings could be left out.  Needs 32 % Q == 0.
+template <int ADDMODE, bool ROLLED, int KMODE = 0>
 __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, ShaMul mul) {
     const ShaAdd<ADDMODE> A(mul);
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
@@ -489,8 +767,10 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
     const uint32_t rank = warp / groups_per_type, group = warp % groups_per_type;
     if (rank >= L + 3) return;
     const uint32_t item = group * 32 + lane;
-    const bool active = item < p.n * Q;
-    const uint32_t i = active ? item / Q : 0, q = active ? item % Q : 0;
+    const bool in_batch = item < p.n * Q;
+    const uint32_t i = in_batch ? item / Q : 0, q = in_batch ? item % Q : 0;
+    const uint32_t used = p.ctx[(size_t)i * CX::WORDS + CX::N_USED];
+    const bool active = in_batch && q < used; // slots >= U are not looked at (SSYM_MODE_QUERY_DEDUP)
     const ssym_stwo_layout_t &lo = p.lo;
     const uint32_t *pk = p.packed + (size_t)i * lo.stride_words;
     const uint32_t query = p.ctx[(size_t)i * CX::WORDS + CX::QUERIES + q];
@@ -530,6 +810,13 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
         path = ((fq & ~1u) + shl32((G - layer) & 0xff, 1u)) >> 1;
     }
     const uint32_t *evp = p.fri_evals + ((size_t)i * (L + 1) * Q + layer * Q + q) * 4;
+    // compact form: this chain's bytes in the proof's derive table (slot = tree's first slot + q * n_sib + level)
+    uint8_t *dv = nullptr;
+    if (KMODE != 0) {
+        const uint32_t tree_first = kind == 0 ? 0u : kind == 1 ? Q * G : Q * (2u * G + layer * (G - 1u) - layer * (layer - 1u) / 2u);
+        dv = p.derive + (size_t)i * p.derive_stride + tree_first + q * n_sib;
+    }
+    const uint32_t grp_base = lane & ~(Q - 1u); // first lane of this proof's tree in the warp (32 % Q == 0)
 
     uint32_t cur[8], nxt[8]; // nxt: next sibling (prefetched one level ahead); during the FRI pre steps: the first leaf hash
 #pragma unroll
@@ -571,6 +858,34 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
         } else { // merkle_compute_step merkle.simf:22-30
             const uint32_t lvl = step - n_pre;
             const bool cur_left = (path & 1u) == 0; // divides_32(2, path): sha256_pair(cur, sib) else (sib, cur)
+            if (KMODE == 1) { // a sibling the record left out = the node another query's path has reached at this level
+                const uint32_t pb = active ? dv[lvl] : 0xffu;
+                const uint32_t src = grp_base + (pb < Q ? pb : 0u);
+                uint32_t got[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) got[k] = __shfl_sync(0xffffffffu, cur[k], src);
+                if (pb < Q) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) nxt[k] = got[k];
+                    uint4 *dst = reinterpret_cast<uint4 *>(p.packed_rw + (sib - p.packed) + 8 * lvl); // the packed record becomes complete
+                    dst[0] = make_uint4(nxt[0], nxt[1], nxt[2], nxt[3]);
+                    dst[1] = make_uint4(nxt[4], nxt[5], nxt[6], nxt[7]);
+                }
+            }
+            if (KMODE == 2) { // which query's node IS this sibling?  (lowest such query; 0xff = none: the digest has to be shipped)
+                uint32_t found = 0xffu;
+#pragma unroll 1
+                for (uint32_t j = 0; j < Q; j++) {
+                    const uint32_t c0 = __shfl_sync(0xffffffffu, cur[0], grp_base + j);
+                    if (__any_sync(0xffffffffu, c0 == nxt[0] && j != q && j < used && found == 0xffu)) {
+                        bool same = c0 == nxt[0];
+#pragma unroll
+                        for (int k = 1; k < 8; k++) same = (__shfl_sync(0xffffffffu, cur[k], grp_base + j) == nxt[k]) && same;
+                        if (same && j != q && j < used && found == 0xffu) found = j;
+                    }
+                }
+                if (active) dv[lvl] = (uint8_t)found;
+            }
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 w[k] = cur_left ? cur[k] : nxt[k];
@@ -612,6 +927,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
 #define DD_INVALID 0x40u
 #define DD_SIBDIFF 0x20u
 #define DD_SAMELEAF 0x1000u // follower whose leaf position IS its leader's (h = 0): nothing to hash in round 1
+#define DD_UNUSED 0x2000u   // query slot >= U under SSYM_MODE_QUERY_DEDUP: no chain
 
 // Appends chain `c` to bin `bin` of round `round`: counters privatised in shared memory, one global atomic per (CTA, bin).
 // Every thread of the CTA calls this (want = false for threads with nothing to append; up to two appends per thread).
@@ -645,7 +961,8 @@ __global__ void __launch_bounds__(512) stwo_plan_kernel(StwoParams p) {
     const bool in_range = i < p.n; // uniform over the 16-lane group
     const uint32_t lane = threadIdx.x & 31u, gmask = 0xffffu << (lane & 16u);
     const uint32_t d = pl == 0 ? G : G - pl, shift = pl;
-    const bool act = in_range && q < Q;
+    const bool slot = in_range && q < Q;
+    const bool act = slot && q < p.ctx[(size_t)i * CX::WORDS + CX::N_USED]; // slots >= U are not looked at (SSYM_MODE_QUERY_DEDUP)
     const uint32_t pos = act ? p.ctx[(size_t)i * CX::WORDS + CX::QUERIES + q] >> shift : 0u;
     uint32_t h = d, lead = DD_NONE;
     for (uint32_t r = 0; r < 15; r++) {
@@ -657,7 +974,7 @@ __global__ void __launch_bounds__(512) stwo_plan_kernel(StwoParams p) {
     }
     // REF_LITERAL: fri_answer (fri/answers.simf:116-126) gives evaluations no prover's FRI trees were built from, so every query's FRI
     // path starts from a leaf of its own and nothing can be shared there: plan those trees per query straight away.
-    if (pl >= 1 && p.cfg.mode == SSYM_MODE_REF_LITERAL) { h = d; lead = DD_NONE; }
+    if (pl >= 1 && SSYM_MODE_SEMANTICS(p.cfg.mode) == SSYM_MODE_REF_LITERAL) { h = d; lead = DD_NONE; }
     const bool follower = act && lead != DD_NONE;
     // leaders: which of my nodes the followers need (at most one follower per height >= 1: three paths cannot first meet in one node)
     uint32_t mask = 0;
@@ -682,6 +999,10 @@ __global__ void __launch_bounds__(512) stwo_plan_kernel(StwoParams p) {
             p.dd.ckpt_to[c] = to;
             if (!same_leaf) { bin[n_app] = p.dd.bin_of[0][kind][lv]; chain[n_app] = c; n_app++; }
         }
+    }
+    if (slot && !act) { // an unused slot: no chain; the check / resolve kernels skip it
+        const uint32_t n_trees = pl == 0 ? 2u : 1u;
+        for (uint32_t t = 0; t < n_trees; t++) p.dd.plan[i * CH + (pl == 0 ? t : pl + 1) * Q + q] = DD_UNUSED;
     }
     dd_append<2>(p.dd, 0, bin, chain, n_app, s_cnt, s_base);
 }
@@ -896,6 +1217,7 @@ __global__ void __launch_bounds__(256) stwo_resolve_kernel(StwoParams p) {
     const uint32_t *root = tree == 0 ? pk + lo.off_commit + 8 : tree == 1 ? pk + lo.off_commit + 16
                            : layer == 0 ? pk + lo.off_fri_first_root : pk + lo.off_fri_inner_root + 8 * (layer - 1);
     uint32_t src = cg, pw = p.dd.plan[src];
+    if (pw & DD_UNUSED) return;
     for (uint32_t hop = 0; hop < SSYM_MAX_QUERIES && (pw & DD_FOLLOWER) && !(pw & DD_INVALID); hop++) { // leaders have lower query numbers
         src = i * CH + tree * Q + ((pw >> 8) & 15u);
         pw = p.dd.plan[src];
@@ -1043,12 +1365,13 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     {
         // NP = 2 (two transcripts per thread in lockstep) raises a warp's issue rate from 0.34 to 0.46 per cycle, but a batch of 1024 proofs has
         // fewer warps than the GPU has schedulers: the launch takes 0.211 ms instead of 0.143 ms.  A knob for very large batches only.
-#ifdef SSYM_TUNING // experiment builds only (build.py --tuning): SSYM_CHANNEL_NP=2 runs two transcripts per thread
-        static const int np = [] { const char *e = getenv("SSYM_CHANNEL_NP"); return e ? atoi(e) : 1; }();
+#ifdef SSYM_TUNING // experiment builds only (build.py --tuning): SSYM_CHANNEL_NP = 1 / 2 runs the one-thread-per-proof kernel with 1 / 2 transcripts per thread
+        static const int np = [] { const char *e = getenv("SSYM_CHANNEL_NP"); return e ? atoi(e) : 0; }();
         if (np == 2 && p.n > 1) stwo_channel_kernel<2><<<((p.n + 1) / 2 + 63) / 64, 64, 0, s1>>>(p, sha_mul_consts());
+        else if (np == 1) stwo_channel_kernel<1><<<(p.n + 63) / 64, 64, 0, s1>>>(p, sha_mul_consts());
         else
 #endif
-            stwo_channel_kernel<1><<<(p.n + 63) / 64, 64, 0, s1>>>(p, sha_mul_consts());
+            stwo_channel_ws_kernel<<<(p.n + 31) / 32, 96, 0, s1>>>(p, sha_mul_consts());
     }
     if (use_front && front_kernels < 2) { cudaEventRecord(front_done, front); cudaStreamWaitEvent(s, front_done, 0); }
     if (prof) { prof->end(0, s); prof->begin(1, s); }
@@ -1058,7 +1381,7 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     case 16: stwo_query_kernel<16><<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p); break;
     default: stwo_query_kernel<SSYM_NUM_COLUMNS><<<(p.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s2>>>(p); break;
     }
-    if (p.dd.enabled) { // decided by the caller (ssym_set_merkle_sharing)
+    if (p.dd.enabled && !p.derive_mode) { // decided by the caller (ssym_set_merkle_sharing); the compact form's derived siblings need the per-query kernel
         // shared-node schedule: plan (on the front stream with K1 / K2 when pipelined), hash the distinct nodes, check the followers, hash
         // what did not match, resolve every query
         stwo_plan_kernel<<<(p.n * (L + 2) * 16 + 511) / 512, 512, 0, s2>>>(p);
@@ -1082,6 +1405,10 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     const uint64_t warps = (uint64_t)groups * (L + 3);
     const uint32_t grid = (uint32_t)((warps + 3) / 4);
 #define SSYM_LAUNCH_MERKLE(AM, RL) stwo_merkle_kernel<AM, RL><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts())
+    if (p.derive_mode) { // compact transport form, version 3: derived siblings (1) / the packer's scan (2)
+        if (p.derive_mode == 1) stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 1><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts());
+        else stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 2><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts());
+    } else {
 #ifdef SSYM_TUNING
     // experiment builds only (build.py --tuning; sha256.cuh): which adds go to the FMA pipe, and whether the 64 rounds are rolled into 4 x 16.
     // The release library contains the one variant DESIGN.md section 4 arrives at.
@@ -1104,6 +1431,7 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
 #else
     SSYM_LAUNCH_MERKLE(SSYM_DEFAULT_ADDMODE, SSYM_DEFAULT_ROLLED != 0);
 #endif
+    }
     if (prof) { prof->end(2, s); prof->begin(3, s); }
     stwo_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
     if (prof) prof->end(3, s);

@@ -35,7 +35,8 @@ struct StwoCtxLayout {
         P2X = 68,        // [4]    sample point of the 16 CP columns: P (REF_LITERAL) or 2P (PROVER_CONSISTENT, Appendix A item 1)
         P2Y = 72,        // [4]
         ALPHA_POW = 76,  // [C + 17][4] deep_alpha^(k+1), k = 0..C+16 (the last: the batch coefficient of fri/answers.simf:126); C <= 16
-        WORDS = 76 + 4 * (SSYM_MAX_COLUMNS + SSYM_NUM_CP_PARTITIONS + 1)
+        N_USED = 76 + 4 * (SSYM_MAX_COLUMNS + SSYM_NUM_CP_PARTITIONS + 1), // [1] U: queries verified (= n_queries, or the distinct ones under SSYM_MODE_QUERY_DEDUP)
+        WORDS = N_USED + 4
     };
 };
 
@@ -86,6 +87,14 @@ struct StwoParams {
     ssym_stwo_trace_t *trace; // n or nullptr
     uint32_t n;
     StwoDedup dd;
+    // Compact transport form, version 3 (compact_kernels.cuh): one byte per sibling slot of a proof (slot order = the compact record's: trace [Q][G],
+    // composition [Q][G], FRI layer l [Q][G-1-l]), at derive + i * derive_stride.
+    //   derive_mode 1 (verify / expand): byte p < Q = the slot's sibling is NOT in the record: it is the node of query p's path of the same tree at
+    //     the same level (the Merkle kernel takes it from p's lane and writes it into the packed record); 0xff = the sibling is in the packed record.
+    //   derive_mode 2 (pack): the kernel WRITES the table: for every slot the lowest p whose node equals the slot's sibling, else 0xff.
+    uint8_t *derive;
+    uint32_t derive_stride, derive_mode;
+    uint32_t *packed_rw; // = packed, writable (derive_mode 1)
 };
 
 // Fills the static part of StwoDedup (bins, capacities) for a configuration and a chunk capacity of `cap` proofs; returns the number of

@@ -45,7 +45,7 @@ static bool read_file(const std::string &path, std::string &out) {
 static void usage() {
     fprintf(stderr,
             "usage: verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--columns {4,8,16}] [--mode {ref-literal,prover-consistent}]\n"
-            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--cost] [--quiet] [--host-pack]\n");
+            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--cost] [--dedup-queries] [--quiet] [--host-pack]\n");
 }
 
 static std::string hex_digest(const uint32_t *w) {
@@ -65,7 +65,7 @@ int main(int argc, char **argv) {
     size_t replicate = 1;
     int gpus = 1;
     uint32_t columns = SSYM_NUM_COLUMNS; // NUM_COLUMNS of the program the witnesses were made for (config.simf:14)
-    bool quiet = false, host_pack = false, want_cost = false;
+    bool quiet = false, host_pack = false, want_cost = false, dedup = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](const char *what) -> std::string {
@@ -85,6 +85,7 @@ int main(int argc, char **argv) {
         else if (a == "--trace") trace_path = next("--trace");
         else if (a == "--quiet") quiet = true;
         else if (a == "--cost") want_cost = true;
+        else if (a == "--dedup-queries") dedup = true;
         else if (a == "--host-pack") host_pack = true;
         else if (a == "--help" || a == "-h") { usage(); return 0; }
         else { fprintf(stderr, "Error: unknown argument %s\n", a.c_str()); usage(); return 2; }
@@ -104,6 +105,7 @@ int main(int argc, char **argv) {
     if (mode == "ref-literal") mode_id = SSYM_MODE_REF_LITERAL;
     else if (mode == "prover-consistent") mode_id = SSYM_MODE_PROVER_CONSISTENT;
     else { usage(); return 2; }
+    if (dedup) mode_id |= SSYM_MODE_QUERY_DEDUP; // fri/queries.simf:41: sort the queries and drop duplicates (include/ssym.h)
 
     const size_t n_files = witnesses.size(), n = n_files * replicate;
     std::vector<uint8_t> parse_reject(n_files, 0); // ill-typed or ill-shaped witness: simfony would refuse it -> reject
@@ -246,7 +248,7 @@ int main(int argc, char **argv) {
         uint64_t total[SSYM_COST_FIELDS] = {0};
         for (size_t i = 0; i < n; i++) {
             ssym_cost_t c;
-            if (parse_reject[i % n_files] || ssym_stwo_cost(&cfg, traces[i].queries, traces[i].draw_retries, &c) != SSYM_OK) continue;
+            if (parse_reject[i % n_files] || ssym_stwo_cost(&cfg, traces[i].queries, traces[i].n_queries_used, traces[i].draw_retries, &c) != SSYM_OK) continue;
             const uint64_t *v = reinterpret_cast<const uint64_t *>(&c);
             if (!quiet) printf("cost %s", witnesses[i % n_files].c_str());
             for (int k = 0; k < SSYM_COST_FIELDS; k++) {

@@ -14,10 +14,12 @@ from . import _lib
 from ._lib import MEM_DEVICE, MEM_HOST, S101Trace, SsymError, StwoConfig, StwoLayout, StwoTrace, check, load
 
 
-def stwo_config(preset: str = "prod", mode: int = _lib.MODE_REF_LITERAL, n_columns: int = 4) -> StwoConfig:
+def stwo_config(preset: str = "prod", mode: int = _lib.MODE_REF_LITERAL, n_columns: int = 4, dedup_queries: bool = False) -> StwoConfig:
     """The two presets of stwo-verifier/src/config.simf:10-51; n_columns = NUM_COLUMNS (config.simf:14: 4 at reference HEAD; 8 and 16 widen
-    the same wide-Fibonacci AIR)."""
+    the same wide-Fibonacci AIR); dedup_queries = the SSYM_MODE_QUERY_DEDUP flag (sorted distinct queries, fri/queries.simf:41)."""
     cfg = StwoConfig()
+    if dedup_queries:
+        mode |= _lib.MODE_QUERY_DEDUP
     check(load().ssym_stwo_config_preset(preset.encode(), mode, C.byref(cfg)))
     cfg.n_columns = n_columns
     return cfg
@@ -184,6 +186,18 @@ class Verifier:
         flags = self._alloc(blob, n) if want_flags else None
         check(self.lib.ssym_stwo_compact_expand(self.h, C.byref(cfg), _ptr(blob), _ptr(offsets), n, _ptr(packed), _ptr(flags), self._space(blob)))
         return packed, flags
+
+    def stwo_compact_hints(self, packed, cfg: StwoConfig, n: Optional[int] = None):
+        """For every sibling slot of every packed proof: the lowest query whose Merkle path reaches a node equal to that sibling at that level,
+        or 0xff (ssym_stwo_compact_hints; slot order = the compact record's).  Returns an (n, slots) uint8 array / tensor."""
+        lo = stwo_layout(cfg)
+        total = packed.numel() if hasattr(packed, "numel") else packed.size
+        n = total // lo.stride_words if n is None else n
+        Q, L, G = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log
+        slots = Q * (2 * G + sum(G - 1 - l for l in range(L + 1)))
+        hints = self._alloc(packed, (n, slots), np.uint8)
+        check(self.lib.ssym_stwo_compact_hints(self.h, C.byref(cfg), _ptr(packed), n, _ptr(hints), self._space(packed)))
+        return hints
 
     def stwo_verify_compact_batch(self, blob, offsets, cfg: StwoConfig, want_status: bool = False, accept_out=None, status_out=None):
         """stwo_verify_batch on compact records (include/ssym.h "compact transport form"): with host arrays, the compact bytes are what

@@ -189,10 +189,12 @@ def pack_stark101_proof_json(proof: Dict[str, Any]) -> np.ndarray:
     return blob
 
 
-def compact_stwo(packed: np.ndarray, cfg: StwoConfig, out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+def compact_stwo(packed: np.ndarray, cfg: StwoConfig, out: Optional[np.ndarray] = None, ver=None) -> Tuple[np.ndarray, np.ndarray]:
     """Packed records -> the compact transport form (ssym_stwo_compact_pack, include/ssym.h): per tree every distinct sibling once plus
     one bit per path slot and one back reference per repeated slot; lossless for any record.  Returns (blob of u32 words, u64 word offsets [n + 1]); `out` may be a
-    preallocated (e.g. pinned) uint32 array of at least ssym_stwo_compact_bound words."""
+    preallocated (e.g. pinned) uint32 array of at least ssym_stwo_compact_bound words.
+    ver: a Verifier -> version 3 records (ssym_stwo_compact_pack_gpu): the GPU finds the siblings that are nodes of other queries' paths and
+    they are left out too (bound to cfg's semantics; see include/ssym.h)."""
     lib = load()
     lo = stwo_layout(cfg)
     flat = np.ascontiguousarray(np.asarray(packed, dtype=np.uint32).ravel())
@@ -202,7 +204,10 @@ def compact_stwo(packed: np.ndarray, cfg: StwoConfig, out: Optional[np.ndarray] 
     bound = int(lib.ssym_stwo_compact_bound(C.byref(cfg), n))
     buf = out if out is not None else np.zeros(bound, dtype=np.uint32)
     offsets = np.zeros(n + 1, dtype=np.uint64)
-    check(lib.ssym_stwo_compact_pack(C.byref(cfg), C.c_void_p(flat.ctypes.data), n, C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(offsets.ctypes.data)))
+    if ver is not None:
+        check(lib.ssym_stwo_compact_pack_gpu(ver.h, C.byref(cfg), C.c_void_p(flat.ctypes.data), n, C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(offsets.ctypes.data)))
+    else:
+        check(lib.ssym_stwo_compact_pack(C.byref(cfg), C.c_void_p(flat.ctypes.data), n, C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(offsets.ctypes.data)))
     return (buf if out is not None else buf[:int(offsets[n])].copy()), offsets
 
 

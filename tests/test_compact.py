@@ -25,8 +25,90 @@ def ocfg(cfg):
     return O.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
 
 
-def numpy_expand(S, cfg, blob, offsets):
-    """Independent restatement of the record format (include/ssym.h): compact -> packed."""
+MAGIC3 = 0x33435353
+
+
+def _sha(words):
+    import hashlib
+
+    return np.frombuffer(hashlib.sha256(np.asarray(words, dtype=">u4").tobytes()).digest(), dtype=">u4").astype(np.uint32)
+
+
+def tree_geometry(cfg):
+    """[(first sibling word of query 0, depth)] per tree in record order, as a function of the layout."""
+    Q, L, G = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log
+    return [G, G] + [G - 1 - l for l in range(L + 1)]
+
+
+def path_nodes(S, orc, cfg, rec, derive=None):
+    """Independent restatement (hashlib + the oracle's trace for the queries and the FRI evaluations) of the nodes every query's Merkle path runs
+    through: nodes[tree][q][k] = the path's node at level k (k = 0: the leaf / leaf pair), for k = 0 .. depth.  With `derive` (slot -> partner query or
+    0xff) the siblings of derived slots are taken from the partner's node — level by level, as the record format defines them — and written into rec."""
+    lo = S.stwo_layout(cfg)
+    Q, L, G, C_ = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log, cfg.n_columns or 4
+    _, _, tr = orc.stwo_verify_batch(ocfg(cfg), rec, 1, want_trace=True)
+    t = tr[0]
+    U = t.n_queries_used
+    queries = list(t.queries)
+    depths = tree_geometry(cfg)
+    sib_off = [lo.off_trace_sib, lo.off_cp_sib] + [lo.off_fri_sib[l] for l in range(L + 1)]
+    nodes, slot0 = [], 0
+    for tree, d in enumerate(depths):
+        cur, pos = [], []
+        for q in range(Q):
+            if tree < 2:
+                qv = rec[lo.off_qvals + (C_ + 16) * q: lo.off_qvals + (C_ + 16) * (q + 1)]
+                cur.append(_sha(qv[:C_] if tree == 0 else qv[C_:]))
+                pos.append(queries[q])
+            else:
+                l = tree - 2
+                ev = np.array(t.fri_answer[q] if l == 0 else t.folded[l - 1][q], dtype=np.uint32)
+                wit = rec[lo.off_fri_wit + (l * Q + q) * 4: lo.off_fri_wit + (l * Q + q) * 4 + 4]
+                fq = queries[q] >> l
+                e0, e1 = (ev, wit) if fq % 2 == 0 else (wit, ev)
+                cur.append(_sha(np.concatenate([_sha(e0), _sha(e1)])))
+                pos.append(fq >> 1)
+        levels = [[c.copy() for c in cur]]
+        for k in range(d):
+            nxt = []
+            for q in range(Q):
+                at = sib_off[tree] + (q * d + k) * 8
+                if derive is not None and derive[slot0 + q * d + k] != 0xFF and q < U:
+                    rec[at:at + 8] = levels[k][int(derive[slot0 + q * d + k])]
+                sib = rec[at:at + 8]
+                pair = (levels[k][q], sib) if (pos[q] >> k) % 2 == 0 else (sib, levels[k][q])
+                nxt.append(_sha(np.concatenate(pair)))
+            levels.append(nxt)
+        nodes.append(levels)
+        slot0 += Q * d
+    return nodes, U
+
+
+def python_hints(S, orc, cfg, rec):
+    """Independent restatement of ssym_stwo_compact_hints for one packed record."""
+    Q = cfg.n_queries
+    lo = S.stwo_layout(cfg)
+    L = cfg.n_fri_layers
+    nodes, U = path_nodes(S, orc, cfg, rec.copy())
+    depths = tree_geometry(cfg)
+    sib_off = [lo.off_trace_sib, lo.off_cp_sib] + [lo.off_fri_sib[l] for l in range(L + 1)]
+    out = []
+    for tree, d in enumerate(depths):
+        for q in range(Q):
+            for k in range(d):
+                sib = rec[sib_off[tree] + (q * d + k) * 8: sib_off[tree] + (q * d + k) * 8 + 8]
+                hit = 0xFF
+                if q < U:
+                    for p_ in range(U):
+                        if p_ != q and (nodes[tree][k][p_] == sib).all():
+                            hit = p_
+                            break
+                out.append(hit)
+    return np.array(out, dtype=np.uint8)
+
+
+def numpy_expand(S, cfg, blob, offsets, orc=None):
+    """Independent restatement of the record format (include/ssym.h): compact -> packed.  Version 3 records (derived slots) need `orc`."""
     lo = S.stwo_layout(cfg)
     Q, L, G = cfg.n_queries, cfg.n_fri_layers, cfg.lde_log
     depths = [G, G] + [G - 1 - l for l in range(L + 1)]
@@ -38,25 +120,40 @@ def numpy_expand(S, cfg, blob, offsets):
     bitmap_words = ((slots + 31) // 32 + 7) // 8 * 8
     for i in range(n):
         rec = blob[int(offsets[i]):int(offsets[i + 1])]
-        assert rec[0] == len(rec) and rec[2] == MAGIC and len(rec) % 8 == 0
-        D, R = int(rec[1]), int(rec[3])
-        assert D + R == slots
+        assert rec[0] == len(rec) and rec[2] in (MAGIC, MAGIC3) and len(rec) % 8 == 0
+        v3 = rec[2] == MAGIC3
+        D, R, X = int(rec[1]), int(rec[3]), int(rec[4]) if v3 else 0
+        assert D + R + X == slots
         off_wit = 8 + fixed
         off_bitmap = off_wit + wit
-        off_refs = off_bitmap + bitmap_words
-        refs_words = (R * idx_bytes + 31) // 32 * 8
+        off_bitmap2 = off_bitmap + bitmap_words
+        off_refs = off_bitmap2 + bitmap_words if v3 else off_bitmap2
+        refs_words = (R * idx_bytes + X + 31) // 32 * 8
         off_tab = off_refs + refs_words
         assert len(rec) == off_tab + 8 * D
         out[i, :fixed] = rec[8:8 + fixed]
         out[i, lo.off_fri_wit:lo.off_fri_wit + wit] = rec[off_wit:off_bitmap]
-        bits = np.unpackbits(rec[off_bitmap:off_refs].view(np.uint8), bitorder="little")
-        assert int(bits[:slots].sum()) == D
-        refs = rec[off_refs:off_tab].view(np.uint8 if idx_bytes == 1 else np.uint16)
+        bits = np.unpackbits(rec[off_bitmap:off_bitmap2].view(np.uint8), bitorder="little")
+        bits2 = np.unpackbits(rec[off_bitmap2:off_refs].view(np.uint8), bitorder="little") if v3 else np.zeros(len(bits), dtype=np.uint8)
+        assert int(bits[:slots].sum()) == D and int(bits2[:slots].sum()) == X and not (bits[:slots] & bits2[:slots]).any()
+        if X:
+            assert orc is not None and int(rec[5]) == (cfg.mode & 1) and 32 % Q == 0
+        ref_bytes = rec[off_refs:off_tab].view(np.uint8)
+        refs = ref_bytes[:R * idx_bytes].view(np.uint8 if idx_bytes == 1 else np.uint16)
+        partners = ref_bytes[R * idx_bytes:R * idx_bytes + X]
         tab = rec[off_tab:].reshape(D, 8)
-        s = new = ref = 0
+        derive = np.full(slots, 0xFF, dtype=np.uint8)
+        s = new = ref = der = 0
         for t, d in enumerate(depths):
             tree_first = new
             for k in range(Q * d):
+                dst = lo.off_trace_sib + 8 * s if s < 2 * Q * G else lo.off_fri_sib[0] + 8 * (s - 2 * Q * G)
+                if bits2[s]:
+                    derive[s] = partners[der]
+                    der += 1
+                    assert derive[s] < Q and derive[s] != k // d
+                    s += 1
+                    continue
                 if bits[s]:
                     e = new
                     new += 1
@@ -64,9 +161,10 @@ def numpy_expand(S, cfg, blob, offsets):
                     e = tree_first + int(refs[ref])
                     ref += 1
                     assert e < new
-                dst = lo.off_trace_sib + 8 * s if s < 2 * Q * G else lo.off_fri_sib[0] + 8 * (s - 2 * Q * G)
                 out[i, dst:dst + 8] = tab[e]
                 s += 1
+        if X:  # the derived siblings: what verify_proof computes on the partner's path from this very record
+            path_nodes(S, orc, cfg, out[i], derive)
     return out
 
 
@@ -91,7 +189,8 @@ def test_compact_pack_is_lossless_and_smaller(S, orc, preset, nc):
     assert (numpy_expand(S, cfg, blob, offsets) == recs).all()
     sizes = np.diff(offsets.astype(np.int64)) * 4
     bound = S.load().ssym_stwo_compact_bound(__import__("ctypes").byref(cfg), 1) * 4
-    assert sizes[-1] == bound  # noise: nothing to share
+    slots = cfg.n_queries * sum(tree_geometry(cfg))
+    assert sizes[-1] == bound - ((slots + 31) // 32 + 7) // 8 * 32  # noise: nothing to share (the bound also covers version 3's second bitmap)
     if preset == "prod":
         assert (sizes[:6] < 0.80 * lo.stride_words * 4).all(), sizes[:6]  # honest proofs: >= 20 % fewer bytes on the link
     # the shipped fixture
@@ -100,6 +199,46 @@ def test_compact_pack_is_lossless_and_smaller(S, orc, preset, nc):
         packed, bad = S.witness.pack_stwo_wits([text], cfg)
         b2, o2 = S.witness.compact_stwo(packed, cfg)
         assert not bad[0] and (numpy_expand(S, cfg, b2, o2)[0] == packed).all()
+
+
+def _pack_hinted(S, cfg, recs, hints):
+    import ctypes as C
+
+    lib = S.load()
+    lo = S.stwo_layout(cfg)
+    flat = np.ascontiguousarray(recs.ravel())
+    n = flat.size // lo.stride_words
+    buf = np.zeros(int(lib.ssym_stwo_compact_bound(C.byref(cfg), n)), dtype=np.uint32)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    h = np.ascontiguousarray(hints, dtype=np.uint8)
+    S._lib.check(lib.ssym_stwo_compact_pack_hinted(C.byref(cfg), C.c_void_p(flat.ctypes.data), C.c_void_p(h.ctypes.data), n, C.c_void_p(buf.ctypes.data), buf.size,
+                                                   C.c_void_p(offsets.ctypes.data)))
+    return buf[: int(offsets[n])].copy(), offsets
+
+
+@pytest.mark.parametrize("preset,mode", [("testing", 1), ("prod", 1), ("prod", 0)])
+def test_version3_records_leave_out_derivable_siblings(S, orc, preset, mode):
+    """The host assembler (ssym_stwo_compact_pack_hinted) fed with hints from the independent Python scan: version 3 records expand — through the
+    independent expander, which recomputes the partner's node with hashlib and the oracle's trace — to exactly the packed records, honest or
+    corrupted, and an honest prod proof shrinks to about the size of upstream's minimal decommitment."""
+    cfg = S.stwo_config(preset, mode)
+    lo = S.stwo_layout(cfg)
+    recs = _records(S, orc, cfg, np.random.default_rng(3))[[0, 1, 6, 7, 8, 11, 14, 15]] if preset == "prod" else _records(S, orc, cfg, np.random.default_rng(3))
+    hints = np.stack([python_hints(S, orc, cfg, r) for r in recs])
+    blob, offsets = _pack_hinted(S, cfg, recs, hints)
+    assert (numpy_expand(S, cfg, blob, offsets, orc) == recs).all()
+    v2_blob, v2_off = S.witness.compact_stwo(recs, cfg)
+    sizes, v2_sizes = np.diff(offsets.astype(np.int64)) * 4, np.diff(v2_off.astype(np.int64)) * 4
+    if preset == "prod":
+        X = [int(blob[int(offsets[i]) + 4]) for i in range(len(recs))]
+        if mode == 1:  # honest proofs (records 0, 1): every merge of two paths leaves two siblings out, in all 11 trees
+            assert X[0] > 200 and X[1] > 200 and sizes[0] < 0.62 * lo.stride_words * 4 and sizes[0] < v2_sizes[0] - 6000, (X, sizes, v2_sizes)
+        else:  # REF_LITERAL: the FRI evaluations are not the prover's (finding F1): only the trace and composition trees have derivable siblings
+            assert 100 <= X[0] <= 180 and sizes[0] < v2_sizes[0], (X, sizes)
+        assert X[-1] == 0  # noise
+    # all-0xff hints give a version 3 record without derived slots; no hints give the version 2 record
+    b0, o0 = _pack_hinted(S, cfg, recs[:2], np.full_like(hints[:2], 0xFF))
+    assert int(b0[2]) == MAGIC3 and int(b0[4]) == 0 and (numpy_expand(S, cfg, b0, o0, orc) == recs[:2]).all()
 
 
 def test_compact_pack_errors(S, orc):
@@ -150,6 +289,121 @@ def test_gpu_expand_and_verify_compact(S, ver, orc, preset, nc):
         assert (d_status.cpu().numpy().view(np.uint32) == ref_status).all() and (d_accept.cpu().numpy().view(np.uint32) == ref_accept).all()
         if mode == S.MODE_PROVER_CONSISTENT:
             assert (status[:6] == 0).all() and (status[6:] != 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,nc,mode", [("testing", 4, 1), ("prod", 4, 1), ("prod", 4, 0), ("prod", 16, 1)])
+def test_gpu_version3_pack_expand_verify(S, ver, orc, preset, nc, mode):
+    """Version 3 records end to end on the GPU: the scan kernel's hints equal the independent Python scan, the GPU-assisted packer's records
+    expand (GPU, host and device buffers) to exactly the packed records and (independent expander) too, verdicts from compact buffers equal the
+    packed path's and the oracle's, and a record with derived slots presented under the other semantics is refused, not mis-expanded."""
+    import torch
+
+    cfg = S.stwo_config(preset, mode, n_columns=nc)
+    recs = _records(S, orc, cfg, np.random.default_rng(4))
+    n = len(recs)
+    hints = ver.stwo_compact_hints(recs.ravel(), cfg, n)
+    for i in (0, 1, 6, n - 1):
+        assert (hints[i] == python_hints(S, orc, cfg, recs[i])).all(), i
+    d_hints = ver.stwo_compact_hints(torch.from_numpy(recs.view(np.int32)).cuda().view(-1), cfg, n)
+    ver.synchronize()
+    assert (d_hints.cpu().numpy() == hints).all()
+    blob, offsets = S.witness.compact_stwo(recs, cfg, ver=ver)
+    assert int(blob[2]) == MAGIC3 and (int(blob[4]) > 0) == (cfg.n_queries > 1)
+    v2_blob, _ = S.witness.compact_stwo(recs, cfg)
+    assert blob.size <= v2_blob.size + n * 64
+    assert (numpy_expand(S, cfg, blob[: int(offsets[3])], offsets[:4], orc) == recs[:3]).all()
+    packed, flags = ver.stwo_compact_expand(blob, offsets, cfg, want_flags=True)
+    assert not flags.any() and (packed == recs).all()
+    d_blob, d_off = torch.from_numpy(blob.view(np.int32)).cuda(), torch.from_numpy(offsets.view(np.int64)).cuda()
+    d_packed, d_flags = ver.stwo_compact_expand(d_blob, d_off, cfg, want_flags=True)
+    ver.synchronize()
+    assert (d_packed.cpu().numpy().view(np.uint32) == recs).all() and not d_flags.cpu().numpy().any()
+    ref_accept, ref_status, _ = ver.stwo_verify_batch(recs.ravel(), cfg, n, want_status=True)
+    _, o_status, _ = orc.stwo_verify_batch(ocfg(cfg), recs.ravel(), n)
+    assert (ref_status == o_status).all()
+    accept, status = ver.stwo_verify_compact_batch(blob, offsets, cfg, want_status=True)
+    assert (status == ref_status).all() and (accept == ref_accept).all()
+    d_accept, d_status = ver.stwo_verify_compact_batch(d_blob, d_off, cfg, want_status=True)
+    ver.synchronize()
+    assert (d_status.cpu().numpy().view(np.uint32) == ref_status).all() and (d_accept.cpu().numpy().view(np.uint32) == ref_accept).all()
+    # the other semantics: records with derived slots are bound to the one they were packed under
+    other = S.stwo_config(preset, 1 - mode, n_columns=nc)
+    _, st_other = ver.stwo_verify_compact_batch(blob, offsets, other, want_status=True)
+    X = np.array([int(blob[int(offsets[i]) + 4]) for i in range(n)])
+    assert ((st_other >> 31 == 1) == (X > 0)).all()
+    _, want_other, _ = orc.stwo_verify_batch(ocfg(other), recs.ravel(), n)
+    assert (st_other[X == 0] == want_other[X == 0]).all()
+
+
+@pytest.mark.gpu
+def test_gpu_version3_chunks_async_and_corruptions(S, ver, orc):
+    """2100 distinct GPU-proven proofs (several staged chunks), every 7th corrupted, as version 3 records from pinned host buffers: synchronous and
+    enqueue-only calls give the packed path's statuses; then random corruptions of the record's bitmaps / partner bytes / header: the GPU flags the
+    record or expands it to exactly what the independent expander computes."""
+    cfg = S.stwo_config("prod", S.MODE_PROVER_CONSISTENT)
+    lo = S.stwo_layout(cfg)
+    n = 2100
+    proofs = ver.stwo_prove_batch(np.arange(n, dtype=np.uint64) + 7000, cfg)
+    classes = list(S.witness.stwo_negative_classes(cfg).values())
+    for j, row in enumerate(range(3, n, 7)):
+        w, d = classes[j % len(classes)]
+        proofs[row, w] = np.uint32((int(proofs[row, w]) + d) & 0xFFFFFFFF)
+    blob, offsets = S.witness.compact_stwo(proofs, cfg, ver=ver)
+    v2_blob, _ = S.witness.compact_stwo(proofs, cfg)
+    assert blob.size < 0.80 * v2_blob.size  # honest proofs lose about a quarter of their version 2 bytes
+    ref_accept, ref_status, _ = ver.stwo_verify_batch(proofs.ravel(), cfg, n, want_status=True)
+    accept, status = ver.stwo_verify_compact_batch(blob, offsets, cfg, want_status=True)
+    assert (status == ref_status).all() and (accept == ref_accept).all()
+    expanded, flags = ver.stwo_compact_expand(blob, offsets, cfg, want_flags=True)
+    assert (expanded == proofs).all() and not flags.any()
+    ver.set_host_async(True)
+    outs = [ver.stwo_verify_compact_batch(blob, offsets, cfg, want_status=True) for _ in range(3)]
+    ver.synchronize()
+    ver.set_host_async(False)
+    for a, st in outs:
+        assert (st == ref_status).all() and (a == ref_accept).all()
+    # corruptions of one record
+    rec = blob[: int(offsets[1])].copy()
+    w = rec.size
+    m = 120
+    tiled = np.tile(rec, m)
+    toff = np.arange(m + 1, dtype=np.uint64) * np.uint64(w)
+    rng = np.random.default_rng(5)
+    fixed, wit = lo.off_trace_sib, lo.off_fri_sib[0] - lo.off_fri_wit
+    slots = cfg.n_queries * sum(tree_geometry(cfg))
+    bm = ((slots + 31) // 32 + 7) // 8 * 8
+    off_bitmap = 8 + fixed + wit
+    off_refs = off_bitmap + 2 * bm
+    R, X = int(rec[3]), int(rec[4])
+    for i in range(1, m):
+        base = i * w
+        kind = i % 5
+        if kind == 0:
+            tiled[base + int(rng.integers(0, 6))] = np.uint32(rng.integers(0, 2**32))                                      # a header word
+        elif kind == 1:
+            tiled[base + off_bitmap + int(rng.integers(0, (slots + 31) // 32))] ^= np.uint32(1 << int(rng.integers(0, 32)))  # "new" bitmap
+        elif kind == 2:
+            tiled[base + off_bitmap + bm + int(rng.integers(0, (slots + 31) // 32))] ^= np.uint32(1 << int(rng.integers(0, 32)))  # "derived" bitmap
+        elif kind == 3:
+            tiled[base + off_refs:base + w].view(np.uint8)[R + int(rng.integers(0, X))] = np.uint8(rng.integers(0, 20))        # a partner byte
+        else:
+            tiled[base + off_refs + (R + X + 31) // 32 * 8 + int(rng.integers(0, 64))] ^= np.uint32(1)                         # a digest word
+    packed, flags = ver.stwo_compact_expand(tiled, toff, cfg, want_flags=True)
+    assert flags[0] == 0 and (packed[0] == proofs[0]).all()
+    seen = set()
+    for i in range(m):
+        r = tiled[i * w:(i + 1) * w]
+        try:
+            want = numpy_expand(S, cfg, r, np.array([0, w], dtype=np.uint64), orc)[0]
+        except (AssertionError, IndexError, ValueError):
+            want = None
+        if flags[i]:
+            assert not packed[i].any() and want is None, i
+        else:
+            assert want is not None and (packed[i] == want).all(), i
+        seen.add(int(flags[i]))
+    assert seen == {0, 1}
 
 
 @pytest.mark.gpu

@@ -27,13 +27,13 @@ def oracle_counts(orc, cfg, packed):
     return [int(x) for x in out], traces[0], int(status[0])
 
 
-def model_counts(S, cfg, queries, retries):
+def model_counts(S, cfg, queries, retries, used=None):
     from stark_symphony_b200 import _lib
 
     scfg = S.StwoConfig(cfg.trace_log, cfg.lde_log, cfg.n_queries, cfg.n_fri_layers, cfg.mode, cfg.n_columns, cfg.pow_target)
     cost = _lib.Cost()
     q = np.ascontiguousarray(queries, dtype=np.uint32)
-    S._lib.check(S.load().ssym_stwo_cost(C.byref(scfg), C.c_void_p(q.ctypes.data), retries, C.byref(cost)))
+    S._lib.check(S.load().ssym_stwo_cost(C.byref(scfg), C.c_void_p(q.ctypes.data), cfg.n_queries if used is None else used, retries, C.byref(cost)))
     return [cost.as_dict()[k] for k in _lib.COST_FIELDS]
 
 
@@ -80,6 +80,18 @@ def test_cost_usage_errors(S):
     cost = S._lib.Cost()
     cfg = S.stwo_config("prod", 0)
     q = np.zeros(16, dtype=np.uint32)
-    assert S.load().ssym_stwo_cost(None, C.c_void_p(q.ctypes.data), 0, C.byref(cost)) == S.ERR_USAGE
+    assert S.load().ssym_stwo_cost(None, C.c_void_p(q.ctypes.data), 16, 0, C.byref(cost)) == S.ERR_USAGE
+    assert S.load().ssym_stwo_cost(C.byref(cfg), C.c_void_p(q.ctypes.data), 15, 0, C.byref(cost)) == S.ERR_USAGE  # fewer used queries only under QUERY_DEDUP
     cfg.n_queries = 99
-    assert S.load().ssym_stwo_cost(C.byref(cfg), C.c_void_p(q.ctypes.data), 0, C.byref(cost)) == S.ERR_USAGE
+    assert S.load().ssym_stwo_cost(C.byref(cfg), C.c_void_p(q.ctypes.data), 99, 0, C.byref(cost)) == S.ERR_USAGE
+
+
+def test_cost_model_with_deduplicated_queries(S, orc):
+    """SSYM_MODE_QUERY_DEDUP: only the U distinct queries are verified; the model with n_queries_used = U equals the oracle's counters."""
+    for G, Q in ((5, 16), (6, 16), (9, 16)):
+        for sem in (O.MODE_REF_LITERAL, O.MODE_PROVER_CONSISTENT):
+            cfg = O.StwoConfig(3, G, Q, 2, sem | O.MODE_QUERY_DEDUP, 4, 0x07FFFFFFFFFFFFFF)
+            for rec in orc.stwo_prove_batch(cfg, np.array([21, 22, 23], dtype=np.uint64)):
+                want, tr, _ = oracle_counts(orc, cfg, rec)
+                assert tr.n_queries_used <= Q
+                assert model_counts(S, cfg, list(tr.queries)[:Q], tr.draw_retries, tr.n_queries_used) == want
