@@ -489,8 +489,10 @@ def main():
     if world > 1:
         dist.barrier()
     o0.record(stream)
+    oh0 = time.perf_counter()
     for k in range(other_steps):
         step(k, cfg_other, accept_other, statuses_other)
+    other_launch_ms = (time.perf_counter() - oh0) * 1e3
     ver.join()
     o1.record(stream)
     torch.cuda.synchronize()
@@ -547,6 +549,9 @@ def main():
         return {"pinned": pinned_buf, "blob": full[:words], "words": words, "off": off_t, "off_view": off_t.numpy().view(np.uint64), "pack_s": secs,
                 "derived_per_proof": int(full[4]) if int(full[2]) == 0x33435353 else 0}
 
+    # Every leg transports records packed under the mode it verifies under (one pass over the kernels).  Records packed under the other mode verify
+    # too — two passes, complete then verify (include/ssym.h) — but on this fixture that costs more GPU time than the bytes it saves on the link
+    # (measured: 1.26 M proofs/s with the 30.7 KB prover-consistent records under ref-literal against 1.40 M with the 38.6 KB ref-literal records).
     cp = pack_compact(cfg)
     cp_other = pack_compact(cfg_other)
     t0 = time.perf_counter()
@@ -705,7 +710,7 @@ def main():
         line.update({
             "other_mode": {"mode": other_name, "value": other_value, "unit": "proofs/s", "steps": other_steps, "accepted_per_gpu": other_accepted,
                            "kernel_ms": {k: v[0] / max(v[1], 1) for k, v in prof_by_mode[other_name].items()}, "serial_ms_per_pass": serial_ms[other_name],
-                           "whole_step_frac_int32_alu": other_frac,
+                           "whole_step_frac_int32_alu": other_frac, "timed_ms": other_ms, "launch_loop_ms": other_launch_ms,
                            "note": "same pipelined loop, same batch, the other semantics switch; under prover-consistent the fixture is ACCEPTED and the Merkle paths "
                                    "of a tree share the nodes above the height where they meet (hashed once, results per query identical: DESIGN.md section 4), "
                                    "so fewer compressions are executed than the reference's per-query count"},
@@ -716,7 +721,7 @@ def main():
                     "frac_of_concurrent_copy": (c_value / world * c_bytes / n / 1e9) / max(min(r[1] for r in conc_ranks), 1e-9),
                     "sync_call_value": c_sync, "bytes_per_proof": c_words * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
                     "gpu_launches_per_pass": c_launches,
-                    "derived_siblings_per_proof": cp["derived_per_proof"],
+                    "derived_siblings_per_proof": cp["derived_per_proof"], "records_packed_under": args.mode,
                     "host_pack": {"proofs_per_s": n / pack_s, "seconds_per_1024": pack_s, "inside_timed_region": False,
                                   "version2_host_only_proofs_per_s_per_core": n / pack_v2_s,
                                   "note": "ssym_stwo_compact_pack_gpu turns packed records into version 3 compact records BEFORE the clock starts: H2D of the packed "
@@ -725,10 +730,10 @@ def main():
                                           "version 2 records (no hashing, host only: ssym_stwo_compact_pack) cost `version2_host_only_proofs_per_s_per_core`"},
                     "other_mode": {"mode": other_name, "value": co_value, "sync_call_value": co_sync, "bytes_per_proof": cp_other["words"] * 4 / n,
                                    "derived_siblings_per_proof": cp_other["derived_per_proof"], "h2d_gbs_achieved": co_value / world * co_bytes / n / 1e9,
-                                   "note": "the same leg under the other semantics.  Which siblings can be left out depends on the proof being consistent with the "
-                                           "verifier: under ref-literal the fixture's FRI evaluations are not the ones its FRI trees were built from (finding F1, "
-                                           "DESIGN.md section 1), so only the trace and composition trees have derivable siblings; under prover-consistent all "
-                                           "eleven trees do and the record is the size of upstream stwo's minimal decommitment"},
+                                   "note": "the same leg under the other semantics, on records packed under it.  Which siblings can be left out depends on the proof "
+                                           "being consistent with the verifier: under ref-literal the fixture's FRI evaluations are not the ones its FRI trees were built "
+                                           "from (finding F1, DESIGN.md section 1), so only the trace and composition trees have derivable siblings; under "
+                                           "prover-consistent all eleven trees do and the record is the size of upstream stwo's minimal decommitment"},
                     "e2e_packed_value": p_value,
                     "note": "ssym_stwo_verify_compact_batch(SSYM_MEM_HOST) on pinned host buffers holding the batch in the compact transport form "
                             "(include/ssym.h, version 3: per Merkle tree every distinct 32-byte sibling once, none at all where another query's path computes it; "

@@ -346,14 +346,18 @@ int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint32_t *packed
  * level is the node the OTHER path has just computed — upstream stwo's decommitments leave those out (its `hash_witness` is minimal; the fork
  * that wrote the reference's fixtures expanded them, stwo-verifier/scripts/generate_wit.py:38-42,150-160).  A version 3 record marks such a
  * slot "derived" and stores one byte, the query whose path supplies the node:
- *   [2] SSYM_COMPACT_MAGIC3   [4] X = derived slots (S = D + R + X)   [5] the semantics (0 / 1) the record was packed under   [6 .. 8) 0
+ *   [2] SSYM_COMPACT_MAGIC3   [4] X = derived slots (S = D + R + X)   [5] cfg->mode the record was packed under   [6 .. 8) 0
  *   a second S-bit bitmap behind the first (1 = derived; never set together with "new"); the X partner bytes behind the R back references.
  * What a derived slot expands to is DEFINED as the node verify_proof computes on that path from this very record — from the queries its
  * transcript draws, the queried values (trace / composition trees) or the evaluations of fri_answer and the folds (FRI trees), and the
  * siblings below — so expansion is a function of the record and of the semantics alone, and ssym_stwo_compact_pack_hinted only marks a slot
- * whose stored digest IS that node (ssym_stwo_compact_hints compares them on the GPU): lossless for any record, honest or not.  For the FRI
- * trees this ties a record to the semantics it was packed under ([5]); under another one it is reported malformed.  Under REF_LITERAL the
- * fixtures' FRI paths do not verify (finding F1), so only their trace / composition trees have derivable siblings.  Requires 32 % Q == 0
+ * whose stored digest IS that node (ssym_stwo_compact_hints compares them on the GPU): lossless for any record, honest or not.  FRI leaves
+ * are hashes of COMPUTED evaluations, so the derived slots of a record are expanded under the mode it was packed under ([5]), whatever mode it
+ * is then verified under: from HOST buffers ssym_stwo_compact_expand / ssym_stwo_verify_compact_batch read that word (all records with derived
+ * slots of one call must carry the same one; another is reported malformed) and, where it differs from cfg->mode, verification takes two
+ * passes over the kernels — complete the records under their own mode, then verify under the call's.  Records in DEVICE memory are expanded
+ * under cfg->mode only (a record with derived slots of another mode is reported malformed).  A proof packed under REF_LITERAL has derivable
+ * siblings in its trace / composition trees only (its FRI paths do not verify, finding F1): pack under PROVER_CONSISTENT.  Requires 32 % Q == 0
  * (the Merkle kernel resolves a derived sibling with a warp shuffle between the Q chains of a tree); otherwise X = 0.
  * ssym_stwo_compact_hints: hints[i * S + s] = the lowest query whose node equals sibling slot s of proof i, or 0xff (S = the slots of a proof
  * in record order).  ssym_stwo_compact_pack_hinted: as ssym_stwo_compact_pack, hints == NULL gives version 2 records.

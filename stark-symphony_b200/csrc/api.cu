@@ -102,6 +102,7 @@ struct ssym_ctx {
         DevBuf stwo_ctx, stwo_evals, status;
         DevBuf dd_plan, dd_to, dd_own, dd_ckpt, dd_bins, dd_list; // shared-node Merkle schedule (StwoDedup)
         bool pending = false;
+        uint64_t scratch_key = 0; // what ensure_lane_scratch last sized this lane for (+ 1; 0 = nothing)
     };
     // Merkle schedule (ssym_set_merkle_sharing): 0 per-query kernel, 1 shared nodes where it pays (PROVER_CONSISTENT), 2 shared nodes always
     int merkle_sharing = [] { const char *e = getenv("SSYM_MERKLE_DEDUP"); return e ? atoi(e) : 1; }();
@@ -112,6 +113,9 @@ struct ssym_ctx {
     bool host_async = false;  // ssym_set_host_async: SSYM_MEM_HOST stwo calls return after enqueueing
     bool wit_host_fallback = true; // ssym_set_wit_host_fallback: witnesses the GPU tokeniser hands back are re-read by the host parser
     uint64_t host_chunks = 0; // staging-buffer parity persists across calls so that asynchronous calls can overlap
+    StwoDedup dd_cache{};       // static part of the shared-node plan for dd_cache_key (configuration, chunk size)
+    uint64_t dd_cache_key = 0;
+    size_t dd_cache_entries = 0;
     // domain tables (per config)
     DevBuf tab_point, tab_fold, tab_flag;
     uint32_t tab_G = 0, tab_L = 0xffffffffu;
@@ -359,6 +363,10 @@ static int ensure_tables(ssym_ctx *c, const ssym_stwo_config_t &cfg) {
 static int ensure_lane_scratch(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, size_t m, bool own_status) {
     const uint32_t Q = cfg.n_queries, L = cfg.n_fri_layers;
     m = std::min(m, STWO_DEVICE_CHUNK);
+    // a loop of equal calls (the pipelined hot path) asks for the same sizes every time: one key compare instead of the planner's bin layout per lane
+    const uint64_t key = ((uint64_t)m << 32) ^ ((uint64_t)Q << 24) ^ ((uint64_t)L << 16) ^ ((uint64_t)cfg.lde_log << 8) ^ ((uint64_t)SSYM_STWO_COLUMNS(&cfg) << 3) ^
+                         ((uint64_t)(cfg.mode & 3u) << 1) ^ (own_status ? 1u : 0u) ^ ((uint64_t)c->merkle_sharing << 60);
+    if (lane.scratch_key == key + 1) return SSYM_OK;
     CUDA_TRY(lane.stwo_ctx.ensure(m * StwoCtxLayout::WORDS * sizeof(uint32_t)));
     CUDA_TRY(lane.stwo_evals.ensure(m * (size_t)(L + 1) * Q * 4 * sizeof(uint32_t)));
     if (own_status) CUDA_TRY(lane.status.ensure(m * sizeof(uint32_t)));
@@ -374,6 +382,7 @@ static int ensure_lane_scratch(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stw
         CUDA_TRY(lane.dd_bins.ensure(2 * STWO_DEDUP_MAX_BINS * sizeof(uint32_t)));
         CUDA_TRY(lane.dd_list.ensure(list_entries * sizeof(uint32_t)));
     }
+    lane.scratch_key = key + 1;
     return SSYM_OK;
 }
 
@@ -408,7 +417,15 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
         p.packed_rw = const_cast<uint32_t *>(p.packed);
         memset(&p.dd, 0, sizeof p.dd);
         const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && SSYM_MODE_SEMANTICS(cfg.mode) == SSYM_MODE_PROVER_CONSISTENT);
-        if (share && stwo_dedup_layout(cfg, m, p.dd)) {
+        if (share) { // the static part of the plan (bins, capacities) depends on the configuration and the chunk size only: computed once
+            const uint64_t dkey = (((uint64_t)m << 32) ^ ((uint64_t)cfg.n_queries << 24) ^ ((uint64_t)cfg.n_fri_layers << 16) ^ ((uint64_t)cfg.lde_log << 8) ^ SSYM_STWO_COLUMNS(&cfg)) + 1;
+            if (c->dd_cache_key != dkey) {
+                c->dd_cache_entries = stwo_dedup_layout(cfg, m, c->dd_cache);
+                c->dd_cache_key = dkey;
+            }
+            if (c->dd_cache_entries) p.dd = c->dd_cache;
+        }
+        if (share && c->dd_cache_entries) {
             p.dd.plan = lane.dd_plan.as<uint32_t>();
             p.dd.ckpt_to = lane.dd_to.as<uint64_t>();
             p.dd.own = lane.dd_own.as<uint32_t>();
@@ -633,7 +650,7 @@ extern "C" int ssym_stwo_compact_pack_hinted(const ssym_stwo_config_t *cfg, cons
         memcpy(r8 + (size_t)R * sh.idx_bytes, partners.data(), X); // version 3: the partner queries of the derived slots
         memcpy(rec.data() + refs_at + refs_words, tab.data(), (size_t)D * 32);
         rec[0] = words; rec[1] = D; rec[2] = v3 ? SSYM_COMPACT_MAGIC3 : SSYM_COMPACT_MAGIC; rec[3] = R;
-        if (v3) { rec[4] = X; rec[5] = SSYM_MODE_SEMANTICS(cfg->mode); }
+        if (v3) { rec[4] = X; rec[5] = cfg->mode; }
         if (out_cap_words - pos < words) return fail(SSYM_ERR_NOMEM, "compact output buffer too small (ssym_stwo_compact_bound gives the worst case)");
         memcpy(out + pos, rec.data(), (size_t)words * 4);
         pos += words;
@@ -652,12 +669,14 @@ static int compact_prepare(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, ssym_st
 
 // A version 3 record leaves out the siblings another query's path computes (include/ssym.h).  host_has_derived: does any record of
 // blob[offsets[0] .. offsets[m]) (host memory) carry such slots?  Records without them take exactly the version 2 path.
-static bool host_has_derived(const uint32_t *blob, const uint64_t *offsets, size_t m) {
+// Returns -1 if none does, else the mode word (header [5]) of the first one: the derived slots of a call are expanded under ONE mode; a record
+// packed under another is reported malformed by the expansion kernel.
+static int64_t host_derived_mode(const uint32_t *blob, const uint64_t *offsets, size_t m) {
     for (size_t i = 0; i < m; i++) {
         const uint32_t *r = blob + offsets[i];
-        if (offsets[i + 1] - offsets[i] >= COMPACT_HDR_WORDS && r[2] == SSYM_COMPACT_MAGIC3 && r[4] != 0) return true;
+        if (offsets[i + 1] - offsets[i] >= COMPACT_HDR_WORDS && r[2] == SSYM_COMPACT_MAGIC3 && r[4] != 0) return (int64_t)r[5];
     }
-    return false;
+    return -1;
 }
 
 extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t *cfg, const uint32_t *blob, const uint64_t *offsets, size_t n,
@@ -672,8 +691,9 @@ extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t 
     cudaStream_t s = c->stream;
     const bool can_derive = (32u % cfg->n_queries) == 0;
     CompactParams p;
-    p.sh = sh; p.lo = lo; p.base = 0; p.mode = SSYM_MODE_SEMANTICS(cfg->mode); p.derive = nullptr;
+    p.sh = sh; p.lo = lo; p.base = 0; p.mode = cfg->mode; p.derive = nullptr;
     const size_t stride_b = (size_t)lo.stride_words * 4;
+    ssym_stwo_config_t xcfg = *cfg; // the configuration derived siblings are expanded under: the records' own mode where the host can see it
     if (memspace == SSYM_MEM_HOST) {
         for (size_t i = 0; i < n; i++)
             if (offsets[i + 1] < offsets[i]) return fail(SSYM_ERR_USAGE, "offsets must be non-decreasing");
@@ -704,7 +724,9 @@ extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t 
         const size_t m = std::min(STWO_DEVICE_CHUNK, n - done);
         bool derived = can_derive;
         if (memspace == SSYM_MEM_HOST) {
-            derived = can_derive && host_has_derived(blob, offsets + done, m);
+            const int64_t dm = host_derived_mode(blob, offsets + done, m);
+            derived = can_derive && dm >= 0 && dm <= 3;
+            if (derived) { xcfg.mode = (uint32_t)dm; p.mode = xcfg.mode; }
             const size_t words = offsets[done + m] - offsets[done];
             CUDA_TRY(cudaMemcpyAsync(c->cstage[0].p, blob + offsets[done], words * 4, cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(c->coffs[0].p, offsets + done, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
@@ -720,7 +742,7 @@ extern "C" int ssym_stwo_compact_expand(ssym_ctx_t *c, const ssym_stwo_config_t 
         launch_stwo_expand(p, s);
         c->launches += 1;
         if (derived) {
-            rc = stwo_launch_chunk(c, c->lanes[0], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>(), c->d_status.as<uint32_t>(), nullptr, s, false, p.derive,
+            rc = stwo_launch_chunk(c, c->lanes[0], xcfg, lo, p.packed, m, c->d_accept.as<uint32_t>(), c->d_status.as<uint32_t>(), nullptr, s, false, p.derive,
                                    sh.slots, 1);
             if (rc) return rc;
         }
@@ -809,7 +831,7 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     const bool can_derive = (32u % cfg->n_queries) == 0;
     cudaStream_t s = c->stream;
     CompactParams p;
-    p.sh = sh; p.lo = lo; p.mode = SSYM_MODE_SEMANTICS(cfg->mode); p.derive = nullptr;
+    p.sh = sh; p.lo = lo; p.mode = cfg->mode; p.derive = nullptr;
     if (memspace == SSYM_MEM_DEVICE) { // expand a chunk into HBM scratch, verify it, next chunk (in order on the handle's stream)
         if (reinterpret_cast<uintptr_t>(blob) & 15u) return fail(SSYM_ERR_USAGE, "a device compact blob must be 16-byte aligned");
         const size_t cap = std::min(n, STWO_DEVICE_CHUNK);
@@ -840,7 +862,13 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     if (c->host_async) hc = std::max<size_t>(512, std::min<size_t>(((n + 1) / 2 + 31) & ~(size_t)31, 4096));
     hc = std::min(hc, (n + 31) & ~(size_t)31);
     const size_t n_words = (n + 31) / 32;
-    const bool derived = can_derive && host_has_derived(blob, offsets, n);
+    // Records with derived siblings: expanded under the mode they were packed under (header word 5).  When that is not the mode of this call, the
+    // chunk takes two passes over the verifier's kernels: one under the records' mode, in which the Merkle kernel completes the packed records,
+    // and the verification proper on the complete records.
+    const int64_t dmode = can_derive ? host_derived_mode(blob, offsets, n) : -1;
+    const bool derived = dmode >= 0 && dmode <= 3, two_pass = derived && (uint32_t)dmode != cfg->mode;
+    ssym_stwo_config_t xcfg = *cfg;
+    if (derived) { xcfg.mode = (uint32_t)dmode; p.mode = xcfg.mode; }
     bool grow = c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4;
     for (int b = 0; b < ssym_ctx::HOST_BUFS; b++)
         grow = grow || c->stage[b].cap < hc * stride_b || c->cstage[b].cap < hc * max_rec_b || c->coffs[b].cap < (hc + 1) * sizeof(uint64_t) ||
@@ -874,8 +902,15 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
         p.packed = c->stage[b].as<uint32_t>(); p.flags = c->cflags[b].as<uint32_t>();
         p.derive = derived ? c->cderive[b].as<uint8_t>() : nullptr; // no version 3 record in the call: exactly the version 2 path (and any Merkle schedule)
         launch_stwo_expand(p, ls);
-        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls, false,
-                               p.derive, sh.slots, 1);
+        if (two_pass) { // complete the records under their own mode (verdicts of this pass are overwritten by the next), then verify under the call's
+            rc = stwo_launch_chunk(c, c->lanes[b], xcfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls, false,
+                                   p.derive, sh.slots, 1);
+            if (rc) return rc;
+            rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls);
+        } else {
+            rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls, false,
+                                   p.derive, sh.slots, 1);
+        }
         if (rc) return rc;
         launch_compact_apply_flags(p.flags, c->d_status.as<uint32_t>() + done, c->d_accept.as<uint32_t>() + done / 32, (uint32_t)m, ls);
         c->launches += 2;

@@ -45,7 +45,7 @@ struct CompactParams {
     uint32_t n;
     uint8_t *derive;         // nullptr, or n * sh.slots bytes: the derive table of StwoParams (0xff, or the partner query of a derived slot); a
                              // version 3 record with derived slots is malformed without it
-    uint32_t mode;           // semantics (0 / 1) of the call: a record with derived slots must have been packed under the same
+    uint32_t mode;           // the mode derived slots are expanded under: a record with derived slots must carry the same in header word 5
 };
 void launch_stwo_expand(const CompactParams &p, cudaStream_t s);
 // status[i] |= SSYM_ST_SHAPE, accept bit i cleared, where flags[i] != 0

@@ -25,9 +25,18 @@ def stwo_config(preset: str = "prod", mode: int = _lib.MODE_REF_LITERAL, n_colum
     return cfg
 
 
+_layout_cache: dict = {}
+
+
 def stwo_layout(cfg: StwoConfig) -> StwoLayout:
-    lo = StwoLayout()
-    check(load().ssym_stwo_layout(C.byref(cfg), C.byref(lo)))
+    """ssym_stwo_layout, memoised per configuration (a loop of calls on one configuration asks for it every time)."""
+    key = bytes(cfg)
+    lo = _layout_cache.get(key)
+    if lo is None:
+        lo = StwoLayout()
+        check(load().ssym_stwo_layout(C.byref(cfg), C.byref(lo)))
+        if len(_layout_cache) < 64:
+            _layout_cache[key] = lo
     return lo
 
 

@@ -137,7 +137,7 @@ def numpy_expand(S, cfg, blob, offsets, orc=None):
         bits2 = np.unpackbits(rec[off_bitmap2:off_refs].view(np.uint8), bitorder="little") if v3 else np.zeros(len(bits), dtype=np.uint8)
         assert int(bits[:slots].sum()) == D and int(bits2[:slots].sum()) == X and not (bits[:slots] & bits2[:slots]).any()
         if X:
-            assert orc is not None and int(rec[5]) == (cfg.mode & 1) and 32 % Q == 0
+            assert orc is not None and int(rec[5]) == cfg.mode and 32 % Q == 0
         ref_bytes = rec[off_refs:off_tab].view(np.uint8)
         refs = ref_bytes[:R * idx_bytes].view(np.uint8 if idx_bytes == 1 else np.uint16)
         partners = ref_bytes[R * idx_bytes:R * idx_bytes + X]
@@ -327,13 +327,20 @@ def test_gpu_version3_pack_expand_verify(S, ver, orc, preset, nc, mode):
     d_accept, d_status = ver.stwo_verify_compact_batch(d_blob, d_off, cfg, want_status=True)
     ver.synchronize()
     assert (d_status.cpu().numpy().view(np.uint32) == ref_status).all() and (d_accept.cpu().numpy().view(np.uint32) == ref_accept).all()
-    # the other semantics: records with derived slots are bound to the one they were packed under
+    # the other semantics: derived slots are expanded under the mode the record was packed under (header word 5).  From host buffers the call sees
+    # the headers and takes two passes (complete the records under their own mode, verify under the call's); the expansion API ignores cfg.mode likewise.
+    # Records in DEVICE memory are expanded under the call's mode only: one with derived slots of another mode is refused, not mis-expanded.
     other = S.stwo_config(preset, 1 - mode, n_columns=nc)
-    _, st_other = ver.stwo_verify_compact_batch(blob, offsets, other, want_status=True)
-    X = np.array([int(blob[int(offsets[i]) + 4]) for i in range(n)])
-    assert ((st_other >> 31 == 1) == (X > 0)).all()
     _, want_other, _ = orc.stwo_verify_batch(ocfg(other), recs.ravel(), n)
-    assert (st_other[X == 0] == want_other[X == 0]).all()
+    acc_other, st_other = ver.stwo_verify_compact_batch(blob, offsets, other, want_status=True)
+    assert (st_other == want_other).all()
+    packed_o, flags_o = ver.stwo_compact_expand(blob, offsets, other, want_flags=True)
+    assert not flags_o.any() and (packed_o == recs).all()
+    _, d_st_other = ver.stwo_verify_compact_batch(d_blob, d_off, other, want_status=True)
+    ver.synchronize()
+    d_st_other = d_st_other.cpu().numpy().view(np.uint32)
+    X = np.array([int(blob[int(offsets[i]) + 4]) for i in range(n)])
+    assert ((d_st_other >> 31 == 1) == (X > 0)).all() and (d_st_other[X == 0] == want_other[X == 0]).all()
 
 
 @pytest.mark.gpu
