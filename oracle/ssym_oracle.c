@@ -994,6 +994,34 @@ EXPORT void oracle_compression_reset(void) { g_compressions = 0; }
 /* M31 operations of the calling thread since the last reset: out = {mul (those inside inversions included), add / sub, inversions} */
 EXPORT void oracle_field_op_counts(uint64_t out[3]) { out[0] = g_m31_mul; out[1] = g_m31_add; out[2] = g_m31_inv; }
 EXPORT void oracle_field_op_reset(void) { g_m31_mul = g_m31_add = g_m31_inv = 0; }
+/* Test-vector search (tests/golden/make_retry_fixture.py): a felt draw is repeated when one of the first four words of the drawn digest is >= 2p
+ * (channel.simf:115-141), which happens once in 2^29 draws — no fixture of the reference exercises it.  Given the channel state BEFORE the trace root is
+ * mixed (evals/commit.simf:23), finds a trace root of the form {base[0..5], hi, lo} for which the cp_alpha draw (evals/commit.simf:29) has to be repeated
+ * at least once.  Scans counters [start, start + count); returns 1 and the root, or 0. */
+EXPORT int oracle_grind_draw_retry(const uint32_t digest_before[8], const uint32_t base[8], uint64_t start, uint64_t count, uint32_t root_out[8]) {
+    const int fast0 = g_fast_sha;
+    if (g_sha_ni < 0) g_sha_ni = cpu_has_sha_ni();
+    g_fast_sha = 1;
+    int found = 0;
+    for (uint64_t k = start; k < start + count && !found; k++) {
+        ChannelState st;
+        memcpy(st.digest.w, digest_before, 32);
+        st.n_sent = 0;
+        u256 root;
+        memcpy(root.w, base, 32);
+        root.w[6] = (uint32_t)(k >> 32);
+        root.w[7] = (uint32_t)k;
+        channel_mix_u256(&st, root);
+        u256 v = channel_draw_u256(&st);
+        if (!is_uniform_n(v.w, 4)) {
+            memcpy(root_out, root.w, 32);
+            found = 1;
+        }
+    }
+    g_fast_sha = fast0;
+    return found;
+}
+
 /* Everything the cost model predicts, in the field order of ssym_cost_t (include/ssym.h), for the calling thread since the last reset. */
 EXPORT void oracle_cost_counts(uint64_t out[SSYM_COST_FIELDS]) {
     const uint64_t v[SSYM_COST_FIELDS] = {g_compressions, g_sha_init, g_sha_add_4, g_sha_add_8, g_sha_add_32, g_sha_finalize, g_sha_bytes,

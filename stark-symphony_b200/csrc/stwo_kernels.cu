@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#define K1_HDR_WORDS (24 + 4 * SSYM_MAX_COLUMNS + 64 + 8 + 8 * (SSYM_MAX_FRI_LAYERS - 1) + 4 + 2 + 6) // the largest header: ssym_stwo_layout's off_qvals
 #define K1_BAR_RS 1 // warps R + S: group produced / group consumed / digest ready / control ready
 #define K1_BAR_F_GO 2   // S arrives, F waits: the three drawn elements the scalars need are in shared memory
 #define K1_BAR_F_DONE 3 // F arrives, S waits: the scalars' status bits are in shared memory
@@ -364,6 +365,10 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
     __shared__ uint32_t s_ctl[4];        // {blocks of the next message, second block is the constant padding block, done}
     __shared__ uint32_t s_felt[12][32];  // oods_t, cp_alpha, deep_alpha (S -> F)
     __shared__ uint32_t s_fbits[32];     // status bits of the scalars (F -> S)
+    // Everything the channel absorbs lies in the proof's header (roots, OODS samples, last coefficient, nonce: words [0, off_qvals)).  The CTA
+    // copies the 32 headers into shared memory first (coalesced 128-bit loads, all in flight together), so that no global-memory latency sits
+    // between two compressions of the chain: warp S assembles a block from shared memory.  [word][proof], rows padded to 33 against bank conflicts.
+    __shared__ uint32_t s_hw[K1_HDR_WORDS][33];
     const ShaAdd<K1_ADDMODE> A(mul);
     const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * 32 + lane;
@@ -371,6 +376,16 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
     const uint32_t idx = live ? i : p.n - 1; // idle lanes of the last CTA replay the last proof and store nothing
     if (p.dd.enabled && blockIdx.x == 0) // the bin counters of stwo_plan_kernel / stwo_check_kernel, later in this stream
         for (uint32_t t = threadIdx.x; t < 2 * STWO_DEDUP_MAX_BINS; t += blockDim.x) p.dd.bin_count[t] = 0;
+    {
+        const uint32_t hq = p.lo.off_qvals / 4; // uint4s per header (sections are 32-byte aligned)
+        for (uint32_t t = threadIdx.x; t < 32 * hq; t += blockDim.x) {
+            const uint32_t pr = t / hq, q4 = t % hq;
+            const uint32_t ip = min(blockIdx.x * 32 + pr, p.n - 1);
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.packed + (size_t)ip * p.lo.stride_words) + q4);
+            s_hw[4 * q4 + 0][pr] = v.x; s_hw[4 * q4 + 1][pr] = v.y; s_hw[4 * q4 + 2][pr] = v.z; s_hw[4 * q4 + 3][pr] = v.w;
+        }
+        __syncthreads();
+    }
 
     if (role == 0) { // ---- warp R: rounds ------------------------------------------------------------------------------------
         uint32_t h[8];
@@ -453,7 +468,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
                 const uint32_t m = b * 16 + j;
                 uint32_t v = 0;
                 if (m < 8) v = d[j & 7]; // only in block 0, where m == j
-                else if (m < nwords) v = draw ? n_sent : __ldg(pk + off + (m - 8));
+                else if (m < nwords) v = draw ? n_sent : s_hw[off + (m - 8)][lane];
                 else if (m == nwords) v = 0x80000000u;
                 else if (m == nblocks * 16 - 1) v = nwords * 32u;
                 w[j] = v;

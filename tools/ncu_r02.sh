@@ -14,5 +14,5 @@ ncu --metrics $M --clock-control none -k regex:stwo_ -s 40 -c 16 --csv --log-fil
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --passes 8 --e2e-passes 4 --no-cpu-baseline > /dev/null 2> gpurun_out/r02_launches.err
 # full captures of the dominant kernel and of the latency-bound transcript kernel
 ncu --set full --clock-control none --import-source on -k regex:stwo_merkle_kernel -s 8 -c 1 -f -o gpurun_out/r02_merkle $HEAD > /dev/null 2> gpurun_out/r02_merkle.err
-ncu --set full --clock-control none --import-source on -k regex:stwo_channel_kernel -s 8 -c 1 -f -o gpurun_out/r02_channel $HEAD > /dev/null 2> gpurun_out/r02_channel.err
+ncu --set full --clock-control none --import-source on -k regex:stwo_channel -s 8 -c 1 -f -o gpurun_out/r02_channel $HEAD > /dev/null 2> gpurun_out/r02_channel.err
 ls -la gpurun_out/r02_*
