@@ -377,12 +377,27 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
     if (p.dd.enabled && blockIdx.x == 0) // the bin counters of stwo_plan_kernel / stwo_check_kernel, later in this stream
         for (uint32_t t = threadIdx.x; t < 2 * STWO_DEDUP_MAX_BINS; t += blockDim.x) p.dd.bin_count[t] = 0;
     {
-        const uint32_t hq = p.lo.off_qvals / 4; // uint4s per header (sections are 32-byte aligned)
-        for (uint32_t t = threadIdx.x; t < 32 * hq; t += blockDim.x) {
-            const uint32_t pr = t / hq, q4 = t % hq;
-            const uint32_t ip = min(blockIdx.x * 32 + pr, p.n - 1);
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.packed + (size_t)ip * p.lo.stride_words) + q4);
-            s_hw[4 * q4 + 0][pr] = v.x; s_hw[4 * q4 + 1][pr] = v.y; s_hw[4 * q4 + 2][pr] = v.z; s_hw[4 * q4 + 3][pr] = v.w;
+        const uint32_t hq = p.lo.off_qvals / 4, total = 32 * hq; // uint4s per header (sections are 32-byte aligned)
+#pragma unroll 1
+        for (uint32_t t0 = threadIdx.x; t0 < total; t0 += 8 * 96) { // eight loads in flight per thread before the first store
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t t = t0 + u * 96;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (t < total) {
+                    const uint32_t ip = min(blockIdx.x * 32 + t / hq, p.n - 1);
+                    v[u] = __ldg(reinterpret_cast<const uint4 *>(p.packed + (size_t)ip * p.lo.stride_words) + t % hq);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t t = t0 + u * 96;
+                if (t < total) {
+                    const uint32_t pr = t / hq, q4 = t % hq;
+                    s_hw[4 * q4 + 0][pr] = v[u].x; s_hw[4 * q4 + 1][pr] = v[u].y; s_hw[4 * q4 + 2][pr] = v[u].z; s_hw[4 * q4 + 3][pr] = v[u].w;
+                }
+            }
         }
         __syncthreads();
     }
