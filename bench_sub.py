@@ -47,7 +47,7 @@ def hbm_peak():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def c1_stark101(S, ver, stream, torch, orc, int32_lanes, log_n=15):
+def c1_stark101(S, ver, stream, torch, orc, int32_lanes, log_n=16):
     """BASELINE config 1: the stark101 Fibonacci-square proof (the reference's `make proof` fixture) replicated x2^log_n + negatives, device resident."""
     golden = os.path.join(ROOT, "tests", "golden")
     blob, _, bad = S.witness.pack_stark101_wits([open(os.path.join(golden, "stark101_proof.wit")).read()])

@@ -1638,6 +1638,30 @@ extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, c
         else { CUDA_TRY(c->lanes[0].status.ensure(n * 4)); p.status = c->lanes[0].status.as<uint32_t>(); }
         p.trace = trace;
         if (trace) CUDA_TRY(cudaMemsetAsync(trace, 0, n * sizeof(ssym_s101_trace_t), s));
+        const size_t CH = 8192; // proofs per chunk of a large call
+        if (n >= 2 * CH && !trace && !c->profiling) {
+            // A large call is cut into chunks on four internal streams: the transcript kernel of one chunk (a dependent chain per proof: channel, field
+            // divisions, fold chain — latency-bound at 256 warps per chunk) runs under the Merkle kernel of the previous one.  Ordered back into the
+            // handle's stream before the call returns.
+            CUDA_TRY(cudaEventRecord(c->lanes[0].in, s));
+            size_t k = 0;
+            for (size_t done = 0; done < n; done += CH, k++) {
+                ssym_ctx::Lane &lane = c->lanes[k % 4];
+                if (k < 4) CUDA_TRY(cudaStreamWaitEvent(lane.s, c->lanes[0].in, 0));
+                S101Params q = p;
+                q.offsets = offsets + done;
+                q.ctx = p.ctx + done * S101_CTX_WORDS;
+                q.status = p.status + done;
+                q.n = (uint32_t)std::min(CH, n - done);
+                launch_s101_verify(q, accept_bits + done / 32, lane.s, &c->launches, nullptr);
+            }
+            for (size_t j = 0; j < std::min<size_t>(k, 4); j++) {
+                CUDA_TRY(cudaEventRecord(c->lanes[j].done, c->lanes[j].s));
+                CUDA_TRY(cudaStreamWaitEvent(s, c->lanes[j].done, 0));
+            }
+            CUDA_TRY(cudaGetLastError());
+            return SSYM_OK;
+        }
         launch_s101_verify(p, accept_bits, s, &c->launches, c->profiling ? &c->profiler : nullptr);
         CUDA_TRY(cudaGetLastError());
         return SSYM_OK;

@@ -243,13 +243,15 @@ def test_stark101_fixture_and_negatives(S, ver, orc):
     assert all(status[1:9] != 0)
 
 
-def test_stark101_replicated_device(S, ver):
+@pytest.mark.parametrize("n", [2048, 40001])  # 40001: a large call is cut into 8192-proof chunks on internal streams (ragged last chunk)
+def test_stark101_replicated_device(S, ver, orc, n):
     import torch
 
     blob, offs, _ = golden_s101(S)
-    n = 2048
     all_blob = np.tile(blob, n)
-    all_blob[100 * len(blob) + 5] += 1  # proof 100: wrong last layer
+    bad = sorted({100, 8191, 8192, 16383, 24576, n - 1} & set(range(n)))
+    for r in bad:
+        all_blob[r * len(blob) + 5] += 1  # wrong last layer
     offsets = np.arange(n + 1, dtype=np.uint64) * len(blob)
     d_blob = torch.from_numpy(all_blob.view(np.int32)).cuda()
     d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
@@ -257,8 +259,11 @@ def test_stark101_replicated_device(S, ver):
     ver.synchronize()
     bits = np.unpackbits(accept.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
     expect = np.ones(n, dtype=bool)
-    expect[100] = False
+    expect[bad] = False
     assert (bits == expect).all()
+    st = status.cpu().numpy().view(np.uint32)
+    _, o_status, _ = orc.s101_verify_batch(all_blob[: 101 * len(blob)], offsets[:102])
+    assert (st[:101] == o_status).all() and (st[bad] == o_status[100]).all() and (st[expect] == 0).all()
 
 
 def test_stark101_device_records_that_lie_about_their_length(S, ver):

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # compute-sanitizer over the GPU test-suite ("sanitizers in CI").  Run on a GPU box:
 #
-#   gpurun --timeout 2400 -- 'bash tools/sanitize.sh'            # all three tools, the default test selection
+#   gpurun --timeout 2400 -- 'bash tools/sanitize.sh'            # all four tools (memcheck, initcheck, racecheck, synccheck), the default test selection
 #   bash tools/sanitize.sh memcheck tests/test_compact.py         # one tool, explicit pytest arguments
 #
 # Logs go to gpurun_out/san_<tool>.log (full), the verdict lines of every run to gpurun_out/san_summary.txt; copy the summary to
@@ -15,8 +15,10 @@ TOOLS=${1:-all}
 shift || true
 # racecheck only sees shared-memory hazards: it gets the shared-memory-heavy code (tokeniser, planner / shared-node schedule, compact expander,
 # prover FFTs).  memcheck / initcheck get the same plus the untrusted-record and ragged-size tests.  Sizes are small: the tools slow kernels 10-100x.
-RACE_TESTS=${*:-"tests/test_wit_ingest.py tests/test_compact.py tests/test_columns.py tests/test_gpu_parity.py::test_stwo_shared_node_schedule_matches_oracle tests/test_gpu_parity.py::test_stwo_fixture_trace_bit_exact tests/test_gpu_prover.py::test_gpu_prover_matches_reference_prover"}
-MEM_TESTS=${*:-"tests/test_wit_ingest.py tests/test_compact.py tests/test_columns.py tests/test_gpu_parity.py tests/test_config_space.py"}
+RACE_TESTS=${*:-"tests/test_wit_ingest.py tests/test_compact.py tests/test_columns.py tests/test_draw_retry.py tests/test_query_dedup.py tests/test_gpu_parity.py::test_stwo_shared_node_schedule_matches_oracle tests/test_gpu_parity.py::test_stwo_fixture_trace_bit_exact tests/test_gpu_prover.py::test_gpu_prover_matches_reference_prover"}
+MEM_TESTS=${*:-"tests/test_wit_ingest.py tests/test_compact.py tests/test_columns.py tests/test_gpu_parity.py tests/test_config_space.py tests/test_draw_retry.py tests/test_query_dedup.py"}
+# synccheck: the named barriers of the warp-specialised transcript kernel (every Stwo test runs it; the repeated-draw records take its uniform retry path)
+SYNC_TESTS=${*:-"tests/test_draw_retry.py tests/test_gpu_parity.py::test_stwo_fixture_trace_bit_exact tests/test_query_dedup.py"}
 rc_all=0
 : > "$OUT/san_summary.txt"
 run() { # tool, extra flags, tests
@@ -33,7 +35,8 @@ run() { # tool, extra flags, tests
 case "$TOOLS" in
     all|memcheck) run memcheck "--leak-check no" "$MEM_TESTS" ;;&
     all|initcheck) run initcheck "" "$MEM_TESTS" ;;&
-    all|racecheck) run racecheck "--racecheck-report all" "$RACE_TESTS" ;;
+    all|racecheck) run racecheck "--racecheck-report all" "$RACE_TESTS" ;;&
+    all|synccheck) run synccheck "" "$SYNC_TESTS" ;;
 esac
 echo "overall: $([ $rc_all -eq 0 ] && echo CLEAN || echo FINDINGS)" | tee -a "$OUT/san_summary.txt"
 exit $rc_all
