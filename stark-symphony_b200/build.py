@@ -51,11 +51,14 @@ def _compile(src: str) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, tuning: bool = False, synccheck: bool = False) -> str:
     """tuning=True adds -DSSYM_TUNING: every kernel variant of the experiments DESIGN.md section 4 reports (SSYM_ADDMODE, SSYM_ROLLED, SSYM_CHANNEL_NP,
     SSYM_FRONT, SSYM_M31_INV_K environment switches).  The release library has none of them."""
     if tuning and "-DSSYM_TUNING" not in NVCC_FLAGS:
         NVCC_FLAGS.append("-DSSYM_TUNING")
+        force = True
+    if synccheck and "-DSSYM_SYNCCHECK" not in NVCC_FLAGS:  # named barriers behind one program location (csrc/stwo_kernels.cu: k1_bar_rs), for tools/sanitize.sh
+        NVCC_FLAGS.append("-DSSYM_SYNCCHECK")
         force = True
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
@@ -77,4 +80,4 @@ def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> s
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tuning="--tuning" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tuning="--tuning" in sys.argv, synccheck="--synccheck" in sys.argv))

@@ -323,13 +323,13 @@ __device__ __forceinline__ void st_digest(uint32_t *dst, const uint32_t (&d)[8])
 __global__ void __launch_bounds__(128) sha256_pair_kernel(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, uint32_t one) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const ShaAdd<1> A{one};
+    const ShaAdd<8> A{one};
     uint32_t l[8], r[8], o[8], w[16];
     ld_digest(left + 8 * i, l);
     ld_digest(right + 8 * i, r);
 #pragma unroll
     for (int k = 0; k < 8; k++) { w[k] = l[k]; w[8 + k] = r[k]; }
-    sha256_64B_rolled<1>(w, o, A);
+    sha256_64B_rolled<8>(w, o, A);
     st_digest(out + 8 * i, o);
 }
 void launch_sha256_pair(const uint32_t *left, const uint32_t *right, uint32_t *out, size_t n, cudaStream_t s) {
@@ -341,7 +341,7 @@ void launch_sha256_pair(const uint32_t *left, const uint32_t *right, uint32_t *o
 __global__ void __launch_bounds__(128) merkle_path_kernel(const uint32_t *leaf, const uint32_t *auth_path, const uint32_t *siblings,
                                                           uint32_t depth, const uint32_t *expected_root, uint32_t *out_root,
                                                           uint32_t *out_path, uint32_t *ok_bits, size_t n, uint32_t one) {
-    const ShaAdd<1> A{one}; // adds on the FMA pipe, rounds rolled 4 x 16: same hashing core as stwo_merkle_kernel
+    const ShaAdd<8> A{one}; // adds on the FMA pipe, rounds rolled 4 x 16: same hashing core as stwo_merkle_kernel
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     const size_t ii = active ? i : 0;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(128) merkle_path_kernel(const uint32_t *leaf, 
             w[8 + k] = cur_left ? nxt[k] : cur[k];
         }
         if (lvl + 1 < depth) ld_digest(sib + 8 * (lvl + 1), nxt);
-        sha256_64B_rolled<1>(w, cur, A);
+        sha256_64B_rolled<8>(w, cur, A);
         path >>= 1;
     }
     bool ok = path == 1u;

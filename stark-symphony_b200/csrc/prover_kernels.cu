@@ -10,7 +10,7 @@
 namespace ssym {
 
 typedef PrvCtx PC;
-typedef ShaAdd<1> ShaA; // adds on the FMA pipe, as in the verifier's Merkle kernel (sha256.cuh)
+typedef ShaAdd<8> ShaA; // adds on the FMA pipe, as in the verifier's Merkle kernel (sha256.cuh)
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -39,7 +39,7 @@ __device__ __forceinline__ void hash_16B(uint4 v, uint32_t (&out)[8], const ShaA
     for (int k = 5; k < 15; k++) w[k] = 0;
     w[15] = 128u;
     sha_iv(out);
-    sha_compress_rolled<1>(out, w, A);
+    sha_compress_rolled<8>(out, w, A);
 }
 
 // Block-wide circle FFT over `ncols` columns in shared memory (column c at v + c * col_stride), 2^n points each, in the basis
@@ -158,12 +158,12 @@ __global__ void __launch_bounds__(128) prv_leaf_trace_kernel(PrvParams p, uint32
 #pragma unroll
         for (int k = 0; k < 16; k++) w[k] = (uint32_t)k < C ? tl[(size_t)k * NG] : 0u;
         if (C == 16) {
-            sha256_64B_rolled<1>(w, d, A);
+            sha256_64B_rolled<8>(w, d, A);
         } else {
             w[8] = 0x80000000u;
             w[15] = 256u;
             sha_iv(d);
-            sha_compress_rolled<1>(d, w, A);
+            sha_compress_rolled<8>(d, w, A);
         }
     }
     store_digest(p.tree_t + ((size_t)i * 2 * NG + NG + q) * 8, d);
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) prv_leaf_cp_kernel(PrvParams p, uint32_t 
     uint32_t w[16], d[8];
 #pragma unroll
     for (int k = 0; k < 16; k++) w[k] = cl[(size_t)k * NG];
-    sha256_64B_rolled<1>(w, d, A);
+    sha256_64B_rolled<8>(w, d, A);
     store_digest(p.tree_c + ((size_t)i * 2 * NG + NG + q) * 8, d);
 }
 __global__ void __launch_bounds__(128) prv_leaf_fri_kernel(PrvParams p, uint32_t layer, uint32_t one) {
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128) prv_tree_level_kernel(uint32_t *base, siz
         const uint4 v = ch[j];
         w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
     }
-    sha256_64B_rolled<1>(w, d, A);
+    sha256_64B_rolled<8>(w, d, A);
     store_digest(tree + (size_t)node * 8, d);
 }
 

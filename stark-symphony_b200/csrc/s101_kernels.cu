@@ -218,7 +218,7 @@ __device__ __forceinline__ void s101_load_digest(const uint32_t *src, uint32_t (
 // Path slots: 0..2 = trace decommitments of f(x), f(gx), f(g^2 x) (air.simf:39-56); 3 + 2l, 4 + 2l = cpa / cpb of
 // FRI layer l (fri.simf:78-80).  merkle_verify_32 here has no `path == 1` assert (stark101/src/merkle.simf:39-43).
 __global__ void __launch_bounds__(128, 8) s101_merkle_kernel(S101Params p, uint32_t groups, ShaMul mul) {
-    const ShaAdd<1> A(mul); // adds on the FMA pipe, rounds rolled 4 x 16, ONE hashing loop: the core of stwo_merkle_kernel (sha256.cuh)
+    const ShaAdd<8> A(mul); // adds on the FMA pipe, rounds rolled 4 x 16, ONE hashing loop: the core of stwo_merkle_kernel (sha256.cuh)
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t slot = warp / groups, group = warp % groups;
     const uint32_t i = group * 32 + lane;
@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(128, 8) s101_merkle_kernel(S101Params p, uint3
             path >>= 1;
         }
         sha_iv(cur);
-        sha_compress_rolled<1>(cur, w, A);
-        if (step) sha_compress_pad64_rolled<1>(cur, A);
+        sha_compress_rolled<8>(cur, w, A);
+        if (step) sha_compress_pad64_rolled<8>(cur, A);
     }
     bool ok = true;
 #pragma unroll

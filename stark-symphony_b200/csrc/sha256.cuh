@@ -86,15 +86,18 @@ __device__ __forceinline__ void sha_iv(uint32_t (&h)[8]) {
 //      (a 1:1 trade of an ALU-pipe SHF for an FMA-pipe instruction); the multipliers arrive as kernel parameters as well
 //   7  as 6, and one rotation of each big Sigma is built on the FMA pipe: rotr(x, n) = x * 2^(32-n) + hi(x * 2^(32-n))
 //      (IMAD.HI + IMAD replace one SHF)
-struct ShaMul { // opaque (kernel-parameter) constants: 1, 2^29, 2^22, 2^10, 2^7
-    uint32_t one, m29, m22, m10, m7;
+//   8  as 1, with a second opaque 1 for the additions of a constant-bank word (ShaAdd::tk)
+//   9  as 8, with the plain shifts of the message schedule as IMAD.HI (mode 6's trade)
+//   10 as 8, with one rotation of Sigma1 as IMAD.HI + IMAD (half of mode 7's trade)
+struct ShaMul { // opaque (kernel-parameter) constants: 1, 2^29, 2^22, 2^10, 2^7, and a second 1 (ADDMODE 8)
+    uint32_t one, m29, m22, m10, m7, onek;
 };
-__host__ __device__ inline ShaMul sha_mul_consts() { return ShaMul{1u, 1u << 29, 1u << 22, 1u << 10, 1u << 7}; }
+__host__ __device__ inline ShaMul sha_mul_consts() { return ShaMul{1u, 1u << 29, 1u << 22, 1u << 10, 1u << 7, 1u}; }
 template <int ADDMODE>
 struct ShaAdd {
-    uint32_t one, m29, m22, m10, m7;
-    __device__ __forceinline__ ShaAdd(uint32_t o) : one(o), m29(0), m22(0), m10(0), m7(0) {}
-    __device__ __forceinline__ ShaAdd(const ShaMul &m) : one(m.one), m29(m.m29), m22(m.m22), m10(m.m10), m7(m.m7) {}
+    uint32_t one, m29, m22, m10, m7, onek;
+    __device__ __forceinline__ ShaAdd(uint32_t o) : one(o), m29(0), m22(0), m10(0), m7(0), onek(o) {}
+    __device__ __forceinline__ ShaAdd(const ShaMul &m) : one(m.one), m29(m.m29), m22(m.m22), m10(m.m10), m7(m.m7), onek(m.onek) {}
     __device__ __forceinline__ uint32_t fma(uint32_t a, uint32_t b) const {
         uint32_t d;
         asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
@@ -110,11 +113,20 @@ struct ShaAdd {
         asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(m), "r"(mulhi(x, m)));
         return d;
     }
-    __device__ __forceinline__ uint32_t ssig0(uint32_t x) const { return rotr32(x, 7) ^ rotr32(x, 18) ^ (ADDMODE >= 6 ? mulhi(x, m29) : (x >> 3)); }
-    __device__ __forceinline__ uint32_t ssig1(uint32_t x) const { return rotr32(x, 17) ^ rotr32(x, 19) ^ (ADDMODE >= 6 ? mulhi(x, m22) : (x >> 10)); }
-    __device__ __forceinline__ uint32_t bSig0(uint32_t x) const { return rotr32(x, 2) ^ rotr32(x, 13) ^ (ADDMODE >= 7 ? rot_fma(x, m10) : rotr32(x, 22)); }
-    __device__ __forceinline__ uint32_t bSig1(uint32_t x) const { return rotr32(x, 6) ^ rotr32(x, 11) ^ (ADDMODE >= 7 ? rot_fma(x, m7) : rotr32(x, 25)); }
+    __device__ __forceinline__ uint32_t ssig0(uint32_t x) const { return rotr32(x, 7) ^ rotr32(x, 18) ^ ((ADDMODE == 6 || ADDMODE == 7 || ADDMODE == 9) ? mulhi(x, m29) : (x >> 3)); }
+    __device__ __forceinline__ uint32_t ssig1(uint32_t x) const { return rotr32(x, 17) ^ rotr32(x, 19) ^ ((ADDMODE == 6 || ADDMODE == 7 || ADDMODE == 9) ? mulhi(x, m22) : (x >> 10)); }
+    __device__ __forceinline__ uint32_t bSig0(uint32_t x) const { return rotr32(x, 2) ^ rotr32(x, 13) ^ (ADDMODE == 7 ? rot_fma(x, m10) : rotr32(x, 22)); }
+    __device__ __forceinline__ uint32_t bSig1(uint32_t x) const { return rotr32(x, 6) ^ rotr32(x, 11) ^ ((ADDMODE == 7 || ADDMODE == 10) ? rot_fma(x, m7) : rotr32(x, 25)); }
     __device__ __forceinline__ uint32_t t1(uint32_t a, uint32_t b) const { return ADDMODE >= 1 ? fma(a, b) : a + b; }    // T1 chain
+    // the additions whose addend is K[t] / K[t] + W[t] from the constant bank: an IMAD takes ONE operand from the uniform datapath, so here the
+    // multiplier 1 has to sit in a vector register.  With the same `one` everywhere ptxas then reads it from that register in EVERY addition
+    // (three vector-register operands each); a second opaque 1 for these leaves the others at two vector operands + a uniform register.
+    __device__ __forceinline__ uint32_t tk(uint32_t a, uint32_t k) const {
+        if (ADDMODE < 8) return t1(a, k);
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(onek), "r"(k));
+        return d;
+    }
     __device__ __forceinline__ uint32_t rnd(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE == 2 || ADDMODE >= 4) ? fma(a, b) : a + b; } // rest of the round
     __device__ __forceinline__ uint32_t sch(uint32_t a, uint32_t b) const { return (ADDMODE == 1 || ADDMODE >= 4) ? fma(a, b) : a + b; }  // message schedule
     // a' = t1 + Sigma0 + Maj
@@ -134,6 +146,13 @@ struct ShaAdd {
         (d) = A.rnd(d, t1_);                                                 \
         (h) = A.rnd3(t1_, A.bSig0(a), Maj(a, b, c));                         \
     }
+// the same round with K[t] + W[t] read from the constant bank (the padding block)
+#define SSYM_SHA_ROUNDK(A, a, b, c, d, e, f, g, h, kw)                       \
+    {                                                                        \
+        uint32_t t1_ = A.t1(A.t1(A.tk(h, kw), Ch(e, f, g)), A.bSig1(e));     \
+        (d) = A.rnd(d, t1_);                                                 \
+        (h) = A.rnd3(t1_, A.bSig0(a), Maj(a, b, c));                         \
+    }
 
 // One compression of `h` with the 16-word block `w` (w is consumed: it becomes the rolling schedule).
 template <int ADDMODE>
@@ -149,14 +168,14 @@ __device__ __forceinline__ void sha_compress(uint32_t (&h)[8], uint32_t (&w)[16]
                 w[i] = A.sch4(w[i], A.ssig0(w[(i + 1) & 15]), w[(i + 9) & 15], A.ssig1(w[(i + 14) & 15]));
             }
         }
-        SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.t1(w[(t + 0) & 15], K.k[t + 0]));
-        SSYM_SHA_ROUND(A, hh, a, b, c, d, e, f, g, A.t1(w[(t + 1) & 15], K.k[t + 1]));
-        SSYM_SHA_ROUND(A, g, hh, a, b, c, d, e, f, A.t1(w[(t + 2) & 15], K.k[t + 2]));
-        SSYM_SHA_ROUND(A, f, g, hh, a, b, c, d, e, A.t1(w[(t + 3) & 15], K.k[t + 3]));
-        SSYM_SHA_ROUND(A, e, f, g, hh, a, b, c, d, A.t1(w[(t + 4) & 15], K.k[t + 4]));
-        SSYM_SHA_ROUND(A, d, e, f, g, hh, a, b, c, A.t1(w[(t + 5) & 15], K.k[t + 5]));
-        SSYM_SHA_ROUND(A, c, d, e, f, g, hh, a, b, A.t1(w[(t + 6) & 15], K.k[t + 6]));
-        SSYM_SHA_ROUND(A, b, c, d, e, f, g, hh, a, A.t1(w[(t + 7) & 15], K.k[t + 7]));
+        SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.tk(w[(t + 0) & 15], K.k[t + 0]));
+        SSYM_SHA_ROUND(A, hh, a, b, c, d, e, f, g, A.tk(w[(t + 1) & 15], K.k[t + 1]));
+        SSYM_SHA_ROUND(A, g, hh, a, b, c, d, e, f, A.tk(w[(t + 2) & 15], K.k[t + 2]));
+        SSYM_SHA_ROUND(A, f, g, hh, a, b, c, d, e, A.tk(w[(t + 3) & 15], K.k[t + 3]));
+        SSYM_SHA_ROUND(A, e, f, g, hh, a, b, c, d, A.tk(w[(t + 4) & 15], K.k[t + 4]));
+        SSYM_SHA_ROUND(A, d, e, f, g, hh, a, b, c, A.tk(w[(t + 5) & 15], K.k[t + 5]));
+        SSYM_SHA_ROUND(A, c, d, e, f, g, hh, a, b, A.tk(w[(t + 6) & 15], K.k[t + 6]));
+        SSYM_SHA_ROUND(A, b, c, d, e, f, g, hh, a, A.tk(w[(t + 7) & 15], K.k[t + 7]));
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
@@ -169,14 +188,14 @@ __device__ __forceinline__ void sha_compress_pad64(uint32_t (&h)[8], const ShaAd
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
     for (int t = 0; t < 64; t += 8) {
-        SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, KW.kw[t + 0]);
-        SSYM_SHA_ROUND(A, hh, a, b, c, d, e, f, g, KW.kw[t + 1]);
-        SSYM_SHA_ROUND(A, g, hh, a, b, c, d, e, f, KW.kw[t + 2]);
-        SSYM_SHA_ROUND(A, f, g, hh, a, b, c, d, e, KW.kw[t + 3]);
-        SSYM_SHA_ROUND(A, e, f, g, hh, a, b, c, d, KW.kw[t + 4]);
-        SSYM_SHA_ROUND(A, d, e, f, g, hh, a, b, c, KW.kw[t + 5]);
-        SSYM_SHA_ROUND(A, c, d, e, f, g, hh, a, b, KW.kw[t + 6]);
-        SSYM_SHA_ROUND(A, b, c, d, e, f, g, hh, a, KW.kw[t + 7]);
+        SSYM_SHA_ROUNDK(A, a, b, c, d, e, f, g, hh, KW.kw[t + 0]);
+        SSYM_SHA_ROUNDK(A, hh, a, b, c, d, e, f, g, KW.kw[t + 1]);
+        SSYM_SHA_ROUNDK(A, g, hh, a, b, c, d, e, f, KW.kw[t + 2]);
+        SSYM_SHA_ROUNDK(A, f, g, hh, a, b, c, d, e, KW.kw[t + 3]);
+        SSYM_SHA_ROUNDK(A, e, f, g, hh, a, b, c, d, KW.kw[t + 4]);
+        SSYM_SHA_ROUNDK(A, d, e, f, g, hh, a, b, c, KW.kw[t + 5]);
+        SSYM_SHA_ROUNDK(A, c, d, e, f, g, hh, a, b, KW.kw[t + 6]);
+        SSYM_SHA_ROUNDK(A, b, c, d, e, f, g, hh, a, KW.kw[t + 7]);
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
@@ -209,27 +228,37 @@ static __constant__ ShaK4 c_sha_kwpad4 = {{
     {0x83613bda, 0xdb48a363, 0x0b02e931, 0x6fd15ca7}, {0x521afaca, 0x31338431, 0x6ed41a95, 0x6d437890},
     {0xc39c91f2, 0x9eccabbd, 0xb5c9a0e6, 0x532fb63c}, {0xd2c741c6, 0x07237ea3, 0xa4954b68, 0x4c191d76}}};
 
+// ADDMODE 8: the multiplier 1 of the round additions, read per 16-round group with a uniform index — a load ptxas keeps in a uniform register
+// (it moves a kernel parameter it has hoisted out of the loop into a vector register instead)
+static __constant__ uint32_t c_sha_ones[4] = {1u, 1u, 1u, 1u};
 #define SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, h, k0, k1, k2, k3) \
     SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, h, k0)                   \
     SSYM_SHA_ROUND(A, h, a, b, c, d, e, f, g, k1)                   \
     SSYM_SHA_ROUND(A, g, h, a, b, c, d, e, f, k2)                   \
     SSYM_SHA_ROUND(A, f, g, h, a, b, c, d, e, k3)
+#define SSYM_SHA_ROUND4K(A, a, b, c, d, e, f, g, h, k0, k1, k2, k3) \
+    SSYM_SHA_ROUNDK(A, a, b, c, d, e, f, g, h, k0)                   \
+    SSYM_SHA_ROUNDK(A, h, a, b, c, d, e, f, g, k1)                   \
+    SSYM_SHA_ROUNDK(A, g, h, a, b, c, d, e, f, k2)                   \
+    SSYM_SHA_ROUNDK(A, f, g, h, a, b, c, d, e, k3)
 
 template <int ADDMODE>
-__device__ __forceinline__ void sha_compress_rolled(uint32_t (&h)[8], uint32_t (&w)[16], const ShaAdd<ADDMODE> A) {
+__device__ __forceinline__ void sha_compress_rolled(uint32_t (&h)[8], uint32_t (&w)[16], const ShaAdd<ADDMODE> A0) {
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    ShaAdd<ADDMODE> A = A0;
 #pragma unroll 1
     for (int grp = 0; grp < 4; grp++) {
+        if (ADDMODE >= 8) A.one = c_sha_ones[grp];
         if (grp) {
 #pragma unroll
             for (int i = 0; i < 16; i++)
                 w[i] = A.sch4(w[i], A.ssig0(w[(i + 1) & 15]), w[(i + 9) & 15], A.ssig1(w[(i + 14) & 15]));
         }
         const uint4 k0 = c_sha_k4.v[grp * 4 + 0], k1 = c_sha_k4.v[grp * 4 + 1], k2 = c_sha_k4.v[grp * 4 + 2], k3 = c_sha_k4.v[grp * 4 + 3];
-        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.t1(w[0], k0.x), A.t1(w[1], k0.y), A.t1(w[2], k0.z), A.t1(w[3], k0.w));
-        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, A.t1(w[4], k1.x), A.t1(w[5], k1.y), A.t1(w[6], k1.z), A.t1(w[7], k1.w));
-        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.t1(w[8], k2.x), A.t1(w[9], k2.y), A.t1(w[10], k2.z), A.t1(w[11], k2.w));
-        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, A.t1(w[12], k3.x), A.t1(w[13], k3.y), A.t1(w[14], k3.z), A.t1(w[15], k3.w));
+        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.tk(w[0], k0.x), A.tk(w[1], k0.y), A.tk(w[2], k0.z), A.tk(w[3], k0.w));
+        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, A.tk(w[4], k1.x), A.tk(w[5], k1.y), A.tk(w[6], k1.z), A.tk(w[7], k1.w));
+        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, A.tk(w[8], k2.x), A.tk(w[9], k2.y), A.tk(w[10], k2.z), A.tk(w[11], k2.w));
+        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, A.tk(w[12], k3.x), A.tk(w[13], k3.y), A.tk(w[14], k3.z), A.tk(w[15], k3.w));
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
@@ -260,7 +289,7 @@ __device__ __forceinline__ void sha_compress_rolled_n(uint32_t (&h)[NP][8], uint
             for (int p = 0; p < NP; p++) {
                 uint32_t &a = v[p][(0 - t) & 7], &b = v[p][(1 - t) & 7], &c = v[p][(2 - t) & 7], &d = v[p][(3 - t) & 7];
                 uint32_t &e = v[p][(4 - t) & 7], &f = v[p][(5 - t) & 7], &g = v[p][(6 - t) & 7], &hh = v[p][(7 - t) & 7];
-                SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.t1(w[p][t], kt));
+                SSYM_SHA_ROUND(A, a, b, c, d, e, f, g, hh, A.tk(w[p][t], kt));
             }
         }
     }
@@ -270,15 +299,17 @@ __device__ __forceinline__ void sha_compress_rolled_n(uint32_t (&h)[NP][8], uint
         for (int k = 0; k < 8; k++) h[p][k] += v[p][k];
 }
 template <int ADDMODE>
-__device__ __forceinline__ void sha_compress_pad64_rolled(uint32_t (&h)[8], const ShaAdd<ADDMODE> A) {
+__device__ __forceinline__ void sha_compress_pad64_rolled(uint32_t (&h)[8], const ShaAdd<ADDMODE> A0) {
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    ShaAdd<ADDMODE> A = A0;
 #pragma unroll 1
     for (int grp = 0; grp < 4; grp++) {
+        if (ADDMODE >= 8) A.one = c_sha_ones[grp];
         const uint4 k0 = c_sha_kwpad4.v[grp * 4 + 0], k1 = c_sha_kwpad4.v[grp * 4 + 1], k2 = c_sha_kwpad4.v[grp * 4 + 2], k3 = c_sha_kwpad4.v[grp * 4 + 3];
-        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, k0.x, k0.y, k0.z, k0.w);
-        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, k1.x, k1.y, k1.z, k1.w);
-        SSYM_SHA_ROUND4(A, a, b, c, d, e, f, g, hh, k2.x, k2.y, k2.z, k2.w);
-        SSYM_SHA_ROUND4(A, e, f, g, hh, a, b, c, d, k3.x, k3.y, k3.z, k3.w);
+        SSYM_SHA_ROUND4K(A, a, b, c, d, e, f, g, hh, k0.x, k0.y, k0.z, k0.w);
+        SSYM_SHA_ROUND4K(A, e, f, g, hh, a, b, c, d, k1.x, k1.y, k1.z, k1.w);
+        SSYM_SHA_ROUND4K(A, a, b, c, d, e, f, g, hh, k2.x, k2.y, k2.z, k2.w);
+        SSYM_SHA_ROUND4K(A, e, f, g, hh, a, b, c, d, k3.x, k3.y, k3.z, k3.w);
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }

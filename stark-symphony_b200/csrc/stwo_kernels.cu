@@ -8,7 +8,7 @@
 #include <cstdlib>
 
 #ifndef SSYM_DEFAULT_ADDMODE
-#define SSYM_DEFAULT_ADDMODE 1
+#define SSYM_DEFAULT_ADDMODE 8
 #endif
 #ifndef SSYM_MERKLE_MINB
 #define SSYM_MERKLE_MINB 8 // resident CTAs per SM the Merkle kernel is compiled for (8 -> 64 registers)
@@ -352,12 +352,31 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
 //           coefficient is drawn, i.e. while the 31 compressions of fri_commit / PoW / queries are still running
 // Same values, same order of hash inputs; lane l of every warp serves proof 32 * blockIdx.x + l.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-#define K1_HDR_WORDS (24 + 4 * SSYM_MAX_COLUMNS + 64 + 8 + 8 * (SSYM_MAX_FRI_LAYERS - 1) + 4 + 2 + 6) // the largest header: ssym_stwo_layout's off_qvals
-#define K1_BAR_RS 1 // warps R + S: group produced / group consumed / digest ready / control ready
+// bar.sync / bar.arrive are warp-aligned instructions: the lanes of a warp that went separate ways (a lane-0 store, a per-lane loop) reconverge first
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    __syncwarp();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+#define K1_BAR_RS 1 // warps R + S: group produced / group consumed / digest ready / control ready (k1_bar_rs)
 #define K1_BAR_F_GO 2   // S arrives, F waits: the three drawn elements the scalars need are in shared memory
 #define K1_BAR_F_DONE 3 // F arrives, S waits: the scalars' status bits are in shared memory
+// The R <-> S hand-over barrier.  compute-sanitizer's synccheck reports "divergent thread(s) in block" whenever the warps of a named barrier arrive
+// from different program locations (tools/synccheck_probe.cu: the plain two-warp producer / consumer pattern of the PTX manual is flagged, the same
+// barrier behind one location is not), so a -DSSYM_SYNCCHECK build (build.py --synccheck, tools/sanitize.sh synccheck) puts it into ONE non-inlined
+// function and the tool then checks the protocol itself: clean.  The release build inlines it: the call costs a lone launch 12 us (0.101 vs 0.089 ms).
+#ifdef SSYM_SYNCCHECK
+__device__ __noinline__ void k1_bar_rs() {
+    __syncwarp();
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+}
+#else
+__device__ __forceinline__ void k1_bar_rs() { named_bar_sync(K1_BAR_RS, 64); }
+#endif
+#define K1_HDR_WORDS (24 + 4 * SSYM_MAX_COLUMNS + 64 + 8 + 8 * (SSYM_MAX_FRI_LAYERS - 1) + 4 + 2 + 6) // the largest header: ssym_stwo_layout's off_qvals
 
 __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMul mul) {
     __shared__ uint32_t s_kw[2][16][32]; // K + W of one 16-round group per buffer, [round][lane]
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
     if (role == 0) { // ---- warp R: rounds ------------------------------------------------------------------------------------
         uint32_t h[8];
         for (;;) {
-            named_bar_sync(K1_BAR_RS, 64); // control ready
+            k1_bar_rs(); // control ready
             const uint32_t nblocks = s_ctl[0], pad64 = s_ctl[1];
             if (s_ctl[2]) break;
             sha_iv(h);
@@ -415,7 +434,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
                 uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll 1
                 for (uint32_t grp = 0; grp < 4; grp++) {
-                    named_bar_sync(K1_BAR_RS, 64); // group `grp` produced (and group grp - 1 consumed: its buffer may be overwritten)
+                    k1_bar_rs(); // group `grp` produced (and group grp - 1 consumed: its buffer may be overwritten)
                     const uint32_t(*kw)[32] = s_kw[grp & 1];
                     SSYM_SHA_ROUND4(A, a, bb, c, d, e, f, g, hh, kw[0][lane], kw[1][lane], kw[2][lane], kw[3][lane]);
                     SSYM_SHA_ROUND4(A, e, f, g, hh, a, bb, c, d, kw[4][lane], kw[5][lane], kw[6][lane], kw[7][lane]);
@@ -426,7 +445,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) s_dig[k][lane] = h[k];
-            named_bar_sync(K1_BAR_RS, 64); // digest ready
+            k1_bar_rs(); // digest ready
         }
         return;
     }
@@ -473,7 +492,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
         const uint32_t nwords = 8 + n, nblocks = (nwords + 3 + 15) >> 4;
         const bool pad64 = nwords == 16; // the 12 digest-sized mixes: the second block is the constant padding block of a 64-byte message
         if (lane == 0) { s_ctl[0] = nblocks; s_ctl[1] = pad64 ? 1u : 0u; s_ctl[2] = 0u; }
-        named_bar_sync(K1_BAR_RS, 64); // control ready
+        k1_bar_rs(); // control ready
 #pragma unroll 1
         for (uint32_t b = 0; b < nblocks; b++) {
             if (pad64 && b == 1) continue;
@@ -503,10 +522,10 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
                     kw[4 * t4 + 2][lane] = A.t1(w[4 * t4 + 2], k4.z);
                     kw[4 * t4 + 3][lane] = A.t1(w[4 * t4 + 3], k4.w);
                 }
-                named_bar_sync(K1_BAR_RS, 64); // group produced
+                k1_bar_rs(); // group produced
             }
         }
-        named_bar_sync(K1_BAR_RS, 64); // digest ready
+        k1_bar_rs(); // digest ready
         uint32_t h[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) h[k] = s_dig[k][lane];
@@ -597,7 +616,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
         }
     }
     if (lane == 0) s_ctl[2] = 1u;
-    named_bar_sync(K1_BAR_RS, 64); // releases warp R
+    k1_bar_rs(); // releases warp R
     uint32_t used = Q;
     if (live && (p.cfg.mode & SSYM_MODE_QUERY_DEDUP)) { // include/ssym.h: sort the drawn queries, keep the distinct ones in slots [0, U), zero the rest
         uint32_t *qs = ctx + CX::QUERIES;
@@ -867,7 +886,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
 #pragma unroll
                 for (int k = 0; k < 8; k++) { w[k] = nxt[k]; w[8 + k] = cur[k]; }
             } else { // 16-byte message in one block: trace leaf, or the left (step 0) / right (step 1) FRI leaf
-                const bool take_eval = kind == 2 && ((step == 0) == fri_even);
+                const bool take_eval = active && kind == 2 && ((step == 0) == fri_even); // (an idle lane has no evaluation: K2 wrote none for it)
                 const uint4 v = take_eval ? *reinterpret_cast<const uint4 *>(evp) : __ldg(reinterpret_cast<const uint4 *>(msg));
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
                 uint4 v2 = make_uint4(0x80000000u, 0u, 0u, 0u); // FIPS 180-4 padding right after a 16-byte message ...
@@ -1456,6 +1475,9 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     case 11: SSYM_LAUNCH_MERKLE(5, true); break;
     case 13: SSYM_LAUNCH_MERKLE(6, true); break;
     case 15: SSYM_LAUNCH_MERKLE(7, true); break;
+    case 17: SSYM_LAUNCH_MERKLE(8, true); break;
+    case 19: SSYM_LAUNCH_MERKLE(9, true); break;
+    case 21: SSYM_LAUNCH_MERKLE(10, true); break;
     default: SSYM_LAUNCH_MERKLE(0, false); break;
     }
 #else

@@ -36,7 +36,11 @@ case "$TOOLS" in
     all|memcheck) run memcheck "--leak-check no" "$MEM_TESTS" ;;&
     all|initcheck) run initcheck "" "$MEM_TESTS" ;;&
     all|racecheck) run racecheck "--racecheck-report all" "$RACE_TESTS" ;;&
-    all|synccheck) run synccheck "" "$SYNC_TESTS" ;;
+    all|synccheck) # synccheck flags a named barrier whose warps arrive from different program locations (tools/synccheck_probe.cu): this tool runs on a
+                   # -DSSYM_SYNCCHECK build, which keeps the transcript kernel's hand-over barrier behind one location; the release build is restored after
+        python stark-symphony_b200/build.py --synccheck > "$OUT/san_build_synccheck.log" 2>&1
+        run synccheck "" "$SYNC_TESTS"
+        python stark-symphony_b200/build.py --force > /dev/null 2>&1 ;;
 esac
 echo "overall: $([ $rc_all -eq 0 ] && echo CLEAN || echo FINDINGS)" | tee -a "$OUT/san_summary.txt"
 exit $rc_all
