@@ -205,7 +205,10 @@ int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *queries, uint3
  *   [1]      n_layers (0..31)
  *   [2..4]   sibling counts of the three trace decommitments (f(x), f(gx), f(g^2 x))
  *   [5]      fri_last_layer
- *   [6..7]   reserved (0)
+ *   [6]      query ordinal k (0..SSYM_S101_MAX_ORDINAL; 0 = the reference's program): the query index is the (k+1)-th
+ *            channel_draw_32(state, DOMAIN_EX_SIZE) after the commitments (verifier.simf:32 draws the first; channel.simf:102-105: every
+ *            draw re-hashes the state).  See ssym_stark101_verify_multi_batch.
+ *   [7]      reserved (0)
  *   [8..15]  p_mt_root
  *   [16..18] f(x), f(gx), f(g^2 x)      [19] reserved
  *   [20 ..]  siblings of eval 0, eval 1, eval 2 (8 words each, leaf -> root)
@@ -221,6 +224,8 @@ int ssym_stwo_cost(const ssym_stwo_config_t *cfg, const uint32_t *queries, uint3
 #define SSYM_S101_ST_LAYER_MERKLE_A (1u << 6)        /* fri.simf:79 */
 #define SSYM_S101_ST_LAYER_MERKLE_B (1u << 7)        /* fri.simf:80 */
 #define SSYM_S101_ST_LAST (1u << 8)                  /* fri.simf:90 */
+#define SSYM_S101_ST_GROUP (1u << 9)                 /* multi-query: ordinal != slot, or commitments differ from the proof's first record */
+#define SSYM_S101_MAX_ORDINAL 255u
 #define SSYM_S101_ST_SHAPE (1u << 31)
 
 typedef struct ssym_s101_trace {
@@ -236,6 +241,8 @@ typedef struct ssym_s101_trace {
     uint32_t layer_mask[SSYM_S101_MAX_LIST]; /* per layer: bit0 cp!=cpa, bit1 merkle a, bit2 merkle b, bit3 beta */
     uint32_t state_final[8];                 /* channel state after the three evaluations are mixed */
     uint32_t trace_root[3][8];               /* recomputed roots of the three trace decommitments */
+    uint32_t query_ordinal;                  /* record word 6 */
+    uint32_t commit_state[8];                /* channel state after fri_read_commitments_32 + the last layer (verifier.simf:30), before any query draw */
 } ssym_s101_trace_t;
 
 /* ------------------------------------------------------------------------- */
@@ -382,6 +389,17 @@ int ssym_stwo_verify_compact_batch(ssym_ctx_t *ctx, const ssym_stwo_config_t *cf
 int ssym_stark101_verify_batch(ssym_ctx_t *ctx, const uint32_t *blob, const uint64_t *offsets,
                                size_t n, uint32_t *accept_bits, uint32_t *status,
                                ssym_s101_trace_t *trace, int memspace);
+
+/* Multi-query stark101.  The reference draws ONE query (verifier.simf:32; prover.py:138): ~3 bits of soundness at
+ * rate 1/8.  A Q-query proof is Q records of the reference's own witness shape — same P_MT_ROOT, FRI roots, betas and last layer, query phase
+ * k (P_EVALS and the FRI decommitments) in record k — and record k is verified by verify_proof with its query index taken from the (k+1)-th
+ * draw (record word 6 = k): the query phase of verifier.simf:32-41 repeated on one channel.  Records are proof-major: record i * Q + k is
+ * query k of proof i.  A proof is accepted iff every one of its records is, carries ordinal k in slot k, and reaches the query phase in the
+ * channel state of the proof's first record (= identical commitments, bound by SHA-256); a record that breaks the last two gets
+ * SSYM_S101_ST_GROUP.  accept_bits: one bit per PROOF (ceil(n_proofs / 32) words); status / trace: one per RECORD (n_proofs * n_queries).
+ * tests/golden/stark101_multiquery.json: the reference's prover run unmodified, its trees asked for three more positions. */
+int ssym_stark101_verify_multi_batch(ssym_ctx_t *ctx, const uint32_t *blob, const uint64_t *offsets, size_t n_proofs, uint32_t n_queries,
+                                     uint32_t *accept_bits, uint32_t *status, ssym_s101_trace_t *trace, int memspace);
 
 /* ------------------------------------------------------------------------- */
 /* Batched prover for the AIR verify_proof checks */

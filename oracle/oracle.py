@@ -72,6 +72,7 @@ class S101Trace(C.Structure):
         ("n_layers", C.c_uint32),
         ("beta_drawn", C.c_uint32 * 31), ("cp_ev", C.c_uint32 * 32), ("layer_mask", C.c_uint32 * 31),
         ("state_final", C.c_uint32 * 8), ("trace_root", (C.c_uint32 * 8) * 3),
+        ("query_ordinal", C.c_uint32), ("commit_state", C.c_uint32 * 8),
     ]
 
 
@@ -140,6 +141,8 @@ class Oracle:
         L.oracle_check_proof_of_work.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint64]
         L.oracle_stwo_verify_batch.argtypes = [C.POINTER(StwoConfig), u32p, C.c_size_t, C.c_size_t, u32p, u32p, C.c_void_p]
         L.oracle_s101_verify_batch.argtypes = [u32p, C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, u32p, u32p, C.c_void_p]
+        L.oracle_s101_group.argtypes = [C.c_size_t, C.c_uint32, u32p, C.c_void_p, u32p]
+        L.oracle_s101_group.restype = None
         L.oracle_sha256_bytes.argtypes = [C.c_char_p, C.c_size_t, u32p]
         assert L.oracle_sizeof_stwo_trace() == C.sizeof(StwoTrace), (L.oracle_sizeof_stwo_trace(), C.sizeof(StwoTrace))
         assert L.oracle_sizeof_s101_trace() == C.sizeof(S101Trace), (L.oracle_sizeof_s101_trace(), C.sizeof(S101Trace))
@@ -350,6 +353,15 @@ class Oracle:
         traces = (S101Trace * n)() if want_trace else None
         self.lib.oracle_s101_verify_batch(ptr(blob), offsets.ctypes.data_as(C.POINTER(C.c_uint64)), 0, n, ptr(accept), ptr(status),
                                           C.cast(traces, C.c_void_p) if want_trace else None)
+        return accept, status, traces
+
+    def s101_verify_multi_batch(self, blob: np.ndarray, offsets: np.ndarray, n_queries: int):
+        """ssym_stark101_verify_multi_batch (include/ssym.h): records proof-major, n_queries per proof -> (accept bits per proof, status per record, traces)."""
+        n = len(offsets) - 1
+        assert n % n_queries == 0
+        _, status, traces = self.s101_verify_batch(blob, offsets, want_trace=True)
+        accept = np.zeros((n // n_queries + 31) // 32, dtype=np.uint32)
+        self.lib.oracle_s101_group(C.c_size_t(n // n_queries), C.c_uint32(n_queries), ptr(status), C.cast(traces, C.c_void_p), ptr(accept))
         return accept, status, traces
 
     # ---- stark101 functions --------------------------------------------------------------

@@ -1316,7 +1316,8 @@ EXPORT void oracle_s101_verify_one(const uint32_t *rec, ssym_s101_trace_t *tr) {
     tr->first_fail_layer = 0xffffffffu;
     uint32_t total = rec[0], n_layers = rec[1];
     uint32_t ns[3] = {rec[2], rec[3], rec[4]};
-    if (n_layers > SSYM_S101_MAX_LIST || ns[0] > SSYM_S101_MAX_LIST || ns[1] > SSYM_S101_MAX_LIST || ns[2] > SSYM_S101_MAX_LIST || total < 20) {
+    if (n_layers > SSYM_S101_MAX_LIST || ns[0] > SSYM_S101_MAX_LIST || ns[1] > SSYM_S101_MAX_LIST || ns[2] > SSYM_S101_MAX_LIST || total < 20 ||
+        rec[6] > SSYM_S101_MAX_ORDINAL) {
         tr->status = SSYM_S101_ST_SHAPE;
         return;
     }
@@ -1332,6 +1333,7 @@ EXPORT void oracle_s101_verify_one(const uint32_t *rec, ssym_s101_trace_t *tr) {
         w += 16 + 8 * (rec[w + 11] + rec[w + 12]);
     }
     if (w != total) { tr->status = SSYM_S101_ST_SHAPE; return; }
+    tr->query_ordinal = rec[6];
 
     u256 state = sha256(root); /* verifier.simf:27 */
     /* fibsquare_read_coefficients air.simf:30-36 */
@@ -1350,8 +1352,10 @@ EXPORT void oracle_s101_verify_one(const uint32_t *rec, ssym_s101_trace_t *tr) {
         lp += 16 + 8 * (lp[11] + lp[12]);
     }
     state = s101_channel_mix_32(state, last_layer);
-    /* verifier.simf:32 */
+    store_u256(tr->commit_state, state);
+    /* verifier.simf:32; query ordinal k (include/ssym.h): the (k+1)-th draw, the query phase repeated on one channel */
     uint32_t idx = s101_channel_draw_32(&state, DOMAIN_EX_SIZE);
+    for (uint32_t k = 0; k < rec[6]; k++) idx = s101_channel_draw_32(&state, DOMAIN_EX_SIZE);
     tr->idx = idx;
     /* fibsquare_read_evaluations_checked air.simf:47-56 */
     uint32_t f[3], cur_idx = idx;
@@ -1413,6 +1417,25 @@ EXPORT void oracle_s101_verify_batch(const uint32_t *blob, const uint64_t *offse
             if (tr->status == 0) __atomic_fetch_or(&accept_bits[i / 32], 1u << (i % 32), __ATOMIC_RELAXED);
             else __atomic_fetch_and(&accept_bits[i / 32], ~(1u << (i % 32)), __ATOMIC_RELAXED);
         }
+    }
+}
+
+/* ssym_stark101_verify_multi_batch (include/ssym.h): records proof-major, n_queries per proof; per-record status (with SSYM_S101_ST_GROUP),
+ * one accept bit per proof.  `trace` as produced by oracle_s101_verify_batch over all n_proofs * n_queries records (its status fields are updated). */
+EXPORT void oracle_s101_group(size_t n_proofs, uint32_t n_queries, uint32_t *status, ssym_s101_trace_t *trace, uint32_t *accept_bits) {
+    for (size_t i = 0; i < n_proofs; i++) {
+        int ok = 1;
+        const ssym_s101_trace_t *first = &trace[i * n_queries];
+        for (uint32_t k = 0; k < n_queries; k++) {
+            ssym_s101_trace_t *tr = &trace[i * n_queries + k];
+            if (!(tr->status & SSYM_S101_ST_SHAPE) &&
+                (tr->query_ordinal != k || (first->status & SSYM_S101_ST_SHAPE) || memcmp(tr->commit_state, first->commit_state, 32) != 0))
+                tr->status |= SSYM_S101_ST_GROUP;
+            if (status) status[i * n_queries + k] = tr->status;
+            if (tr->status) ok = 0;
+        }
+        if (ok) accept_bits[i / 32] |= 1u << (i % 32);
+        else accept_bits[i / 32] &= ~(1u << (i % 32));
     }
 }
 

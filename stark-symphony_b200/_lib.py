@@ -63,6 +63,7 @@ class S101Trace(C.Structure):
         ("alpha", C.c_uint32 * 3), ("idx", C.c_uint32), ("x", C.c_uint32), ("cp0", C.c_uint32), ("n_layers", C.c_uint32),
         ("beta_drawn", C.c_uint32 * S101_MAX_LIST), ("cp_ev", C.c_uint32 * (S101_MAX_LIST + 1)), ("layer_mask", C.c_uint32 * S101_MAX_LIST),
         ("state_final", C.c_uint32 * 8), ("trace_root", (C.c_uint32 * 8) * 3),
+        ("query_ordinal", C.c_uint32), ("commit_state", C.c_uint32 * 8),
     ]
 
 
@@ -96,6 +97,7 @@ SYMBOLS = {
     "ssym_stwo_compact_pack_gpu": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _SZ, _V]),
     "ssym_stwo_verify_compact_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _V, _SZ, _V, _V, _I]),
     "ssym_stark101_verify_batch": (_I, [_V, _V, _V, _SZ, _V, _V, _V, _I]),
+    "ssym_stark101_verify_multi_batch": (_I, [_V, _V, _V, _SZ, _U32, _V, _V, _V, _I]),
     "ssym_stwo_prove_batch": (_I, [_V, C.POINTER(StwoConfig), _V, _SZ, _V, _I]),
     "ssym_m31_add": (_I, [_V, _V, _V, _V, _SZ, _I]),
     "ssym_m31_sub": (_I, [_V, _V, _V, _V, _SZ, _I]),

@@ -1615,8 +1615,9 @@ extern "C" int ssym_stwo_prove_batch(ssym_ctx_t *c, const ssym_stwo_config_t *cf
 }
 
 /* ---- stark101 batch -------------------------------------------------------------------------------- */
-extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, const uint64_t *offsets, size_t n, uint32_t *accept_bits,
-                                          uint32_t *status, ssym_s101_trace_t *trace, int memspace) {
+// n records; Q = 0: every record is a proof (ssym_stark101_verify_batch); Q >= 1: Q records per proof, one accept bit per proof (.._multi_batch)
+static int s101_verify_impl(ssym_ctx_t *c, const uint32_t *blob, const uint64_t *offsets, size_t n, uint32_t Q, uint32_t *accept_bits,
+                            uint32_t *status, ssym_s101_trace_t *trace, int memspace) {
     if (!c || !accept_bits || ((!blob || !offsets) && n)) return fail(SSYM_ERR_USAGE, "NULL argument");
     if (n == 0) return SSYM_OK;
     if (n > 0x7fffffffull) return fail(SSYM_ERR_USAGE, "batch too large for one call");
@@ -1639,7 +1640,7 @@ extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, c
         p.trace = trace;
         if (trace) CUDA_TRY(cudaMemsetAsync(trace, 0, n * sizeof(ssym_s101_trace_t), s));
         const size_t CH = 8192; // proofs per chunk of a large call
-        if (n >= 2 * CH && !trace && !c->profiling) {
+        if (n >= 2 * CH && !trace && !c->profiling && Q == 0) {
             // A large call is cut into chunks on four internal streams: the transcript kernel of one chunk (a dependent chain per proof: channel, field
             // divisions, fold chain — latency-bound at 256 warps per chunk) runs under the Merkle kernel of the previous one.  Ordered back into the
             // handle's stream before the call returns.
@@ -1662,7 +1663,8 @@ extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, c
             CUDA_TRY(cudaGetLastError());
             return SSYM_OK;
         }
-        launch_s101_verify(p, accept_bits, s, &c->launches, c->profiling ? &c->profiler : nullptr);
+        if (Q) launch_s101_verify_multi(p, Q, accept_bits, s, &c->launches, c->profiling ? &c->profiler : nullptr);
+        else launch_s101_verify(p, accept_bits, s, &c->launches, c->profiling ? &c->profiler : nullptr);
         CUDA_TRY(cudaGetLastError());
         return SSYM_OK;
     }
@@ -1675,7 +1677,7 @@ extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, c
         max_layers = std::max(max_layers, std::min<uint32_t>(blob[offsets[i] + 1], SSYM_S101_MAX_LIST));
     }
     p.max_layers = max_layers;
-    const size_t n_words = (n + 31) / 32;
+    const size_t n_words = ((Q ? n / Q : n) + 31) / 32;
     CUDA_TRY(c->stage[0].ensure(total_words * 4));
     CUDA_TRY(c->d_offsets.ensure((n + 1) * 8));
     CUDA_TRY(c->d_accept.ensure(n_words * 4));
@@ -1688,13 +1690,26 @@ extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, c
     p.status = c->d_status.as<uint32_t>();
     p.trace = trace ? c->d_trace.as<ssym_s101_trace_t>() : nullptr;
     if (trace) CUDA_TRY(cudaMemsetAsync(p.trace, 0, n * sizeof(ssym_s101_trace_t), s));
-    launch_s101_verify(p, c->d_accept.as<uint32_t>(), s, &c->launches, c->profiling ? &c->profiler : nullptr);
+    if (Q) launch_s101_verify_multi(p, Q, c->d_accept.as<uint32_t>(), s, &c->launches, c->profiling ? &c->profiler : nullptr);
+    else launch_s101_verify(p, c->d_accept.as<uint32_t>(), s, &c->launches, c->profiling ? &c->profiler : nullptr);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
     if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_s101_trace_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return SSYM_OK;
+}
+
+extern "C" int ssym_stark101_verify_batch(ssym_ctx_t *c, const uint32_t *blob, const uint64_t *offsets, size_t n, uint32_t *accept_bits,
+                                          uint32_t *status, ssym_s101_trace_t *trace, int memspace) {
+    return s101_verify_impl(c, blob, offsets, n, 0, accept_bits, status, trace, memspace);
+}
+
+extern "C" int ssym_stark101_verify_multi_batch(ssym_ctx_t *c, const uint32_t *blob, const uint64_t *offsets, size_t n_proofs, uint32_t n_queries,
+                                                uint32_t *accept_bits, uint32_t *status, ssym_s101_trace_t *trace, int memspace) {
+    if (n_queries == 0 || n_queries > SSYM_S101_MAX_ORDINAL + 1u) return fail(SSYM_ERR_USAGE, "n_queries must be in 1 .. 256");
+    if (n_proofs > 0x7fffffffull / n_queries) return fail(SSYM_ERR_USAGE, "batch too large for one call");
+    return s101_verify_impl(c, blob, offsets, n_proofs * n_queries, n_queries, accept_bits, status, trace, memspace);
 }
 
 /* ---- element-wise jets ------------------------------------------------------------------------------- */

@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(64) s101_transcript_kernel(S101Params p) {
     const uint32_t total = shape_ok ? rec[0] : 0, n_layers = shape_ok ? rec[1] : 0;
     const uint32_t ns0 = shape_ok ? rec[2] : 0, ns1 = shape_ok ? rec[3] : 0, ns2 = shape_ok ? rec[4] : 0;
     shape_ok = shape_ok && n_layers <= SSYM_S101_MAX_LIST && ns0 <= SSYM_S101_MAX_LIST && ns1 <= SSYM_S101_MAX_LIST && ns2 <= SSYM_S101_MAX_LIST;
+    const uint32_t ordinal = shape_ok ? rec[6] : 0;
+    shape_ok = shape_ok && ordinal <= SSYM_S101_MAX_ORDINAL;
     uint32_t w = 20 + 8 * (ns0 + ns1 + ns2);
     if (shape_ok) {
         for (uint32_t l = 0; l < n_layers; l++) {
@@ -154,7 +156,16 @@ __global__ void __launch_bounds__(64) s101_transcript_kernel(S101Params p) {
         }
     }
     s101_hash_state(state, &last_layer, 1); // channel_mix_32
-    const uint32_t idx = s101_draw(state, 8192u); // verifier.simf:32
+#pragma unroll
+    for (int k = 0; k < 8; k++) ctx[S101_CTX_COMMIT + k] = state[k];
+    ctx[S101_CTX_ORD] = ordinal;
+    if (tr) {
+        tr->query_ordinal = ordinal;
+        for (int k = 0; k < 8; k++) tr->commit_state[k] = state[k];
+    }
+    uint32_t idx = s101_draw(state, 8192u); // verifier.simf:32
+#pragma unroll 1
+    for (uint32_t k = 0; k < ordinal; k++) idx = s101_draw(state, 8192u); // query ordinal k (include/ssym.h): the query phase repeated on one channel
     const uint32_t f0 = rec[16], f1 = rec[17], f2 = rec[18];
     if (tr) { // the channel keeps absorbing the three evaluations (air.simf:43); nothing downstream reads it
         uint32_t st[8];
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(256) s101_finalize_kernel(S101Params p, uint32
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t s = i < p.n ? p.status[i] : 1u;
     const uint32_t ballot = __ballot_sync(0xffffffffu, s == 0);
-    if ((threadIdx.x & 31) == 0 && i < p.n) accept_bits[i >> 5] = ballot;
+    if ((threadIdx.x & 31) == 0 && i < p.n && accept_bits) accept_bits[i >> 5] = ballot;
     if (i < p.n && p.trace) {
         ssym_s101_trace_t *tr = p.trace + i;
         tr->status = s;
@@ -309,6 +320,35 @@ __global__ void __launch_bounds__(256) s101_finalize_kernel(S101Params p, uint32
             tr->first_fail_layer = ff;
         }
     }
+}
+
+// Multi-query grouping (ssym_stark101_verify_multi_batch): one thread per proof over its n_queries records — ordinal k in slot k, the channel state
+// after the commitments equal to the first record's (identical commitments), every record accepted.
+__global__ void __launch_bounds__(256) s101_group_kernel(S101Params p, uint32_t n_queries, uint32_t n_proofs, uint32_t *accept_bits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = i < n_proofs;
+    if (i < n_proofs) {
+        const uint32_t r0 = i * n_queries;
+        const uint32_t *c0 = p.ctx + (size_t)r0 * S101_CTX_WORDS;
+        const bool first_shape = (p.status[r0] & SSYM_S101_ST_SHAPE) != 0;
+        for (uint32_t k = 0; k < n_queries; k++) {
+            const uint32_t r = r0 + k;
+            uint32_t st = p.status[r];
+            if (!(st & SSYM_S101_ST_SHAPE)) {
+                const uint32_t *c = p.ctx + (size_t)r * S101_CTX_WORDS;
+                bool same = !first_shape && c[S101_CTX_ORD] == k;
+                for (int w = 0; w < 8; w++) same = same && c[S101_CTX_COMMIT + w] == c0[S101_CTX_COMMIT + w];
+                if (!same) {
+                    st |= SSYM_S101_ST_GROUP;
+                    p.status[r] = st;
+                    if (p.trace) p.trace[r].status = st;
+                }
+            }
+            ok = ok && st == 0;
+        }
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && i < n_proofs) accept_bits[i >> 5] = ballot;
 }
 
 void launch_s101_verify(const S101Params &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof) {
@@ -324,6 +364,14 @@ void launch_s101_verify(const S101Params &p, uint32_t *accept_bits, cudaStream_t
     s101_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
     if (prof) prof->end(6, s);
     if (launch_counter) *launch_counter += 3;
+}
+
+void launch_s101_verify_multi(const S101Params &p, uint32_t n_queries, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof) {
+    if (p.n == 0 || n_queries == 0) return;
+    launch_s101_verify(p, nullptr, s, launch_counter, prof); // every record on its own (per-record status and trace), then the proofs
+    const uint32_t n_proofs = p.n / n_queries;
+    s101_group_kernel<<<(n_proofs + 255) / 256, 256, 0, s>>>(p, n_queries, n_proofs, accept_bits);
+    if (launch_counter) *launch_counter += 1;
 }
 
 } // namespace ssym

@@ -9,7 +9,8 @@
 
 namespace ssym {
 
-enum : uint32_t { S101_CTX_NLAYERS = 0, S101_CTX_IDX = 1, S101_CTX_LAYER_OFF = 2, S101_CTX_WORDS = 40 };
+// per-record scratch: layer offsets at [2, 33); the query ordinal and the channel state after the commitments (multi-query grouping)
+enum : uint32_t { S101_CTX_NLAYERS = 0, S101_CTX_IDX = 1, S101_CTX_LAYER_OFF = 2, S101_CTX_ORD = 33, S101_CTX_COMMIT = 34, S101_CTX_WORDS = 48 };
 
 struct S101Params {
     const uint32_t *blob;    // concatenated records (include/ssym.h)
@@ -22,5 +23,7 @@ struct S101Params {
 };
 
 void launch_s101_verify(const S101Params &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof);
+// ssym_stark101_verify_multi_batch: p.n = n_proofs * n_queries records (proof-major); accept_bits: one bit per proof
+void launch_s101_verify_multi(const S101Params &p, uint32_t n_queries, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof);
 
 } // namespace ssym

@@ -257,6 +257,27 @@ class Verifier:
         check(self.lib.ssym_stark101_verify_batch(self.h, _ptr(blob), _ptr(offsets), n, _ptr(accept), _ptr(status), tptr, space))
         return accept, status, traces
 
+    def stark101_verify_multi_batch(self, blob, offsets, n_queries: int, want_trace: bool = False):
+        """Multi-query stark101 (ssym_stark101_verify_multi_batch, include/ssym.h): records proof-major, `n_queries` records of the reference's
+        witness shape per proof, record k verified under the (k+1)-th query draw.  Returns (accept bits per PROOF, status per RECORD, traces)."""
+        n = (offsets.numel() if hasattr(offsets, "numel") else offsets.size) - 1
+        if n_queries < 1 or n % n_queries:
+            raise SsymError("the number of records must be a multiple of n_queries")
+        n_proofs = n // n_queries
+        space = self._space(blob)
+        accept = self._alloc(blob, (n_proofs + 31) // 32)
+        status = self._alloc(blob, n)
+        traces, tptr = None, None
+        if want_trace:
+            if space == MEM_DEVICE:
+                traces = self._alloc(blob, n * C.sizeof(S101Trace), np.uint8)
+                tptr = _ptr(traces)
+            else:
+                traces = (S101Trace * n)()
+                tptr = C.cast(traces, C.c_void_p)
+        check(self.lib.ssym_stark101_verify_multi_batch(self.h, _ptr(blob), _ptr(offsets), n_proofs, n_queries, _ptr(accept), _ptr(status), tptr, space))
+        return accept, status, traces
+
     # ---- `.wit` text in (GPU tokeniser, csrc/wit_kernels.cu) ---------------------------------------------
     def stwo_pack_wit_batch(self, text, offsets, cfg: StwoConfig):
         """n `.wit` JSON texts (concatenated in `text`, witness i = bytes [offsets[i], offsets[i+1])) -> (packed (n, stride_words),

@@ -189,6 +189,19 @@ def pack_stark101_proof_json(proof: Dict[str, Any]) -> np.ndarray:
     return blob
 
 
+def pack_stark101_multiquery(queries: Sequence[Dict[str, Any]]) -> Tuple[np.ndarray, np.ndarray]:
+    """One multi-query stark101 proof (include/ssym.h, ssym_stark101_verify_multi_batch): queries[k] in the reference's proof-JSON shape
+    (scripts/fibsquare/prover.py:94-171; tests/golden/make_s101_multiquery.py) -> (blob, offsets) of len(queries) records, record k with ordinal k."""
+    recs = []
+    for k, q in enumerate(queries):
+        rec = pack_stark101_proof_json(q).copy()
+        rec[6] = k
+        recs.append(rec)
+    offsets = np.zeros(len(recs) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(r) for r in recs])
+    return np.concatenate(recs), offsets
+
+
 def compact_stwo(packed: np.ndarray, cfg: StwoConfig, out: Optional[np.ndarray] = None, ver=None) -> Tuple[np.ndarray, np.ndarray]:
     """Packed records -> the compact transport form (ssym_stwo_compact_pack, include/ssym.h): per tree every distinct sibling once plus
     one bit per path slot and one back reference per repeated slot; lossless for any record.  Returns (blob of u32 words, u64 word offsets [n + 1]); `out` may be a
