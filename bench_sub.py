@@ -19,9 +19,18 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 P = 2147483647
-# ALU-pipe lane-instructions per SHA-256 compression of the shared rolled / IMAD hashing loop (ncu: 103 994 368 ALU-pipe warp instructions for
-# 1024 x 3760 compressions, profiles/step_pipe_counts.json): used where a kernel built on that loop has no ncu count of its own (marked "estimate")
-ALU_LANES_PER_COMPRESSION = 103994368 * 32 / (1024 * 3760)
+# ALU-pipe lane-instructions per SHA-256 compression of the shared rolled / IMAD hashing loop: the ncu count of stwo_merkle_kernel over its 1024 x 3760
+# compressions, read from profiles/step_pipe_counts.json; used where a kernel built on that loop has no ncu count of its own (marked "estimate")
+def _alu_lanes_per_compression():
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "step_pipe_counts.json")))
+        m = c["modes"]["ref-literal"]
+        return m["kernels"]["stwo_merkle_kernel"]["alu_pipe_warp_inst"] * 32 / (m["proofs_per_launch"] * 3760)
+    except Exception:
+        return 104011264 * 32 / (1024 * 3760)
+
+
+ALU_LANES_PER_COMPRESSION = _alu_lanes_per_compression()
 
 
 def timed(torch, fn, stream, reps=5, warm=3):
@@ -77,7 +86,29 @@ def c1_stark101(S, ver, stream, torch, orc, int32_lanes, log_n=16):
         ver.stark101_verify_batch(d_blob, d_off)
     ver.profile_enable(False)
     kernel_ms = {k: v[0] / max(v[1], 1) for k, v in ver.profile_read().items()}
-    return {"kernel_ms": kernel_ms, "workload": f"BASELINE config 1: stark101 proof (p = 3*2^30+1, 1023-step trace, blowup 8) replicated x{n} + {len(bad_rows)} corrupted, device resident",
+    # multi-query stark101 (ssym_stark101_verify_multi_batch): the reference's proof decommitted at four positions, x 2^(log_n - 2) proofs
+    mq = json.load(open(os.path.join(golden, "stark101_multiquery.json")))
+    one, offs1 = S.witness.pack_stark101_multiquery(mq["queries"])
+    Q, n_mq = mq["n_queries"], n >> 2
+    mq_blob = np.tile(one, n_mq)
+    mq_off = np.zeros(n_mq * Q + 1, dtype=np.uint64)
+    mq_off[1:] = np.cumsum(np.tile(np.diff(offs1), n_mq))
+    mq_bad = list(range(5, n_mq, 101))
+    for r in mq_bad:
+        mq_blob[int(mq_off[r * Q + r % Q]) + 16] ^= 1  # f(x) of one of the proof's queries
+    dm_blob = torch.from_numpy(mq_blob.view(np.int32)).cuda()
+    dm_off = torch.from_numpy(mq_off.view(np.int64)).cuda()
+    ms_mq = timed(torch, lambda: ver.stark101_verify_multi_batch(dm_blob, dm_off, Q), stream)
+    m_accept, _, _ = ver.stark101_verify_multi_batch(dm_blob, dm_off, Q)
+    ver.synchronize()
+    m_bits = np.unpackbits(m_accept.cpu().numpy().view(np.uint8), bitorder="little")[:n_mq].astype(bool)
+    m_expect = np.ones(n_mq, dtype=bool)
+    m_expect[mq_bad] = False
+    assert (m_bits == m_expect).all()
+    multi = {"workload": f"the same proof decommitted at {Q} query positions (tests/golden/stark101_multiquery.json) x{n_mq} + {len(mq_bad)} corrupted", "queries_per_proof": Q,
+             "proofs": n_mq, "ms": ms_mq, "value": n_mq / (ms_mq * 1e-3), "unit": "proofs/s", "records_per_s": n_mq * Q / (ms_mq * 1e-3),
+             "parity": f"one accept bit per proof as constructed ({len(mq_bad)} rejected)"}
+    return {"kernel_ms": kernel_ms, "multi_query": multi, "workload": f"BASELINE config 1: stark101 proof (p = 3*2^30+1, 1023-step trace, blowup 8) replicated x{n} + {len(bad_rows)} corrupted, device resident",
             "proofs": n, "ms": ms, "value": n / (ms * 1e-3), "unit": "proofs/s", "compressions_per_s": comp, "packed_bytes_per_proof": int(len(blob) * 4),
             "input_mb": all_blob.nbytes / 1e6, "gb_per_s": all_blob.nbytes / (ms * 1e-3) / 1e9,
             "roofline": {"bound": "int32_alu", "frac": comp * ALU_LANES_PER_COMPRESSION / int32_lanes, "basis": "estimate: 480 compressions/proof x ALU-pipe lane-instructions "
