@@ -16,7 +16,7 @@ shift || true
 # racecheck only sees shared-memory hazards: it gets the shared-memory-heavy code (tokeniser, planner / shared-node schedule, compact expander,
 # prover FFTs).  memcheck / initcheck get the same plus the untrusted-record and ragged-size tests.  Sizes are small: the tools slow kernels 10-100x.
 RACE_TESTS=${*:-"tests/test_wit_ingest.py tests/test_compact.py tests/test_columns.py tests/test_draw_retry.py tests/test_query_dedup.py tests/test_gpu_parity.py::test_stwo_shared_node_schedule_matches_oracle tests/test_gpu_parity.py::test_stwo_fixture_trace_bit_exact tests/test_gpu_prover.py::test_gpu_prover_matches_reference_prover"}
-MEM_TESTS=${*:-"tests/test_wit_ingest.py tests/test_compact.py tests/test_columns.py tests/test_gpu_parity.py tests/test_config_space.py tests/test_draw_retry.py tests/test_query_dedup.py"}
+MEM_TESTS=${*:-"tests/test_wit_ingest.py tests/test_compact.py tests/test_columns.py tests/test_gpu_parity.py tests/test_config_space.py tests/test_draw_retry.py tests/test_query_dedup.py tests/test_s101_multiquery.py"}
 # synccheck: the named barriers of the warp-specialised transcript kernel (every Stwo test runs it; the repeated-draw records take its uniform retry path)
 SYNC_TESTS=${*:-"tests/test_draw_retry.py tests/test_gpu_parity.py::test_stwo_fixture_trace_bit_exact tests/test_query_dedup.py"}
 rc_all=0
