@@ -549,9 +549,10 @@ def main():
         return {"pinned": pinned_buf, "blob": full[:words], "words": words, "off": off_t, "off_view": off_t.numpy().view(np.uint64), "pack_s": secs,
                 "derived_per_proof": int(full[4]) if int(full[2]) == 0x33435353 else 0}
 
-    # Every leg transports records packed under the mode it verifies under (one pass over the kernels).  Records packed under the other mode verify
-    # too — two passes, complete then verify (include/ssym.h) — but on this fixture that costs more GPU time than the bytes it saves on the link
-    # (measured: 1.26 M proofs/s with the 30.7 KB prover-consistent records under ref-literal against 1.40 M with the 38.6 KB ref-literal records).
+    # The headline leg ships the records packed under prover-consistent — the smallest lossless form of the batch (30.7 KB per proof: every tree's
+    # siblings are derivable where paths meet) — whatever mode it verifies under.  Under ref-literal the library then takes the cross path
+    # (include/ssym.h; launch_stwo_verify_cross): one transcript, the records' own FRI evaluations and chains to complete the packed records, then the
+    # verification proper; bit-identical statuses (tests/test_compact.py).  `same_mode_records` is the leg on records packed under the call's own mode.
     cp = pack_compact(cfg)
     cp_other = pack_compact(cfg_other)
     t0 = time.perf_counter()
@@ -613,16 +614,23 @@ def main():
 
     c_bytes = c_words * 4 + c_off.numpy().nbytes
     c_value, c_sync, c_launches, bits_c = host_leg(lambda acc: ver.stwo_verify_compact_batch(c_blob, c_off_view, cfg, accept_out=acc), c_bytes)
+    ship = cp if args.mode == "prover-consistent" else cp_other  # the records packed under prover-consistent
+    s_bytes = ship["words"] * 4 + ship["off"].numpy().nbytes
+    if ship is cp:
+        s_value, s_sync, s_launches, bits_s = c_value, c_sync, c_launches, bits_c
+    else:
+        s_value, s_sync, s_launches, bits_s = host_leg(lambda acc: ver.stwo_verify_compact_batch(ship["blob"], ship["off_view"], cfg, accept_out=acc), s_bytes)
+    assert (bits_s == bits_c).all(), "records packed under the other mode verify differently"
     co_bytes = cp_other["words"] * 4 + cp_other["off"].numpy().nbytes
     co_value, co_sync, _, bits_co = host_leg(lambda acc: ver.stwo_verify_compact_batch(cp_other["blob"], cp_other["off_view"], cfg_other, accept_out=acc), co_bytes)
     assert int(np.unpackbits(bits_co.view(np.uint8), bitorder="little")[:n].sum()) == (n if other_mode == S.MODE_PROVER_CONSISTENT else 0)
     p_bytes = n * lo.stride_words * 4
     p_value, p_sync, p_launches, bits_p = host_leg(lambda acc: ver.stwo_verify_batch(host_view, cfg, n, accept_out=acc), p_bytes)
     assert (bits_c == bits_p).all() and (np.unpackbits(bits_p.view(np.uint8), bitorder="little")[:n] == bits[:n]).all(), "host legs disagree with the device leg"
-    copy_alone = plain_copy_gbs(c_pinned[:c_words], c_words * 4, False)
+    copy_alone = plain_copy_gbs(ship["pinned"][:ship["words"]], ship["words"] * 4, False)
     if world > 1:
         dist.barrier()
-    copy_conc = plain_copy_gbs(c_pinned[:c_words], c_words * 4, True)
+    copy_conc = plain_copy_gbs(ship["pinned"][:ship["words"]], ship["words"] * 4, True)
     conc_ranks = gather_ranks(torch, dist, world, [copy_alone, copy_conc])
 
     # end to end from the reference's own input format: `.wit` JSON TEXT in pinned host memory -> accept bits
@@ -714,14 +722,17 @@ def main():
                            "note": "same pipelined loop, same batch, the other semantics switch; under prover-consistent the fixture is ACCEPTED and the Merkle paths "
                                    "of a tree share the nodes above the height where they meet (hashed once, results per query identical: DESIGN.md section 4), "
                                    "so fewer compressions are executed than the reference's per-query count"},
-            "e2e": {"value": c_value, "unit": "proofs/s", "h2d_bytes_per_step": int(c_bytes * Re), "d2h_bytes_per_step": int(acc_host.nbytes * Re),
-                    "steps": e2e_steps, "passes_per_step": Re, "h2d_gbs_achieved": c_value / world * c_bytes / n / 1e9,
+            "e2e": {"value": s_value, "unit": "proofs/s", "h2d_bytes_per_step": int(s_bytes * Re), "d2h_bytes_per_step": int(acc_host.nbytes * Re),
+                    "steps": e2e_steps, "passes_per_step": Re, "h2d_gbs_achieved": s_value / world * s_bytes / n / 1e9,
                     "h2d_gbs_plain_copy": copy_alone, "h2d_gbs_plain_copy_concurrent": min(r[1] for r in conc_ranks),
                     "h2d_gbs_plain_copy_concurrent_per_rank": [r[1] for r in conc_ranks], "h2d_gbs_plain_copy_concurrent_aggregate": sum(r[1] for r in conc_ranks),
-                    "frac_of_concurrent_copy": (c_value / world * c_bytes / n / 1e9) / max(min(r[1] for r in conc_ranks), 1e-9),
-                    "sync_call_value": c_sync, "bytes_per_proof": c_words * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
-                    "gpu_launches_per_pass": c_launches,
-                    "derived_siblings_per_proof": cp["derived_per_proof"], "records_packed_under": args.mode,
+                    "frac_of_concurrent_copy": (s_value / world * s_bytes / n / 1e9) / max(min(r[1] for r in conc_ranks), 1e-9),
+                    "sync_call_value": s_sync, "bytes_per_proof": ship["words"] * 4 / n, "packed_bytes_per_proof": lo.stride_words * 4,
+                    "gpu_launches_per_pass": s_launches,
+                    "derived_siblings_per_proof": ship["derived_per_proof"], "records_packed_under": "prover-consistent", "verified_under": args.mode,
+                    "same_mode_records": {"value": c_value, "sync_call_value": c_sync, "bytes_per_proof": c_words * 4 / n, "records_packed_under": args.mode,
+                                          "derived_siblings_per_proof": cp["derived_per_proof"], "gpu_launches_per_pass": c_launches,
+                                          "note": "the same leg on records packed under the call's own mode (one pass over the kernels)"},
                     "host_pack": {"proofs_per_s": n / pack_s, "seconds_per_1024": pack_s, "inside_timed_region": False,
                                   "version2_host_only_proofs_per_s_per_core": n / pack_v2_s,
                                   "note": "ssym_stwo_compact_pack_gpu turns packed records into version 3 compact records BEFORE the clock starts: H2D of the packed "
@@ -737,7 +748,10 @@ def main():
                     "e2e_packed_value": p_value,
                     "note": "ssym_stwo_verify_compact_batch(SSYM_MEM_HOST) on pinned host buffers holding the batch in the compact transport form "
                             "(include/ssym.h, version 3: per Merkle tree every distinct 32-byte sibling once, none at all where another query's path computes it; "
-                            "lossless for any record; expanded on the GPU by stwo_expand_kernel + the Merkle kernel itself): chunked multi-buffered H2D -> expand -> verifier kernels -> D2H bitmap, every "
+                            "lossless for any record; expanded on the GPU by stwo_expand_kernel + the Merkle kernel itself).  The records are the ones packed under "
+                            "prover-consistent (the size of upstream stwo's minimal decommitment); verified under ref-literal they take one transcript, the records' own "
+                            "FRI chains to complete them and then the verification proper (launch_stwo_verify_cross), statuses bit-identical to the packed path: "
+                            "chunked multi-buffered H2D -> expand -> verifier kernels -> D2H bitmap, every "
                             "pass's copies inside the timed region.  PACKING IS OUTSIDE THE CLOCK (host_pack).  `value`: calls enqueued back to back "
                             "(ssym_set_host_async), one synchronize per step; `sync_call_value`: each call returns with its bitmap in host memory.  Bound by the host link; "
                             "`e2e_packed` is the same measurement on the reference-shaped fixed-stride packed records (no host packing at all)"},

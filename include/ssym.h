@@ -282,7 +282,8 @@ int ssym_synchronize(ssym_ctx_t *ctx);
 int ssym_set_pipeline_depth(ssym_ctx_t *ctx, int depth);
 /* Asynchronous SSYM_MEM_HOST mode for ssym_stwo_verify_batch (default off = the call returns with the results in place).
  * With on = 1 a host-buffer call only ENQUEUES its chunked H2D copies, kernels and D2H copies and returns; consecutive calls
- * then overlap (the H2D of call k+1 runs under the kernel tail of call k), and every output is valid after ssym_synchronize.
+ * then overlap (the H2D and the kernels of call k+1 run under the kernels of call k: the device-side result buffers are a ring over four calls),
+ * and every output is valid after ssym_synchronize.
  * The caller's buffers must be pinned (cudaHostAlloc / torch pin_memory) and must not be touched until then. */
 int ssym_set_host_async(ssym_ctx_t *ctx, int on);
 /* Witness texts the GPU tokeniser does not keep on its fast path (JSON escapes, `_` separators, upper-case hex, redundant parentheses,
@@ -362,7 +363,10 @@ int ssym_stwo_compact_pack(const ssym_stwo_config_t *cfg, const uint32_t *packed
  * are hashes of COMPUTED evaluations, so the derived slots of a record are expanded under the mode it was packed under ([5]), whatever mode it
  * is then verified under: from HOST buffers ssym_stwo_compact_expand / ssym_stwo_verify_compact_batch read that word (all records with derived
  * slots of one call must carry the same one; another is reported malformed) and, where it differs from cfg->mode, verification takes two
- * passes over the kernels — complete the records under their own mode, then verify under the call's.  Records in DEVICE memory are expanded
+ * passes over the kernels — complete the records under their own mode, then verify under the call's.  When only the semantics differ (same
+ * flags: the transcript does not depend on the semantics) the first pass is the records' FRI evaluations and FRI chains alone, on the one
+ * transcript both passes share: records packed under PROVER_CONSISTENT (the smallest form) verify under REF_LITERAL at the rate of the host
+ * link, with the statuses of the packed path.  Records in DEVICE memory are expanded
  * under cfg->mode only (a record with derived slots of another mode is reported malformed).  A proof packed under REF_LITERAL has derivable
  * siblings in its trace / composition trees only (its FRI paths do not verify, finding F1): pack under PROVER_CONSISTENT.  Requires 32 % Q == 0
  * (the Merkle kernel resolves a derived sibling with a warp shuffle between the Q chains of a tree); otherwise X = 0.

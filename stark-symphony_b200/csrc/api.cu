@@ -113,6 +113,13 @@ struct ssym_ctx {
     bool host_async = false;  // ssym_set_host_async: SSYM_MEM_HOST stwo calls return after enqueueing
     bool wit_host_fallback = true; // ssym_set_wit_host_fallback: witnesses the GPU tokeniser hands back are re-read by the host parser
     uint64_t host_chunks = 0; // staging-buffer parity persists across calls so that asynchronous calls can overlap
+    // Result buffers of host-buffer calls (accept bitmap, status words), a ring over consecutive calls: an enqueue-only call (host_async) writes a slot
+    // while the D2H of the previous call still reads another, so its kernels wait for the call RES_RING back — not for the one just enqueued
+    static const int RES_RING = 4;
+    DevBuf r_accept[RES_RING], r_status[RES_RING];
+    cudaEvent_t ev_res[RES_RING] = {nullptr, nullptr, nullptr, nullptr}; // recorded on the handle's stream after a call's D2H
+    bool res_used[RES_RING] = {false, false, false, false};
+    uint64_t host_calls = 0;
     StwoDedup dd_cache{};       // static part of the shared-node plan for dd_cache_key (configuration, chunk size)
     uint64_t dd_cache_key = 0;
     size_t dd_cache_entries = 0;
@@ -171,6 +178,7 @@ int ssym_create(int device, ssym_ctx_t **out) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < ssym_ctx::RES_RING; i++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_res[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wit_flags[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wit_parsed[i], cudaEventDisableTiming));
@@ -206,6 +214,10 @@ void ssym_destroy(ssym_ctx_t *c) {
         c->stage[i].release(); c->cstage[i].release(); c->coffs[i].release(); c->cflags[i].release(); c->cderive[i].release();
         cudaEventDestroy(c->ev_h2d[i]);
         cudaEventDestroy(c->ev_done[i]);
+    }
+    for (int i = 0; i < ssym_ctx::RES_RING; i++) {
+        c->r_accept[i].release(); c->r_status[i].release();
+        cudaEventDestroy(c->ev_res[i]);
     }
     DevBuf *bufs[] = {&c->tab_point, &c->tab_fold, &c->tab_flag,
                       &c->d_accept, &c->d_status, &c->d_trace, &c->d_offsets, &c->s101_ctx};
@@ -415,6 +427,9 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
         p.derive_stride = derive_stride;
         p.derive_mode = derive ? derive_mode : 0;
         p.packed_rw = const_cast<uint32_t *>(p.packed);
+        p.ctx_mode = cfg.mode;
+        p.derive_kinds = 3u;
+        p.fri_only = 0;
         memset(&p.dd, 0, sizeof p.dd);
         const bool share = c->merkle_sharing == 2 || (c->merkle_sharing == 1 && SSYM_MODE_SEMANTICS(cfg.mode) == SSYM_MODE_PROVER_CONSISTENT);
         if (share) { // the static part of the plan (bins, capacities) depends on the configuration and the chunk size only: computed once
@@ -442,13 +457,65 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
     return SSYM_OK;
 }
 
+// One chunk (<= STWO_DEVICE_CHUNK proofs) of version 3 compact records packed under `rec_mode`, verified under cfg.mode: same flags, other semantics
+// (launch_stwo_verify_cross: one transcript, the records' evaluations + FRI chains to complete the packed records, then the verification proper).
+static int stwo_launch_chunk_cross(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, uint32_t rec_mode, const ssym_stwo_layout_t &lo,
+                                   uint32_t *d_packed, size_t m, uint32_t *d_accept, uint32_t *d_status, cudaStream_t s, uint8_t *derive,
+                                   uint32_t derive_stride) {
+    int rc = ensure_lane_scratch(c, lane, cfg, m, true);
+    if (rc) return rc;
+    StwoParams p;
+    p.cfg = cfg;
+    p.lo = lo;
+    p.tab.point = c->tab_point.as<uint2>();
+    p.tab.fold_inv = c->tab_fold.as<uint32_t>();
+    for (uint32_t l = 0; l < SSYM_MAX_FRI_LAYERS; l++) p.tab.fold_off[l] = c->fold_off[l];
+    p.packed = d_packed;
+    p.packed_rw = d_packed;
+    p.ctx = lane.stwo_ctx.as<uint32_t>();
+    p.fri_evals = lane.stwo_evals.as<uint32_t>();
+    p.status = d_status;
+    p.trace = nullptr;
+    p.n = (uint32_t)m;
+    p.derive = derive;
+    p.derive_stride = derive_stride;
+    p.derive_mode = 1;
+    p.ctx_mode = cfg.mode;
+    p.derive_kinds = 3u;
+    p.fri_only = 0;
+    memset(&p.dd, 0, sizeof p.dd);
+    launch_stwo_verify_cross(p, rec_mode, lane.status.as<uint32_t>(), d_accept, s, &c->launches);
+    CUDA_TRY(cudaGetLastError());
+    return SSYM_OK;
+}
+
 // Host-buffer calls run chunk k's kernels on lane (k % HOST_BUFS)'s own stream: the latency-bound channel kernel of one chunk then overlaps the Merkle
 // kernel of the other instead of queueing behind it (a 256-proof chunk is 0.15 ms of channel kernel + 0.1 ms of everything else).
 // host_fork orders both lane streams after what the handle's stream holds (e.g. the previous call's D2H of the shared result buffers);
 // host_join orders the handle's stream after the chunks.
-static int host_fork(ssym_ctx *c) {
+static int host_fork(ssym_ctx *c, int ring_slot) {
+    if (c->host_async) { // enqueue-only calls overlap: this call's kernels only wait for the D2H of the call that used its result slot last
+        if (c->res_used[ring_slot])
+            for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) CUDA_TRY(cudaStreamWaitEvent(c->lanes[b].s, c->ev_res[ring_slot], 0));
+        return SSYM_OK;
+    }
     CUDA_TRY(cudaEventRecord(c->lanes[0].in, c->stream));
     for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) CUDA_TRY(cudaStreamWaitEvent(c->lanes[b].s, c->lanes[0].in, 0));
+    return SSYM_OK;
+}
+// the result slot of the next host-buffer call, its buffers sized for n proofs (all slots grow together: growing frees)
+static int host_result_slot(ssym_ctx *c, size_t n, int *slot) {
+    const size_t n_words = (n + 31) / 32;
+    if (c->r_accept[0].cap < n_words * 4 || c->r_status[0].cap < n * 4) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+        for (int r = 0; r < ssym_ctx::RES_RING; r++) {
+            CUDA_TRY(c->r_accept[r].ensure(n_words * 4));
+            CUDA_TRY(c->r_status[r].ensure(n * 4));
+            c->res_used[r] = false;
+        }
+    }
+    *slot = (int)(c->host_calls++ % ssym_ctx::RES_RING);
     return SSYM_OK;
 }
 static int host_join(ssym_ctx *c, const bool (&used)[ssym_ctx::HOST_BUFS]) {
@@ -514,17 +581,24 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     const size_t n_words = (n + 31) / 32;
     bool grow_stage = false;
     for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) grow_stage = grow_stage || c->stage[b].cap < hc * stride_b;
-    if (c->host_async && (grow_stage || c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4 ||
-                          (trace && c->d_trace.cap < n * sizeof(ssym_stwo_trace_t)))) { // growing a buffer frees it: drain the calls still using it
+    if (c->host_async && (grow_stage || (trace && c->d_trace.cap < n * sizeof(ssym_stwo_trace_t)))) { // growing a buffer frees it: drain the calls still using it
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     }
     for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) CUDA_TRY(c->stage[b].ensure(hc * stride_b));
-    CUDA_TRY(c->d_accept.ensure(n_words * 4));
-    CUDA_TRY(c->d_status.ensure(n * 4));
-    if (trace) CUDA_TRY(c->d_trace.ensure(n * sizeof(ssym_stwo_trace_t)));
+    int slot = 0;
+    rc = host_result_slot(c, n, &slot);
+    if (rc) return rc;
+    uint32_t *const r_accept = c->r_accept[slot].as<uint32_t>(), *const r_status = c->r_status[slot].as<uint32_t>();
+    if (trace) { // the trace buffer is not ringed: a call that wants traces waits for its predecessor
+        CUDA_TRY(c->d_trace.ensure(n * sizeof(ssym_stwo_trace_t)));
+        if (c->host_async) {
+            CUDA_TRY(cudaEventRecord(c->lanes[0].in, c->stream));
+            for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) CUDA_TRY(cudaStreamWaitEvent(c->lanes[b].s, c->lanes[0].in, 0));
+        }
+    }
     cudaStream_t s = c->stream;
-    rc = host_fork(c);
+    rc = host_fork(c, slot);
     if (rc) return rc;
     bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
     for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
@@ -535,17 +609,19 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
         CUDA_TRY(cudaMemcpyAsync(c->stage[b].p, packed + done * (size_t)lo.stride_words, m * stride_b, cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(ls, c->ev_h2d[b], 0));
-        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, c->stage[b].as<uint32_t>(), m, c->d_accept.as<uint32_t>() + done / 32,
-                               c->d_status.as<uint32_t>() + done, trace ? c->d_trace.as<ssym_stwo_trace_t>() + done : nullptr, ls);
+        rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, c->stage[b].as<uint32_t>(), m, r_accept + done / 32,
+                               r_status + done, trace ? c->d_trace.as<ssym_stwo_trace_t>() + done : nullptr, ls);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev_done[b], ls));
         used[b] = true;
     }
     rc = host_join(c, used);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
-    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(accept_bits, r_accept, n_words * 4, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, r_status, n * 4, cudaMemcpyDeviceToHost, s));
     if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_stwo_trace_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(c->ev_res[slot], s));
+    c->res_used[slot] = true;
     if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
@@ -867,9 +943,11 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     // and the verification proper on the complete records.
     const int64_t dmode = can_derive ? host_derived_mode(blob, offsets, n) : -1;
     const bool derived = dmode >= 0 && dmode <= 3, two_pass = derived && (uint32_t)dmode != cfg->mode;
+    // the transcript depends on the flags (sorted / de-duplicated queries), not on the semantics
+    const bool cross = two_pass && ((uint32_t)dmode & ~1u) == (cfg->mode & ~1u) && hc <= STWO_DEVICE_CHUNK && !c->profiling;
     ssym_stwo_config_t xcfg = *cfg;
     if (derived) { xcfg.mode = (uint32_t)dmode; p.mode = xcfg.mode; }
-    bool grow = c->d_accept.cap < n_words * 4 || c->d_status.cap < n * 4;
+    bool grow = false;
     for (int b = 0; b < ssym_ctx::HOST_BUFS; b++)
         grow = grow || c->stage[b].cap < hc * stride_b || c->cstage[b].cap < hc * max_rec_b || c->coffs[b].cap < (hc + 1) * sizeof(uint64_t) ||
                c->cflags[b].cap < hc * sizeof(uint32_t) || (derived && c->cderive[b].cap < hc * (size_t)sh.slots);
@@ -884,9 +962,11 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
         CUDA_TRY(c->cflags[b].ensure(hc * sizeof(uint32_t)));
         if (derived) CUDA_TRY(c->cderive[b].ensure(hc * (size_t)sh.slots));
     }
-    CUDA_TRY(c->d_accept.ensure(n_words * 4));
-    CUDA_TRY(c->d_status.ensure(n * 4));
-    rc = host_fork(c);
+    int slot = 0;
+    rc = host_result_slot(c, n, &slot);
+    if (rc) return rc;
+    uint32_t *const r_accept = c->r_accept[slot].as<uint32_t>(), *const r_status = c->r_status[slot].as<uint32_t>();
+    rc = host_fork(c, slot);
     if (rc) return rc;
     bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
     for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
@@ -902,25 +982,29 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
         p.packed = c->stage[b].as<uint32_t>(); p.flags = c->cflags[b].as<uint32_t>();
         p.derive = derived ? c->cderive[b].as<uint8_t>() : nullptr; // no version 3 record in the call: exactly the version 2 path (and any Merkle schedule)
         launch_stwo_expand(p, ls);
-        if (two_pass) { // complete the records under their own mode (verdicts of this pass are overwritten by the next), then verify under the call's
-            rc = stwo_launch_chunk(c, c->lanes[b], xcfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls, false,
+        if (two_pass && cross) { // other semantics, same flags: one transcript serves both passes and the first pass runs the FRI chains only
+            rc = stwo_launch_chunk_cross(c, c->lanes[b], *cfg, xcfg.mode, lo, p.packed, m, r_accept + done / 32, r_status + done, ls, p.derive, sh.slots);
+        } else if (two_pass) { // complete the records under their own mode (verdicts of this pass are overwritten by the next), then verify under the call's
+            rc = stwo_launch_chunk(c, c->lanes[b], xcfg, lo, p.packed, m, r_accept + done / 32, r_status + done, nullptr, ls, false,
                                    p.derive, sh.slots, 1);
             if (rc) return rc;
-            rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls);
+            rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, r_accept + done / 32, r_status + done, nullptr, ls);
         } else {
-            rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, c->d_accept.as<uint32_t>() + done / 32, c->d_status.as<uint32_t>() + done, nullptr, ls, false,
+            rc = stwo_launch_chunk(c, c->lanes[b], *cfg, lo, p.packed, m, r_accept + done / 32, r_status + done, nullptr, ls, false,
                                    p.derive, sh.slots, 1);
         }
         if (rc) return rc;
-        launch_compact_apply_flags(p.flags, c->d_status.as<uint32_t>() + done, c->d_accept.as<uint32_t>() + done / 32, (uint32_t)m, ls);
+        launch_compact_apply_flags(p.flags, r_status + done, r_accept + done / 32, (uint32_t)m, ls);
         c->launches += 2;
         CUDA_TRY(cudaEventRecord(c->ev_done[b], ls));
         used[b] = true;
     }
     rc = host_join(c, used);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(accept_bits, c->d_accept.p, n_words * 4, cudaMemcpyDeviceToHost, s));
-    if (status) CUDA_TRY(cudaMemcpyAsync(status, c->d_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(accept_bits, r_accept, n_words * 4, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, r_status, n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(c->ev_res[slot], s));
+    c->res_used[slot] = true;
     if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));

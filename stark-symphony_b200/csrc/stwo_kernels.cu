@@ -697,7 +697,12 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
 
     // the per-proof scalars come from K1: the OODS point P, the sample point of batch A, the powers of the DEEP coefficient
     const QM31 px = qm31_load4(ctx + CX::PX), py = qm31_load4(ctx + CX::PY);
-    const QM31 p2x = qm31_load4(ctx + CX::P2X), p2y = qm31_load4(ctx + CX::P2Y);
+    QM31 p2x = qm31_load4(ctx + CX::P2X), p2y = qm31_load4(ctx + CX::P2Y);
+    if (SSYM_MODE_SEMANTICS(p.ctx_mode) != SSYM_MODE_SEMANTICS(p.cfg.mode)) { // the transcript ran under the other semantics: stwo_scalars' other branch
+        const QM31 pxy = qm31_mul_nl(px, py);
+        p2x = literal ? px : qm31_point_dbl_x(px);
+        p2y = literal ? py : qm31_add(pxy, pxy);
+    }
 
     // ---- phase B: lane k computes the line coefficients of column k (aggregation order) with alpha^(k+1) ----
     QM31 sum_a_A, sum_c_A, sum_a_B, sum_c_B;
@@ -813,7 +818,9 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     // warp -> (chain type rank, group); ranks are ordered longest chain first: 0 = CP, 1 = FRI layer 0, 2 = trace,
     // 3.. = FRI layers 1..L
-    const uint32_t rank = warp / groups_per_type, group = warp % groups_per_type;
+    uint32_t rank = warp / groups_per_type;
+    const uint32_t group = warp % groups_per_type;
+    if (KMODE == 1 && p.fri_only) rank = rank == 0 ? 1u : rank + 2u; // FRI layer 0, then layers 1..L
     if (rank >= L + 3) return;
     const uint32_t item = group * 32 + lane;
     const bool in_batch = item < p.n * Q;
@@ -908,7 +915,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
             const uint32_t lvl = step - n_pre;
             const bool cur_left = (path & 1u) == 0; // divides_32(2, path): sha256_pair(cur, sib) else (sib, cur)
             if (KMODE == 1) { // a sibling the record left out = the node another query's path has reached at this level
-                const uint32_t pb = active ? dv[lvl] : 0xffu;
+                const uint32_t pb = active && ((p.derive_kinds >> (kind == 2 ? 1 : 0)) & 1u) ? dv[lvl] : 0xffu;
                 const uint32_t src = grp_base + (pb < Q ? pb : 0u);
                 uint32_t got[8];
 #pragma unroll
@@ -1488,6 +1495,43 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     stwo_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
     if (prof) prof->end(3, s);
     if (launch_counter) *launch_counter += 4;
+}
+
+void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *scratch_status, uint32_t *accept_bits, cudaStream_t s,
+                              uint64_t *launch_counter) {
+    if (p.n == 0) return;
+    const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
+    const uint32_t groups = (p.n * Q + 31) / 32;
+    auto k2 = [&](const StwoParams &q) {
+        switch (SSYM_STWO_COLUMNS(&q.cfg)) {
+        case 8: stwo_query_kernel<8><<<(q.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s>>>(q); break;
+        case 16: stwo_query_kernel<16><<<(q.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s>>>(q); break;
+        default: stwo_query_kernel<SSYM_NUM_COLUMNS><<<(q.n + K2_WARPS - 1) / K2_WARPS, 32 * K2_WARPS, 0, s>>>(q); break;
+        }
+    };
+    auto k3 = [&](const StwoParams &q, uint32_t ranks) {
+        const uint64_t warps = (uint64_t)groups * ranks;
+        stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 1><<<(uint32_t)((warps + 3) / 4), 128, 0, s>>>(q, groups, sha_mul_consts());
+    };
+    StwoParams pc = p; // the call's pass
+    pc.ctx_mode = p.cfg.mode;
+    pc.derive_mode = 1;
+    pc.derive_kinds = 1u; // the trace and composition trees derive the same nodes under either semantics; the FRI siblings are complete by then
+    pc.fri_only = 0;
+    memset(&pc.dd, 0, sizeof pc.dd);
+    stwo_channel_ws_kernel<<<(p.n + 31) / 32, 96, 0, s>>>(pc, sha_mul_consts());
+    StwoParams pr = pc; // the records' pass: evaluations and FRI chains only
+    pr.cfg.mode = rec_mode;
+    pr.status = scratch_status;
+    pr.trace = nullptr;
+    pr.derive_kinds = 2u;
+    pr.fri_only = 1;
+    k2(pr);
+    k3(pr, L + 1);
+    k2(pc);
+    k3(pc, L + 3);
+    stwo_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(pc, accept_bits);
+    if (launch_counter) *launch_counter += 6;
 }
 
 } // namespace ssym

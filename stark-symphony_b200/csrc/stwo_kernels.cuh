@@ -95,6 +95,10 @@ struct StwoParams {
     uint8_t *derive;
     uint32_t derive_stride, derive_mode;
     uint32_t *packed_rw; // = packed, writable (derive_mode 1)
+    // Records packed under another semantics than the call's (launch_stwo_verify_cross): the kernels of one pass run on the transcript context of
+    // the other.  ctx_mode = the mode K1 ran under (K2 re-derives the sample point of the CP columns when its own semantics differ);
+    // derive_kinds: which trees take derived siblings in this pass (bit 0 trace + composition, bit 1 FRI); fri_only: K3 runs the FRI chains only.
+    uint32_t ctx_mode, derive_kinds, fri_only;
 };
 
 // Fills the static part of StwoDedup (bins, capacities) for a configuration and a chunk capacity of `cap` proofs; returns the number of
@@ -111,5 +115,10 @@ void launch_stwo_tables(uint32_t lde_log, uint32_t n_fri_layers, uint2 *point, u
                         uint32_t *zero_flag, cudaStream_t s);
 void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof,
                         cudaStream_t front = nullptr, cudaEvent_t front_done = nullptr, int front_kernels = 0);
+// Version 3 compact records whose derived siblings were packed under `rec_mode`, verified under p.cfg.mode (same flags, other semantics): the
+// transcript once; the evaluations and the FRI chains of the records' mode, which complete the FRI siblings in the packed records (their verdicts go to
+// scratch_status and are dropped); then the verification proper.  p.derive / derive_stride as for derive_mode 1.
+void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *scratch_status, uint32_t *accept_bits, cudaStream_t s,
+                              uint64_t *launch_counter);
 
 } // namespace ssym

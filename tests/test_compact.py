@@ -370,6 +370,22 @@ def test_gpu_version3_chunks_async_and_corruptions(S, ver, orc):
     ver.set_host_async(False)
     for a, st in outs:
         assert (st == ref_status).all() and (a == ref_accept).all()
+    # the same records (packed under prover-consistent) verified under the reference's literal semantics — what bench.py's e2e leg ships: one
+    # transcript, the records' FRI chains to complete them, then the verification proper (launch_stwo_verify_cross); blocking and enqueue-only
+    # calls (overlapping: the result buffers are a ring) give the statuses of the packed path under that mode, which are the oracle's
+    lit = S.stwo_config("prod", S.MODE_REF_LITERAL)
+    lit_accept, lit_status, _ = ver.stwo_verify_batch(proofs.ravel(), lit, n, want_status=True)
+    _, o_lit, _ = orc.stwo_verify_batch(ocfg(lit), proofs[:64].ravel(), 64)
+    assert (lit_status[:64] == o_lit).all() and lit_status.all()
+    accept, status = ver.stwo_verify_compact_batch(blob, offsets, lit, want_status=True)
+    assert (status == lit_status).all() and (accept == lit_accept).all()
+    ver.set_host_async(True)
+    outs = [ver.stwo_verify_compact_batch(blob, offsets, lit if k % 2 == 0 else cfg, want_status=True) for k in range(7)]
+    ver.synchronize()
+    ver.set_host_async(False)
+    for k, (a, st) in enumerate(outs):
+        want_st, want_a = (lit_status, lit_accept) if k % 2 == 0 else (ref_status, ref_accept)
+        assert (st == want_st).all() and (a == want_a).all(), k
     # corruptions of one record
     rec = blob[: int(offsets[1])].copy()
     w = rec.size
