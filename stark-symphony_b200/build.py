@@ -60,6 +60,10 @@ def build(force: bool = False, verbose: bool = False, tuning: bool = False, sync
     if synccheck and "-DSSYM_SYNCCHECK" not in NVCC_FLAGS:  # named barriers behind one program location (csrc/stwo_kernels.cu: k1_bar_rs), for tools/sanitize.sh
         NVCC_FLAGS.append("-DSSYM_SYNCCHECK")
         force = True
+    extra = os.environ.get("SSYM_NVCC_EXTRA", "").split()  # experiment builds: extra -D switches (e.g. -DK1_R_ADDMODE=0)
+    if extra:
+        NVCC_FLAGS.extend(f for f in extra if f not in NVCC_FLAGS)
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
     stale = force or not os.path.exists(LIB) or not os.path.exists(CLI) or min(os.path.getmtime(LIB), os.path.getmtime(CLI)) < _deps_mtime()

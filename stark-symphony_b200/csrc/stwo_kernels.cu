@@ -138,6 +138,11 @@ __device__ __noinline__ uint32_t stwo_scalars(const StwoParams &p, uint32_t i, Q
 #define K1_ADDMODE 1 // adds as IMAD, as in the Merkle kernels.  Plain adds (0: 3-input IADD3s, shorter chains) make a lone launch 4 % faster (0.123 vs
                      // 0.129 ms), but in the pipelined loop this kernel runs under Merkle kernels that are bound by the ALU pipe, where every ALU slot counts
 #endif
+#ifndef K1_R_ADDMODE
+#define K1_R_ADDMODE 4 // the round warp of the warp-specialised kernel: a lone dependent chain whose latency is what a lone launch costs.  a' = T1 + Sigma0 + Maj
+                       // as ONE 3-input IADD3 shortens it: 88.6 -> 82.5 us per launch (mode 1: 88.6, plain adds: 84.7, T1 chain only: 82.8); its ALU
+                       // slots are 1.5 % of a pass
+#endif
 template <int NP>
 __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul mul) {
     const ShaAdd<K1_ADDMODE> A(mul);
@@ -422,6 +427,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
     }
 
     if (role == 0) { // ---- warp R: rounds ------------------------------------------------------------------------------------
+        const ShaAdd<K1_R_ADDMODE> AR(mul);
         uint32_t h[8];
         for (;;) {
             k1_bar_rs(); // control ready
@@ -430,16 +436,16 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
             sha_iv(h);
 #pragma unroll 1
             for (uint32_t b = 0; b < nblocks; b++) {
-                if (pad64 && b == 1) { sha_compress_pad64_rolled<K1_ADDMODE>(h, A); continue; }
+                if (pad64 && b == 1) { sha_compress_pad64_rolled<K1_R_ADDMODE>(h, AR); continue; }
                 uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll 1
                 for (uint32_t grp = 0; grp < 4; grp++) {
                     k1_bar_rs(); // group `grp` produced (and group grp - 1 consumed: its buffer may be overwritten)
                     const uint32_t(*kw)[32] = s_kw[grp & 1];
-                    SSYM_SHA_ROUND4(A, a, bb, c, d, e, f, g, hh, kw[0][lane], kw[1][lane], kw[2][lane], kw[3][lane]);
-                    SSYM_SHA_ROUND4(A, e, f, g, hh, a, bb, c, d, kw[4][lane], kw[5][lane], kw[6][lane], kw[7][lane]);
-                    SSYM_SHA_ROUND4(A, a, bb, c, d, e, f, g, hh, kw[8][lane], kw[9][lane], kw[10][lane], kw[11][lane]);
-                    SSYM_SHA_ROUND4(A, e, f, g, hh, a, bb, c, d, kw[12][lane], kw[13][lane], kw[14][lane], kw[15][lane]);
+                    SSYM_SHA_ROUND4(AR, a, bb, c, d, e, f, g, hh, kw[0][lane], kw[1][lane], kw[2][lane], kw[3][lane]);
+                    SSYM_SHA_ROUND4(AR, e, f, g, hh, a, bb, c, d, kw[4][lane], kw[5][lane], kw[6][lane], kw[7][lane]);
+                    SSYM_SHA_ROUND4(AR, a, bb, c, d, e, f, g, hh, kw[8][lane], kw[9][lane], kw[10][lane], kw[11][lane]);
+                    SSYM_SHA_ROUND4(AR, e, f, g, hh, a, bb, c, d, kw[12][lane], kw[13][lane], kw[14][lane], kw[15][lane]);
                 }
                 h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
             }
