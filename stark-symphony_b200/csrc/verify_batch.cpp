@@ -10,6 +10,7 @@
 //
 //   verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--mode {ref-literal,prover-consistent}]
 //                (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--cost] [--quiet] [--host-pack]
+//                [--queries Q]
 //
 // --cost (stwo): after verifying, prints what the reference PROGRAM executes per proof — sha_256_ctx_8_* jet calls and compressions, M31
 // multiplications / additions / inversions, eq_256 — from the cost model of include/ssym.h (ssym_stwo_cost) fed with the queries each
@@ -45,7 +46,8 @@ static bool read_file(const std::string &path, std::string &out) {
 static void usage() {
     fprintf(stderr,
             "usage: verify-batch --program {stwo,stark101} [--preset {prod,testing}] [--columns {4,8,16}] [--mode {ref-literal,prover-consistent}]\n"
-            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--cost] [--dedup-queries] [--quiet] [--host-pack]\n");
+            "                    (--witness a.wit [b.wit ...] | --witness-dir DIR) [--replicate N] [--gpus K] [--trace out.json] [--cost] [--dedup-queries] [--quiet] [--host-pack]\n"
+            "                    [--queries Q]   (stark101: every Q consecutive witnesses are ONE proof, witness k under the (k+1)-th query draw)\n");
 }
 
 static std::string hex_digest(const uint32_t *w) {
@@ -66,6 +68,7 @@ int main(int argc, char **argv) {
     int gpus = 1;
     uint32_t columns = SSYM_NUM_COLUMNS; // NUM_COLUMNS of the program the witnesses were made for (config.simf:14)
     bool quiet = false, host_pack = false, want_cost = false, dedup = false;
+    uint32_t queries = 1; // stark101 multi-query (include/ssym.h ssym_stark101_verify_multi_batch): witnesses per proof
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](const char *what) -> std::string {
@@ -87,6 +90,7 @@ int main(int argc, char **argv) {
         else if (a == "--cost") want_cost = true;
         else if (a == "--dedup-queries") dedup = true;
         else if (a == "--host-pack") host_pack = true;
+        else if (a == "--queries") queries = (uint32_t)strtoul(next("--queries").c_str(), nullptr, 10);
         else if (a == "--help" || a == "-h") { usage(); return 0; }
         else { fprintf(stderr, "Error: unknown argument %s\n", a.c_str()); usage(); return 2; }
     }
@@ -101,6 +105,13 @@ int main(int argc, char **argv) {
         std::sort(witnesses.begin(), witnesses.end());
     }
     if ((program != "stwo" && program != "stark101") || witnesses.empty() || replicate < 1 || gpus < 1) { usage(); return 2; }
+    if (queries != 1) {
+        if (program != "stark101" || queries < 1 || queries > SSYM_S101_MAX_ORDINAL + 1u || witnesses.size() % queries) {
+            fprintf(stderr, "Error: --queries Q groups the witnesses of --program stark101 by Q (1 .. 256); %zu witnesses given\n", witnesses.size());
+            return 2;
+        }
+        host_pack = true; // the query ordinal is a word of the packed record
+    }
     uint32_t mode_id;
     if (mode == "ref-literal") mode_id = SSYM_MODE_REF_LITERAL;
     else if (mode == "prover-consistent") mode_id = SSYM_MODE_PROVER_CONSISTENT;
@@ -175,6 +186,7 @@ int main(int argc, char **argv) {
                 std::fill(rec.begin(), rec.begin() + 20, 0u);
                 rec[0] = 20;
             }
+            if (rc == SSYM_OK) rec[6] = (uint32_t)(f % queries); // query ordinal: witness k of a proof is verified under the (k+1)-th draw
             blob.insert(blob.end(), rec.begin(), rec.begin() + words);
             offsets.push_back(blob.size());
         }
@@ -188,11 +200,13 @@ int main(int argc, char **argv) {
     auto t1 = std::chrono::steady_clock::now();
 
     // contiguous shards over the GPUs, one host thread and one handle per GPU; shard sizes are multiples of 32
-    gpus = (int)std::min<size_t>((size_t)gpus, (n + 31) / 32);
+    const size_t unit = 32 * (size_t)queries; // shard sizes are multiples of 32 proofs
+    gpus = (int)std::min<size_t>((size_t)gpus, (n + unit - 1) / unit);
     std::vector<int> rcs(gpus, 0);
     std::vector<std::string> errs(gpus);
     std::vector<std::thread> threads;
-    const size_t per = (((n + gpus - 1) / gpus) + 31) & ~(size_t)31;
+    const size_t per = (((n + gpus - 1) / gpus) + unit - 1) / unit * unit;
+    std::vector<uint32_t> proof_accept((n / queries + 31) / 32, 0); // --queries: one bit per proof
     for (int g = 0; g < gpus; g++) {
         threads.emplace_back([&, g]() {
             const size_t b = std::min(n, g * per), e = std::min(n, b + per);
@@ -215,8 +229,12 @@ int main(int argc, char **argv) {
                     std::vector<uint64_t> offs(offsets.begin() + b, offsets.begin() + e + 1);
                     const uint64_t base = offs[0];
                     for (auto &o : offs) o -= base;
-                    rc = ssym_stark101_verify_batch(ctx, blob.data() + base, offs.data(), e - b, accept.data() + b / 32, status.data() + b,
-                                                    want_trace ? traces101.data() + b : nullptr, SSYM_MEM_HOST);
+                    if (queries > 1)
+                        rc = ssym_stark101_verify_multi_batch(ctx, blob.data() + base, offs.data(), (e - b) / queries, queries, proof_accept.data() + b / queries / 32,
+                                                              status.data() + b, want_trace ? traces101.data() + b : nullptr, SSYM_MEM_HOST);
+                    else
+                        rc = ssym_stark101_verify_batch(ctx, blob.data() + base, offs.data(), e - b, accept.data() + b / 32, status.data() + b,
+                                                        want_trace ? traces101.data() + b : nullptr, SSYM_MEM_HOST);
                 }
             }
             if (rc != SSYM_OK) errs[g] = ssym_last_error();
@@ -233,7 +251,8 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < n; i++) {
         const size_t f = i % n_files;
         if (gpu_ingest && wit_flags[i] != SSYM_WIT_OK) parse_reject[f] = 1;
-        bool ok = ((accept[i / 32] >> (i % 32)) & 1) && !parse_reject[f];
+        bool ok = (queries > 1 ? status[i] == 0 && ((proof_accept[i / queries / 32] >> (i / queries % 32)) & 1) : ((accept[i / 32] >> (i % 32)) & 1)) && !parse_reject[f];
+        if (queries > 1 && !ok && status[i] == 0 && !parse_reject[f]) status[i] |= SSYM_S101_ST_GROUP; // rejected with its proof: another of its records failed
         if (parse_reject[f]) status[i] |= SSYM_ST_SHAPE;
         n_accept += ok;
         if (!quiet) printf("%s %s%s\n", ok ? "accept" : "reject", witnesses[f].c_str(), ok ? "" : (" status=0x" + [&] { char b[16]; snprintf(b, sizeof b, "%08x", status[i]); return std::string(b); }()).c_str());

@@ -218,3 +218,26 @@ def test_multiquery_replicated_device(S, ver, orc):
     st = status.cpu().numpy().view(np.uint32).reshape(n, Q)
     for i, k in bad.items():
         assert st[i, k] != 0 and not np.delete(st[i], k).any()
+
+
+@pytest.mark.gpu
+def test_cli_multiquery(S, tmp_path):
+    """verify-batch --program stark101 --queries 4: every four consecutive witnesses (the reference's `.wit` shape) are one proof."""
+    import subprocess
+
+    g = golden()
+    Q = g["n_queries"]
+    paths = []
+    for k in range(Q):
+        p = tmp_path / f"q{k}.wit"
+        p.write_text(wit_text(g["queries"][k]))
+        paths.append(str(p))
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stark-symphony_b200", "bin", "verify-batch")
+    ok = subprocess.run([cli, "--program", "stark101", "--queries", str(Q), "--witness", *paths, "--replicate", "3"], capture_output=True, text=True)
+    assert ok.returncode == 0 and ok.stdout.count("accept") == 3 * Q, (ok.stdout, ok.stderr)
+    swapped = [paths[1], paths[0]] + paths[2:]
+    bad = subprocess.run([cli, "--program", "stark101", "--queries", str(Q), "--witness", *swapped], capture_output=True, text=True)
+    assert bad.returncode == 1 and bad.stdout.count("reject") == Q and "Error: Failed to run program" in bad.stderr, (bad.stdout, bad.stderr)
+    # without --queries each witness is a one-query proof under the FIRST draw: only the reference's own proof (query 0) is accepted
+    single = subprocess.run([cli, "--program", "stark101", "--host-pack", "--witness", *paths], capture_output=True, text=True)
+    assert single.returncode == 1 and single.stdout.splitlines()[0].startswith("accept") and single.stdout.count("reject") == Q - 1
