@@ -493,6 +493,31 @@ static int stwo_launch_chunk_cross(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym
 // kernel of the other instead of queueing behind it (a 256-proof chunk is 0.15 ms of channel kernel + 0.1 ms of everything else).
 // host_fork orders both lane streams after what the handle's stream holds (e.g. the previous call's D2H of the shared result buffers);
 // host_join orders the handle's stream after the chunks.
+// Chunk sizes of a host-buffer call (multiples of 32, each <= hc).  Enqueue-only calls: uniform (the next call's copies run under this call's tail).
+// Blocking calls: the call ends one chunk-chain after its last byte arrives (~0.24 ms of latency-bound kernels whatever the chunk's size), and the
+// chain of the chunk before must have ended by then too — so the chunks taper: the last two are small, the bytes they give up travel earlier.
+static std::vector<size_t> host_chunk_plan(size_t n, size_t hc, bool async) {
+    std::vector<size_t> sizes; // every chunk but the last is a multiple of 32 (a chunk's accept bits start at a word)
+    size_t left = n;
+    if (!async && hc >= 256 && n > 256 && n <= 8 * hc) {
+        size_t last = std::min<size_t>(224, std::max<size_t>(64, (n / 8 + 31) & ~(size_t)31));
+        const size_t prev = std::min<size_t>(hc, (last * 3 / 2 + 31) & ~(size_t)31);
+        if (last + prev + 32 <= n) {
+            size_t body = n - last - prev;
+            last += body % 32; // the remainder travels in the last chunk (<= 255 proofs)
+            body -= body % 32;
+            const size_t k = (body + hc - 1) / hc;
+            const size_t each = ((body + k - 1) / k + 31) & ~(size_t)31;
+            for (size_t rest = body; rest;) { const size_t m = std::min(each, rest); sizes.push_back(m); rest -= m; }
+            sizes.push_back(prev);
+            sizes.push_back(last);
+            return sizes;
+        }
+    }
+    while (left) { const size_t m = std::min(hc, left); sizes.push_back(m); left -= m; }
+    return sizes;
+}
+
 static int host_fork(ssym_ctx *c, int ring_slot) {
     if (c->host_async) { // enqueue-only calls overlap: this call's kernels only wait for the D2H of the call that used its result slot last
         if (c->res_used[ring_slot])
@@ -601,8 +626,8 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     rc = host_fork(c, slot);
     if (rc) return rc;
     bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
-    for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
-        const size_t m = std::min(hc, n - done);
+    size_t done = 0;
+    for (const size_t m : host_chunk_plan(n, hc, c->host_async || c->profiling)) {
         const int b = (int)(c->host_chunks % ssym_ctx::HOST_BUFS);
         cudaStream_t ls = c->profiling ? s : c->lanes[b].s; // per-kernel event timing wants one strictly serial stream
         if (c->host_chunks >= (uint64_t)ssym_ctx::HOST_BUFS) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
@@ -614,6 +639,8 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev_done[b], ls));
         used[b] = true;
+        done += m;
+        c->host_chunks++;
     }
     rc = host_join(c, used);
     if (rc) return rc;
@@ -969,8 +996,8 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     rc = host_fork(c, slot);
     if (rc) return rc;
     bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
-    for (size_t done = 0; done < n; done += hc, c->host_chunks++) {
-        const size_t m = std::min(hc, n - done);
+    size_t done = 0;
+    for (const size_t m : host_chunk_plan(n, hc, c->host_async || c->profiling)) {
         const int b = (int)(c->host_chunks % ssym_ctx::HOST_BUFS);
         cudaStream_t ls = c->profiling ? s : c->lanes[b].s;
         if (c->host_chunks >= (uint64_t)ssym_ctx::HOST_BUFS) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
@@ -998,6 +1025,8 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
         c->launches += 2;
         CUDA_TRY(cudaEventRecord(c->ev_done[b], ls));
         used[b] = true;
+        done += m;
+        c->host_chunks++;
     }
     rc = host_join(c, used);
     if (rc) return rc;

@@ -49,6 +49,10 @@ def main():
             ref = np.zeros(words, dtype=np.uint32)
             for _ in range(3):
                 call(ref)
+            t0 = time.perf_counter()
+            for _ in range(32):
+                call(ref)  # blocking calls
+            sync_rate = n * 32 / (time.perf_counter() - t0)
             ver.set_host_async(True)
             for k in range(4):
                 call(rows[k])
@@ -67,7 +71,7 @@ def main():
             assert (rows == ref[None, :]).all()
             accepted = int(np.unpackbits(ref.view(np.uint8), bitorder="little")[:n].sum())
             out[f"packed {packed_under} / verified {verify_under}"] = {
-                "proofs_per_s": n * passes * steps / secs, "bytes_per_proof": bytes_per_proof, "h2d_gbs": n * passes * steps * bytes_per_proof / secs / 1e9,
+                "proofs_per_s": n * passes * steps / secs, "blocking_calls_proofs_per_s": sync_rate, "bytes_per_proof": bytes_per_proof, "h2d_gbs": n * passes * steps * bytes_per_proof / secs / 1e9,
                 "host_enqueue_share": enq / secs, "accepted": accepted}
     print(json.dumps(out, indent=1))
     ver.close()
