@@ -170,6 +170,7 @@ int ssym_create(int device, ssym_ctx_t **out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(SSYM_ERR_CUDA, "libssym is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
     CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(stwo_kernels_init_device());
     ssym_ctx *c = new ssym_ctx();
     c->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));

@@ -367,8 +367,9 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 #define K1_BAR_RS 1 // warps R + S: group produced / group consumed / digest ready / control ready (k1_bar_rs)
-#define K1_BAR_F_GO 2   // S arrives, F waits: the three drawn elements the scalars need are in shared memory
+#define K1_BAR_F_GO 2   // D arrives, F waits: the three drawn elements the scalars need are in shared memory
 #define K1_BAR_F_DONE 3 // F arrives, S waits: the scalars' status bits are in shared memory
+#define K1_BAR_D_DONE 4 // D arrives, S waits: the draws are stored, their status bits are in shared memory
 // The R <-> S hand-over barrier.  compute-sanitizer's synccheck reports "divergent thread(s) in block" whenever the warps of a named barrier arrive
 // from different program locations (tools/synccheck_probe.cu: the plain two-warp producer / consumer pattern of the PTX manual is flagged, the same
 // barrier behind one location is not), so a -DSSYM_SYNCCHECK build (build.py --synccheck, tools/sanitize.sh synccheck) puts it into ONE non-inlined
@@ -383,12 +384,15 @@ __device__ __forceinline__ void k1_bar_rs() { named_bar_sync(K1_BAR_RS, 64); }
 #endif
 #define K1_HDR_WORDS (24 + 4 * SSYM_MAX_COLUMNS + 64 + 8 + 8 * (SSYM_MAX_FRI_LAYERS - 1) + 4 + 2 + 6) // the largest header: ssym_stwo_layout's off_qvals
 
-__global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMul mul) {
+__global__ void __launch_bounds__(128) stwo_channel_ws_kernel(StwoParams p, ShaMul mul) {
     __shared__ uint32_t s_kw[2][16][32]; // K + W of one 16-round group per buffer, [round][lane]
     __shared__ uint32_t s_dig[8][32];    // digest of the finished message (R -> S)
     __shared__ uint32_t s_ctl[4];        // {blocks of the next message, second block is the constant padding block, done}
     __shared__ uint32_t s_felt[12][32];  // oods_t, cp_alpha, deep_alpha (S -> F)
     __shared__ uint32_t s_fbits[32];     // status bits of the scalars (F -> S)
+    __shared__ uint32_t s_dbits[32];     // status bits of the draws (D -> S)
+    __shared__ uint32_t s_seq[1];        // digests published so far (S -> D)
+    extern __shared__ __align__(16) uint32_t s_dyn[]; // the published digests, (L + 5) x [8][32] words
     // Everything the channel absorbs lies in the proof's header (roots, OODS samples, last coefficient, nonce: words [0, off_qvals)).  The CTA
     // copies the 32 headers into shared memory first (coalesced 128-bit loads, all in flight together), so that no global-memory latency sits
     // between two compressions of the chain: warp S assembles a block from shared memory.  [word][proof], rows padded to 33 against bank conflicts.
@@ -403,11 +407,12 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
     {
         const uint32_t hq = p.lo.off_qvals / 4, total = 32 * hq; // uint4s per header (sections are 32-byte aligned)
 #pragma unroll 1
-        for (uint32_t t0 = threadIdx.x; t0 < total; t0 += 8 * 96) { // eight loads in flight per thread before the first store
+        if (threadIdx.x == 0) s_seq[0] = 0;
+        for (uint32_t t0 = threadIdx.x; t0 < total; t0 += 8 * 128) { // eight loads in flight per thread before the first store
             uint4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const uint32_t t = t0 + u * 96;
+                const uint32_t t = t0 + u * 128;
                 v[u] = make_uint4(0, 0, 0, 0);
                 if (t < total) {
                     const uint32_t ip = min(blockIdx.x * 32 + t / hq, p.n - 1);
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const uint32_t t = t0 + u * 96;
+                const uint32_t t = t0 + u * 128;
                 if (t < total) {
                     const uint32_t pr = t / hq, q4 = t % hq;
                     s_hw[4 * q4 + 0][pr] = v[u].x; s_hw[4 * q4 + 1][pr] = v[u].y; s_hw[4 * q4 + 2][pr] = v[u].z; s_hw[4 * q4 + 3][pr] = v[u].w;
@@ -467,34 +472,136 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
         named_bar_arrive(K1_BAR_F_DONE, 64);
         return;
     }
-    // ---- warp S: state machine + message schedule ---------------------------------------------------------------------------
     const ssym_stwo_layout_t &lo = p.lo;
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
-    const uint32_t NCOL = SSYM_STWO_COLUMNS(&p.cfg) + SSYM_NUM_CP_PARTITIONS;
-    const uint32_t *pk = p.packed + (size_t)idx * lo.stride_words;
     uint32_t *ctx = p.ctx + (size_t)idx * CX::WORDS;
     ssym_stwo_trace_t *tr = p.trace && live ? p.trace + idx : nullptr;
-    uint32_t status = 0, n_sent = 0, tries = 0, retries = 0, d[8]; // channel_init channel.simf:31-33
-    bool exhausted = false, settled = false;
-    QM31 felt = qm31_zero();
+    uint32_t(*s_dq)[8][32] = reinterpret_cast<uint32_t(*)[8][32]>(s_dyn); // digest after the mix that precedes draw group k (S -> D), k = 0 .. L + 4
+
+    if (role == 3) { // ---- warp D: the draws ----------------------------------------------------------------------------------
+        // A draw hashes digest || counter and leaves the digest alone (channel.simf:36-44), and a mix hashes digest || proof data and restarts the
+        // counter (:154-172): the MIXES are the transcript's one dependent chain (32 of its 46 compressions), every draw hangs off the digest of the mix
+        // before it.  This warp takes those digests from warp S in order and runs the draws beside the chain: cp_alpha, oods_t, deep_alpha, one
+        // folding coefficient per FRI layer, the queries.  A draw is one block, digest || n_sent || padding, compressed here with its own schedule.
+        uint32_t retries = 0, dbits = 0;
+        const uint32_t query_mask = shl32(G & 0xff, 1u) - 1u;
+        const volatile uint32_t *seq = &s_seq[0];
+#pragma unroll 1
+        for (uint32_t k = 0; k < L + 5; k++) {
+            while (*seq <= k) {}
+            __threadfence_block();
+            uint32_t d[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = s_dq[k][j][lane];
+            uint32_t n_sent = 0;
+            if (k == L + 4) { // fri_generate_queries fri/queries.simf:30-43: 8 queries per draw, masked to the LDE domain
+#pragma unroll 1
+                for (uint32_t q0 = 0; q0 < Q; q0 += 8) {
+                    uint32_t w[16], h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) w[j] = d[j];
+                    w[8] = n_sent; w[9] = 0x80000000u;
+#pragma unroll
+                    for (int j = 10; j < 15; j++) w[j] = 0;
+                    w[15] = 9u * 32u;
+                    sha_iv(h);
+                    sha_compress_rolled<K1_ADDMODE>(h, w, A);
+                    n_sent = n_sent + 1u;
+                    for (uint32_t j = 0; live && j < 8 && q0 + j < Q; j++) {
+                        ctx[CX::QUERIES + q0 + j] = h[j] & query_mask;
+                        if (tr) tr->queries[q0 + j] = h[j] & query_mask;
+                    }
+                }
+                break;
+            }
+            // channel_draw_qm31 (channel.simf:115-141): retry (<= 256 draws) until the first four words are < 2p.  The step is uniform over the warp:
+            // a settled proof hashes along (its hash is not looked at) while another repeats its draw.
+            bool settled = false;
+            uint32_t tries = 0;
+            QM31 felt = qm31_zero();
+#pragma unroll 1
+            do {
+                uint32_t w[16], h[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) w[j] = d[j];
+                w[8] = n_sent; w[9] = 0x80000000u;
+#pragma unroll
+                for (int j = 10; j < 15; j++) w[j] = 0;
+                w[15] = 9u * 32u;
+                sha_iv(h);
+                sha_compress_rolled<K1_ADDMODE>(h, w, A);
+                if (!settled) {
+                    const bool ok = h[0] < 4294967294u && h[1] < 4294967294u && h[2] < 4294967294u && h[3] < 4294967294u;
+                    tries++;
+                    if (ok || tries == 256) {
+                        retries += tries - 1u;
+                        settled = true;
+                        if (!ok) dbits |= SSYM_ST_DRAW_EXHAUSTED;
+                        felt = qm31(m31_reduce(h[0]), m31_reduce(h[1]), m31_reduce(h[2]), m31_reduce(h[3]));
+                    }
+                    n_sent = n_sent + 1u; // channel_draw_u256 channel.simf:36-44
+                }
+            } while (!__all_sync(0xffffffffu, settled));
+            if (k == 0) {
+                if (live) qm31_store4(ctx + CX::CP_ALPHA, felt);
+                if (tr) qm31_store(tr->cp_alpha, felt);
+                s_felt[4][lane] = felt.r.a; s_felt[5][lane] = felt.r.b; s_felt[6][lane] = felt.i.a; s_felt[7][lane] = felt.i.b;
+            } else if (k == 1) { // channel.simf:143-144
+                s_felt[0][lane] = felt.r.a; s_felt[1][lane] = felt.r.b; s_felt[2][lane] = felt.i.a; s_felt[3][lane] = felt.i.b;
+            } else if (k == 2) {
+                if (live) qm31_store4(ctx + CX::DEEP_ALPHA, felt);
+                if (tr) qm31_store(tr->deep_alpha, felt);
+                s_felt[8][lane] = felt.r.a; s_felt[9][lane] = felt.r.b; s_felt[10][lane] = felt.i.a; s_felt[11][lane] = felt.i.b;
+                __threadfence_block();
+                named_bar_arrive(K1_BAR_F_GO, 64); // warp F starts on the scalars
+            } else {
+                if (live) qm31_store4(ctx + CX::FRI_ALPHA + 4 * (k - 3), felt);
+                if (tr) qm31_store(tr->fri_alpha[k - 3], felt);
+            }
+        }
+        uint32_t used = Q;
+        if (live && (p.cfg.mode & SSYM_MODE_QUERY_DEDUP)) { // include/ssym.h: sort the drawn queries, keep the distinct ones in slots [0, U), zero the rest
+            uint32_t *qs = ctx + CX::QUERIES;
+            for (uint32_t a = 1; a < Q; a++) {
+                const uint32_t v = qs[a];
+                uint32_t b = a;
+                for (; b > 0 && qs[b - 1] > v; b--) qs[b] = qs[b - 1];
+                qs[b] = v;
+            }
+            used = 0;
+            for (uint32_t a = 0; a < Q; a++) {
+                const uint32_t v = qs[a];
+                if (a == 0 || v != qs[used - 1]) qs[used++] = v;
+            }
+            for (uint32_t a = used; a < Q; a++) qs[a] = 0;
+            if (tr)
+                for (uint32_t a = 0; a < Q; a++) tr->queries[a] = qs[a];
+        }
+        if (live) {
+            ctx[CX::N_USED] = used;
+            if (tr) { tr->n_queries_used = used; tr->draw_retries = retries; }
+        }
+        s_dbits[lane] = dbits;
+        __threadfence_block();
+        named_bar_arrive(K1_BAR_D_DONE, 64);
+        return;
+    }
+
+    // ---- warp S: the mixes (the dependent chain) + their message schedule ------------------------------------------------------
+    const uint32_t NCOL = SSYM_STWO_COLUMNS(&p.cfg) + SSYM_NUM_CP_PARTITIONS;
+    uint32_t status = 0, d[8]; // channel_init channel.simf:31-33
 #pragma unroll
     for (int j = 0; j < 8; j++) d[j] = 0;
-    uint32_t state = TX_MIX_CONST, layer = 0, q0 = 0;
-    const uint32_t query_mask = shl32(G & 0xff, 1u) - 1u;
+    // mix m: 0 constant root, 1 trace root, 2 composition root (evals/commit.simf:20-35), 3 OODS samples (deep/oods.simf:44-64), 4 .. 4 + L the FRI
+    // roots, 5 + L the last-layer coefficient (fri/commit.simf:72-85), 6 + L the nonce (pow.simf:22-35)
 #pragma unroll 1
-    while (state != TX_DONE) {
-        uint32_t off = 0, n = 1;
-        bool draw = false;
-        switch (state) {
-        case TX_MIX_CONST: off = lo.off_commit; n = 8; break;
-        case TX_MIX_TRACE: off = lo.off_commit + 8; n = 8; break;
-        case TX_MIX_CP: off = lo.off_commit + 16; n = 8; break;
-        case TX_MIX_OODS: off = lo.off_oods_trace; n = 4 * NCOL; break;
-        case TX_MIX_FRI_ROOT: off = layer == 0 ? lo.off_fri_first_root : lo.off_fri_inner_root + 8 * (layer - 1); n = 8; break;
-        case TX_MIX_LAST: off = lo.off_last_coeff; n = 4; break;
-        case TX_MIX_NONCE: off = lo.off_pow_nonce; n = 2; break;
-        default: draw = true; break;
-        }
+    for (uint32_t m = 0; m < L + 7; m++) {
+        uint32_t off, n = 8;
+        if (m < 3) off = lo.off_commit + 8 * m;
+        else if (m == 3) { off = lo.off_oods_trace; n = 4 * NCOL; }
+        else if (m < 5 + L) off = m == 4 ? lo.off_fri_first_root : lo.off_fri_inner_root + 8 * (m - 5);
+        else if (m == 5 + L) { off = lo.off_last_coeff; n = 4; }
+        else { off = lo.off_pow_nonce; n = 2; }
         const uint32_t nwords = 8 + n, nblocks = (nwords + 3 + 15) >> 4;
         const bool pad64 = nwords == 16; // the 12 digest-sized mixes: the second block is the constant padding block of a 64-byte message
         if (lane == 0) { s_ctl[0] = nblocks; s_ctl[1] = pad64 ? 1u : 0u; s_ctl[2] = 0u; }
@@ -505,12 +612,12 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
             uint32_t w[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                const uint32_t m = b * 16 + j;
+                const uint32_t mw = b * 16 + j;
                 uint32_t v = 0;
-                if (m < 8) v = d[j & 7]; // only in block 0, where m == j
-                else if (m < nwords) v = draw ? n_sent : s_hw[off + (m - 8)][lane];
-                else if (m == nwords) v = 0x80000000u;
-                else if (m == nblocks * 16 - 1) v = nwords * 32u;
+                if (mw < 8) v = d[j & 7]; // only in block 0, where mw == j
+                else if (mw < nwords) v = s_hw[off + (mw - 8)][lane];
+                else if (mw == nwords) v = 0x80000000u;
+                else if (mw == nblocks * 16 - 1) v = nwords * 32u;
                 w[j] = v;
             }
 #pragma unroll 1
@@ -532,123 +639,38 @@ __global__ void __launch_bounds__(96) stwo_channel_ws_kernel(StwoParams p, ShaMu
             }
         }
         k1_bar_rs(); // digest ready
-        uint32_t h[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) h[k] = s_dig[k][lane];
-        // ---- what the step does with the hash (as in the one-thread kernel above) ----
-        if (!draw) { // channel_mix_*: the digest moves, the counter restarts
+        for (int k = 0; k < 8; k++) d[k] = s_dig[k][lane]; // channel_mix_*: the digest moves, the counter restarts
+        // which draw group hangs off this digest: trace root -> cp_alpha, composition root -> oods_t, OODS samples -> deep_alpha, FRI root l -> its
+        // folding coefficient, nonce -> the queries
+        const uint32_t slot = m == 0 || m == 5 + L ? 0xffffffffu : m <= 4 + L ? m - 1 : L + 4;
+        if (slot != 0xffffffffu) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) d[j] = h[j];
-            n_sent = 0;
-            if (state == TX_MIX_CP && tr)
-                for (int j = 0; j < 8; j++) tr->digest_commit[j] = d[j];
-            if (state == TX_MIX_LAST && tr)
-                for (int j = 0; j < 8; j++) tr->digest_fri[j] = d[j];
-            if (state == TX_MIX_NONCE) { // check_proof_of_work pow.simf:22-35
-                const uint64_t value = ((uint64_t)__byte_perm(d[7], 0, 0x0123) << 32) | __byte_perm(d[6], 0, 0x0123);
-                if (!(value < p.cfg.pow_target)) status |= SSYM_ST_POW_FAIL;
-                if (tr) {
-                    for (int j = 0; j < 8; j++) tr->digest_pow[j] = d[j];
-                    tr->pow_value[0] = (uint32_t)(value >> 32);
-                    tr->pow_value[1] = (uint32_t)value;
-                }
-            }
-            switch (state) {
-            case TX_MIX_CONST: state = TX_MIX_TRACE; break;
-            case TX_MIX_TRACE: state = TX_DRAW_CP_ALPHA; break;
-            case TX_MIX_CP: state = TX_DRAW_OODS_T; break;
-            case TX_MIX_OODS: state = TX_DRAW_DEEP_ALPHA; break;
-            case TX_MIX_FRI_ROOT: state = TX_DRAW_FRI_ALPHA; break;
-            case TX_MIX_LAST: state = TX_MIX_NONCE; break;
-            default: state = TX_DRAW_QUERIES; break; // TX_MIX_NONCE
-            }
-            continue;
-        }
-        if (state == TX_DRAW_QUERIES) { // fri_generate_queries fri/queries.simf:30-43: 8 queries per draw, masked to the LDE domain
-            n_sent = n_sent + 1u;
-            for (uint32_t j = 0; live && j < 8 && q0 + j < Q; j++) {
-                ctx[CX::QUERIES + q0 + j] = h[j] & query_mask;
-                if (tr) tr->queries[q0 + j] = h[j] & query_mask;
-            }
-            q0 += 8;
-            if (q0 >= Q) state = TX_DONE;
-            continue;
-        }
-        // channel_draw_qm31 (channel.simf:115-141): retry (<= 256 draws) until the first four words are < 2p.  The step is uniform over the warp:
-        // a settled proof hashes along (its hash is not looked at) while another repeats its draw.
-        if (!settled) {
-            const bool ok = h[0] < 4294967294u && h[1] < 4294967294u && h[2] < 4294967294u && h[3] < 4294967294u;
-            tries++;
-            if (ok || tries == 256) {
-                retries += tries - 1u;
-                settled = true;
-                exhausted = exhausted || !ok;
-                felt = qm31(m31_reduce(h[0]), m31_reduce(h[1]), m31_reduce(h[2]), m31_reduce(h[3]));
-            }
-            n_sent = n_sent + 1u; // channel_draw_u256 channel.simf:36-44
-        }
-        if (!__all_sync(0xffffffffu, settled)) continue;
-        settled = false;
-        tries = 0;
-        switch (state) {
-        case TX_DRAW_CP_ALPHA:
-            if (live) qm31_store4(ctx + CX::CP_ALPHA, felt);
-            if (tr) qm31_store(tr->cp_alpha, felt);
-            s_felt[4][lane] = felt.r.a; s_felt[5][lane] = felt.r.b; s_felt[6][lane] = felt.i.a; s_felt[7][lane] = felt.i.b;
-            break;
-        case TX_DRAW_OODS_T: // channel.simf:143-144
-            s_felt[0][lane] = felt.r.a; s_felt[1][lane] = felt.r.b; s_felt[2][lane] = felt.i.a; s_felt[3][lane] = felt.i.b;
-            break;
-        case TX_DRAW_DEEP_ALPHA:
-            if (live) qm31_store4(ctx + CX::DEEP_ALPHA, felt);
-            if (tr) {
-                for (int j = 0; j < 8; j++) tr->digest_oods[j] = d[j];
-                qm31_store(tr->deep_alpha, felt);
-            }
-            s_felt[8][lane] = felt.r.a; s_felt[9][lane] = felt.r.b; s_felt[10][lane] = felt.i.a; s_felt[11][lane] = felt.i.b;
+            for (int k = 0; k < 8; k++) s_dq[slot][k][lane] = d[k];
             __threadfence_block();
-            named_bar_arrive(K1_BAR_F_GO, 64); // warp F starts on the scalars; this warp goes on with fri_commit
-            break;
-        default: // TX_DRAW_FRI_ALPHA
-            if (live) qm31_store4(ctx + CX::FRI_ALPHA + 4 * layer, felt);
-            if (tr) qm31_store(tr->fri_alpha[layer], felt);
-            break;
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_seq[0]) = slot + 1;
         }
-        switch (state) {
-        case TX_DRAW_CP_ALPHA: state = TX_MIX_CP; break;
-        case TX_DRAW_OODS_T: state = TX_MIX_OODS; break;
-        case TX_DRAW_DEEP_ALPHA: state = TX_MIX_FRI_ROOT; break;
-        default: layer++; state = layer <= L ? TX_MIX_FRI_ROOT : TX_MIX_LAST; break;
+        if (tr) {
+            uint32_t *dst = m == 2 ? tr->digest_commit : m == 3 ? tr->digest_oods : m == 5 + L ? tr->digest_fri : m == 6 + L ? tr->digest_pow : nullptr;
+            if (dst)
+                for (int j = 0; j < 8; j++) dst[j] = d[j];
+        }
+        if (m == 6 + L) { // check_proof_of_work pow.simf:22-35
+            const uint64_t value = ((uint64_t)__byte_perm(d[7], 0, 0x0123) << 32) | __byte_perm(d[6], 0, 0x0123);
+            if (!(value < p.cfg.pow_target)) status |= SSYM_ST_POW_FAIL;
+            if (tr) {
+                tr->pow_value[0] = (uint32_t)(value >> 32);
+                tr->pow_value[1] = (uint32_t)value;
+            }
         }
     }
     if (lane == 0) s_ctl[2] = 1u;
     k1_bar_rs(); // releases warp R
-    uint32_t used = Q;
-    if (live && (p.cfg.mode & SSYM_MODE_QUERY_DEDUP)) { // include/ssym.h: sort the drawn queries, keep the distinct ones in slots [0, U), zero the rest
-        uint32_t *qs = ctx + CX::QUERIES;
-        for (uint32_t a = 1; a < Q; a++) {
-            const uint32_t v = qs[a];
-            uint32_t b = a;
-            for (; b > 0 && qs[b - 1] > v; b--) qs[b] = qs[b - 1];
-            qs[b] = v;
-        }
-        used = 0;
-        for (uint32_t a = 0; a < Q; a++) {
-            const uint32_t v = qs[a];
-            if (a == 0 || v != qs[used - 1]) qs[used++] = v;
-        }
-        for (uint32_t a = used; a < Q; a++) qs[a] = 0;
-        if (tr)
-            for (uint32_t a = 0; a < Q; a++) tr->queries[a] = qs[a];
-    }
-    if (exhausted) status |= SSYM_ST_DRAW_EXHAUSTED;
     if (SSYM_MODE_SEMANTICS(p.cfg.mode) == SSYM_MODE_REF_LITERAL && ((G - (L + 1u)) & 0xff) != 0) status |= SSYM_ST_FINAL_LOG; // fri/verify.simf:127
-    named_bar_sync(K1_BAR_F_DONE, 64); // the scalars are done (long ago)
-    if (live) {
-        ctx[CX::N_USED] = used;
-        if (tr) { tr->n_queries_used = used; tr->draw_retries = retries; }
-        p.status[idx] = status | s_fbits[lane];
-    }
+    named_bar_sync(K1_BAR_F_DONE, 64); // the scalars are done
+    named_bar_sync(K1_BAR_D_DONE, 64); // the draws are done
+    if (live) p.status[idx] = status | s_fbits[lane] | s_dbits[lane];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1414,6 +1436,13 @@ void launch_stwo_tables(uint32_t G, uint32_t L, uint2 *point, uint32_t *fold_inv
     stwo_tables_kernel<<<(total + 127) / 128, 128, 0, s>>>(G, L, point, fold_inv, offs, zero_flag);
 }
 
+// dynamic shared memory of the transcript kernel: one [8][32]-word digest per draw group; with its ~38 KB of static arrays the CTA passes 48 KB,
+// so every device that runs it opts in once (ssym_create)
+static size_t k1_dyn_smem(const StwoParams &p) { return (size_t)(p.cfg.n_fri_layers + 5) * 8 * 32 * sizeof(uint32_t); }
+cudaError_t stwo_kernels_init_device() {
+    return cudaFuncSetAttribute(stwo_channel_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (SSYM_MAX_FRI_LAYERS + 5) * 8 * 32 * (int)sizeof(uint32_t));
+}
+
 void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof,
                         cudaStream_t front, cudaEvent_t front_done, int front_kernels) {
     if (p.n == 0) return;
@@ -1433,7 +1462,7 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
         else if (np == 1) stwo_channel_kernel<1><<<(p.n + 63) / 64, 64, 0, s1>>>(p, sha_mul_consts());
         else
 #endif
-            stwo_channel_ws_kernel<<<(p.n + 31) / 32, 96, 0, s1>>>(p, sha_mul_consts());
+            stwo_channel_ws_kernel<<<(p.n + 31) / 32, 128, k1_dyn_smem(p), s1>>>(p, sha_mul_consts());
     }
     if (use_front && front_kernels < 2) { cudaEventRecord(front_done, front); cudaStreamWaitEvent(s, front_done, 0); }
     if (prof) { prof->end(0, s); prof->begin(1, s); }
@@ -1525,7 +1554,7 @@ void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *
     pc.derive_kinds = 1u; // the trace and composition trees derive the same nodes under either semantics; the FRI siblings are complete by then
     pc.fri_only = 0;
     memset(&pc.dd, 0, sizeof pc.dd);
-    stwo_channel_ws_kernel<<<(p.n + 31) / 32, 96, 0, s>>>(pc, sha_mul_consts());
+    stwo_channel_ws_kernel<<<(pc.n + 31) / 32, 128, k1_dyn_smem(pc), s>>>(pc, sha_mul_consts());
     StwoParams pr = pc; // the records' pass: evaluations and FRI chains only
     pr.cfg.mode = rec_mode;
     pr.status = scratch_status;

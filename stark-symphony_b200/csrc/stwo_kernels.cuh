@@ -111,6 +111,7 @@ struct Profiler {
     virtual void end(int kernel_id, cudaStream_t s) = 0;
 };
 
+cudaError_t stwo_kernels_init_device(); // once per device, before the first launch (opt-in shared memory of the transcript kernel)
 void launch_stwo_tables(uint32_t lde_log, uint32_t n_fri_layers, uint2 *point, uint32_t *fold_inv, const uint32_t *fold_off,
                         uint32_t *zero_flag, cudaStream_t s);
 void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof,
