@@ -347,15 +347,22 @@ __global__ void __launch_bounds__(64) stwo_channel_kernel(StwoParams p, ShaMul m
 }
 
 // ------------------------------------------------------------------------------------------
-// K1, warp-specialised (the default).  A transcript is one dependent chain, and a lone warp issues at most one instruction every ~2 cycles per pipe
+// K1, warp-specialised (the default).  A transcript is a dependent chain, and a lone warp issues at most one instruction every ~2 cycles per pipe
 // (ncu on the one-thread-per-proof kernel above: 0.34 instructions per cycle, 1.15 cycles of fixed-latency wait per issue): its latency is its
-// instruction count.  So the instruction stream of 32 transcripts is cut across THREE warps of one CTA, on three schedulers:
-//   warp R  the 64 rounds of every compression and nothing else: K[t] + W[t] comes from shared memory                 (~1000 instructions / compression)
-//   warp S  the state machine of the transcript (what is hashed next, draws, retries, PoW, queries) and the message schedule: it assembles each block
-//           and produces K + W for rounds 16 g .. 16 g + 15 one group AHEAD of warp R (double-buffered; one named barrier per group)
+// instruction count on the chain.  Two cuts:
+//  * only the MIXES are a chain.  A draw hashes digest || counter and leaves the digest alone (channel.simf:36-44); a mix hashes digest || proof data
+//    and restarts the counter (:154-172); and what is mixed is proof data only.  So of the 46 compressions 32 (the mixes) depend on one another and
+//    the 14 draws each hang off the digest of the mix before them: they run on a warp of their own, beside the chain;
+//  * the instruction stream of the chain itself is cut across two warps on two schedulers.
+//   warp R  the 64 rounds of every compression of a mix and nothing else: K[t] + W[t] comes from shared memory       (~1000 instructions / compression)
+//   warp S  which mix comes next, the PoW check and the message schedule: it assembles each block and produces K + W for rounds 16 g .. 16 g + 15 one
+//           group AHEAD of warp R (double-buffered; one named barrier per group); after a mix it publishes the digest for warp D (one mbarrier per
+//           digest: arrive = release, no reuse, so the chain never waits for the draws)
+//   warp D  the draws, in order: cp_alpha, oods_t, deep_alpha, one folding coefficient per FRI layer, the queries — retries, sorting / de-duplication
+//           of the queries included; each draw is one block, compressed here with its own schedule
 //   warp F  the per-proof scalars (stwo_scalars: OODS point, composition-polynomial check, powers of the DEEP coefficient) as soon as the DEEP
-//           coefficient is drawn, i.e. while the 31 compressions of fri_commit / PoW / queries are still running
-// Same values, same order of hash inputs; lane l of every warp serves proof 32 * blockIdx.x + l.
+//           coefficient is drawn, i.e. while fri_commit / PoW / queries are still running
+// Same values, same hash inputs; lane l of every warp serves proof 32 * blockIdx.x + l.
 // ------------------------------------------------------------------------------------------
 // bar.sync / bar.arrive are warp-aligned instructions: the lanes of a warp that went separate ways (a lane-0 store, a per-lane loop) reconverge first
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -382,6 +389,20 @@ __device__ __noinline__ void k1_bar_rs() {
 #else
 __device__ __forceinline__ void k1_bar_rs() { named_bar_sync(K1_BAR_RS, 64); }
 #endif
+// mbarrier (shared-memory barrier object, phase 0 only): the S -> D hand-over of a digest.  32 arrivals complete the phase; arrive has release, a
+// successful try_wait acquire semantics at CTA scope; compute-sanitizer's racecheck / synccheck follow it.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE;\n\tbra WAIT;\n\tDONE:\n\t}" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(bar)),
+                 "r"(parity)
+                 : "memory");
+}
 #define K1_HDR_WORDS (24 + 4 * SSYM_MAX_COLUMNS + 64 + 8 + 8 * (SSYM_MAX_FRI_LAYERS - 1) + 4 + 2 + 6) // the largest header: ssym_stwo_layout's off_qvals
 
 __global__ void __launch_bounds__(128) stwo_channel_ws_kernel(StwoParams p, ShaMul mul) {
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(128) stwo_channel_ws_kernel(StwoParams p, ShaM
     __shared__ uint32_t s_felt[12][32];  // oods_t, cp_alpha, deep_alpha (S -> F)
     __shared__ uint32_t s_fbits[32];     // status bits of the scalars (F -> S)
     __shared__ uint32_t s_dbits[32];     // status bits of the draws (D -> S)
-    __shared__ uint32_t s_seq[1];        // digests published so far (S -> D)
+    __shared__ __align__(8) uint64_t s_mbar[SSYM_MAX_FRI_LAYERS + 5]; // one mbarrier per published digest (S arrives, D waits): no reuse, no flow control
     extern __shared__ __align__(16) uint32_t s_dyn[]; // the published digests, (L + 5) x [8][32] words
     // Everything the channel absorbs lies in the proof's header (roots, OODS samples, last coefficient, nonce: words [0, off_qvals)).  The CTA
     // copies the 32 headers into shared memory first (coalesced 128-bit loads, all in flight together), so that no global-memory latency sits
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(128) stwo_channel_ws_kernel(StwoParams p, ShaM
     {
         const uint32_t hq = p.lo.off_qvals / 4, total = 32 * hq; // uint4s per header (sections are 32-byte aligned)
 #pragma unroll 1
-        if (threadIdx.x == 0) s_seq[0] = 0;
+        if (threadIdx.x < p.cfg.n_fri_layers + 5) mbar_init(&s_mbar[threadIdx.x], 32);
         for (uint32_t t0 = threadIdx.x; t0 < total; t0 += 8 * 128) { // eight loads in flight per thread before the first store
             uint4 v[8];
 #pragma unroll
@@ -485,11 +506,9 @@ __global__ void __launch_bounds__(128) stwo_channel_ws_kernel(StwoParams p, ShaM
         // folding coefficient per FRI layer, the queries.  A draw is one block, digest || n_sent || padding, compressed here with its own schedule.
         uint32_t retries = 0, dbits = 0;
         const uint32_t query_mask = shl32(G & 0xff, 1u) - 1u;
-        const volatile uint32_t *seq = &s_seq[0];
 #pragma unroll 1
         for (uint32_t k = 0; k < L + 5; k++) {
-            while (*seq <= k) {}
-            __threadfence_block();
+            mbar_wait(&s_mbar[k], 0);
             uint32_t d[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) d[j] = s_dq[k][j][lane];
@@ -647,9 +666,7 @@ __global__ void __launch_bounds__(128) stwo_channel_ws_kernel(StwoParams p, ShaM
         if (slot != 0xffffffffu) {
 #pragma unroll
             for (int k = 0; k < 8; k++) s_dq[slot][k][lane] = d[k];
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_seq[0]) = slot + 1;
+            mbar_arrive(&s_mbar[slot]); // release: the digest is visible to the waiter
         }
         if (tr) {
             uint32_t *dst = m == 2 ? tr->digest_commit : m == 3 ? tr->digest_oods : m == 5 + L ? tr->digest_fri : m == 6 + L ? tr->digest_pow : nullptr;
