@@ -67,7 +67,7 @@ How the bench line's roofline follows from these (recompute with the bench line'
 * PROVER_CONSISTENT pass: {alu_pc:,.0f} ALU-pipe warp instructions ({alu_pc / alu_all:.3f} x the per-query schedule: every distinct node hashed once), {pc_ms:.4f} ms per pass pipelined = {alu_pc / pc_ms / 1e6 / peak:.2f}.
 * DRAM traffic of K3: {k3['dram_read_bytes'] / 1e6:.2f} MB read + {k3['dram_write_bytes'] / 1e6:.2f} MB written per launch against 55.80 MB algorithmic (1024 x 54 488 B): {(k3['dram_read_bytes'] + k3['dram_write_bytes']) / 55795712:.2f} x, no re-reads; HBM fraction {r['hbm']['frac'] * 100:.1f} %.
 
-Share of the step (ref-literal, from `r02_step_metrics.csv`, cold-cache serialised durations): K3 {dur['stwo_merkle_kernel']:.1f} us = {dur['stwo_merkle_kernel'] / tot * 100:.1f} %, K1 {dur['stwo_channel_ws_kernel']:.1f} us = {dur['stwo_channel_ws_kernel'] / tot * 100:.1f} % (latency-bound: 32 x 3 warps on
+Share of the step (ref-literal, from `r02_step_metrics.csv`, cold-cache serialised durations): K3 {dur['stwo_merkle_kernel']:.1f} us = {dur['stwo_merkle_kernel'] / tot * 100:.1f} %, K1 {dur['stwo_channel_ws_kernel']:.1f} us = {dur['stwo_channel_ws_kernel'] / tot * 100:.1f} % (latency-bound: 32 x 4 warps on
 592 schedulers), K2 {dur['stwo_query_kernel']:.1f} us, K4 {dur['stwo_finalize_kernel']:.1f} us — the same shares as the CUDA-event `kernel_ms` of the bench line ({d['kernel_ms']['stwo_merkle']:.3f} / {d['kernel_ms']['stwo_channel']:.3f} / {d['kernel_ms']['stwo_query']:.3f} / {d['kernel_ms']['stwo_finalize']:.3f} ms).
 
 Warp-state samples of K3 by opcode (source page of `{os.path.basename(merkle_rep)}`; {total_samples} samples): `SHF` {S('SHF', '# Samples')} (math-pipe throttle {S('SHF', 'stall_math')}, not selected {S('SHF', 'stall_not_selected')}), `LOP3` {S('LOP3', '# Samples')}

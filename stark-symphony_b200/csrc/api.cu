@@ -463,7 +463,7 @@ static int stwo_launch_chunk(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_
 static int stwo_launch_chunk_cross(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym_stwo_config_t &cfg, uint32_t rec_mode, const ssym_stwo_layout_t &lo,
                                    uint32_t *d_packed, size_t m, uint32_t *d_accept, uint32_t *d_status, cudaStream_t s, uint8_t *derive,
                                    uint32_t derive_stride) {
-    int rc = ensure_lane_scratch(c, lane, cfg, m, true);
+    int rc = ensure_lane_scratch(c, lane, cfg, m, false);
     if (rc) return rc;
     StwoParams p;
     p.cfg = cfg;
@@ -485,7 +485,7 @@ static int stwo_launch_chunk_cross(ssym_ctx *c, ssym_ctx::Lane &lane, const ssym
     p.derive_kinds = 3u;
     p.fri_only = 0;
     memset(&p.dd, 0, sizeof p.dd);
-    launch_stwo_verify_cross(p, rec_mode, lane.status.as<uint32_t>(), d_accept, s, &c->launches);
+    launch_stwo_verify_cross(p, rec_mode, d_accept, s, &c->launches);
     CUDA_TRY(cudaGetLastError());
     return SSYM_OK;
 }

@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS, 8) stwo_query_kernel(StwoParams
         }
     }
     status = __reduce_or_sync(0xffffffffu, status);
-    if (lane == 0 && status) atomicOr(&p.status[i], status);
+    if (lane == 0 && status && p.status) atomicOr(&p.status[i], status); // (no status: the records' pass of launch_stwo_verify_cross)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(Stwo
     bool ok = path == 1u; // merkle.simf:42
 #pragma unroll
     for (int k = 0; k < 8; k++) ok = ok && (cur[k] == r[k]); // merkle.simf:43
-    if (active && !ok) atomicOr(&p.status[i], fail_bit);
+    if (active && !ok && p.status) atomicOr(&p.status[i], fail_bit);
     if (active && p.trace) {
         ssym_stwo_trace_t *tr = p.trace + i;
         uint32_t *dst = kind == 0 ? tr->trace_root[q] : kind == 1 ? tr->cp_root[q] : tr->fri_root[layer][q];
@@ -1549,8 +1549,7 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     if (launch_counter) *launch_counter += 4;
 }
 
-void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *scratch_status, uint32_t *accept_bits, cudaStream_t s,
-                              uint64_t *launch_counter) {
+void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter) {
     if (p.n == 0) return;
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers;
     const uint32_t groups = (p.n * Q + 31) / 32;
@@ -1574,7 +1573,7 @@ void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *
     stwo_channel_ws_kernel<<<(pc.n + 31) / 32, 128, k1_dyn_smem(pc), s>>>(pc, sha_mul_consts());
     StwoParams pr = pc; // the records' pass: evaluations and FRI chains only
     pr.cfg.mode = rec_mode;
-    pr.status = scratch_status;
+    pr.status = nullptr; // its verdicts are not wanted
     pr.trace = nullptr;
     pr.derive_kinds = 2u;
     pr.fri_only = 1;

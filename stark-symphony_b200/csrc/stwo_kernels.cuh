@@ -117,9 +117,8 @@ void launch_stwo_tables(uint32_t lde_log, uint32_t n_fri_layers, uint2 *point, u
 void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter, Profiler *prof,
                         cudaStream_t front = nullptr, cudaEvent_t front_done = nullptr, int front_kernels = 0);
 // Version 3 compact records whose derived siblings were packed under `rec_mode`, verified under p.cfg.mode (same flags, other semantics): the
-// transcript once; the evaluations and the FRI chains of the records' mode, which complete the FRI siblings in the packed records (their verdicts go to
-// scratch_status and are dropped); then the verification proper.  p.derive / derive_stride as for derive_mode 1.
-void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *scratch_status, uint32_t *accept_bits, cudaStream_t s,
-                              uint64_t *launch_counter);
+// transcript once; the evaluations and the FRI chains of the records' mode, which complete the FRI siblings in the packed records (that pass has no
+// status: its verdicts are not wanted); then the verification proper.  p.derive / derive_stride as for derive_mode 1.
+void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *accept_bits, cudaStream_t s, uint64_t *launch_counter);
 
 } // namespace ssym

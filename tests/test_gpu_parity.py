@@ -203,6 +203,34 @@ def test_stwo_ragged_batch_sizes(S, ver):
         assert (bits == expect).all(), n
 
 
+@pytest.mark.gpu
+def test_host_chunk_plan_sizes(S, ver):
+    """Blocking host-buffer calls taper their chunks (csrc/api.cu host_chunk_plan): sizes around the plan's break points, a corrupted proof every 37,
+    packed and compact records, blocking and enqueue-only calls — the bitmap of the device-resident call every time."""
+    import torch
+
+    cfg, packed = golden_stwo(S, "testing", 1)
+    lo = S.stwo_layout(cfg)
+    for n in (256, 257, 289, 511, 1023, 1025, 2047, 2049, 2304):
+        batch = np.tile(packed, n)
+        for r in range(5, n, 37):
+            batch[r * lo.stride_words + lo.off_last_coeff] ^= 1
+        d_accept, _, _ = ver.stwo_verify_batch(torch.from_numpy(batch.view(np.int32)).cuda(), cfg, n)
+        ver.synchronize()
+        want = d_accept.cpu().numpy().view(np.uint32)
+        expect = np.ones(n, dtype=bool)
+        expect[5::37] = False
+        assert (np.unpackbits(want.view(np.uint8), bitorder="little")[:n].astype(bool) == expect).all(), n
+        blob, offsets = S.witness.compact_stwo(batch, cfg)
+        for async_mode in (False, True):
+            ver.set_host_async(async_mode)
+            a1, _, _ = ver.stwo_verify_batch(batch, cfg, n)
+            a2, _ = ver.stwo_verify_compact_batch(blob, offsets, cfg)
+            ver.synchronize()
+            ver.set_host_async(False)
+            assert (a1 == want).all() and (a2 == want).all(), (n, async_mode)
+
+
 def golden_s101(S):
     return S.witness.pack_stark101_wits([open(os.path.join(GOLDEN, "stark101_proof.wit")).read()])
 
