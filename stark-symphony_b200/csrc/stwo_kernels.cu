@@ -10,8 +10,13 @@
 #ifndef SSYM_DEFAULT_ADDMODE
 #define SSYM_DEFAULT_ADDMODE 8
 #endif
+#ifndef SSYM_MERKLE_THREADS
+#define SSYM_MERKLE_THREADS 32 // threads per CTA of the per-query Merkle kernel.  A warp never talks to another, so any multiple of 32 computes the same; with
+                              // one warp per CTA a finished chain frees its slot at once for the next (shorter) one — a lone 1024-proof launch 230 -> 222 us
+                              // (64: 227, 256: 234), the pipelined rate is the same
+#endif
 #ifndef SSYM_MERKLE_MINB
-#define SSYM_MERKLE_MINB 8 // resident CTAs per SM the Merkle kernel is compiled for (8 -> 64 registers)
+#define SSYM_MERKLE_MINB (1024 / SSYM_MERKLE_THREADS) // resident CTAs per SM the Merkle kernels are compiled for (32 warps -> 64 registers)
 #endif
 #ifndef SSYM_DEFAULT_ROLLED
 #define SSYM_DEFAULT_ROLLED 1
@@ -857,7 +862,7 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t (&d)[8
 // are the nodes of other queries' paths — the 16 (Q) chains of one tree of one proof sit in one warp and step through the levels together, so a
 // derived sibling is a warp shuffle away; KMODE 2 finds, for the packer, which siblings could be left out.  Needs 32 % Q == 0.
 template <int ADDMODE, bool ROLLED, int KMODE = 0>
-__global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, ShaMul mul) {
+__global__ void __launch_bounds__(SSYM_MERKLE_THREADS, SSYM_MERKLE_MINB) stwo_merkle_kernel(StwoParams p, uint32_t groups_per_type, ShaMul mul) {
     const ShaAdd<ADDMODE> A(mul);
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1112,7 +1117,7 @@ __global__ void __launch_bounds__(512) stwo_plan_kernel(StwoParams p) {
 // Round 1: chain c from its leaf up lv levels (plan: a follower stops one level below its meeting node), storing the nodes its followers need.
 // Round 2: the followers whose check failed, from their node at height lv (same-leaf followers: from their leaf) to the root with their own siblings.
 template <int ADDMODE>
-__global__ void __launch_bounds__(128, SSYM_MERKLE_MINB) stwo_merkle_shared_kernel(StwoParams p, uint32_t round, ShaMul mul) {
+__global__ void __launch_bounds__(128, 8) stwo_merkle_shared_kernel(StwoParams p, uint32_t round, ShaMul mul) {
     const ShaAdd<ADDMODE> A(mul);
     const uint32_t Q = p.cfg.n_queries, L = p.cfg.n_fri_layers, G = p.cfg.lde_log;
     const uint32_t lane = threadIdx.x & 31, grid_warps = (gridDim.x * blockDim.x) >> 5;
@@ -1499,7 +1504,7 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
         const uint64_t max_warps = ((uint64_t)n_chains + 31) / 32 + STWO_DEDUP_MAX_BINS;
         stwo_merkle_shared_kernel<SSYM_DEFAULT_ADDMODE><<<(uint32_t)((max_warps + 3) / 4), 128, 0, s>>>(p, 0u, sha_mul_consts());
         stwo_check_kernel<<<(n_chains + 255) / 256, 256, 0, s>>>(p);
-        stwo_merkle_shared_kernel<SSYM_DEFAULT_ADDMODE><<<(uint32_t)std::min<uint64_t>((max_warps + 3) / 4, 148 * SSYM_MERKLE_MINB), 128, 0, s>>>(p, 1u, sha_mul_consts());
+        stwo_merkle_shared_kernel<SSYM_DEFAULT_ADDMODE><<<(uint32_t)std::min<uint64_t>((max_warps + 3) / 4, 148 * 8), 128, 0, s>>>(p, 1u, sha_mul_consts());
         stwo_resolve_kernel<<<(n_chains + 255) / 256, 256, 0, s>>>(p);
         if (prof) { prof->end(2, s); prof->begin(3, s); }
         stwo_finalize_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, accept_bits);
@@ -1511,11 +1516,11 @@ void launch_stwo_verify(const StwoParams &p, uint32_t *accept_bits, cudaStream_t
     if (prof) { prof->end(1, s); prof->begin(2, s); }
     const uint32_t groups = (items + 31) / 32;
     const uint64_t warps = (uint64_t)groups * (L + 3);
-    const uint32_t grid = (uint32_t)((warps + 3) / 4);
-#define SSYM_LAUNCH_MERKLE(AM, RL) stwo_merkle_kernel<AM, RL><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts())
+    const uint32_t wpc = SSYM_MERKLE_THREADS / 32, grid = (uint32_t)((warps + wpc - 1) / wpc);
+#define SSYM_LAUNCH_MERKLE(AM, RL) stwo_merkle_kernel<AM, RL><<<grid, SSYM_MERKLE_THREADS, 0, s>>>(p, groups, sha_mul_consts())
     if (p.derive_mode) { // compact transport form, version 3: derived siblings (1) / the packer's scan (2)
-        if (p.derive_mode == 1) stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 1><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts());
-        else stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 2><<<grid, 128, 0, s>>>(p, groups, sha_mul_consts());
+        if (p.derive_mode == 1) stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 1><<<grid, SSYM_MERKLE_THREADS, 0, s>>>(p, groups, sha_mul_consts());
+        else stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 2><<<grid, SSYM_MERKLE_THREADS, 0, s>>>(p, groups, sha_mul_consts());
     } else {
 #ifdef SSYM_TUNING
     // experiment builds only (build.py --tuning; sha256.cuh): which adds go to the FMA pipe, and whether the 64 rounds are rolled into 4 x 16.
@@ -1562,7 +1567,8 @@ void launch_stwo_verify_cross(const StwoParams &p, uint32_t rec_mode, uint32_t *
     };
     auto k3 = [&](const StwoParams &q, uint32_t ranks) {
         const uint64_t warps = (uint64_t)groups * ranks;
-        stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 1><<<(uint32_t)((warps + 3) / 4), 128, 0, s>>>(q, groups, sha_mul_consts());
+        const uint32_t wpc = SSYM_MERKLE_THREADS / 32;
+        stwo_merkle_kernel<SSYM_DEFAULT_ADDMODE, true, 1><<<(uint32_t)((warps + wpc - 1) / wpc), SSYM_MERKLE_THREADS, 0, s>>>(q, groups, sha_mul_consts());
     };
     StwoParams pc = p; // the call's pass
     pc.ctx_mode = p.cfg.mode;
