@@ -60,8 +60,7 @@ hash of the CUDA tree the counts belong to: `{c['csrc_sha16']}` (`bench.py` comp
 How the bench line's roofline follows from these (recompute with the bench line's `kernel_ms.stwo_merkle` and `roofline.peak`):
 
 * `roofline.frac` = {alu_k3:,.0f} ALU-pipe warp instructions (K3, 1024 proofs) / `kernel_ms.stwo_merkle` / (`int32_peak_probe` lanes/s / 32).  With {ms_k3:.4f} ms and
-  {peak * 32 / 1e3:.2f} T lanes/s: {alu_k3 / ms_k3 / 1e6:.1f} / {peak:.1f} G warp-instructions/s = **{alu_k3 / ms_k3 / 1e6 / peak:.3f}** (a lone launch: 1408 CTAs on 1184 slots = 1.19 waves; ncu below: ALU pipe
-  79 % of elapsed, 89 % of active cycles).  Before the uniform-register multiplier: 0.733 – 0.755 at 0.241 – 0.248 ms (ncu: 73.2 % / 82.7 %).
+  {peak * 32 / 1e3:.2f} T lanes/s: {alu_k3 / ms_k3 / 1e6:.1f} / {peak:.1f} G warp-instructions/s = **{alu_k3 / ms_k3 / 1e6 / peak:.3f}** (a lone launch: 5 632 one-warp CTAs on 4 736 slots = 1.19 waves; ncu below).  Before the uniform-register multiplier: 0.733 – 0.755 at 0.241 – 0.248 ms (ncu: 73.2 % / 82.7 %).
 * `roofline.whole_step_frac` = {alu_all:,.0f} (all four kernels of a pass) / `config.ms_per_pass` / the same peak = **{alu_all / ms_pass / 1e6 / peak:.3f}** at {ms_pass:.4f} ms per pass (depth-8 pipeline: the
   tails of consecutive launches overlap).
 * PROVER_CONSISTENT pass: {alu_pc:,.0f} ALU-pipe warp instructions ({alu_pc / alu_all:.3f} x the per-query schedule: every distinct node hashed once), {pc_ms:.4f} ms per pass pipelined = {alu_pc / pc_ms / 1e6 / peak:.2f}.
