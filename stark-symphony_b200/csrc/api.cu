@@ -120,6 +120,8 @@ struct ssym_ctx {
     cudaEvent_t ev_res[RES_RING] = {nullptr, nullptr, nullptr, nullptr}; // recorded on the handle's stream after a call's D2H
     bool res_used[RES_RING] = {false, false, false, false};
     uint64_t host_calls = 0;
+    bool tail_is_host_call = false; // nothing but host-buffer Stwo calls was issued on the handle since the last one (ssym_join, which every other entry
+                                    // point that shares lane / staging scratch starts with, clears it): such a call need not wait for the handle's stream
     StwoDedup dd_cache{};       // static part of the shared-node plan for dd_cache_key (configuration, chunk size)
     uint64_t dd_cache_key = 0;
     size_t dd_cache_entries = 0;
@@ -255,6 +257,7 @@ void ssym_pinned_free(void *ptr) {
 int ssym_set_stream(ssym_ctx_t *c, void *cuda_stream) {
     if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
     c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    c->tail_is_host_call = false;
     return SSYM_OK;
 }
 int ssym_set_pipeline_depth(ssym_ctx_t *c, int depth) {
@@ -267,6 +270,7 @@ int ssym_set_pipeline_depth(ssym_ctx_t *c, int depth) {
 int ssym_join(ssym_ctx_t *c) {
     if (!c) return fail(SSYM_ERR_USAGE, "ctx is NULL");
     CUDA_TRY(cudaSetDevice(c->device));
+    c->tail_is_host_call = false;
     for (auto &l : c->lanes)
         if (l.pending) {
             CUDA_TRY(cudaStreamWaitEvent(c->stream, l.done, 0));
@@ -519,8 +523,9 @@ static std::vector<size_t> host_chunk_plan(size_t n, size_t hc, bool async) {
     return sizes;
 }
 
-static int host_fork(ssym_ctx *c, int ring_slot) {
-    if (c->host_async) { // enqueue-only calls overlap: this call's kernels only wait for the D2H of the call that used its result slot last
+static int host_fork(ssym_ctx *c, int ring_slot, bool after_host_call) {
+    if (c->host_async && after_host_call) { // enqueue-only calls overlap: this call's kernels only wait for the D2H of the call that used its result slot last
+                                            // (after anything else the lanes are ordered behind the handle's stream: it may hold work on their scratch)
         if (c->res_used[ring_slot])
             for (int b = 0; b < ssym_ctx::HOST_BUFS; b++) CUDA_TRY(cudaStreamWaitEvent(c->lanes[b].s, c->ev_res[ring_slot], 0));
         return SSYM_OK;
@@ -593,6 +598,7 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
         return c->depth == 1 ? ssym_join(c) : SSYM_OK;
     }
     if (memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
+    const bool after_host_call = c->tail_is_host_call;
     rc = ssym_join(c); // host chunks run on the lanes' streams with the lanes' scratch
     if (rc) return rc;
 
@@ -624,7 +630,7 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
         }
     }
     cudaStream_t s = c->stream;
-    rc = host_fork(c, slot);
+    rc = host_fork(c, slot, after_host_call);
     if (rc) return rc;
     bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
     size_t done = 0;
@@ -650,6 +656,7 @@ extern "C" int ssym_stwo_verify_batch(ssym_ctx_t *c, const ssym_stwo_config_t *c
     if (trace) CUDA_TRY(cudaMemcpyAsync(trace, c->d_trace.p, n * sizeof(ssym_stwo_trace_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(c->ev_res[slot], s));
     c->res_used[slot] = true;
+    c->tail_is_host_call = true;
     if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
@@ -926,6 +933,7 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     if (memspace != SSYM_MEM_DEVICE && memspace != SSYM_MEM_HOST) return fail(SSYM_ERR_USAGE, "bad memspace");
     ssym_stwo_layout_t lo;
     CompactShape sh;
+    const bool after_host_call = c->tail_is_host_call;
     int rc = compact_prepare(c, cfg, lo, sh);
     if (rc || n == 0) return rc;
     if (n > 0xffffffffull / SSYM_MAX_QUERIES) return fail(SSYM_ERR_USAGE, "batch too large for one call");
@@ -994,7 +1002,7 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     rc = host_result_slot(c, n, &slot);
     if (rc) return rc;
     uint32_t *const r_accept = c->r_accept[slot].as<uint32_t>(), *const r_status = c->r_status[slot].as<uint32_t>();
-    rc = host_fork(c, slot);
+    rc = host_fork(c, slot, after_host_call);
     if (rc) return rc;
     bool used[ssym_ctx::HOST_BUFS] = {false, false, false, false};
     size_t done = 0;
@@ -1035,6 +1043,7 @@ extern "C" int ssym_stwo_verify_compact_batch(ssym_ctx_t *c, const ssym_stwo_con
     if (status) CUDA_TRY(cudaMemcpyAsync(status, r_status, n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(c->ev_res[slot], s));
     c->res_used[slot] = true;
+    c->tail_is_host_call = true;
     if (c->host_async) return SSYM_OK; // results are valid after ssym_synchronize
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
