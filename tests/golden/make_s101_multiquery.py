@@ -81,6 +81,22 @@ def main():
                 idx = channel.receive_random_int(0, len(p_mt.data) - 1, f"query #{k}")
         idxs.append(idx)
         proofs.append(decommit(idx))
+    # every decommitment of every query against the reference's own checker (merkle.py:73-86 verify_decommitment)
+    from fibsquare.field import FieldElement
+    from fibsquare.merkle import verify_decommitment
+
+    def as_path(ints_):
+        return [int(x).to_bytes(32, "big") for x in ints_[::-1]]  # back to root -> leaf, the order get_authentication_path returns
+
+    for idx, pr in zip(idxs, proofs):
+        root = int(pr["p_mt_root"]).to_bytes(32, "big")
+        for j, (val, path) in enumerate(pr["evals"]):
+            assert verify_decommitment(idx + j * DOMAIN_EX_MULT, FieldElement(val), as_path(path), root)
+        for i, (lroot, _beta, cpa, pa, cpb, pb) in enumerate(pr["fri_layers"]):
+            length = len(fri_mts[i].data)
+            lr = int(lroot).to_bytes(32, "big")
+            assert verify_decommitment(idx % length, FieldElement(cpa), as_path(pa), lr)
+            assert verify_decommitment((idx + length // 2) % length, FieldElement(cpb), as_path(pb), lr)
     assert proofs[0] == res0, "query 0 must be the reference's own proof"
     golden = json.load(open(os.path.join(HERE, "stark101_proof.json")))
     assert proofs[0] == golden, "query 0 must equal tests/golden/stark101_proof.json"
