@@ -53,7 +53,7 @@ hash of the CUDA tree the counts belong to: `{c['csrc_sha16']}` (`bench.py` comp
 | `step_pipe_counts.json` | per-kernel per-pass medians of the two files above (`profiles/pipe_counts.py`) — **`bench.py` and `bench_sub.py` read their roofline numerators from this file** |
 | `r02_launches.csv` | launch list (`gpu__time_duration.sum`) of the first 600 launches of `bench.py --steps 2 --warmup 3 --passes 8 --e2e-passes 4` |
 | `r02_k3_sass_excerpt.md` | instruction mix and excerpts of the K3 hashing loops from `cuobjdump -sass` |
-| `{os.path.basename(bench).replace('.json', '_n1.json') if '_n1' not in bench else os.path.basename(bench)}`, `r02o_reference_arm.json` | the bench line of the same build (`python bench.py --steps 20 --warmup 5`) and the reference arm (`--impl reference`); `r02u_bench_n{{2,4}}.json`, `r02t_bench_n8.json`: the multi-GPU lines; `r02o_bench_n1.json`: before the host-path changes (e2e on records packed under the call's own mode) |
+| `{os.path.basename(bench).replace('.json', '_n1.json') if '_n1' not in bench else os.path.basename(bench)}`, `r02o_reference_arm.json` | the bench line of the same build (`python bench.py --steps 20 --warmup 5`) and the reference arm (`--impl reference`); `r02u_bench_n{{2,4}}.json`, `r02t_bench_n8.json`: the multi-GPU lines; `r02d_bench_n1.json` / `r02o_bench_n1.json`: earlier in the round — before the uniform-register multiplier / before the host-path changes, the draw warp of K1 and the one-warp CTAs of K3 |
 | `r02_micro.json`, `r02_config3.json`, `r02_config5_n8.json` | full-size runs of BASELINE configs 4 / 1, 3 and 5 (`bench_micro.py`, `bench_configs.py`) |
 | `r02_sanitizer_summary.txt` | `tools/sanitize.sh all`: memcheck, initcheck (87 tests each), racecheck (66), synccheck (31): 0 errors / 0 hazards |
 
